@@ -1,0 +1,582 @@
+// =====================================================================================
+// oracle/qmc_oracle_driver.hpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (see qmc_oracle.hpp).
+//
+// Restatement of the batched VMC particle-by-particle sweep and of the per-walker wavefunction
+// state it drives:
+//   ref: QMCDrivers/VMC/VMCBatched.cpp:58-226 (advanceWalkers; hot loop :107-176)
+//   ref: QMCWaveFunctions/TrialWaveFunction.cpp:568-592 (mw_evalGrad), :685-741 (mw_calcRatioGrad),
+//        :790-833 (mw_accept_rejectMove), :833-869 (mw_completeUpdates), :869-930 (mw_evaluateGL)
+//   ref: Fermion/DiracDeterminantBatched.cpp:184-208 (mw_evalGrad), :308-354 (mw_ratioGrad), :464-521
+//        (mw_accept_rejectMove), :545-591 (mw_completeUpdates), :594-604 (computeGL), :1122-1198 (mw_recompute)
+//   ref: Particle/ParticleSet.cpp:397-428 (mw_makeMove), :717-758 (mw_accept_rejectMove)
+// Organisation = the reference's batched CPU path: one crowd per OpenMP thread, walkers looped inside
+// every mw_* call (QMCWaveFunctions/SPOSet.cpp:115-126, WaveFunctionComponent.cpp:145-190).
+//
+// When QMC_ORACLE_USE_REFERENCE is defined (oracle/_ref build), the spline VGH evaluation, the delayed
+// update engine and the matrix inversion are the reference's own compiled code
+// (spline2::evaluate_vgh_impl, DelayedUpdate<T>, DiracMatrix<T>); see ref_kernels.hpp.
+// =====================================================================================
+#pragma once
+#include "qmc_oracle.hpp"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace orc
+{
+struct VMCParams
+{
+  int precision;   // 0 = full (double), 1 = mixed (float)
+  int n_up, n_dn;  // electrons per spin group; N = n_up + n_dn
+  double lattice[9];
+  // spline tables (real R2R), one per spin (may alias); ST-typed [M0+3][M1+3][M2+3][npad]
+  const void* coefs[2];
+  int grid[3];
+  int npad;
+  // J2: functor parameter tables uu and ud (10 params each for NiO); n_j2 = 0 disables
+  int n_j2;
+  const double* j2_uu;
+  const double* j2_ud;
+  double j2_rcut;
+  // J1: nions = 0 disables
+  int nions;
+  const double* ion_pos; // [nions][3]
+  const int* ion_grp;    // [nions]
+  int n_ion_groups;
+  int n_j1;              // params per group
+  const double* j1_params; // [n_ion_groups][n_j1]
+  const double* j1_rcut;   // [n_ion_groups]
+  // driver
+  int nw, ncrowds;
+  const uint32_t* seeds; // [ncrowds]
+  double tau;
+  int use_drift;
+  int delay_rank;
+  int batched_engine; // 1: DelayedUpdateBatched semantics (crowd-wide delay_count + pseudo-accept); 0: per-walker DelayedUpdate
+};
+
+#ifndef QMC_ORACLE_USE_REFERENCE
+template<typename ST>
+inline void kernel_vgh(const SplineTable<ST>& s, ST x, ST y, ST z, ST* v, ST* g, ST* h, size_t stride)
+{
+  evaluate_vgh(s, x, y, z, v, g, h, stride);
+}
+template<typename T>
+using Engine = DelayedUpdate<T>;
+template<typename VT>
+inline void kernel_invert_transpose(const VT* amat, int n, int a_cols, VT* inv, int lda, std::complex<double>& logdet)
+{
+  invert_transpose(amat, n, a_cols, inv, lda, logdet);
+}
+#endif
+
+template<typename RT, typename ST, typename VT>
+struct VMC
+{
+  using J2 = TwoBodyJastrow<RT>;
+  using J1 = OneBodyJastrow<RT>;
+
+  struct Det
+  {
+    int n = 0, lda = 0, first = 0;
+    std::vector<VT> psiMinv, dpsiM, d2psiM; // [n][lda], [n][n][3], [n][n]
+    std::vector<VT> invRow;
+    int invRow_id = -1;
+    Engine<VT> eng;
+    std::complex<double> log_value;
+    double curRatio = 1.0;
+  };
+
+  struct Walker
+  {
+    std::vector<RT> R;    // [N][3]
+    std::vector<RT> rsoa; // [3][npad_pos]
+    Det det[2];
+    typename J2::State j2;
+    typename J1::State j1;
+    RT newpos[3];
+    std::vector<RT> dist_new, dist_old; // [4][npad] AA temp rows
+    std::vector<ST> myV, myG, myH;
+    std::vector<VT> phi_vgl;            // [5][n] of the proposed move
+    double weight = 1.0;
+    long n_accept = 0, n_reject = 0;
+  };
+
+  struct Crowd
+  {
+    int w0 = 0, w1 = 0;
+    StdRandom rng;
+    int delay_count[2] = {0, 0}; // leader's delay_count in batched_engine mode
+    std::vector<RT> walker_deltas;
+  };
+
+  VMCParams prm;
+  int N = 0, nw = 0;
+  size_t npad_pos = 0;
+  LatticeG latG;
+  MinImage<RT> mi;
+  SplineTable<ST> tab[2];
+  J2 j2;
+  J1 j1;
+  bool has_j2 = false, has_j1 = false;
+  std::vector<Walker> walkers;
+  std::vector<Crowd> crowds;
+  std::vector<uint8_t> accept_log; // filled by sweep when requested: [step][iat][nw]
+
+  int group_of(int iat) const { return iat < prm.n_up ? 0 : 1; }
+  int first_of(int ig) const { return ig == 0 ? 0 : prm.n_up; }
+  int last_of(int ig) const { return ig == 0 ? prm.n_up : N; }
+
+  explicit VMC(const VMCParams& p) : prm(p)
+  {
+    N        = p.n_up + p.n_dn;
+    nw       = p.nw;
+    npad_pos = aligned_size<RT>(N);
+    // G = inverse(R) (CrystalLattice.cpp:63)
+    const double* R = p.lattice;
+    MinImage<double> tmp;
+    tmp.set(R);
+    double G[9];
+    for (int i = 0; i < 9; ++i)
+      G[i] = tmp.g[i];
+    latG.set(G, nullptr);
+    mi.set(R);
+    for (int s = 0; s < 2; ++s)
+      tab[s].set(static_cast<const ST*>(p.coefs[s]), p.grid, s == 0 ? p.n_up : p.n_dn, p.npad);
+    std::vector<int> gids(N);
+    for (int i = 0; i < N; ++i)
+      gids[i] = group_of(i);
+    has_j2 = p.n_j2 > 0;
+    j2.init(N, 2, gids.data());
+    if (has_j2)
+    {
+      // cusp: -1/4 like spin, -1/2 unlike spin (Jastrow/RadialJastrowBuilder.cpp:200-208)
+      j2.F[0].set(p.j2_uu, p.n_j2, p.j2_rcut, -0.25);
+      j2.F[3].set(p.j2_uu, p.n_j2, p.j2_rcut, -0.25);
+      j2.F[1].set(p.j2_ud, p.n_j2, p.j2_rcut, -0.5);
+      j2.F[2].set(p.j2_ud, p.n_j2, p.j2_rcut, -0.5);
+    }
+    has_j1 = p.nions > 0;
+    if (has_j1)
+    {
+      j1.init(p.nions, p.ion_pos, p.ion_grp, p.n_ion_groups, N);
+      for (int g = 0; g < p.n_ion_groups; ++g)
+        j1.F[g].set(p.j1_params + (size_t)g * p.n_j1, p.n_j1, p.j1_rcut[g], 0.0);
+    }
+    walkers.resize(nw);
+    for (auto& w : walkers)
+    {
+      w.R.assign(3 * (size_t)N, RT(0));
+      w.rsoa.assign(3 * npad_pos, RT(0));
+      for (int s = 0; s < 2; ++s)
+      {
+        Det& d  = w.det[s];
+        d.n     = s == 0 ? p.n_up : p.n_dn;
+        d.first = first_of(s);
+#ifdef QMC_ORACLE_USE_REFERENCE
+        d.lda = d.n; // the reference CPU engine addresses Ainv with lda == norb (DelayedUpdate.h:93)
+#else
+        d.lda = (int)aligned_size<VT>(d.n);
+#endif
+        d.psiMinv.assign((size_t)d.n * d.lda, VT(0));
+        d.dpsiM.assign((size_t)d.n * d.n * 3, VT(0));
+        d.d2psiM.assign((size_t)d.n * d.n, VT(0));
+        d.invRow.assign(d.n, VT(0));
+        d.eng.resize(d.n, p.delay_rank);
+      }
+      j2.initState(w.j2);
+      if (has_j1)
+        j1.initState(w.j1);
+      w.dist_new.assign(4 * j2.npad, RT(0));
+      w.dist_old.assign(4 * j2.npad, RT(0));
+      w.myV.assign(p.npad, ST(0));
+      w.myG.assign(3 * (size_t)p.npad, ST(0));
+      w.myH.assign(6 * (size_t)p.npad, ST(0));
+      w.phi_vgl.assign(5 * (size_t)std::max(p.n_up, p.n_dn), VT(0));
+    }
+    crowds.resize(p.ncrowds);
+    // walkers are dealt to crowds in contiguous blocks (MCPopulation::redistributeWalkers / fairDivide:
+    // the first (nw % ncrowds) crowds get one extra walker; QMCDrivers/MCPopulation.h + QMCDriverNew.cpp)
+    int base = nw / p.ncrowds, extra = nw % p.ncrowds, w0 = 0;
+    for (int c = 0; c < p.ncrowds; ++c)
+    {
+      const int cnt = base + (c < extra ? 1 : 0);
+      crowds[c].w0  = w0;
+      crowds[c].w1  = w0 + cnt;
+      crowds[c].rng = StdRandom(p.seeds[c]);
+      w0 += cnt;
+    }
+  }
+
+  void setPositions(const double* R /*[nw][N][3]*/)
+  {
+    for (int iw = 0; iw < nw; ++iw)
+    {
+      Walker& w = walkers[iw];
+      for (int i = 0; i < N; ++i)
+        for (int d = 0; d < 3; ++d)
+        {
+          w.R[3 * i + d]             = (RT)R[((size_t)iw * N + i) * 3 + d];
+          w.rsoa[d * npad_pos + i] = w.R[3 * i + d];
+        }
+    }
+  }
+
+  // ---- SPO evaluation for one walker at `pos` for spin s: fills phi_vgl[5][n] (SplineR2R.cpp:338-412)
+  void spoVGL(Walker& w, int s, const RT pos[3], VT* psi, VT* dpsi /*AoS*/, VT* d2psi)
+  {
+    ST ru[3];
+    const int bc_sign       = convertPos<ST, RT>(latG, pos, ru);
+    const SplineTable<ST>& t = tab[s];
+    const size_t np         = t.npad;
+    kernel_vgh(t, ru[0], ru[1], ru[2], w.myV.data(), w.myG.data(), w.myH.data(), np);
+    const ST signed_one = (bc_sign & 1) ? -1 : 1;
+    const ST g00 = latG.G[0], g01 = latG.G[1], g02 = latG.G[2], g10 = latG.G[3], g11 = latG.G[4], g12 = latG.G[5],
+             g20 = latG.G[6], g21 = latG.G[7], g22 = latG.G[8];
+    const ST symGG[6] = {ST(latG.GGt[0]), ST(latG.GGt[1]) + ST(latG.GGt[3]), ST(latG.GGt[2]) + ST(latG.GGt[6]),
+                         ST(latG.GGt[4]), ST(latG.GGt[5]) + ST(latG.GGt[7]), ST(latG.GGt[8])};
+    const ST *g0 = w.myG.data(), *g1 = g0 + np, *g2 = g0 + 2 * np;
+    const ST *h00 = w.myH.data(), *h01 = h00 + np, *h02 = h00 + 2 * np, *h11 = h00 + 3 * np, *h12 = h00 + 4 * np,
+             *h22 = h00 + 5 * np;
+    const int n = t.ns;
+    for (int j = 0; j < n; ++j)
+    {
+      psi[j]          = signed_one * w.myV[j];
+      dpsi[3 * j + 0] = signed_one * (g00 * g0[j] + g01 * g1[j] + g02 * g2[j]);
+      dpsi[3 * j + 1] = signed_one * (g10 * g0[j] + g11 * g1[j] + g12 * g2[j]);
+      dpsi[3 * j + 2] = signed_one * (g20 * g0[j] + g21 * g1[j] + g22 * g2[j]);
+      d2psi[j]        = signed_one * SymTrace(h00[j], h01[j], h02[j], h11[j], h12[j], h22[j], symGG);
+    }
+  }
+
+  // ---- from-scratch: psiM/dpsiM/d2psiM, inverse, Jastrows.  DiracDeterminantBatched.cpp:1122-1198
+  void recomputeWalker(Walker& w)
+  {
+    for (int s = 0; s < 2; ++s)
+    {
+      Det& d = w.det[s];
+      const int n = d.n;
+      if (n == 0)
+        continue;
+      std::vector<VT> psiM((size_t)n * n), dtmp(3 * (size_t)n);
+      for (int e = 0; e < n; ++e)
+      {
+        const RT* pos = &w.R[3 * (size_t)(d.first + e)];
+        spoVGL(w, s, pos, &psiM[(size_t)e * n], &d.dpsiM[(size_t)e * n * 3], &d.d2psiM[(size_t)e * n]);
+      }
+      kernel_invert_transpose(psiM.data(), n, n, d.psiMinv.data(), d.lda, d.log_value);
+      d.eng.delay_count = 0;
+      d.invRow_id       = -1;
+      d.curRatio        = 1.0;
+    }
+    if (has_j2)
+      j2.recompute(w.j2, mi, w.rsoa.data(), npad_pos);
+    if (has_j1)
+      j1.recompute(w.j1, mi, w.rsoa.data(), npad_pos);
+  }
+
+  void recompute()
+  {
+#pragma omp parallel for schedule(dynamic)
+    for (int iw = 0; iw < nw; ++iw)
+      recomputeWalker(walkers[iw]);
+    for (auto& c : crowds)
+      c.delay_count[0] = c.delay_count[1] = 0;
+  }
+
+  // ---- determinant pieces (per walker)
+  void prepareInvRow(Det& d, int row)
+  {
+    if (d.invRow_id != row)
+    {
+      d.eng.getInvRow(d.psiMinv.data(), d.lda, row, d.invRow.data());
+      d.invRow_id = row;
+    }
+  }
+
+  // one sweep step for one crowd
+  void advanceCrowd(Crowd& cr, uint8_t* acc_log /* [N][nw] or null */)
+  {
+    const int cw = cr.w1 - cr.w0;
+    if (cw == 0)
+      return;
+    const bool use_drift = prm.use_drift != 0;
+    std::vector<RT> log_gf(cw, RT(0)), log_gb(cw, RT(0)), prob(cw);
+    std::vector<double> ratios(cw);
+    std::vector<RT> deltas(3 * (size_t)cw), drifts(3 * (size_t)cw), grads_now(3 * (size_t)cw),
+        grads_new(3 * (size_t)cw);
+    std::vector<char> isAccepted(cw);
+
+    // makeGaussRandomWithEngine(walker_deltas, rng): nw*N*3 Gaussians in one go (VMCBatched.cpp:109)
+    cr.walker_deltas.resize(3 * (size_t)cw * N);
+    assignGaussRand(cr.walker_deltas.data(), (unsigned)cr.walker_deltas.size(), cr.rng);
+
+    for (int ig = 0; ig < 2; ++ig)
+    {
+      // TauParams (QMCDrivers/TauParams.hpp:29-40), mass = 1
+      const RT tauovermass = RT(prm.tau) * RT(1.0);
+      const RT oneover2tau = 0.5 / (tauovermass);
+      const RT sqrttau     = std::sqrt(tauovermass);
+      for (int iat = first_of(ig); iat < last_of(ig); ++iat)
+      {
+        const int row = iat - first_of(ig);
+        // deltas for this particle: walker_deltas[iat*cw + iw] (VMCBatched.cpp:122), scaled by sqrt(tau)
+        for (int i = 0; i < cw; ++i)
+          for (int d = 0; d < 3; ++d)
+            deltas[3 * i + d] = cr.walker_deltas[3 * ((size_t)iat * cw + i) + d] * sqrttau;
+
+        if (use_drift)
+        {
+          // TWF::mw_evalGrad: components in order SlaterDet, J2, J1; grads summed in ValueType
+          for (int i = 0; i < cw; ++i)
+          {
+            Walker& w = walkers[cr.w0 + i];
+            Det& d    = w.det[ig];
+            prepareInvRow(d, row);
+            VT g[3] = {VT(0), VT(0), VT(0)};
+            const VT* dp = &d.dpsiM[(size_t)row * d.n * 3];
+            for (int j = 0; j < d.n; ++j)
+            {
+              g[0] += d.invRow[j] * dp[3 * j];
+              g[1] += d.invRow[j] * dp[3 * j + 1];
+              g[2] += d.invRow[j] * dp[3 * j + 2];
+            }
+            RT gt[3] = {RT(g[0]), RT(g[1]), RT(g[2])};
+            if (has_j2)
+              for (int dd = 0; dd < 3; ++dd)
+                gt[dd] += w.j2.dUat[dd * j2.npad + iat]; // TwoBodyJastrow::evalGrad (:524-528)
+            if (has_j1)
+              for (int dd = 0; dd < 3; ++dd)
+                gt[dd] += w.j1.Grad[3 * iat + dd];
+            for (int dd = 0; dd < 3; ++dd)
+              grads_now[3 * i + dd] = gt[dd];
+          }
+          for (int i = 0; i < cw; ++i)
+          {
+            getDrift<RT>(tauovermass, &grads_now[3 * i], &drifts[3 * i]);
+            for (int d = 0; d < 3; ++d)
+              drifts[3 * i + d] += deltas[3 * i + d];
+          }
+        }
+        else
+          drifts = deltas;
+
+        // ParticleSet::mw_makeMove: newpos = R[iat] + displ; distance-table temp/old rows
+        for (int i = 0; i < cw; ++i)
+        {
+          Walker& w = walkers[cr.w0 + i];
+          for (int d = 0; d < 3; ++d)
+            w.newpos[d] = w.R[3 * iat + d] + drifts[3 * i + d];
+          if (has_j2)
+          {
+            mi.row(w.newpos, w.rsoa.data(), npad_pos, N, iat, w.dist_new.data());
+            // note: dist_new needs stride j2.npad; npad_pos == j2.npad (both aligned_size<RT>(N))
+            RT oldpos[3] = {w.rsoa[iat], w.rsoa[npad_pos + iat], w.rsoa[2 * npad_pos + iat]};
+            mi.row(oldpos, w.rsoa.data(), npad_pos, N, iat, w.dist_old.data());
+            w.dist_old[iat] = std::numeric_limits<RT>::max();
+          }
+        }
+
+        // TWF::mw_calcRatioGrad
+        for (int i = 0; i < cw; ++i)
+        {
+          Walker& w = walkers[cr.w0 + i];
+          Det& d    = w.det[ig];
+          const int n = d.n;
+          VT* psi   = w.phi_vgl.data();
+          std::vector<VT> dpsi(3 * (size_t)n);
+          VT* d2psi = w.phi_vgl.data() + 4 * (size_t)n;
+          spoVGL(w, ig, w.newpos, psi, dpsi.data(), d2psi);
+          for (int j = 0; j < n; ++j)
+          {
+            w.phi_vgl[1 * (size_t)n + j] = dpsi[3 * j];
+            w.phi_vgl[2 * (size_t)n + j] = dpsi[3 * j + 1];
+            w.phi_vgl[3 * (size_t)n + j] = dpsi[3 * j + 2];
+          }
+          prepareInvRow(d, row);
+          VT ratio(0), gx(0), gy(0), gz(0);
+          for (int j = 0; j < n; ++j)
+            ratio += d.invRow[j] * psi[j];
+          for (int j = 0; j < n; ++j)
+          {
+            gx += d.invRow[j] * dpsi[3 * j];
+            gy += d.invRow[j] * dpsi[3 * j + 1];
+            gz += d.invRow[j] * dpsi[3 * j + 2];
+          }
+          d.curRatio = (double)ratio;
+          RT gn[3]   = {RT(gx / ratio), RT(gy / ratio), RT(gz / ratio)};
+          double r   = d.curRatio;
+          if (has_j2)
+            r *= j2.ratioGrad(w.j2, iat, w.dist_new.data(), gn);
+          if (has_j1)
+            r *= j1.ratioGrad(w.j1, mi, iat, w.newpos, gn);
+          ratios[i] = r;
+          for (int dd = 0; dd < 3; ++dd)
+            grads_new[3 * i + dd] = gn[dd];
+        }
+
+        if (use_drift)
+        {
+          for (int i = 0; i < cw; ++i)
+          {
+            const RT* dl = &deltas[3 * i];
+            log_gf[i]    = -oneover2tau * (dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
+            RT dr[3];
+            getDrift<RT>(tauovermass, &grads_new[3 * i], dr);
+            for (int d = 0; d < 3; ++d)
+              dr[d] += drifts[3 * i + d];
+            log_gb[i] = -oneover2tau * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
+          }
+        }
+        for (int i = 0; i < cw; ++i)
+          prob[i] = (RT)(ratios[i] * ratios[i]); // std::norm of a real PsiValue
+
+        // accept test: RNG consumed only if the first two conditions hold (VMCBatched.cpp:156-158)
+        for (int i = 0; i < cw; ++i)
+        {
+          const bool valid = true; // periodic cell: every move is valid
+          if (valid && prob[i] >= std::numeric_limits<RT>::epsilon() &&
+              cr.rng() < prob[i] * std::exp(log_gb[i] - log_gf[i]))
+            isAccepted[i] = 1;
+          else
+            isAccepted[i] = 0;
+        }
+
+        // TWF::mw_accept_rejectMove -> determinant, J2, J1; then ParticleSet::mw_accept_rejectMove
+        const bool batched = prm.batched_engine != 0;
+        for (int i = 0; i < cw; ++i)
+        {
+          Walker& w = walkers[cr.w0 + i];
+          Det& d    = w.det[ig];
+          d.invRow_id = -1;
+          if (isAccepted[i])
+          {
+            if (d.curRatio == 0.0)
+              throw std::runtime_error("oracle: accepted move with curRatio == 0");
+            d.log_value += std::log(std::complex<double>(d.curRatio));
+            const int n = d.n;
+            // save G/L rows (add_delay_list_save_sigma_VGL: AccelMatrixUpdateOMPTarget.hpp:125-136)
+            VT* dp = &d.dpsiM[(size_t)row * n * 3];
+            for (int j = 0; j < n; ++j)
+            {
+              dp[3 * j]     = w.phi_vgl[1 * (size_t)n + j];
+              dp[3 * j + 1] = w.phi_vgl[2 * (size_t)n + j];
+              dp[3 * j + 2] = w.phi_vgl[3 * (size_t)n + j];
+              d.d2psiM[(size_t)row * n + j] = w.phi_vgl[4 * (size_t)n + j];
+            }
+            // batched engine: sigma = Value(1)/ratios_local (VT arithmetic, DelayedUpdateBatched.h:599);
+            // CPU engine: RATIOT = PsiValue(double)
+            if (batched)
+              d.eng.acceptRow(d.psiMinv.data(), d.lda, row, w.phi_vgl.data(), (VT)d.curRatio);
+            else
+              d.eng.acceptRow(d.psiMinv.data(), d.lda, row, w.phi_vgl.data(), d.curRatio);
+            if (has_j2)
+              j2.acceptMove(w.j2, iat, w.dist_new.data(), w.dist_old.data());
+            if (has_j1)
+              j1.acceptMove(w.j1, iat);
+            for (int dd = 0; dd < 3; ++dd)
+            {
+              w.R[3 * iat + dd]             = w.newpos[dd];
+              w.rsoa[dd * npad_pos + iat] = w.newpos[dd];
+            }
+            w.n_accept++;
+          }
+          else
+          {
+            if (batched && prm.delay_rank > 1)
+              d.eng.pseudoAcceptRow(d.psiMinv.data(), d.lda, row);
+            w.n_reject++;
+          }
+          d.curRatio = 1.0;
+          if (acc_log)
+            acc_log[(size_t)iat * nw + cr.w0 + i] = isAccepted[i];
+        }
+      }
+    }
+    // flex_completeUpdates (DiracDeterminantBatched.cpp:545-591): flush pending delays
+    for (int i = 0; i < cw; ++i)
+      for (int s = 0; s < 2; ++s)
+      {
+        Det& d = walkers[cr.w0 + i].det[s];
+        d.eng.updateInvMat(d.psiMinv.data(), d.lda);
+        d.invRow_id = -1;
+      }
+  }
+
+  void sweep(int nsteps, bool log_accept)
+  {
+    if (log_accept)
+      accept_log.assign((size_t)nsteps * N * nw, 0);
+    for (int step = 0; step < nsteps; ++step)
+    {
+      uint8_t* lg = log_accept ? accept_log.data() + (size_t)step * N * nw : nullptr;
+#pragma omp parallel for schedule(static, 1)
+      for (int c = 0; c < (int)crowds.size(); ++c)
+        advanceCrowd(crowds[c], lg);
+    }
+  }
+
+  // ---- G, L of all particles and kinetic energy -1/2 sum(L + G.G)  (mw_evaluateGL, fromscratch=false;
+  // DiracDeterminantBatched.cpp:594-604 computeGL; TwoBodyJastrow.cpp:769-808; J1OrbitalSoA.h:112-123;
+  // QMCHamiltonians/BareKineticEnergy: KE = -1/2 (sum L + sum G.G), L = laplacian of log psi)
+  void evaluateGL(int iw, double* G /*[N][3]*/, double* L /*[N]*/, double* logpsi, double* ke)
+  {
+    Walker& w = walkers[iw];
+    std::vector<RT> g(3 * (size_t)N, RT(0)), l(N, RT(0));
+    for (int s = 0; s < 2; ++s)
+    {
+      Det& d = w.det[s];
+      for (int i = 0; i < d.n; ++i)
+      {
+        const VT* inv = &d.psiMinv[(size_t)i * d.lda];
+        const VT* dp  = &d.dpsiM[(size_t)i * d.n * 3];
+        const VT* d2  = &d.d2psiM[(size_t)i * d.n];
+        VT rv[3] = {VT(0), VT(0), VT(0)}, lap(0);
+        for (int j = 0; j < d.n; ++j)
+        {
+          rv[0] += inv[j] * dp[3 * j];
+          rv[1] += inv[j] * dp[3 * j + 1];
+          rv[2] += inv[j] * dp[3 * j + 2];
+        }
+        for (int j = 0; j < d.n; ++j)
+          lap += inv[j] * d2[j];
+        const int iat = d.first + i;
+        for (int dd = 0; dd < 3; ++dd)
+          g[3 * iat + dd] += rv[dd];
+        l[iat] += lap - (rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2]);
+      }
+    }
+    if (has_j2)
+      for (int i = 0; i < N; ++i)
+      {
+        for (int dd = 0; dd < 3; ++dd)
+          g[3 * i + dd] += w.j2.dUat[dd * j2.npad + i];
+        l[i] += w.j2.d2Uat[i];
+      }
+    if (has_j1)
+      for (int i = 0; i < N; ++i)
+      {
+        for (int dd = 0; dd < 3; ++dd)
+          g[3 * i + dd] += w.j1.Grad[3 * i + dd];
+        l[i] -= w.j1.Lap[i];
+      }
+    double kin = 0;
+    for (int i = 0; i < N; ++i)
+    {
+      kin += (double)l[i] + (double)g[3 * i] * g[3 * i] + (double)g[3 * i + 1] * g[3 * i + 1] +
+          (double)g[3 * i + 2] * g[3 * i + 2];
+      if (G)
+        for (int dd = 0; dd < 3; ++dd)
+          G[3 * i + dd] = g[3 * i + dd];
+      if (L)
+        L[i] = l[i];
+    }
+    if (ke)
+      *ke = -0.5 * kin;
+    if (logpsi)
+      *logpsi = w.det[0].log_value.real() + w.det[1].log_value.real() + (has_j2 ? w.j2.log_value : 0.0) +
+          (has_j1 ? w.j1.log_value : 0.0);
+  }
+};
+
+} // namespace orc

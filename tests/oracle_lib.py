@@ -1,0 +1,421 @@
+"""ctypes bindings for the CPU oracle (oracle/liboracle.so and, when built, oracle/_ref/libqmcref.so).
+
+TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs import this module.  The product package (qmcpack_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+PORT_SO = os.path.join(ORACLE_DIR, "liboracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libqmcref.so")
+
+c_dp = C.POINTER(C.c_double)
+c_fp = C.POINTER(C.c_float)
+c_ip = C.POINTER(C.c_int)
+
+
+def build(force=False):
+    """Compile the oracle with oracle/Makefile (g++ only).  oracle/_ref is (re)built only where /root/reference exists."""
+    if force or not os.path.exists(PORT_SO):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, PORT_SO], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference/src") and (force or not os.path.exists(REF_SO)):
+        subprocess.call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
+class VMCParams(C.Structure):
+    _fields_ = [
+        ("precision", C.c_int), ("n_up", C.c_int), ("n_dn", C.c_int),
+        ("lattice", C.c_double * 9),
+        ("coefs", C.c_void_p * 2), ("grid", C.c_int * 3), ("npad", C.c_int),
+        ("n_j2", C.c_int), ("j2_uu", c_dp), ("j2_ud", c_dp), ("j2_rcut", C.c_double),
+        ("nions", C.c_int), ("ion_pos", c_dp), ("ion_grp", c_ip), ("n_ion_groups", C.c_int),
+        ("n_j1", C.c_int), ("j1_params", c_dp), ("j1_rcut", c_dp),
+        ("nw", C.c_int), ("ncrowds", C.c_int), ("seeds", C.POINTER(C.c_uint32)),
+        ("tau", C.c_double), ("use_drift", C.c_int), ("delay_rank", C.c_int), ("batched_engine", C.c_int),
+    ]
+
+
+def azeros(shape, dtype, align=64):
+    """64-byte aligned zeros: the reference kernels in oracle/_ref use aligned SIMD loads/stores."""
+    dtype = np.dtype(dtype)
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    n = int(np.prod(shape))
+    buf = np.zeros(n * dtype.itemsize + align, np.uint8)
+    off = (-buf.ctypes.data) % align
+    return buf[off:off + n * dtype.itemsize].view(dtype).reshape(shape)
+
+
+def _np(a, dt):
+    a = np.ascontiguousarray(a, dtype=dt)
+    if a.ctypes.data % 64:
+        b = azeros(a.shape, a.dtype)
+        b[...] = a
+        a = b
+    return a
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """Thin numpy-facing wrapper around one oracle shared library."""
+
+    def __init__(self, path):
+        self.path = path
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_symtrace.restype = C.c_double
+        L.orc_symtrace.argtypes = [C.c_double] * 6 + [c_dp]
+        L.orc_aligned_size.restype = C.c_long
+        L.orc_aligned_size.argtypes = [C.c_int, C.c_long]
+        L.orc_vmc_create.restype = C.c_void_p
+        L.orc_vmc_create.argtypes = [C.POINTER(VMCParams)]
+        for name in ("orc_du_create_d", "orc_du_create_f"):
+            getattr(L, name).restype = C.c_void_p
+        self.is_reference = bool(L.orc_is_reference_build())
+
+    # -- helpers
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.lib.orc_last_error().decode())
+
+    @staticmethod
+    def suf(dtype):
+        return "f" if np.dtype(dtype) == np.float32 else "d"
+
+    def aligned_size(self, dtype, n):
+        return int(self.lib.orc_aligned_size(1 if np.dtype(dtype) == np.float32 else 0, n))
+
+    # -- golden-vector pieces
+    def symtrace(self, h, gg):
+        g = _np(gg, np.float64)
+        return self.lib.orc_symtrace(*[C.c_double(x) for x in h], g.ctypes.data_as(c_dp))
+
+    def prefactors(self, t, dtype=np.float64):
+        a, da, d2a = (np.zeros(4, dtype) for _ in range(3))
+        ct = C.c_float if self.suf(dtype) == "f" else C.c_double
+        getattr(self.lib, "orc_prefactors_" + self.suf(dtype))(ct(t), _p(a), _p(da), _p(d2a))
+        return a, da, d2a
+
+    def create_periodic_coefs(self, data):
+        data = _np(data, np.float64)
+        M = np.array(data.shape, dtype=np.int32)
+        coefs = np.zeros(tuple(int(m) + 3 for m in M), np.float64)
+        self.lib.orc_create_periodic_coefs_3d(_p(M), _p(data), _p(coefs))
+        return coefs
+
+    def spline_eval(self, coefs, ns, which, pos):
+        """coefs [Nx][Ny][Nz][npad]; pos unit coords; returns (v, g, h) with g/h shaped [3|6][npad] ([3][npad] twice for VGL)."""
+        dt = coefs.dtype
+        grid = np.array([s - 3 for s in coefs.shape[:3]], np.int32)
+        npad = coefs.shape[3]
+        coefs = _np(coefs, dt)
+        v = azeros(npad, dt)
+        g = azeros((3, npad), dt)
+        h = azeros((6 if which == 2 else 3, npad), dt)
+        ct = C.c_float if dt == np.float32 else C.c_double
+        f = getattr(self.lib, "orc_spline_eval_" + self.suf(dt))
+        self._chk(f(_p(coefs), _p(grid), C.c_int(ns), C.c_long(npad), C.c_int(which), ct(pos[0]), ct(pos[1]),
+                    ct(pos[2]), _p(v), _p(g), _p(h)))
+        return v, g, h
+
+    # -- SPOSet level
+    def r2r_vgl(self, coefs, G, norb, r, halfG=None):
+        dt = coefs.dtype
+        grid = np.array([s - 3 for s in coefs.shape[:3]], np.int32)
+        npad = coefs.shape[3]
+        r = _np(r, np.float64)
+        nw = r.shape[0]
+        G = _np(G, np.float64)
+        hg = _np(halfG if halfG is not None else [0, 0, 0], np.int32)
+        psi = np.zeros((nw, norb), dt)
+        dpsi = np.zeros((nw, norb, 3), dt)
+        d2psi = np.zeros((nw, norb), dt)
+        f = getattr(self.lib, "orc_r2r_mw_evaluate_vgl_" + self.suf(dt))
+        self._chk(f(_p(coefs), _p(grid), C.c_int(norb), C.c_long(npad), _p(G), _p(hg), C.c_int(norb), C.c_int(nw),
+                    _p(r), _p(psi), _p(dpsi), _p(d2psi)))
+        return psi, dpsi, d2psi
+
+    def r2r_value(self, coefs, G, norb, r, halfG=None):
+        dt = coefs.dtype
+        grid = np.array([s - 3 for s in coefs.shape[:3]], np.int32)
+        npad = coefs.shape[3]
+        r = _np(r, np.float64)
+        nw = r.shape[0]
+        G = _np(G, np.float64)
+        hg = _np(halfG if halfG is not None else [0, 0, 0], np.int32)
+        psi = np.zeros((nw, norb), dt)
+        f = getattr(self.lib, "orc_r2r_mw_evaluate_value_" + self.suf(dt))
+        self._chk(f(_p(coefs), _p(grid), C.c_int(norb), C.c_long(npad), _p(G), _p(hg), C.c_int(norb), C.c_int(nw),
+                    _p(r), _p(psi)))
+        return psi
+
+    def r2r_vgl_ratio_grads(self, coefs, G, norb, r, invrow, halfG=None):
+        dt = coefs.dtype
+        grid = np.array([s - 3 for s in coefs.shape[:3]], np.int32)
+        npad = coefs.shape[3]
+        r = _np(r, np.float64)
+        nw = r.shape[0]
+        G = _np(G, np.float64)
+        hg = _np(halfG if halfG is not None else [0, 0, 0], np.int32)
+        invrow = _np(invrow, dt)
+        phi = np.zeros((5, nw, norb), dt)
+        ratios = np.zeros(nw, dt)
+        grads = np.zeros((nw, 3), dt)
+        f = getattr(self.lib, "orc_r2r_mw_vgl_ratio_grads_" + self.suf(dt))
+        self._chk(f(_p(coefs), _p(grid), C.c_int(norb), C.c_long(npad), _p(G), _p(hg), C.c_int(norb), C.c_int(nw),
+                    _p(r), _p(invrow), C.c_long(invrow.shape[1]), _p(phi), _p(ratios), _p(grads)))
+        return phi, ratios, grads
+
+    def c2c_vgl(self, coefs, G, kcart, norb, r, value_only=False):
+        dt = coefs.dtype
+        cdt = np.complex64 if dt == np.float32 else np.complex128
+        grid = np.array([s - 3 for s in coefs.shape[:3]], np.int32)
+        npad = coefs.shape[3]
+        r = _np(r, np.float64)
+        nw = r.shape[0]
+        G = _np(G, np.float64)
+        k = _np(kcart, np.float64)
+        psi = np.zeros((nw, norb), cdt)
+        dpsi = np.zeros((nw, norb, 3), cdt)
+        d2psi = np.zeros((nw, norb), cdt)
+        f = getattr(self.lib, "orc_c2c_mw_evaluate_vgl_" + self.suf(dt))
+        self._chk(f(_p(coefs), _p(grid), C.c_int(2 * norb), C.c_long(npad), _p(G), _p(k), C.c_int(norb), C.c_int(nw),
+                    _p(r), _p(psi), _p(dpsi), _p(d2psi), C.c_int(1 if value_only else 0)))
+        return (psi,) if value_only else (psi, dpsi, d2psi)
+
+    def c2c_vgl_ratio_grads(self, coefs, G, kcart, norb, r, invrow):
+        dt = coefs.dtype
+        cdt = np.complex64 if dt == np.float32 else np.complex128
+        grid = np.array([s - 3 for s in coefs.shape[:3]], np.int32)
+        npad = coefs.shape[3]
+        r = _np(r, np.float64)
+        nw = r.shape[0]
+        G = _np(G, np.float64)
+        k = _np(kcart, np.float64)
+        invrow = _np(invrow, cdt)
+        phi = np.zeros((5, nw, norb), cdt)
+        ratios = np.zeros(nw, cdt)
+        grads = np.zeros((nw, 3), cdt)
+        f = getattr(self.lib, "orc_c2c_mw_vgl_ratio_grads_" + self.suf(dt))
+        self._chk(f(_p(coefs), _p(grid), C.c_int(2 * norb), C.c_long(npad), _p(G), _p(k), C.c_int(norb), C.c_int(nw),
+                    _p(r), _p(invrow), C.c_long(invrow.shape[1]), _p(phi), _p(ratios), _p(grads)))
+        return phi, ratios, grads
+
+    # -- dense inverse
+    def invert_transpose(self, a, lda=None):
+        a = np.ascontiguousarray(a)
+        dt = a.dtype
+        n = a.shape[0]
+        lda = lda or n
+        inv = np.zeros((n, lda), dt)
+        logdet = np.zeros(2, np.float64)
+        f = getattr(self.lib, "orc_invert_transpose_" + self.suf(dt))
+        self._chk(f(_p(a), C.c_int(n), C.c_int(a.shape[1]), _p(inv), C.c_int(lda), _p(logdet)))
+        return inv, complex(logdet[0], logdet[1])
+
+    # -- delayed update engine
+    def du(self, n, k, dtype=np.float64):
+        return DelayedUpdateHandle(self, n, k, dtype)
+
+    # -- Jastrow / distances
+    def functor_eval(self, params, rcut, cusp, r, dtype=np.float64):
+        params = _np(params, np.float64)
+        r = _np(r, dtype)
+        u, du, d2u = (np.zeros_like(r) for _ in range(3))
+        f = getattr(self.lib, "orc_functor_eval_" + self.suf(dtype))
+        self._chk(f(_p(params), C.c_int(len(params)), C.c_double(rcut), C.c_double(cusp), C.c_int(len(r)), _p(r),
+                    _p(u), _p(du), _p(d2u)))
+        return u, du, d2u
+
+    def functor_coefs(self, params, rcut, cusp, dtype=np.float64):
+        params = _np(params, np.float64)
+        coefs = np.zeros(len(params) + 4, dtype)
+        dri = np.zeros(1, dtype)
+        f = getattr(self.lib, "orc_functor_coefs_" + self.suf(dtype))
+        self._chk(f(_p(params), C.c_int(len(params)), C.c_double(rcut), C.c_double(cusp), _p(coefs), _p(dri)))
+        return coefs, dri[0]
+
+    def dist_row(self, lattice, pos, rsoa, nsrc, flip_ind, dtype=np.float64):
+        lattice = _np(lattice, np.float64)
+        pos = _np(pos, dtype)
+        rsoa = _np(rsoa, dtype)
+        npad = rsoa.shape[1]
+        out = np.zeros((4, npad), dtype)
+        f = getattr(self.lib, "orc_dist_row_" + self.suf(dtype))
+        self._chk(f(_p(lattice), _p(pos), _p(rsoa), C.c_long(npad), C.c_int(nsrc), C.c_int(flip_ind), _p(out)))
+        return out
+
+    # -- RNG
+    def rng_uniform(self, seed, n):
+        out = np.zeros(n, np.float64)
+        self.lib.orc_rng_uniform(C.c_uint32(seed), C.c_int(n), _p(out))
+        return out
+
+    def rng_raw(self, seed, n):
+        out = np.zeros(n, np.uint32)
+        self.lib.orc_rng_raw(C.c_uint32(seed), C.c_long(n), _p(out))
+        return out
+
+    def rng_gauss(self, seed, n, dtype=np.float64):
+        out = np.zeros(n, dtype)
+        getattr(self.lib, "orc_rng_gauss_" + self.suf(dtype))(C.c_uint32(seed), C.c_int(n), _p(out))
+        return out
+
+    def vmc(self, system, **kw):
+        return OracleVMC(self, system, **kw)
+
+
+class DelayedUpdateHandle:
+    def __init__(self, orc, n, k, dtype):
+        self.o, self.n, self.k, self.dt = orc, n, k, np.dtype(dtype)
+        self.s = orc.suf(dtype)
+        self.h = C.c_void_p(getattr(orc.lib, "orc_du_create_" + self.s)(C.c_int(n), C.c_int(k)))
+
+    def __del__(self):
+        try:
+            getattr(self.o.lib, "orc_du_destroy_" + self.s)(self.h)
+        except Exception:
+            pass
+
+    def get_inv_row(self, Ainv, row):
+        out = np.zeros(self.n, self.dt)
+        getattr(self.o.lib, "orc_du_get_inv_row_" + self.s)(self.h, _p(Ainv), C.c_int(Ainv.shape[1]), C.c_int(row), _p(out))
+        return out
+
+    def accept_row(self, Ainv, row, psiV, ratio):
+        psiV = _np(psiV, self.dt)
+        getattr(self.o.lib, "orc_du_accept_row_" + self.s)(self.h, _p(Ainv), C.c_int(Ainv.shape[1]), C.c_int(row),
+                                                          _p(psiV), C.c_double(ratio))
+
+    def pseudo_accept_row(self, Ainv, row):
+        getattr(self.o.lib, "orc_du_pseudo_accept_row_" + self.s)(self.h, _p(Ainv), C.c_int(Ainv.shape[1]), C.c_int(row))
+
+    def update_inv_mat(self, Ainv):
+        getattr(self.o.lib, "orc_du_update_inv_mat_" + self.s)(self.h, _p(Ainv), C.c_int(Ainv.shape[1]))
+
+    @property
+    def delay_count(self):
+        return int(getattr(self.o.lib, "orc_du_delay_count_" + self.s)(self.h))
+
+
+class OracleVMC:
+    """The oracle's restatement of VMCBatched::advanceWalkers over a synthetic system (see qmcpack_b200.workload)."""
+
+    def __init__(self, orc, system, nw, ncrowds=1, seeds=None, tau=0.3, use_drift=True, delay_rank=32,
+                 batched_engine=True, precision=None):
+        self.o = orc
+        s = system
+        prec = precision if precision is not None else (1 if s["coefs"][0].dtype == np.float32 else 0)
+        p = VMCParams()
+        p.precision = prec
+        p.n_up, p.n_dn = s["n_up"], s["n_dn"]
+        p.lattice[:] = list(np.asarray(s["lattice"], np.float64).ravel())
+        self._keep = []
+        for i in range(2):
+            c = s["coefs"][i]
+            assert c.flags["C_CONTIGUOUS"]
+            p.coefs[i] = c.ctypes.data
+            self._keep.append(c)
+        p.grid[:] = [int(x) - 3 for x in s["coefs"][0].shape[:3]]
+        p.npad = int(s["coefs"][0].shape[3])
+        j2 = s.get("j2")
+        if j2:
+            uu, ud = _np(j2["uu"], np.float64), _np(j2["ud"], np.float64)
+            self._keep += [uu, ud]
+            p.n_j2, p.j2_uu, p.j2_ud, p.j2_rcut = len(uu), uu.ctypes.data_as(c_dp), ud.ctypes.data_as(c_dp), j2["rcut"]
+        j1 = s.get("j1")
+        if j1:
+            ip = _np(j1["ion_pos"], np.float64)
+            ig = _np(j1["ion_grp"], np.int32)
+            prm = _np(j1["params"], np.float64)
+            rc = _np(j1["rcut"], np.float64)
+            self._keep += [ip, ig, prm, rc]
+            p.nions, p.ion_pos, p.ion_grp = len(ig), ip.ctypes.data_as(c_dp), ig.ctypes.data_as(c_ip)
+            p.n_ion_groups, p.n_j1 = prm.shape[0], prm.shape[1]
+            p.j1_params, p.j1_rcut = prm.ctypes.data_as(c_dp), rc.ctypes.data_as(c_dp)
+        p.nw, p.ncrowds = nw, ncrowds
+        sd = _np(seeds if seeds is not None else [1000 + c for c in range(ncrowds)], np.uint32)
+        self._keep.append(sd)
+        p.seeds = sd.ctypes.data_as(C.POINTER(C.c_uint32))
+        p.tau, p.use_drift, p.delay_rank = tau, int(use_drift), delay_rank
+        p.batched_engine = int(batched_engine and not orc.is_reference)
+        self.p = p
+        self.N = p.n_up + p.n_dn
+        self.nw = nw
+        self.h = C.c_void_p(orc.lib.orc_vmc_create(C.byref(p)))
+        if not self.h:
+            raise RuntimeError(orc.lib.orc_last_error().decode())
+
+    def __del__(self):
+        try:
+            self.o.lib.orc_vmc_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_positions(self, R):
+        R = _np(R, np.float64)
+        assert R.shape == (self.nw, self.N, 3)
+        self.o._chk(self.o.lib.orc_vmc_set_positions(self.h, _p(R)))
+
+    def recompute(self):
+        self.o._chk(self.o.lib.orc_vmc_recompute(self.h))
+
+    def sweep(self, nsteps=1, log_accept=False):
+        log = np.zeros((nsteps, self.N, self.nw), np.uint8) if log_accept else None
+        sec = C.c_double(0)
+        self.o._chk(self.o.lib.orc_vmc_sweep(self.h, C.c_int(nsteps), _p(log) if log_accept else None, C.byref(sec)))
+        self.last_seconds = sec.value
+        return log
+
+    def positions(self):
+        R = np.zeros((self.nw, self.N, 3), np.float64)
+        self.o._chk(self.o.lib.orc_vmc_get_positions(self.h, _p(R)))
+        return R
+
+    def evaluate_gl(self):
+        logpsi, ke = np.zeros(self.nw), np.zeros(self.nw)
+        G, L = np.zeros((self.nw, self.N, 3)), np.zeros((self.nw, self.N))
+        self.o._chk(self.o.lib.orc_vmc_evaluate_gl(self.h, _p(logpsi), _p(ke), _p(G), _p(L)))
+        return logpsi, ke, G, L
+
+    def counts(self):
+        a, r = np.zeros(self.nw, np.int64), np.zeros(self.nw, np.int64)
+        self.o._chk(self.o.lib.orc_vmc_get_counts(self.h, _p(a), _p(r)))
+        return a, r
+
+    def psiminv(self, iw, s):
+        n = self.p.n_up if s == 0 else self.p.n_dn
+        out = np.zeros((n, n))
+        ld = C.c_double(0)
+        self.o._chk(self.o.lib.orc_vmc_get_psiminv(self.h, C.c_int(iw), C.c_int(s), _p(out), C.byref(ld)))
+        return out, ld.value
+
+    def j2_state(self, iw):
+        Uat, dUat, d2Uat = np.zeros(self.N), np.zeros((3, self.N)), np.zeros(self.N)
+        self.o._chk(self.o.lib.orc_vmc_get_j2(self.h, C.c_int(iw), _p(Uat), _p(dUat), _p(d2Uat)))
+        return Uat, dUat, d2Uat
+
+
+_cache = {}
+
+
+def port():
+    if "port" not in _cache:
+        build()
+        _cache["port"] = Oracle(PORT_SO)
+    return _cache["port"]
+
+
+def ref():
+    """The reference-compiled checker, or None when oracle/_ref has not been built."""
+    if "ref" not in _cache:
+        build()
+        _cache["ref"] = Oracle(REF_SO) if os.path.exists(REF_SO) else None
+    return _cache["ref"]

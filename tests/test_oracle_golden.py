@@ -1,0 +1,261 @@
+"""Pins the CPU oracle (oracle/) against the golden vectors of the reference's own unit tests and, when
+oracle/_ref was built from the reference sources, against the reference's compiled kernels.
+
+Golden sources (paths under /root/reference/src):
+  spline2/tests/test_multi_spline.cpp:27-41 (SymTrace), :44-80 (prefactors), :231-314 (5^3 sine grid V/G/H/L)
+  QMCWaveFunctions/tests/createTestMatrix.h:36-67 + test_DiracMatrix.cpp:58-81 (3x3 inverse, logdet)
+  QMCWaveFunctions/tests/test_DiracMatrix.cpp:315-366 (row update: det ratio 0.178276269185, updated inverse)
+  QMCWaveFunctions/tests/test_J2_bspline.cpp:145-175 (functor u,du,d2u table), :84-88, :219-259 (logpsi, ratios)
+"""
+import numpy as np
+import pytest
+
+approx = pytest.approx
+
+
+def test_symtrace(orc):
+    assert orc.symtrace([1, 2, 3, 4.4, 1.1, 0.9], [0.1, 1.6, 1.2, 2.3, 9.4, 2.3]) == approx(29.43)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_prefactors(orc, dt):
+    a, _, _ = orc.prefactors(0.1, dt)
+    assert a == approx([0.1215, 0.657167, 0.221167, 0.000166667], rel=1e-5)
+    a, da, d2a = orc.prefactors(0.8, dt)
+    assert a == approx([0.00133333, 0.282667, 0.630667, 0.0853333], rel=1e-5)
+    assert da == approx([-0.02, -0.64, 0.34, 0.32], rel=1e-5)
+    assert d2a == approx([0.2, 0.4, -1.4, 0.8], rel=1e-5)
+
+
+def sine_grid(N=5):
+    i = np.arange(N) / N
+    tpi = 2 * np.pi
+    return (np.sin(tpi * i)[:, None, None] + np.sin(3 * tpi * i)[None, :, None] + np.sin(4 * tpi * i)[None, None, :])
+
+
+def multi_table(coefs1, dt, nspl=1):
+    from qmcpack_b200.workload import aligned_size
+    npad = aligned_size(dt, nspl)
+    out = np.zeros(coefs1.shape + (npad,), dt)
+    for m in range(nspl):
+        out[..., m] = coefs1
+    return out
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_multi_bspline_periodic_5cubed(orc, dt):
+    """test_multi_spline.cpp:231-314, float and double."""
+    coefs = multi_table(orc.create_periodic_coefs(sine_grid()), dt)
+    tol = dict(rel=2e-5, abs=2e-5) if dt == np.float32 else dict(rel=1e-8, abs=1e-8)
+    v, _, _ = orc.spline_eval(coefs, 1, 0, (0, 0, 0))
+    assert v[0] == approx(-3.529930688e-12, abs=1e-6)
+    v, g, h = orc.spline_eval(coefs, 1, 2, (0, 0, 0))
+    assert g[:, 0] == approx([6.178320809, -7.402942564, -6.178320809], **tol)
+    assert h[:, 0] == approx(np.zeros(6), abs=2e-4 if dt == np.float32 else 1e-8)
+    pos = (0.1, 0.2, 0.3)
+    v, _, _ = orc.spline_eval(coefs, 1, 0, pos)
+    assert v[0] == approx(-0.9476393279, **tol)
+    v, g, h = orc.spline_eval(coefs, 1, 2, pos)
+    assert v[0] == approx(-0.9476393279, **tol)
+    assert g[:, 0] == approx([5.111042137, 5.989106342, 1.952244379], **tol)
+    habs = 2e-4 if dt == np.float32 else 1e-7
+    assert h[:, 0] == approx([-21.34557341, 1.174505743e-09, -1.1483271e-09, 133.9204891, -2.15319293e-09,
+                              34.53786329], rel=2e-5, abs=habs)
+    v, g, l = orc.spline_eval(coefs, 1, 1, pos)
+    assert v[0] == approx(-0.9476393279, **tol)
+    assert g[:, 0] == approx([5.111042137, 5.989106342, 1.952244379], **tol)
+    assert l[0, 0] == approx(147.1127789, rel=2e-5)
+
+
+def test_batched_positions_match_single(orc):
+    """test_multi_spline.cpp:316-349: the batched position API returns the single-position numbers."""
+    coefs = multi_table(orc.create_periodic_coefs(sine_grid()), np.float64)
+    G = np.eye(3)
+    psi, dpsi, d2psi = orc.r2r_vgl(coefs, G, 1, [[0.1, 0.2, 0.3], [0.3, 0.1, 0.2], [0.1, 0.2, 0.3]])
+    assert psi[0, 0] == approx(-0.9476393279)
+    assert psi[2, 0] == approx(-0.9476393279)
+    assert dpsi[0, 0, 1] == approx(5.989106342)
+    assert d2psi[2, 0] == approx(147.1127789)
+
+
+def test_dirac_matrix_inverse(orc):
+    a = np.array([[2.3, 4.5, 2.6], [0.5, 8.5, 3.3], [1.8, 4.4, 4.9]])
+    b = np.array([[0.6159749342, -0.2408954682, -0.1646081192], [0.07923894288, 0.1496231042, -0.1428117337],
+                  [-0.2974298429, -0.04586322768, 0.3927890292]])
+    inv, logdet = orc.invert_transpose(np.ascontiguousarray(a.T))
+    assert inv == approx(b, rel=1e-8)
+    assert logdet.real == approx(3.78518913425)
+    assert np.exp(1j * logdet.imag) == approx(1.0, abs=1e-12)  # phase is defined modulo 2*pi (LogComplexApprox)
+    inv, logdet = orc.invert_transpose(np.eye(3))
+    assert inv == approx(np.eye(3))
+    assert abs(logdet) == approx(0.0, abs=1e-14)
+
+
+def test_dirac_matrix_update_row(orc):
+    """test_DiracMatrix.cpp:315-366 with delay rank 1."""
+    a = np.array([[2.3, 4.5, 2.6], [0.5, 8.5, 3.3], [1.8, 4.4, 4.9]])
+    a_inv, _ = orc.invert_transpose(np.ascontiguousarray(a.T))
+    eng = orc.du(3, 1)
+    v = np.array([1.9, 2.0, 3.1])
+    row = eng.get_inv_row(a_inv, 0)
+    ratio = float(v @ row)
+    assert ratio == approx(0.178276269185)
+    eng.accept_row(a_inv, 0, v, ratio)
+    b = np.array([[3.455170657, -1.35124809, -0.9233316353], [0.05476311768, 0.1591951095, -0.1362710138],
+                  [-2.235099338, 0.7119205298, 0.9105960265]])
+    assert a_inv == approx(b, rel=1e-8)
+
+
+@pytest.mark.parametrize("k", [1, 2, 4, 8])
+@pytest.mark.parametrize("batched", [False, True])
+def test_delayed_update_equals_fresh_inverse(orc, k, batched):
+    """Procedure of test_DiracDeterminantBatched.cpp:262-470: after any accept sequence the delayed engine must equal
+    a fresh LU inverse of the explicitly updated matrix; in batched mode rejected moves are pseudo-accepted."""
+    rng = np.random.default_rng(5 + k)
+    n = 24
+    psiM = rng.normal(size=(n, n))
+    ainv, logdet0 = orc.invert_transpose(psiM, lda=32)
+    eng = orc.du(n, k)
+    logdet = logdet0.real
+    for move in range(3 * n):
+        r = move % n
+        new = rng.normal(size=n)
+        row = eng.get_inv_row(ainv, r)
+        ratio = float(row @ new)
+        accept = rng.random() < 0.6
+        if accept:
+            eng.accept_row(ainv, r, new, ratio)
+            psiM[r] = new
+            logdet += np.log(abs(ratio))
+        elif batched and k > 1:
+            eng.pseudo_accept_row(ainv, r)
+    eng.update_inv_mat(ainv)
+    fresh, ld = orc.invert_transpose(psiM, lda=32)
+    assert ainv[:, :n] == approx(fresh[:, :n], rel=1e-7, abs=1e-9)
+    assert logdet == approx(ld.real, rel=1e-9)
+
+
+J2_UD_TEST = [0.02904699284, -0.1004179, -0.1752703883, -0.2232576505, -0.2728029201, -0.3253286875, -0.3624525145,
+              -0.3958223107, -0.4268582166, -0.4394531176]
+J2_VALS = [(0.00, 0.1374071801, -0.5, 0.7866949593), (0.60, -0.04952403966, -0.1706645865, 0.3110897524),
+           (1.20, -0.121361995, -0.09471371432, 0.055337302), (1.80, -0.1695590431, -0.06815900213, 0.0331784053),
+           (2.40, -0.2058414025, -0.05505192964, 0.01049597156), (3.00, -0.2382237097, -0.05422744821, -0.002401552969),
+           (3.60, -0.2712606182, -0.05600918024, -0.003537553803), (4.20, -0.3047843679, -0.05428535477, 0.0101841028),
+           (4.80, -0.3347515004, -0.04506573714, 0.01469003611), (5.40, -0.3597048574, -0.03904232165, 0.005388015505),
+           (6.00, -0.3823503292, -0.03657502025, 0.003511355265), (6.60, -0.4036800017, -0.03415678101, 0.007891305516),
+           (7.20, -0.4219818468, -0.02556305518, 0.02075444724), (7.80, -0.4192355508, 0.06799438701, 0.3266190181),
+           (8.40, -0.3019238309, 0.32586994, 0.2880861726), (9.00, -0.09726352421, 0.2851358014, -0.4238666348),
+           (9.60, -0.006239062395, 0.04679296796, -0.2339648398), (10.20, 0, 0, 0), (10.80, 0, 0, 0), (11.40, 0, 0, 0)]
+
+
+def test_bspline_functor_table(orc):
+    """test_J2_bspline.cpp:145-175 (u-d functor, cusp -1/2, rcut 10)."""
+    r = np.array([v[0] for v in J2_VALS])
+    u, du, d2u = orc.functor_eval(J2_UD_TEST, 10.0, -0.5, r)
+    assert u == approx([v[1] for v in J2_VALS], rel=1e-6, abs=1e-9)
+    assert du == approx([v[2] for v in J2_VALS], rel=1e-6, abs=1e-9)
+    assert d2u == approx([v[3] for v in J2_VALS], rel=1e-6, abs=1e-9)
+
+
+def _two_electron_system():
+    # open-boundary test geometry emulated by a huge cubic cell (rcut = 10 << L/2)
+    L = 400.0
+    table = np.zeros((4, 4, 4, 8), np.float64)  # 1^3 grid, constant orbitals (never used in this test)
+    return dict(n_up=1, n_dn=1, lattice=np.eye(3) * L, coefs=[table, table],
+                j2=dict(uu=J2_UD_TEST, ud=J2_UD_TEST, rcut=10.0))
+
+
+def test_j2_logpsi_two_electrons(orc):
+    """test_J2_bspline.cpp:84-88: electrons at (1,0,0),(0,0,0): log psi = 0.1012632641, KE = -0.1616624771."""
+    import oracle_lib
+    sysd = _two_electron_system()
+    # constant non-zero orbital tables so the 1x1 determinants are regular; J2 is what is checked
+    sysd["coefs"] = [np.ones((4, 4, 4, 8)), np.ones((4, 4, 4, 8))]
+    vmc = oracle_lib.OracleVMC(orc, sysd, nw=1, delay_rank=1)
+    vmc.set_positions(np.array([[[1.0, 0, 0], [0, 0, 0]]]))
+    vmc.recompute()
+    Uat, dUat, d2Uat = vmc.j2_state(0)
+    logpsi_j2 = -0.5 * Uat.sum()
+    assert logpsi_j2 == approx(0.1012632641)
+    ke = -0.5 * ((dUat ** 2).sum() + d2Uat.sum())
+    assert ke == approx(-0.1616624771)
+
+
+def test_mt19937_stream(orc):
+    """std::mt19937 KAT (10000th output of a default-seeded engine is 4123659995, [rand.predef]) and the
+    uniform_real_distribution_as_boost mapping (Utilities/StdRandom.h:43-47)."""
+    raw = orc.rng_raw(5489, 10000)
+    assert int(raw[-1]) == 4123659995
+    u = orc.rng_uniform(5489, 4)
+    assert u == approx(raw[:4].astype(np.float64) / 4294967296.0, rel=0, abs=0)
+
+
+def test_box_muller(orc):
+    """RandomSeqGenerator.h:33-52 restated in numpy from the same raw stream."""
+    n = 7
+    u = orc.rng_uniform(911, 8)
+    g = orc.rng_gauss(911, n)
+    exp = []
+    for i in range(0, 8, 2):
+        t1 = np.sqrt(-2.0 * np.log(1.0 - (1.0 - np.finfo(np.float64).eps) * u[i]))
+        t2 = 2.0 * np.pi * u[i + 1]
+        exp += [t1 * np.cos(t2), t1 * np.sin(t2)]
+    assert g == approx(exp[:n], rel=1e-14)
+
+
+# ---------------------------------------------------------------------------------------------------
+# restatement vs the reference's own compiled kernels (oracle/_ref)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_port_matches_reference_spline_kernels(orc, orc_ref, dt):
+    from qmcpack_b200.workload import random_table
+    coefs = random_table((7, 5, 6), 19, dt, seed=3)
+    rng = np.random.default_rng(0)
+    for pos in rng.random((20, 3)):
+        for which in (0, 1, 2):
+            a = orc.spline_eval(coefs, 19, which, pos)
+            b = orc_ref.spline_eval(coefs, 19, which, pos)
+            for x, y in zip(a, b):
+                # same association order; only FMA contraction choices of the two compilations may differ
+                assert x[..., :19] == approx(y[..., :19], rel=5e-6 if dt == np.float32 else 1e-13,
+                                             abs=1e-4 if dt == np.float32 else 1e-11)
+
+
+def test_port_matches_reference_einspline_solver(orc, orc_ref):
+    data = np.random.default_rng(1).normal(size=(6, 5, 7))
+    assert orc.create_periodic_coefs(data) == approx(orc_ref.create_periodic_coefs(data), rel=1e-12, abs=1e-13)
+
+
+def test_port_matches_reference_inverse(orc, orc_ref):
+    a = np.random.default_rng(2).normal(size=(40, 40))
+    i1, l1 = orc.invert_transpose(a)
+    i2, l2 = orc_ref.invert_transpose(a)
+    assert i1 == approx(i2, rel=1e-9, abs=1e-11)
+    assert l1.real == approx(l2.real, rel=1e-12)
+    assert np.cos(l1.imag) == approx(np.cos(l2.imag), abs=1e-12)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("k", [1, 4, 8])
+def test_port_matches_reference_delayed_update(orc, orc_ref, dt, k):
+    """Same accept sequence through the restated engine and through qmcplusplus::DelayedUpdate<T>."""
+    rng = np.random.default_rng(11)
+    n = 16
+    psiM = rng.normal(size=(n, n)).astype(dt)
+    a1, _ = orc.invert_transpose(psiM)
+    a2 = a1.copy()
+    e1, e2 = orc.du(n, k, dt), orc_ref.du(n, k, dt)
+    tol = dict(rel=5e-3, abs=5e-3) if dt == np.float32 else dict(rel=1e-8, abs=1e-9)
+    for move in range(2 * n + 3):
+        r = move % n
+        new = rng.normal(size=n).astype(dt)
+        r1, r2 = e1.get_inv_row(a1, r), e2.get_inv_row(a2, r)
+        assert r1 == approx(r2, **tol)
+        ratio = float(r2 @ new)
+        if rng.random() < 0.7 and abs(ratio) > 0.2:  # keep the walk well conditioned: rounding is what differs
+            e1.accept_row(a1, r, new, ratio)
+            e2.accept_row(a2, r, new, ratio)
+    e1.update_inv_mat(a1)
+    e2.update_inv_mat(a2)
+    scale = float(np.abs(a2).max())
+    assert a1 == approx(a2, rel=tol["rel"], abs=tol["abs"] * max(1.0, scale))
