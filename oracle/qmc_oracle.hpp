@@ -29,6 +29,7 @@
 #include <complex>
 #include <cstdint>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 #include <random>
 #include <stdexcept>
@@ -45,6 +46,38 @@ inline size_t aligned_size(size_t n)
   constexpr size_t ND = 64 / sizeof(T);
   return ((n + ND - 1) / ND) * ND;
 }
+
+// 64-byte aligned std::vector (the reference kernels compiled into oracle/_ref use aligned SIMD access,
+// `#pragma omp simd aligned(...: QMC_SIMD_ALIGNMENT)`, so every buffer handed to them must be aligned)
+template<typename T>
+struct AlignedAlloc
+{
+  using value_type = T;
+  AlignedAlloc() = default;
+  template<class U>
+  AlignedAlloc(const AlignedAlloc<U>&)
+  {}
+  T* allocate(size_t n)
+  {
+    void* p = nullptr;
+    if (posix_memalign(&p, 64, std::max<size_t>(64, ((n * sizeof(T) + 63) / 64) * 64)))
+      throw std::bad_alloc();
+    return static_cast<T*>(p);
+  }
+  void deallocate(T* p, size_t) { free(p); }
+  template<class U>
+  bool operator==(const AlignedAlloc<U>&) const
+  {
+    return true;
+  }
+  template<class U>
+  bool operator!=(const AlignedAlloc<U>&) const
+  {
+    return false;
+  }
+};
+template<typename T>
+using avec = std::vector<T, AlignedAlloc<T>>;
 
 // -------------------------------------------------------------------------------------
 // ref: Numerics/SplineBound.hpp:37-62.  T is the type of the scaled coordinate (double for the
@@ -425,7 +458,7 @@ struct SplineR2R
   SplineTable<ST> tab;
   LatticeG lat;
   int norb = 0; // OrbitalSetSize (<= tab.ns)
-  std::vector<ST> myV, myG, myH;
+  avec<ST> myV, myG, myH;
 
   void init(const SplineTable<ST>& t, const LatticeG& l, int n)
   {
@@ -487,7 +520,7 @@ struct SplineC2C
   LatticeG lat;
   int norb = 0;
   std::vector<ST> kx, ky, kz, mKK;
-  std::vector<ST> myV, myG, myH;
+  avec<ST> myV, myG, myH;
 
   void init(const SplineTable<ST>& t, const LatticeG& l, int n, const double* kcart /*[n][3]*/)
   {

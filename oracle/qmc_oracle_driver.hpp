@@ -96,7 +96,7 @@ struct VMC
     typename J1::State j1;
     RT newpos[3];
     std::vector<RT> dist_new, dist_old; // [4][npad] AA temp rows
-    std::vector<ST> myV, myG, myH;
+    avec<ST> myV, myG, myH;
     std::vector<VT> phi_vgl;            // [5][n] of the proposed move
     double weight = 1.0;
     long n_accept = 0, n_reject = 0;
