@@ -1,0 +1,186 @@
+/* =====================================================================================================
+ * include/qmcb.h -- C ABI of libqmcb.so, the B200 (sm_100a) batched per-electron-move engine.
+ *
+ * Drop-in boundary for QMCPACK's batched drivers.  QMCPACK has no C ABI / plugin loader for this path: the
+ * path sits behind C++ virtual interfaces.  Each entry point below names the reference interface it replaces
+ * (paths relative to /root/reference/src); INTEGRATION.md shows the thin in-tree adapter classes
+ * (class SplineB200 : public BsplineSet, an UpdateEngine for DiracDeterminantBatched, a TwoBodyJastrow
+ * forwarding class) a maintainer would add to bind them.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; qmcb_last_error() (thread-local) gives the message.
+ *    The adapter turns non-zero into `throw std::runtime_error(qmcb_last_error())`, the reference's error
+ *    convention (DiracDeterminantBatched.cpp:443-448, DelayedUpdateBatched.h:164-168).
+ *  - plain pointers and sizes only.  `_host` arguments are host buffers (pinned or pageable), copied inside
+ *    the call; `_dev` arguments are device pointers that stay resident (the reference passes device pointers
+ *    for the inverse rows when SPOSet::isOMPoffload() is true, DiracDeterminantBatched.cpp:334-336).
+ *  - precision: QMCB_FULL = RealType/ValueType/spline all double; QMCB_MIXED = all float with the matrix
+ *    inversion and log-determinants in double (the reference's MIXED_PRECISION build).
+ *  - handles are thread-compatible; one qmcb_crowd (walker batch + stream) per host thread, like one Crowd /
+ *    MultiWalkerResource per OpenMP thread in the reference (VMCBatched.cpp:348,405; DelayedUpdateBatched.h:58-109).
+ *  - there is NO CPU fallback: every call fails with a clear error when no CUDA device is present.
+ * ===================================================================================================== */
+#ifndef QMCB_H
+#define QMCB_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QMCB_FULL 0
+#define QMCB_MIXED 1
+#define QMCB_R2R 0 /* SplineR2R: real table -> real orbitals      (BsplineFactory/SplineR2R.h:36)  */
+#define QMCB_C2C 1 /* SplineC2C: real pairs + twist -> complex    (BsplineFactory/SplineC2C.h:36)  */
+
+typedef struct qmcb_spline qmcb_spline; /* one SPOSet (read-only table, shared by clones like SplineR2R.h:82) */
+typedef struct qmcb_crowd qmcb_crowd;   /* nw walkers: positions, 2 determinants, J1/J2, scratch, one stream   */
+
+/* ---- library ------------------------------------------------------------------------------------ */
+int qmcb_init(int device);             /* cudaSetDevice + capability check (sm_100 required)            */
+const char* qmcb_last_error(void);
+int qmcb_device_count(void);           /* 0 when no usable CUDA device (never an error)                  */
+size_t qmcb_aligned_size(int precision, size_t n); /* getAlignedSize<T> (Platforms/CPU/SIMD/aligned_allocator.hpp:41) */
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches counter) */
+unsigned long long qmcb_kernel_launch_count(void);
+
+/* ---- SPOSet: tricubic B-spline orbitals ----------------------------------------------------------- *
+ * replaces BsplineSet / SplineR2R / SplineC2C(OMPTarget) evaluation entry points.                     */
+/* coefs_host: [grid[0]+3][grid[1]+3][grid[2]+3][npad] in ST (multi_UBspline_3d_{s,d} layout,
+ * spline2/MultiBsplineBase.hpp:75-128).  n_spl = real components (n_orb for R2R, 2*n_orb for C2C).
+ * G: prim_lattice.G row-major (ru = r . G).  halfG: SplineR2R bc_sign parities (NULL = Gamma).  kcart: [n_orb][3]
+ * Cartesian twist vectors for C2C (NULL for R2R).  finalizeConstruction() == this call (table pushed to HBM). */
+int qmcb_spline_create(qmcb_spline** h, int precision, int kind, const int grid[3], int n_orb, int n_spl, size_t npad,
+                       const void* coefs_host, const double G[9], const int halfG[3], const double* kcart);
+int qmcb_spline_destroy(qmcb_spline* h);
+size_t qmcb_spline_table_bytes(const qmcb_spline* h);
+/* SPOSet::mw_evaluateValue (SPOSet.h:300).  r_host [nw][3] Cartesian doubles; psi_host [nw][n_orb] VT (complex interleaved for C2C) */
+int qmcb_spline_mw_evaluate_value(qmcb_spline* h, int nw, const double* r_host, void* psi_host);
+/* SPOSet::mw_evaluateVGL (SPOSet.h:313).  dpsi_host [nw][n_orb][3], d2psi_host [nw][n_orb] */
+int qmcb_spline_mw_evaluate_vgl(qmcb_spline* h, int nw, const double* r_host, void* psi_host, void* dpsi_host,
+                                void* d2psi_host);
+/* SPOSet::mw_evaluateVGLandDetRatioGrads (SPOSet.h:346-352).  invrow_host [nw][ld_inv] VT.  Outputs:
+ * phi_vgl_host [5][nw][n_orb] (may be NULL), ratios_host [nw], grads_host [nw][3] (already divided by ratio). */
+int qmcb_spline_mw_evaluate_vgl_ratio_grads(qmcb_spline* h, int nw, const double* r_host, const void* invrow_host,
+                                            size_t ld_inv, void* phi_vgl_host, void* ratios_host, void* grads_host);
+/* SPOSet::mw_evaluateDetRatios (SPOSet.h:257): V-only evaluation at nvp virtual positions, each dotted with the
+ * inverse row of its reference walker: ratios[i] = sum_j invrow[ref_walker[i]][j] * psi_j(r_vp[i]). */
+int qmcb_spline_mw_evaluate_det_ratios(qmcb_spline* h, int nvp, const double* r_vp_host, const int* ref_walker_host,
+                                       int n_ref, const void* invrow_host, size_t ld_inv, void* ratios_host);
+/* device-resident variant used inside the sweep and by bench.py's kernel-only timing: positions and inverse rows
+ * already in HBM, nothing copied, nothing synchronised.  r_dev [nw][3] RT; invrow_dev [nw][ld_inv]; phi_vgl_dev
+ * [5][nw][n_orb]; ratio_grad_dev [nw][4] = ratio, grad*ratio (x,y,z) -- undivided, like the reference kernel's
+ * per-team partials (SplineR2R.cpp:566-581).  stream: a cudaStream_t cast to void* (NULL = default stream). */
+int qmcb_spline_mw_vgl_ratio_grads_dev(qmcb_spline* h, int nw, const void* r_dev, const void* invrow_dev, size_t ld_inv,
+                                       void* phi_vgl_dev, void* ratio_grad_dev, void* stream);
+
+/* ---- crowd: walker batch + trial wavefunction state ---------------------------------------------- */
+typedef struct qmcb_system
+{
+  int precision;      /* QMCB_FULL / QMCB_MIXED                                                    */
+  int n_up, n_dn;     /* electrons (= orbitals) per spin determinant                               */
+  double lattice[9];  /* rows = cell vectors (bohr), periodic in all directions                     */
+  qmcb_spline* spo[2];/* SPOSet of each spin determinant (may be the same handle)                   */
+  int delay_rank;     /* slaterdeterminant delay_rank (Fermion/SlaterDetBuilder.cpp:402-409)        */
+  /* two-body Jastrow, B-spline functors uu (= dd) and ud; n_j2 = 0 disables (Jastrow/TwoBodyJastrow.h:57) */
+  int n_j2;
+  const double* j2_uu;
+  const double* j2_ud;
+  double j2_rcut;
+  /* one-body Jastrow (Jastrow/J1OrbitalSoA.h); nions = 0 disables */
+  int nions;
+  const double* ion_pos; /* [nions][3] */
+  const int* ion_grp;    /* [nions]    */
+  int n_ion_groups;
+  int n_j1;
+  const double* j1_params; /* [n_ion_groups][n_j1] */
+  const double* j1_rcut;   /* [n_ion_groups]       */
+} qmcb_system;
+
+int qmcb_crowd_create(qmcb_crowd** c, const qmcb_system* sys, int nw);
+int qmcb_crowd_destroy(qmcb_crowd* c);
+int qmcb_crowd_sync(qmcb_crowd* c);
+size_t qmcb_crowd_device_bytes(const qmcb_crowd* c);
+/* ParticleSet::R for every walker, [nw][N][3] doubles (loadWalker) */
+int qmcb_crowd_set_positions(qmcb_crowd* c, const double* R_host);
+int qmcb_crowd_get_positions(qmcb_crowd* c, double* R_host);
+
+/* WaveFunctionComponent::mw_recompute / DiracDeterminantBatched::mw_recompute (DiracDeterminantBatched.cpp:1122-1198)
+ * + TwoBodyJastrow::mw_recompute + J1: from-scratch psiM, FP64 inverse + log-determinant, Jastrow sums.          */
+int qmcb_twf_mw_recompute(qmcb_crowd* c);
+/* TrialWaveFunction::mw_evalGrad (TrialWaveFunction.cpp:568): grads_host [nw][3] doubles = sum over components.  */
+int qmcb_twf_mw_eval_grad(qmcb_crowd* c, int iat, double* grads_host);
+/* ParticleSet::mw_makeMove (Particle/ParticleSet.cpp:397): proposes R[iat] + displ for every walker and launches the
+ * distance-table rows (SoaDistanceTableAAOMPTarget::mw_move :265-371); asynchronous.  displ_host [nw][3] doubles.  */
+int qmcb_ps_mw_make_move(qmcb_crowd* c, int iat, const double* displ_host);
+/* TrialWaveFunction::mw_calcRatioGrad (:685): ratios_host [nw] (PsiValue, double), grads_host [nw][3] doubles.    */
+int qmcb_twf_mw_calc_ratio_grad(qmcb_crowd* c, int iat, double* ratios_host, double* grads_host);
+/* TrialWaveFunction::mw_accept_rejectMove (:790) followed by ParticleSet::mw_accept_rejectMove (ParticleSet.cpp:717).
+ * accepted_host [nw] (0/1).  safe_to_delay = 0 forces the Woodbury flush at once (DiracDeterminantBatched.cpp:519).   */
+int qmcb_twf_mw_accept_reject(qmcb_crowd* c, int iat, const uint8_t* accepted_host, int safe_to_delay);
+/* TrialWaveFunction::mw_completeUpdates (:833): flush pending delayed updates of both determinants.               */
+int qmcb_twf_mw_complete_updates(qmcb_crowd* c);
+/* TrialWaveFunction::mw_evaluateGL (:869), fromscratch = false: G_host [nw][N][3], L_host [nw][N] (either may be
+ * NULL), logpsi_host [nw] (real part of log psi), ke_host [nw] = -1/2 sum(L + G.G) (BareKineticEnergy).            */
+int qmcb_twf_mw_evaluate_gl(qmcb_crowd* c, double* G_host, double* L_host, double* logpsi_host, double* ke_host);
+
+/* ---- component level: DiracDeterminantBatched + DelayedUpdateBatched engine ----------------------- *
+ * `spin` selects the determinant; `row` = iat - FirstIndex.                                           */
+/* DelayedUpdateBatched::mw_evalGrad (Fermion/DelayedUpdateBatched.h:354-400): prepares the inverse rows
+ * (mw_prepareInvRow :174-235) and returns grad_now = invRow . dpsiM[row]; grads_host [nw][3] VT.        */
+int qmcb_det_mw_eval_grad(qmcb_crowd* c, int spin, int row, void* grads_host);
+/* DelayedUpdateBatched::mw_getInvRow (:763-810): device pointer to the contiguous [nw][ld] current inverse rows
+ * (prepared if needed); *ld receives the row stride.  invrow_host, if not NULL, receives a copy [nw][n].        */
+int qmcb_det_mw_get_inv_row(qmcb_crowd* c, int spin, int row, const void** invrow_dev, size_t* ld, void* invrow_host);
+/* DiracDeterminantBatched::mw_ratioGrad (DiracDeterminantBatched.cpp:308-354): spline VGL at the proposed positions
+ * (set by qmcb_ps_mw_make_move) + ratio/grad against the current inverse rows.  ratios_host [nw] VT, grads_host [nw][3] VT */
+int qmcb_det_mw_ratio_grad(qmcb_crowd* c, int spin, int row, void* ratios_host, void* grads_host);
+/* DelayedUpdateBatched::mw_accept_rejectRow (:542-670) incl. pseudo-accept of rejected walkers and the flush when
+ * delay_count reaches delay_rank (mw_updateInvMat :675-738).                                                        */
+int qmcb_det_mw_accept_reject(qmcb_crowd* c, int spin, int row, const uint8_t* accepted_host);
+/* DelayedUpdateBatched::mw_updateInvMat + mw_transferAinv_D2H: flush, then copy psiMinv [nw][n][n] VT (padding
+ * stripped) and log-determinants [nw][2] (re, im) to the host; either output may be NULL.                            */
+int qmcb_det_mw_complete_updates(qmcb_crowd* c, int spin, void* psiMinv_host, double* logdet_host);
+/* test hook mirroring the unit tests with FakeSPO (test_DiracDeterminantBatched.cpp:262-470): load psiM/dpsiM/d2psiM
+ * directly ([nw][n][n], [nw][n][n][3], [nw][n][n] VT) and invert.                                                      */
+int qmcb_det_mw_recompute_from_matrices(qmcb_crowd* c, int spin, const void* psiM_host, const void* dpsiM_host,
+                                        const void* d2psiM_host);
+/* load externally computed orbital VGL of the proposed move ([5][nw][n] VT) in place of the spline evaluation
+ * (FakeSPO-style determinant tests).                                                                                 */
+int qmcb_det_set_phi_vgl(qmcb_crowd* c, int spin, const void* phi_vgl_host);
+int qmcb_det_mw_ratio_grad_from_phi(qmcb_crowd* c, int spin, int row, void* ratios_host, void* grads_host);
+int qmcb_det_delay_count(qmcb_crowd* c, int spin);
+
+/* ---- component level: distance rows + two-body Jastrow -------------------------------------------- */
+/* SoaDistanceTableAAOMPTarget::mw_move temp/old rows after qmcb_ps_mw_make_move: [2][nw][4][N] RT (r,dx,dy,dz; new then old) */
+int qmcb_dtaa_get_temp_rows(qmcb_crowd* c, void* rows_host);
+/* TwoBodyJastrow::mw_ratioGrad (Jastrow/TwoBodyJastrow.cpp:542-578): ratios_host [nw] doubles, grads_host [nw][3] RT */
+int qmcb_j2_mw_ratio_grad(qmcb_crowd* c, int iat, double* ratios_host, void* grads_host);
+/* TwoBodyJastrow::mw_accept_rejectMove (:631-664) */
+int qmcb_j2_mw_accept_reject(qmcb_crowd* c, int iat, const uint8_t* accepted_host);
+/* per-particle sums of walker iw: Uat [N], dUat [3][N], d2Uat [N] as doubles */
+int qmcb_j2_get_state(qmcb_crowd* c, int iw, double* Uat, double* dUat, double* d2Uat);
+
+/* ---- device-resident driver: VMCBatched::advanceWalkers p-by-p loop (VMC/VMCBatched.cpp:106-176) --- *
+ * One call = `nsteps` sweeps of all N electrons of all walkers with the accept/reject test done on the device from
+ * a std::mt19937 stream (Utilities/StdRandom.h:34-48) and Box-Muller Gaussians (RandomSeqGenerator.h:33-52); no
+ * host round trip inside the sweep.  accept_log_host (optional) [nsteps][N][nw].                                      */
+typedef struct qmcb_vmc_params
+{
+  double tau;
+  int use_drift;
+  uint32_t seed;      /* the crowd's std::mt19937 seed */
+  int use_cuda_graph; /* capture one sweep into a CUDA graph and replay it */
+} qmcb_vmc_params;
+int qmcb_vmc_init(qmcb_crowd* c, const qmcb_vmc_params* p);
+int qmcb_vmc_sweep(qmcb_crowd* c, int nsteps, uint8_t* accept_log_host);
+/* asynchronous launch of one sweep on the crowd's stream (bench.py brackets it with CUDA events) */
+int qmcb_vmc_sweep_async(qmcb_crowd* c);
+int qmcb_vmc_counts(qmcb_crowd* c, long long* n_accept, long long* n_reject);
+/* the crowd's cudaStream_t as void* so callers can record events on the launching stream */
+void* qmcb_crowd_stream(qmcb_crowd* c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMCB_H */

@@ -343,6 +343,19 @@ void orc_rng_gauss_f(uint32_t seed, int n, float* out)
   assignGaussRand(out, (unsigned)n, r);
 }
 
+// stateful generator (one per crowd, like ContextForSteps::get_random_gen())
+void* orc_rng_create(uint32_t seed) { return new StdRandom(seed); }
+void orc_rng_destroy(void* h) { delete static_cast<StdRandom*>(h); }
+double orc_rng_next(void* h) { return (*static_cast<StdRandom*>(h))(); }
+void orc_rng_next_n(void* h, int n, double* out)
+{
+  auto& r = *static_cast<StdRandom*>(h);
+  for (int i = 0; i < n; ++i)
+    out[i] = r();
+}
+void orc_rng_gauss_next_d(void* h, int n, double* out) { assignGaussRand(out, (unsigned)n, *static_cast<StdRandom*>(h)); }
+void orc_rng_gauss_next_f(void* h, int n, float* out) { assignGaussRand(out, (unsigned)n, *static_cast<StdRandom*>(h)); }
+
 // ---------------------------------------------------------------- VMC harness
 struct VMCHandle
 {

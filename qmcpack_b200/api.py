@@ -1,0 +1,382 @@
+"""ctypes binding of libqmcb.so (include/qmcb.h) with numpy-facing classes whose method names mirror the reference
+interfaces they stand in for:
+
+  SplineSPOSet        SPOSet / BsplineSet / SplineR2R / SplineC2C      mw_evaluateValue, mw_evaluateVGL,
+                                                                       mw_evaluateVGLandDetRatioGrads, mw_evaluateDetRatios
+  Crowd               Crowd + TrialWaveFunction + ParticleSet batch    mw_recompute, mw_evalGrad, mw_makeMove,
+                                                                       mw_calcRatioGrad, mw_accept_rejectMove, ...
+  Crowd.det_*         DiracDeterminantBatched / DelayedUpdateBatched   mw_evalGrad, mw_getInvRow, mw_ratioGrad,
+                                                                       mw_accept_rejectRow, mw_updateInvMat
+  Crowd.j2_*          TwoBodyJastrow                                   mw_ratioGrad, mw_accept_rejectMove
+
+This is the thin test/bench-facing layer; the product is the C ABI.  The library is REQUIRED: importing works without
+it (so CPU-only tooling can inspect the package) but every call raises if libqmcb.so or a CUDA device is missing --
+there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libqmcb.so")
+FULL, MIXED = 0, 1
+R2R, C2C = 0, 1
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_u8p = C.POINTER(C.c_uint8)
+vp = C.c_void_p
+
+
+class QmcbSystem(C.Structure):
+    _fields_ = [
+        ("precision", C.c_int), ("n_up", C.c_int), ("n_dn", C.c_int),
+        ("lattice", C.c_double * 9),
+        ("spo", vp * 2), ("delay_rank", C.c_int),
+        ("n_j2", C.c_int), ("j2_uu", c_dp), ("j2_ud", c_dp), ("j2_rcut", C.c_double),
+        ("nions", C.c_int), ("ion_pos", c_dp), ("ion_grp", c_ip), ("n_ion_groups", C.c_int),
+        ("n_j1", C.c_int), ("j1_params", c_dp), ("j1_rcut", c_dp),
+    ]
+
+
+class QmcbVmcParams(C.Structure):
+    _fields_ = [("tau", C.c_double), ("use_drift", C.c_int), ("seed", C.c_uint32), ("use_cuda_graph", C.c_int)]
+
+
+_lib = None
+
+# every symbol include/qmcb.h declares (checked by tests/test_abi.py against the header text)
+SYMBOLS = [
+    "qmcb_init", "qmcb_last_error", "qmcb_device_count", "qmcb_aligned_size", "qmcb_kernel_launch_count",
+    "qmcb_spline_create", "qmcb_spline_destroy", "qmcb_spline_table_bytes", "qmcb_spline_mw_evaluate_value",
+    "qmcb_spline_mw_evaluate_vgl", "qmcb_spline_mw_evaluate_vgl_ratio_grads", "qmcb_spline_mw_evaluate_det_ratios",
+    "qmcb_spline_mw_vgl_ratio_grads_dev",
+    "qmcb_crowd_create", "qmcb_crowd_destroy", "qmcb_crowd_sync", "qmcb_crowd_device_bytes",
+    "qmcb_crowd_set_positions", "qmcb_crowd_get_positions",
+    "qmcb_twf_mw_recompute", "qmcb_twf_mw_eval_grad", "qmcb_ps_mw_make_move", "qmcb_twf_mw_calc_ratio_grad",
+    "qmcb_twf_mw_accept_reject", "qmcb_twf_mw_complete_updates", "qmcb_twf_mw_evaluate_gl",
+    "qmcb_det_mw_eval_grad", "qmcb_det_mw_get_inv_row", "qmcb_det_mw_ratio_grad", "qmcb_det_mw_accept_reject",
+    "qmcb_det_mw_complete_updates", "qmcb_det_mw_recompute_from_matrices", "qmcb_det_set_phi_vgl",
+    "qmcb_det_mw_ratio_grad_from_phi", "qmcb_det_delay_count",
+    "qmcb_dtaa_get_temp_rows", "qmcb_j2_mw_ratio_grad", "qmcb_j2_mw_accept_reject", "qmcb_j2_get_state",
+    "qmcb_vmc_init", "qmcb_vmc_sweep", "qmcb_vmc_sweep_async", "qmcb_vmc_counts", "qmcb_crowd_stream",
+]
+
+
+def lib():
+    """Loads libqmcb.so; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m qmcpack_b200.build` "
+                               "(nvcc, sm_100a).  There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.qmcb_last_error.restype = C.c_char_p
+        L.qmcb_aligned_size.restype = C.c_size_t
+        L.qmcb_aligned_size.argtypes = [C.c_int, C.c_size_t]
+        L.qmcb_kernel_launch_count.restype = C.c_ulonglong
+        L.qmcb_spline_table_bytes.restype = C.c_size_t
+        L.qmcb_spline_table_bytes.argtypes = [vp]
+        L.qmcb_crowd_device_bytes.restype = C.c_size_t
+        L.qmcb_crowd_device_bytes.argtypes = [vp]
+        L.qmcb_crowd_stream.restype = vp
+        L.qmcb_crowd_stream.argtypes = [vp]
+        L.qmcb_spline_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, c_ip, C.c_int, C.c_int, C.c_size_t, vp, c_dp,
+                                         c_ip, c_dp]
+        L.qmcb_spline_mw_evaluate_vgl_ratio_grads.argtypes = [vp, C.c_int, vp, vp, C.c_size_t, vp, vp, vp]
+        L.qmcb_spline_mw_evaluate_det_ratios.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_size_t, vp]
+        L.qmcb_spline_mw_vgl_ratio_grads_dev.argtypes = [vp, C.c_int, vp, vp, C.c_size_t, vp, vp, vp]
+        L.qmcb_crowd_create.argtypes = [C.POINTER(vp), C.POINTER(QmcbSystem), C.c_int]
+        L.qmcb_det_mw_get_inv_row.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), vp]
+        _lib = L
+    return _lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise RuntimeError(lib().qmcb_last_error().decode())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+def device_count():
+    return int(lib().qmcb_device_count())
+
+
+def init(device=0):
+    _chk(lib().qmcb_init(C.c_int(device)))
+
+
+def kernel_launch_count():
+    return int(lib().qmcb_kernel_launch_count())
+
+
+def _vt(precision, kind=R2R):
+    if kind == C2C:
+        return np.complex64 if precision == MIXED else np.complex128
+    return np.float32 if precision == MIXED else np.float64
+
+
+class SplineSPOSet:
+    """Tricubic B-spline orbital set resident in HBM (reference: BsplineSet / SplineR2R / SplineC2C)."""
+
+    def __init__(self, coefs, n_orb, G, kind=R2R, halfG=None, kcart=None):
+        coefs = np.ascontiguousarray(coefs)
+        assert coefs.dtype in (np.float32, np.float64) and coefs.ndim == 4
+        self.precision = MIXED if coefs.dtype == np.float32 else FULL
+        self.kind = kind
+        self.n_orb = int(n_orb)
+        self.n_spl = (2 if kind == C2C else 1) * self.n_orb
+        self.vt = _vt(self.precision, kind)
+        self.st = coefs.dtype
+        grid = np.array([s - 3 for s in coefs.shape[:3]], np.int32)
+        Gd = np.ascontiguousarray(G, np.float64).reshape(9)
+        hg = None if halfG is None else np.ascontiguousarray(halfG, np.int32)
+        kc = None if kcart is None else np.ascontiguousarray(kcart, np.float64)
+        self.h = vp()
+        _chk(lib().qmcb_spline_create(C.byref(self.h), self.precision, kind, grid.ctypes.data_as(c_ip), self.n_orb,
+                                      self.n_spl, coefs.shape[3], _p(coefs), Gd.ctypes.data_as(c_dp),
+                                      None if hg is None else hg.ctypes.data_as(c_ip),
+                                      None if kc is None else kc.ctypes.data_as(c_dp)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().qmcb_spline_destroy(self.h)
+        except Exception:
+            pass
+
+    @property
+    def table_bytes(self):
+        return int(lib().qmcb_spline_table_bytes(self.h))
+
+    def mw_evaluateValue(self, r):
+        r = np.ascontiguousarray(r, np.float64)
+        psi = np.zeros((r.shape[0], self.n_orb), self.vt)
+        _chk(lib().qmcb_spline_mw_evaluate_value(self.h, C.c_int(r.shape[0]), _p(r), _p(psi)))
+        return psi
+
+    def mw_evaluateVGL(self, r):
+        r = np.ascontiguousarray(r, np.float64)
+        nw = r.shape[0]
+        psi = np.zeros((nw, self.n_orb), self.vt)
+        dpsi = np.zeros((nw, self.n_orb, 3), self.vt)
+        d2psi = np.zeros((nw, self.n_orb), self.vt)
+        _chk(lib().qmcb_spline_mw_evaluate_vgl(self.h, C.c_int(nw), _p(r), _p(psi), _p(dpsi), _p(d2psi)))
+        return psi, dpsi, d2psi
+
+    def mw_evaluateVGLandDetRatioGrads(self, r, invrow):
+        r = np.ascontiguousarray(r, np.float64)
+        nw = r.shape[0]
+        invrow = np.ascontiguousarray(invrow, self.vt)
+        phi = np.zeros((5, nw, self.n_orb), self.vt)
+        ratios = np.zeros(nw, self.vt)
+        grads = np.zeros((nw, 3), self.vt)
+        _chk(lib().qmcb_spline_mw_evaluate_vgl_ratio_grads(self.h, nw, _p(r), _p(invrow), invrow.shape[1], _p(phi),
+                                                           _p(ratios), _p(grads)))
+        return phi, ratios, grads
+
+    def mw_evaluateDetRatios(self, r_vp, ref_walker, invrow):
+        r_vp = np.ascontiguousarray(r_vp, np.float64)
+        ref = np.ascontiguousarray(ref_walker, np.int32)
+        invrow = np.ascontiguousarray(invrow, self.vt)
+        ratios = np.zeros(r_vp.shape[0], self.vt)
+        _chk(lib().qmcb_spline_mw_evaluate_det_ratios(self.h, r_vp.shape[0], _p(r_vp), _p(ref), invrow.shape[0],
+                                                      _p(invrow), invrow.shape[1], _p(ratios)))
+        return ratios
+
+
+class Crowd:
+    """nw walkers with their trial-wavefunction state on the device; one CUDA stream (reference: Crowd + the
+    multi-walker resources of TrialWaveFunction / DiracDeterminantBatched / TwoBodyJastrow / ParticleSet)."""
+
+    def __init__(self, system, nw, delay_rank=32, spo=None):
+        s = system
+        c0 = s["coefs"][0]
+        self.precision = MIXED if c0.dtype == np.float32 else FULL
+        self.T = np.float32 if self.precision == MIXED else np.float64
+        self.n_up, self.n_dn = int(s["n_up"]), int(s["n_dn"])
+        self.N = self.n_up + self.n_dn
+        self.nw = int(nw)
+        self.k = int(delay_rank)
+        lat = np.ascontiguousarray(s["lattice"], np.float64).reshape(3, 3)
+        G = np.linalg.inv(lat)  # CrystalLattice: G = inverse(R), ru = r . G
+        if spo is None:
+            up = SplineSPOSet(s["coefs"][0], self.n_up, G)
+            dn = up if s["coefs"][1] is s["coefs"][0] and self.n_dn == self.n_up else SplineSPOSet(s["coefs"][1], self.n_dn, G)
+            spo = (up, dn)
+        self.spo = spo
+        q = QmcbSystem()
+        q.precision, q.n_up, q.n_dn = self.precision, self.n_up, self.n_dn
+        q.lattice[:] = list(lat.ravel())
+        q.spo[0], q.spo[1] = spo[0].h.value, spo[1].h.value
+        q.delay_rank = self.k
+        self._keep = []
+        j2 = s.get("j2")
+        if j2:
+            uu, ud = np.ascontiguousarray(j2["uu"], np.float64), np.ascontiguousarray(j2["ud"], np.float64)
+            self._keep += [uu, ud]
+            q.n_j2, q.j2_uu, q.j2_ud, q.j2_rcut = len(uu), uu.ctypes.data_as(c_dp), ud.ctypes.data_as(c_dp), j2["rcut"]
+        j1 = s.get("j1")
+        if j1:
+            ip = np.ascontiguousarray(j1["ion_pos"], np.float64)
+            ig = np.ascontiguousarray(j1["ion_grp"], np.int32)
+            prm = np.ascontiguousarray(j1["params"], np.float64)
+            rc = np.ascontiguousarray(j1["rcut"], np.float64)
+            self._keep += [ip, ig, prm, rc]
+            q.nions, q.ion_pos, q.ion_grp = len(ig), ip.ctypes.data_as(c_dp), ig.ctypes.data_as(c_ip)
+            q.n_ion_groups, q.n_j1 = prm.shape[0], prm.shape[1]
+            q.j1_params, q.j1_rcut = prm.ctypes.data_as(c_dp), rc.ctypes.data_as(c_dp)
+        self.h = vp()
+        _chk(lib().qmcb_crowd_create(C.byref(self.h), C.byref(q), self.nw))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().qmcb_crowd_destroy(self.h)
+        except Exception:
+            pass
+
+    def n_of(self, spin):
+        return self.n_up if spin == 0 else self.n_dn
+
+    @property
+    def device_bytes(self):
+        return int(lib().qmcb_crowd_device_bytes(self.h))
+
+    @property
+    def stream(self):
+        return lib().qmcb_crowd_stream(self.h)
+
+    def sync(self):
+        _chk(lib().qmcb_crowd_sync(self.h))
+
+    # ---- ParticleSet
+    def set_positions(self, R):
+        R = np.ascontiguousarray(R, np.float64)
+        assert R.shape == (self.nw, self.N, 3)
+        _chk(lib().qmcb_crowd_set_positions(self.h, _p(R)))
+
+    def positions(self):
+        R = np.zeros((self.nw, self.N, 3))
+        _chk(lib().qmcb_crowd_get_positions(self.h, _p(R)))
+        return R
+
+    def mw_makeMove(self, iat, displ):
+        d = np.ascontiguousarray(displ, np.float64)
+        assert d.shape == (self.nw, 3)
+        _chk(lib().qmcb_ps_mw_make_move(self.h, C.c_int(iat), _p(d)))
+
+    # ---- TrialWaveFunction
+    def mw_recompute(self):
+        _chk(lib().qmcb_twf_mw_recompute(self.h))
+
+    def mw_evalGrad(self, iat):
+        g = np.zeros((self.nw, 3))
+        _chk(lib().qmcb_twf_mw_eval_grad(self.h, C.c_int(iat), _p(g)))
+        return g
+
+    def mw_calcRatioGrad(self, iat):
+        r, g = np.zeros(self.nw), np.zeros((self.nw, 3))
+        _chk(lib().qmcb_twf_mw_calc_ratio_grad(self.h, C.c_int(iat), _p(r), _p(g)))
+        return r, g
+
+    def mw_accept_rejectMove(self, iat, accepted, safe_to_delay=True):
+        a = np.ascontiguousarray(accepted, np.uint8)
+        assert a.shape == (self.nw,)
+        _chk(lib().qmcb_twf_mw_accept_reject(self.h, C.c_int(iat), _p(a), C.c_int(1 if safe_to_delay else 0)))
+
+    def mw_completeUpdates(self):
+        _chk(lib().qmcb_twf_mw_complete_updates(self.h))
+
+    def mw_evaluateGL(self):
+        G, L = np.zeros((self.nw, self.N, 3)), np.zeros((self.nw, self.N))
+        lp, ke = np.zeros(self.nw), np.zeros(self.nw)
+        _chk(lib().qmcb_twf_mw_evaluate_gl(self.h, _p(G), _p(L), _p(lp), _p(ke)))
+        return lp, ke, G, L
+
+    # ---- DiracDeterminantBatched / DelayedUpdateBatched
+    def det_mw_evalGrad(self, spin, row):
+        g = np.zeros((self.nw, 3), self.T)
+        _chk(lib().qmcb_det_mw_eval_grad(self.h, C.c_int(spin), C.c_int(row), _p(g)))
+        return g
+
+    def det_mw_getInvRow(self, spin, row):
+        out = np.zeros((self.nw, self.n_of(spin)), self.T)
+        dev, ld = vp(), C.c_size_t()
+        _chk(lib().qmcb_det_mw_get_inv_row(self.h, spin, row, C.byref(dev), C.byref(ld), _p(out)))
+        return out
+
+    def det_mw_ratioGrad(self, spin, row, from_phi=False):
+        r, g = np.zeros(self.nw, self.T), np.zeros((self.nw, 3), self.T)
+        f = lib().qmcb_det_mw_ratio_grad_from_phi if from_phi else lib().qmcb_det_mw_ratio_grad
+        _chk(f(self.h, C.c_int(spin), C.c_int(row), _p(r), _p(g)))
+        return r, g
+
+    def det_mw_accept_rejectRow(self, spin, row, accepted):
+        a = np.ascontiguousarray(accepted, np.uint8)
+        _chk(lib().qmcb_det_mw_accept_reject(self.h, C.c_int(spin), C.c_int(row), _p(a)))
+
+    def det_mw_completeUpdates(self, spin):
+        n = self.n_of(spin)
+        inv = np.zeros((self.nw, n, n), self.T)
+        ld = np.zeros((self.nw, 2))
+        _chk(lib().qmcb_det_mw_complete_updates(self.h, C.c_int(spin), _p(inv), _p(ld)))
+        return inv, ld
+
+    def det_recompute_from_matrices(self, spin, psiM, dpsiM=None, d2psiM=None):
+        n = self.n_of(spin)
+        psiM = np.ascontiguousarray(psiM, self.T)
+        assert psiM.shape == (self.nw, n, n)
+        dp = None if dpsiM is None else np.ascontiguousarray(dpsiM, self.T)
+        d2 = None if d2psiM is None else np.ascontiguousarray(d2psiM, self.T)
+        _chk(lib().qmcb_det_mw_recompute_from_matrices(self.h, C.c_int(spin), _p(psiM), _p(dp), _p(d2)))
+
+    def det_set_phi_vgl(self, spin, phi):
+        phi = np.ascontiguousarray(phi, self.T)
+        assert phi.shape == (5, self.nw, self.n_of(spin))
+        _chk(lib().qmcb_det_set_phi_vgl(self.h, C.c_int(spin), _p(phi)))
+
+    def det_delay_count(self, spin):
+        return int(lib().qmcb_det_delay_count(self.h, C.c_int(spin)))
+
+    # ---- distance rows / TwoBodyJastrow
+    def dtaa_temp_rows(self):
+        rows = np.zeros((2, self.nw, 4, self.N), self.T)
+        _chk(lib().qmcb_dtaa_get_temp_rows(self.h, _p(rows)))
+        return rows
+
+    def j2_mw_ratioGrad(self, iat):
+        r, g = np.zeros(self.nw), np.zeros((self.nw, 3), self.T)
+        _chk(lib().qmcb_j2_mw_ratio_grad(self.h, C.c_int(iat), _p(r), _p(g)))
+        return r, g
+
+    def j2_mw_accept_rejectMove(self, iat, accepted):
+        a = np.ascontiguousarray(accepted, np.uint8)
+        _chk(lib().qmcb_j2_mw_accept_reject(self.h, C.c_int(iat), _p(a)))
+
+    def j2_state(self, iw):
+        U, dU, d2U = np.zeros(self.N), np.zeros((3, self.N)), np.zeros(self.N)
+        _chk(lib().qmcb_j2_get_state(self.h, C.c_int(iw), _p(U), _p(dU), _p(d2U)))
+        return U, dU, d2U
+
+    # ---- device-resident VMC driver
+    def vmc_init(self, tau=0.3, use_drift=True, seed=1000, use_cuda_graph=True):
+        p = QmcbVmcParams(tau, int(use_drift), seed, int(use_cuda_graph))
+        _chk(lib().qmcb_vmc_init(self.h, C.byref(p)))
+
+    def vmc_sweep(self, nsteps=1, log_accept=False):
+        log = np.zeros((nsteps, self.N, self.nw), np.uint8) if log_accept else None
+        _chk(lib().qmcb_vmc_sweep(self.h, C.c_int(nsteps), _p(log)))
+        return log
+
+    def vmc_sweep_async(self):
+        _chk(lib().qmcb_vmc_sweep_async(self.h))
+
+    def vmc_counts(self):
+        a, r = np.zeros(self.nw, np.int64), np.zeros(self.nw, np.int64)
+        _chk(lib().qmcb_vmc_counts(self.h, _p(a), _p(r)))
+        return a, r

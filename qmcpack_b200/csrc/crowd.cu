@@ -1,0 +1,1118 @@
+// qmcpack_b200/csrc/crowd.cu -- the walker batch ("crowd"): per-walker wavefunction state in HBM and the multi-walker
+// operations of the reference's TrialWaveFunction / DiracDeterminantBatched / TwoBodyJastrow / ParticleSet on it.
+#include "internal.h"
+#include "spline.cuh"
+#include "det.cuh"
+#include "jastrow.cuh"
+#include "driver.cuh"
+#include <cublas_v2.h>
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+
+namespace qmcb
+{
+#define QMCB_CUBLAS(call)                                                                      \
+  do                                                                                           \
+  {                                                                                            \
+    cublasStatus_t s__ = (call);                                                               \
+    if (s__ != CUBLAS_STATUS_SUCCESS)                                                          \
+      throw std::runtime_error(std::string(#call) + " failed with cuBLAS status " + std::to_string((int)s__)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// small glue kernels of the trial wavefunction (component sums)
+// ------------------------------------------------------------------------------------------------------------
+// TrialWaveFunction::mw_evalGrad: grads_now = det + J2 dUat[iat] + J1 Grad[iat]  (component order det, J2, J1)
+template<typename T>
+__global__ void twf_grad_kernel(const JastrowDev<T> J, const int iat, const T* det_grads, T* grads_now)
+{
+  const int iw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iw >= J.nw)
+    return;
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+  {
+    T g = det_grads ? det_grads[3 * iw + d] : T(0);
+    if (J.has_j2)
+      g += J.dUat[((size_t)iw * 3 + d) * J.npad + iat];
+    if (J.has_j1)
+      g += J.Grad1[((size_t)iw * 3 + d) * J.N + iat];
+    grads_now[3 * iw + d] = g;
+  }
+}
+
+// ParticleSet::mw_makeMove: newpos = R[iat] + displ
+template<typename T>
+__global__ void make_move_kernel(const JastrowDev<T> J, const int iat, const T* displ)
+{
+  const int iw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iw >= J.nw)
+    return;
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    J.newpos[3 * iw + d] = J.rsoa[((size_t)iw * 3 + d) * J.npad + iat] + displ[3 * iw + d];
+}
+
+// device driver: drift + delta -> proposed position
+template<typename T>
+__global__ void propose_kernel(const DriverDev<T> Dr, const JastrowDev<T> J, const int iat, const T* det_grads)
+{
+  const int iw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iw >= J.nw)
+    return;
+  T delta[3], disp[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    delta[d] = Dr.deltas[((size_t)iat * Dr.nw + iw) * 3 + d] * Dr.sqrttau;
+  if (Dr.use_drift)
+  {
+    T g[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+      T v = det_grads[3 * iw + d];
+      if (J.has_j2)
+        v += J.dUat[((size_t)iw * 3 + d) * J.npad + iat];
+      if (J.has_j1)
+        v += J.Grad1[((size_t)iw * 3 + d) * J.N + iat];
+      g[d] = v;
+    }
+    get_drift<T>(Dr.tauovermass, g, disp);
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      disp[d] += delta[d];
+  }
+  else
+  {
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      disp[d] = delta[d];
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+  {
+    Dr.drifts[3 * iw + d]    = disp[d];
+    Dr.delta_cur[3 * iw + d] = delta[d];
+    J.newpos[3 * iw + d]     = J.rsoa[((size_t)iw * 3 + d) * J.npad + iat] + disp[d];
+  }
+}
+
+// TrialWaveFunction::mw_calcRatioGrad combination for one walker
+template<typename T>
+__device__ __forceinline__ double twf_ratio_grad(const JastrowDev<T>& J, int iw, int iat, const T* rg, T gn[3])
+{
+  const T rdet  = rg[4 * (size_t)iw];
+  double ratio  = (double)rdet;
+  gn[0]         = rg[4 * (size_t)iw + 1] / rdet;
+  gn[1]         = rg[4 * (size_t)iw + 2] / rdet;
+  gn[2]         = rg[4 * (size_t)iw + 3] / rdet;
+  if (J.has_j2)
+  {
+    const T* vgl = J.j2_vgl + (size_t)iw * 5;
+    ratio *= exp((double)(J.Uat[(size_t)iw * J.npad + iat] - vgl[0]));
+    gn[0] += vgl[1];
+    gn[1] += vgl[2];
+    gn[2] += vgl[3];
+  }
+  if (J.has_j1)
+  {
+    const T* cur = J.j1_cur + (size_t)iw * 5;
+    ratio *= exp((double)(J.Vat[(size_t)iw * J.N + iat] - cur[0]));
+    gn[0] += cur[1];
+    gn[1] += cur[2];
+    gn[2] += cur[3];
+  }
+  return ratio;
+}
+
+template<typename T>
+__global__ void twf_ratio_kernel(const JastrowDev<T> J, const int iat, const T* rg, double* ratios, T* grads)
+{
+  const int iw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iw >= J.nw)
+    return;
+  T gn[3];
+  ratios[iw]       = twf_ratio_grad(J, iw, iat, rg, gn);
+  grads[3 * iw]     = gn[0];
+  grads[3 * iw + 1] = gn[1];
+  grads[3 * iw + 2] = gn[2];
+}
+
+// J2-only ratio/grad for the component-level API
+template<typename T>
+__global__ void j2_ratio_kernel(const JastrowDev<T> J, const int iat, double* ratios, T* grads)
+{
+  const int iw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iw >= J.nw)
+    return;
+  const T* vgl = J.j2_vgl + (size_t)iw * 5;
+  ratios[iw]   = exp((double)(J.Uat[(size_t)iw * J.npad + iat] - vgl[0]));
+  grads[3 * iw]     = vgl[1];
+  grads[3 * iw + 1] = vgl[2];
+  grads[3 * iw + 2] = vgl[3];
+}
+
+// device driver: Metropolis test for the whole crowd in one CTA (VMCBatched.cpp:139-167)
+template<typename T>
+__global__ void __launch_bounds__(1024)
+    decide_kernel(const DriverDev<T> Dr, const JastrowDev<T> J, RngDev R, const int iat, const T* rg)
+{
+  __shared__ unsigned warp_cnt[32];
+  __shared__ unsigned long long s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  if (tid == 0)
+    s_base = *R.pos;
+  __syncthreads();
+  const T eps = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
+  for (int base = 0; base < Dr.nw; base += blockDim.x)
+  {
+    const int iw  = base + tid;
+    bool need     = false;
+    T prob = T(0), log_gf = T(0), log_gb = T(0);
+    if (iw < Dr.nw)
+    {
+      T gn[3];
+      const double ratio = twf_ratio_grad(J, iw, iat, rg, gn);
+      if (Dr.use_drift)
+      {
+        const T* dl = Dr.delta_cur + 3 * iw;
+        log_gf      = -Dr.oneover2tau * (dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
+        T dr[3];
+        get_drift<T>(Dr.tauovermass, gn, dr);
+        dr[0] += Dr.drifts[3 * iw];
+        dr[1] += Dr.drifts[3 * iw + 1];
+        dr[2] += Dr.drifts[3 * iw + 2];
+        log_gb = -Dr.oneover2tau * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
+      }
+      prob = (T)(ratio * ratio);
+      need = prob >= eps; // periodic cell: every move is valid
+    }
+    // exclusive scan of `need` in walker order
+    const unsigned bal = __ballot_sync(0xffffffffu, need);
+    const unsigned pre = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0)
+      warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    unsigned woff = 0, total = 0;
+    for (int w = 0; w < nwarp; ++w)
+    {
+      const unsigned cnt = warp_cnt[w];
+      if (w < warp)
+        woff += cnt;
+      total += cnt;
+    }
+    if (iw < Dr.nw)
+    {
+      bool acc = false;
+      if (need)
+      {
+        const double u = rng_uniform(R, s_base + woff + pre);
+        acc            = u < (double)(prob * exp(log_gb - log_gf));
+      }
+      Dr.accepted[iw] = acc ? 1 : 0;
+      if (acc)
+        Dr.n_accept[iw] += 1;
+      else
+        Dr.n_reject[iw] += 1;
+      if (Dr.accept_log)
+        Dr.accept_log[(size_t)iat * Dr.nw + iw] = acc ? 1 : 0;
+    }
+    __syncthreads();
+    if (tid == 0)
+      s_base += total;
+    __syncthreads();
+  }
+  if (tid == 0)
+    *R.pos = s_base;
+}
+
+// kinetic energy and log psi per walker: ke = -1/2 sum_i (L_i + G_i.G_i)
+template<typename T>
+__global__ void __launch_bounds__(256) ke_kernel(int N, const T* Gd, const T* Ld, double* ke)
+{
+  __shared__ double red[32];
+  const int iw = blockIdx.x, tid = threadIdx.x;
+  double acc[1] = {0.0};
+  for (int i = tid; i < N; i += blockDim.x)
+  {
+    const T* g = Gd + ((size_t)iw * N + i) * 3;
+    acc[0] += (double)Ld[(size_t)iw * N + i] + (double)g[0] * g[0] + (double)g[1] * g[1] + (double)g[2] * g[2];
+  }
+  block_sum<double, 1>(acc, red);
+  if (tid == 0)
+    ke[iw] = -0.5 * acc[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+template<typename T>
+struct Crowd : CrowdBase
+{
+  qmcb_system sys;
+  int nw = 0, N = 0, k = 1;
+  int nel[2], first[2], lda[2];
+  int nmax = 0;
+  size_t npad = 0;
+  SplineSPOBase* spo[2];
+  cudaStream_t st = nullptr, st2 = nullptr, st3 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_rng = nullptr, ev_rng_done = nullptr;
+  cublasHandle_t blas = nullptr;
+
+  // determinants
+  DetDev<T> det[2];
+  DevBuf<T> Ainv[2], GL[2], U[2], V[2], Binv[2], wvec[2], invRow[2], tempMat[2], Up[2];
+  DevBuf<int> list[2];
+  DevBuf<double> logdet[2];
+  int delay_count[2] = {0, 0};
+  int invrow_id[2]   = {-1, -1};
+  // jastrow / particle set
+  JastrowDev<T> jas;
+  DevBuf<T> rsoa, newpos, rows, cur_allu, j2_vgl, Uat, dUat, d2Uat, j1_cur, Vat, Grad1, Lap1, ion_rsoa, fcoefs;
+  DevBuf<int> ion_grp;
+  DevBuf<double> j2_log, j1_log;
+  // shared scratch
+  DevBuf<T> phi_vgl, rg, det_grads, grads_tmp, displ, Gd, Ld;
+  DevBuf<double> ratios_d, ke_d;
+  DevBuf<unsigned char> accepted;
+  PinBuf<unsigned char> h_acc;
+  PinBuf<T> h_t;
+  PinBuf<double> h_d;
+  // driver
+  DriverDev<T> drv;
+  RngDev rng;
+  DevBuf<T> deltas, drifts, delta_cur;
+  DevBuf<uint32_t> rng_state, rng_ring;
+  DevBuf<unsigned long long> rng_cnt, n_acc, n_rej;
+  DevBuf<unsigned char> accept_log;
+  bool vmc_ready = false, use_graph = false;
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_logs = false;
+  unsigned long long sweep_backlog = 0;
+  size_t dev_bytes = 0;
+
+  template<typename X>
+  void A(DevBuf<X>& b, size_t n)
+  {
+    b.alloc(n);
+    dev_bytes += b.bytes();
+  }
+
+  static void fill_functor(FunctorDev<T>& f, std::vector<T>& pool, const double* params, int np, double rcut, double cusp)
+  {
+    // ref: BsplineFunctor.h:102-131 resize/reset, arithmetic in Real = T
+    const T cutoff     = (T)rcut;
+    const int numCoefs = np + 4;
+    const int numKnots = numCoefs - 2;
+    const T DeltaR     = cutoff / (T)(numKnots - 1);
+    const T DeltaRInv  = (T)(1.0 / DeltaR);
+    std::vector<T> c(numCoefs, T(0)), P(params, params + np);
+    c[1] = P[0];
+    c[2] = P[1];
+    c[0] = (T)(P[1] - 2.0 * DeltaR * (T)cusp);
+    for (int i = 2; i < np; ++i)
+      c[i + 1] = P[i];
+    f.coefs     = reinterpret_cast<const T*>(pool.size()); // offset for now, patched after upload
+    f.DeltaRInv = DeltaRInv;
+    f.rcut      = cutoff;
+    f.max_index = numCoefs - 4;
+    pool.insert(pool.end(), c.begin(), c.end());
+  }
+
+  Crowd(const qmcb_system* s, int nw_) : sys(*s), nw(nw_)
+  {
+    if (nw <= 0)
+      throw std::runtime_error("crowd: nw must be positive");
+    N        = sys.n_up + sys.n_dn;
+    k        = std::max(1, sys.delay_rank);
+    nel[0]   = sys.n_up;
+    nel[1]   = sys.n_dn;
+    first[0] = 0;
+    first[1] = sys.n_up;
+    nmax     = std::max(nel[0], nel[1]);
+    npad     = aligned_size<T>(N);
+    for (int i = 0; i < 2; ++i)
+    {
+      if (!sys.spo[i])
+        throw std::runtime_error("crowd: missing SPOSet handle");
+      spo[i] = sys.spo[i]->impl.get();
+      if (spo[i]->precision != sys.precision || spo[i]->kind != QMCB_R2R)
+        throw std::runtime_error("crowd: SPOSet precision/kind mismatch (real determinants need SplineR2R tables)");
+      if (spo[i]->n_orb != nel[i])
+        throw std::runtime_error("crowd: the SPOSet of each determinant must hold exactly n_el orbitals");
+      if (k > std::max(1, nel[i]) && nel[i] > 0)
+        throw std::runtime_error("crowd: delay_rank larger than the determinant");
+    }
+    QMCB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    QMCB_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+    QMCB_CUDA(cudaStreamCreateWithFlags(&st3, cudaStreamNonBlocking));
+    QMCB_CUDA(cudaEventCreateWithFlags(&ev_rng_done, cudaEventDisableTiming));
+    QMCB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    QMCB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    QMCB_CUDA(cudaEventCreateWithFlags(&ev_rng, cudaEventDisableTiming));
+    QMCB_CUBLAS(cublasCreate(&blas));
+    QMCB_CUBLAS(cublasSetStream(blas, st));
+
+    for (int s2 = 0; s2 < 2; ++s2)
+    {
+      const int n = nel[s2];
+      lda[s2]     = (int)aligned_size<T>(n);
+      A(Ainv[s2], (size_t)nw * n * lda[s2]);
+      A(GL[s2], (size_t)nw * n * 4 * n);
+      A(U[s2], (size_t)nw * k * n);
+      A(V[s2], (size_t)nw * k * n);
+      A(Binv[s2], (size_t)nw * k * k);
+      A(wvec[s2], (size_t)nw * k);
+      A(list[s2], (size_t)nw * k);
+      A(invRow[s2], (size_t)nw * n);
+      A(tempMat[s2], (size_t)nw * n * k);
+      A(Up[s2], (size_t)nw * k * n);
+      A(logdet[s2], (size_t)nw * 2);
+      DetDev<T>& D = det[s2];
+      D.n = n, D.lda = lda[s2], D.k = k, D.nw = nw;
+      D.Ainv = Ainv[s2].p, D.GL = GL[s2].p, D.U = U[s2].p, D.V = V[s2].p, D.Binv = Binv[s2].p, D.wvec = wvec[s2].p;
+      D.list = list[s2].p, D.invRow = invRow[s2].p, D.tempMat = tempMat[s2].p, D.Up = Up[s2].p, D.logdet = logdet[s2].p;
+    }
+    A(phi_vgl, (size_t)5 * nw * nmax);
+    A(rg, (size_t)nw * 4);
+    A(det_grads, (size_t)nw * 3);
+    A(grads_tmp, (size_t)nw * 3);
+    A(displ, (size_t)nw * 3);
+    A(Gd, (size_t)nw * N * 3);
+    A(Ld, (size_t)nw * N);
+    A(ratios_d, nw);
+    A(ke_d, nw);
+    A(accepted, nw);
+    h_acc.alloc(nw);
+    h_t.alloc(std::max<size_t>((size_t)nw * 8, 64));
+    h_d.alloc(std::max<size_t>((size_t)nw * 8, 64));
+
+    // ---- particle set + Jastrows
+    std::memset(&jas, 0, sizeof(jas));
+    jas.N = N, jas.npad = (int)npad, jas.n_up = sys.n_up, jas.nw = nw;
+    set_cell(jas.cell, sys.lattice);
+    A(rsoa, (size_t)nw * 3 * npad);
+    A(newpos, (size_t)nw * 3);
+    jas.rsoa = rsoa.p, jas.newpos = newpos.p;
+    std::vector<T> pool;
+    jas.has_j2 = sys.n_j2 > 0;
+    if (jas.has_j2)
+    {
+      A(rows, (size_t)2 * nw * 4 * npad);
+      A(cur_allu, (size_t)nw * 3 * npad);
+      A(j2_vgl, (size_t)nw * 5);
+      A(Uat, (size_t)nw * npad);
+      A(dUat, (size_t)nw * 3 * npad);
+      A(d2Uat, (size_t)nw * npad);
+      A(j2_log, nw);
+      jas.rows = rows.p, jas.cur_allu = cur_allu.p, jas.j2_vgl = j2_vgl.p, jas.Uat = Uat.p, jas.dUat = dUat.p;
+      jas.d2Uat = d2Uat.p, jas.j2_log = j2_log.p;
+      // cusp -1/4 like spin, -1/2 unlike spin (Jastrow/RadialJastrowBuilder.cpp:200-208)
+      fill_functor(jas.F2[0], pool, sys.j2_uu, sys.n_j2, sys.j2_rcut, -0.25);
+      fill_functor(jas.F2[1], pool, sys.j2_ud, sys.n_j2, sys.j2_rcut, -0.5);
+      fill_functor(jas.F2[2], pool, sys.j2_ud, sys.n_j2, sys.j2_rcut, -0.5);
+      fill_functor(jas.F2[3], pool, sys.j2_uu, sys.n_j2, sys.j2_rcut, -0.25);
+    }
+    jas.has_j1 = sys.nions > 0;
+    if (jas.has_j1)
+    {
+      if (sys.n_ion_groups > 8)
+        throw std::runtime_error("crowd: at most 8 ion groups");
+      jas.nions    = sys.nions;
+      jas.npad_ion = (int)aligned_size<T>(sys.nions);
+      std::vector<T> ir(3 * (size_t)jas.npad_ion, T(0));
+      for (int i = 0; i < sys.nions; ++i)
+        for (int d = 0; d < 3; ++d)
+          ir[(size_t)d * jas.npad_ion + i] = (T)sys.ion_pos[3 * i + d];
+      A(ion_rsoa, ir.size());
+      QMCB_CUDA(cudaMemcpy(ion_rsoa.p, ir.data(), ir.size() * sizeof(T), cudaMemcpyHostToDevice));
+      A(ion_grp, sys.nions);
+      QMCB_CUDA(cudaMemcpy(ion_grp.p, sys.ion_grp, sys.nions * sizeof(int), cudaMemcpyHostToDevice));
+      A(j1_cur, (size_t)nw * 5);
+      A(Vat, (size_t)nw * N);
+      A(Grad1, (size_t)nw * 3 * N);
+      A(Lap1, (size_t)nw * N);
+      A(j1_log, nw);
+      jas.ion_rsoa = ion_rsoa.p, jas.ion_grp = ion_grp.p, jas.j1_cur = j1_cur.p, jas.Vat = Vat.p, jas.Grad1 = Grad1.p;
+      jas.Lap1 = Lap1.p, jas.j1_log = j1_log.p;
+      for (int g = 0; g < sys.n_ion_groups; ++g)
+        fill_functor(jas.F1[g], pool, sys.j1_params + (size_t)g * sys.n_j1, sys.n_j1, sys.j1_rcut[g], 0.0);
+    }
+    if (!pool.empty())
+    {
+      A(fcoefs, pool.size());
+      QMCB_CUDA(cudaMemcpy(fcoefs.p, pool.data(), pool.size() * sizeof(T), cudaMemcpyHostToDevice));
+      auto patch = [&](FunctorDev<T>& f) { f.coefs = fcoefs.p + reinterpret_cast<size_t>(f.coefs); };
+      if (jas.has_j2)
+        for (int i = 0; i < 4; ++i)
+          patch(jas.F2[i]);
+      if (jas.has_j1)
+        for (int g = 0; g < sys.n_ion_groups; ++g)
+          patch(jas.F1[g]);
+    }
+    QMCB_CUDA(cudaDeviceSynchronize());
+  }
+
+  ~Crowd() override
+  {
+    if (graph_exec)
+      cudaGraphExecDestroy(graph_exec);
+    if (blas)
+      cublasDestroy(blas);
+    if (ev_fork)
+      cudaEventDestroy(ev_fork);
+    if (ev_join)
+      cudaEventDestroy(ev_join);
+    if (ev_rng)
+      cudaEventDestroy(ev_rng);
+    if (st)
+      cudaStreamDestroy(st);
+    if (st2)
+      cudaStreamDestroy(st2);
+    if (st3)
+      cudaStreamDestroy(st3);
+    if (ev_rng_done)
+      cudaEventDestroy(ev_rng_done);
+  }
+
+  static void set_cell(CellDev<T>& C, const double R[9])
+  {
+    C.ortho = (R[1] == 0 && R[2] == 0 && R[3] == 0 && R[5] == 0 && R[6] == 0 && R[7] == 0) ? 1 : 0;
+    const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) +
+        R[2] * (R[3] * R[7] - R[4] * R[6]);
+    if (det == 0)
+      throw std::runtime_error("crowd: singular lattice");
+    double G[9];
+    G[0] = (R[4] * R[8] - R[5] * R[7]) / det;
+    G[1] = (R[2] * R[7] - R[1] * R[8]) / det;
+    G[2] = (R[1] * R[5] - R[2] * R[4]) / det;
+    G[3] = (R[5] * R[6] - R[3] * R[8]) / det;
+    G[4] = (R[0] * R[8] - R[2] * R[6]) / det;
+    G[5] = (R[2] * R[3] - R[0] * R[5]) / det;
+    G[6] = (R[3] * R[7] - R[4] * R[6]) / det;
+    G[7] = (R[1] * R[6] - R[0] * R[7]) / det;
+    G[8] = (R[0] * R[4] - R[1] * R[3]) / det;
+    for (int i = 0; i < 9; ++i)
+    {
+      C.r[i] = (T)R[i];
+      C.g[i] = (T)G[i];
+    }
+    for (int d = 0; d < 3; ++d)
+    {
+      const double len = std::sqrt(R[3 * d] * R[3 * d] + R[3 * d + 1] * R[3 * d + 1] + R[3 * d + 2] * R[3 * d + 2]);
+      C.L[d]           = (T)len;
+      C.Linv[d]        = (T)(1.0 / len);
+      const T a0 = (T)R[0 + d], a1 = (T)R[3 + d], a2 = (T)R[6 + d];
+      C.corners[d][0] = T(0);
+      C.corners[d][1] = T(-1) * a0;
+      C.corners[d][2] = T(-1) * a1;
+      C.corners[d][3] = T(-1) * a2;
+      C.corners[d][4] = T(-1) * (a0 + a1);
+      C.corners[d][5] = T(-1) * (a0 + a2);
+      C.corners[d][6] = T(-1) * (a1 + a2);
+      C.corners[d][7] = T(-1) * (a0 + a1 + a2);
+    }
+  }
+
+  cudaStream_t stream() override { return st; }
+  void sync() override { QMCB_CUDA(cudaStreamSynchronize(st)); }
+  size_t device_bytes() const override { return dev_bytes; }
+  int spin_of(int iat) const { return iat < sys.n_up ? 0 : 1; }
+  static int blocks(int n, int tpb) { return (n + tpb - 1) / tpb; }
+  void check_iat(int iat) const
+  {
+    if (iat < 0 || iat >= N)
+      throw std::runtime_error("electron index out of range");
+  }
+  void check_row(int spin, int row) const
+  {
+    if (spin < 0 || spin > 1 || row < 0 || row >= nel[spin])
+      throw std::runtime_error("determinant row out of range");
+  }
+
+  // ---------------------------------------------------------------- positions
+  void set_positions(const double* R) override
+  {
+    std::vector<T> h((size_t)nw * 3 * npad, T(0));
+    for (int iw = 0; iw < nw; ++iw)
+      for (int i = 0; i < N; ++i)
+        for (int d = 0; d < 3; ++d)
+          h[((size_t)iw * 3 + d) * npad + i] = (T)R[((size_t)iw * N + i) * 3 + d];
+    QMCB_CUDA(cudaMemcpyAsync(rsoa.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    sync();
+  }
+  void get_positions(double* R) override
+  {
+    std::vector<T> h((size_t)nw * 3 * npad);
+    QMCB_CUDA(cudaMemcpyAsync(h.data(), rsoa.p, h.size() * sizeof(T), cudaMemcpyDeviceToHost, st));
+    sync();
+    for (int iw = 0; iw < nw; ++iw)
+      for (int i = 0; i < N; ++i)
+        for (int d = 0; d < 3; ++d)
+          R[((size_t)iw * N + i) * 3 + d] = (double)h[((size_t)iw * 3 + d) * npad + i];
+  }
+
+  // ---------------------------------------------------------------- determinant engine
+  void launch_prepare(int spin, int row, T* grads)
+  {
+    const DetDev<T>& D = det[spin];
+    const size_t smem  = (size_t)(D.n + 2 * D.k) * sizeof(T);
+    det_prepare_row_kernel<T><<<nw, DET_TPB, smem, st>>>(D, row, delay_count[spin], grads);
+    QMCB_LAUNCH_CHECK();
+    invrow_id[spin] = row;
+  }
+  void ensure_row(int spin, int row)
+  {
+    if (invrow_id[spin] != row)
+      launch_prepare(spin, row, nullptr);
+  }
+  void launch_flush(int spin)
+  {
+    const int c = delay_count[spin];
+    if (c == 0)
+      return;
+    const DetDev<T>& D = det[spin];
+    const int n        = D.n;
+    // tempMat[n x c] = Ainv[n x n] * U^T, with the -1 fix-up (applyW) fused
+    gemm_batched_kernel<T, true, true><<<dim3(blocks(c, 64), blocks(n, 64), nw), 256, 0, st>>>(
+        n, c, n, T(1), D.Ainv, D.lda, (size_t)n * D.lda, D.U, n, (size_t)D.k * n, T(0), D.tempMat, D.k, (size_t)n * D.k,
+        D.list, D.k);
+    QMCB_LAUNCH_CHECK();
+    // Up[c x n] = Binv[c x c] * V[c x n]
+    gemm_batched_kernel<T, false, false><<<dim3(blocks(n, 64), blocks(c, 64), nw), 256, 0, st>>>(
+        c, n, c, T(1), D.Binv, D.k, (size_t)D.k * D.k, D.V, n, (size_t)D.k * n, T(0), D.Up, n, (size_t)D.k * n, nullptr, 0);
+    QMCB_LAUNCH_CHECK();
+    // Ainv -= tempMat * Up
+    gemm_batched_kernel<T, false, false><<<dim3(blocks(n, 64), blocks(n, 64), nw), 256, 0, st>>>(
+        n, n, c, T(-1), D.tempMat, D.k, (size_t)n * D.k, D.Up, n, (size_t)D.k * n, T(1), D.Ainv, D.lda, (size_t)n * D.lda,
+        nullptr, 0);
+    QMCB_LAUNCH_CHECK();
+    delay_count[spin] = 0;
+    invrow_id[spin]   = -1;
+  }
+  void launch_accept(int spin, int row, const unsigned char* acc_dev, const T* rg_dev, const T* phi_dev)
+  {
+    const DetDev<T>& D = det[spin];
+    const size_t smem  = (size_t)(D.n + 2 * D.k) * sizeof(T);
+    det_accept_kernel<T><<<nw, DET_TPB, smem, st>>>(D, row, delay_count[spin], acc_dev, rg_dev, phi_dev);
+    QMCB_LAUNCH_CHECK();
+    delay_count[spin]++;
+    invrow_id[spin] = -1;
+    if (delay_count[spin] == k)
+      launch_flush(spin);
+  }
+  void launch_spline(int spin, int mode, const void* invrow, size_t ld, void* phi, void* rgp, cudaStream_t s)
+  {
+    spo[spin]->evaluate_dev(mode, nw, newpos.p, invrow, ld, nullptr, phi, rgp, s);
+  }
+
+  void det_eval_grad(int spin, int row, void* grads) override
+  {
+    check_row(spin, row);
+    launch_prepare(spin, row, det_grads.p);
+    QMCB_CUDA(cudaMemcpyAsync(h_t.p, det_grads.p, (size_t)nw * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    sync();
+    std::memcpy(grads, h_t.p, (size_t)nw * 3 * sizeof(T));
+  }
+  void det_get_inv_row(int spin, int row, const void** dev, size_t* ld, void* host) override
+  {
+    check_row(spin, row);
+    ensure_row(spin, row);
+    if (dev)
+      *dev = invRow[spin].p;
+    if (ld)
+      *ld = det[spin].n;
+    if (host)
+    {
+      QMCB_CUDA(cudaMemcpyAsync(host, invRow[spin].p, (size_t)nw * det[spin].n * sizeof(T), cudaMemcpyDeviceToHost, st));
+      sync();
+    }
+  }
+  void det_ratio_grad(int spin, int row, void* ratios, void* grads, bool from_phi) override
+  {
+    check_row(spin, row);
+    ensure_row(spin, row);
+    if (from_phi)
+    {
+      det_ratio_from_phi_kernel<T><<<nw, DET_TPB, 0, st>>>(det[spin], phi_vgl.p, rg.p);
+      QMCB_LAUNCH_CHECK();
+    }
+    else
+      launch_spline(spin, MODE_VGL, invRow[spin].p, det[spin].n, phi_vgl.p, rg.p, st);
+    QMCB_CUDA(cudaMemcpyAsync(h_t.p, rg.p, (size_t)nw * 4 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    sync();
+    T* r = static_cast<T*>(ratios);
+    T* g = static_cast<T*>(grads);
+    for (int iw = 0; iw < nw; ++iw)
+    {
+      const T ratio = h_t.p[4 * iw];
+      r[iw]         = ratio;
+      if (g)
+        for (int d = 0; d < 3; ++d)
+          g[3 * iw + d] = h_t.p[4 * iw + 1 + d] / ratio; // SPOSet.cpp:171 grads = dot / ratio
+    }
+  }
+  void upload_flags(const uint8_t* acc)
+  {
+    std::memcpy(h_acc.p, acc, nw);
+    QMCB_CUDA(cudaMemcpyAsync(accepted.p, h_acc.p, nw, cudaMemcpyHostToDevice, st));
+  }
+  void det_accept_reject(int spin, int row, const uint8_t* acc) override
+  {
+    check_row(spin, row);
+    upload_flags(acc);
+    launch_accept(spin, row, accepted.p, rg.p, phi_vgl.p);
+    sync(); // h_acc is reused by the next call
+  }
+  void det_complete_updates(int spin, void* psiMinv, double* logdet_h) override
+  {
+    if (spin < 0 || spin > 1)
+      throw std::runtime_error("bad spin");
+    launch_flush(spin);
+    const int n = nel[spin];
+    if (psiMinv)
+      QMCB_CUDA(cudaMemcpy2DAsync(psiMinv, (size_t)n * sizeof(T), Ainv[spin].p, (size_t)lda[spin] * sizeof(T),
+                                  (size_t)n * sizeof(T), (size_t)nw * n, cudaMemcpyDeviceToHost, st));
+    if (logdet_h)
+      QMCB_CUDA(cudaMemcpyAsync(logdet_h, logdet[spin].p, (size_t)nw * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    sync();
+  }
+  int det_delay_count(int spin) override { return delay_count[spin]; }
+  void det_set_phi_vgl(int spin, const void* phi) override
+  {
+    const int n = nel[spin];
+    // host layout [5][nw][n] -> device layout [5][nw][n] with the same n (phi_vgl is sized for nmax but indexed with D.n)
+    QMCB_CUDA(cudaMemcpyAsync(phi_vgl.p, phi, (size_t)5 * nw * n * sizeof(T), cudaMemcpyHostToDevice, st));
+    sync();
+  }
+
+  // FP64 inversion of the transposed matrices in AT (column-major psiM), result into Ainv, log-determinants
+  void invert_from_AT(int spin, DevBuf<double>& AT)
+  {
+    const int n = nel[spin];
+    DevBuf<double> inv;
+    DevBuf<int> piv, info;
+    DevBuf<double*> ptrs;
+    inv.alloc((size_t)nw * n * n, false);
+    piv.alloc((size_t)nw * n);
+    info.alloc(nw);
+    ptrs.alloc(2 * (size_t)nw);
+    std::vector<double*> hp(2 * (size_t)nw);
+    for (int iw = 0; iw < nw; ++iw)
+    {
+      hp[iw]      = AT.p + (size_t)iw * n * n;
+      hp[nw + iw] = inv.p + (size_t)iw * n * n;
+    }
+    QMCB_CUDA(cudaMemcpyAsync(ptrs.p, hp.data(), hp.size() * sizeof(double*), cudaMemcpyHostToDevice, st));
+    QMCB_CUBLAS(cublasDgetrfBatched(blas, n, ptrs.p, n, piv.p, info.p, nw));
+    g_launch_count.fetch_add(1);
+    det_logdet_kernel<<<nw, 128, 0, st>>>(AT.p, piv.p, n, logdet[spin].p);
+    QMCB_LAUNCH_CHECK();
+    QMCB_CUBLAS(cublasDgetriBatched(blas, n, ptrs.p, n, piv.p, ptrs.p + nw, n, info.p, nw));
+    g_launch_count.fetch_add(1);
+    det_store_inverse_kernel<T><<<dim3(blocks(n, 128), n, nw), 128, 0, st>>>(det[spin], inv.p);
+    QMCB_LAUNCH_CHECK();
+    std::vector<int> hinfo(nw);
+    QMCB_CUDA(cudaMemcpyAsync(hinfo.data(), info.p, nw * sizeof(int), cudaMemcpyDeviceToHost, st));
+    sync();
+    for (int iw = 0; iw < nw; ++iw)
+      if (hinfo[iw] != 0)
+        throw std::runtime_error("matrix inversion failed (singular Slater matrix) for walker " + std::to_string(iw));
+    delay_count[spin] = 0;
+    invrow_id[spin]   = -1;
+  }
+
+  void det_recompute_from_matrices(int spin, const void* psiM, const void* dpsiM, const void* d2psiM) override
+  {
+    const int n = nel[spin];
+    const T* pm = static_cast<const T*>(psiM);
+    const T* dp = static_cast<const T*>(dpsiM);
+    const T* d2 = static_cast<const T*>(d2psiM);
+    std::vector<double> at((size_t)nw * n * n);
+    std::vector<T> gl((size_t)nw * n * 4 * n, T(0));
+    for (int iw = 0; iw < nw; ++iw)
+      for (int e = 0; e < n; ++e)
+        for (int j = 0; j < n; ++j)
+        {
+          at[((size_t)iw * n + j) * n + e] = (double)pm[((size_t)iw * n + e) * n + j];
+          T* g                             = &gl[((size_t)iw * n + e) * 4 * n];
+          if (dp)
+            for (int d = 0; d < 3; ++d)
+              g[(size_t)d * n + j] = dp[(((size_t)iw * n + e) * n + j) * 3 + d];
+          if (d2)
+            g[(size_t)3 * n + j] = d2[((size_t)iw * n + e) * n + j];
+        }
+    DevBuf<double> AT;
+    AT.alloc(at.size(), false);
+    QMCB_CUDA(cudaMemcpyAsync(AT.p, at.data(), at.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    QMCB_CUDA(cudaMemcpyAsync(GL[spin].p, gl.data(), gl.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    invert_from_AT(spin, AT);
+  }
+
+  // ---------------------------------------------------------------- trial wavefunction level
+  void twf_recompute() override
+  {
+    for (int spin = 0; spin < 2; ++spin)
+    {
+      const int n = nel[spin];
+      if (n == 0)
+        continue;
+      DevBuf<double> AT;
+      AT.alloc((size_t)nw * n * n, false);
+      // SPOSet::mw_evaluate_notranspose for splines = loop over electrons calling mw_evaluateVGL (BsplineSet.h:142-189)
+      for (int e = 0; e < n; ++e)
+      {
+        const int iat = first[spin] + e;
+        make_move_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, displ_zero());
+        QMCB_LAUNCH_CHECK();
+        launch_spline(spin, MODE_VGL, nullptr, 0, phi_vgl.p, nullptr, st);
+        det_scatter_row_kernel<T><<<dim3(blocks(n, 128), nw), 128, 0, st>>>(det[spin], e, phi_vgl.p, AT.p);
+        QMCB_LAUNCH_CHECK();
+      }
+      invert_from_AT(spin, AT);
+    }
+    if (jas.has_j2 || jas.has_j1)
+    {
+      jastrow_recompute_kernel<T><<<nw, JAS_TPB, 0, st>>>(jas);
+      QMCB_LAUNCH_CHECK();
+    }
+    sync();
+  }
+  const T* displ_zero()
+  {
+    QMCB_CUDA(cudaMemsetAsync(displ.p, 0, displ.bytes(), st));
+    return displ.p;
+  }
+
+  void twf_eval_grad(int iat, double* grads) override
+  {
+    check_iat(iat);
+    const int spin = spin_of(iat), row = iat - first[spin];
+    launch_prepare(spin, row, det_grads.p);
+    twf_grad_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, det_grads.p, grads_tmp.p);
+    QMCB_LAUNCH_CHECK();
+    QMCB_CUDA(cudaMemcpyAsync(h_t.p, grads_tmp.p, (size_t)nw * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    sync();
+    for (int i = 0; i < 3 * nw; ++i)
+      grads[i] = (double)h_t.p[i];
+  }
+
+  void ps_make_move(int iat, const double* dsp) override
+  {
+    check_iat(iat);
+    T* h = h_t.p + 4 * (size_t)nw; // second half of the staging buffer
+    for (int i = 0; i < 3 * nw; ++i)
+      h[i] = (T)dsp[i];
+    QMCB_CUDA(cudaMemcpyAsync(displ.p, h, (size_t)nw * 3 * sizeof(T), cudaMemcpyHostToDevice, st));
+    make_move_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, displ.p);
+    QMCB_LAUNCH_CHECK();
+    if (jas.has_j2 || jas.has_j1)
+    {
+      jastrow_move_kernel<T><<<nw, JAS_TPB, 0, st>>>(jas, iat);
+      QMCB_LAUNCH_CHECK();
+    }
+  }
+
+  void twf_calc_ratio_grad(int iat, double* ratios, double* grads) override
+  {
+    check_iat(iat);
+    const int spin = spin_of(iat), row = iat - first[spin];
+    ensure_row(spin, row);
+    launch_spline(spin, MODE_VGL, invRow[spin].p, det[spin].n, phi_vgl.p, rg.p, st);
+    twf_ratio_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, rg.p, ratios_d.p, grads_tmp.p);
+    QMCB_LAUNCH_CHECK();
+    QMCB_CUDA(cudaMemcpyAsync(h_d.p, ratios_d.p, (size_t)nw * sizeof(double), cudaMemcpyDeviceToHost, st));
+    QMCB_CUDA(cudaMemcpyAsync(h_t.p, grads_tmp.p, (size_t)nw * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    sync();
+    std::memcpy(ratios, h_d.p, (size_t)nw * sizeof(double));
+    for (int i = 0; i < 3 * nw; ++i)
+      grads[i] = (double)h_t.p[i];
+  }
+
+  void twf_accept_reject(int iat, const uint8_t* acc, int safe_to_delay) override
+  {
+    check_iat(iat);
+    const int spin = spin_of(iat), row = iat - first[spin];
+    upload_flags(acc);
+    launch_accept(spin, row, accepted.p, rg.p, phi_vgl.p);
+    if (!safe_to_delay)
+      launch_flush(spin);
+    jastrow_accept_kernel<T><<<nw, JAS_TPB, 0, st>>>(jas, iat, accepted.p);
+    QMCB_LAUNCH_CHECK();
+    sync(); // the pinned flag buffer is reused by the next call
+  }
+
+  void twf_complete_updates() override
+  {
+    launch_flush(0);
+    launch_flush(1);
+  }
+
+  void twf_evaluate_gl(double* G, double* L, double* logpsi, double* ke) override
+  {
+    twf_complete_updates();
+    QMCB_CUDA(cudaMemsetAsync(Gd.p, 0, Gd.bytes(), st));
+    QMCB_CUDA(cudaMemsetAsync(Ld.p, 0, Ld.bytes(), st));
+    for (int spin = 0; spin < 2; ++spin)
+      if (nel[spin] > 0)
+      {
+        det_compute_gl_kernel<T, T><<<dim3(nel[spin], nw), 128, 0, st>>>(det[spin], first[spin], N, Gd.p, Ld.p);
+        QMCB_LAUNCH_CHECK();
+      }
+    if (jas.has_j2 || jas.has_j1)
+    {
+      jastrow_add_gl_kernel<T><<<dim3(blocks(N, 256), nw), 256, 0, st>>>(jas, Gd.p, Ld.p);
+      QMCB_LAUNCH_CHECK();
+    }
+    ke_kernel<T><<<nw, 256, 0, st>>>(N, Gd.p, Ld.p, ke_d.p);
+    QMCB_LAUNCH_CHECK();
+    std::vector<T> hg, hl;
+    std::vector<double> hk(nw), l0(2 * (size_t)nw), l1(2 * (size_t)nw), lj2(nw, 0.0), lj1(nw, 0.0);
+    if (G)
+    {
+      hg.resize((size_t)nw * N * 3);
+      QMCB_CUDA(cudaMemcpyAsync(hg.data(), Gd.p, hg.size() * sizeof(T), cudaMemcpyDeviceToHost, st));
+    }
+    if (L)
+    {
+      hl.resize((size_t)nw * N);
+      QMCB_CUDA(cudaMemcpyAsync(hl.data(), Ld.p, hl.size() * sizeof(T), cudaMemcpyDeviceToHost, st));
+    }
+    QMCB_CUDA(cudaMemcpyAsync(hk.data(), ke_d.p, nw * sizeof(double), cudaMemcpyDeviceToHost, st));
+    QMCB_CUDA(cudaMemcpyAsync(l0.data(), logdet[0].p, l0.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    QMCB_CUDA(cudaMemcpyAsync(l1.data(), logdet[1].p, l1.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (jas.has_j2)
+      QMCB_CUDA(cudaMemcpyAsync(lj2.data(), j2_log.p, nw * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (jas.has_j1)
+      QMCB_CUDA(cudaMemcpyAsync(lj1.data(), j1_log.p, nw * sizeof(double), cudaMemcpyDeviceToHost, st));
+    sync();
+    if (G)
+      for (size_t i = 0; i < hg.size(); ++i)
+        G[i] = (double)hg[i];
+    if (L)
+      for (size_t i = 0; i < hl.size(); ++i)
+        L[i] = (double)hl[i];
+    for (int iw = 0; iw < nw; ++iw)
+    {
+      if (ke)
+        ke[iw] = hk[iw];
+      if (logpsi)
+        logpsi[iw] = l0[2 * iw] + l1[2 * iw] + lj2[iw] + lj1[iw];
+    }
+  }
+
+  // ---------------------------------------------------------------- component level: DT rows + J2
+  void dtaa_get_temp_rows(void* out) override
+  {
+    if (!jas.has_j2)
+      throw std::runtime_error("distance rows are only kept when a two-body Jastrow is present");
+    // device [2][nw][4][npad] -> host [2][nw][4][N]
+    QMCB_CUDA(cudaMemcpy2DAsync(out, (size_t)N * sizeof(T), rows.p, npad * sizeof(T), (size_t)N * sizeof(T),
+                                (size_t)2 * nw * 4, cudaMemcpyDeviceToHost, st));
+    sync();
+  }
+  void j2_ratio_grad(int iat, double* ratios, void* grads) override
+  {
+    check_iat(iat);
+    if (!jas.has_j2)
+      throw std::runtime_error("no two-body Jastrow in this crowd");
+    j2_ratio_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, ratios_d.p, grads_tmp.p);
+    QMCB_LAUNCH_CHECK();
+    QMCB_CUDA(cudaMemcpyAsync(ratios, ratios_d.p, (size_t)nw * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (grads)
+      QMCB_CUDA(cudaMemcpyAsync(grads, grads_tmp.p, (size_t)nw * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    sync();
+  }
+  void j2_accept_reject(int iat, const uint8_t* acc) override
+  {
+    check_iat(iat);
+    upload_flags(acc);
+    jastrow_accept_kernel<T><<<nw, JAS_TPB, 0, st>>>(jas, iat, accepted.p);
+    QMCB_LAUNCH_CHECK();
+    sync();
+  }
+  void j2_get_state(int iw, double* Uat_h, double* dUat_h, double* d2Uat_h) override
+  {
+    if (!jas.has_j2 || iw < 0 || iw >= nw)
+      throw std::runtime_error("j2_get_state: bad walker or no J2");
+    std::vector<T> u(npad), du(3 * npad), d2(npad);
+    QMCB_CUDA(cudaMemcpyAsync(u.data(), Uat.p + (size_t)iw * npad, npad * sizeof(T), cudaMemcpyDeviceToHost, st));
+    QMCB_CUDA(cudaMemcpyAsync(du.data(), dUat.p + (size_t)iw * 3 * npad, 3 * npad * sizeof(T), cudaMemcpyDeviceToHost, st));
+    QMCB_CUDA(cudaMemcpyAsync(d2.data(), d2Uat.p + (size_t)iw * npad, npad * sizeof(T), cudaMemcpyDeviceToHost, st));
+    sync();
+    for (int i = 0; i < N; ++i)
+    {
+      Uat_h[i]   = u[i];
+      d2Uat_h[i] = d2[i];
+      for (int d = 0; d < 3; ++d)
+        dUat_h[(size_t)d * N + i] = du[(size_t)d * npad + i];
+    }
+  }
+
+  // ---------------------------------------------------------------- device-resident VMC driver
+  void vmc_init(const qmcb_vmc_params* p) override
+  {
+    if (graph_exec)
+    {
+      cudaGraphExecDestroy(graph_exec);
+      graph_exec = nullptr;
+    }
+    std::memset(&drv, 0, sizeof(drv));
+    drv.nw = nw, drv.N = N;
+    // TauParams (QMCDrivers/TauParams.hpp:29-40), unit mass
+    drv.tauovermass = (T)p->tau * (T)1.0;
+    drv.oneover2tau = (T)(0.5 / drv.tauovermass);
+    drv.sqrttau     = (T)std::sqrt(drv.tauovermass);
+    drv.use_drift   = p->use_drift;
+    use_graph       = p->use_cuda_graph != 0;
+    A(deltas, (size_t)N * nw * 3);
+    A(drifts, (size_t)nw * 3);
+    A(delta_cur, (size_t)nw * 3);
+    A(n_acc, nw);
+    A(n_rej, nw);
+    A(accept_log, (size_t)N * nw);
+    drv.deltas = deltas.p, drv.drifts = drifts.p, drv.delta_cur = delta_cur.p, drv.grads_now = grads_tmp.p;
+    drv.accepted = accepted.p, drv.n_accept = n_acc.p, drv.n_reject = n_rej.p, drv.accept_log = nullptr;
+    // raw stream: one sweep consumes at most 2*ceil(3*nw*N/2) (Box-Muller) + nw*N (accept tests) outputs
+    const unsigned long long gcount = 3ull * nw * N;
+    sweep_backlog                   = 2 * ((gcount + 1) / 2) + (unsigned long long)nw * N;
+    unsigned long long ring = 1;
+    while (ring < 3 * sweep_backlog + 2 * 624)
+      ring <<= 1;
+    A(rng_state, 624);
+    A(rng_ring, ring);
+    A(rng_cnt, 2);
+    rng.state = rng_state.p, rng.ring = rng_ring.p, rng.gen = rng_cnt.p, rng.pos = rng_cnt.p + 1;
+    rng.ring_mask = (unsigned)(ring - 1);
+    mt19937_seed_kernel<<<1, 32, 0, st>>>(rng, p->seed);
+    QMCB_LAUNCH_CHECK();
+    mt19937_fill_kernel<<<1, 256, 0, st>>>(rng, 2 * sweep_backlog);
+    QMCB_LAUNCH_CHECK();
+    sync();
+    vmc_ready = true;
+  }
+
+  // enqueue one full sweep on `st` (st2 carries the RNG top-up and the Jastrow branch)
+  void enqueue_sweep(bool log_accept)
+  {
+    drv.accept_log = log_accept ? accept_log.p : nullptr;
+    // fork: top the raw stream up for the NEXT sweep on a side stream while this sweep runs.  The fill kernel may read a
+    // stale (smaller) consumption counter: it then generates less, but the invariant "at least one sweep's worth is
+    // available at sweep start" holds because it tops up to TWO sweeps' worth and a sweep consumes at most one.
+    QMCB_CUDA(cudaEventRecord(ev_rng, st));
+    QMCB_CUDA(cudaStreamWaitEvent(st3, ev_rng, 0));
+    mt19937_fill_kernel<<<1, 256, 0, st3>>>(rng, 2 * sweep_backlog);
+    QMCB_LAUNCH_CHECK();
+    QMCB_CUDA(cudaEventRecord(ev_rng_done, st3));
+    const unsigned long long gcount = 3ull * nw * N;
+    gauss_kernel<T><<<(unsigned)(((gcount + 1) / 2 + 255) / 256), 256, 0, st>>>(rng, deltas.p, gcount);
+    QMCB_LAUNCH_CHECK();
+    rng_advance_kernel<<<1, 32, 0, st>>>(rng, 2 * ((gcount + 1) / 2));
+    QMCB_LAUNCH_CHECK();
+    for (int ig = 0; ig < 2; ++ig)
+      for (int iat = first[ig]; iat < first[ig] + nel[ig]; ++iat)
+      {
+        const int row = iat - first[ig];
+        launch_prepare(ig, row, drv.use_drift ? det_grads.p : nullptr);
+        propose_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(drv, jas, iat, det_grads.p);
+        QMCB_LAUNCH_CHECK();
+        // Jastrow rows and spline gather only share the proposed positions: run them side by side
+        const bool jast = jas.has_j2 || jas.has_j1;
+        if (jast)
+        {
+          QMCB_CUDA(cudaEventRecord(ev_fork, st));
+          QMCB_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
+          jastrow_move_kernel<T><<<nw, JAS_TPB, 0, st2>>>(jas, iat);
+          QMCB_LAUNCH_CHECK();
+          QMCB_CUDA(cudaEventRecord(ev_join, st2));
+        }
+        launch_spline(ig, MODE_VGL, invRow[ig].p, det[ig].n, phi_vgl.p, rg.p, st);
+        if (jast)
+          QMCB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+        decide_kernel<T><<<1, std::min(1024, ((nw + 31) / 32) * 32), 0, st>>>(drv, jas, rng, iat, rg.p);
+        QMCB_LAUNCH_CHECK();
+        launch_accept(ig, row, accepted.p, rg.p, phi_vgl.p);
+        jastrow_accept_kernel<T><<<nw, JAS_TPB, 0, st>>>(jas, iat, accepted.p);
+        QMCB_LAUNCH_CHECK();
+      }
+    twf_complete_updates();
+    // RNG top-up branch joins here
+    QMCB_CUDA(cudaStreamWaitEvent(st, ev_rng_done, 0));
+  }
+
+  void vmc_sweep_async() override
+  {
+    if (!vmc_ready)
+      throw std::runtime_error("qmcb_vmc_init has not been called");
+    launch_sweep(false);
+  }
+
+  void launch_sweep(bool log_accept)
+  {
+    if (delay_count[0] != 0 || delay_count[1] != 0)
+      twf_complete_updates();
+    if (!use_graph)
+    {
+      enqueue_sweep(log_accept);
+      return;
+    }
+    if (!graph_exec || graph_logs != log_accept)
+    {
+      if (graph_exec)
+      {
+        cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+      }
+      // spline scratch must exist before capture (allocation is illegal while capturing): warm it with one evaluation
+      launch_spline(0, MODE_VGL, invRow[0].p, det[0].n, phi_vgl.p, rg.p, st);
+      if (nel[1] > 0)
+        launch_spline(1, MODE_VGL, invRow[1].p, det[1].n, phi_vgl.p, rg.p, st);
+      sync();
+      const unsigned long long before = g_launch_count.load();
+      cudaGraph_t graph;
+      QMCB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      enqueue_sweep(log_accept);
+      QMCB_CUDA(cudaStreamEndCapture(st, &graph));
+      QMCB_CUDA(cudaGraphInstantiate(&graph_exec, graph, 0));
+      QMCB_CUDA(cudaGraphDestroy(graph));
+      graph_logs       = log_accept;
+      launches_per_sweep = g_launch_count.load() - before;
+      g_launch_count.store(before); // captured, not yet executed
+    }
+    QMCB_CUDA(cudaGraphLaunch(graph_exec, st));
+    g_launch_count.fetch_add(launches_per_sweep);
+  }
+  unsigned long long launches_per_sweep = 0;
+
+  void vmc_sweep(int nsteps, uint8_t* log_host) override
+  {
+    if (!vmc_ready)
+      throw std::runtime_error("qmcb_vmc_init has not been called");
+    for (int s = 0; s < nsteps; ++s)
+    {
+      launch_sweep(log_host != nullptr);
+      if (log_host)
+      {
+        QMCB_CUDA(cudaMemcpyAsync(log_host + (size_t)s * N * nw, accept_log.p, (size_t)N * nw, cudaMemcpyDeviceToHost, st));
+        sync();
+      }
+    }
+    sync();
+  }
+  void vmc_counts(long long* na, long long* nr) override
+  {
+    QMCB_CUDA(cudaMemcpyAsync(na, n_acc.p, nw * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    QMCB_CUDA(cudaMemcpyAsync(nr, n_rej.p, nw * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    sync();
+  }
+};
+
+CrowdBase* make_crowd(const qmcb_system* sys, int nw)
+{
+  if (sys->precision == QMCB_MIXED)
+    return new Crowd<float>(sys, nw);
+  if (sys->precision == QMCB_FULL)
+    return new Crowd<double>(sys, nw);
+  throw std::runtime_error("unknown precision code");
+}
+
+} // namespace qmcb

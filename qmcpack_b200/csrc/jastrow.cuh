@@ -1,0 +1,426 @@
+// qmcpack_b200/csrc/jastrow.cuh -- distance-table rows, two-body and one-body B-spline Jastrow kernels (sm_100a).
+//
+// Replaces (reference paths under /root/reference/src):
+//   SoaDistanceTableAAOMPTarget::mw_move        Particle/SoaDistanceTableAAOMPTarget.h:265-371     (K17)
+//   DTD_BConds::computeDistancesOffload         Particle/Lattice/ParticleBConds3DSoa.h:141-168 (PPPO), :452-510 (PPPG)
+//   BsplineFunctor::mw_evaluateVGL / mw_updateVGL  QMCWaveFunctions/Jastrow/BsplineFunctor.cpp:26-131, :203-326   (K16)
+//   TwoBodyJastrow::mw_ratioGrad / mw_accept_rejectMove / recompute   Jastrow/TwoBodyJastrow.cpp:542-578, :631-664, :667-713
+//   J1OrbitalSoA ratioGrad / acceptMove / recompute   Jastrow/J1OrbitalSoA.h:136-185, :441-469 (host loop in the reference)
+// One CTA per walker; the five sums of a move are reduced with warp shuffles in a fixed order.  The temp/old rows and
+// the per-pair u, u'/r, u'' of the proposed row stay in HBM between the ratio and the accept kernels exactly like
+// mw_new_old_dist_displ / mw_cur_allu of the reference (TwoBodyJastrow.cpp:63-86).
+#pragma once
+#include "common.cuh"
+
+namespace qmcb
+{
+template<typename RT>
+struct FunctorDev
+{
+  const RT* coefs;
+  RT DeltaRInv, rcut;
+  int max_index;
+};
+
+template<typename RT>
+struct CellDev
+{
+  int ortho;
+  RT L[3], Linv[3];
+  RT r[9], g[9];
+  RT corners[3][8];
+};
+
+template<typename RT>
+struct JastrowDev
+{
+  int N, npad, n_up, nw;
+  CellDev<RT> cell;
+  // J2
+  int has_j2;
+  FunctorDev<RT> F2[4];     // [group(iat)*2 + group(j)]
+  RT* rsoa;                 // [nw][3][npad]  committed positions
+  RT* newpos;               // [nw][3]
+  RT* rows;                 // [2][nw][4][npad]  new then old: r, dx, dy, dz
+  RT* cur_allu;             // [nw][3][npad]
+  RT* j2_vgl;               // [nw][5]  cur_Uat, grad(3), -lapl
+  RT* Uat;                  // [nw][npad]
+  RT* dUat;                 // [nw][3][npad]
+  RT* d2Uat;                // [nw][npad]
+  double* j2_log;           // [nw]
+  // J1
+  int has_j1, nions, npad_ion;
+  const RT* ion_rsoa;       // [3][npad_ion]
+  const int* ion_grp;       // [nions]
+  FunctorDev<RT> F1[8];
+  RT* j1_cur;               // [nw][5]  curAt, curGrad(3), curLap
+  RT* Vat;                  // [nw][N]
+  RT* Grad1;                // [nw][3][N]
+  RT* Lap1;                 // [nw][N]
+  double* j1_log;           // [nw]
+};
+
+#ifdef __CUDACC__
+constexpr int JAS_TPB = 256;
+
+// ref: Numerics/SplineBound.hpp:37-62 with T = RT
+template<typename RT>
+__device__ __forceinline__ void spline_bound_rt(RT x, int nmax, int& ind, RT& dx)
+{
+  if (x < 0)
+  {
+    ind = 0;
+    dx  = RT(0);
+  }
+  else
+  {
+    RT ipart;
+    dx  = modf(x, &ipart);
+    ind = (int)ipart;
+    if (ind > nmax)
+    {
+      ind = nmax;
+      dx  = RT(1) - (sizeof(RT) == 4 ? RT(1.1920929e-07f) : RT(2.220446049250313e-16));
+    }
+  }
+}
+
+// ref: BsplineFunctor.h:254-285 evaluate_impl; returns u, sets du = u'/r and d2u = u'' (zero beyond the cutoff)
+template<typename RT>
+__device__ __forceinline__ RT functor_eval(const FunctorDev<RT>& f, RT r, RT& du_over_r, RT& d2u)
+{
+  RT u(0);
+  du_over_r = RT(0);
+  d2u       = RT(0);
+  if (f.coefs != nullptr && r < f.rcut)
+  {
+    RT rr = r * f.DeltaRInv;
+    int i;
+    RT t;
+    spline_bound_rt(rr, f.max_index, i, t);
+    const RT c0 = f.coefs[i], c1 = f.coefs[i + 1], c2 = f.coefs[i + 2], c3 = f.coefs[i + 3];
+    d2u = f.DeltaRInv * f.DeltaRInv *
+        (c0 * (RT(-1.0) * t + RT(1.0)) + c1 * (RT(3.0) * t + RT(-2.0)) + c2 * (RT(-3.0) * t + RT(1.0)) +
+         c3 * (RT(1.0) * t + RT(0.0)));
+    RT dudr = f.DeltaRInv *
+        (c0 * ((RT(-0.5) * t + RT(1.0)) * t + RT(-0.5)) + c1 * ((RT(1.5) * t + RT(-2.0)) * t + RT(0.0)) +
+         c2 * ((RT(-1.5) * t + RT(1.0)) * t + RT(0.5)) + c3 * ((RT(0.5) * t + RT(0.0)) * t + RT(0.0)));
+    u = (c0 * (((RT(-1.0 / 6.0) * t + RT(3.0 / 6.0)) * t + RT(-3.0 / 6.0)) * t + RT(1.0 / 6.0)) +
+         c1 * (((RT(3.0 / 6.0) * t + RT(-6.0 / 6.0)) * t + RT(0.0 / 6.0)) * t + RT(4.0 / 6.0)) +
+         c2 * (((RT(-3.0 / 6.0) * t + RT(3.0 / 6.0)) * t + RT(3.0 / 6.0)) * t + RT(1.0 / 6.0)) +
+         c3 * (((RT(1.0 / 6.0) * t + RT(0.0 / 6.0)) * t + RT(0.0 / 6.0)) * t + RT(0.0 / 6.0)));
+    du_over_r = dudr * (RT(1) / r);
+  }
+  return u;
+}
+
+// minimum-image displacement src - pos.  ref: ParticleBConds3DSoa.h:141-168 (ortho), :452-510 (general)
+template<typename RT>
+__device__ __forceinline__ void min_image(const CellDev<RT>& C, const RT pos[3], RT px, RT py, RT pz, int iel, int flip_ind,
+                                          RT& rr, RT& dx, RT& dy, RT& dz)
+{
+  if (C.ortho)
+  {
+    const RT x = (px - pos[0]) * C.Linv[0];
+    const RT y = (py - pos[1]) * C.Linv[1];
+    const RT z = (pz - pos[2]) * C.Linv[2];
+    dx         = C.L[0] * (x - round(x));
+    dy         = C.L[1] * (y - round(y));
+    dz         = C.L[2] * (z - round(z));
+    rr         = sqrt(dx * dx + dy * dy + dz * dz);
+  }
+  else
+  {
+    const RT flip    = iel < flip_ind ? RT(1) : RT(-1);
+    const RT displ_0 = (px - pos[0]) * flip;
+    const RT displ_1 = (py - pos[1]) * flip;
+    const RT displ_2 = (pz - pos[2]) * flip;
+    const RT ar_0    = -floor(displ_0 * C.g[0] + displ_1 * C.g[3] + displ_2 * C.g[6]);
+    const RT ar_1    = -floor(displ_0 * C.g[1] + displ_1 * C.g[4] + displ_2 * C.g[7]);
+    const RT ar_2    = -floor(displ_0 * C.g[2] + displ_1 * C.g[5] + displ_2 * C.g[8]);
+    const RT delx    = displ_0 + ar_0 * C.r[0] + ar_1 * C.r[3] + ar_2 * C.r[6];
+    const RT dely    = displ_1 + ar_0 * C.r[1] + ar_1 * C.r[4] + ar_2 * C.r[7];
+    const RT delz    = displ_2 + ar_0 * C.r[2] + ar_1 * C.r[5] + ar_2 * C.r[8];
+    RT rmin          = delx * delx + dely * dely + delz * delz;
+    int ic           = 0;
+#pragma unroll
+    for (int c = 1; c < 8; ++c)
+    {
+      const RT x  = delx + C.corners[0][c];
+      const RT y  = dely + C.corners[1][c];
+      const RT z  = delz + C.corners[2][c];
+      const RT r2 = x * x + y * y + z * z;
+      ic          = (r2 < rmin) ? c : ic;
+      rmin        = (r2 < rmin) ? r2 : rmin;
+    }
+    rr = sqrt(rmin);
+    dx = flip * (delx + C.corners[0][ic]);
+    dy = flip * (dely + C.corners[1][ic]);
+    dz = flip * (delz + C.corners[2][ic]);
+  }
+}
+
+// one-body sums at position pos: at = sum u, lap = sum(u'' + 2u'/r), grad = sum (u'/r) d   (J1OrbitalSoA.h:136-185)
+// must be called by every thread of the CTA
+template<typename RT>
+__device__ __forceinline__ void j1_sums(const JastrowDev<RT>& J, const RT pos[3], RT out[5], RT* red)
+{
+  RT acc[5] = {RT(0), RT(0), RT(0), RT(0), RT(0)};
+  for (int j = threadIdx.x; j < J.nions; j += blockDim.x)
+  {
+    RT r, dx, dy, dz, du, d2u;
+    min_image(J.cell, pos, J.ion_rsoa[j], J.ion_rsoa[J.npad_ion + j], J.ion_rsoa[2 * J.npad_ion + j], j, 0, r, dx, dy, dz);
+    const RT u = functor_eval(J.F1[J.ion_grp[j]], r, du, d2u);
+    acc[0] += u;
+    acc[1] += du * dx;
+    acc[2] += du * dy;
+    acc[3] += du * dz;
+    acc[4] += d2u + RT(2) * du;
+  }
+  block_sum<RT, 5>(acc, red);
+#pragma unroll
+  for (int e = 0; e < 5; ++e)
+    out[e] = acc[e];
+}
+
+// ---- proposed move: temp + old distance rows, J2 cur_allu / vgl, J1 current sums.  grid = nw
+template<typename RT>
+__global__ void __launch_bounds__(JAS_TPB) jastrow_move_kernel(const JastrowDev<RT> J, const int iat)
+{
+  __shared__ RT red[5 * 32];
+  const int iw = blockIdx.x, tid = threadIdx.x, N = J.N, np = J.npad;
+  const RT* rs = J.rsoa + (size_t)iw * 3 * np;
+  RT pos[3]    = {J.newpos[3 * iw], J.newpos[3 * iw + 1], J.newpos[3 * iw + 2]};
+  if (J.has_j2)
+  {
+    RT old[3]   = {rs[iat], rs[np + iat], rs[2 * np + iat]};
+    RT* rnew    = J.rows + (size_t)iw * 4 * np;
+    RT* rold    = J.rows + ((size_t)J.nw + iw) * 4 * np;
+    RT* cur     = J.cur_allu + (size_t)iw * 3 * np;
+    const int gi = (iat < J.n_up ? 0 : 1) * 2;
+    RT acc[5]   = {RT(0), RT(0), RT(0), RT(0), RT(0)};
+    for (int j = tid; j < N; j += JAS_TPB)
+    {
+      const RT px = rs[j], py = rs[np + j], pz = rs[2 * np + j];
+      RT r, dx, dy, dz;
+      min_image(J.cell, pos, px, py, pz, j, iat, r, dx, dy, dz);
+      rnew[j]          = r;
+      rnew[np + j]     = dx;
+      rnew[2 * np + j] = dy;
+      rnew[3 * np + j] = dz;
+      RT ro, ox, oy, oz;
+      min_image(J.cell, old, px, py, pz, j, iat, ro, ox, oy, oz);
+      rold[j]          = (j == iat) ? (sizeof(RT) == 4 ? RT(3.402823466e+38f) : RT(1.7976931348623157e+308)) : ro;
+      rold[np + j]     = ox;
+      rold[2 * np + j] = oy;
+      rold[3 * np + j] = oz;
+      if (j != iat)
+      {
+        RT du, d2u;
+        const RT u      = functor_eval(J.F2[gi + (j < J.n_up ? 0 : 1)], r, du, d2u);
+        cur[j]          = u;
+        cur[np + j]     = du;
+        cur[2 * np + j] = d2u;
+        acc[0] += u;
+        acc[1] += du * dx;
+        acc[2] += du * dy;
+        acc[3] += du * dz;
+        acc[4] += d2u + RT(2) * du;
+      }
+    }
+    block_sum<RT, 5>(acc, red);
+    if (tid == 0)
+    {
+      RT* vgl = J.j2_vgl + (size_t)iw * 5;
+      vgl[0]  = acc[0];
+      vgl[1]  = acc[1];
+      vgl[2]  = acc[2];
+      vgl[3]  = acc[3];
+      vgl[4]  = -acc[4];
+    }
+  }
+  if (J.has_j1)
+  {
+    RT o[5];
+    j1_sums(J, pos, o, red);
+    if (tid < 5)
+      J.j1_cur[(size_t)iw * 5 + tid] = o[tid];
+  }
+}
+
+// ---- accept: J2 per-particle sums (BsplineFunctor.cpp:262-324), J1 commit, position commit.  grid = nw
+template<typename RT>
+__global__ void __launch_bounds__(JAS_TPB)
+    jastrow_accept_kernel(const JastrowDev<RT> J, const int iat, const unsigned char* accepted)
+{
+  const int iw = blockIdx.x, tid = threadIdx.x, N = J.N, np = J.npad;
+  if (!accepted[iw])
+    return;
+  if (J.has_j2)
+  {
+    const RT* rnew = J.rows + (size_t)iw * 4 * np;
+    const RT* rold = J.rows + ((size_t)J.nw + iw) * 4 * np;
+    const RT* cur  = J.cur_allu + (size_t)iw * 3 * np;
+    RT* Uat        = J.Uat + (size_t)iw * np;
+    RT* dU         = J.dUat + (size_t)iw * 3 * np;
+    RT* d2U        = J.d2Uat + (size_t)iw * np;
+    const RT* vgl  = J.j2_vgl + (size_t)iw * 5;
+    const int gi   = (iat < J.n_up ? 0 : 1) * 2;
+    const RT Uold_iat = Uat[iat];
+    __syncthreads();
+    for (int j = tid; j < N; j += JAS_TPB)
+    {
+      if (j == iat)
+        continue;
+      RT du, d2u;
+      const RT ro = rold[j];
+      const RT u  = functor_eval(J.F2[gi + (j < J.n_up ? 0 : 1)], ro, du, d2u);
+      const RT cu = cur[j], cdu = cur[np + j], cd2 = cur[2 * np + j];
+      Uat[j] += cu - u;
+      dU[j] -= rnew[np + j] * cdu - rold[np + j] * du;
+      dU[np + j] -= rnew[2 * np + j] * cdu - rold[2 * np + j] * du;
+      dU[2 * np + j] -= rnew[3 * np + j] * cdu - rold[3 * np + j] * du;
+      d2U[j] -= cd2 + RT(2) * cdu - (d2u + RT(2) * du);
+    }
+    if (tid == 0)
+    {
+      J.j2_log[iw] += (double)(Uold_iat - vgl[0]); // TwoBodyJastrow.cpp:656-659
+      Uat[iat]         = vgl[0];
+      dU[iat]          = vgl[1];
+      dU[np + iat]     = vgl[2];
+      dU[2 * np + iat] = vgl[3];
+      d2U[iat]         = vgl[4];
+    }
+  }
+  if (J.has_j1 && tid == 0)
+  {
+    const RT* cur = J.j1_cur + (size_t)iw * 5;
+    RT* Vat       = J.Vat + (size_t)iw * N;
+    J.j1_log[iw] += (double)(Vat[iat] - cur[0]); // J1OrbitalSoA.h:463
+    Vat[iat]                                  = cur[0];
+    J.Grad1[((size_t)iw * 3 + 0) * N + iat]   = cur[1];
+    J.Grad1[((size_t)iw * 3 + 1) * N + iat]   = cur[2];
+    J.Grad1[((size_t)iw * 3 + 2) * N + iat]   = cur[3];
+    J.Lap1[(size_t)iw * N + iat]              = cur[4];
+  }
+  // ParticleSet::mw_accept_rejectMove (ParticleSet.cpp:717-758): commit the position
+  if (tid < 3)
+    J.rsoa[(size_t)iw * 3 * np + tid * np + iat] = J.newpos[3 * iw + tid];
+}
+
+// ---- from scratch (TwoBodyJastrow.cpp:667-713 lower-triangle form; J1OrbitalSoA.h:237-250).  grid = nw.
+// The per-particle sums are accumulated row by row exactly like the reference (row iat touches j < iat).
+template<typename RT>
+__global__ void __launch_bounds__(JAS_TPB) jastrow_recompute_kernel(const JastrowDev<RT> J)
+{
+  __shared__ RT red[5 * 32];
+  const int iw = blockIdx.x, tid = threadIdx.x, N = J.N, np = J.npad;
+  const RT* rs = J.rsoa + (size_t)iw * 3 * np;
+  if (J.has_j2)
+  {
+    RT* Uat = J.Uat + (size_t)iw * np;
+    RT* dU  = J.dUat + (size_t)iw * 3 * np;
+    RT* d2U = J.d2Uat + (size_t)iw * np;
+    for (int j = tid; j < np; j += JAS_TPB)
+    {
+      Uat[j] = RT(0);
+      d2U[j] = RT(0);
+      dU[j] = dU[np + j] = dU[2 * np + j] = RT(0);
+    }
+    __syncthreads();
+    for (int iat = 0; iat < N; ++iat)
+    {
+      const RT pos[3] = {rs[iat], rs[np + iat], rs[2 * np + iat]};
+      const int gi    = (iat < J.n_up ? 0 : 1) * 2;
+      RT acc[5]       = {RT(0), RT(0), RT(0), RT(0), RT(0)};
+      for (int j = tid; j < iat; j += JAS_TPB)
+      {
+        RT r, dx, dy, dz, du, d2u;
+        min_image(J.cell, pos, rs[j], rs[np + j], rs[2 * np + j], j, iat, r, dx, dy, dz);
+        const RT u = functor_eval(J.F2[gi + (j < J.n_up ? 0 : 1)], r, du, d2u);
+        acc[0] += u;
+        acc[1] += du * dx;
+        acc[2] += du * dy;
+        acc[3] += du * dz;
+        acc[4] += d2u + RT(2) * du;
+        Uat[j] += u;
+        d2U[j] -= d2u + RT(2) * du;
+        dU[j] -= du * dx;
+        dU[np + j] -= du * dy;
+        dU[2 * np + j] -= du * dz;
+      }
+      block_sum<RT, 5>(acc, red);
+      if (tid == 0)
+      {
+        Uat[iat]         = acc[0];
+        dU[iat]          = acc[1];
+        dU[np + iat]     = acc[2];
+        dU[2 * np + iat] = acc[3];
+        d2U[iat]         = -acc[4];
+      }
+      __syncthreads();
+    }
+    // log_value = -0.5 * sum Uat (TwoBodyJastrow.cpp:769-781)
+    double lv[1] = {0.0};
+    for (int j = tid; j < N; j += JAS_TPB)
+      lv[0] -= 0.5 * (double)Uat[j];
+    __shared__ double dred[32];
+    block_sum<double, 1>(lv, dred);
+    if (tid == 0)
+      J.j2_log[iw] = lv[0];
+  }
+  if (J.has_j1)
+  {
+    double lv = 0.0;
+    for (int iat = 0; iat < N; ++iat)
+    {
+      const RT pos[3] = {rs[iat], rs[np + iat], rs[2 * np + iat]};
+      RT o[5];
+      j1_sums(J, pos, o, red);
+      if (tid == 0)
+      {
+        J.Vat[(size_t)iw * N + iat]             = o[0];
+        J.Grad1[((size_t)iw * 3 + 0) * N + iat] = o[1];
+        J.Grad1[((size_t)iw * 3 + 1) * N + iat] = o[2];
+        J.Grad1[((size_t)iw * 3 + 2) * N + iat] = o[3];
+        J.Lap1[(size_t)iw * N + iat]            = o[4];
+        lv -= (double)o[0];
+      }
+    }
+    if (tid == 0)
+      J.j1_log[iw] = lv;
+  }
+}
+
+// G += dUat, L += d2Uat (J2);  G += Grad, L -= Lap (J1).   grid = (ceil(N/256), nw)
+template<typename RT>
+__global__ void jastrow_add_gl_kernel(const JastrowDev<RT> J, RT* Gd, RT* Ld)
+{
+  const int iw = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x, N = J.N, np = J.npad;
+  if (i >= N)
+    return;
+  RT g[3] = {RT(0), RT(0), RT(0)}, l(0);
+  if (J.has_j2)
+  {
+    const RT* dU = J.dUat + (size_t)iw * 3 * np;
+    g[0] += dU[i];
+    g[1] += dU[np + i];
+    g[2] += dU[2 * np + i];
+    l += J.d2Uat[(size_t)iw * np + i];
+  }
+  if (J.has_j1)
+  {
+    g[0] += J.Grad1[((size_t)iw * 3 + 0) * N + i];
+    g[1] += J.Grad1[((size_t)iw * 3 + 1) * N + i];
+    g[2] += J.Grad1[((size_t)iw * 3 + 2) * N + i];
+    l -= J.Lap1[(size_t)iw * N + i];
+  }
+  RT* go = Gd + ((size_t)iw * N + i) * 3;
+  go[0] += g[0];
+  go[1] += g[1];
+  go[2] += g[2];
+  Ld[(size_t)iw * N + i] += l;
+}
+#endif
+
+} // namespace qmcb

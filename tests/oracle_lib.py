@@ -76,8 +76,10 @@ class Oracle:
         L.orc_aligned_size.argtypes = [C.c_int, C.c_long]
         L.orc_vmc_create.restype = C.c_void_p
         L.orc_vmc_create.argtypes = [C.POINTER(VMCParams)]
-        for name in ("orc_du_create_d", "orc_du_create_f"):
+        for name in ("orc_du_create_d", "orc_du_create_f", "orc_rng_create"):
             getattr(L, name).restype = C.c_void_p
+        L.orc_rng_next.restype = C.c_double
+        L.orc_rng_next.argtypes = [C.c_void_p]
         self.is_reference = bool(L.orc_is_reference_build())
 
     # -- helpers
@@ -268,8 +270,33 @@ class Oracle:
         getattr(self.lib, "orc_rng_gauss_" + self.suf(dtype))(C.c_uint32(seed), C.c_int(n), _p(out))
         return out
 
+    def rng(self, seed):
+        return OracleRng(self, seed)
+
     def vmc(self, system, **kw):
         return OracleVMC(self, system, **kw)
+
+
+class OracleRng:
+    """Stateful StdRandom<double> (std::mt19937 + boost-style uniform) with the reference's Box-Muller."""
+
+    def __init__(self, orc, seed):
+        self.o = orc
+        self.h = C.c_void_p(orc.lib.orc_rng_create(C.c_uint32(seed)))
+
+    def __del__(self):
+        try:
+            self.o.lib.orc_rng_destroy(self.h)
+        except Exception:
+            pass
+
+    def uniform(self):
+        return self.o.lib.orc_rng_next(self.h)
+
+    def gauss(self, n, dtype=np.float64):
+        out = np.zeros(n, dtype)
+        getattr(self.o.lib, "orc_rng_gauss_next_" + self.o.suf(dtype))(self.h, C.c_int(n), _p(out))
+        return out
 
 
 class DelayedUpdateHandle:

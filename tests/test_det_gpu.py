@@ -1,0 +1,135 @@
+"""GPU parity: delayed-update determinant engine through the C ABI vs the CPU oracle, following the procedure of the
+reference's test_DiracDeterminantBatched.cpp:262-470 (fixed matrices instead of a spline SPOSet: "FakeSPO")."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from qmcpack_b200 import api as a, build
+    build.build()
+    a.init(0)
+    return a
+
+
+def tiny_system(n, dt):
+    """a crowd needs an SPOSet handle per determinant; the determinant tests feed orbital rows directly"""
+    from qmcpack_b200.workload import random_table
+    t = random_table((4, 4, 4), n, dt, seed=1)
+    return dict(n_up=n, n_dn=n, lattice=np.eye(3) * 4.0, coefs=[t, t])
+
+
+def test_reference_3x3_literals(api):
+    """test_DiracMatrix.cpp:58-81 and :315-366 literals through the CUDA engine (delay rank 1)"""
+    a = np.array([[2.3, 4.5, 2.6], [0.5, 8.5, 3.3], [1.8, 4.4, 4.9]])
+    crowd = api.Crowd(tiny_system(3, np.float64), nw=2, delay_rank=1)
+    psiM = np.stack([a.T, a.T])  # the test inverts a_T: a_inv = (a_T^-1)^T
+    crowd.det_recompute_from_matrices(0, psiM)
+    inv, logdet = crowd.det_mw_completeUpdates(0)
+    b = np.array([[0.6159749342, -0.2408954682, -0.1646081192], [0.07923894288, 0.1496231042, -0.1428117337],
+                  [-0.2974298429, -0.04586322768, 0.3927890292]])
+    assert inv[0] == pytest.approx(b, rel=1e-8)
+    assert logdet[0, 0] == pytest.approx(3.78518913425)
+    v = np.array([1.9, 2.0, 3.1])
+    phi = np.zeros((5, 2, 3))
+    phi[0, :, :] = v
+    crowd.det_set_phi_vgl(0, phi)
+    ratios, _ = crowd.det_mw_ratioGrad(0, 0, from_phi=True)
+    assert ratios[0] == pytest.approx(0.178276269185)
+    crowd.det_mw_accept_rejectRow(0, 0, [1, 0])
+    inv, logdet = crowd.det_mw_completeUpdates(0)
+    b2 = np.array([[3.455170657, -1.35124809, -0.9233316353], [0.05476311768, 0.1591951095, -0.1362710138],
+                   [-2.235099338, 0.7119205298, 0.9105960265]])
+    assert inv[0] == pytest.approx(b2, rel=1e-8)
+    assert inv[1] == pytest.approx(b, rel=1e-8)  # rejected walker untouched
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n,k", [(24, 1), (24, 2), (24, 8), (70, 16), (192, 32), (130, 64)])
+def test_delayed_update_sequence_matches_oracle(api, orc, dt, n, k):
+    """random accept/reject sequence, every walker with its own flags: inverse rows, ratios, gradients at every move and
+    the flushed inverse / log-determinant at the end must match the oracle's batched engine (pseudo-accepts included)
+    and a fresh inverse of the explicitly updated matrix."""
+    nw = 5
+    rng = np.random.default_rng(100 + n + k)
+    crowd = api.Crowd(tiny_system(n, dt), nw=nw, delay_rank=k)
+    psiM = (2 * np.eye(n) + 0.4 * rng.normal(size=(nw, n, n))).astype(dt)
+    dpsiM = rng.normal(size=(nw, n, n, 3)).astype(dt)
+    d2psiM = rng.normal(size=(nw, n, n)).astype(dt)
+    crowd.det_recompute_from_matrices(1, psiM, dpsiM, d2psiM)
+    lda = orc.aligned_size(dt, n)
+    ainv, logdet, eng = [], [], []
+    for iw in range(nw):
+        a, ld = orc.invert_transpose(psiM[iw], lda=lda)
+        ainv.append(a)
+        logdet.append(ld.real)
+        eng.append(orc.du(n, k, dt))
+    inv0, ld0 = crowd.det_mw_completeUpdates(1)
+    tol = 1e-8 if dt == np.float64 else 2e-4
+    for iw in range(nw):
+        assert np.abs(inv0[iw] - ainv[iw][:, :n]).max() < tol * np.abs(ainv[iw]).max()
+        assert ld0[iw, 0] == pytest.approx(logdet[iw], rel=1e-10)
+    cur_dpsiM = dpsiM.copy()
+    nmoves = 2 * n + 3
+    for move in range(nmoves):
+        row = move % n
+        grads_now = crowd.det_mw_evalGrad(1, row)
+        rows_gpu = crowd.det_mw_getInvRow(1, row)
+        phi = np.zeros((5, nw, n), dt)
+        phi[0] = (2 * np.eye(n)[row] + 0.4 * rng.normal(size=(nw, n))).astype(dt)
+        phi[1:] = rng.normal(size=(4, nw, n)).astype(dt)
+        crowd.det_set_phi_vgl(1, phi)
+        ratios, grads = crowd.det_mw_ratioGrad(1, row, from_phi=True)
+        acc = (rng.random(nw) < 0.6).astype(np.uint8)
+        for iw in range(nw):
+            r = eng[iw].get_inv_row(ainv[iw], row)
+            assert np.abs(rows_gpu[iw] - r).max() < tol * max(1.0, np.abs(r).max())
+            g_ref = r.astype(np.float64) @ cur_dpsiM[iw, row].astype(np.float64)
+            assert np.abs(grads_now[iw] - g_ref).max() < tol * 50 * max(1.0, np.abs(g_ref).max())
+            ratio_ref = float(r.astype(np.float64) @ phi[0, iw].astype(np.float64))
+            assert ratios[iw] == pytest.approx(ratio_ref, rel=tol * 10, abs=tol * 10)
+            gn_ref = (r.astype(np.float64) @ phi[1:4, iw].astype(np.float64).T) / ratio_ref
+            assert np.abs(grads[iw] - gn_ref).max() < tol * 100 * max(1.0, np.abs(gn_ref).max())
+            if acc[iw]:
+                eng[iw].accept_row(ainv[iw], row, phi[0, iw], float(ratios[iw]))
+                psiM[iw, row] = phi[0, iw]
+                cur_dpsiM[iw, row] = phi[1:4, iw].T
+                logdet[iw] += np.log(abs(float(ratios[iw])))
+            elif k > 1:
+                eng[iw].pseudo_accept_row(ainv[iw], row)
+        crowd.det_mw_accept_rejectRow(1, row, acc)
+        assert crowd.det_delay_count(1) == (move + 1) % k
+    inv, ld = crowd.det_mw_completeUpdates(1)
+    for iw in range(nw):
+        eng[iw].update_inv_mat(ainv[iw])
+        scale = np.abs(ainv[iw]).max()
+        assert np.abs(inv[iw] - ainv[iw][:, :n]).max() < tol * scale
+        fresh, fld = orc.invert_transpose(psiM[iw], lda=lda)
+        assert np.abs(inv[iw] - fresh[:, :n]).max() < (1e-8 if dt == np.float64 else 5e-3) * scale
+        assert ld[iw, 0] == pytest.approx(fld.real, rel=1e-9 if dt == np.float64 else 1e-4, abs=1e-5)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_determinant_from_spline_recompute(api, orc, dt):
+    """mw_recompute through the spline SPOSet: psiM rows are orbital values at the electron positions; inverse and
+    log-determinant against the oracle's LU."""
+    from qmcpack_b200.workload import make_system, initial_positions
+    s = make_system(N=32, M=6, dtype=dt, L=5.0, with_j1=False, with_j2=False)
+    nw = 3
+    crowd = api.Crowd(s, nw=nw, delay_rank=4)
+    R = initial_positions(s, nw)
+    crowd.set_positions(R)
+    crowd.mw_recompute()
+    G = np.linalg.inv(s["lattice"])
+    for spin in (0, 1):
+        n = 16
+        inv, ld = crowd.det_mw_completeUpdates(spin)
+        for iw in range(nw):
+            pos = R[iw, spin * 16:(spin + 1) * 16]
+            psiM, _, _ = orc.r2r_vgl(s["coefs"][spin], G, n, pos)
+            ref, rld = orc.invert_transpose(np.ascontiguousarray(psiM))
+            tol = 1e-8 if dt == np.float64 else 5e-3
+            assert np.abs(inv[iw] - ref).max() < tol * np.abs(ref).max()
+            assert ld[iw, 0] == pytest.approx(rld.real, rel=1e-9 if dt == np.float64 else 1e-4, abs=1e-4)
