@@ -424,6 +424,12 @@ int orc_vmc_sweep(void* hv, int nsteps, uint8_t* accept_log, double* seconds)
       *seconds = std::chrono::duration<double>(t1 - t0).count();
   });
 }
+// teacher-forced variant: accept flags imposed ([nsteps][N][nw]); ratio_log (optional) receives every move's ratio
+int orc_vmc_sweep_forced(void* hv, int nsteps, const uint8_t* forced, double* ratio_log)
+{
+  auto* h = static_cast<VMCHandle*>(hv);
+  return guarded([&] { VMC_DISPATCH(h, v.sweep(nsteps, false, forced, ratio_log)); });
+}
 int orc_vmc_get_positions(void* hv, double* R)
 {
   auto* h = static_cast<VMCHandle*>(hv);

@@ -295,7 +295,11 @@ struct VMC
   }
 
   // one sweep step for one crowd
-  void advanceCrowd(Crowd& cr, uint8_t* acc_log /* [N][nw] or null */)
+  // forced (optional, [N][nw]): accept flags imposed from outside ("teacher forcing" for mixed-precision parity: the
+  // uniform is still drawn under the reference's rule so that the stream stays aligned); ratio_log (optional, [N][nw]):
+  // the total wavefunction ratio of every proposed move
+  void advanceCrowd(Crowd& cr, uint8_t* acc_log /* [N][nw] or null */, const uint8_t* forced = nullptr,
+                    double* ratio_log = nullptr)
   {
     const int cw = cr.w1 - cr.w0;
     if (cw == 0)
@@ -440,6 +444,10 @@ struct VMC
             isAccepted[i] = 1;
           else
             isAccepted[i] = 0;
+          if (forced)
+            isAccepted[i] = forced[(size_t)iat * nw + cr.w0 + i];
+          if (ratio_log)
+            ratio_log[(size_t)iat * nw + cr.w0 + i] = ratios[i];
         }
 
         // TWF::mw_accept_rejectMove -> determinant, J2, J1; then ParticleSet::mw_accept_rejectMove
@@ -503,16 +511,18 @@ struct VMC
       }
   }
 
-  void sweep(int nsteps, bool log_accept)
+  void sweep(int nsteps, bool log_accept, const uint8_t* forced = nullptr, double* ratio_log = nullptr)
   {
     if (log_accept)
       accept_log.assign((size_t)nsteps * N * nw, 0);
     for (int step = 0; step < nsteps; ++step)
     {
-      uint8_t* lg = log_accept ? accept_log.data() + (size_t)step * N * nw : nullptr;
+      uint8_t* lg       = log_accept ? accept_log.data() + (size_t)step * N * nw : nullptr;
+      const uint8_t* fc = forced ? forced + (size_t)step * N * nw : nullptr;
+      double* rl        = ratio_log ? ratio_log + (size_t)step * N * nw : nullptr;
 #pragma omp parallel for schedule(static, 1)
       for (int c = 0; c < (int)crowds.size(); ++c)
-        advanceCrowd(crowds[c], lg);
+        advanceCrowd(crowds[c], lg, fc, rl);
     }
   }
 

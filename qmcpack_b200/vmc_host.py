@@ -23,7 +23,7 @@ def get_drift(tau, g, RT):
     return (g * sc[:, None]).astype(RT)
 
 
-def advance_walkers(crowd, rng, tau=0.3, use_drift=True, log_accept=None):
+def advance_walkers(crowd, rng, tau=0.3, use_drift=True, log_accept=None, log_ratio=None):
     """One sweep (sub_steps = 1) over all electrons of all walkers of `crowd`; returns the number of accepted moves."""
     RT = crowd.T
     nw, N = crowd.nw, crowd.N
@@ -57,5 +57,7 @@ def advance_walkers(crowd, rng, tau=0.3, use_drift=True, log_accept=None):
         n_acc += int(accepted.sum())
         if log_accept is not None:
             log_accept[iat] = accepted
+        if log_ratio is not None:
+            log_ratio[iat] = ratios
     crowd.mw_completeUpdates()
     return n_acc

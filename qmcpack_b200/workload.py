@@ -60,16 +60,59 @@ def random_table(M, n_spl, dtype, seed, scale=0.5):
     return c
 
 
+def pw_table(M, n_spl, dtype, seed):
+    """Smooth synthetic orbitals: a random ORTHOGONAL mixture (seeded) of the n_spl lowest plane-wave functions
+    {1, cos(G.r), sin(G.r)} of the cell, sampled on the coefficient grid and used directly as B-spline coefficients.
+    Same shape, strides and access pattern as any other table -- the gather kernels never look at the values -- but the
+    Slater matrices are as well conditioned as a free-electron determinant's, so mixed-precision VMC stays meaningful
+    (i.i.d. coefficients at 0.3 bohr spacing give a white-noise wavefunction whose inverse loses all digits within one
+    sweep even in FP64)."""
+    if np.isscalar(M):
+        M = (M, M, M)
+    npad = aligned_size(dtype, n_spl)
+    rng = np.random.default_rng(seed)
+    # integer reciprocal vectors, one of each +-G pair, sorted by |G|^2
+    gmax = 1
+    while (2 * gmax + 1) ** 3 < 2 * n_spl + 8:
+        gmax += 1
+    g = np.array([(i, j, k) for i in range(-gmax, gmax + 1) for j in range(-gmax, gmax + 1)
+                  for k in range(-gmax, gmax + 1)])
+    keep = [(i, j, k) for (i, j, k) in g if (i, j, k) > (0, 0, 0)]
+    keep.sort(key=lambda t: (t[0] ** 2 + t[1] ** 2 + t[2] ** 2, t))
+    funcs = [((0, 0, 0), 0)]
+    for t in keep:
+        funcs.append((t, 0))
+        funcs.append((t, 1))
+        if len(funcs) >= n_spl:
+            break
+    funcs = funcs[:n_spl]
+    gv = np.array([f[0] for f in funcs], np.float64)
+    is_sin = np.array([f[1] for f in funcs], bool)
+    Q, _ = np.linalg.qr(rng.normal(size=(n_spl, n_spl)))
+    Q = (Q * np.sqrt(2.0)).astype(np.float32 if np.dtype(dtype) == np.float32 else np.float64)
+    c = aligned_zeros((M[0] + 3, M[1] + 3, M[2] + 3, npad), dtype)
+    ys, zs = np.meshgrid(np.arange(M[1] + 3) / M[1], np.arange(M[2] + 3) / M[2], indexing="ij")
+    pyz = 2 * np.pi * (ys.reshape(-1, 1) * gv[None, :, 1] + zs.reshape(-1, 1) * gv[None, :, 2])
+    for ix in range(M[0]):
+        ph = pyz + 2 * np.pi * (ix / M[0]) * gv[None, :, 0]
+        basis = np.where(is_sin[None, :], np.sin(ph), np.cos(ph)).astype(Q.dtype)
+        c[ix, :, :, :n_spl] = (basis @ Q).reshape(M[1] + 3, M[2] + 3, n_spl)
+    c[M[0]:, :, :, :] = c[:3, :, :, :]
+    return c
+
+
 def make_system(N=768, M=60, dtype=np.float32, L=None, seed=20240, with_j1=True, with_j2=True, lattice=None,
-                same_table=False):
-    """A synthetic NiO-like system: cubic cell scaled so the electron density matches a64, two spin tables."""
+                same_table=False, table="pw"):
+    """A synthetic NiO-like system: cubic cell scaled so the electron density matches a64, two spin tables.
+    table = "pw" (random orthogonal plane-wave mixtures, default) or "iid" (i.i.d. uniform coefficients)."""
     n_up = N // 2
     n_dn = N - n_up
     if L is None:
         L = L_A64 * (N / 768.0) ** (1.0 / 3.0)
     lat = np.asarray(lattice, np.float64).reshape(3, 3) if lattice is not None else np.eye(3) * L
-    t_up = random_table(M, n_up, dtype, seed)
-    t_dn = t_up if same_table else random_table(M, n_dn, dtype, seed + 1)
+    mk = pw_table if table == "pw" else random_table
+    t_up = mk(M, n_up, dtype, seed)
+    t_dn = t_up if same_table else mk(M, n_dn, dtype, seed + 1)
     s = dict(n_up=n_up, n_dn=n_dn, lattice=lat, coefs=[t_up, t_dn], grid=(M, M, M) if np.isscalar(M) else tuple(M))
     if with_j2:
         s["j2"] = dict(uu=J2_UU, ud=J2_UD, rcut=min(J2_RCUT, 0.4999 * L_wigner_seitz(lat)))

@@ -401,6 +401,15 @@ class OracleVMC:
         self.last_seconds = sec.value
         return log
 
+    def sweep_forced(self, forced, want_ratios=True):
+        forced = _np(forced, np.uint8)
+        nsteps = forced.shape[0]
+        assert forced.shape == (nsteps, self.N, self.nw)
+        ratios = np.zeros((nsteps, self.N, self.nw), np.float64) if want_ratios else None
+        self.o._chk(self.o.lib.orc_vmc_sweep_forced(self.h, C.c_int(nsteps), _p(forced),
+                                                    _p(ratios) if want_ratios else None))
+        return ratios
+
     def positions(self):
         R = np.zeros((self.nw, self.N, 3), np.float64)
         self.o._chk(self.o.lib.orc_vmc_get_positions(self.h, _p(R)))

@@ -158,29 +158,78 @@ def test_mixed_precision_sweep_statistically_equal(api, orc):
     assert lp2 == pytest.approx(lp, rel=2e-4, abs=2e-3)
 
 
-def test_nio_a32_shape_parity_one_sweep(api, orc):
-    """BASELINE config 2 shape (384 electrons, 192 orbitals/spin, 48^3 grid, float, k=32) at a walker count the oracle
-    finishes in seconds: device-resident sweep vs oracle, mixed precision"""
+def _a32_forced(api, orc, dt, tau=0.3, nw=4, seed=31):
+    """product sweep (host-driven C-ABI calls) at the NiO-a32 shape, then the oracle teacher-forced with the product's
+    accept flags; returns per-move total ratios of both"""
     from qmcpack_b200.workload import make_system, initial_positions
+    from qmcpack_b200 import vmc_host
     import oracle_lib
-    s = make_system(N=384, M=48, dtype=np.float32)
-    nw, seed, tau = 4, 31, 0.05
+    N = 384
+    s = make_system(N=N, M=48, dtype=dt)
     R = initial_positions(s, nw)
-    ov = oracle_lib.OracleVMC(orc, s, nw=nw, ncrowds=1, seeds=[seed], tau=tau, delay_rank=32)
-    ov.set_positions(R)
-    ov.recompute()
-    olog = ov.sweep(1, log_accept=True)
     crowd = api.Crowd(s, nw=nw, delay_rank=32)
     crowd.set_positions(R)
     crowd.mw_recompute()
-    lp0, _, _, _ = crowd.mw_evaluateGL()
-    olp0 = ov.evaluate_gl()[0] * 0 + lp0  # placeholder keeps shapes; log psi compared after the sweep below
-    crowd.vmc_init(tau=tau, use_drift=True, seed=seed, use_cuda_graph=True)
-    log = crowd.vmc_sweep(1, log_accept=True)
-    agree = (log == olog).mean()
-    assert agree > 0.97, agree
-    assert abs(log.mean() - olog.mean()) < 0.03
+    rng = orc.rng(seed)
+    log = np.zeros((1, N, nw), np.uint8)
+    ratios = np.zeros((1, N, nw))
+    vmc_host.advance_walkers(crowd, rng, tau=tau, log_accept=log[0], log_ratio=ratios[0])
+    ov = oracle_lib.OracleVMC(orc, s, nw=nw, ncrowds=1, seeds=[seed], tau=tau, delay_rank=32)
+    ov.set_positions(R)
+    ov.recompute()
+    oratios = ov.sweep_forced(log)
+    return s, R, crowd, ov, log, ratios, oratios
+
+
+def test_nio_a32_shape_fp64_every_move(api, orc):
+    """BASELINE config 2 shape (384 electrons, 192 orbitals/spin, 48^3 grid, delay rank 32) in full precision: every
+    move's total wavefunction ratio within 1e-8 relative of the oracle, and the free-running oracle takes the same
+    decisions (identical acceptance sequence)."""
+    import oracle_lib
+    s, R, crowd, ov, log, ratios, oratios = _a32_forced(api, orc, np.float64)
+    rel = np.abs(ratios - oratios) / np.maximum(np.abs(oratios), 1e-2)
+    assert rel.max() < 1e-8, rel.max()
+    assert crowd.positions() == pytest.approx(ov.positions(), rel=1e-10, abs=1e-10)
+    lp, ke, _, _ = crowd.mw_evaluateGL()
+    olp, oke, _, _ = ov.evaluate_gl()
+    assert lp == pytest.approx(olp, rel=1e-10, abs=1e-8)
+    assert ke == pytest.approx(oke, rel=1e-7)
+    ov2 = oracle_lib.OracleVMC(orc, s, nw=4, ncrowds=1, seeds=[31], tau=0.3, delay_rank=32)
+    ov2.set_positions(R)
+    ov2.recompute()
+    assert np.array_equal(ov2.sweep(1, log_accept=True), log)
+
+
+def test_nio_a32_shape_mixed_precision_every_move(api, orc):
+    """Same shape with float tables / float inverse (the benchmark's precision).  A rounding-borderline Metropolis
+    decision makes two correct mixed-precision implementations part ways, so the oracle is teacher-forced with the
+    product's decisions and EVERY move's ratio is compared (median relative error < 1e-4, 95th percentile < 5e-3,
+    worst move < 5e-2: float inverse rows of a Slater matrix with condition number ~1e3).  Then the free-running device driver is checked for the
+    oracle's acceptance rate and for consistency with a from-scratch recompute (checkGL_after_moves)."""
+    import oracle_lib
+    s, R, crowd, ov, log, ratios, oratios = _a32_forced(api, orc, np.float32)
+    N, nw = 384, 4
+    rel = np.abs(ratios - oratios) / np.maximum(np.abs(oratios), 0.1)
+    # float32 inverse rows of a Slater matrix with condition number ~1e3, errors compounding over 384 rank-1 updates
+    assert rel.max() < 5e-2, rel.max()
+    assert np.percentile(rel, 95) < 5e-3
+    assert np.median(rel) < 1e-4
+    lp, ke, _, _ = crowd.mw_evaluateGL()
+    olp, oke, _, _ = ov.evaluate_gl()
+    assert lp == pytest.approx(olp, rel=1e-5, abs=2e-2)
+    assert ke == pytest.approx(oke, rel=5e-3)
+    ov2 = oracle_lib.OracleVMC(orc, s, nw=nw, ncrowds=1, seeds=[31], tau=0.3, delay_rank=32)
+    ov2.set_positions(R)
+    ov2.recompute()
+    olog = ov2.sweep(1, log_accept=True)
+    crowd.set_positions(R)
+    crowd.mw_recompute()
+    crowd.vmc_init(tau=0.3, use_drift=True, seed=31, use_cuda_graph=True)
+    dlog = crowd.vmc_sweep(1, log_accept=True)
+    assert abs(dlog.mean() - olog.mean()) < 0.03
+    assert (dlog == olog).mean() > 0.9
     lp, ke, _, _ = crowd.mw_evaluateGL()
     crowd.mw_recompute()
     lp2, ke2, _, _ = crowd.mw_evaluateGL()
-    assert lp2 == pytest.approx(lp, rel=1e-4, abs=5e-2)
+    assert lp2 == pytest.approx(lp, rel=1e-5, abs=2e-2)
+    assert ke2 == pytest.approx(ke, rel=5e-3)
