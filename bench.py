@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- NiO-a64 batched VMC electron-moves/s (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                            the reference's CPU implementation of the same path
+
+One "step" = one particle-by-particle VMC sweep (every electron of every walker proposed once: drift + Gaussian
+move, distance rows, spline SPO evaluation, determinant ratio/gradient, J1/J2, Metropolis test, delayed update).
+
+  value     whole-job electron-moves/s with everything resident in HBM: the device-resident sweep (on-device
+            std::mt19937 + Metropolis test, one CUDA graph per sweep), timed with CUDA events on the launching stream,
+            max over ranks.
+  e2e       the same metric through the reference-facing C ABI with HOST buffers: the compiled host driver
+            (include/qmcb_driver.h) issues evalGrad / makeMove / calcRatioGrad / accept_reject per electron, positions,
+            gradients, ratios and accept flags cross PCIe every move, accept test on the host -- how QMCPACK's batched
+            driver would call this library.
+  roofline  the spline gather kernel timed alone (CUDA events on its stream): algorithmic bytes per launch
+            (64*Npad*4 stencil + 5*n*4 phi_vgl write + n*4 inverse-row read per walker) / average duration, against
+            the measured HBM copy bandwidth of MEASURED_PEAKS.json (burst figure).
+  cpu_baseline  the reference's CPU path (oracle/_ref: spline2::evaluate_vgh_impl + DelayedUpdate<T> + DiracMatrix compiled
+            from /root/reference, else the oracle port) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "NiO-a64 VMC electron-moves/s"
+UNIT = "electron-moves/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="NiO-a64")
+    ap.add_argument("--walkers", type=int, default=512, help="walkers per GPU")
+    ap.add_argument("--crowds", type=int, default=4, help="crowds (host threads / streams) of the e2e host driver")
+    ap.add_argument("--tau", type=float, default=0.3)
+    ap.add_argument("--cpu-walkers", type=int, default=0, help="walkers of the CPU sample (default 2 per core)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def workload_desc(cfg, args):
+    from qmcpack_b200 import workload
+    c = workload.CONFIGS[cfg]
+    n = c["N"] // 2
+    npad = workload.aligned_size(c["dtype"], n)
+    tab_mb = (c["M"] + 3) ** 3 * npad * np.dtype(c["dtype"]).itemsize / 1e6
+    return (f"{cfg} synthetic: {c['N']} electrons, {n} orbitals/spin, {c['M']}^3 spline grid "
+            f"({tab_mb:.0f} MB/spin, {np.dtype(c['dtype']).name}), J1+J2 B-spline Jastrows, batched VMC with drift "
+            f"(tau={args.tau}), delay_rank {c['k']}, {args.walkers} walkers/GPU")
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """samples SM clock and throttle reasons during the timed region (NVML)"""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.ok:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.ok:
+            self.t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(cfg, args, steps, warmup, nw_cpu=None):
+    """the reference's CPU implementation of the path on the host cores (bounded sample of the workload)"""
+    import oracle_lib
+    from qmcpack_b200 import workload
+    orc = oracle_lib.ref() or oracle_lib.port()
+    kind = "reference" if orc.is_reference else "port"
+    cores = os.cpu_count() or 1
+    c = workload.CONFIGS[cfg]
+    nw = nw_cpu or args.cpu_walkers or 8 * cores
+    ncrowds = min(cores, nw)
+    s = workload.make_system(N=c["N"], M=c["M"], dtype=c["dtype"])
+    v = orc.vmc(s, nw=nw, ncrowds=ncrowds, seeds=[1000 + i for i in range(ncrowds)], tau=args.tau, use_drift=True,
+                delay_rank=c["k"], batched_engine=False)
+    v.set_positions(workload.initial_positions(s, nw))
+    v.recompute()
+    if warmup:
+        v.sweep(warmup)
+    t0 = time.perf_counter()
+    v.sweep(steps)
+    dt = time.perf_counter() - t0
+    moves = steps * nw * c["N"]
+    acc, rej = v.counts()
+    return dict(value=moves / dt, seconds=dt, kind=kind, cores=ncrowds, nw=nw, steps=steps,
+                acceptance=float(acc.sum() / max(1, (acc + rej).sum())),
+                sample=f"{steps} sweeps of {nw} walkers ({moves} moves) of {cfg}, {ncrowds} crowds = {ncrowds} OpenMP "
+                       f"threads, {'oracle/_ref (reference kernels + OpenBLAS)' if kind == 'reference' else 'oracle port'}")
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    res = cpu_reference_run(args.config, args, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_desc(args.config, args), "cpu_sample": res["sample"]},
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
+                         "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, local_rank, world):
+    import torch
+    from qmcpack_b200 import api, workload, build
+    build.build()
+    torch.cuda.set_device(local_rank)
+    api.init(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    c = workload.CONFIGS[args.config]
+    N, k, nw = c["N"], c["k"], args.walkers
+    s = workload.make_system(N=N, M=c["M"], dtype=c["dtype"])
+    lat = np.asarray(s["lattice"])
+    G = np.linalg.inv(lat)
+    n = N // 2
+    up = api.SplineSPOSet(s["coefs"][0], n, G)
+    dn = api.SplineSPOSet(s["coefs"][1], n, G)
+    spo = (up, dn)
+    R = workload.initial_positions(s, nw, seed=7 + 100003 * rank)  # every rank owns its own walkers (weak scaling)
+
+    # ---------------- device-resident sweep (value)
+    crowd = api.Crowd(s, nw=nw, delay_rank=k, spo=spo)
+    crowd.set_positions(R)
+    crowd.mw_recompute()
+    crowd.vmc_init(tau=args.tau, use_drift=True, seed=1000 + rank, use_cuda_graph=True)
+    stream = torch.cuda.ExternalStream(crowd.stream, device=torch.device("cuda", local_rank))
+    for _ in range(max(args.warmup, 3)):
+        crowd.vmc_sweep_async()
+    crowd.sync()
+    a0, r0 = crowd.vmc_counts()
+    launches0 = api.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clk:
+        e0.record(stream)
+        for _ in range(args.steps):
+            crowd.vmc_sweep_async()
+        e1.record(stream)
+        crowd.sync()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = api.kernel_launch_count() - launches0
+    a1, r1 = crowd.vmc_counts()
+    acc_rate = float((a1 - a0).sum() / max(1, ((a1 - a0) + (r1 - r0)).sum()))
+    # block estimator: kinetic energy of the walkers, reduced over ranks (the path's only collective: one small
+    # all-reduce per block, EstimatorManagerNew.cpp:338,363)
+    lp, ke, _, _ = crowd.mw_evaluateGL()
+    est = torch.tensor([ke.sum(), (ke * ke).sum(), float(nw), float((a1 - a0).sum()), float((r1 - r0).sum())],
+                       dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(est)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_max = float(tmax.item())
+    value = world * nw * N * args.steps / (ms_max * 1e-3)
+    ke_mean = float(est[0] / est[2])
+    sane = bool(np.isfinite(ke).all() and np.isfinite(lp).all())
+
+    # ---------------- spline gather kernel alone (roofline)
+    T = np.float32 if c["dtype"] == np.float32 else np.float64
+    tdt = torch.float32 if T == np.float32 else torch.float64
+    nsets = 24
+    gen = torch.Generator(device="cuda").manual_seed(5 + rank)
+    pos = (torch.rand((nsets, nw, 3), generator=gen, device="cuda", dtype=torch.float64) @
+           torch.tensor(lat, device="cuda")).to(tdt).contiguous()
+    inv = torch.randn((nw, n), generator=gen, device="cuda", dtype=tdt).contiguous()
+    phi = torch.empty((5, nw, n), device="cuda", dtype=tdt)
+    rg = torch.empty((nw, 4), device="cuda", dtype=tdt)
+    ts = torch.cuda.Stream()
+    lib = api.lib()
+
+    def spline_launch(i):
+        rc = lib.qmcb_spline_mw_vgl_ratio_grads_dev(up.h, nw, pos[i % nsets].data_ptr(), inv.data_ptr(), n,
+                                                    phi.data_ptr(), rg.data_ptr(), ts.cuda_stream)
+        if rc:
+            raise RuntimeError(lib.qmcb_last_error().decode())
+    for i in range(4):
+        spline_launch(i)
+    ts.synchronize()
+    nrep = 40
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(ts)
+    for i in range(nrep):
+        spline_launch(4 + i)
+    s1.record(ts)
+    ts.synchronize()
+    t_spl = s0.elapsed_time(s1) * 1e-3 / nrep
+    npad = workload.aligned_size(T, n)
+    esz = np.dtype(T).itemsize
+    b_spl = 64 * npad * esz + 5 * n * esz + n * esz  # stencil + phi_vgl write + inverse-row read
+    achieved = b_spl * nw / t_spl / 1e9
+    pk = peaks()
+    peak = pk["hbm_gbs"] if pk else 6650.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "spline_gather_kernel (VGL + ratio/grad)",
+                "algorithmic_bytes_per_launch": b_spl * nw, "us_per_launch": t_spl * 1e6,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if pk else "fallback 6.65 TB/s",
+                "evals_per_s": nw / t_spl}
+
+    # ---------------- end to end through the C ABI with host buffers
+    e2e = None
+    if not args.no_e2e:
+        ncr = max(1, min(args.crowds, nw))
+        base, extra = divmod(nw, ncr)
+        sizes = [base + (1 if i < extra else 0) for i in range(ncr)]
+        crowds, off = [], 0
+        del crowd
+        for i in range(ncr):
+            cr = api.Crowd(s, nw=sizes[i], delay_rank=k, spo=spo)
+            cr.set_positions(R[off:off + sizes[i]])
+            cr.mw_recompute()
+            crowds.append(cr)
+            off += sizes[i]
+        drv = api.HostVMC(crowds, [2000 + 17 * rank + i for i in range(ncr)], tau=args.tau, use_drift=True)
+        drv.run(1)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        drv.run(args.steps)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d, d2h = drv.bytes_per_sweep()
+        e2e = {"value": world * nw * N * args.steps / float(tt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "crowds": ncr,
+               "ms_per_step": 1e3 * float(tt.item()) / args.steps,
+               "path": "qmcb_host_vmc_run: per-electron qmcb_twf_mw_eval_grad / qmcb_ps_mw_make_move / "
+                       "qmcb_twf_mw_calc_ratio_grad / qmcb_twf_mw_accept_reject with host buffers, accept test on the host"}
+        del drv, crowds
+
+    # ---------------- CPU baseline beside it (rank 0, single-GPU run only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        res = cpu_reference_run(args.config, args, steps=12, warmup=1, nw_cpu=4 * (os.cpu_count() or 1))
+        cpu = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if T == np.float32 else "f64", "data": "synthetic",
+            "config": {"workload": workload_desc(args.config, args), "walkers_per_gpu": nw, "electrons": N,
+                       "delay_rank": k, "table": "random orthogonal mixtures of the lowest plane waves (workload.pw_table)",
+                       "l2": "inputs larger than L2: 2 x 384 MB spline tables + %.1f GB walker state vs 126 MB L2"
+                             % (3.1 * nw / 512),
+                       "parallelism": f"walkers sharded over {world} GPU(s), no data-path collective; one all-reduce per block",
+                       "acceptance": acc_rate, "ke_mean_hartree": ke_mean, "finite": sane},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,10 @@ SYMBOLS = [
 ]
 
 
+DRIVER_SYMBOLS = ["qmcb_host_vmc_last_error", "qmcb_host_vmc_create", "qmcb_host_vmc_destroy", "qmcb_host_vmc_run",
+                  "qmcb_host_vmc_counts", "qmcb_host_vmc_bytes_per_sweep"]
+
+
 def lib():
     """Loads libqmcb.so; raises (loudly) when it has not been built."""
     global _lib
@@ -89,6 +93,7 @@ def lib():
         L.qmcb_spline_mw_vgl_ratio_grads_dev.argtypes = [vp, C.c_int, vp, vp, C.c_size_t, vp, vp, vp]
         L.qmcb_crowd_create.argtypes = [C.POINTER(vp), C.POINTER(QmcbSystem), C.c_int]
         L.qmcb_det_mw_get_inv_row.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), vp]
+        L.qmcb_host_vmc_last_error.restype = C.c_char_p
         _lib = L
     return _lib
 
@@ -380,3 +385,48 @@ class Crowd:
         a, r = np.zeros(self.nw, np.int64), np.zeros(self.nw, np.int64)
         _chk(lib().qmcb_vmc_counts(self.h, _p(a), _p(r)))
         return a, r
+
+
+class HostVMC:
+    """The compiled host driver above the C ABI (include/qmcb_driver.h): VMCBatched::advanceWalkers with one host thread
+    per crowd, host buffers crossing PCIe every move."""
+
+    def __init__(self, crowds, seeds, tau=0.3, use_drift=True):
+        self.crowds = list(crowds)
+        nc = len(self.crowds)
+        arr = (vp * nc)(*[c.h.value for c in self.crowds])
+        nws = np.array([c.nw for c in self.crowds], np.int32)
+        sd = np.ascontiguousarray(seeds, np.uint32)
+        assert len(sd) == nc
+        self.N = self.crowds[0].N
+        self.nw_total = int(nws.sum())
+        self.h = vp()
+        rc = lib().qmcb_host_vmc_create(C.byref(self.h), arr, _p(nws), C.c_int(nc), C.c_int(self.N),
+                                        C.c_int(self.crowds[0].precision), _p(sd), C.c_double(tau),
+                                        C.c_int(int(use_drift)))
+        if rc:
+            raise RuntimeError(lib().qmcb_host_vmc_last_error().decode())
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().qmcb_host_vmc_destroy(self.h)
+        except Exception:
+            pass
+
+    def run(self, nsteps=1, log_accept=False):
+        log = np.zeros((nsteps, self.N, self.nw_total), np.uint8) if log_accept else None
+        rc = lib().qmcb_host_vmc_run(self.h, C.c_int(nsteps), _p(log))
+        if rc:
+            raise RuntimeError(lib().qmcb_host_vmc_last_error().decode())
+        return log
+
+    def counts(self):
+        a, r = C.c_longlong(), C.c_longlong()
+        lib().qmcb_host_vmc_counts(self.h, C.byref(a), C.byref(r))
+        return a.value, r.value
+
+    def bytes_per_sweep(self):
+        a, r = C.c_longlong(), C.c_longlong()
+        lib().qmcb_host_vmc_bytes_per_sweep(self.h, C.byref(a), C.byref(r))
+        return a.value, r.value

@@ -6,9 +6,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libqmcb.so")
-SOURCES = ["spline.cu", "crowd.cu", "api.cu"]
+SOURCES = ["spline.cu", "crowd.cu", "api.cu", "vmc_host.cpp"]
 HEADERS = ["common.cuh", "spline.cuh", "det.cuh", "jastrow.cuh", "driver.cuh", "internal.h",
-           os.path.join("..", "..", "include", "qmcb.h")]
+           os.path.join("..", "..", "include", "qmcb.h"), os.path.join("..", "..", "include", "qmcb_driver.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-ccbin", "/usr/bin/g++"]
@@ -29,7 +29,7 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
         cmd = [NVCC] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

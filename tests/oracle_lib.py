@@ -8,6 +8,10 @@ import os
 import subprocess
 import numpy as np
 
+# the reference runs BLAS single-threaded inside each crowd thread (BlasThreadingEnv, DelayedUpdate.h:163-170): the
+# OpenBLAS that oracle/_ref links must not spawn its own pool under the OpenMP crowd loop
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 PORT_SO = os.path.join(ORACLE_DIR, "liboracle.so")

@@ -17,8 +17,8 @@ def lib():
     return api.lib()
 
 
-def header_symbols():
-    txt = open(os.path.join(ROOT, "include", "qmcb.h")).read()
+def header_symbols(name="qmcb.h"):
+    txt = open(os.path.join(ROOT, "include", name)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(qmcb_[a-z0-9_]+)\s*\(", txt)))
 
@@ -30,6 +30,10 @@ def test_library_exports_every_declared_symbol(lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/qmcb.h but not exported by libqmcb.so"
     assert sorted(api.SYMBOLS) == syms
+    dsyms = header_symbols("qmcb_driver.h")
+    for s in dsyms:
+        assert hasattr(lib, s), f"{s} declared in include/qmcb_driver.h but not exported"
+    assert sorted(api.DRIVER_SYMBOLS) == dsyms
 
 
 def test_aligned_size_matches_reference_rule(lib):

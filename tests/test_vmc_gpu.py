@@ -126,6 +126,43 @@ def test_device_driver_identical_acceptance_fp64(api, orc):
         assert (na + nr == nsteps * 24).all() and na.sum() == olog.sum()
 
 
+@pytest.mark.parametrize("ncrowds", [1, 3])
+def test_compiled_host_driver_matches_oracle_multi_crowd(api, orc, ncrowds):
+    """the C++ host driver above the C ABI (one thread and one mt19937 stream per crowd) against the oracle with the same
+    crowd partition and seeds: identical acceptance sequences in FP64"""
+    from qmcpack_b200.workload import initial_positions
+    import oracle_lib
+    s = small_system(np.float64)
+    nw, k, nsteps, tau = 7, 4, 2, 0.1
+    seeds = [11 + 5 * c for c in range(ncrowds)]
+    R = initial_positions(s, nw)
+    ov = oracle_lib.OracleVMC(orc, s, nw=nw, ncrowds=ncrowds, seeds=seeds, tau=tau, delay_rank=k)
+    ov.set_positions(R)
+    ov.recompute()
+    olog = ov.sweep(nsteps, log_accept=True)
+    # same contiguous fair division of walkers over crowds as the oracle / MCPopulation
+    base, extra = divmod(nw, ncrowds)
+    sizes = [base + (1 if c < extra else 0) for c in range(ncrowds)]
+    crowds, off = [], 0
+    spo = None
+    for c in range(ncrowds):
+        cr = api.Crowd(s, nw=sizes[c], delay_rank=k, spo=spo)
+        spo = cr.spo  # crowds share the read-only tables like clones share the SPOSet (SplineR2R.h:82)
+        cr.set_positions(R[off:off + sizes[c]])
+        cr.mw_recompute()
+        crowds.append(cr)
+        off += sizes[c]
+    drv = api.HostVMC(crowds, seeds, tau=tau, use_drift=True)
+    log = drv.run(nsteps, log_accept=True)
+    assert np.array_equal(log, olog)
+    acc, rej = drv.counts()
+    assert acc == olog.sum() and acc + rej == olog.size
+    got = np.concatenate([c.positions() for c in crowds])
+    assert got == pytest.approx(ov.positions(), rel=1e-9, abs=1e-9)
+    up, down = drv.bytes_per_sweep()
+    assert up == 24 * (nw * 3 * 8 + nw) and down == 24 * (nw * 3 * 8 * 2 + nw * 8)
+
+
 def test_device_driver_no_drift(api, orc):
     from qmcpack_b200.workload import initial_positions
     import oracle_lib
