@@ -242,7 +242,7 @@ def run_b200(args, rank, local_rank, world):
            torch.tensor(lat, device="cuda")).to(tdt).contiguous()
     inv = torch.randn((nw, n), generator=gen, device="cuda", dtype=tdt).contiguous()
     phi = torch.empty((5, nw, n), device="cuda", dtype=tdt)
-    rg = torch.empty((nw, 4), device="cuda", dtype=tdt)
+    rg = torch.empty((nw, up.rg_parts, 4), device="cuda", dtype=tdt)
     ts = torch.cuda.Stream()
     lib = api.lib()
 

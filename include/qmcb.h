@@ -69,10 +69,12 @@ int qmcb_spline_mw_evaluate_det_ratios(qmcb_spline* h, int nvp, const double* r_
                                        int n_ref, const void* invrow_host, size_t ld_inv, void* ratios_host);
 /* device-resident variant used inside the sweep and by bench.py's kernel-only timing: positions and inverse rows
  * already in HBM, nothing copied, nothing synchronised.  r_dev [nw][3] RT; invrow_dev [nw][ld_inv]; phi_vgl_dev
- * [5][nw][n_orb]; ratio_grad_dev [nw][4] = ratio, grad*ratio (x,y,z) -- undivided, like the reference kernel's
- * per-team partials (SplineR2R.cpp:566-581).  stream: a cudaStream_t cast to void* (NULL = default stream). */
+ * [5][nw][n_orb]; rg_parts_dev [nw][qmcb_spline_rg_parts(h)][4] = partial sums of ratio, grad*ratio (x,y,z) --
+ * undivided and to be added in index order, like the reference kernel's per-team partials which its host code adds
+ * (SplineR2R.cpp:566-581).  stream: a cudaStream_t cast to void* (NULL = default stream). */
 int qmcb_spline_mw_vgl_ratio_grads_dev(qmcb_spline* h, int nw, const void* r_dev, const void* invrow_dev, size_t ld_inv,
-                                       void* phi_vgl_dev, void* ratio_grad_dev, void* stream);
+                                       void* phi_vgl_dev, void* rg_parts_dev, void* stream);
+int qmcb_spline_rg_parts(const qmcb_spline* h);
 
 /* ---- crowd: walker batch + trial wavefunction state ---------------------------------------------- */
 typedef struct qmcb_system

@@ -51,7 +51,7 @@ SYMBOLS = [
     "qmcb_init", "qmcb_last_error", "qmcb_device_count", "qmcb_aligned_size", "qmcb_kernel_launch_count",
     "qmcb_spline_create", "qmcb_spline_destroy", "qmcb_spline_table_bytes", "qmcb_spline_mw_evaluate_value",
     "qmcb_spline_mw_evaluate_vgl", "qmcb_spline_mw_evaluate_vgl_ratio_grads", "qmcb_spline_mw_evaluate_det_ratios",
-    "qmcb_spline_mw_vgl_ratio_grads_dev",
+    "qmcb_spline_mw_vgl_ratio_grads_dev", "qmcb_spline_rg_parts",
     "qmcb_crowd_create", "qmcb_crowd_destroy", "qmcb_crowd_sync", "qmcb_crowd_device_bytes",
     "qmcb_crowd_set_positions", "qmcb_crowd_get_positions",
     "qmcb_twf_mw_recompute", "qmcb_twf_mw_eval_grad", "qmcb_ps_mw_make_move", "qmcb_twf_mw_calc_ratio_grad",
@@ -153,6 +153,10 @@ class SplineSPOSet:
                 lib().qmcb_spline_destroy(self.h)
         except Exception:
             pass
+
+    @property
+    def rg_parts(self):
+        return int(lib().qmcb_spline_rg_parts(self.h))
 
     @property
     def table_bytes(self):

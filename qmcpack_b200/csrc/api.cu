@@ -65,7 +65,7 @@ void spline_eval_host(qmcb_spline* h, int mode, int nw, const double* r_host, co
   {
     g.inv.alloc((size_t)n_rows * ld_inv * vt, false);
     QMCB_CUDA(cudaMemcpy(g.inv.p, invrow_host, g.inv.bytes(), cudaMemcpyHostToDevice));
-    g.rg.alloc((size_t)nw * 4 * vt);
+    g.rg.alloc((size_t)nw * S.rg_parts() * 4 * vt);
   }
   if (ref_host)
   {
@@ -84,8 +84,15 @@ void spline_eval_host(qmcb_spline* h, int mode, int nw, const double* r_host, co
   }
   if (rg_out && invrow_host)
   {
-    rg_out->resize((size_t)nw * 4 * vt);
-    QMCB_CUDA(cudaMemcpy(rg_out->data(), g.rg.p, rg_out->size() * sizeof(T), cudaMemcpyDeviceToHost));
+    // add the per-(tile, warp) partial dots in index order
+    const int np = S.rg_parts(), nred = 4 * vt;
+    std::vector<T> parts((size_t)nw * np * nred);
+    QMCB_CUDA(cudaMemcpy(parts.data(), g.rg.p, parts.size() * sizeof(T), cudaMemcpyDeviceToHost));
+    rg_out->assign((size_t)nw * nred, T(0));
+    for (int iw = 0; iw < nw; ++iw)
+      for (int q = 0; q < np; ++q)
+        for (int e = 0; e < nred; ++e)
+          (*rg_out)[(size_t)iw * nred + e] += parts[((size_t)iw * np + q) * nred + e];
   }
 }
 
@@ -298,6 +305,8 @@ int qmcb_spline_mw_vgl_ratio_grads_dev(qmcb_spline* h, int nw, const void* r_dev
                           static_cast<cudaStream_t>(stream));
   });
 }
+
+int qmcb_spline_rg_parts(const qmcb_spline* h) { return h ? h->impl->rg_parts() : 0; }
 
 // ---- crowd
 int qmcb_crowd_create(qmcb_crowd** c, const qmcb_system* sys, int nw)

@@ -100,13 +100,15 @@ __global__ void propose_kernel(const DriverDev<T> Dr, const JastrowDev<T> J, con
 
 // TrialWaveFunction::mw_calcRatioGrad combination for one walker
 template<typename T>
-__device__ __forceinline__ double twf_ratio_grad(const JastrowDev<T>& J, int iw, int iat, const T* rg, T gn[3])
+__device__ __forceinline__ double twf_ratio_grad(const JastrowDev<T>& J, int iw, int iat, const T* rg, int nparts, T gn[3])
 {
-  const T rdet  = rg[4 * (size_t)iw];
+  T q[4];
+  sum_rg_parts<T, 4>(rg, iw, nparts, q);
+  const T rdet  = q[0];
   double ratio  = (double)rdet;
-  gn[0]         = rg[4 * (size_t)iw + 1] / rdet;
-  gn[1]         = rg[4 * (size_t)iw + 2] / rdet;
-  gn[2]         = rg[4 * (size_t)iw + 3] / rdet;
+  gn[0]         = q[1] / rdet;
+  gn[1]         = q[2] / rdet;
+  gn[2]         = q[3] / rdet;
   if (J.has_j2)
   {
     const T* vgl = J.j2_vgl + (size_t)iw * 5;
@@ -127,13 +129,14 @@ __device__ __forceinline__ double twf_ratio_grad(const JastrowDev<T>& J, int iw,
 }
 
 template<typename T>
-__global__ void twf_ratio_kernel(const JastrowDev<T> J, const int iat, const T* rg, double* ratios, T* grads)
+__global__ void twf_ratio_kernel(const JastrowDev<T> J, const int iat, const T* rg, const int nparts, double* ratios,
+                                 T* grads)
 {
   const int iw = blockIdx.x * blockDim.x + threadIdx.x;
   if (iw >= J.nw)
     return;
   T gn[3];
-  ratios[iw]       = twf_ratio_grad(J, iw, iat, rg, gn);
+  ratios[iw]       = twf_ratio_grad(J, iw, iat, rg, nparts, gn);
   grads[3 * iw]     = gn[0];
   grads[3 * iw + 1] = gn[1];
   grads[3 * iw + 2] = gn[2];
@@ -156,7 +159,7 @@ __global__ void j2_ratio_kernel(const JastrowDev<T> J, const int iat, double* ra
 // device driver: Metropolis test for the whole crowd in one CTA (VMCBatched.cpp:139-167)
 template<typename T>
 __global__ void __launch_bounds__(1024)
-    decide_kernel(const DriverDev<T> Dr, const JastrowDev<T> J, RngDev R, const int iat, const T* rg)
+    decide_kernel(const DriverDev<T> Dr, const JastrowDev<T> J, RngDev R, const int iat, const T* rg, const int nparts)
 {
   __shared__ unsigned warp_cnt[32];
   __shared__ unsigned long long s_base;
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(1024)
     if (iw < Dr.nw)
     {
       T gn[3];
-      const double ratio = twf_ratio_grad(J, iw, iat, rg, gn);
+      const double ratio = twf_ratio_grad(J, iw, iat, rg, nparts, gn);
       if (Dr.use_drift)
       {
         const T* dl = Dr.delta_cur + 3 * iw;
@@ -263,6 +266,7 @@ struct Crowd : CrowdBase
   DevBuf<T> Ainv[2], GL[2], U[2], V[2], Binv[2], wvec[2], invRow[2], tempMat[2], Up[2];
   DevBuf<int> list[2];
   DevBuf<double> logdet[2];
+  int rg_cap = 1, rg_nparts = 1; // slots per walker in `rg` / slots filled by the last evaluation
   int delay_count[2] = {0, 0};
   int invrow_id[2]   = {-1, -1};
   // jastrow / particle set
@@ -373,7 +377,8 @@ struct Crowd : CrowdBase
       D.list = list[s2].p, D.invRow = invRow[s2].p, D.tempMat = tempMat[s2].p, D.Up = Up[s2].p, D.logdet = logdet[s2].p;
     }
     A(phi_vgl, (size_t)5 * nw * nmax);
-    A(rg, (size_t)nw * 4);
+    rg_cap = std::max(1, std::max(spo[0]->rg_parts(), spo[1]->rg_parts()));
+    A(rg, (size_t)nw * rg_cap * 4);
     A(det_grads, (size_t)nw * 3);
     A(grads_tmp, (size_t)nw * 3);
     A(displ, (size_t)nw * 3);
@@ -593,7 +598,7 @@ struct Crowd : CrowdBase
   {
     const DetDev<T>& D = det[spin];
     const size_t smem  = (size_t)(D.n + 2 * D.k) * sizeof(T);
-    det_accept_kernel<T><<<nw, DET_TPB, smem, st>>>(D, row, delay_count[spin], acc_dev, rg_dev, phi_dev);
+    det_accept_kernel<T><<<nw, DET_TPB, smem, st>>>(D, row, delay_count[spin], acc_dev, rg_dev, rg_nparts, phi_dev);
     QMCB_LAUNCH_CHECK();
     delay_count[spin]++;
     invrow_id[spin] = -1;
@@ -603,6 +608,8 @@ struct Crowd : CrowdBase
   void launch_spline(int spin, int mode, const void* invrow, size_t ld, void* phi, void* rgp, cudaStream_t s)
   {
     spo[spin]->evaluate_dev(mode, nw, newpos.p, invrow, ld, nullptr, phi, rgp, s);
+    if (rgp)
+      rg_nparts = spo[spin]->rg_parts();
   }
 
   void det_eval_grad(int spin, int row, void* grads) override
@@ -635,20 +642,23 @@ struct Crowd : CrowdBase
     {
       det_ratio_from_phi_kernel<T><<<nw, DET_TPB, 0, st>>>(det[spin], phi_vgl.p, rg.p);
       QMCB_LAUNCH_CHECK();
+      rg_nparts = 1;
     }
     else
       launch_spline(spin, MODE_VGL, invRow[spin].p, det[spin].n, phi_vgl.p, rg.p, st);
-    QMCB_CUDA(cudaMemcpyAsync(h_t.p, rg.p, (size_t)nw * 4 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    std::vector<T> parts((size_t)nw * rg_nparts * 4);
+    QMCB_CUDA(cudaMemcpyAsync(parts.data(), rg.p, parts.size() * sizeof(T), cudaMemcpyDeviceToHost, st));
     sync();
     T* r = static_cast<T*>(ratios);
     T* g = static_cast<T*>(grads);
     for (int iw = 0; iw < nw; ++iw)
     {
-      const T ratio = h_t.p[4 * iw];
-      r[iw]         = ratio;
+      T q[4];
+      sum_rg_parts<T, 4>(parts.data(), iw, rg_nparts, q);
+      r[iw] = q[0];
       if (g)
         for (int d = 0; d < 3; ++d)
-          g[3 * iw + d] = h_t.p[4 * iw + 1 + d] / ratio; // SPOSet.cpp:171 grads = dot / ratio
+          g[3 * iw + d] = q[1 + d] / q[0]; // SPOSet.cpp:171 grads = dot / ratio
     }
   }
   void upload_flags(const uint8_t* acc)
@@ -818,7 +828,7 @@ struct Crowd : CrowdBase
     const int spin = spin_of(iat), row = iat - first[spin];
     ensure_row(spin, row);
     launch_spline(spin, MODE_VGL, invRow[spin].p, det[spin].n, phi_vgl.p, rg.p, st);
-    twf_ratio_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, rg.p, ratios_d.p, grads_tmp.p);
+    twf_ratio_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, rg.p, rg_nparts, ratios_d.p, grads_tmp.p);
     QMCB_LAUNCH_CHECK();
     QMCB_CUDA(cudaMemcpyAsync(h_d.p, ratios_d.p, (size_t)nw * sizeof(double), cudaMemcpyDeviceToHost, st));
     QMCB_CUDA(cudaMemcpyAsync(h_t.p, grads_tmp.p, (size_t)nw * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
@@ -1028,7 +1038,7 @@ struct Crowd : CrowdBase
         launch_spline(ig, MODE_VGL, invRow[ig].p, det[ig].n, phi_vgl.p, rg.p, st);
         if (jast)
           QMCB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
-        decide_kernel<T><<<1, std::min(1024, ((nw + 31) / 32) * 32), 0, st>>>(drv, jas, rng, iat, rg.p);
+        decide_kernel<T><<<1, std::min(1024, ((nw + 31) / 32) * 32), 0, st>>>(drv, jas, rng, iat, rg.p, rg_nparts);
         QMCB_LAUNCH_CHECK();
         launch_accept(ig, row, accepted.p, rg.p, phi_vgl.p);
         jastrow_accept_kernel<T><<<nw, JAS_TPB, 0, st>>>(jas, iat, accepted.p);
@@ -1062,10 +1072,6 @@ struct Crowd : CrowdBase
         cudaGraphExecDestroy(graph_exec);
         graph_exec = nullptr;
       }
-      // spline scratch must exist before capture (allocation is illegal while capturing): warm it with one evaluation
-      launch_spline(0, MODE_VGL, invRow[0].p, det[0].n, phi_vgl.p, rg.p, st);
-      if (nel[1] > 0)
-        launch_spline(1, MODE_VGL, invRow[1].p, det[1].n, phi_vgl.p, rg.p, st);
       sync();
       const unsigned long long before = g_launch_count.load();
       cudaGraph_t graph;

@@ -133,12 +133,12 @@ __global__ void __launch_bounds__(DET_TPB) det_ratio_from_phi_kernel(const DetDe
     rg[(size_t)iw * 4 + tid] = acc[tid];
 }
 
-// accept / pseudo-accept of slot c.  rg[iw][0] = determinant ratio of the proposed move.
+// accept / pseudo-accept of slot c.  rg[iw][part][0] = partial determinant ratios of the proposed move.
 // dynamic smem: (n + 2k) * sizeof(T)
 template<typename T>
 __global__ void __launch_bounds__(DET_TPB)
     det_accept_kernel(const DetDev<T> D, const int row, const int c, const unsigned char* accepted, const T* rg,
-                      const T* phi_vgl)
+                      const int rg_nparts, const T* phi_vgl)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* phi = reinterpret_cast<T*>(smem_raw);
@@ -180,7 +180,10 @@ __global__ void __launch_bounds__(DET_TPB)
         p[a] = -s;
     }
     __syncthreads();
-    const T ratio = rg[(size_t)iw * 4];
+    // determinant ratio = sum of the spline kernel's partial dots in index order
+    T ratio(0);
+    for (int q = 0; q < rg_nparts; ++q)
+      ratio += rg[((size_t)iw * rg_nparts + q) * 4];
     const T sigma = T(1) / ratio;
     const T* w    = D.wvec + (size_t)iw * k;
     if (tid < c)

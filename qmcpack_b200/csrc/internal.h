@@ -24,8 +24,11 @@ struct SplineSPOBase
   virtual size_t table_bytes() const = 0;
   int vt_per_orb() const { return kind == QMCB_C2C ? 2 : 1; } // scalars per orbital value
   size_t elem_size() const { return precision == QMCB_MIXED ? 4 : 8; }
+  // number of partial ratio/gradient slots per walker written by one evaluation (tiles x consumer warps)
+  virtual int rg_parts() const = 0;
   // device-resident evaluation.  r_dev [nw][3] RT; invrow_dev [*][ld_inv] (may be null); ref_dev optional row map;
-  // phi_dev: MODE_VGL [5][nw][n_orb], MODE_V [nw][n_orb] (may be null); rg_dev [nw][4*vt] (may be null)
+  // phi_dev: MODE_VGL [5][nw][n_orb], MODE_V [nw][n_orb] (may be null); rg_dev [nw][rg_parts()][4*vt] partial
+  // dots to be added in index order (may be null)
   virtual void evaluate_dev(int mode, int nw, const void* r_dev, const void* invrow_dev, size_t ld_inv,
                             const int* ref_dev, void* phi_dev, void* rg_dev, cudaStream_t st) = 0;
 };

@@ -2,7 +2,6 @@
 #include "internal.h"
 #include "spline.cuh"
 #include <cstring>
-#include <mutex>
 
 namespace qmcb
 {
@@ -25,26 +24,65 @@ int sm_count()
 // tile/stage shapes per (storage type, kind); shared memory per CTA = STAGES * 64 * TILE * sizeof(ST)
 template<typename ST, bool C2C>
 struct Shape;
+// MINB CTAs per SM share the 227 KB of shared memory and the register file
 template<>
 struct Shape<float, false>
 {
-  static constexpr int TILE = 192, STAGES = 4, VEC = 1;
-}; // 48 KB / stage
+  static constexpr int TILE = 192, STAGES = 2, VEC = 1, MINB = 2;
+}; // 48 KB / stage, 2 CTAs/SM
 template<>
 struct Shape<double, false>
 {
-  static constexpr int TILE = 128, STAGES = 3, VEC = 1;
+  static constexpr int TILE = 128, STAGES = 3, VEC = 1, MINB = 1;
 }; // 64 KB / stage
 template<>
 struct Shape<float, true>
 {
-  static constexpr int TILE = 256, STAGES = 3, VEC = 2;
+  static constexpr int TILE = 256, STAGES = 3, VEC = 2, MINB = 1;
 }; // 64 KB / stage
 template<>
 struct Shape<double, true>
 {
-  static constexpr int TILE = 128, STAGES = 3, VEC = 2;
+  static constexpr int TILE = 128, STAGES = 3, VEC = 2, MINB = 1;
 }; // 64 KB / stage
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled()
+{
+  static EncodeTiledFn fn = nullptr;
+  if (!fn)
+  {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    QMCB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess)
+      throw std::runtime_error("cuTensorMapEncodeTiled is not available from the driver");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// the table as a 4-D tensor (component fastest, then z, y, x); box = TILE components x 4 x 4 x 4 grid planes
+template<typename ST>
+CUtensorMap make_tensor_map(const ST* coefs, const int grid[3], size_t npad, int tile)
+{
+  CUtensorMap m;
+  const cuuint64_t dims[4]    = {(cuuint64_t)npad, (cuuint64_t)(grid[2] + 3), (cuuint64_t)(grid[1] + 3),
+                                 (cuuint64_t)(grid[0] + 3)};
+  const cuuint64_t strides[3] = {(cuuint64_t)npad * sizeof(ST), (cuuint64_t)npad * sizeof(ST) * (grid[2] + 3),
+                                 (cuuint64_t)npad * sizeof(ST) * (grid[2] + 3) * (grid[1] + 3)};
+  const cuuint32_t box[4]     = {(cuuint32_t)tile, 4, 4, 4};
+  const cuuint32_t estr[4]    = {1, 1, 1, 1};
+  const CUresult r = encode_tiled()(&m, sizeof(ST) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4,
+                                    const_cast<ST*>(coefs), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw std::runtime_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return m;
+}
 } // namespace
 
 template<typename ST>
@@ -52,17 +90,7 @@ struct SplineSPO : SplineSPOBase
 {
   DevBuf<ST> coefs, kc, mkk;
   SplineDev<ST> dev;
-  // cross-tile reduction scratch (grown on demand; one evaluation at a time per handle+stream is the contract,
-  // crowds own their own scratch through scratch_for())
-  struct Scratch
-  {
-    DevBuf<ST> partial;
-    DevBuf<unsigned> ticket;
-    int nw_cap = 0;
-  };
-  std::mutex mtx;
-  std::vector<std::pair<cudaStream_t, std::unique_ptr<Scratch>>> scratch;
-
+  CUtensorMap tmap; // box shape follows Shape<ST, kind == C2C>
   size_t table_bytes() const override { return coefs.bytes(); }
 
   SplineSPO(int prec, int kind_, const int g[3], int norb, int nspl, size_t npad_, const void* host, const double G_[9],
@@ -119,6 +147,7 @@ struct SplineSPO : SplineSPOBase
     dev.symGG[5] = (ST)GGt[8];
     dev.kcart    = nullptr;
     dev.mKK      = nullptr;
+    tmap = make_tensor_map<ST>(coefs.p, grid, npad, kind == QMCB_C2C ? Shape<ST, true>::TILE : Shape<ST, false>::TILE);
     if (kind == QMCB_C2C)
     {
       if (!kcart)
@@ -140,26 +169,15 @@ struct SplineSPO : SplineSPOBase
     }
   }
 
-  Scratch& scratch_for(cudaStream_t st, int nw, int ntiles, int nred)
+  int rg_parts() const override
   {
-    std::lock_guard<std::mutex> lk(mtx);
-    Scratch* s = nullptr;
-    for (auto& e : scratch)
-      if (e.first == st)
-        s = e.second.get();
-    if (!s)
+    if (kind == QMCB_C2C)
     {
-      scratch.emplace_back(st, std::make_unique<Scratch>());
-      s = scratch.back().second.get();
+      using SH = Shape<ST, true>;
+      return ((2 * n_orb + SH::TILE - 1) / SH::TILE) * (SH::TILE / SH::VEC / 32);
     }
-    if (s->nw_cap < nw)
-    {
-      QMCB_CUDA(cudaStreamSynchronize(st));
-      s->partial.alloc((size_t)nw * ntiles * nred);
-      s->ticket.alloc(nw);
-      s->nw_cap = nw;
-    }
-    return *s;
+    using SH = Shape<ST, false>;
+    return ((n_orb + SH::TILE - 1) / SH::TILE) * (SH::TILE / SH::VEC / 32);
   }
 
   template<bool C2C, int MODE>
@@ -167,10 +185,9 @@ struct SplineSPO : SplineSPOBase
               void* rg_dev, cudaStream_t st)
   {
     using SH            = Shape<ST, C2C>;
-    constexpr int TILE  = SH::TILE, STAGES = SH::STAGES, VEC = SH::VEC;
+    constexpr int TILE  = SH::TILE, STAGES = SH::STAGES, VEC = SH::VEC, MINB = SH::MINB;
     const int ncomp     = C2C ? 2 * n_orb : n_orb; // real components that matter
     const int ntiles    = (ncomp + TILE - 1) / TILE;
-    constexpr int nred  = C2C ? 8 : 4;
     SplineArgs<ST, ST> A;
     A.nw         = nw;
     A.r          = static_cast<const ST*>(r_dev);
@@ -178,16 +195,9 @@ struct SplineSPO : SplineSPOBase
     A.ref        = ref_dev;
     A.ld_inv     = (long long)ld_inv;
     A.phi_vgl    = static_cast<ST*>(phi_dev);
-    A.ratio_grad = static_cast<ST*>(rg_dev);
-    A.partial    = nullptr;
-    A.ticket     = nullptr;
-    if (rg_dev && ntiles > 1)
-    {
-      Scratch& s = scratch_for(st, nw, ntiles, nred);
-      A.partial  = s.partial.p;
-      A.ticket   = s.ticket.p;
-    }
-    auto kern            = spline_gather_kernel<ST, ST, TILE, STAGES, VEC, MODE, C2C>;
+    A.rg_partial = static_cast<ST*>(rg_dev);
+    A.nparts     = ntiles * (TILE / VEC / 32);
+    auto kern            = spline_gather_kernel<ST, ST, TILE, STAGES, VEC, MODE, C2C, MINB>;
     constexpr size_t smem = SplineSmem<ST, TILE, STAGES, VEC>::BYTES;
     static bool attr_set = false;
     if (!attr_set)
@@ -198,8 +208,8 @@ struct SplineSPO : SplineSPOBase
     const int nunits = nw * ntiles;
     if (nunits == 0)
       return;
-    const int grid_x = std::min(nunits, sm_count());
-    kern<<<grid_x, TILE / VEC + 32, smem, st>>>(dev, A, ntiles);
+    const int grid_x = std::min(nunits, MINB * sm_count());
+    kern<<<grid_x, TILE / VEC + 32, smem, st>>>(tmap, dev, A, ntiles);
     QMCB_LAUNCH_CHECK();
   }
 

@@ -10,16 +10,21 @@
 //
 // Design (not a port of the OpenMP-target regions):
 //   * one persistent CTA per SM slot; work unit = (walker, orbital tile of TILE real components)
-//   * a producer warp stages the unit's 4x4x4 coefficient stencil (64 rows x TILE components) into shared
-//     memory with cp.async.bulk (TMA bulk engine, SASS UBLKCP) completing on an mbarrier; STAGES units in flight
-//     per CTA, so HBM latency is covered by the bulk engine instead of by registers/occupancy
+//   * the table is described to the TMA unit as a 4-D tensor (component, z, y, x); one elected producer thread stages
+//     a unit's whole 4x4x4 coefficient stencil (64 rows x TILE components, 48-64 KB) into shared memory with ONE
+//     cp.async.bulk.tensor.4d request (SASS UTMALDG) completing on an mbarrier; STAGES units in flight per CTA, so HBM
+//     latency is covered by the TMA engine instead of by registers/occupancy.  Out-of-range components of the last
+//     tile are zero-filled by the TMA unit.
 //   * consumer threads own VEC consecutive components each, read the staged rows conflict-free, keep
 //     v/g(3)/h(6) in registers (the reference round-trips an 11-field scratch through global memory,
 //     SplineR2R.cpp:459,485-498), apply the lattice contraction, write phi_vgl[5][nw][n] coalesced and
-//     reduce ratio/grad in a fixed order (warp shuffle -> shared -> per-tile partial -> last tile sums tiles
-//     in index order): deterministic, no floating-point atomics
+//     reduce ratio/grad per warp with shuffles; every (tile, warp) deposits its partial sums in a fixed slot
+//     rg_partial[walker][part][4] and whoever consumes the ratio adds the parts in index order (sum_rg_parts): the
+//     result is deterministic, needs no floating-point atomics, and the consumer warps never meet at a CTA barrier,
+//     so one warp's epilogue overlaps the others' arithmetic
 #pragma once
 #include "common.cuh"
+#include <cuda.h>
 
 namespace qmcb
 {
@@ -56,10 +61,21 @@ struct SplineArgs
   const int* ref;      // optional [nw] row index into invrow (virtual-particle ratios); nullptr -> iw
   long long ld_inv;    // in VT elements
   ST* phi_vgl;         // MODE_VGL: [5][nw][n_orb] ; MODE_V: [nw][n_orb] ; may be nullptr
-  ST* ratio_grad;      // [nw][4] (x2 for complex): ratio, gx, gy, gz undivided; may be nullptr
-  ST* partial;         // [nw][ntiles][4] (x2 complex) scratch for the cross-tile reduction
-  unsigned* ticket;    // [nw] zero-initialised tickets
+  ST* rg_partial;      // [nw][nparts][4] (x2 for complex): per-(tile, warp) partial ratio, gx, gy, gz (undivided); may be nullptr
+  int nparts;          // ntiles * consumer warps
 };
+
+// sum the partial ratio/gradient dots of one walker in index order (NRED = 4 real, 8 complex)
+template<typename ST, int NRED>
+__host__ __device__ inline void sum_rg_parts(const ST* rg_partial, int iw, int nparts, ST out[NRED])
+{
+  for (int e = 0; e < NRED; ++e)
+    out[e] = ST(0);
+  const ST* p = rg_partial + (size_t)iw * nparts * NRED;
+  for (int q = 0; q < nparts; ++q)
+    for (int e = 0; e < NRED; ++e)
+      out[e] += p[q * NRED + e];
+}
 
 #ifdef __CUDACC__
 namespace ptx
@@ -100,6 +116,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                    smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// TMA tensor engine: one 4-D box (TILE components x 4 x 4 x 4) global -> shared (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+               "%5, %6}], [%2];" ::"r"(smem_u32(dst_smem)),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tmap)
+{
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
@@ -189,13 +218,14 @@ struct SplineSmem
 {
   static constexpr int ROWS        = 64;
   static constexpr size_t STAGE_B  = (size_t)ROWS * TILE * sizeof(ST);
-  static constexpr size_t BYTES    = STAGES * STAGE_B + 2 * STAGES * sizeof(uint64_t) + 8 * 32 * sizeof(ST) + 64;
+  static constexpr size_t BYTES    = STAGES * STAGE_B + 2 * STAGES * sizeof(uint64_t) + 64;
 };
 
 // MODE: SplineMode.  C2C: complex orbitals from pairs of components (VEC == 2), otherwise VEC == 1.
-template<typename ST, typename RT, int TILE, int STAGES, int VEC, int MODE, bool C2C>
-__global__ void __launch_bounds__(TILE / VEC + 32, 1)
-    spline_gather_kernel(const SplineDev<ST> S, const SplineArgs<ST, RT> A, const int ntiles)
+template<typename ST, typename RT, int TILE, int STAGES, int VEC, int MODE, bool C2C, int MINB>
+__global__ void __launch_bounds__(TILE / VEC + 32, MINB)
+    spline_gather_kernel(const __grid_constant__ CUtensorMap tmap, const SplineDev<ST> S, const SplineArgs<ST, RT> A,
+                         const int ntiles)
 {
   constexpr int NCONS = TILE / VEC; // consumer threads
   constexpr int ROWS  = 64;
@@ -204,8 +234,6 @@ __global__ void __launch_bounds__(TILE / VEC + 32, 1)
   ST* stage_base     = reinterpret_cast<ST*>(smem_raw);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * ROWS * TILE * sizeof(ST));
   uint64_t* empty_bar = full_bar + STAGES;
-  ST* red            = reinterpret_cast<ST*>(empty_bar + STAGES);
-  __shared__ unsigned s_last;
 
   const int tid       = threadIdx.x;
   const int nunits    = A.nw * ntiles;
@@ -224,34 +252,24 @@ __global__ void __launch_bounds__(TILE / VEC + 32, 1)
 
   if (producer)
   {
-    // ===== producer warp: one bulk copy per stencil row, 2 rows per lane =====
-    const int lane = tid - NCONS;
-    int q = 0;
-    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++q)
+    // ===== producer warp: ONE tensor-TMA request per unit, issued by one elected lane =====
+    if (tid == NCONS)
     {
-      const int stage = q % STAGES;
-      const unsigned ph = (q / STAGES) & 1;
-      const int iw = u / ntiles, tile = u - iw * ntiles;
-      ST ru[3], t[3];
-      int ind[3];
-      convert_pos<ST, RT>(S, A.r + 3 * (size_t)iw, ru);
-      locate(S, ru, ind, t);
-      const int comp0 = tile * TILE;
-      const int ncomp = min(TILE, S.npad - comp0);
-      const unsigned row_bytes = (unsigned)(ncomp * sizeof(ST));
-      ptx::mbar_wait(&empty_bar[stage], ph ^ 1u);
-      if (lane == 0)
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], row_bytes * ROWS);
-      __syncwarp();
-      ST* dst = stage_base + (size_t)stage * ROWS * TILE;
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr)
+      ptx::prefetch_tensormap(&tmap);
+      int q = 0;
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++q)
       {
-        const int row = lane * 2 + rr; // row = (i*4 + j)*4 + k
-        const int i = row >> 4, j = (row >> 2) & 3, k = row & 3;
-        const ST* src = S.coefs + ((long long)(ind[0] + i) * S.xs + (long long)(ind[1] + j) * S.ys +
-                                   (long long)(ind[2] + k) * S.npad + comp0);
-        ptx::bulk_g2s(dst + (size_t)row * TILE, src, row_bytes, &full_bar[stage]);
+        const int stage   = q % STAGES;
+        const unsigned ph = (q / STAGES) & 1;
+        const int iw = u / ntiles, tile = u - iw * ntiles;
+        ST ru[3], t[3];
+        int ind[3];
+        convert_pos<ST, RT>(S, A.r + 3 * (size_t)iw, ru);
+        locate(S, ru, ind, t);
+        ptx::mbar_wait(&empty_bar[stage], ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], (unsigned)(ROWS * TILE * sizeof(ST)));
+        ptx::tma_load_4d(stage_base + (size_t)stage * ROWS * TILE, &tmap, tile * TILE, ind[2], ind[1], ind[0],
+                         &full_bar[stage]);
       }
     }
     return;
@@ -280,6 +298,27 @@ __global__ void __launch_bounds__(TILE / VEC + 32, 1)
     for (int e = 0; e < VEC; ++e)
       v[e] = gx[e] = gy[e] = gz[e] = hxx[e] = hxy[e] = hxz[e] = hyy[e] = hyz[e] = hzz[e] = ST(0);
 
+    // fetch this thread's inverse-row element(s) while the stencil is still in flight
+    const int row_id = A.ref ? A.ref[iw] : iw;
+    ST wr = ST(0), wi = ST(0);
+    if (A.invrow)
+    {
+      if (!C2C)
+      {
+        const int m = tile * TILE + tid;
+        if (m < S.n_orb)
+          wr = A.invrow[(size_t)row_id * A.ld_inv + m];
+      }
+      else
+      {
+        const int jorb = (tile * TILE) / 2 + tid;
+        if (jorb < S.n_orb)
+        {
+          wr = A.invrow[((size_t)row_id * A.ld_inv + jorb) * 2];
+          wi = A.invrow[((size_t)row_id * A.ld_inv + jorb) * 2 + 1];
+        }
+      }
+    }
     ptx::mbar_wait(&full_bar[stage], ph);
     const ST* sm = stage_base + (size_t)stage * ROWS * TILE + tid * VEC;
 #pragma unroll
@@ -331,7 +370,6 @@ __global__ void __launch_bounds__(TILE / VEC + 32, 1)
     for (int e = 0; e < NRED; ++e)
       acc[e] = ST(0);
     const size_t fstride = (size_t)A.nw * S.n_orb * (C2C ? 2 : 1);
-    const int row_id     = A.ref ? A.ref[iw] : iw;
 
     if (!C2C)
     {
@@ -344,8 +382,7 @@ __global__ void __launch_bounds__(TILE / VEC + 32, 1)
           const ST psi = sgn * v[0];
           if (A.phi_vgl)
             A.phi_vgl[(size_t)iw * S.n_orb + m] = psi;
-          if (A.invrow)
-            acc[0] = psi * A.invrow[(size_t)row_id * A.ld_inv + m];
+          acc[0] = psi * wr;
         }
         else
         {
@@ -368,14 +405,10 @@ __global__ void __launch_bounds__(TILE / VEC + 32, 1)
             out[3 * fstride] = dz;
             out[4 * fstride] = lap;
           }
-          if (A.invrow)
-          {
-            const ST w = A.invrow[(size_t)row_id * A.ld_inv + m];
-            acc[0]     = psi * w;
-            acc[1]     = dx * w;
-            acc[2]     = dy * w;
-            acc[3]     = dz * w;
-          }
+          acc[0] = psi * wr;
+          acc[1] = dx * wr;
+          acc[2] = dy * wr;
+          acc[3] = dz * wr;
         }
       }
     }
@@ -389,12 +422,6 @@ __global__ void __launch_bounds__(TILE / VEC + 32, 1)
         ST s, cs;
         sincos(-(x * kX + y * kY + z * kZ), &s, &cs);
         const ST val_r = v[0], val_i = v[1];
-        ST wr = ST(0), wi = ST(0);
-        if (A.invrow)
-        {
-          wr = A.invrow[((size_t)row_id * A.ld_inv + jorb) * 2];
-          wi = A.invrow[((size_t)row_id * A.ld_inv + jorb) * 2 + 1];
-        }
         const ST psi_r = cs * val_r - s * val_i, psi_i = cs * val_i + s * val_r;
         if (MODE == MODE_V)
         {
@@ -458,53 +485,35 @@ __global__ void __launch_bounds__(TILE / VEC + 32, 1)
       }
     }
 
-    if (A.ratio_grad)
+    if (A.rg_partial)
     {
-      // fixed-order reduction: lanes (xor tree) -> warps (index order) -> tiles (index order)
+      // per-warp partial sums in a fixed slot; consumers of the ratio add the slots in index order
 #pragma unroll
       for (int e = 0; e < NRED; ++e)
         acc[e] = warp_sum(acc[e]);
-      ptx::named_bar_sync(1, NCONS); // `red` free again
-      if (lane == 0)
+      if (lane < NRED)
+      {
+        ST mine = acc[0];
 #pragma unroll
-        for (int e = 0; e < NRED; ++e)
-          red[e * 32 + warp] = acc[e];
-      ptx::named_bar_sync(1, NCONS);
-      if (tid < NRED)
-      {
-        ST ssum = ST(0);
-        for (int w = 0; w < NCONS / 32; ++w)
-          ssum += red[tid * 32 + w];
-        if (ntiles == 1)
-          A.ratio_grad[(size_t)iw * NRED + tid] = ssum;
-        else
-          A.partial[((size_t)iw * ntiles + tile) * NRED + tid] = ssum;
-      }
-      if (ntiles > 1)
-      {
-        // the CTA that deposits the last tile of this walker sums all tiles in index order
-        if (tid < NRED)
-          __threadfence();
-        ptx::named_bar_sync(1, NCONS);
-        if (tid == 0)
-        {
-          const unsigned tk = atomicAdd(&A.ticket[iw], 1u);
-          s_last            = (tk == (unsigned)(ntiles - 1));
-          if (s_last)
-            A.ticket[iw] = 0;
-        }
-        ptx::named_bar_sync(1, NCONS);
-        if (s_last && tid < NRED)
-        {
-          __threadfence();
-          ST ssum = ST(0);
-          for (int tt = 0; tt < ntiles; ++tt)
-            ssum += __ldcg(&A.partial[((size_t)iw * ntiles + tt) * NRED + tid]);
-          A.ratio_grad[(size_t)iw * NRED + tid] = ssum;
-        }
+        for (int e = 1; e < NRED; ++e)
+          mine = (lane == e) ? acc[e] : mine;
+        A.rg_partial[((size_t)iw * A.nparts + tile * (NCONS / 32) + warp) * NRED + lane] = mine;
       }
     }
   }
+}
+
+// rg[nw][NRED] = sum of the parts (standalone API and tests; inside the sweep the consumers add the parts themselves)
+template<typename ST, int NRED>
+__global__ void spline_finalize_rg_kernel(const ST* rg_partial, int nw, int nparts, ST* rg)
+{
+  const int iw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iw >= nw)
+    return;
+  ST out[NRED];
+  sum_rg_parts<ST, NRED>(rg_partial, iw, nparts, out);
+  for (int e = 0; e < NRED; ++e)
+    rg[(size_t)iw * NRED + e] = out[e];
 }
 #endif // __CUDACC__
 
