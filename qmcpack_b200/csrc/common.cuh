@@ -111,6 +111,37 @@ __device__ __forceinline__ double warp_sum(double v)
   return v;
 }
 
+// a group of threads of one CTA that synchronise on their own named barrier (bar 0 with the full CTA == __syncthreads)
+struct Group
+{
+  int tid, n, bar;
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(n) : "memory"); }
+};
+__device__ __forceinline__ Group cta_group() { return Group{(int)threadIdx.x, (int)blockDim.x, 0}; }
+
+// group-wide sum of NV values per thread, result valid in every thread of the group; `red` >= NV*32 T of shared memory;
+// g.n must be a multiple of 32 and every thread of the group must call it
+template<typename T, int NV>
+__device__ __forceinline__ void group_sum(const Group& g, T (&v)[NV], T* red)
+{
+  const int lane = g.tid & 31, warp = g.tid >> 5, nwarp = g.n >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    v[i] = warp_sum(v[i]);
+  g.sync();
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      red[i * 32 + warp] = v[i];
+  g.sync();
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+  {
+    T x  = lane < nwarp ? red[i * 32 + lane] : T(0);
+    v[i] = warp_sum(x);
+  }
+}
+
 // block-wide sum of NV values per thread, result valid in every thread.  `red` is shared scratch of >= NV*32 T.
 // All threads of the block must call it (uses __syncthreads).
 template<typename T, int NV>

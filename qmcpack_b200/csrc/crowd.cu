@@ -54,50 +54,6 @@ __global__ void make_move_kernel(const JastrowDev<T> J, const int iat, const T* 
     J.newpos[3 * iw + d] = J.rsoa[((size_t)iw * 3 + d) * J.npad + iat] + displ[3 * iw + d];
 }
 
-// device driver: drift + delta -> proposed position
-template<typename T>
-__global__ void propose_kernel(const DriverDev<T> Dr, const JastrowDev<T> J, const int iat, const T* det_grads)
-{
-  const int iw = blockIdx.x * blockDim.x + threadIdx.x;
-  if (iw >= J.nw)
-    return;
-  T delta[3], disp[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d)
-    delta[d] = Dr.deltas[((size_t)iat * Dr.nw + iw) * 3 + d] * Dr.sqrttau;
-  if (Dr.use_drift)
-  {
-    T g[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-    {
-      T v = det_grads[3 * iw + d];
-      if (J.has_j2)
-        v += J.dUat[((size_t)iw * 3 + d) * J.npad + iat];
-      if (J.has_j1)
-        v += J.Grad1[((size_t)iw * 3 + d) * J.N + iat];
-      g[d] = v;
-    }
-    get_drift<T>(Dr.tauovermass, g, disp);
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-      disp[d] += delta[d];
-  }
-  else
-  {
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-      disp[d] = delta[d];
-  }
-#pragma unroll
-  for (int d = 0; d < 3; ++d)
-  {
-    Dr.drifts[3 * iw + d]    = disp[d];
-    Dr.delta_cur[3 * iw + d] = delta[d];
-    J.newpos[3 * iw + d]     = J.rsoa[((size_t)iw * 3 + d) * J.npad + iat] + disp[d];
-  }
-}
-
 // TrialWaveFunction::mw_calcRatioGrad combination for one walker
 template<typename T>
 __device__ __forceinline__ double twf_ratio_grad(const JastrowDev<T>& J, int iw, int iat, const T* rg, int nparts, T gn[3])
@@ -156,27 +112,73 @@ __global__ void j2_ratio_kernel(const JastrowDev<T> J, const int iat, double* ra
   grads[3 * iw + 2] = vgl[3];
 }
 
-// device driver: Metropolis test for the whole crowd in one CTA (VMCBatched.cpp:139-167)
+// ------------------------------------------------------------------------------------------------------------
+// device driver: everything that happens for ONE walker between two spline evaluations, in one CTA:
+//   part 1 (electron iat_prev):  Metropolis test (VMCBatched.cpp:139-167) + determinant accept / pseudo-accept
+//                                + Jastrow accept + position commit
+//   part 2 (electron iat_next):  inverse-row preparation + old gradient + UNR drift + proposed position
+// The only cross-walker dependency of the reference's loop is the ORDER in which walkers draw their uniform from the
+// crowd's generator (drawn only when prob >= eps, walkers in index order).  Each CTA publishes "needs a draw" in a
+// flag tagged with the move's epoch and looks back over the lower-index walkers (which the hardware dispatched earlier)
+// to find its position in the stream: no grid-wide barrier, no single-CTA kernel.
+// 256 threads: threads 0-127 determinant group, 128-255 Jastrow group; dynamic smem (n + 2k) * sizeof(T).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int MB_TPB = 256;
+
 template<typename T>
-__global__ void __launch_bounds__(1024)
-    decide_kernel(const DriverDev<T> Dr, const JastrowDev<T> J, RngDev R, const int iat, const T* rg, const int nparts)
+__global__ void __launch_bounds__(MB_TPB, 4)
+    move_boundary_kernel(const DriverDev<T> Dr, const JastrowDev<T> J, const RngDev R, const DetDev<T> Dacc,
+                         const int iat_prev, const int row_prev, const int c_prev, const T* rg, const int rg_nparts,
+                         const T* phi_vgl, const DetDev<T> Dprep, const int iat_next, const int row_next, const int c_next,
+                         T* det_grads_out)
 {
-  __shared__ unsigned warp_cnt[32];
-  __shared__ unsigned long long s_base;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-  if (tid == 0)
-    s_base = *R.pos;
-  __syncthreads();
-  const T eps = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
-  for (int base = 0; base < Dr.nw; base += blockDim.x)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ T red[3 * 32];
+  __shared__ int s_acc;
+  __shared__ T s_ratio;
+  const int iw = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  if (iat_prev >= 0)
   {
-    const int iw  = base + tid;
-    bool need     = false;
-    T prob = T(0), log_gf = T(0), log_gb = T(0);
-    if (iw < Dr.nw)
+    if (tid < 32)
     {
-      T gn[3];
-      const double ratio = twf_ratio_grad(J, iw, iat, rg, nparts, gn);
+      // ---- Metropolis test of this walker (warp 0)
+      // partial ratio/gradient dots of the spline kernel: lanes fetch, lane 0 adds in index order
+      T q[4] = {T(0), T(0), T(0), T(0)};
+      {
+        T mine[4] = {T(0), T(0), T(0), T(0)};
+        if (lane < rg_nparts)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            mine[e] = rg[((size_t)iw * rg_nparts + lane) * 4 + e];
+        for (int part = 0; part < rg_nparts && part < 32; ++part)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            q[e] += __shfl_sync(0xffffffffu, mine[e], part);
+        for (int part = 32; part < rg_nparts; ++part) // more than 32 parts (very wide determinants)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            q[e] += rg[((size_t)iw * rg_nparts + part) * 4 + e];
+      }
+      const T rdet = q[0];
+      double ratio = (double)rdet;
+      T gn[3]      = {q[1] / rdet, q[2] / rdet, q[3] / rdet};
+      if (J.has_j2)
+      {
+        const T* vgl = J.j2_vgl + (size_t)iw * 5;
+        ratio *= exp((double)(J.Uat[(size_t)iw * J.npad + iat_prev] - vgl[0]));
+        gn[0] += vgl[1];
+        gn[1] += vgl[2];
+        gn[2] += vgl[3];
+      }
+      if (J.has_j1)
+      {
+        const T* cur = J.j1_cur + (size_t)iw * 5;
+        ratio *= exp((double)(J.Vat[(size_t)iw * J.N + iat_prev] - cur[0]));
+        gn[0] += cur[1];
+        gn[1] += cur[2];
+        gn[2] += cur[3];
+      }
+      T log_gf = T(0), log_gb = T(0);
       if (Dr.use_drift)
       {
         const T* dl = Dr.delta_cur + 3 * iw;
@@ -188,46 +190,109 @@ __global__ void __launch_bounds__(1024)
         dr[2] += Dr.drifts[3 * iw + 2];
         log_gb = -Dr.oneover2tau * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
       }
-      prob = (T)(ratio * ratio);
-      need = prob >= eps; // periodic cell: every move is valid
-    }
-    // exclusive scan of `need` in walker order
-    const unsigned bal = __ballot_sync(0xffffffffu, need);
-    const unsigned pre = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0)
-      warp_cnt[warp] = __popc(bal);
-    __syncthreads();
-    unsigned woff = 0, total = 0;
-    for (int w = 0; w < nwarp; ++w)
-    {
-      const unsigned cnt = warp_cnt[w];
-      if (w < warp)
-        woff += cnt;
-      total += cnt;
-    }
-    if (iw < Dr.nw)
-    {
-      bool acc = false;
-      if (need)
+      const T eps     = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
+      const T prob    = (T)(ratio * ratio);
+      const bool need = prob >= eps; // periodic cell: every move is valid
+      // ---- position of this walker's draw in the crowd's stream: look back over the lower-index walkers
+      const unsigned epoch = (*R.sweep) * (unsigned)(Dr.N + 1) + (unsigned)iat_prev + 1u;
+      if (lane == 0)
       {
-        const double u = rng_uniform(R, s_base + woff + pre);
-        acc            = u < (double)(prob * exp(log_gb - log_gf));
+        __threadfence();
+        *((volatile unsigned*)(R.flags + iw)) = (epoch << 1) | (need ? 1u : 0u);
       }
-      Dr.accepted[iw] = acc ? 1 : 0;
-      if (acc)
-        Dr.n_accept[iw] += 1;
-      else
-        Dr.n_reject[iw] += 1;
-      if (Dr.accept_log)
-        Dr.accept_log[(size_t)iat * Dr.nw + iw] = acc ? 1 : 0;
+      unsigned cnt = 0;
+      for (int j = lane; j < iw; j += 32)
+      {
+        unsigned f;
+        do
+        {
+          f = *((volatile unsigned*)(R.flags + j));
+        } while ((f >> 1) != epoch);
+        cnt += f & 1u;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (lane == 0)
+      {
+        const unsigned long long base = R.pos[iat_prev & 1];
+        bool acc = false;
+        if (need)
+        {
+          const double u = rng_uniform(R, base + cnt);
+          acc            = u < (double)(prob * exp(log_gb - log_gf));
+        }
+        if (iw == Dr.nw - 1)
+          R.pos[(iat_prev + 1) & 1] = base + cnt + (need ? 1u : 0u);
+        s_acc   = acc ? 1 : 0;
+        s_ratio = rdet;
+        Dr.accepted[iw] = acc ? 1 : 0;
+        if (acc)
+          Dr.n_accept[iw] += 1;
+        else
+          Dr.n_reject[iw] += 1;
+        if (Dr.accept_log)
+          Dr.accept_log[(size_t)iat_prev * Dr.nw + iw] = acc ? 1 : 0;
+      }
     }
     __syncthreads();
-    if (tid == 0)
-      s_base += total;
+    const bool acc = s_acc != 0;
+    if (tid < MB_TPB / 2)
+    {
+      T* phi = reinterpret_cast<T*>(smem_raw);
+      T* p   = phi + Dacc.n;
+      T* y   = p + Dacc.k;
+      det_accept_body<T>(Group{tid, MB_TPB / 2, 1}, Dacc, iw, row_prev, c_prev, acc, s_ratio, phi_vgl, phi, p, y);
+    }
+    else if (acc)
+      jastrow_accept_body<T>(Group{tid - MB_TPB / 2, MB_TPB / 2, 2}, J, iw, iat_prev);
     __syncthreads();
   }
-  if (tid == 0)
-    *R.pos = s_base;
+  if (iat_next >= 0)
+  {
+    T* x = reinterpret_cast<T*>(smem_raw);
+    T* p = x + Dprep.n;
+    T* w = p + Dprep.k;
+    T g[3];
+    det_prepare_row_body<T>(cta_group(), Dprep, iw, row_next, c_next, x, p, w, red, Dr.use_drift != 0, g);
+    if (tid == 0)
+    {
+      T delta[3], disp[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        delta[d] = Dr.deltas[((size_t)iat_next * Dr.nw + iw) * 3 + d] * Dr.sqrttau;
+      if (Dr.use_drift)
+      {
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+        {
+          if (det_grads_out)
+            det_grads_out[3 * iw + d] = g[d];
+          if (J.has_j2)
+            g[d] += J.dUat[((size_t)iw * 3 + d) * J.npad + iat_next];
+          if (J.has_j1)
+            g[d] += J.Grad1[((size_t)iw * 3 + d) * J.N + iat_next];
+        }
+        get_drift<T>(Dr.tauovermass, g, disp);
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          disp[d] += delta[d];
+      }
+      else
+      {
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          disp[d] = delta[d];
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+      {
+        Dr.drifts[3 * iw + d]    = disp[d];
+        Dr.delta_cur[3 * iw + d] = delta[d];
+        J.newpos[3 * iw + d]     = J.rsoa[((size_t)iw * 3 + d) * J.npad + iat_next] + disp[d];
+      }
+    }
+  }
 }
 
 // kinetic energy and log psi per walker: ke = -1/2 sum_i (L_i + G_i.G_i)
@@ -287,6 +352,7 @@ struct Crowd : CrowdBase
   DevBuf<T> deltas, drifts, delta_cur;
   DevBuf<uint32_t> rng_state, rng_ring;
   DevBuf<unsigned long long> rng_cnt, n_acc, n_rej;
+  DevBuf<unsigned> rng_flags;
   DevBuf<unsigned char> accept_log;
   bool vmc_ready = false, use_graph = false;
   cudaGraphExec_t graph_exec = nullptr;
@@ -990,8 +1056,10 @@ struct Crowd : CrowdBase
       ring <<= 1;
     A(rng_state, 624);
     A(rng_ring, ring);
-    A(rng_cnt, 2);
+    A(rng_cnt, 4);
+    A(rng_flags, (size_t)nw + 1);
     rng.state = rng_state.p, rng.ring = rng_ring.p, rng.gen = rng_cnt.p, rng.pos = rng_cnt.p + 1;
+    rng.sweep = rng_flags.p + nw, rng.flags = rng_flags.p;
     rng.ring_mask = (unsigned)(ring - 1);
     mt19937_seed_kernel<<<1, 32, 0, st>>>(rng, p->seed);
     QMCB_LAUNCH_CHECK();
@@ -1014,36 +1082,67 @@ struct Crowd : CrowdBase
     QMCB_LAUNCH_CHECK();
     QMCB_CUDA(cudaEventRecord(ev_rng_done, st3));
     const unsigned long long gcount = 3ull * nw * N;
-    gauss_kernel<T><<<(unsigned)(((gcount + 1) / 2 + 255) / 256), 256, 0, st>>>(rng, deltas.p, gcount);
+    gauss_kernel<T><<<(unsigned)(((gcount + 1) / 2 + 255) / 256), 256, 0, st>>>(rng, deltas.p, gcount, N & 1);
     QMCB_LAUNCH_CHECK();
-    rng_advance_kernel<<<1, 32, 0, st>>>(rng, 2 * ((gcount + 1) / 2));
+    rng_advance_kernel<<<1, 32, 0, st>>>(rng, 2 * ((gcount + 1) / 2), N & 1);
     QMCB_LAUNCH_CHECK();
-    for (int ig = 0; ig < 2; ++ig)
-      for (int iat = first[ig]; iat < first[ig] + nel[ig]; ++iat)
+    // per electron: [accept(iat-1) + prepare/propose(iat)] -> {spline gather || Jastrow rows}; the boundary kernel is
+    // split in two around a Woodbury flush
+    auto spin_row = [&](int iat, int& ig, int& row) {
+      ig  = spin_of(iat);
+      row = iat - first[ig];
+    };
+    auto boundary = [&](int iat_prev, int iat_next) {
+      int igp = 0, rp = 0, ign = 0, rn = 0;
+      if (iat_prev >= 0)
+        spin_row(iat_prev, igp, rp);
+      if (iat_next >= 0)
+        spin_row(iat_next, ign, rn);
+      const int cp = iat_prev >= 0 ? delay_count[igp] : 0;
+      int cn       = iat_next >= 0 ? delay_count[ign] : 0;
+      if (iat_prev >= 0 && iat_next >= 0 && igp == ign)
+        cn = cp + 1; // the slot appended by part 1 of this very launch
+      const int nmx     = std::max(iat_prev >= 0 ? det[igp].n : 0, iat_next >= 0 ? det[ign].n : 0);
+      const size_t smem = (size_t)(nmx + 2 * k) * sizeof(T);
+      move_boundary_kernel<T><<<nw, MB_TPB, smem, st>>>(drv, jas, rng, det[igp], iat_prev, rp, cp, rg.p, rg_nparts,
+                                                        phi_vgl.p, det[ign], iat_next, rn, cn, det_grads.p);
+      QMCB_LAUNCH_CHECK();
+      if (iat_prev >= 0)
       {
-        const int row = iat - first[ig];
-        launch_prepare(ig, row, drv.use_drift ? det_grads.p : nullptr);
-        propose_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(drv, jas, iat, det_grads.p);
-        QMCB_LAUNCH_CHECK();
-        // Jastrow rows and spline gather only share the proposed positions: run them side by side
-        const bool jast = jas.has_j2 || jas.has_j1;
-        if (jast)
-        {
-          QMCB_CUDA(cudaEventRecord(ev_fork, st));
-          QMCB_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
-          jastrow_move_kernel<T><<<nw, JAS_TPB, 0, st2>>>(jas, iat);
-          QMCB_LAUNCH_CHECK();
-          QMCB_CUDA(cudaEventRecord(ev_join, st2));
-        }
-        launch_spline(ig, MODE_VGL, invRow[ig].p, det[ig].n, phi_vgl.p, rg.p, st);
-        if (jast)
-          QMCB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
-        decide_kernel<T><<<1, std::min(1024, ((nw + 31) / 32) * 32), 0, st>>>(drv, jas, rng, iat, rg.p, rg_nparts);
-        QMCB_LAUNCH_CHECK();
-        launch_accept(ig, row, accepted.p, rg.p, phi_vgl.p);
-        jastrow_accept_kernel<T><<<nw, JAS_TPB, 0, st>>>(jas, iat, accepted.p);
-        QMCB_LAUNCH_CHECK();
+        delay_count[igp]++;
+        invrow_id[igp] = -1;
       }
+      if (iat_next >= 0)
+        invrow_id[ign] = rn;
+    };
+    boundary(-1, 0);
+    for (int iat = 0; iat < N; ++iat)
+    {
+      const int ig = spin_of(iat);
+      const bool jast = jas.has_j2 || jas.has_j1;
+      if (jast)
+      {
+        QMCB_CUDA(cudaEventRecord(ev_fork, st));
+        QMCB_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
+        jastrow_move_kernel<T><<<nw, JAS_TPB, 0, st2>>>(jas, iat);
+        QMCB_LAUNCH_CHECK();
+        QMCB_CUDA(cudaEventRecord(ev_join, st2));
+      }
+      launch_spline(ig, MODE_VGL, invRow[ig].p, det[ig].n, phi_vgl.p, rg.p, st);
+      if (jast)
+        QMCB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+      const int next = iat + 1 < N ? iat + 1 : -1;
+      const bool flush_after = (delay_count[ig] + 1 == k) || (next >= 0 && spin_of(next) != ig);
+      if (flush_after || next < 0)
+      {
+        boundary(iat, -1);
+        launch_flush(ig);
+        if (next >= 0)
+          boundary(-1, next);
+      }
+      else
+        boundary(iat, next);
+    }
     twf_complete_updates();
     // RNG top-up branch joins here
     QMCB_CUDA(cudaStreamWaitEvent(st, ev_rng_done, 0));

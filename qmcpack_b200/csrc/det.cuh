@@ -41,22 +41,19 @@ struct DetDev
 #ifdef __CUDACC__
 constexpr int DET_TPB = 256;
 
-// invRow = Ainv[row] - V^T (Binv^T (U Ainv[row]))  and  grad_now = invRow . dpsiM[row]
-// grads (optional) [nw][3].  One CTA per walker.  dynamic smem: (n + 2k) * sizeof(T)
+// invRow = Ainv[row] - V^T (Binv^T (U Ainv[row]))  and  grad_now = invRow . dpsiM[row]   (walker iw, thread group g)
+// x[n], p[k], w[k] shared scratch; red >= 3*32.  On return every thread of the group holds grad_now in gout (if asked).
 template<typename T>
-__global__ void __launch_bounds__(DET_TPB) det_prepare_row_kernel(const DetDev<T> D, const int row, const int c, T* grads)
+__device__ __forceinline__ void det_prepare_row_body(const Group& g, const DetDev<T>& D, const int iw, const int row,
+                                                     const int c, T* x, T* p, T* w, T* red, const bool want_grads,
+                                                     T gout[3])
 {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* x = reinterpret_cast<T*>(smem_raw);
-  T* p = x + D.n;
-  T* w = p + D.k;
-  __shared__ T red[3 * 32];
-  const int iw = blockIdx.x, tid = threadIdx.x, n = D.n, k = D.k;
-  const int lane = tid & 31, warp = tid >> 5, nwarp = DET_TPB / 32;
+  const int n = D.n, k = D.k;
+  const int lane = g.tid & 31, warp = g.tid >> 5, nwarp = g.n >> 5;
   const T* arow = D.Ainv + ((size_t)iw * n + row) * D.lda;
-  for (int j = tid; j < n; j += DET_TPB)
+  for (int j = g.tid; j < n; j += g.n)
     x[j] = arow[j];
-  __syncthreads();
+  g.sync();
   if (c > 0)
   {
     const T* U = D.U + (size_t)iw * k * n;
@@ -71,43 +68,59 @@ __global__ void __launch_bounds__(DET_TPB) det_prepare_row_kernel(const DetDev<T
       if (lane == 0)
         p[a] = s;
     }
-    __syncthreads();
-    if (tid < c)
+    g.sync();
+    if (g.tid < c)
     {
       T s(0);
       for (int a = 0; a < c; ++a)
-        s += B[a * k + tid] * p[a];
-      w[tid]                        = -s;
-      D.wvec[(size_t)iw * k + tid] = -s;
+        s += B[a * k + g.tid] * p[a];
+      w[g.tid]                        = -s;
+      D.wvec[(size_t)iw * k + g.tid] = -s;
     }
-    __syncthreads();
-    for (int j = tid; j < n; j += DET_TPB)
+    g.sync();
+    for (int j = g.tid; j < n; j += g.n)
     {
       T s(0);
       for (int a = 0; a < c; ++a)
         s += V[(size_t)a * n + j] * w[a];
       x[j] += s;
     }
-    __syncthreads();
+    g.sync();
   }
   T* out = D.invRow + (size_t)iw * n;
-  for (int j = tid; j < n; j += DET_TPB)
+  for (int j = g.tid; j < n; j += g.n)
     out[j] = x[j];
-  if (grads)
+  if (want_grads)
   {
-    const T* g = D.GL + ((size_t)iw * n + row) * 4 * n;
-    T acc[3]   = {T(0), T(0), T(0)};
-    for (int j = tid; j < n; j += DET_TPB)
+    const T* gl = D.GL + ((size_t)iw * n + row) * 4 * n;
+    T acc[3]    = {T(0), T(0), T(0)};
+    for (int j = g.tid; j < n; j += g.n)
     {
       const T xv = x[j];
-      acc[0] += xv * g[j];
-      acc[1] += xv * g[n + j];
-      acc[2] += xv * g[2 * n + j];
+      acc[0] += xv * gl[j];
+      acc[1] += xv * gl[n + j];
+      acc[2] += xv * gl[2 * n + j];
     }
-    block_sum<T, 3>(acc, red);
-    if (tid < 3)
-      grads[(size_t)iw * 3 + tid] = acc[tid];
+    group_sum<T, 3>(g, acc, red);
+    gout[0] = acc[0];
+    gout[1] = acc[1];
+    gout[2] = acc[2];
   }
+}
+
+// grads (optional) [nw][3].  One CTA per walker.  dynamic smem: (n + 2k) * sizeof(T)
+template<typename T>
+__global__ void __launch_bounds__(DET_TPB) det_prepare_row_kernel(const DetDev<T> D, const int row, const int c, T* grads)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* x = reinterpret_cast<T*>(smem_raw);
+  T* p = x + D.n;
+  T* w = p + D.k;
+  __shared__ T red[3 * 32];
+  T gout[3];
+  det_prepare_row_body<T>(cta_group(), D, blockIdx.x, row, c, x, p, w, red, grads != nullptr, gout);
+  if (grads && threadIdx.x < 3)
+    grads[(size_t)blockIdx.x * 3 + threadIdx.x] = gout[threadIdx.x];
 }
 
 // ratio/grad of externally supplied orbital rows (FakeSPO-style tests): rg[iw][4] = invRow . {v, gx, gy, gz}
@@ -133,33 +146,26 @@ __global__ void __launch_bounds__(DET_TPB) det_ratio_from_phi_kernel(const DetDe
     rg[(size_t)iw * 4 + tid] = acc[tid];
 }
 
-// accept / pseudo-accept of slot c.  rg[iw][part][0] = partial determinant ratios of the proposed move.
-// dynamic smem: (n + 2k) * sizeof(T)
+// accept / pseudo-accept of slot c for walker iw by thread group g.  phi[n], p[k], y[k] shared scratch.
 template<typename T>
-__global__ void __launch_bounds__(DET_TPB)
-    det_accept_kernel(const DetDev<T> D, const int row, const int c, const unsigned char* accepted, const T* rg,
-                      const int rg_nparts, const T* phi_vgl)
+__device__ __forceinline__ void det_accept_body(const Group& g, const DetDev<T>& D, const int iw, const int row, const int c,
+                                                const bool acc, const T ratio, const T* phi_vgl, T* phi, T* p, T* y)
 {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* phi = reinterpret_cast<T*>(smem_raw);
-  T* p   = phi + D.n;
-  T* y   = p + D.k;
-  const int iw = blockIdx.x, tid = threadIdx.x, n = D.n, k = D.k;
-  const int lane = tid & 31, warp = tid >> 5, nwarp = DET_TPB / 32;
-  T* U             = D.U + (size_t)iw * k * n;
-  T* V             = D.V + (size_t)iw * k * n;
-  T* B             = D.Binv + (size_t)iw * k * k;
-  const T* arow    = D.Ainv + ((size_t)iw * n + row) * D.lda;
-  const bool acc   = accepted[iw] != 0;
-  const size_t fs  = (size_t)D.nw * n;
+  const int n = D.n, k = D.k;
+  const int lane = g.tid & 31, warp = g.tid >> 5, nwarp = g.n >> 5;
+  T* U            = D.U + (size_t)iw * k * n;
+  T* V            = D.V + (size_t)iw * k * n;
+  T* B            = D.Binv + (size_t)iw * k * k;
+  const T* arow   = D.Ainv + ((size_t)iw * n + row) * D.lda;
+  const size_t fs = (size_t)D.nw * n;
   // V[c] = Ainv[row] (stale stored row) for every walker, DelayedUpdateBatched.h:646
-  for (int j = tid; j < n; j += DET_TPB)
+  for (int j = g.tid; j < n; j += g.n)
     V[(size_t)c * n + j] = arow[j];
   if (acc)
   {
     const T* ph = phi_vgl + (size_t)iw * n;
     T* gl       = D.GL + ((size_t)iw * n + row) * 4 * n;
-    for (int j = tid; j < n; j += DET_TPB)
+    for (int j = g.tid; j < n; j += g.n)
     {
       const T v = ph[j];
       phi[j]    = v;
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(DET_TPB)
       gl[2 * n + j] = ph[3 * fs + j];
       gl[3 * n + j] = ph[4 * fs + j];
     }
-    __syncthreads();
+    g.sync();
     for (int a = warp; a < c; a += nwarp)
     {
       T s(0);
@@ -179,35 +185,31 @@ __global__ void __launch_bounds__(DET_TPB)
       if (lane == 0)
         p[a] = -s;
     }
-    __syncthreads();
-    // determinant ratio = sum of the spline kernel's partial dots in index order
-    T ratio(0);
-    for (int q = 0; q < rg_nparts; ++q)
-      ratio += rg[((size_t)iw * rg_nparts + q) * 4];
+    g.sync();
     const T sigma = T(1) / ratio;
     const T* w    = D.wvec + (size_t)iw * k;
-    if (tid < c)
+    if (g.tid < c)
     {
       T s(0);
       for (int b = 0; b < c; ++b)
-        s += B[tid * k + b] * p[b];
-      y[tid] = sigma * s;
+        s += B[g.tid * k + b] * p[b];
+      y[g.tid] = sigma * s;
     }
-    __syncthreads();
-    for (int e = tid; e < c * c; e += DET_TPB)
+    g.sync();
+    for (int e = g.tid; e < c * c; e += g.n)
     {
       const int a = e / c, b = e - a * c;
       B[a * k + b] += y[a] * w[b];
     }
-    if (tid < c)
+    if (g.tid < c)
     {
-      B[tid * k + c] = y[tid];
-      B[c * k + tid] = sigma * w[tid];
+      B[g.tid * k + c] = y[g.tid];
+      B[c * k + g.tid] = sigma * w[g.tid];
     }
-    if (tid == 0)
+    if (g.tid == 0)
     {
-      B[c * k + c]                  = sigma;
-      D.list[(size_t)iw * k + c]    = row;
+      B[c * k + c]               = sigma;
+      D.list[(size_t)iw * k + c] = row;
       // log_value += log(curRatio) (complex log), DiracDeterminantBatched.cpp:501
       const double r = (double)ratio;
       D.logdet[2 * (size_t)iw] += log(fabs(r));
@@ -218,19 +220,37 @@ __global__ void __launch_bounds__(DET_TPB)
   else
   {
     // pseudo-accept: detail/OMPTarget/AccelMatrixUpdateOMPTarget.hpp:139-160
-    for (int j = tid; j < n; j += DET_TPB)
+    for (int j = g.tid; j < n; j += g.n)
       U[(size_t)c * n + j] = T(0);
-    if (tid < c)
+    if (g.tid < c)
     {
-      B[c * k + tid] = T(0);
-      B[tid * k + c] = T(0);
+      B[c * k + g.tid] = T(0);
+      B[g.tid * k + c] = T(0);
     }
-    if (tid == 0)
+    if (g.tid == 0)
     {
       B[c * k + c]               = T(1);
       D.list[(size_t)iw * k + c] = -1;
     }
   }
+}
+
+// rg[iw][part][0] = partial determinant ratios of the proposed move.  dynamic smem: (n + 2k) * sizeof(T)
+template<typename T>
+__global__ void __launch_bounds__(DET_TPB)
+    det_accept_kernel(const DetDev<T> D, const int row, const int c, const unsigned char* accepted, const T* rg,
+                      const int rg_nparts, const T* phi_vgl)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* phi = reinterpret_cast<T*>(smem_raw);
+  T* p   = phi + D.n;
+  T* y   = p + D.k;
+  const int iw = blockIdx.x;
+  // determinant ratio = sum of the spline kernel's partial dots in index order
+  T ratio(0);
+  for (int q = 0; q < rg_nparts; ++q)
+    ratio += rg[((size_t)iw * rg_nparts + q) * 4];
+  det_accept_body<T>(cta_group(), D, iw, row, c, accepted[iw] != 0, ratio, phi_vgl, phi, p, y);
 }
 
 // ---- Woodbury flush, first (SIMT) form: three small batched GEMMs with the -1 fix-up fused into the first.

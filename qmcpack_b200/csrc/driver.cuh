@@ -17,7 +17,11 @@ struct RngDev
   uint32_t* state;          // [624] mt19937 state vector
   uint32_t* ring;           // [ring_size] raw outputs
   unsigned long long* gen;  // number of raw outputs generated so far
-  unsigned long long* pos;  // number consumed so far
+  unsigned long long* pos;  // pos[2]: number consumed so far, double-buffered by move parity: the Metropolis test of
+                            // electron iat reads pos[iat & 1] and publishes pos[(iat + 1) & 1], so CTAs that start late
+                            // never see the value their own kernel wrote; the sweep prologue leaves its result in pos[0]
+  unsigned* sweep;          // sweeps started so far (epoch of the cross-CTA flags)
+  unsigned* flags;          // [nw] (epoch << 1 | needs_draw) published by each walker's CTA
   unsigned ring_mask;       // ring_size - 1 (power of two)
 };
 
@@ -51,8 +55,9 @@ __global__ void mt19937_seed_kernel(RngDev R, uint32_t seed)
       x          = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i;
       R.state[i] = x;
     }
-    *R.gen = 0;
-    *R.pos = 0;
+    *R.gen   = 0;
+    R.pos[0] = R.pos[1] = 0;
+    *R.sweep = 0;
   }
 }
 
@@ -68,7 +73,7 @@ __global__ void __launch_bounds__(256) mt19937_fill_kernel(RngDev R, unsigned lo
   if (tid == 0)
     s_gen = *R.gen;
   __syncthreads();
-  const unsigned long long pos = *R.pos;
+  const unsigned long long pos = R.pos[0]; // possibly stale (smaller): see the fork comment in enqueue_sweep
   unsigned long long gen       = s_gen;
   auto twist = [](uint32_t xi, uint32_t xi1, uint32_t xm) {
     const uint32_t y = (xi & 0x80000000u) | (xi1 & 0x7fffffffu);
@@ -128,13 +133,13 @@ __device__ __forceinline__ double rng_uniform(const RngDev& R, unsigned long lon
 // Gaussians of one sub-step: count = 3*nw*N values from pairs of uniforms starting at *pos; the kernel that runs last
 // in stream order (gauss_advance_kernel) moves *pos.
 template<typename RT>
-__global__ void gauss_kernel(RngDev R, RT* out, unsigned long long count)
+__global__ void gauss_kernel(RngDev R, RT* out, unsigned long long count, int last_parity)
 {
   const unsigned long long pair = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long i    = 2 * pair;
   if (i >= count)
     return;
-  const unsigned long long base   = *R.pos;
+  const unsigned long long base   = R.pos[last_parity]; // left by the last Metropolis test of the previous sweep
   const double slightly_less_one  = 1.0 - 2.220446049250313e-16;
   const double u1 = rng_uniform(R, base + i), u2 = rng_uniform(R, base + i + 1);
   const double t1 = sqrt(-2.0 * log(1.0 - slightly_less_one * u1));
@@ -145,10 +150,13 @@ __global__ void gauss_kernel(RngDev R, RT* out, unsigned long long count)
   if (i + 1 < count)
     out[i + 1] = (RT)(t1 * s);
 }
-__global__ void rng_advance_kernel(RngDev R, unsigned long long n)
+__global__ void rng_advance_kernel(RngDev R, unsigned long long n, int last_parity)
 {
   if (threadIdx.x == 0 && blockIdx.x == 0)
-    *R.pos += n;
+  {
+    R.pos[0] = R.pos[last_parity] + n;
+    *R.sweep += 1;
+  }
 }
 
 // ref: DriftModifierUNR.cpp:20-31 (a = 1)

@@ -248,14 +248,11 @@ __global__ void __launch_bounds__(JAS_TPB) jastrow_move_kernel(const JastrowDev<
   }
 }
 
-// ---- accept: J2 per-particle sums (BsplineFunctor.cpp:262-324), J1 commit, position commit.  grid = nw
+// ---- accept (walker iw, thread group g): J2 per-particle sums (BsplineFunctor.cpp:262-324), J1 commit, position commit
 template<typename RT>
-__global__ void __launch_bounds__(JAS_TPB)
-    jastrow_accept_kernel(const JastrowDev<RT> J, const int iat, const unsigned char* accepted)
+__device__ __forceinline__ void jastrow_accept_body(const Group& g, const JastrowDev<RT>& J, const int iw, const int iat)
 {
-  const int iw = blockIdx.x, tid = threadIdx.x, N = J.N, np = J.npad;
-  if (!accepted[iw])
-    return;
+  const int tid = g.tid, N = J.N, np = J.npad;
   if (J.has_j2)
   {
     const RT* rnew = J.rows + (size_t)iw * 4 * np;
@@ -267,8 +264,8 @@ __global__ void __launch_bounds__(JAS_TPB)
     const RT* vgl  = J.j2_vgl + (size_t)iw * 5;
     const int gi   = (iat < J.n_up ? 0 : 1) * 2;
     const RT Uold_iat = Uat[iat];
-    __syncthreads();
-    for (int j = tid; j < N; j += JAS_TPB)
+    g.sync();
+    for (int j = tid; j < N; j += g.n)
     {
       if (j == iat)
         continue;
@@ -297,15 +294,24 @@ __global__ void __launch_bounds__(JAS_TPB)
     const RT* cur = J.j1_cur + (size_t)iw * 5;
     RT* Vat       = J.Vat + (size_t)iw * N;
     J.j1_log[iw] += (double)(Vat[iat] - cur[0]); // J1OrbitalSoA.h:463
-    Vat[iat]                                  = cur[0];
-    J.Grad1[((size_t)iw * 3 + 0) * N + iat]   = cur[1];
-    J.Grad1[((size_t)iw * 3 + 1) * N + iat]   = cur[2];
-    J.Grad1[((size_t)iw * 3 + 2) * N + iat]   = cur[3];
-    J.Lap1[(size_t)iw * N + iat]              = cur[4];
+    Vat[iat]                                = cur[0];
+    J.Grad1[((size_t)iw * 3 + 0) * N + iat] = cur[1];
+    J.Grad1[((size_t)iw * 3 + 1) * N + iat] = cur[2];
+    J.Grad1[((size_t)iw * 3 + 2) * N + iat] = cur[3];
+    J.Lap1[(size_t)iw * N + iat]            = cur[4];
   }
   // ParticleSet::mw_accept_rejectMove (ParticleSet.cpp:717-758): commit the position
   if (tid < 3)
     J.rsoa[(size_t)iw * 3 * np + tid * np + iat] = J.newpos[3 * iw + tid];
+}
+
+template<typename RT>
+__global__ void __launch_bounds__(JAS_TPB)
+    jastrow_accept_kernel(const JastrowDev<RT> J, const int iat, const unsigned char* accepted)
+{
+  if (!accepted[blockIdx.x])
+    return;
+  jastrow_accept_body<RT>(cta_group(), J, blockIdx.x, iat);
 }
 
 // ---- from scratch (TwoBodyJastrow.cpp:667-713 lower-triangle form; J1OrbitalSoA.h:237-250).  grid = nw.
