@@ -197,7 +197,7 @@ def run_b200(args, rank, local_rank, world):
     crowd = api.Crowd(s, nw=nw, delay_rank=k, spo=spo)
     crowd.set_positions(R)
     crowd.mw_recompute()
-    crowd.vmc_init(tau=args.tau, use_drift=True, seed=1000 + rank, use_cuda_graph=True)
+    crowd.vmc_init(tau=args.tau, use_drift=True, seed=1000 + rank, use_cuda_graph=True)  # one stream per rank
     stream = torch.cuda.ExternalStream(crowd.stream, device=torch.device("cuda", local_rank))
     for _ in range(max(args.warmup, 3)):
         crowd.vmc_sweep_async()
@@ -222,13 +222,10 @@ def run_b200(args, rank, local_rank, world):
     # block estimator: kinetic energy of the walkers, reduced over ranks (the path's only collective: one small
     # all-reduce per block, EstimatorManagerNew.cpp:338,363)
     lp, ke, _, _ = crowd.mw_evaluateGL()
-    est = torch.tensor([ke.sum(), (ke * ke).sum(), float(nw), float((a1 - a0).sum()), float((r1 - r0).sum())],
-                       dtype=torch.float64, device="cuda")
-    tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist:
-        dist.all_reduce(est)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_max = float(tmax.item())
+    from qmcpack_b200 import sharding
+    est = sharding.reduce_block_estimator([ke.sum(), (ke * ke).sum(), float(nw), float((a1 - a0).sum()),
+                                           float((r1 - r0).sum())], dist, device="cuda")
+    ms_max = sharding.max_over_ranks(ms, dist, device="cuda")
     value = world * nw * N * args.steps / (ms_max * 1e-3)
     ke_mean = float(est[0] / est[2])
     sane = bool(np.isfinite(ke).all() and np.isfinite(lp).all())
@@ -297,13 +294,11 @@ def run_b200(args, rank, local_rank, world):
         drv.run(args.steps)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if dist:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt_max = sharding.max_over_ranks(dt, dist, device="cuda")
         h2d, d2h = drv.bytes_per_sweep()
-        e2e = {"value": world * nw * N * args.steps / float(tt.item()), "unit": UNIT,
+        e2e = {"value": world * nw * N * args.steps / dt_max, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "crowds": ncr,
-               "ms_per_step": 1e3 * float(tt.item()) / args.steps,
+               "ms_per_step": 1e3 * dt_max / args.steps,
                "path": "qmcb_host_vmc_run: per-electron qmcb_twf_mw_eval_grad / qmcb_ps_mw_make_move / "
                        "qmcb_twf_mw_calc_ratio_grad / qmcb_twf_mw_accept_reject with host buffers, accept test on the host"}
         del drv, crowds

@@ -5,6 +5,8 @@
 #include "det.cuh"
 #include "jastrow.cuh"
 #include "driver.cuh"
+#include "woodbury.cuh"
+#include <type_traits>
 #include <cublas_v2.h>
 #include <cmath>
 #include <cstring>
@@ -125,6 +127,112 @@ __global__ void j2_ratio_kernel(const JastrowDev<T> J, const int iat, double* ra
 // ------------------------------------------------------------------------------------------------------------
 constexpr int MB_TPB = 256;
 
+// Metropolis test of walker iw for electron iat_prev by ONE warp (all 32 lanes call it); returns acc and the determinant
+// ratio in lane 0
+template<typename T>
+__device__ __forceinline__ bool metropolis_warp(const DriverDev<T>& Dr, const JastrowDev<T>& J, const RngDev& R, const int iw,
+                                                const int iat_prev, const T* rg, const int rg_nparts, T& rdet_out)
+{
+  const int lane = threadIdx.x & 31;
+  // partial ratio/gradient dots of the spline kernel: lanes fetch, every lane adds in index order
+  T q[4] = {T(0), T(0), T(0), T(0)};
+  {
+    T mine[4] = {T(0), T(0), T(0), T(0)};
+    if (lane < rg_nparts)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        mine[e] = rg[((size_t)iw * rg_nparts + lane) * 4 + e];
+    for (int part = 0; part < rg_nparts && part < 32; ++part)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        q[e] += __shfl_sync(0xffffffffu, mine[e], part);
+    for (int part = 32; part < rg_nparts; ++part) // more than 32 parts (very wide determinants)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        q[e] += rg[((size_t)iw * rg_nparts + part) * 4 + e];
+  }
+  const unsigned long long base = R.pos[iat_prev & 1];
+  const unsigned sweep          = *R.sweep;
+  const T rdet = q[0];
+  double ratio = (double)rdet;
+  T gn[3]      = {q[1] / rdet, q[2] / rdet, q[3] / rdet};
+  if (J.has_j2)
+  {
+    const T* vgl = J.j2_vgl + (size_t)iw * 5;
+    ratio *= exp((double)(J.Uat[(size_t)iw * J.npad + iat_prev] - vgl[0]));
+    gn[0] += vgl[1];
+    gn[1] += vgl[2];
+    gn[2] += vgl[3];
+  }
+  if (J.has_j1)
+  {
+    const T* cur = J.j1_cur + (size_t)iw * 5;
+    ratio *= exp((double)(J.Vat[(size_t)iw * J.N + iat_prev] - cur[0]));
+    gn[0] += cur[1];
+    gn[1] += cur[2];
+    gn[2] += cur[3];
+  }
+  T log_gf = T(0), log_gb = T(0);
+  if (Dr.use_drift)
+  {
+    const T* dl = Dr.delta_cur + 3 * iw;
+    log_gf      = -Dr.oneover2tau * (dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
+    T dr[3];
+    get_drift<T>(Dr.tauovermass, gn, dr);
+    dr[0] += Dr.drifts[3 * iw];
+    dr[1] += Dr.drifts[3 * iw + 1];
+    dr[2] += Dr.drifts[3 * iw + 2];
+    log_gb = -Dr.oneover2tau * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
+  }
+  const T eps     = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
+  const T prob    = (T)(ratio * ratio);
+  const bool need = prob >= eps; // periodic cell: every move is valid
+  // ---- position of this walker's draw in the crowd's stream: look back over the lower-index walkers
+  const unsigned epoch = sweep * (unsigned)(Dr.N + 1) + (unsigned)iat_prev + 1u;
+  if (lane == 0)
+    *((volatile unsigned*)(R.flags + iw)) = (epoch << 1) | (need ? 1u : 0u);
+  unsigned cnt = 0;
+  for (int j = lane; j < iw; j += 32)
+  {
+    unsigned f;
+    do
+    {
+      f = *((volatile unsigned*)(R.flags + j));
+    } while ((f >> 1) != epoch);
+    cnt += f & 1u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  bool acc = false;
+  if (lane == 0)
+  {
+    if (need)
+    {
+      const double u = rng_uniform(R, base + cnt);
+      acc            = u < (double)(prob * exp(log_gb - log_gf));
+    }
+    if (iw == Dr.nw - 1)
+      R.pos[(iat_prev + 1) & 1] = base + cnt + (need ? 1u : 0u);
+    Dr.accepted[iw] = acc ? 1 : 0;
+    if (acc)
+      Dr.n_accept[iw] += 1;
+    else
+      Dr.n_reject[iw] += 1;
+    if (Dr.accept_log)
+      Dr.accept_log[(size_t)iat_prev * Dr.nw + iw] = acc ? 1 : 0;
+  }
+  rdet_out = rdet;
+  return acc;
+}
+
+// Phase A (independent of the Metropolis decision, overlapped with it):
+//   warp 7: Metropolis test.   warps 0-6: phi = new orbital row, x = Ainv[row_next], then the two big dot sweeps
+//   pA[a] = -V[a].phi (accept) and pB[a] = U[a].x (next row preparation) over the cA rows that are already final,
+//   two rows per warp iteration for memory-level parallelism.
+// Phase B: threads 0-127 determinant accept (small k x k work, U/GL row stores) then the rest of the row preparation
+//   (the one decision-dependent dot, w, x += V^T w, gradient); threads 128-255 Jastrow accept + position commit.
+// Then thread 0 proposes the next move.
 template<typename T>
 __global__ void __launch_bounds__(MB_TPB, 4)
     move_boundary_kernel(const DriverDev<T> Dr, const JastrowDev<T> J, const RngDev R, const DetDev<T> Dacc,
@@ -136,161 +244,136 @@ __global__ void __launch_bounds__(MB_TPB, 4)
   __shared__ T red[3 * 32];
   __shared__ int s_acc;
   __shared__ T s_ratio;
-  const int iw = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-  if (iat_prev >= 0)
+  const int iw = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool part1 = iat_prev >= 0, part2 = iat_next >= 0;
+  const int nA = part1 ? Dacc.n : 0, nB = part2 ? Dprep.n : 0, kk = part1 ? Dacc.k : Dprep.k;
+  T* phi = reinterpret_cast<T*>(smem_raw); // [nA]
+  T* x   = phi + nA;                       // [nB]
+  T* pA  = x + nB;                         // [k]  accept:  -V.phi
+  T* pB  = pA + kk;                        // [k]  prepare:  U.x
+  T* y   = pB + kk;                        // [k]
+  T* w   = y + kk;                         // [k]
+  // rows of U / V that are final before this kernel: the slot appended by part 1 (same determinant) is not
+  const bool same_det = part1 && part2 && Dacc.U == Dprep.U;
+  const int cA = part1 ? c_prev : 0;                         // rows for the accept dots
+  const int cB = part2 ? (same_det ? c_prev : c_next) : 0;   // rows for the decision-independent prepare dots
+
+  if (warp == 7)
   {
-    if (tid < 32)
+    if (part1)
     {
-      // ---- Metropolis test of this walker (warp 0)
-      // partial ratio/gradient dots of the spline kernel: lanes fetch, lane 0 adds in index order
-      T q[4] = {T(0), T(0), T(0), T(0)};
-      {
-        T mine[4] = {T(0), T(0), T(0), T(0)};
-        if (lane < rg_nparts)
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            mine[e] = rg[((size_t)iw * rg_nparts + lane) * 4 + e];
-        for (int part = 0; part < rg_nparts && part < 32; ++part)
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            q[e] += __shfl_sync(0xffffffffu, mine[e], part);
-        for (int part = 32; part < rg_nparts; ++part) // more than 32 parts (very wide determinants)
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            q[e] += rg[((size_t)iw * rg_nparts + part) * 4 + e];
-      }
-      const T rdet = q[0];
-      double ratio = (double)rdet;
-      T gn[3]      = {q[1] / rdet, q[2] / rdet, q[3] / rdet};
-      if (J.has_j2)
-      {
-        const T* vgl = J.j2_vgl + (size_t)iw * 5;
-        ratio *= exp((double)(J.Uat[(size_t)iw * J.npad + iat_prev] - vgl[0]));
-        gn[0] += vgl[1];
-        gn[1] += vgl[2];
-        gn[2] += vgl[3];
-      }
-      if (J.has_j1)
-      {
-        const T* cur = J.j1_cur + (size_t)iw * 5;
-        ratio *= exp((double)(J.Vat[(size_t)iw * J.N + iat_prev] - cur[0]));
-        gn[0] += cur[1];
-        gn[1] += cur[2];
-        gn[2] += cur[3];
-      }
-      T log_gf = T(0), log_gb = T(0);
-      if (Dr.use_drift)
-      {
-        const T* dl = Dr.delta_cur + 3 * iw;
-        log_gf      = -Dr.oneover2tau * (dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
-        T dr[3];
-        get_drift<T>(Dr.tauovermass, gn, dr);
-        dr[0] += Dr.drifts[3 * iw];
-        dr[1] += Dr.drifts[3 * iw + 1];
-        dr[2] += Dr.drifts[3 * iw + 2];
-        log_gb = -Dr.oneover2tau * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
-      }
-      const T eps     = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
-      const T prob    = (T)(ratio * ratio);
-      const bool need = prob >= eps; // periodic cell: every move is valid
-      // ---- position of this walker's draw in the crowd's stream: look back over the lower-index walkers
-      const unsigned epoch = (*R.sweep) * (unsigned)(Dr.N + 1) + (unsigned)iat_prev + 1u;
+      T rdet;
+      const bool acc = metropolis_warp<T>(Dr, J, R, iw, iat_prev, rg, rg_nparts, rdet);
       if (lane == 0)
       {
-        __threadfence();
-        *((volatile unsigned*)(R.flags + iw)) = (epoch << 1) | (need ? 1u : 0u);
-      }
-      unsigned cnt = 0;
-      for (int j = lane; j < iw; j += 32)
-      {
-        unsigned f;
-        do
-        {
-          f = *((volatile unsigned*)(R.flags + j));
-        } while ((f >> 1) != epoch);
-        cnt += f & 1u;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      if (lane == 0)
-      {
-        const unsigned long long base = R.pos[iat_prev & 1];
-        bool acc = false;
-        if (need)
-        {
-          const double u = rng_uniform(R, base + cnt);
-          acc            = u < (double)(prob * exp(log_gb - log_gf));
-        }
-        if (iw == Dr.nw - 1)
-          R.pos[(iat_prev + 1) & 1] = base + cnt + (need ? 1u : 0u);
         s_acc   = acc ? 1 : 0;
         s_ratio = rdet;
-        Dr.accepted[iw] = acc ? 1 : 0;
-        if (acc)
-          Dr.n_accept[iw] += 1;
-        else
-          Dr.n_reject[iw] += 1;
-        if (Dr.accept_log)
-          Dr.accept_log[(size_t)iat_prev * Dr.nw + iw] = acc ? 1 : 0;
       }
     }
-    __syncthreads();
-    const bool acc = s_acc != 0;
-    if (tid < MB_TPB / 2)
-    {
-      T* phi = reinterpret_cast<T*>(smem_raw);
-      T* p   = phi + Dacc.n;
-      T* y   = p + Dacc.k;
-      det_accept_body<T>(Group{tid, MB_TPB / 2, 1}, Dacc, iw, row_prev, c_prev, acc, s_ratio, phi_vgl, phi, p, y);
-    }
-    else if (acc)
-      jastrow_accept_body<T>(Group{tid - MB_TPB / 2, MB_TPB / 2, 2}, J, iw, iat_prev);
-    __syncthreads();
   }
-  if (iat_next >= 0)
+  else
   {
-    T* x = reinterpret_cast<T*>(smem_raw);
-    T* p = x + Dprep.n;
-    T* w = p + Dprep.k;
-    T g[3];
-    det_prepare_row_body<T>(cta_group(), Dprep, iw, row_next, c_next, x, p, w, red, Dr.use_drift != 0, g);
-    if (tid == 0)
+    const Group ga{tid, 7 * 32, 1};
+    if (part1)
     {
-      T delta[3], disp[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d)
-        delta[d] = Dr.deltas[((size_t)iat_next * Dr.nw + iw) * 3 + d] * Dr.sqrttau;
-      if (Dr.use_drift)
+      const T* ph = phi_vgl + (size_t)iw * nA;
+      for (int j = tid; j < nA; j += ga.n)
+        phi[j] = ph[j];
+    }
+    if (part2)
+    {
+      const T* arow = Dprep.Ainv + ((size_t)iw * nB + row_next) * Dprep.lda;
+      for (int j = tid; j < nB; j += ga.n)
+        x[j] = arow[j];
+    }
+    ga.sync();
+    const T* Va = part1 ? Dacc.V + (size_t)iw * Dacc.k * nA : nullptr;
+    const T* Ub = part2 ? Dprep.U + (size_t)iw * Dprep.k * nB : nullptr;
+    const int ntask = cA + cB;
+    for (int t0 = warp; t0 < ntask; t0 += 14)
+    {
+      const int t1    = t0 + 7;
+      const bool has1 = t1 < ntask;
+      const T* r0     = t0 < cA ? Va + (size_t)t0 * nA : Ub + (size_t)(t0 - cA) * nB;
+      const T* v0     = t0 < cA ? phi : x;
+      const int n0    = t0 < cA ? nA : nB;
+      const T* r1     = has1 ? (t1 < cA ? Va + (size_t)t1 * nA : Ub + (size_t)(t1 - cA) * nB) : r0;
+      const T* v1     = has1 ? (t1 < cA ? phi : x) : v0;
+      const int n1    = has1 ? (t1 < cA ? nA : nB) : 0;
+      T s0(0), s1(0);
+      const int nmax = n0 > n1 ? n0 : n1;
+      for (int j = lane; j < nmax; j += 32)
       {
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
+        if (j < n0)
+          s0 += r0[j] * v0[j];
+        if (j < n1)
+          s1 += r1[j] * v1[j];
+      }
+      s0 = warp_sum(s0);
+      s1 = warp_sum(s1);
+      if (lane == 0)
+      {
+        if (t0 < cA)
+          pA[t0] = -s0;
+        else
+          pB[t0 - cA] = s0;
+        if (has1)
         {
-          if (det_grads_out)
-            det_grads_out[3 * iw + d] = g[d];
-          if (J.has_j2)
-            g[d] += J.dUat[((size_t)iw * 3 + d) * J.npad + iat_next];
-          if (J.has_j1)
-            g[d] += J.Grad1[((size_t)iw * 3 + d) * J.N + iat_next];
+          if (t1 < cA)
+            pA[t1] = -s1;
+          else
+            pB[t1 - cA] = s1;
         }
-        get_drift<T>(Dr.tauovermass, g, disp);
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-          disp[d] += delta[d];
       }
-      else
-      {
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-          disp[d] = delta[d];
-      }
-#pragma unroll
-      for (int d = 0; d < 3; ++d)
-      {
-        Dr.drifts[3 * iw + d]    = disp[d];
-        Dr.delta_cur[3 * iw + d] = delta[d];
-        J.newpos[3 * iw + d]     = J.rsoa[((size_t)iw * 3 + d) * J.npad + iat_next] + disp[d];
-      }
+    }
+  }
+  __syncthreads();
+
+  T g[3] = {T(0), T(0), T(0)};
+  if (tid < MB_TPB / 2)
+  {
+    const Group gd{tid, MB_TPB / 2, 1};
+    if (part1)
+      det_accept_body<T>(gd, Dacc, iw, row_prev, c_prev, s_acc != 0, s_ratio, phi_vgl, phi, pA, y, true);
+    if (part2)
+    {
+      gd.sync(); // the row appended above (U[c], V[c], Binv) is read back below
+      det_prepare_row_body<T>(gd, Dprep, iw, row_next, c_next, x, pB, w, red, Dr.use_drift != 0, g, true, cB);
+    }
+  }
+  else if (part1 && s_acc != 0)
+    jastrow_accept_body<T>(Group{tid - MB_TPB / 2, MB_TPB / 2, 2}, J, iw, iat_prev);
+  __syncthreads();
+
+  if (part2 && tid < 32)
+  {
+    // proposal: lanes 0-2 own one Cartesian component each (independent loads), |g|^2 through shuffles
+    const int d = lane < 3 ? lane : 0;
+    const T delta = Dr.deltas[((size_t)iat_next * Dr.nw + iw) * 3 + d] * Dr.sqrttau;
+    const T rold  = J.rsoa[((size_t)iw * 3 + d) * J.npad + iat_next];
+    T disp        = delta;
+    if (Dr.use_drift)
+    {
+      // thread 0 holds the determinant gradient (every thread of the determinant group does after group_sum)
+      T gd = d == 0 ? g[0] : (d == 1 ? g[1] : g[2]);
+      if (det_grads_out && lane < 3)
+        det_grads_out[3 * iw + d] = gd;
+      if (J.has_j2)
+        gd += J.dUat[((size_t)iw * 3 + d) * J.npad + iat_next];
+      if (J.has_j1)
+        gd += J.Grad1[((size_t)iw * 3 + d) * J.N + iat_next];
+      const T g0 = __shfl_sync(0xffffffffu, gd, 0), g1 = __shfl_sync(0xffffffffu, gd, 1),
+              g2 = __shfl_sync(0xffffffffu, gd, 2);
+      const T gv[3] = {g0, g1, g2};
+      T dr[3];
+      get_drift<T>(Dr.tauovermass, gv, dr);
+      disp = (d == 0 ? dr[0] : (d == 1 ? dr[1] : dr[2])) + delta;
+    }
+    if (lane < 3)
+    {
+      Dr.drifts[3 * iw + d]    = disp;
+      Dr.delta_cur[3 * iw + d] = delta;
+      J.newpos[3 * iw + d]     = rold + disp;
     }
   }
 }
@@ -643,6 +726,28 @@ struct Crowd : CrowdBase
       return;
     const DetDev<T>& D = det[spin];
     const int n        = D.n;
+    if constexpr (std::is_same<T, float>::value)
+    {
+      // one-pass tensor-core flush (woodbury.cuh) whenever U, U' and a 64-row tile of Ainv fit in shared memory
+      const size_t smem = wb::smem_bytes_f32(n);
+      if (c <= wb::KD && n % 4 == 0 && smem <= 227 * 1024)
+      {
+        static bool attr_set = false;
+        if (!attr_set)
+        {
+          QMCB_CUDA(cudaFuncSetAttribute(wb::woodbury_flush_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024));
+          attr_set = true;
+        }
+        const int ntiles = (n + wb::RT - 1) / wb::RT;
+        const int split  = std::min(ntiles, 2);
+        wb::woodbury_flush_tf32_kernel<<<dim3(nw, split), wb::TPB, smem, st>>>(D, c);
+        QMCB_LAUNCH_CHECK();
+        delay_count[spin] = 0;
+        invrow_id[spin]   = -1;
+        return;
+      }
+    }
     // tempMat[n x c] = Ainv[n x n] * U^T, with the -1 fix-up (applyW) fused
     gemm_batched_kernel<T, true, true><<<dim3(blocks(c, 64), blocks(n, 64), nw), 256, 0, st>>>(
         n, c, n, T(1), D.Ainv, D.lda, (size_t)n * D.lda, D.U, n, (size_t)D.k * n, T(0), D.tempMat, D.k, (size_t)n * D.k,
@@ -1103,7 +1208,7 @@ struct Crowd : CrowdBase
       if (iat_prev >= 0 && iat_next >= 0 && igp == ign)
         cn = cp + 1; // the slot appended by part 1 of this very launch
       const int nmx     = std::max(iat_prev >= 0 ? det[igp].n : 0, iat_next >= 0 ? det[ign].n : 0);
-      const size_t smem = (size_t)(nmx + 2 * k) * sizeof(T);
+      const size_t smem = (size_t)(2 * nmx + 4 * k) * sizeof(T);
       move_boundary_kernel<T><<<nw, MB_TPB, smem, st>>>(drv, jas, rng, det[igp], iat_prev, rp, cp, rg.p, rg_nparts,
                                                         phi_vgl.p, det[ign], iat_next, rn, cn, det_grads.p);
       QMCB_LAUNCH_CHECK();

@@ -43,23 +43,27 @@ constexpr int DET_TPB = 256;
 
 // invRow = Ainv[row] - V^T (Binv^T (U Ainv[row]))  and  grad_now = invRow . dpsiM[row]   (walker iw, thread group g)
 // x[n], p[k], w[k] shared scratch; red >= 3*32.  On return every thread of the group holds grad_now in gout (if asked).
+// x_ready: x[] already holds Ainv[row]; p_ready: p[0..p_ready) = U[a].x already computed by the caller
 template<typename T>
 __device__ __forceinline__ void det_prepare_row_body(const Group& g, const DetDev<T>& D, const int iw, const int row,
                                                      const int c, T* x, T* p, T* w, T* red, const bool want_grads,
-                                                     T gout[3])
+                                                     T gout[3], const bool x_ready = false, const int p_ready = 0)
 {
   const int n = D.n, k = D.k;
   const int lane = g.tid & 31, warp = g.tid >> 5, nwarp = g.n >> 5;
-  const T* arow = D.Ainv + ((size_t)iw * n + row) * D.lda;
-  for (int j = g.tid; j < n; j += g.n)
-    x[j] = arow[j];
-  g.sync();
+  if (!x_ready)
+  {
+    const T* arow = D.Ainv + ((size_t)iw * n + row) * D.lda;
+    for (int j = g.tid; j < n; j += g.n)
+      x[j] = arow[j];
+    g.sync();
+  }
   if (c > 0)
   {
     const T* U = D.U + (size_t)iw * k * n;
     const T* V = D.V + (size_t)iw * k * n;
     const T* B = D.Binv + (size_t)iw * k * k;
-    for (int a = warp; a < c; a += nwarp)
+    for (int a = p_ready + warp; a < c; a += nwarp)
     {
       T s(0);
       for (int j = lane; j < n; j += 32)
@@ -147,9 +151,11 @@ __global__ void __launch_bounds__(DET_TPB) det_ratio_from_phi_kernel(const DetDe
 }
 
 // accept / pseudo-accept of slot c for walker iw by thread group g.  phi[n], p[k], y[k] shared scratch.
+// have_p: phi[] already holds the new orbital values and p[a] = -V[a].phi (a < c) was computed by the caller
 template<typename T>
 __device__ __forceinline__ void det_accept_body(const Group& g, const DetDev<T>& D, const int iw, const int row, const int c,
-                                                const bool acc, const T ratio, const T* phi_vgl, T* phi, T* p, T* y)
+                                                const bool acc, const T ratio, const T* phi_vgl, T* phi, T* p, T* y,
+                                                const bool have_p = false)
 {
   const int n = D.n, k = D.k;
   const int lane = g.tid & 31, warp = g.tid >> 5, nwarp = g.n >> 5;
@@ -167,7 +173,7 @@ __device__ __forceinline__ void det_accept_body(const Group& g, const DetDev<T>&
     T* gl       = D.GL + ((size_t)iw * n + row) * 4 * n;
     for (int j = g.tid; j < n; j += g.n)
     {
-      const T v = ph[j];
+      const T v = have_p ? phi[j] : ph[j];
       phi[j]    = v;
       U[(size_t)c * n + j] = v;
       gl[j]         = ph[fs + j];
@@ -176,16 +182,19 @@ __device__ __forceinline__ void det_accept_body(const Group& g, const DetDev<T>&
       gl[3 * n + j] = ph[4 * fs + j];
     }
     g.sync();
-    for (int a = warp; a < c; a += nwarp)
+    if (!have_p)
     {
-      T s(0);
-      for (int j = lane; j < n; j += 32)
-        s += V[(size_t)a * n + j] * phi[j];
-      s = warp_sum(s);
-      if (lane == 0)
-        p[a] = -s;
+      for (int a = warp; a < c; a += nwarp)
+      {
+        T s(0);
+        for (int j = lane; j < n; j += 32)
+          s += V[(size_t)a * n + j] * phi[j];
+        s = warp_sum(s);
+        if (lane == 0)
+          p[a] = -s;
+      }
+      g.sync();
     }
-    g.sync();
     const T sigma = T(1) / ratio;
     const T* w    = D.wvec + (size_t)iw * k;
     if (g.tid < c)

@@ -265,19 +265,53 @@ __device__ __forceinline__ void jastrow_accept_body(const Group& g, const Jastro
     const int gi   = (iat < J.n_up ? 0 : 1) * 2;
     const RT Uold_iat = Uat[iat];
     g.sync();
-    for (int j = tid; j < N; j += g.n)
+    // two elements per thread at a time: every load of a chunk is issued before the first store, so the HBM round trips
+    // overlap instead of queueing behind the read-modify-write stores (which the compiler must assume may alias)
+    constexpr int CH = 2;
+    for (int j0 = tid; j0 < N; j0 += CH * g.n)
     {
-      if (j == iat)
-        continue;
-      RT du, d2u;
-      const RT ro = rold[j];
-      const RT u  = functor_eval(J.F2[gi + (j < J.n_up ? 0 : 1)], ro, du, d2u);
-      const RT cu = cur[j], cdu = cur[np + j], cd2 = cur[2 * np + j];
-      Uat[j] += cu - u;
-      dU[j] -= rnew[np + j] * cdu - rold[np + j] * du;
-      dU[np + j] -= rnew[2 * np + j] * cdu - rold[2 * np + j] * du;
-      dU[2 * np + j] -= rnew[3 * np + j] * cdu - rold[3 * np + j] * du;
-      d2U[j] -= cd2 + RT(2) * cdu - (d2u + RT(2) * du);
+      RT ro[CH], ox[CH], oy[CH], oz[CH], nx[CH], ny[CH], nz[CH], cu[CH], cdu[CH], cd2[CH], ua[CH], da[CH], db[CH], dc[CH],
+          l2[CH];
+      bool on[CH];
+#pragma unroll
+      for (int q = 0; q < CH; ++q)
+      {
+        const int j = j0 + q * g.n;
+        on[q]       = j < N && j != iat;
+        if (on[q])
+        {
+          ro[q]  = rold[j];
+          ox[q]  = rold[np + j];
+          oy[q]  = rold[2 * np + j];
+          oz[q]  = rold[3 * np + j];
+          nx[q]  = rnew[np + j];
+          ny[q]  = rnew[2 * np + j];
+          nz[q]  = rnew[3 * np + j];
+          cu[q]  = cur[j];
+          cdu[q] = cur[np + j];
+          cd2[q] = cur[2 * np + j];
+          ua[q]  = Uat[j];
+          da[q]  = dU[j];
+          db[q]  = dU[np + j];
+          dc[q]  = dU[2 * np + j];
+          l2[q]  = d2U[j];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < CH; ++q)
+      {
+        const int j = j0 + q * g.n;
+        if (on[q])
+        {
+          RT du, d2u;
+          const RT u = functor_eval(J.F2[gi + (j < J.n_up ? 0 : 1)], ro[q], du, d2u);
+          Uat[j]         = ua[q] + (cu[q] - u);
+          dU[j]          = da[q] - (nx[q] * cdu[q] - ox[q] * du);
+          dU[np + j]     = db[q] - (ny[q] * cdu[q] - oy[q] * du);
+          dU[2 * np + j] = dc[q] - (nz[q] * cdu[q] - oz[q] * du);
+          d2U[j]         = l2[q] - (cd2[q] + RT(2) * cdu[q] - (d2u + RT(2) * du));
+        }
+      }
     }
     if (tid == 0)
     {
