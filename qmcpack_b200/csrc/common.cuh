@@ -65,7 +65,12 @@ struct DevBuf
       return;
     QMCB_CUDA(cudaMalloc(&p, count * sizeof(T)));
     if (zero)
+    {
+      // cudaMemset runs on the legacy default stream and is asynchronous to the host; the crowd streams are
+      // non-blocking, so without this wait a later kernel or copy on them could be overtaken by the memset
       QMCB_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+      QMCB_CUDA(cudaDeviceSynchronize());
+    }
   }
   size_t bytes() const { return n * sizeof(T); }
 };

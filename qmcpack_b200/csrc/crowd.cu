@@ -227,12 +227,13 @@ __device__ __forceinline__ bool metropolis_warp(const DriverDev<T>& Dr, const Ja
 }
 
 // Phase A (independent of the Metropolis decision, overlapped with it):
-//   warp 7: Metropolis test.   warps 0-6: phi = new orbital row, x = Ainv[row_next], then the two big dot sweeps
-//   pA[a] = -V[a].phi (accept) and pB[a] = U[a].x (next row preparation) over the cA rows that are already final,
-//   two rows per warp iteration for memory-level parallelism.
-// Phase B: threads 0-127 determinant accept (small k x k work, U/GL row stores) then the rest of the row preparation
-//   (the one decision-dependent dot, w, x += V^T w, gradient); threads 128-255 Jastrow accept + position commit.
-// Then thread 0 proposes the next move.
+//   warp 7: Metropolis test.   warps 0-6 stage into shared memory: phi_vgl rows of the proposed move, x = Ainv[row_next],
+//   vrow = Ainv[row_prev] (the future V[c]), the gradient rows of electron row_next, Binv and the previous w; then run
+//   the big dot sweeps pA[a] = -V[a].phi (accept) and pB[a] = U[a].x (next row preparation) over the rows that are
+//   already final, two rows per warp iteration for memory-level parallelism, plus phi.x for the slot being appended.
+// Phase B: threads 0-127: bordered update of Binv entirely in shared memory, row stores (U[c], V[c], G/L rows), then
+//   w = -Binv^T p, x += V^T w (one pass over V), inverse-row store and the gradient dot from the staged rows;
+//   threads 128-255: Jastrow accept + position commit.   Then warp 0 proposes the next move.
 template<typename T>
 __global__ void __launch_bounds__(MB_TPB, 4)
     move_boundary_kernel(const DriverDev<T> Dr, const JastrowDev<T> J, const RngDev R, const DetDev<T> Dacc,
@@ -246,17 +247,24 @@ __global__ void __launch_bounds__(MB_TPB, 4)
   __shared__ T s_ratio;
   const int iw = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool part1 = iat_prev >= 0, part2 = iat_next >= 0;
-  const int nA = part1 ? Dacc.n : 0, nB = part2 ? Dprep.n : 0, kk = part1 ? Dacc.k : Dprep.k;
-  T* phi = reinterpret_cast<T*>(smem_raw); // [nA]
-  T* x   = phi + nA;                       // [nB]
-  T* pA  = x + nB;                         // [k]  accept:  -V.phi
-  T* pB  = pA + kk;                        // [k]  prepare:  U.x
-  T* y   = pB + kk;                        // [k]
-  T* w   = y + kk;                         // [k]
-  // rows of U / V that are final before this kernel: the slot appended by part 1 (same determinant) is not
-  const bool same_det = part1 && part2 && Dacc.U == Dprep.U;
-  const int cA = part1 ? c_prev : 0;                         // rows for the accept dots
-  const int cB = part2 ? (same_det ? c_prev : c_next) : 0;   // rows for the decision-independent prepare dots
+  const int nA = part1 ? Dacc.n : 0, nB = part2 ? Dprep.n : 0, k = part1 ? Dacc.k : Dprep.k;
+  const int kb = k + 1; // padded row stride of the staged Binv (conflict-free row AND column walks)
+  T* phi   = reinterpret_cast<T*>(smem_raw); // [5][nA]  value, gx, gy, gz, lap of the proposed move
+  T* vrow  = phi + 5 * nA;                   // [nA]     Ainv[row_prev]
+  T* x     = vrow + nA;                      // [nB]     Ainv[row_next] -> inverse row
+  T* glrow = x + nB;                         // [3][nB]  gradient rows of electron row_next
+  T* Bs    = glrow + 3 * nB;                 // [k][k+1] Binv of the determinant being updated / prepared
+  T* pA    = Bs + k * kb;                    // [k]  accept:  -V.phi
+  T* pB    = pA + k;                         // [k]  prepare:  U.x
+  T* y     = pB + k;                         // [k]
+  T* w     = y + k;                          // [k]  new w
+  T* wold  = w + k;                          // [k]  w left by the previous preparation (needed by the bordered update)
+  // a spin change or a flush always splits the boundary, so when both parts are present they share the determinant
+  const bool same_det = part1 && part2;
+  const int cA = part1 ? c_prev : 0;                          // rows of V for the accept dots
+  const int cB = part2 ? (same_det ? c_prev : c_next) : 0;    // rows of U that are final before this kernel
+  const DetDev<T>& Dm = part1 ? Dacc : Dprep;                 // determinant whose Binv is staged
+  const int cM        = part1 ? c_prev : c_next;              // its pending count before this kernel
 
   if (warp == 7)
   {
@@ -276,30 +284,65 @@ __global__ void __launch_bounds__(MB_TPB, 4)
     const Group ga{tid, 7 * 32, 1};
     if (part1)
     {
-      const T* ph = phi_vgl + (size_t)iw * nA;
+      const size_t fs = (size_t)Dacc.nw * nA;
+      const T* ph     = phi_vgl + (size_t)iw * nA;
+      const T* arow   = Dacc.Ainv + ((size_t)iw * nA + row_prev) * Dacc.lda;
       for (int j = tid; j < nA; j += ga.n)
-        phi[j] = ph[j];
+      {
+        phi[j]          = ph[j];
+        phi[nA + j]     = ph[fs + j];
+        phi[2 * nA + j] = ph[2 * fs + j];
+        phi[3 * nA + j] = ph[3 * fs + j];
+        phi[4 * nA + j] = ph[4 * fs + j];
+        vrow[j]         = arow[j];
+      }
+      const T* wv = Dacc.wvec + (size_t)iw * k;
+      for (int b = tid; b < cA; b += ga.n)
+        wold[b] = wv[b];
     }
     if (part2)
     {
       const T* arow = Dprep.Ainv + ((size_t)iw * nB + row_next) * Dprep.lda;
+      const T* gl   = Dprep.GL + ((size_t)iw * nB + row_next) * 4 * nB;
       for (int j = tid; j < nB; j += ga.n)
-        x[j] = arow[j];
+      {
+        x[j]              = arow[j];
+        glrow[j]          = gl[j];
+        glrow[nB + j]     = gl[nB + j];
+        glrow[2 * nB + j] = gl[2 * nB + j];
+      }
+    }
+    {
+      const T* B = Dm.Binv + (size_t)iw * k * k;
+      for (int e = tid; e < cM * k; e += ga.n)
+      {
+        const int a = e / k, b = e - a * k;
+        if (b < cM)
+          Bs[a * kb + b] = B[a * k + b];
+      }
     }
     ga.sync();
-    const T* Va = part1 ? Dacc.V + (size_t)iw * Dacc.k * nA : nullptr;
-    const T* Ub = part2 ? Dprep.U + (size_t)iw * Dprep.k * nB : nullptr;
-    const int ntask = cA + cB;
+    const T* Va = part1 ? Dacc.V + (size_t)iw * k * nA : nullptr;
+    const T* Ub = part2 ? Dprep.U + (size_t)iw * k * nB : nullptr;
+    const int nspec = same_det ? 1 : 0; // phi.x for the slot this kernel appends (shared memory only)
+    const int ntask = cA + cB + nspec;
     for (int t0 = warp; t0 < ntask; t0 += 14)
     {
-      const int t1    = t0 + 7;
-      const bool has1 = t1 < ntask;
-      const T* r0     = t0 < cA ? Va + (size_t)t0 * nA : Ub + (size_t)(t0 - cA) * nB;
-      const T* v0     = t0 < cA ? phi : x;
-      const int n0    = t0 < cA ? nA : nB;
-      const T* r1     = has1 ? (t1 < cA ? Va + (size_t)t1 * nA : Ub + (size_t)(t1 - cA) * nB) : r0;
-      const T* v1     = has1 ? (t1 < cA ? phi : x) : v0;
-      const int n1    = has1 ? (t1 < cA ? nA : nB) : 0;
+      const int t1 = t0 + 7;
+      const T *r0, *v0, *r1, *v1;
+      int n0, n1 = 0;
+      auto pick = [&](int t, const T*& r, const T*& v, int& nn) {
+        if (t < cA)
+          r = Va + (size_t)t * nA, v = phi, nn = nA;
+        else if (t < cA + cB)
+          r = Ub + (size_t)(t - cA) * nB, v = x, nn = nB;
+        else
+          r = phi, v = x, nn = nB;
+      };
+      pick(t0, r0, v0, n0);
+      r1 = r0, v1 = v0;
+      if (t1 < ntask)
+        pick(t1, r1, v1, n1);
       T s0(0), s1(0);
       const int nmax = n0 > n1 ? n0 : n1;
       for (int j = lane; j < nmax; j += 32)
@@ -317,7 +360,7 @@ __global__ void __launch_bounds__(MB_TPB, 4)
           pA[t0] = -s0;
         else
           pB[t0 - cA] = s0;
-        if (has1)
+        if (t1 < ntask)
         {
           if (t1 < cA)
             pA[t1] = -s1;
@@ -333,12 +376,124 @@ __global__ void __launch_bounds__(MB_TPB, 4)
   if (tid < MB_TPB / 2)
   {
     const Group gd{tid, MB_TPB / 2, 1};
+    int cN = cM; // pending rows of the staged determinant after part 1
     if (part1)
-      det_accept_body<T>(gd, Dacc, iw, row_prev, c_prev, s_acc != 0, s_ratio, phi_vgl, phi, pA, y, true);
+    {
+      const bool acc = s_acc != 0;
+      const int c    = c_prev;
+      T* U           = Dacc.U + (size_t)iw * k * nA;
+      T* V           = Dacc.V + (size_t)iw * k * nA;
+      // rows: V[c] = Ainv[row_prev] for every walker (DelayedUpdateBatched.h:646); U[c] and the G/L rows on accept
+      T* gl = Dacc.GL + ((size_t)iw * nA + row_prev) * 4 * nA;
+      for (int j = tid; j < nA; j += gd.n)
+      {
+        V[(size_t)c * nA + j] = vrow[j];
+        U[(size_t)c * nA + j] = acc ? phi[j] : T(0);
+        if (acc)
+        {
+          gl[j]          = phi[nA + j];
+          gl[nA + j]     = phi[2 * nA + j];
+          gl[2 * nA + j] = phi[3 * nA + j];
+          gl[3 * nA + j] = phi[4 * nA + j];
+        }
+      }
+      if (acc)
+      {
+        // bordered update of Binv (DelayedUpdate.h:113-141) on the staged copy
+        const T sigma = T(1) / s_ratio;
+        if (tid < c)
+        {
+          T sacc(0);
+          for (int b = 0; b < c; ++b)
+            sacc += Bs[tid * kb + b] * pA[b];
+          y[tid] = sigma * sacc;
+        }
+        gd.sync();
+        for (int e = tid; e < c * c; e += gd.n)
+        {
+          const int a = e / c, b = e - a * c;
+          Bs[a * kb + b] += y[a] * wold[b];
+        }
+        if (tid < c)
+        {
+          Bs[tid * kb + c] = y[tid];
+          Bs[c * kb + tid] = sigma * wold[tid];
+        }
+        if (tid == 0)
+        {
+          Bs[c * kb + c]                = sigma;
+          Dacc.list[(size_t)iw * k + c] = row_prev;
+          const double r                = (double)s_ratio; // log_value += log(curRatio), DiracDeterminantBatched.cpp:501
+          Dacc.logdet[2 * (size_t)iw] += log(fabs(r));
+          if (r < 0)
+            Dacc.logdet[2 * (size_t)iw + 1] += 3.14159265358979323846;
+        }
+      }
+      else
+      {
+        // pseudo-accept: detail/OMPTarget/AccelMatrixUpdateOMPTarget.hpp:139-160
+        if (tid < c)
+        {
+          Bs[c * kb + tid] = T(0);
+          Bs[tid * kb + c] = T(0);
+        }
+        if (tid == 0)
+        {
+          Bs[c * kb + c]                = T(1);
+          Dacc.list[(size_t)iw * k + c] = -1;
+        }
+      }
+      cN = c + 1;
+      gd.sync();
+      // write the updated core back (rows/columns < cN)
+      T* B = Dacc.Binv + (size_t)iw * k * k;
+      for (int e = tid; e < cN * k; e += gd.n)
+      {
+        const int a = e / k, b = e - a * k;
+        if (b < cN)
+          B[a * k + b] = Bs[a * kb + b];
+      }
+    }
     if (part2)
     {
-      gd.sync(); // the row appended above (U[c], V[c], Binv) is read back below
-      det_prepare_row_body<T>(gd, Dprep, iw, row_next, c_next, x, pB, w, red, Dr.use_drift != 0, g, true, cB);
+      // p'[a] = U[a].x : rows < cB from phase A; the appended row is phi.x on accept and 0 for a pseudo-accept
+      if (same_det && tid == 0)
+        pB[c_prev] = s_acc != 0 ? pB[cB] : T(0);
+      gd.sync();
+      // w = -Binv^T p'  (DelayedUpdate.h:100-101), kept for the accept of this electron
+      if (tid < cN)
+      {
+        T sacc(0);
+        for (int a = 0; a < cN; ++a)
+          sacc += Bs[a * kb + tid] * pB[a];
+        w[tid]                            = -sacc;
+        Dprep.wvec[(size_t)iw * k + tid] = -sacc;
+      }
+      gd.sync();
+      // x += V^T w : rows < cB from HBM/L2, the row appended by part 1 from shared memory
+      const T* V = Dprep.V + (size_t)iw * k * nB;
+      T acc3[3]  = {T(0), T(0), T(0)};
+      T* out     = Dprep.invRow + (size_t)iw * nB;
+      for (int j = tid; j < nB; j += gd.n)
+      {
+        T sacc(0);
+        for (int a = 0; a < cB; ++a)
+          sacc += V[(size_t)a * nB + j] * w[a];
+        if (same_det)
+          sacc += vrow[j] * w[c_prev];
+        const T xv = x[j] + sacc;
+        out[j]     = xv;
+        acc3[0] += xv * glrow[j];
+        acc3[1] += xv * glrow[nB + j];
+        acc3[2] += xv * glrow[2 * nB + j];
+      }
+      if (Dr.use_drift)
+      {
+        group_sum<T, 3>(gd, acc3, red);
+        g[0] = acc3[0];
+        g[1] = acc3[1];
+        g[2] = acc3[2];
+      }
     }
   }
   else if (part1 && s_acc != 0)
@@ -437,7 +592,7 @@ struct Crowd : CrowdBase
   DevBuf<unsigned long long> rng_cnt, n_acc, n_rej;
   DevBuf<unsigned> rng_flags;
   DevBuf<unsigned char> accept_log;
-  bool vmc_ready = false, use_graph = false;
+  bool vmc_ready = false, use_graph = false, mb_attr_set = false;
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_logs = false;
   unsigned long long sweep_backlog = 0;
@@ -1208,7 +1363,12 @@ struct Crowd : CrowdBase
       if (iat_prev >= 0 && iat_next >= 0 && igp == ign)
         cn = cp + 1; // the slot appended by part 1 of this very launch
       const int nmx     = std::max(iat_prev >= 0 ? det[igp].n : 0, iat_next >= 0 ? det[ign].n : 0);
-      const size_t smem = (size_t)(2 * nmx + 4 * k) * sizeof(T);
+      const size_t smem = (size_t)(10 * nmx + k * (k + 1) + 5 * k) * sizeof(T);
+      if (smem > 48 * 1024 && !mb_attr_set)
+      {
+        QMCB_CUDA(cudaFuncSetAttribute(move_boundary_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        mb_attr_set = true;
+      }
       move_boundary_kernel<T><<<nw, MB_TPB, smem, st>>>(drv, jas, rng, det[igp], iat_prev, rp, cp, rg.p, rg_nparts,
                                                         phi_vgl.p, det[ign], iat_next, rn, cn, det_grads.p);
       QMCB_LAUNCH_CHECK();
