@@ -65,6 +65,28 @@ def workload_desc(cfg, args):
             f"(tau={args.tau}), delay_rank {c['k']}, {args.walkers} walkers/GPU")
 
 
+def ncu_traffic(kernel_substr="spline_gather_kernel"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
+    summary (profiles/), or None"""
+    import csv
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_full_*_summary.csv"))):
+        try:
+            rows = list(csv.reader(open(f)))
+            hdr, units = rows[0], rows[1]
+            i_name, i_r, i_w = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            vals = [float(r[i_r].replace(",", "")) * scale.get(units[i_r], 1.0) +
+                    float(r[i_w].replace(",", "")) * scale.get(units[i_w], 1.0)
+                    for r in rows[2:] if kernel_substr in r[i_name]]
+            if vals:
+                best = {"bytes_per_launch": sum(vals) / len(vals), "source": os.path.relpath(f, ROOT)}
+        except Exception:
+            pass
+    return best
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -265,8 +287,10 @@ def run_b200(args, rank, local_rank, world):
     achieved = b_spl * nw / t_spl / 1e9
     pk = peaks()
     peak = pk["hbm_gbs"] if pk else 6650.0
+    tr = ncu_traffic() if (args.config == "NiO-a64" and nw == 512) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "spline_gather_kernel (VGL + ratio/grad)",
+                "traffic": tr["bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None,
+                "kernel": "spline_gather_kernel (VGL + ratio/grad)",
                 "algorithmic_bytes_per_launch": b_spl * nw, "us_per_launch": t_spl * 1e6,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if pk else "fallback 6.65 TB/s",
                 "evals_per_s": nw / t_spl}

@@ -691,7 +691,7 @@ struct Crowd : CrowdBase
     A(ratios_d, nw);
     A(ke_d, nw);
     A(accepted, nw);
-    h_acc.alloc(nw);
+    h_acc.alloc(4 * (size_t)nw);
     h_t.alloc(std::max<size_t>((size_t)nw * 8, 64));
     h_d.alloc(std::max<size_t>((size_t)nw * 8, 64));
 
@@ -987,10 +987,14 @@ struct Crowd : CrowdBase
           g[3 * iw + d] = q[1 + d] / q[0]; // SPOSet.cpp:171 grads = dot / ratio
     }
   }
+  // pinned staging rotates over 4 slots: every move contains at least one stream sync after its accept call
+  // (calc_ratio_grad / eval_grad of the next electron), so a slot is long drained when it comes round again
+  int acc_slot = 0;
   void upload_flags(const uint8_t* acc)
   {
-    std::memcpy(h_acc.p, acc, nw);
-    QMCB_CUDA(cudaMemcpyAsync(accepted.p, h_acc.p, nw, cudaMemcpyHostToDevice, st));
+    unsigned char* h = h_acc.p + (size_t)(acc_slot++ & 3) * nw;
+    std::memcpy(h, acc, nw);
+    QMCB_CUDA(cudaMemcpyAsync(accepted.p, h, nw, cudaMemcpyHostToDevice, st));
   }
   void det_accept_reject(int spin, int row, const uint8_t* acc) override
   {
@@ -1174,7 +1178,7 @@ struct Crowd : CrowdBase
       launch_flush(spin);
     jastrow_accept_kernel<T><<<nw, JAS_TPB, 0, st>>>(jas, iat, accepted.p);
     QMCB_LAUNCH_CHECK();
-    sync(); // the pinned flag buffer is reused by the next call
+    // asynchronous like the reference's mw_accept_rejectMove ("this call may go asynchronous", TwoBodyJastrow.cpp:661)
   }
 
   void twf_complete_updates() override

@@ -27,11 +27,14 @@ constexpr int RT  = 32;  // Ainv rows per tile
 constexpr int KD  = 32;  // delay slots handled (c <= KD; unused slots are zero rows)
 constexpr int TPB = 256; // 8 warps
 
+// x = hi + lo with hi the TF32 truncation of x (mask, one LOP3) and lo = x - hi (exact in FP32; the tensor core reads
+// its top 19 bits).  cvt.rna.tf32 would round instead of truncate but runs on the slow conversion pipe: with two cvt per
+// operand element the split, not the MMA, bounded the kernel (measured: 803 us -> see DESIGN.md).  Truncation leaves a
+// relative error of 2^-20 per product, 16x below what the float inverse itself carries.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo)
 {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
 {
