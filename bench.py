@@ -158,6 +158,7 @@ def cpu_reference_run(cfg, args, steps, warmup, nw_cpu=None):
     c = workload.CONFIGS[cfg]
     nw = nw_cpu or args.cpu_walkers or 8 * cores
     ncrowds = min(cores, nw)
+    orc.lib.orc_set_threads(ncrowds)  # torchrun exports OMP_NUM_THREADS=1: the CPU arm must use every host core
     s = workload.make_system(N=c["N"], M=c["M"], dtype=c["dtype"])
     v = orc.vmc(s, nw=nw, ncrowds=ncrowds, seeds=[1000 + i for i in range(ncrowds)], tau=args.tau, use_drift=True,
                 delay_rank=c["k"], batched_engine=False)

@@ -207,6 +207,7 @@ int qmcb_spline_create(qmcb_spline** h, int precision, int kind, const int grid[
     require_device();
     auto* s = new qmcb_spline;
     s->impl.reset(make_spline(precision, kind, grid, n_orb, n_spl, npad, coefs_host, G, halfG, kcart));
+    QMCB_CUDA(cudaGetDevice(&s->impl->device));
     *h = s;
   });
 }
@@ -220,6 +221,7 @@ int qmcb_spline_mw_evaluate_value(qmcb_spline* h, int nw, const double* r_host, 
 {
   return guarded([&] {
     need(h, "spline");
+    QMCB_CUDA(cudaSetDevice(h->impl->device));
     need(r_host, "r_host");
     need(psi_host, "psi_host");
     if (h->impl->precision == QMCB_MIXED)
@@ -241,6 +243,7 @@ int qmcb_spline_mw_evaluate_vgl(qmcb_spline* h, int nw, const double* r_host, vo
 {
   return guarded([&] {
     need(h, "spline");
+    QMCB_CUDA(cudaSetDevice(h->impl->device));
     need(r_host, "r_host");
     if (h->impl->precision == QMCB_MIXED)
       spline_vgl_host<float>(h, nw, r_host, psi_host, dpsi_host, d2psi_host);
@@ -253,6 +256,7 @@ int qmcb_spline_mw_evaluate_vgl_ratio_grads(qmcb_spline* h, int nw, const double
 {
   return guarded([&] {
     need(h, "spline");
+    QMCB_CUDA(cudaSetDevice(h->impl->device));
     need(r_host, "r_host");
     need(invrow_host, "invrow_host");
     need(ratios_host, "ratios_host");
@@ -267,6 +271,7 @@ int qmcb_spline_mw_evaluate_det_ratios(qmcb_spline* h, int nvp, const double* r_
 {
   return guarded([&] {
     need(h, "spline");
+    QMCB_CUDA(cudaSetDevice(h->impl->device));
     need(r_vp_host, "r_vp_host");
     need(ref_walker_host, "ref_walker_host");
     need(invrow_host, "invrow_host");
@@ -300,6 +305,7 @@ int qmcb_spline_mw_vgl_ratio_grads_dev(qmcb_spline* h, int nw, const void* r_dev
 {
   return guarded([&] {
     need(h, "spline");
+    QMCB_CUDA(cudaSetDevice(h->impl->device));
     need(r_dev, "r_dev");
     h->impl->evaluate_dev(MODE_VGL, nw, r_dev, invrow_dev, ld_inv, nullptr, phi_vgl_dev, ratio_grad_dev,
                           static_cast<cudaStream_t>(stream));
@@ -317,6 +323,7 @@ int qmcb_crowd_create(qmcb_crowd** c, const qmcb_system* sys, int nw)
     require_device();
     auto* p = new qmcb_crowd;
     p->impl.reset(make_crowd(sys, nw));
+    QMCB_CUDA(cudaGetDevice(&p->impl->device));
     *c = p;
   });
 }
@@ -324,10 +331,11 @@ int qmcb_crowd_destroy(qmcb_crowd* c)
 {
   return guarded([&] { delete c; });
 }
-#define CROWD_CALL(expr)        \
-  return guarded([&] {          \
-    need(c, "crowd");           \
-    c->impl->expr;              \
+#define CROWD_CALL(expr)                        \
+  return guarded([&] {                          \
+    need(c, "crowd");                           \
+    QMCB_CUDA(cudaSetDevice(c->impl->device));  \
+    c->impl->expr;                              \
   })
 int qmcb_crowd_sync(qmcb_crowd* c) { CROWD_CALL(sync()); }
 size_t qmcb_crowd_device_bytes(const qmcb_crowd* c) { return c ? c->impl->device_bytes() : 0; }

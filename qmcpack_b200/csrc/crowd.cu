@@ -643,6 +643,10 @@ struct Crowd : CrowdBase
       if (!sys.spo[i])
         throw std::runtime_error("crowd: missing SPOSet handle");
       spo[i] = sys.spo[i]->impl.get();
+      int dev_now = 0;
+      QMCB_CUDA(cudaGetDevice(&dev_now));
+      if (spo[i]->device != dev_now)
+        throw std::runtime_error("crowd: the SPOSet lives on another CUDA device (tables are replicated per GPU)");
       if (spo[i]->precision != sys.precision || spo[i]->kind != QMCB_R2R)
         throw std::runtime_error("crowd: SPOSet precision/kind mismatch (real determinants need SplineR2R tables)");
       if (spo[i]->n_orb != nel[i])

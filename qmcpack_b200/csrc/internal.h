@@ -14,6 +14,7 @@ namespace qmcb
 // SPOSet (read-only table in HBM; evaluation scratch owned per call site)
 struct SplineSPOBase
 {
+  int device = 0; // CUDA device the table lives on (the current device at creation)
   int precision = 0, kind = 0;
   int grid[3]   = {0, 0, 0};
   int n_orb = 0, n_spl = 0;
@@ -40,6 +41,8 @@ SplineSPOBase* make_spline(int precision, int kind, const int grid[3], int n_orb
 // crowd = nw walkers with all wavefunction state; typed implementation behind a virtual interface
 struct CrowdBase
 {
+  int device = 0; // CUDA device of this crowd; every ABI entry binds the calling host thread to it (one crowd per
+                  // host thread, and new threads start on device 0)
   virtual ~CrowdBase() {}
   virtual void sync()                                                                                       = 0;
   virtual size_t device_bytes() const                                                                       = 0;
