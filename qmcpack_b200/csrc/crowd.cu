@@ -239,8 +239,10 @@ __global__ void __launch_bounds__(MB_TPB, 4)
     move_boundary_kernel(const DriverDev<T> Dr, const JastrowDev<T> J, const RngDev R, const DetDev<T> Dacc,
                          const int iat_prev, const int row_prev, const int c_prev, const T* rg, const int rg_nparts,
                          const T* phi_vgl, const DetDev<T> Dprep, const int iat_next, const int row_next, const int c_next,
-                         T* det_grads_out)
+                         T* det_grads_out, const unsigned char* ext_accept, T* twf_grads_out)
 {
+  // ext_accept != nullptr: host-driven mode (the Metropolis test ran on the host, flags come from the caller) and
+  // twf_grads_out receives the component-summed old gradient instead of a device-side proposal
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ T red[3 * 32];
   __shared__ int s_acc;
@@ -268,7 +270,17 @@ __global__ void __launch_bounds__(MB_TPB, 4)
 
   if (warp == 7)
   {
-    if (part1)
+    if (part1 && ext_accept)
+    {
+      if (lane == 0)
+      {
+        T q[4];
+        sum_rg_parts<T, 4>(rg, iw, rg_nparts, q);
+        s_acc   = ext_accept[iw] ? 1 : 0;
+        s_ratio = q[0];
+      }
+    }
+    else if (part1)
     {
       T rdet;
       const bool acc = metropolis_warp<T>(Dr, J, R, iw, iat_prev, rg, rg_nparts, rdet);
@@ -500,7 +512,20 @@ __global__ void __launch_bounds__(MB_TPB, 4)
     jastrow_accept_body<T>(Group{tid - MB_TPB / 2, MB_TPB / 2, 2}, J, iw, iat_prev);
   __syncthreads();
 
-  if (part2 && tid < 32)
+  if (part2 && twf_grads_out)
+  {
+    // host-driven mode: TrialWaveFunction::mw_evalGrad = determinant + J2 + J1 gradients of electron iat_next
+    if (tid < 3)
+    {
+      T gd = tid == 0 ? g[0] : (tid == 1 ? g[1] : g[2]);
+      if (J.has_j2)
+        gd += J.dUat[((size_t)iw * 3 + tid) * J.npad + iat_next];
+      if (J.has_j1)
+        gd += J.Grad1[((size_t)iw * 3 + tid) * J.N + iat_next];
+      twf_grads_out[3 * iw + tid] = gd;
+    }
+  }
+  else if (part2 && tid < 32)
   {
     // proposal: lanes 0-2 own one Cartesian component each (independent loads), |g|^2 through shuffles
     const int d = lane < 3 ? lane : 0;
@@ -762,6 +787,9 @@ struct Crowd : CrowdBase
         for (int g = 0; g < sys.n_ion_groups; ++g)
           patch(jas.F1[g]);
     }
+    std::memset(&drv_host, 0, sizeof(drv_host));
+    drv_host.nw = nw, drv_host.N = N, drv_host.use_drift = 1, drv_host.accepted = accepted.p;
+    std::memset(&rng, 0, sizeof(rng));
     QMCB_CUDA(cudaDeviceSynchronize());
   }
 
@@ -845,6 +873,7 @@ struct Crowd : CrowdBase
   // ---------------------------------------------------------------- positions
   void set_positions(const double* R) override
   {
+    flush_pending();
     std::vector<T> h((size_t)nw * 3 * npad, T(0));
     for (int iw = 0; iw < nw; ++iw)
       for (int i = 0; i < N; ++i)
@@ -855,6 +884,7 @@ struct Crowd : CrowdBase
   }
   void get_positions(double* R) override
   {
+    flush_pending();
     std::vector<T> h((size_t)nw * 3 * npad);
     QMCB_CUDA(cudaMemcpyAsync(h.data(), rsoa.p, h.size() * sizeof(T), cudaMemcpyDeviceToHost, st));
     sync();
@@ -944,6 +974,7 @@ struct Crowd : CrowdBase
 
   void det_eval_grad(int spin, int row, void* grads) override
   {
+    flush_pending();
     check_row(spin, row);
     launch_prepare(spin, row, det_grads.p);
     QMCB_CUDA(cudaMemcpyAsync(h_t.p, det_grads.p, (size_t)nw * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
@@ -952,6 +983,7 @@ struct Crowd : CrowdBase
   }
   void det_get_inv_row(int spin, int row, const void** dev, size_t* ld, void* host) override
   {
+    flush_pending();
     check_row(spin, row);
     ensure_row(spin, row);
     if (dev)
@@ -966,6 +998,7 @@ struct Crowd : CrowdBase
   }
   void det_ratio_grad(int spin, int row, void* ratios, void* grads, bool from_phi) override
   {
+    flush_pending();
     check_row(spin, row);
     ensure_row(spin, row);
     if (from_phi)
@@ -1002,6 +1035,7 @@ struct Crowd : CrowdBase
   }
   void det_accept_reject(int spin, int row, const uint8_t* acc) override
   {
+    flush_pending();
     check_row(spin, row);
     upload_flags(acc);
     launch_accept(spin, row, accepted.p, rg.p, phi_vgl.p);
@@ -1009,6 +1043,7 @@ struct Crowd : CrowdBase
   }
   void det_complete_updates(int spin, void* psiMinv, double* logdet_h) override
   {
+    flush_pending();
     if (spin < 0 || spin > 1)
       throw std::runtime_error("bad spin");
     launch_flush(spin);
@@ -1095,6 +1130,7 @@ struct Crowd : CrowdBase
   // ---------------------------------------------------------------- trial wavefunction level
   void twf_recompute() override
   {
+    flush_pending();
     for (int spin = 0; spin < 2; ++spin)
     {
       const int n = nel[spin];
@@ -1130,10 +1166,9 @@ struct Crowd : CrowdBase
   void twf_eval_grad(int iat, double* grads) override
   {
     check_iat(iat);
-    const int spin = spin_of(iat), row = iat - first[spin];
-    launch_prepare(spin, row, det_grads.p);
-    twf_grad_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, det_grads.p, grads_tmp.p);
-    QMCB_LAUNCH_CHECK();
+    // [accept of the previous electron, if one is pending] + inverse row + component-summed gradient: one launch
+    join_jastrow();
+    apply_pending(iat, grads_tmp.p);
     QMCB_CUDA(cudaMemcpyAsync(h_t.p, grads_tmp.p, (size_t)nw * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
     sync();
     for (int i = 0; i < 3 * nw; ++i)
@@ -1143,6 +1178,7 @@ struct Crowd : CrowdBase
   void ps_make_move(int iat, const double* dsp) override
   {
     check_iat(iat);
+    flush_pending();
     T* h = h_t.p + 4 * (size_t)nw; // second half of the staging buffer
     for (int i = 0; i < 3 * nw; ++i)
       h[i] = (T)dsp[i];
@@ -1151,17 +1187,33 @@ struct Crowd : CrowdBase
     QMCB_LAUNCH_CHECK();
     if (jas.has_j2 || jas.has_j1)
     {
-      jastrow_move_kernel<T><<<nw, JAS_TPB, 0, st>>>(jas, iat);
+      // distance rows + Jastrow sums run on the side stream, beside the spline gather of the coming ratio call
+      QMCB_CUDA(cudaEventRecord(ev_fork, st));
+      QMCB_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
+      jastrow_move_kernel<T><<<nw, JAS_TPB, 0, st2>>>(jas, iat);
       QMCB_LAUNCH_CHECK();
+      QMCB_CUDA(cudaEventRecord(ev_join, st2));
+      jastrow_inflight = true;
+    }
+  }
+  bool jastrow_inflight = false;
+  void join_jastrow()
+  {
+    if (jastrow_inflight)
+    {
+      QMCB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+      jastrow_inflight = false;
     }
   }
 
   void twf_calc_ratio_grad(int iat, double* ratios, double* grads) override
   {
     check_iat(iat);
+    flush_pending();
     const int spin = spin_of(iat), row = iat - first[spin];
     ensure_row(spin, row);
     launch_spline(spin, MODE_VGL, invRow[spin].p, det[spin].n, phi_vgl.p, rg.p, st);
+    join_jastrow();
     twf_ratio_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, rg.p, rg_nparts, ratios_d.p, grads_tmp.p);
     QMCB_LAUNCH_CHECK();
     QMCB_CUDA(cudaMemcpyAsync(h_d.p, ratios_d.p, (size_t)nw * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1175,18 +1227,21 @@ struct Crowd : CrowdBase
   void twf_accept_reject(int iat, const uint8_t* acc, int safe_to_delay) override
   {
     check_iat(iat);
-    const int spin = spin_of(iat), row = iat - first[spin];
+    flush_pending();
     upload_flags(acc);
-    launch_accept(spin, row, accepted.p, rg.p, phi_vgl.p);
-    if (!safe_to_delay)
-      launch_flush(spin);
-    jastrow_accept_kernel<T><<<nw, JAS_TPB, 0, st>>>(jas, iat, accepted.p);
-    QMCB_LAUNCH_CHECK();
+    // deferred: applied together with whatever the driver asks next (normally the gradient of the next electron);
     // asynchronous like the reference's mw_accept_rejectMove ("this call may go asynchronous", TwoBodyJastrow.cpp:661)
+    pending_iat = iat;
+    if (!safe_to_delay)
+    {
+      flush_pending();
+      launch_flush(spin_of(iat));
+    }
   }
 
   void twf_complete_updates() override
   {
+    flush_pending();
     launch_flush(0);
     launch_flush(1);
   }
@@ -1247,6 +1302,7 @@ struct Crowd : CrowdBase
   // ---------------------------------------------------------------- component level: DT rows + J2
   void dtaa_get_temp_rows(void* out) override
   {
+    flush_pending();
     if (!jas.has_j2)
       throw std::runtime_error("distance rows are only kept when a two-body Jastrow is present");
     // device [2][nw][4][npad] -> host [2][nw][4][N]
@@ -1256,6 +1312,7 @@ struct Crowd : CrowdBase
   }
   void j2_ratio_grad(int iat, double* ratios, void* grads) override
   {
+    flush_pending();
     check_iat(iat);
     if (!jas.has_j2)
       throw std::runtime_error("no two-body Jastrow in this crowd");
@@ -1268,6 +1325,7 @@ struct Crowd : CrowdBase
   }
   void j2_accept_reject(int iat, const uint8_t* acc) override
   {
+    flush_pending();
     check_iat(iat);
     upload_flags(acc);
     jastrow_accept_kernel<T><<<nw, JAS_TPB, 0, st>>>(jas, iat, accepted.p);
@@ -1276,6 +1334,7 @@ struct Crowd : CrowdBase
   }
   void j2_get_state(int iw, double* Uat_h, double* dUat_h, double* d2Uat_h) override
   {
+    flush_pending();
     if (!jas.has_j2 || iw < 0 || iw >= nw)
       throw std::runtime_error("j2_get_state: bad walker or no J2");
     std::vector<T> u(npad), du(3 * npad), d2(npad);
@@ -1337,6 +1396,78 @@ struct Crowd : CrowdBase
     vmc_ready = true;
   }
 
+  // one launch of move_boundary_kernel: accept of electron iat_prev (or -1) and row preparation of iat_next (or -1).
+  // ext_flags / twf_grads_out select the host-driven mode (Metropolis test done by the caller).
+  void launch_boundary(const DriverDev<T>& dr, int iat_prev, int iat_next, const unsigned char* ext_flags, T* twf_grads_out)
+  {
+    int igp = 0, rp = 0, ign = 0, rn = 0;
+    if (iat_prev >= 0)
+    {
+      igp = spin_of(iat_prev);
+      rp  = iat_prev - first[igp];
+    }
+    if (iat_next >= 0)
+    {
+      ign = spin_of(iat_next);
+      rn  = iat_next - first[ign];
+    }
+    if (iat_prev >= 0 && iat_next >= 0 && igp != ign)
+      throw std::runtime_error("launch_boundary: both parts must belong to one determinant");
+    const int cp = iat_prev >= 0 ? delay_count[igp] : 0;
+    int cn       = iat_next >= 0 ? delay_count[ign] : 0;
+    if (iat_prev >= 0 && iat_next >= 0)
+      cn = cp + 1; // the slot appended by part 1 of this very launch
+    const int nmx     = std::max(iat_prev >= 0 ? det[igp].n : 0, iat_next >= 0 ? det[ign].n : 0);
+    const size_t smem = (size_t)(10 * nmx + k * (k + 1) + 5 * k) * sizeof(T);
+    if (smem > 48 * 1024 && !mb_attr_set)
+    {
+      QMCB_CUDA(cudaFuncSetAttribute(move_boundary_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      mb_attr_set = true;
+    }
+    move_boundary_kernel<T><<<nw, MB_TPB, smem, st>>>(dr, jas, rng, det[igp], iat_prev, rp, cp, rg.p, rg_nparts, phi_vgl.p,
+                                                      det[ign], iat_next, rn, cn, det_grads.p, ext_flags, twf_grads_out);
+    QMCB_LAUNCH_CHECK();
+    if (iat_prev >= 0)
+    {
+      delay_count[igp]++;
+      invrow_id[igp] = -1;
+    }
+    if (iat_next >= 0)
+      invrow_id[ign] = rn;
+  }
+
+  // ---- host-driven mode: the accept of an electron is deferred until the next call tells what follows it, so that
+  // accept(iat) + evalGrad(iat+1) -- two consecutive calls of the reference's driver loop -- become ONE launch
+  int pending_iat = -1;
+  DriverDev<T> drv_host{};
+  void apply_pending(int iat_next, T* twf_grads_out)
+  {
+    if (pending_iat < 0)
+    {
+      if (iat_next >= 0)
+        launch_boundary(drv_host, -1, iat_next, accepted.p, twf_grads_out);
+      return;
+    }
+    const int prev = pending_iat, ig = spin_of(prev);
+    pending_iat    = -1;
+    const bool split = iat_next < 0 || spin_of(iat_next) != ig || delay_count[ig] + 1 == k;
+    if (!split)
+    {
+      launch_boundary(drv_host, prev, iat_next, accepted.p, twf_grads_out);
+      return;
+    }
+    launch_boundary(drv_host, prev, -1, accepted.p, nullptr);
+    if (delay_count[ig] == k)
+      launch_flush(ig);
+    if (iat_next >= 0)
+      launch_boundary(drv_host, -1, iat_next, accepted.p, twf_grads_out);
+  }
+  void flush_pending()
+  {
+    join_jastrow();
+    apply_pending(-1, nullptr);
+  }
+
   // enqueue one full sweep on `st` (st2 carries the RNG top-up and the Jastrow branch)
   void enqueue_sweep(bool log_accept)
   {
@@ -1356,38 +1487,7 @@ struct Crowd : CrowdBase
     QMCB_LAUNCH_CHECK();
     // per electron: [accept(iat-1) + prepare/propose(iat)] -> {spline gather || Jastrow rows}; the boundary kernel is
     // split in two around a Woodbury flush
-    auto spin_row = [&](int iat, int& ig, int& row) {
-      ig  = spin_of(iat);
-      row = iat - first[ig];
-    };
-    auto boundary = [&](int iat_prev, int iat_next) {
-      int igp = 0, rp = 0, ign = 0, rn = 0;
-      if (iat_prev >= 0)
-        spin_row(iat_prev, igp, rp);
-      if (iat_next >= 0)
-        spin_row(iat_next, ign, rn);
-      const int cp = iat_prev >= 0 ? delay_count[igp] : 0;
-      int cn       = iat_next >= 0 ? delay_count[ign] : 0;
-      if (iat_prev >= 0 && iat_next >= 0 && igp == ign)
-        cn = cp + 1; // the slot appended by part 1 of this very launch
-      const int nmx     = std::max(iat_prev >= 0 ? det[igp].n : 0, iat_next >= 0 ? det[ign].n : 0);
-      const size_t smem = (size_t)(10 * nmx + k * (k + 1) + 5 * k) * sizeof(T);
-      if (smem > 48 * 1024 && !mb_attr_set)
-      {
-        QMCB_CUDA(cudaFuncSetAttribute(move_boundary_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        mb_attr_set = true;
-      }
-      move_boundary_kernel<T><<<nw, MB_TPB, smem, st>>>(drv, jas, rng, det[igp], iat_prev, rp, cp, rg.p, rg_nparts,
-                                                        phi_vgl.p, det[ign], iat_next, rn, cn, det_grads.p);
-      QMCB_LAUNCH_CHECK();
-      if (iat_prev >= 0)
-      {
-        delay_count[igp]++;
-        invrow_id[igp] = -1;
-      }
-      if (iat_next >= 0)
-        invrow_id[ign] = rn;
-    };
+    auto boundary = [&](int iat_prev, int iat_next) { launch_boundary(drv, iat_prev, iat_next, nullptr, nullptr); };
     boundary(-1, 0);
     for (int iat = 0; iat < N; ++iat)
     {
@@ -1423,6 +1523,7 @@ struct Crowd : CrowdBase
 
   void vmc_sweep_async() override
   {
+    flush_pending();
     if (!vmc_ready)
       throw std::runtime_error("qmcb_vmc_init has not been called");
     launch_sweep(false);
@@ -1463,6 +1564,7 @@ struct Crowd : CrowdBase
 
   void vmc_sweep(int nsteps, uint8_t* log_host) override
   {
+    flush_pending();
     if (!vmc_ready)
       throw std::runtime_error("qmcb_vmc_init has not been called");
     for (int s = 0; s < nsteps; ++s)
