@@ -1209,7 +1209,7 @@ struct Crowd : CrowdBase
   void twf_calc_ratio_grad(int iat, double* ratios, double* grads) override
   {
     check_iat(iat);
-    flush_pending();
+    apply_pending(-1, nullptr); // (make_move already applied it; the Jastrow rows keep running beside the gather below)
     const int spin = spin_of(iat), row = iat - first[spin];
     ensure_row(spin, row);
     launch_spline(spin, MODE_VGL, invRow[spin].p, det[spin].n, phi_vgl.p, rg.p, st);

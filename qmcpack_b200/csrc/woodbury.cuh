@@ -25,7 +25,7 @@ namespace wb
 {
 constexpr int RT  = 32;  // Ainv rows per tile
 constexpr int KD  = 32;  // delay slots handled (c <= KD; unused slots are zero rows)
-constexpr int TPB = 256; // 8 warps
+constexpr int TPB = 512; // 16 warps: one CTA per SM (208 KB of shared memory), so the warps must come from the CTA
 
 // x = hi + lo with hi the TF32 truncation of x (mask, one LOP3) and lo = x - hi (exact in FP32; the tensor core reads
 // its top 19 bits).  cvt.rna.tf32 would round instead of truncate but runs on the slow conversion pipe: with two cvt per
@@ -65,7 +65,7 @@ inline size_t smem_bytes_f32(int n)
   return sizeof(float) * ((size_t)KD * stride_a(n)       /* Us   [KD][sa]     */
                           + (size_t)KD * stride_b(n)     /* Ups  [KD][sb]     */
                           + (size_t)2 * RT * stride_a(n) /* At   [2][RT][sa]  */
-                          + (size_t)RT * (KD + 4))       /* Ts   [RT][KD+4]   */
+                          + (size_t)2 * RT * (KD + 4))   /* Ts   [2][RT][KD+4] (one per K half) */
       + KD * sizeof(int);
 }
 
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(TPB, 1) woodbury_flush_tf32_kernel(const DetDe
   float* Ups = Us + (size_t)KD * sa;
   float* At0 = Ups + (size_t)KD * sb;
   float* Ts  = At0 + (size_t)2 * RT * sa;
-  int* lst   = reinterpret_cast<int*>(Ts + (size_t)RT * st);
+  int* lst   = reinterpret_cast<int*>(Ts + (size_t)2 * RT * st);
   const int iw = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const float* U = D.U + (size_t)iw * k * n;
@@ -171,15 +171,18 @@ __global__ void __launch_bounds__(TPB, 1) woodbury_flush_tf32_kernel(const DetDe
     cp_async_wait<1>();
     __syncthreads();
 
-    // ---- GEMM 1: T[RT x KD] = At[RT x n8] * Us^T ; 2 x 4 warp grid, one 16 x 8 tile per warp, three independent chains
+    // ---- GEMM 1: T[RT x KD] = At[RT x n8] * Us^T ; 2 (rows) x 4 (slots) x 2 (K halves) warps, one 16 x 8 tile each,
+    //      three independent accumulator chains (one per split product); the K halves are added when GEMM 2 loads T
     {
-      const int r0 = (warp & 1) * 16, a0 = (warp >> 1) * 8;
+      const int r0 = (warp & 1) * 16, a0 = ((warp >> 1) & 3) * 8, kh = warp >> 3;
+      const int kmid = ((n8 / 8 + 1) / 2) * 8;
+      const int kbeg = kh ? kmid : 0, kend = kh ? n8 : kmid;
       float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
       const float* Ar0 = At + (size_t)(r0 + g) * sa + t;
       const float* Ar1 = Ar0 + 8 * sa;
       const float* Ub  = Us + (size_t)(a0 + g) * sa + t;
 #pragma unroll 4
-      for (int kk = 0; kk < n8; kk += 8)
+      for (int kk = kbeg; kk < kend; kk += 8)
       {
         uint32_t ah[4], al[4], bh[2], bl[2];
         split_tf32(Ar0[kk], ah[0], al[0]);
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(TPB, 1) woodbury_flush_tf32_kernel(const DetDe
         mma_tf32(acc2, ah, bh);
       }
       // store -T (the second product then ADDS (-T) * U'); small terms first
-      float* d0 = Ts + (size_t)(r0 + g) * st + a0 + 2 * t;
+      float* d0 = Ts + (size_t)kh * RT * st + (size_t)(r0 + g) * st + a0 + 2 * t;
       d0[0]          = -((acc0[0] + acc1[0]) + acc2[0]);
       d0[1]          = -((acc0[1] + acc1[1]) + acc2[1]);
       d0[8 * st]     = -((acc0[2] + acc1[2]) + acc2[2]);
@@ -209,9 +212,9 @@ __global__ void __launch_bounds__(TPB, 1) woodbury_flush_tf32_kernel(const DetDe
     }
     __syncthreads();
 
-    // ---- GEMM 2: tile += (-T)[RT x KD] * U'[KD x n8] ; every warp owns all 32 rows x (n8/8)/8 column tiles
+    // ---- GEMM 2: tile += (-T)[RT x KD] * U'[KD x n8] ; every warp owns all 32 rows x (n8/8)/16 column tiles
     {
-      const int ntw = (n8 / 8 + 7) / 8; // 8-column tiles per warp (6 for n = 384)
+      const int ntw = (n8 / 8 + 15) / 16; // 8-column tiles per warp (3 for n = 384)
       const int j0  = warp * ntw * 8;
       uint32_t ah[2][4][4], al[2][4][4]; // [m-tile][k-step][frag]
 #pragma unroll
@@ -220,10 +223,11 @@ __global__ void __launch_bounds__(TPB, 1) woodbury_flush_tf32_kernel(const DetDe
         for (int ks = 0; ks < 4; ++ks)
         {
           const float* T0 = Ts + (size_t)(mt * 16 + g) * st + ks * 8 + t;
-          split_tf32(T0[0], ah[mt][ks][0], al[mt][ks][0]);
-          split_tf32(T0[8 * st], ah[mt][ks][1], al[mt][ks][1]);
-          split_tf32(T0[4], ah[mt][ks][2], al[mt][ks][2]);
-          split_tf32(T0[8 * st + 4], ah[mt][ks][3], al[mt][ks][3]);
+          const float* T1 = T0 + (size_t)RT * st; // second K half
+          split_tf32(T0[0] + T1[0], ah[mt][ks][0], al[mt][ks][0]);
+          split_tf32(T0[8 * st] + T1[8 * st], ah[mt][ks][1], al[mt][ks][1]);
+          split_tf32(T0[4] + T1[4], ah[mt][ks][2], al[mt][ks][2]);
+          split_tf32(T0[8 * st + 4] + T1[8 * st + 4], ah[mt][ks][3], al[mt][ks][3]);
         }
       for (int nt = 0; nt < ntw; ++nt)
       {
