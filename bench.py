@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--config", default="NiO-a64")
     ap.add_argument("--walkers", type=int, default=512, help="walkers per GPU")
     ap.add_argument("--crowds", type=int, default=4, help="crowds (host threads / streams) of the e2e host driver")
+    ap.add_argument("--device-crowds", type=int, default=4,
+                    help="crowds of the device-resident sweep: walkers/GPU are split over this many crowds, each with its own "
+                         "RNG stream and CUDA graph on its own stream (QMCDriverNew gives every crowd its own generator)")
     ap.add_argument("--tau", type=float, default=0.3)
     ap.add_argument("--cpu-walkers", type=int, default=0, help="walkers of the CPU sample (default 2 per core)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -217,34 +220,57 @@ def run_b200(args, rank, local_rank, world):
     R = workload.initial_positions(s, nw, seed=7 + 100003 * rank)  # every rank owns its own walkers (weak scaling)
 
     # ---------------- device-resident sweep (value)
-    crowd = api.Crowd(s, nw=nw, delay_rank=k, spo=spo)
-    crowd.set_positions(R)
-    crowd.mw_recompute()
-    crowd.vmc_init(tau=args.tau, use_drift=True, seed=1000 + rank, use_cuda_graph=True)  # one stream per rank
-    stream = torch.cuda.ExternalStream(crowd.stream, device=torch.device("cuda", local_rank))
+    ndc = max(1, min(args.device_crowds, nw))
+    dsizes = [nw // ndc + (1 if i < nw % ndc else 0) for i in range(ndc)]
+    dcrowds, streams, off = [], [], 0
+    for i in range(ndc):
+        cr = api.Crowd(s, nw=dsizes[i], delay_rank=k, spo=spo)
+        cr.set_positions(R[off:off + dsizes[i]])
+        cr.mw_recompute()
+        cr.vmc_init(tau=args.tau, use_drift=True, seed=1000 + 7919 * rank + i, use_cuda_graph=True)  # one stream per crowd
+        dcrowds.append(cr)
+        streams.append(torch.cuda.ExternalStream(cr.stream, device=torch.device("cuda", local_rank)))
+        off += dsizes[i]
+    crowd = dcrowds[0]
+
+    def counts():
+        a = np.concatenate([cr.vmc_counts()[0] for cr in dcrowds])
+        r = np.concatenate([cr.vmc_counts()[1] for cr in dcrowds])
+        return a, r
     for _ in range(max(args.warmup, 3)):
-        crowd.vmc_sweep_async()
-    crowd.sync()
-    a0, r0 = crowd.vmc_counts()
+        for cr in dcrowds:
+            cr.vmc_sweep_async()
+    for cr in dcrowds:
+        cr.sync()
+    a0, r0 = counts()
     launches0 = api.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    joins = [torch.cuda.Event() for _ in range(ndc - 1)]
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
     with ClockSampler(local_rank) as clk:
-        e0.record(stream)
+        e0.record(streams[0])
+        for st_i in streams[1:]:
+            st_i.wait_event(e0)
         for _ in range(args.steps):
-            crowd.vmc_sweep_async()
-        e1.record(stream)
-        crowd.sync()
+            for cr in dcrowds:
+                cr.vmc_sweep_async()
+        for ev, st_i in zip(joins, streams[1:]):
+            ev.record(st_i)
+            streams[0].wait_event(ev)
+        e1.record(streams[0])
+        for cr in dcrowds:
+            cr.sync()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     launches = api.kernel_launch_count() - launches0
-    a1, r1 = crowd.vmc_counts()
+    a1, r1 = counts()
     acc_rate = float((a1 - a0).sum() / max(1, ((a1 - a0) + (r1 - r0)).sum()))
     # block estimator: kinetic energy of the walkers, reduced over ranks (the path's only collective: one small
     # all-reduce per block, EstimatorManagerNew.cpp:338,363)
-    lp, ke, _, _ = crowd.mw_evaluateGL()
+    gl = [cr.mw_evaluateGL() for cr in dcrowds]
+    lp, ke = np.concatenate([g[0] for g in gl]), np.concatenate([g[1] for g in gl])
     from qmcpack_b200 import sharding
     est = sharding.reduce_block_estimator([ke.sum(), (ke * ke).sum(), float(nw), float((a1 - a0).sum()),
                                            float((r1 - r0).sum())], dist, device="cuda")
@@ -303,7 +329,7 @@ def run_b200(args, rank, local_rank, world):
         base, extra = divmod(nw, ncr)
         sizes = [base + (1 if i < extra else 0) for i in range(ncr)]
         crowds, off = [], 0
-        del crowd
+        del crowd, dcrowds, streams
         for i in range(ncr):
             cr = api.Crowd(s, nw=sizes[i], delay_rank=k, spo=spo)
             cr.set_positions(R[off:off + sizes[i]])
@@ -339,7 +365,7 @@ def run_b200(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if T == np.float32 else "f64", "data": "synthetic",
-            "config": {"workload": workload_desc(args.config, args), "walkers_per_gpu": nw, "electrons": N,
+            "config": {"workload": workload_desc(args.config, args), "walkers_per_gpu": nw, "device_crowds": ndc, "electrons": N,
                        "delay_rank": k, "table": "random orthogonal mixtures of the lowest plane waves (workload.pw_table)",
                        "l2": "inputs larger than L2: 2 x 384 MB spline tables + %.1f GB walker state vs 126 MB L2"
                              % (3.1 * nw / 512),
