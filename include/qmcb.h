@@ -103,6 +103,12 @@ int qmcb_crowd_create(qmcb_crowd** c, const qmcb_system* sys, int nw);
 int qmcb_crowd_destroy(qmcb_crowd* c);
 int qmcb_crowd_sync(qmcb_crowd* c);
 size_t qmcb_crowd_device_bytes(const qmcb_crowd* c);
+/* 1 when the crowd was created over SplineC2C tables: the determinant value type VT is then complex (the reference's
+ * QMC_COMPLEX build) and every VT / PsiValue / gradient buffer below holds interleaved (re, im) pairs:
+ *   component level (qmcb_det_*): VT = complex<float> (mixed) or complex<double> (full);
+ *   trial-wavefunction level (qmcb_twf_*): ratios [nw][2], grads [nw][3][2], G [nw][N][3][2], L [nw][N][2] doubles.
+ * The Jastrow factors, positions, drifts and the kinetic energy stay real.                                          */
+int qmcb_crowd_is_complex(const qmcb_crowd* c);
 /* ParticleSet::R for every walker, [nw][N][3] doubles (loadWalker) */
 int qmcb_crowd_set_positions(qmcb_crowd* c, const double* R_host);
 int qmcb_crowd_get_positions(qmcb_crowd* c, double* R_host);

@@ -258,6 +258,35 @@ int orc_invert_transpose_f(const float* a, int n, int a_cols, float* inv, int ld
   });
 }
 
+// complex variants: buffers are std::complex (interleaved re, im), FullPrecValueType = complex<double>
+int orc_invert_transpose_z(const std::complex<double>* a, int n, int a_cols, std::complex<double>* inv, int lda,
+                           double* logdet)
+{
+  return guarded([&] {
+    std::complex<double> ld;
+    kernel_invert_transpose(a, n, a_cols, inv, lda, ld);
+    logdet[0] = ld.real();
+    logdet[1] = ld.imag();
+  });
+}
+int orc_invert_transpose_c(const std::complex<float>* a, int n, int a_cols, std::complex<float>* inv, int lda, double* logdet)
+{
+  return guarded([&] {
+    std::complex<double> ld;
+    kernel_invert_transpose(a, n, a_cols, inv, lda, ld);
+    logdet[0] = ld.real();
+    logdet[1] = ld.imag();
+  });
+}
+} // extern "C"
+template<typename T>
+static inline T make_value(double re, double) { return (T)re; }
+template<>
+inline std::complex<double> make_value<std::complex<double>>(double re, double im) { return {re, im}; }
+template<>
+inline std::complex<float> make_value<std::complex<float>>(double re, double im) { return {(float)re, (float)im}; }
+extern "C" {
+
 // ---------------------------------------------------------------- delayed-update engine (one walker)
 #define ORC_DU(SUF, T)                                                                                                 \
   void* orc_du_create_##SUF(int n, int k)                                                                              \
@@ -271,9 +300,9 @@ int orc_invert_transpose_f(const float* a, int n, int a_cols, float* inv, int ld
   {                                                                                                                    \
     static_cast<Engine<T>*>(h)->getInvRow(Ainv, lda, row, invRow);                                              \
   }                                                                                                                    \
-  void orc_du_accept_row_##SUF(void* h, T* Ainv, int lda, int row, const T* psiV, double ratio)                        \
+  void orc_du_accept_row_##SUF(void* h, T* Ainv, int lda, int row, const T* psiV, double ratio, double ratio_im)       \
   {                                                                                                                    \
-    static_cast<Engine<T>*>(h)->acceptRow(Ainv, lda, row, psiV, (T)ratio);                                      \
+    static_cast<Engine<T>*>(h)->acceptRow(Ainv, lda, row, psiV, make_value<T>(ratio, ratio_im));                \
   }                                                                                                                    \
   void orc_du_pseudo_accept_row_##SUF(void* h, T* Ainv, int lda, int row)                                              \
   {                                                                                                                    \
@@ -284,6 +313,8 @@ int orc_invert_transpose_f(const float* a, int n, int a_cols, float* inv, int ld
 
 ORC_DU(d, double)
 ORC_DU(f, float)
+ORC_DU(z, std::complex<double>)
+ORC_DU(c, std::complex<float>)
 
 // ---------------------------------------------------------------- Jastrow functor + distance rows
 #define ORC_J(SUF, RT)                                                                                                 \
@@ -362,6 +393,8 @@ struct VMCHandle
   int precision;
   VMC<double, double, double>* d = nullptr;
   VMC<float, float, float>* f   = nullptr;
+  VMC<double, double, std::complex<double>>* zd = nullptr; // complex orbitals (SplineC2C), full precision
+  VMC<float, float, std::complex<float>>* cf    = nullptr; // complex orbitals, mixed precision
 };
 
 void* orc_vmc_create(const VMCParams* p)
@@ -370,7 +403,14 @@ void* orc_vmc_create(const VMCParams* p)
   int rc       = guarded([&] {
     h            = new VMCHandle;
     h->precision = p->precision;
-    if (p->precision == 0)
+    if (p->complex_orbitals)
+    {
+      if (p->precision == 0)
+        h->zd = new VMC<double, double, std::complex<double>>(*p);
+      else
+        h->cf = new VMC<float, float, std::complex<float>>(*p);
+    }
+    else if (p->precision == 0)
       h->d = new VMC<double, double, double>(*p);
     else
       h->f = new VMC<float, float, float>(*p);
@@ -384,6 +424,8 @@ void orc_vmc_destroy(void* hv)
     return;
   delete h->d;
   delete h->f;
+  delete h->zd;
+  delete h->cf;
   delete h;
 }
 #define VMC_DISPATCH(h, expr)                                                                                          \
@@ -394,9 +436,19 @@ void orc_vmc_destroy(void* hv)
       auto& v = *(h)->d;                                                                                               \
       expr;                                                                                                            \
     }                                                                                                                  \
-    else                                                                                                               \
+    else if ((h)->f)                                                                                                   \
     {                                                                                                                  \
       auto& v = *(h)->f;                                                                                               \
+      expr;                                                                                                            \
+    }                                                                                                                  \
+    else if ((h)->zd)                                                                                                  \
+    {                                                                                                                  \
+      auto& v = *(h)->zd;                                                                                              \
+      expr;                                                                                                            \
+    }                                                                                                                  \
+    else                                                                                                               \
+    {                                                                                                                  \
+      auto& v = *(h)->cf;                                                                                              \
       expr;                                                                                                            \
     }                                                                                                                  \
   } while (0)
@@ -443,8 +495,8 @@ int orc_vmc_evaluate_gl(void* hv, double* logpsi, double* ke, double* G, double*
 {
   auto* h = static_cast<VMCHandle*>(hv);
   return guarded([&] {
-    VMC_DISPATCH(h, for (int iw = 0; iw < v.nw; ++iw)
-                        v.evaluateGL(iw, G ? G + (size_t)iw * 3 * v.N : nullptr, L ? L + (size_t)iw * v.N : nullptr,
+    VMC_DISPATCH(h, const size_t cs = v.is_cplx ? 2 : 1; for (int iw = 0; iw < v.nw; ++iw)
+                        v.evaluateGL(iw, G ? G + (size_t)iw * 3 * v.N * cs : nullptr, L ? L + (size_t)iw * v.N * cs : nullptr,
                                      logpsi ? logpsi + iw : nullptr, ke ? ke + iw : nullptr));
   });
 }
@@ -458,13 +510,23 @@ int orc_vmc_get_counts(void* hv, long* n_accept, long* n_reject)
     });
   });
 }
-// psiMinv of spin s for walker iw, as doubles [n][n] (padding stripped); logdet (re)
+} // extern "C"
+static inline void put_value(double* out, size_t i, double v) { out[i] = v; }
+static inline void put_value(double* out, size_t i, float v) { out[i] = v; }
+template<typename R>
+static inline void put_value(double* out, size_t i, const std::complex<R>& v)
+{
+  out[2 * i]     = v.real();
+  out[2 * i + 1] = v.imag();
+}
+extern "C" {
+// psiMinv of spin s for walker iw, as doubles [n][n] (padding stripped; complex: [n][n][2]); logdet (re)
 int orc_vmc_get_psiminv(void* hv, int iw, int s, double* out, double* logdet)
 {
   auto* h = static_cast<VMCHandle*>(hv);
   return guarded([&] {
     VMC_DISPATCH(h, auto& d = v.walkers[iw].det[s]; for (int i = 0; i < d.n; ++i) for (int j = 0; j < d.n; ++j)
-                                                         out[(size_t)i * d.n + j] = d.psiMinv[(size_t)i * d.lda + j];
+                                                         put_value(out, (size_t)i * d.n + j, d.psiMinv[(size_t)i * d.lda + j]);
                  if (logdet) *logdet = d.log_value.real());
   });
 }

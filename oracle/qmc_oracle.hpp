@@ -510,6 +510,48 @@ struct SplineR2R
   int size() const { return norb; }
 };
 
+// ref: BsplineFactory/SplineC2C.cpp:200-277 assign_vgl (same arithmetic in ApplyPhaseC2C.hpp:48-118): complex orbital j
+// from the real component pair (2j, 2j+1) of the VGH scratch, twist phase from the CARTESIAN position r
+template<typename ST, typename VT>
+inline void c2c_assign_vgl(const LatticeG& lat, size_t np, int norb, const ST* myV, const ST* myG, const ST* myH, const ST* kx,
+                           const ST* ky, const ST* kz, const ST* mKK, const ST r[3], VT* psi, VT* dpsi, VT* d2psi)
+{
+  constexpr ST two(2);
+  const ST g00 = lat.G[0], g01 = lat.G[1], g02 = lat.G[2], g10 = lat.G[3], g11 = lat.G[4], g12 = lat.G[5],
+           g20 = lat.G[6], g21 = lat.G[7], g22 = lat.G[8];
+  const ST x = r[0], y = r[1], z = r[2];
+  const ST symGG[6] = {ST(lat.GGt[0]), ST(lat.GGt[1]) + ST(lat.GGt[3]), ST(lat.GGt[2]) + ST(lat.GGt[6]),
+                       ST(lat.GGt[4]), ST(lat.GGt[5]) + ST(lat.GGt[7]), ST(lat.GGt[8])};
+  const ST *g0 = myG, *g1 = g0 + np, *g2 = g0 + 2 * np;
+  const ST *h00 = myH, *h01 = h00 + np, *h02 = h00 + 2 * np, *h11 = h00 + 3 * np, *h12 = h00 + 4 * np,
+           *h22 = h00 + 5 * np;
+  for (int j = 0; j < norb; ++j)
+  {
+    const size_t jr = 2 * (size_t)j, ji = jr + 1;
+    const ST kX = kx[j], kY = ky[j], kZ = kz[j];
+    const ST val_r = myV[jr], val_i = myV[ji];
+    const ST ph = -(x * kX + y * kY + z * kZ);
+    const ST s = std::sin(ph), c = std::cos(ph);
+    const ST dX_r = g00 * g0[jr] + g01 * g1[jr] + g02 * g2[jr];
+    const ST dY_r = g10 * g0[jr] + g11 * g1[jr] + g12 * g2[jr];
+    const ST dZ_r = g20 * g0[jr] + g21 * g1[jr] + g22 * g2[jr];
+    const ST dX_i = g00 * g0[ji] + g01 * g1[ji] + g02 * g2[ji];
+    const ST dY_i = g10 * g0[ji] + g11 * g1[ji] + g12 * g2[ji];
+    const ST dZ_i = g20 * g0[ji] + g21 * g1[ji] + g22 * g2[ji];
+    const ST gX_r = dX_r + val_i * kX, gY_r = dY_r + val_i * kY, gZ_r = dZ_r + val_i * kZ;
+    const ST gX_i = dX_i - val_r * kX, gY_i = dY_i - val_r * kY, gZ_i = dZ_i - val_r * kZ;
+    const ST lcart_r = SymTrace(h00[jr], h01[jr], h02[jr], h11[jr], h12[jr], h22[jr], symGG);
+    const ST lcart_i = SymTrace(h00[ji], h01[ji], h02[ji], h11[ji], h12[ji], h22[ji], symGG);
+    const ST lap_r   = lcart_r + mKK[j] * val_r + two * (kX * dX_i + kY * dY_i + kZ * dZ_i);
+    const ST lap_i   = lcart_i + mKK[j] * val_i - two * (kX * dX_r + kY * dY_r + kZ * dZ_r);
+    psi[j]           = VT(c * val_r - s * val_i, c * val_i + s * val_r);
+    dpsi[3 * j + 0]  = VT(c * gX_r - s * gX_i, c * gX_i + s * gX_r);
+    dpsi[3 * j + 1]  = VT(c * gY_r - s * gY_i, c * gY_i + s * gY_r);
+    dpsi[3 * j + 2]  = VT(c * gZ_r - s * gZ_i, c * gZ_i + s * gZ_r);
+    d2psi[j]         = VT(c * lap_r - s * lap_i, c * lap_i + s * lap_r);
+  }
+}
+
 // Complex orbitals from a table of 2*norb real components + twist phase.
 // ref: BsplineFactory/SplineC2C.cpp:146-168 (assign_v), :200-277 (assign_vgl), identical math in
 // ApplyPhaseC2C.hpp:20-118; kpoints: myKcart[j], mKK[j] = -|k_j|^2 (SplineC2C.h / BsplineSet.h:48-52).
@@ -584,40 +626,9 @@ struct SplineC2C
     toUnit_floor(r, ru);
     const size_t np = tab.npad;
     evaluate_vgh(tab, ru[0], ru[1], ru[2], myV.data(), myG.data(), myH.data(), np);
-    constexpr ST two(2);
-    const ST g00 = lat.G[0], g01 = lat.G[1], g02 = lat.G[2], g10 = lat.G[3], g11 = lat.G[4], g12 = lat.G[5],
-             g20 = lat.G[6], g21 = lat.G[7], g22 = lat.G[8];
-    const ST x = r[0], y = r[1], z = r[2];
-    const ST symGG[6] = {ST(lat.GGt[0]), ST(lat.GGt[1]) + ST(lat.GGt[3]), ST(lat.GGt[2]) + ST(lat.GGt[6]),
-                         ST(lat.GGt[4]), ST(lat.GGt[5]) + ST(lat.GGt[7]), ST(lat.GGt[8])};
-    const ST *g0 = myG.data(), *g1 = g0 + np, *g2 = g0 + 2 * np;
-    const ST *h00 = myH.data(), *h01 = h00 + np, *h02 = h00 + 2 * np, *h11 = h00 + 3 * np, *h12 = h00 + 4 * np,
-             *h22 = h00 + 5 * np;
-    for (int j = 0; j < norb; ++j)
-    {
-      const size_t jr = 2 * (size_t)j, ji = jr + 1;
-      const ST kX = kx[j], kY = ky[j], kZ = kz[j];
-      const ST val_r = myV[jr], val_i = myV[ji];
-      const ST ph = -(x * kX + y * kY + z * kZ);
-      const ST s = std::sin(ph), c = std::cos(ph);
-      const ST dX_r = g00 * g0[jr] + g01 * g1[jr] + g02 * g2[jr];
-      const ST dY_r = g10 * g0[jr] + g11 * g1[jr] + g12 * g2[jr];
-      const ST dZ_r = g20 * g0[jr] + g21 * g1[jr] + g22 * g2[jr];
-      const ST dX_i = g00 * g0[ji] + g01 * g1[ji] + g02 * g2[ji];
-      const ST dY_i = g10 * g0[ji] + g11 * g1[ji] + g12 * g2[ji];
-      const ST dZ_i = g20 * g0[ji] + g21 * g1[ji] + g22 * g2[ji];
-      const ST gX_r = dX_r + val_i * kX, gY_r = dY_r + val_i * kY, gZ_r = dZ_r + val_i * kZ;
-      const ST gX_i = dX_i - val_r * kX, gY_i = dY_i - val_r * kY, gZ_i = dZ_i - val_r * kZ;
-      const ST lcart_r = SymTrace(h00[jr], h01[jr], h02[jr], h11[jr], h12[jr], h22[jr], symGG);
-      const ST lcart_i = SymTrace(h00[ji], h01[ji], h02[ji], h11[ji], h12[ji], h22[ji], symGG);
-      const ST lap_r   = lcart_r + mKK[j] * val_r + two * (kX * dX_i + kY * dY_i + kZ * dZ_i);
-      const ST lap_i   = lcart_i + mKK[j] * val_i - two * (kX * dX_r + kY * dY_r + kZ * dZ_r);
-      psi[j]           = VT(c * val_r - s * val_i, c * val_i + s * val_r);
-      dpsi[3 * j + 0]  = VT(c * gX_r - s * gX_i, c * gX_i + s * gX_r);
-      dpsi[3 * j + 1]  = VT(c * gY_r - s * gY_i, c * gY_i + s * gY_r);
-      dpsi[3 * j + 2]  = VT(c * gZ_r - s * gZ_i, c * gZ_i + s * gZ_r);
-      d2psi[j]         = VT(c * lap_r - s * lap_i, c * lap_i + s * lap_r);
-    }
+    const ST rc[3] = {ST(r[0]), ST(r[1]), ST(r[2])};
+    c2c_assign_vgl<ST, VT>(lat, np, norb, myV.data(), myG.data(), myH.data(), kx.data(), ky.data(), kz.data(), mKK.data(), rc,
+                           psi, dpsi, d2psi);
   }
   int size() const { return norb; }
 };
@@ -755,18 +766,31 @@ inline void lu_invert_colmajor(T* a, int n, int lda, std::complex<double>& logde
 
 // invert_transpose: amat is psiM [n][n_cols>=n] row-major (row = electron, col = orbital), invMat is
 // [n][lda] row-major and receives (psiM^-1)^T, computed in double, cast to VT.
+// FPVT of a value type: double for real VT, std::complex<double> for complex VT (Configuration.h FullPrecValueType)
+template<typename VT>
+struct FullPrec
+{
+  using type = double;
+};
+template<typename R>
+struct FullPrec<std::complex<R>>
+{
+  using type = std::complex<double>;
+};
+
 template<typename VT>
 inline void invert_transpose(const VT* amat, int n, int a_cols, VT* invMat, int lda, std::complex<double>& logdet)
 {
+  using FP = typename FullPrec<VT>::type;
   // simd::transpose(amat) -> psiM_fp[n][lda] row-major; that buffer read column-major by LAPACK is amat.
-  std::vector<double> fp((size_t)n * lda, 0.0);
+  std::vector<FP> fp((size_t)n * lda, FP(0));
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j)
-      fp[(size_t)j * lda + i] = (double)amat[(size_t)i * a_cols + j];
+      fp[(size_t)j * lda + i] = static_cast<FP>(amat[(size_t)i * a_cols + j]);
   lu_invert_colmajor(fp.data(), n, lda, logdet);
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j)
-      invMat[(size_t)i * lda + j] = (VT)fp[(size_t)i * lda + j];
+      invMat[(size_t)i * lda + j] = static_cast<VT>(fp[(size_t)i * lda + j]);
 }
 
 // =====================================================================================

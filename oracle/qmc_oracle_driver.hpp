@@ -53,6 +53,9 @@ struct VMCParams
   int use_drift;
   int delay_rank;
   int batched_engine; // 1: DelayedUpdateBatched semantics (crowd-wide delay_count + pseudo-accept); 0: per-walker DelayedUpdate
+  // complex orbitals (SplineC2C): tables hold 2*n real components per spin, kpts[s] = [n][3] Cartesian twist vectors
+  int complex_orbitals;
+  const double* kpts[2];
 };
 
 #ifndef QMC_ORACLE_USE_REFERENCE
@@ -75,6 +78,17 @@ struct VMC
 {
   using J2 = TwoBodyJastrow<RT>;
   using J1 = OneBodyJastrow<RT>;
+  // complex build of the reference: ValueType = complex<RT>, PsiValue = complex<double> (Configuration.h:QMCTraits)
+  static constexpr bool is_cplx = !std::is_same<VT, RT>::value;
+  using PsiV                    = typename FullPrec<VT>::type;
+  static RT real_of(const VT& v)
+  {
+    // convertToReal (type_traits/ConvertToReal.h:37-44): the real part
+    if constexpr (is_cplx)
+      return v.real();
+    else
+      return v;
+  }
 
   struct Det
   {
@@ -84,7 +98,7 @@ struct VMC
     int invRow_id = -1;
     Engine<VT> eng;
     std::complex<double> log_value;
-    double curRatio = 1.0;
+    PsiV curRatio = PsiV(1);
   };
 
   struct Walker
@@ -116,6 +130,7 @@ struct VMC
   LatticeG latG;
   MinImage<RT> mi;
   SplineTable<ST> tab[2];
+  std::vector<ST> kx[2], ky[2], kz[2], mKK[2]; // complex orbitals only (BsplineSet.h:48-52 kPoints / mKK)
   J2 j2;
   J1 j1;
   bool has_j2 = false, has_j1 = false;
@@ -141,8 +156,23 @@ struct VMC
       G[i] = tmp.g[i];
     latG.set(G, nullptr);
     mi.set(R);
+    if (is_cplx != (p.complex_orbitals != 0))
+      throw std::runtime_error("oracle VMC: complex_orbitals does not match the instantiated value type");
     for (int s = 0; s < 2; ++s)
-      tab[s].set(static_cast<const ST*>(p.coefs[s]), p.grid, s == 0 ? p.n_up : p.n_dn, p.npad);
+    {
+      const int n = s == 0 ? p.n_up : p.n_dn;
+      tab[s].set(static_cast<const ST*>(p.coefs[s]), p.grid, is_cplx ? 2 * n : n, p.npad);
+      if (is_cplx)
+      {
+        kx[s].resize(n), ky[s].resize(n), kz[s].resize(n), mKK[s].resize(n);
+        for (int j = 0; j < n; ++j)
+        {
+          const double* kk = p.kpts[s] + 3 * (size_t)j;
+          kx[s][j] = kk[0], ky[s][j] = kk[1], kz[s][j] = kk[2];
+          mKK[s][j] = -(kk[0] * kk[0] + kk[1] * kk[1] + kk[2] * kk[2]);
+        }
+      }
+    }
     std::vector<int> gids(N);
     for (int i = 0; i < N; ++i)
       gids[i] = group_of(i);
@@ -225,6 +255,34 @@ struct VMC
   // ---- SPO evaluation for one walker at `pos` for spin s: fills phi_vgl[5][n] (SplineR2R.cpp:338-412)
   void spoVGL(Walker& w, int s, const RT pos[3], VT* psi, VT* dpsi /*AoS*/, VT* d2psi)
   {
+    if constexpr (is_cplx)
+    {
+      // SplineC2C::evaluateVGL (SplineC2C.cpp:280-300): toUnit_floor, VGH of the 2n real components, assign_vgl
+      ST ru[3];
+      for (int j = 0; j < 3; ++j)
+      {
+        ST v = ST(0);
+        for (int i = 0; i < 3; ++i)
+          v += ST(pos[i]) * ST(latG.G[i * 3 + j]);
+        ru[j] = v;
+      }
+      for (int i = 0; i < 3; i++) // CrystalLattice.h:187-198
+        if (-std::numeric_limits<ST>::epsilon() < ru[i] && ru[i] < 0)
+          ru[i] = ST(0.0);
+        else
+          ru[i] -= std::floor(ru[i]);
+      const SplineTable<ST>& t = tab[s];
+      kernel_vgh(t, ru[0], ru[1], ru[2], w.myV.data(), w.myG.data(), w.myH.data(), t.npad);
+      const ST rc[3] = {ST(pos[0]), ST(pos[1]), ST(pos[2])};
+      c2c_assign_vgl<ST, VT>(latG, t.npad, t.ns / 2, w.myV.data(), w.myG.data(), w.myH.data(), kx[s].data(), ky[s].data(),
+                             kz[s].data(), mKK[s].data(), rc, psi, dpsi, d2psi);
+      return;
+    }
+    else
+      spoVGL_real(w, s, pos, psi, dpsi, d2psi);
+  }
+  void spoVGL_real(Walker& w, int s, const RT pos[3], VT* psi, VT* dpsi /*AoS*/, VT* d2psi)
+  {
     ST ru[3];
     const int bc_sign       = convertPos<ST, RT>(latG, pos, ru);
     const SplineTable<ST>& t = tab[s];
@@ -241,11 +299,11 @@ struct VMC
     const int n = t.ns;
     for (int j = 0; j < n; ++j)
     {
-      psi[j]          = signed_one * w.myV[j];
-      dpsi[3 * j + 0] = signed_one * (g00 * g0[j] + g01 * g1[j] + g02 * g2[j]);
-      dpsi[3 * j + 1] = signed_one * (g10 * g0[j] + g11 * g1[j] + g12 * g2[j]);
-      dpsi[3 * j + 2] = signed_one * (g20 * g0[j] + g21 * g1[j] + g22 * g2[j]);
-      d2psi[j]        = signed_one * SymTrace(h00[j], h01[j], h02[j], h11[j], h12[j], h22[j], symGG);
+      psi[j]          = VT(signed_one * w.myV[j]);
+      dpsi[3 * j + 0] = VT(signed_one * (g00 * g0[j] + g01 * g1[j] + g02 * g2[j]));
+      dpsi[3 * j + 1] = VT(signed_one * (g10 * g0[j] + g11 * g1[j] + g12 * g2[j]));
+      dpsi[3 * j + 2] = VT(signed_one * (g20 * g0[j] + g21 * g1[j] + g22 * g2[j]));
+      d2psi[j]        = VT(signed_one * SymTrace(h00[j], h01[j], h02[j], h11[j], h12[j], h22[j], symGG));
     }
   }
 
@@ -267,7 +325,7 @@ struct VMC
       kernel_invert_transpose(psiM.data(), n, n, d.psiMinv.data(), d.lda, d.log_value);
       d.eng.delay_count = 0;
       d.invRow_id       = -1;
-      d.curRatio        = 1.0;
+      d.curRatio        = PsiV(1);
     }
     if (has_j2)
       j2.recompute(w.j2, mi, w.rsoa.data(), npad_pos);
@@ -306,7 +364,7 @@ struct VMC
       return;
     const bool use_drift = prm.use_drift != 0;
     std::vector<RT> log_gf(cw, RT(0)), log_gb(cw, RT(0)), prob(cw);
-    std::vector<double> ratios(cw);
+    std::vector<PsiV> ratios(cw);
     std::vector<RT> deltas(3 * (size_t)cw), drifts(3 * (size_t)cw), grads_now(3 * (size_t)cw),
         grads_new(3 * (size_t)cw);
     std::vector<char> isAccepted(cw);
@@ -345,7 +403,8 @@ struct VMC
               g[1] += d.invRow[j] * dp[3 * j + 1];
               g[2] += d.invRow[j] * dp[3 * j + 2];
             }
-            RT gt[3] = {RT(g[0]), RT(g[1]), RT(g[2])};
+            // complex gradients reach the drift through convertToReal (DriftModifierUNR.cpp:20-23): real part
+            RT gt[3] = {real_of(g[0]), real_of(g[1]), real_of(g[2])};
             if (has_j2)
               for (int dd = 0; dd < 3; ++dd)
                 gt[dd] += w.j2.dUat[dd * j2.npad + iat]; // TwoBodyJastrow::evalGrad (:524-528)
@@ -407,13 +466,13 @@ struct VMC
             gy += d.invRow[j] * dpsi[3 * j + 1];
             gz += d.invRow[j] * dpsi[3 * j + 2];
           }
-          d.curRatio = (double)ratio;
-          RT gn[3]   = {RT(gx / ratio), RT(gy / ratio), RT(gz / ratio)};
-          double r   = d.curRatio;
+          d.curRatio = static_cast<PsiV>(ratio);
+          RT gn[3]   = {real_of(gx / ratio), real_of(gy / ratio), real_of(gz / ratio)};
+          PsiV r     = d.curRatio;
           if (has_j2)
-            r *= j2.ratioGrad(w.j2, iat, w.dist_new.data(), gn);
+            r *= (double)j2.ratioGrad(w.j2, iat, w.dist_new.data(), gn);
           if (has_j1)
-            r *= j1.ratioGrad(w.j1, mi, iat, w.newpos, gn);
+            r *= (double)j1.ratioGrad(w.j1, mi, iat, w.newpos, gn);
           ratios[i] = r;
           for (int dd = 0; dd < 3; ++dd)
             grads_new[3 * i + dd] = gn[dd];
@@ -433,7 +492,7 @@ struct VMC
           }
         }
         for (int i = 0; i < cw; ++i)
-          prob[i] = (RT)(ratios[i] * ratios[i]); // std::norm of a real PsiValue
+          prob[i] = (RT)std::norm(ratios[i]); // VMCBatched.cpp:152 (squared modulus; x*x for a real PsiValue)
 
         // accept test: RNG consumed only if the first two conditions hold (VMCBatched.cpp:156-158)
         for (int i = 0; i < cw; ++i)
@@ -447,7 +506,15 @@ struct VMC
           if (forced)
             isAccepted[i] = forced[(size_t)iat * nw + cr.w0 + i];
           if (ratio_log)
-            ratio_log[(size_t)iat * nw + cr.w0 + i] = ratios[i];
+          {
+            if constexpr (is_cplx)
+            {
+              ratio_log[2 * ((size_t)iat * nw + cr.w0 + i)]     = ratios[i].real();
+              ratio_log[2 * ((size_t)iat * nw + cr.w0 + i) + 1] = ratios[i].imag();
+            }
+            else
+              ratio_log[(size_t)iat * nw + cr.w0 + i] = ratios[i];
+          }
         }
 
         // TWF::mw_accept_rejectMove -> determinant, J2, J1; then ParticleSet::mw_accept_rejectMove
@@ -459,7 +526,7 @@ struct VMC
           d.invRow_id = -1;
           if (isAccepted[i])
           {
-            if (d.curRatio == 0.0)
+            if (d.curRatio == PsiV(0))
               throw std::runtime_error("oracle: accepted move with curRatio == 0");
             d.log_value += std::log(std::complex<double>(d.curRatio));
             const int n = d.n;
@@ -475,7 +542,7 @@ struct VMC
             // batched engine: sigma = Value(1)/ratios_local (VT arithmetic, DelayedUpdateBatched.h:599);
             // CPU engine: RATIOT = PsiValue(double)
             if (batched)
-              d.eng.acceptRow(d.psiMinv.data(), d.lda, row, w.phi_vgl.data(), (VT)d.curRatio);
+              d.eng.acceptRow(d.psiMinv.data(), d.lda, row, w.phi_vgl.data(), static_cast<VT>(d.curRatio));
             else
               d.eng.acceptRow(d.psiMinv.data(), d.lda, row, w.phi_vgl.data(), d.curRatio);
             if (has_j2)
@@ -495,7 +562,7 @@ struct VMC
               d.eng.pseudoAcceptRow(d.psiMinv.data(), d.lda, row);
             w.n_reject++;
           }
-          d.curRatio = 1.0;
+          d.curRatio = PsiV(1);
           if (acc_log)
             acc_log[(size_t)iat * nw + cr.w0 + i] = isAccepted[i];
         }
@@ -519,7 +586,7 @@ struct VMC
     {
       uint8_t* lg       = log_accept ? accept_log.data() + (size_t)step * N * nw : nullptr;
       const uint8_t* fc = forced ? forced + (size_t)step * N * nw : nullptr;
-      double* rl        = ratio_log ? ratio_log + (size_t)step * N * nw : nullptr;
+      double* rl        = ratio_log ? ratio_log + (size_t)step * N * nw * (is_cplx ? 2 : 1) : nullptr;
 #pragma omp parallel for schedule(static, 1)
       for (int c = 0; c < (int)crowds.size(); ++c)
         advanceCrowd(crowds[c], lg, fc, rl);
@@ -529,10 +596,13 @@ struct VMC
   // ---- G, L of all particles and kinetic energy -1/2 sum(L + G.G)  (mw_evaluateGL, fromscratch=false;
   // DiracDeterminantBatched.cpp:594-604 computeGL; TwoBodyJastrow.cpp:769-808; J1OrbitalSoA.h:112-123;
   // QMCHamiltonians/BareKineticEnergy: KE = -1/2 (sum L + sum G.G), L = laplacian of log psi)
+  // complex value type: G [N][3][2], L [N][2] interleaved; KE = -1/2 (Sum(L) + Dot(G,G)) with the reference's complex
+  // form real(CplxDot(G,G) + CplxSum(L)) = sum(re*re - im*im) + sum(re L) (QMCHamiltonians/BareKineticEnergy.cpp:114,
+  // Platforms/CPU/VectorOps.h:141-152)
   void evaluateGL(int iw, double* G /*[N][3]*/, double* L /*[N]*/, double* logpsi, double* ke)
   {
     Walker& w = walkers[iw];
-    std::vector<RT> g(3 * (size_t)N, RT(0)), l(N, RT(0));
+    std::vector<VT> g(3 * (size_t)N, VT(0)), l(N, VT(0));
     for (int s = 0; s < 2; ++s)
     {
       Det& d = w.det[s];
@@ -573,13 +643,35 @@ struct VMC
     double kin = 0;
     for (int i = 0; i < N; ++i)
     {
-      kin += (double)l[i] + (double)g[3 * i] * g[3 * i] + (double)g[3 * i + 1] * g[3 * i + 1] +
-          (double)g[3 * i + 2] * g[3 * i + 2];
-      if (G)
+      if constexpr (is_cplx)
+      {
+        kin += (double)l[i].real();
         for (int dd = 0; dd < 3; ++dd)
-          G[3 * i + dd] = g[3 * i + dd];
-      if (L)
-        L[i] = l[i];
+        {
+          const double re = g[3 * i + dd].real(), im = g[3 * i + dd].imag();
+          kin += re * re - im * im;
+          if (G)
+          {
+            G[2 * (3 * i + dd)]     = re;
+            G[2 * (3 * i + dd) + 1] = im;
+          }
+        }
+        if (L)
+        {
+          L[2 * i]     = l[i].real();
+          L[2 * i + 1] = l[i].imag();
+        }
+      }
+      else
+      {
+        kin += (double)l[i] + (double)g[3 * i] * g[3 * i] + (double)g[3 * i + 1] * g[3 * i + 1] +
+            (double)g[3 * i + 2] * g[3 * i + 2];
+        if (G)
+          for (int dd = 0; dd < 3; ++dd)
+            G[3 * i + dd] = g[3 * i + dd];
+        if (L)
+          L[i] = l[i];
+      }
     }
     if (ke)
       *ke = -0.5 * kin;

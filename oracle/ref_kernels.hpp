@@ -107,7 +107,7 @@ inline void kernel_invert_transpose(const VT* amat, int n, int a_cols, VT* inv, 
 {
   if (a_cols != n || lda != n)
     throw std::runtime_error("reference invert_transpose adapter needs unpadded matrices");
-  qmcplusplus::DiracMatrix<double> dm;
+  qmcplusplus::DiracMatrix<typename FullPrec<VT>::type> dm;
   qmcplusplus::Matrix<VT> a(const_cast<VT*>(amat), n, n);
   qmcplusplus::Matrix<VT> b(inv, n, n);
   dm.invert_transpose(a, b, logdet);

@@ -52,7 +52,7 @@ SYMBOLS = [
     "qmcb_spline_create", "qmcb_spline_destroy", "qmcb_spline_table_bytes", "qmcb_spline_mw_evaluate_value",
     "qmcb_spline_mw_evaluate_vgl", "qmcb_spline_mw_evaluate_vgl_ratio_grads", "qmcb_spline_mw_evaluate_det_ratios",
     "qmcb_spline_mw_vgl_ratio_grads_dev", "qmcb_spline_rg_parts",
-    "qmcb_crowd_create", "qmcb_crowd_destroy", "qmcb_crowd_sync", "qmcb_crowd_device_bytes",
+    "qmcb_crowd_create", "qmcb_crowd_destroy", "qmcb_crowd_sync", "qmcb_crowd_device_bytes", "qmcb_crowd_is_complex",
     "qmcb_crowd_set_positions", "qmcb_crowd_get_positions",
     "qmcb_twf_mw_recompute", "qmcb_twf_mw_eval_grad", "qmcb_ps_mw_make_move", "qmcb_twf_mw_calc_ratio_grad",
     "qmcb_twf_mw_accept_reject", "qmcb_twf_mw_complete_updates", "qmcb_twf_mw_evaluate_gl",
@@ -213,11 +213,21 @@ class Crowd:
         self.k = int(delay_rank)
         lat = np.ascontiguousarray(s["lattice"], np.float64).reshape(3, 3)
         G = np.linalg.inv(lat)  # CrystalLattice: G = inverse(R), ru = r . G
+        kp = s.get("kpts")
         if spo is None:
-            up = SplineSPOSet(s["coefs"][0], self.n_up, G)
-            dn = up if s["coefs"][1] is s["coefs"][0] and self.n_dn == self.n_up else SplineSPOSet(s["coefs"][1], self.n_dn, G)
+            if kp is not None:  # complex orbitals: SplineC2C tables + twist vectors
+                up = SplineSPOSet(s["coefs"][0], self.n_up, G, kind=C2C, kcart=kp[0])
+                dn = SplineSPOSet(s["coefs"][1], self.n_dn, G, kind=C2C, kcart=kp[1])
+            else:
+                up = SplineSPOSet(s["coefs"][0], self.n_up, G)
+                dn = up if s["coefs"][1] is s["coefs"][0] and self.n_dn == self.n_up else SplineSPOSet(s["coefs"][1], self.n_dn, G)
             spo = (up, dn)
         self.spo = spo
+        self.cplx = spo[0].kind == C2C
+        # V: determinant value type (inverse rows, orbital rows, ratios of the component-level calls);
+        # P: PsiValue / gradient type of the trial-wavefunction-level calls (always double precision)
+        self.V = _vt(self.precision, C2C if self.cplx else R2R)
+        self.P = np.complex128 if self.cplx else np.float64
         q = QmcbSystem()
         q.precision, q.n_up, q.n_dn = self.precision, self.n_up, self.n_dn
         q.lattice[:] = list(lat.ravel())
@@ -284,12 +294,12 @@ class Crowd:
         _chk(lib().qmcb_twf_mw_recompute(self.h))
 
     def mw_evalGrad(self, iat):
-        g = np.zeros((self.nw, 3))
+        g = np.zeros((self.nw, 3), self.P)
         _chk(lib().qmcb_twf_mw_eval_grad(self.h, C.c_int(iat), _p(g)))
         return g
 
     def mw_calcRatioGrad(self, iat):
-        r, g = np.zeros(self.nw), np.zeros((self.nw, 3))
+        r, g = np.zeros(self.nw, self.P), np.zeros((self.nw, 3), self.P)
         _chk(lib().qmcb_twf_mw_calc_ratio_grad(self.h, C.c_int(iat), _p(r), _p(g)))
         return r, g
 
@@ -302,25 +312,25 @@ class Crowd:
         _chk(lib().qmcb_twf_mw_complete_updates(self.h))
 
     def mw_evaluateGL(self):
-        G, L = np.zeros((self.nw, self.N, 3)), np.zeros((self.nw, self.N))
+        G, L = np.zeros((self.nw, self.N, 3), self.P), np.zeros((self.nw, self.N), self.P)
         lp, ke = np.zeros(self.nw), np.zeros(self.nw)
         _chk(lib().qmcb_twf_mw_evaluate_gl(self.h, _p(G), _p(L), _p(lp), _p(ke)))
         return lp, ke, G, L
 
     # ---- DiracDeterminantBatched / DelayedUpdateBatched
     def det_mw_evalGrad(self, spin, row):
-        g = np.zeros((self.nw, 3), self.T)
+        g = np.zeros((self.nw, 3), self.V)
         _chk(lib().qmcb_det_mw_eval_grad(self.h, C.c_int(spin), C.c_int(row), _p(g)))
         return g
 
     def det_mw_getInvRow(self, spin, row):
-        out = np.zeros((self.nw, self.n_of(spin)), self.T)
+        out = np.zeros((self.nw, self.n_of(spin)), self.V)
         dev, ld = vp(), C.c_size_t()
         _chk(lib().qmcb_det_mw_get_inv_row(self.h, spin, row, C.byref(dev), C.byref(ld), _p(out)))
         return out
 
     def det_mw_ratioGrad(self, spin, row, from_phi=False):
-        r, g = np.zeros(self.nw, self.T), np.zeros((self.nw, 3), self.T)
+        r, g = np.zeros(self.nw, self.V), np.zeros((self.nw, 3), self.V)
         f = lib().qmcb_det_mw_ratio_grad_from_phi if from_phi else lib().qmcb_det_mw_ratio_grad
         _chk(f(self.h, C.c_int(spin), C.c_int(row), _p(r), _p(g)))
         return r, g
@@ -331,21 +341,21 @@ class Crowd:
 
     def det_mw_completeUpdates(self, spin):
         n = self.n_of(spin)
-        inv = np.zeros((self.nw, n, n), self.T)
+        inv = np.zeros((self.nw, n, n), self.V)
         ld = np.zeros((self.nw, 2))
         _chk(lib().qmcb_det_mw_complete_updates(self.h, C.c_int(spin), _p(inv), _p(ld)))
         return inv, ld
 
     def det_recompute_from_matrices(self, spin, psiM, dpsiM=None, d2psiM=None):
         n = self.n_of(spin)
-        psiM = np.ascontiguousarray(psiM, self.T)
+        psiM = np.ascontiguousarray(psiM, self.V)
         assert psiM.shape == (self.nw, n, n)
-        dp = None if dpsiM is None else np.ascontiguousarray(dpsiM, self.T)
-        d2 = None if d2psiM is None else np.ascontiguousarray(d2psiM, self.T)
+        dp = None if dpsiM is None else np.ascontiguousarray(dpsiM, self.V)
+        d2 = None if d2psiM is None else np.ascontiguousarray(d2psiM, self.V)
         _chk(lib().qmcb_det_mw_recompute_from_matrices(self.h, C.c_int(spin), _p(psiM), _p(dp), _p(d2)))
 
     def det_set_phi_vgl(self, spin, phi):
-        phi = np.ascontiguousarray(phi, self.T)
+        phi = np.ascontiguousarray(phi, self.V)
         assert phi.shape == (5, self.nw, self.n_of(spin))
         _chk(lib().qmcb_det_set_phi_vgl(self.h, C.c_int(spin), _p(phi)))
 

@@ -339,6 +339,7 @@ int qmcb_crowd_destroy(qmcb_crowd* c)
   })
 int qmcb_crowd_sync(qmcb_crowd* c) { CROWD_CALL(sync()); }
 size_t qmcb_crowd_device_bytes(const qmcb_crowd* c) { return c ? c->impl->device_bytes() : 0; }
+int qmcb_crowd_is_complex(const qmcb_crowd* c) { return (c && c->impl->is_complex()) ? 1 : 0; }
 int qmcb_crowd_set_positions(qmcb_crowd* c, const double* R) { CROWD_CALL(set_positions(R)); }
 int qmcb_crowd_get_positions(qmcb_crowd* c, double* R) { CROWD_CALL(get_positions(R)); }
 int qmcb_twf_mw_recompute(qmcb_crowd* c) { CROWD_CALL(twf_recompute()); }

@@ -100,6 +100,124 @@ struct PinBuf
   }
 };
 
+// ---- complex value type of the C2C (complex orbital) determinants: plain {re, im} pair, layout-compatible with
+// std::complex / the interleaved arrays of the C ABI; trivially constructible so that it can live in __shared__ arrays
+#ifdef __CUDACC__
+#define QMCB_HD __host__ __device__ __forceinline__
+#else
+#define QMCB_HD inline
+#endif
+template<typename T>
+struct cx
+{
+  T re, im;
+  cx() = default;
+  QMCB_HD cx(T r) : re(r), im(T(0)) {}
+  QMCB_HD cx(T r, T i) : re(r), im(i) {}
+  template<typename U>
+  QMCB_HD explicit cx(const cx<U>& o) : re((T)o.re), im((T)o.im)
+  {}
+  QMCB_HD cx& operator+=(const cx& o)
+  {
+    re += o.re;
+    im += o.im;
+    return *this;
+  }
+  QMCB_HD cx& operator-=(const cx& o)
+  {
+    re -= o.re;
+    im -= o.im;
+    return *this;
+  }
+};
+template<typename T>
+QMCB_HD cx<T> operator+(const cx<T>& a, const cx<T>& b)
+{
+  return cx<T>(a.re + b.re, a.im + b.im);
+}
+template<typename T>
+QMCB_HD cx<T> operator-(const cx<T>& a, const cx<T>& b)
+{
+  return cx<T>(a.re - b.re, a.im - b.im);
+}
+template<typename T>
+QMCB_HD cx<T> operator-(const cx<T>& a)
+{
+  return cx<T>(-a.re, -a.im);
+}
+template<typename T>
+QMCB_HD cx<T> operator*(const cx<T>& a, const cx<T>& b)
+{
+  return cx<T>(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+template<typename T>
+QMCB_HD cx<T> operator*(const cx<T>& a, const T b)
+{
+  return cx<T>(a.re * b, a.im * b);
+}
+template<typename T>
+QMCB_HD cx<T> operator/(const cx<T>& a, const cx<T>& b)
+{
+  // textbook quotient (a * conj(b)) / |b|^2
+  const T d = b.re * b.re + b.im * b.im;
+  return cx<T>((a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d);
+}
+template<typename T>
+QMCB_HD bool operator!=(const cx<T>& a, const cx<T>& b)
+{
+  return a.re != b.re || a.im != b.im;
+}
+template<typename T>
+QMCB_HD bool operator==(const cx<T>& a, const cx<T>& b)
+{
+  return a.re == b.re && a.im == b.im;
+}
+
+// scalar type, double-precision counterpart and a few accessors that read the same for real and complex values
+template<typename V>
+struct value_traits
+{
+  using real_t                     = V;
+  using dbl_t                      = double;
+  static constexpr bool is_complex = false;
+  static constexpr int ncomp       = 1;
+};
+template<typename T>
+struct value_traits<cx<T>>
+{
+  using real_t                     = T;
+  using dbl_t                      = cx<double>;
+  static constexpr bool is_complex = true;
+  static constexpr int ncomp       = 2;
+};
+QMCB_HD float real_part(float v) { return v; }
+QMCB_HD double real_part(double v) { return v; }
+template<typename T>
+QMCB_HD T real_part(const cx<T>& v)
+{
+  return v.re;
+}
+QMCB_HD double to_dbl(float v) { return (double)v; }
+QMCB_HD double to_dbl(double v) { return v; }
+template<typename T>
+QMCB_HD cx<double> to_dbl(const cx<T>& v)
+{
+  return cx<double>((double)v.re, (double)v.im);
+}
+template<typename V>
+QMCB_HD V from_dbl(double v)
+{
+  return (V)v;
+}
+template<typename V>
+QMCB_HD V from_dbl(const cx<double>& v)
+{
+  return V(v);
+}
+// squared modulus (std::norm)
+QMCB_HD double norm2(double v) { return v * v; }
+QMCB_HD double norm2(const cx<double>& v) { return v.re * v.re + v.im * v.im; }
+
 #ifdef __CUDACC__
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -114,6 +232,12 @@ __device__ __forceinline__ double warp_sum(double v)
   for (int o = 16; o > 0; o >>= 1)
     v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+template<typename T>
+__device__ __forceinline__ cx<T> warp_sum(cx<T> v)
+{
+  return cx<T>(warp_sum(v.re), warp_sum(v.im));
 }
 
 // a group of threads of one CTA that synchronise on their own named barrier (bar 0 with the full CTA == __syncthreads)

@@ -26,8 +26,9 @@ namespace qmcb
 // small glue kernels of the trial wavefunction (component sums)
 // ------------------------------------------------------------------------------------------------------------
 // TrialWaveFunction::mw_evalGrad: grads_now = det + J2 dUat[iat] + J1 Grad[iat]  (component order det, J2, J1)
-template<typename T>
-__global__ void twf_grad_kernel(const JastrowDev<T> J, const int iat, const T* det_grads, T* grads_now)
+// T = real type of positions and Jastrows, V = determinant value type (T, or cx<T> with complex orbitals)
+template<typename T, typename V>
+__global__ void twf_grad_kernel(const JastrowDev<T> J, const int iat, const V* det_grads, V* grads_now)
 {
   const int iw = blockIdx.x * blockDim.x + threadIdx.x;
   if (iw >= J.nw)
@@ -35,11 +36,11 @@ __global__ void twf_grad_kernel(const JastrowDev<T> J, const int iat, const T* d
 #pragma unroll
   for (int d = 0; d < 3; ++d)
   {
-    T g = det_grads ? det_grads[3 * iw + d] : T(0);
+    V g = det_grads ? det_grads[3 * iw + d] : V(0);
     if (J.has_j2)
-      g += J.dUat[((size_t)iw * 3 + d) * J.npad + iat];
+      g += V(J.dUat[((size_t)iw * 3 + d) * J.npad + iat]);
     if (J.has_j1)
-      g += J.Grad1[((size_t)iw * 3 + d) * J.N + iat];
+      g += V(J.Grad1[((size_t)iw * 3 + d) * J.N + iat]);
     grads_now[3 * iw + d] = g;
   }
 }
@@ -57,44 +58,47 @@ __global__ void make_move_kernel(const JastrowDev<T> J, const int iat, const T* 
 }
 
 // TrialWaveFunction::mw_calcRatioGrad combination for one walker
-template<typename T>
-__device__ __forceinline__ double twf_ratio_grad(const JastrowDev<T>& J, int iw, int iat, const T* rg, int nparts, T gn[3])
+// (PsiValue ratio = double or cx<double>; the Jastrow factors are real)
+template<typename T, typename V>
+__device__ __forceinline__ typename value_traits<V>::dbl_t twf_ratio_grad(const JastrowDev<T>& J, int iw, int iat, const V* rg,
+                                                                          int nparts, V gn[3])
 {
-  T q[4];
-  sum_rg_parts<T, 4>(rg, iw, nparts, q);
-  const T rdet  = q[0];
-  double ratio  = (double)rdet;
-  gn[0]         = q[1] / rdet;
-  gn[1]         = q[2] / rdet;
-  gn[2]         = q[3] / rdet;
+  using PsiV = typename value_traits<V>::dbl_t;
+  V q[4];
+  sum_rg_parts<V, 4>(rg, iw, nparts, q);
+  const V rdet = q[0];
+  PsiV ratio   = to_dbl(rdet);
+  gn[0]        = q[1] / rdet;
+  gn[1]        = q[2] / rdet;
+  gn[2]        = q[3] / rdet;
   if (J.has_j2)
   {
     const T* vgl = J.j2_vgl + (size_t)iw * 5;
-    ratio *= exp((double)(J.Uat[(size_t)iw * J.npad + iat] - vgl[0]));
-    gn[0] += vgl[1];
-    gn[1] += vgl[2];
-    gn[2] += vgl[3];
+    ratio        = ratio * exp((double)(J.Uat[(size_t)iw * J.npad + iat] - vgl[0]));
+    gn[0] += V(vgl[1]);
+    gn[1] += V(vgl[2]);
+    gn[2] += V(vgl[3]);
   }
   if (J.has_j1)
   {
     const T* cur = J.j1_cur + (size_t)iw * 5;
-    ratio *= exp((double)(J.Vat[(size_t)iw * J.N + iat] - cur[0]));
-    gn[0] += cur[1];
-    gn[1] += cur[2];
-    gn[2] += cur[3];
+    ratio        = ratio * exp((double)(J.Vat[(size_t)iw * J.N + iat] - cur[0]));
+    gn[0] += V(cur[1]);
+    gn[1] += V(cur[2]);
+    gn[2] += V(cur[3]);
   }
   return ratio;
 }
 
-template<typename T>
-__global__ void twf_ratio_kernel(const JastrowDev<T> J, const int iat, const T* rg, const int nparts, double* ratios,
-                                 T* grads)
+template<typename T, typename V>
+__global__ void twf_ratio_kernel(const JastrowDev<T> J, const int iat, const V* rg, const int nparts,
+                                 typename value_traits<V>::dbl_t* ratios, V* grads)
 {
   const int iw = blockIdx.x * blockDim.x + threadIdx.x;
   if (iw >= J.nw)
     return;
-  T gn[3];
-  ratios[iw]       = twf_ratio_grad(J, iw, iat, rg, nparts, gn);
+  V gn[3];
+  ratios[iw]       = twf_ratio_grad<T, V>(J, iw, iat, rg, nparts, gn);
   grads[3 * iw]     = gn[0];
   grads[3 * iw + 1] = gn[1];
   grads[3 * iw + 2] = gn[2];
@@ -129,15 +133,23 @@ constexpr int MB_TPB = 256;
 
 // Metropolis test of walker iw for electron iat_prev by ONE warp (all 32 lanes call it); returns acc and the determinant
 // ratio in lane 0
+__device__ __forceinline__ float shfl_value(const float v, const int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shfl_value(const double v, const int src) { return __shfl_sync(0xffffffffu, v, src); }
 template<typename T>
+__device__ __forceinline__ cx<T> shfl_value(const cx<T>& v, const int src)
+{
+  return cx<T>(__shfl_sync(0xffffffffu, v.re, src), __shfl_sync(0xffffffffu, v.im, src));
+}
+
+template<typename T, typename V>
 __device__ __forceinline__ bool metropolis_warp(const DriverDev<T>& Dr, const JastrowDev<T>& J, const RngDev& R, const int iw,
-                                                const int iat_prev, const T* rg, const int rg_nparts, T& rdet_out)
+                                                const int iat_prev, const V* rg, const int rg_nparts, V& rdet_out)
 {
   const int lane = threadIdx.x & 31;
   // partial ratio/gradient dots of the spline kernel: lanes fetch, every lane adds in index order
-  T q[4] = {T(0), T(0), T(0), T(0)};
+  V q[4] = {V(0), V(0), V(0), V(0)};
   {
-    T mine[4] = {T(0), T(0), T(0), T(0)};
+    V mine[4] = {V(0), V(0), V(0), V(0)};
     if (lane < rg_nparts)
 #pragma unroll
       for (int e = 0; e < 4; ++e)
@@ -145,7 +157,7 @@ __device__ __forceinline__ bool metropolis_warp(const DriverDev<T>& Dr, const Ja
     for (int part = 0; part < rg_nparts && part < 32; ++part)
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        q[e] += __shfl_sync(0xffffffffu, mine[e], part);
+        q[e] += shfl_value(mine[e], part);
     for (int part = 32; part < rg_nparts; ++part) // more than 32 parts (very wide determinants)
 #pragma unroll
       for (int e = 0; e < 4; ++e)
@@ -153,13 +165,15 @@ __device__ __forceinline__ bool metropolis_warp(const DriverDev<T>& Dr, const Ja
   }
   const unsigned long long base = R.pos[iat_prev & 1];
   const unsigned sweep          = *R.sweep;
-  const T rdet = q[0];
-  double ratio = (double)rdet;
-  T gn[3]      = {q[1] / rdet, q[2] / rdet, q[3] / rdet};
+  const V rdet = q[0];
+  // PsiValue ratio (double / complex double) and the REAL part of the new gradient: a complex gradient reaches the drift
+  // through convertToReal (DriftModifierUNR.cpp:20-23)
+  typename value_traits<V>::dbl_t ratio = to_dbl(rdet);
+  T gn[3] = {real_part(q[1] / rdet), real_part(q[2] / rdet), real_part(q[3] / rdet)};
   if (J.has_j2)
   {
     const T* vgl = J.j2_vgl + (size_t)iw * 5;
-    ratio *= exp((double)(J.Uat[(size_t)iw * J.npad + iat_prev] - vgl[0]));
+    ratio        = ratio * exp((double)(J.Uat[(size_t)iw * J.npad + iat_prev] - vgl[0]));
     gn[0] += vgl[1];
     gn[1] += vgl[2];
     gn[2] += vgl[3];
@@ -167,7 +181,7 @@ __device__ __forceinline__ bool metropolis_warp(const DriverDev<T>& Dr, const Ja
   if (J.has_j1)
   {
     const T* cur = J.j1_cur + (size_t)iw * 5;
-    ratio *= exp((double)(J.Vat[(size_t)iw * J.N + iat_prev] - cur[0]));
+    ratio        = ratio * exp((double)(J.Vat[(size_t)iw * J.N + iat_prev] - cur[0]));
     gn[0] += cur[1];
     gn[1] += cur[2];
     gn[2] += cur[3];
@@ -185,7 +199,7 @@ __device__ __forceinline__ bool metropolis_warp(const DriverDev<T>& Dr, const Ja
     log_gb = -Dr.oneover2tau * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
   }
   const T eps     = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
-  const T prob    = (T)(ratio * ratio);
+  const T prob    = (T)norm2(ratio); // std::norm(ratio), VMCBatched.cpp:152
   const bool need = prob >= eps; // periodic cell: every move is valid
   // ---- position of this walker's draw in the crowd's stream: look back over the lower-index walkers
   const unsigned epoch = sweep * (unsigned)(Dr.N + 1) + (unsigned)iat_prev + 1u;
@@ -234,38 +248,38 @@ __device__ __forceinline__ bool metropolis_warp(const DriverDev<T>& Dr, const Ja
 // Phase B: threads 0-127: bordered update of Binv entirely in shared memory, row stores (U[c], V[c], G/L rows), then
 //   w = -Binv^T p, x += V^T w (one pass over V), inverse-row store and the gradient dot from the staged rows;
 //   threads 128-255: Jastrow accept + position commit.   Then warp 0 proposes the next move.
-template<typename T>
-__global__ void __launch_bounds__(MB_TPB, 4)
-    move_boundary_kernel(const DriverDev<T> Dr, const JastrowDev<T> J, const RngDev R, const DetDev<T> Dacc,
-                         const int iat_prev, const int row_prev, const int c_prev, const T* rg, const int rg_nparts,
-                         const T* phi_vgl, const DetDev<T> Dprep, const int iat_next, const int row_next, const int c_next,
-                         T* det_grads_out, const unsigned char* ext_accept, T* twf_grads_out)
+template<typename T, typename V>
+__global__ void __launch_bounds__(MB_TPB, (sizeof(V) > 8 ? 2 : 4))
+    move_boundary_kernel(const DriverDev<T> Dr, const JastrowDev<T> J, const RngDev R, const DetDev<V> Dacc,
+                         const int iat_prev, const int row_prev, const int c_prev, const V* rg, const int rg_nparts,
+                         const V* phi_vgl, const DetDev<V> Dprep, const int iat_next, const int row_next, const int c_next,
+                         V* det_grads_out, const unsigned char* ext_accept, V* twf_grads_out)
 {
   // ext_accept != nullptr: host-driven mode (the Metropolis test ran on the host, flags come from the caller) and
   // twf_grads_out receives the component-summed old gradient instead of a device-side proposal
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ T red[3 * 32];
+  __shared__ V red[3 * 32];
   __shared__ int s_acc;
-  __shared__ T s_ratio;
+  __shared__ V s_ratio;
   const int iw = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool part1 = iat_prev >= 0, part2 = iat_next >= 0;
   const int nA = part1 ? Dacc.n : 0, nB = part2 ? Dprep.n : 0, k = part1 ? Dacc.k : Dprep.k;
   const int kb = k + 1; // padded row stride of the staged Binv (conflict-free row AND column walks)
-  T* phi   = reinterpret_cast<T*>(smem_raw); // [5][nA]  value, gx, gy, gz, lap of the proposed move
-  T* vrow  = phi + 5 * nA;                   // [nA]     Ainv[row_prev]
-  T* x     = vrow + nA;                      // [nB]     Ainv[row_next] -> inverse row
-  T* glrow = x + nB;                         // [3][nB]  gradient rows of electron row_next
-  T* Bs    = glrow + 3 * nB;                 // [k][k+1] Binv of the determinant being updated / prepared
-  T* pA    = Bs + k * kb;                    // [k]  accept:  -V.phi
-  T* pB    = pA + k;                         // [k]  prepare:  U.x
-  T* y     = pB + k;                         // [k]
-  T* w     = y + k;                          // [k]  new w
-  T* wold  = w + k;                          // [k]  w left by the previous preparation (needed by the bordered update)
+  V* phi   = reinterpret_cast<V*>(smem_raw); // [5][nA]  value, gx, gy, gz, lap of the proposed move
+  V* vrow  = phi + 5 * nA;                   // [nA]     Ainv[row_prev]
+  V* x     = vrow + nA;                      // [nB]     Ainv[row_next] -> inverse row
+  V* glrow = x + nB;                         // [3][nB]  gradient rows of electron row_next
+  V* Bs    = glrow + 3 * nB;                 // [k][k+1] Binv of the determinant being updated / prepared
+  V* pA    = Bs + k * kb;                    // [k]  accept:  -V.phi
+  V* pB    = pA + k;                         // [k]  prepare:  U.x
+  V* y     = pB + k;                         // [k]
+  V* w     = y + k;                          // [k]  new w
+  V* wold  = w + k;                          // [k]  w left by the previous preparation (needed by the bordered update)
   // a spin change or a flush always splits the boundary, so when both parts are present they share the determinant
   const bool same_det = part1 && part2;
   const int cA = part1 ? c_prev : 0;                          // rows of V for the accept dots
   const int cB = part2 ? (same_det ? c_prev : c_next) : 0;    // rows of U that are final before this kernel
-  const DetDev<T>& Dm = part1 ? Dacc : Dprep;                 // determinant whose Binv is staged
+  const DetDev<V>& Dm = part1 ? Dacc : Dprep;                 // determinant whose Binv is staged
   const int cM        = part1 ? c_prev : c_next;              // its pending count before this kernel
 
   if (warp == 7)
@@ -274,16 +288,16 @@ __global__ void __launch_bounds__(MB_TPB, 4)
     {
       if (lane == 0)
       {
-        T q[4];
-        sum_rg_parts<T, 4>(rg, iw, rg_nparts, q);
+        V q[4];
+        sum_rg_parts<V, 4>(rg, iw, rg_nparts, q);
         s_acc   = ext_accept[iw] ? 1 : 0;
         s_ratio = q[0];
       }
     }
     else if (part1)
     {
-      T rdet;
-      const bool acc = metropolis_warp<T>(Dr, J, R, iw, iat_prev, rg, rg_nparts, rdet);
+      V rdet;
+      const bool acc = metropolis_warp<T, V>(Dr, J, R, iw, iat_prev, rg, rg_nparts, rdet);
       if (lane == 0)
       {
         s_acc   = acc ? 1 : 0;
@@ -297,8 +311,8 @@ __global__ void __launch_bounds__(MB_TPB, 4)
     if (part1)
     {
       const size_t fs = (size_t)Dacc.nw * nA;
-      const T* ph     = phi_vgl + (size_t)iw * nA;
-      const T* arow   = Dacc.Ainv + ((size_t)iw * nA + row_prev) * Dacc.lda;
+      const V* ph     = phi_vgl + (size_t)iw * nA;
+      const V* arow   = Dacc.Ainv + ((size_t)iw * nA + row_prev) * Dacc.lda;
       for (int j = tid; j < nA; j += ga.n)
       {
         phi[j]          = ph[j];
@@ -308,14 +322,14 @@ __global__ void __launch_bounds__(MB_TPB, 4)
         phi[4 * nA + j] = ph[4 * fs + j];
         vrow[j]         = arow[j];
       }
-      const T* wv = Dacc.wvec + (size_t)iw * k;
+      const V* wv = Dacc.wvec + (size_t)iw * k;
       for (int b = tid; b < cA; b += ga.n)
         wold[b] = wv[b];
     }
     if (part2)
     {
-      const T* arow = Dprep.Ainv + ((size_t)iw * nB + row_next) * Dprep.lda;
-      const T* gl   = Dprep.GL + ((size_t)iw * nB + row_next) * 4 * nB;
+      const V* arow = Dprep.Ainv + ((size_t)iw * nB + row_next) * Dprep.lda;
+      const V* gl   = Dprep.GL + ((size_t)iw * nB + row_next) * 4 * nB;
       for (int j = tid; j < nB; j += ga.n)
       {
         x[j]              = arow[j];
@@ -325,7 +339,7 @@ __global__ void __launch_bounds__(MB_TPB, 4)
       }
     }
     {
-      const T* B = Dm.Binv + (size_t)iw * k * k;
+      const V* B = Dm.Binv + (size_t)iw * k * k;
       for (int e = tid; e < cM * k; e += ga.n)
       {
         const int a = e / k, b = e - a * k;
@@ -334,16 +348,16 @@ __global__ void __launch_bounds__(MB_TPB, 4)
       }
     }
     ga.sync();
-    const T* Va = part1 ? Dacc.V + (size_t)iw * k * nA : nullptr;
-    const T* Ub = part2 ? Dprep.U + (size_t)iw * k * nB : nullptr;
+    const V* Va = part1 ? Dacc.V + (size_t)iw * k * nA : nullptr;
+    const V* Ub = part2 ? Dprep.U + (size_t)iw * k * nB : nullptr;
     const int nspec = same_det ? 1 : 0; // phi.x for the slot this kernel appends (shared memory only)
     const int ntask = cA + cB + nspec;
     for (int t0 = warp; t0 < ntask; t0 += 14)
     {
       const int t1 = t0 + 7;
-      const T *r0, *v0, *r1, *v1;
+      const V *r0, *v0, *r1, *v1;
       int n0, n1 = 0;
-      auto pick = [&](int t, const T*& r, const T*& v, int& nn) {
+      auto pick = [&](int t, const V*& r, const V*& v, int& nn) {
         if (t < cA)
           r = Va + (size_t)t * nA, v = phi, nn = nA;
         else if (t < cA + cB)
@@ -355,7 +369,7 @@ __global__ void __launch_bounds__(MB_TPB, 4)
       r1 = r0, v1 = v0;
       if (t1 < ntask)
         pick(t1, r1, v1, n1);
-      T s0(0), s1(0);
+      V s0(0), s1(0);
       const int nmax = n0 > n1 ? n0 : n1;
       for (int j = lane; j < nmax; j += 32)
       {
@@ -384,7 +398,7 @@ __global__ void __launch_bounds__(MB_TPB, 4)
   }
   __syncthreads();
 
-  T g[3] = {T(0), T(0), T(0)};
+  V g[3] = {V(0), V(0), V(0)};
   if (tid < MB_TPB / 2)
   {
     const Group gd{tid, MB_TPB / 2, 1};
@@ -393,14 +407,14 @@ __global__ void __launch_bounds__(MB_TPB, 4)
     {
       const bool acc = s_acc != 0;
       const int c    = c_prev;
-      T* U           = Dacc.U + (size_t)iw * k * nA;
-      T* V           = Dacc.V + (size_t)iw * k * nA;
+      V* U           = Dacc.U + (size_t)iw * k * nA;
+      V* Vm          = Dacc.V + (size_t)iw * k * nA;
       // rows: V[c] = Ainv[row_prev] for every walker (DelayedUpdateBatched.h:646); U[c] and the G/L rows on accept
-      T* gl = Dacc.GL + ((size_t)iw * nA + row_prev) * 4 * nA;
+      V* gl = Dacc.GL + ((size_t)iw * nA + row_prev) * 4 * nA;
       for (int j = tid; j < nA; j += gd.n)
       {
-        V[(size_t)c * nA + j] = vrow[j];
-        U[(size_t)c * nA + j] = acc ? phi[j] : T(0);
+        Vm[(size_t)c * nA + j] = vrow[j];
+        U[(size_t)c * nA + j]  = acc ? phi[j] : V(0);
         if (acc)
         {
           gl[j]          = phi[nA + j];
@@ -412,10 +426,10 @@ __global__ void __launch_bounds__(MB_TPB, 4)
       if (acc)
       {
         // bordered update of Binv (DelayedUpdate.h:113-141) on the staged copy
-        const T sigma = T(1) / s_ratio;
+        const V sigma = V(1) / s_ratio;
         if (tid < c)
         {
-          T sacc(0);
+          V sacc(0);
           for (int b = 0; b < c; ++b)
             sacc += Bs[tid * kb + b] * pA[b];
           y[tid] = sigma * sacc;
@@ -435,10 +449,7 @@ __global__ void __launch_bounds__(MB_TPB, 4)
         {
           Bs[c * kb + c]                = sigma;
           Dacc.list[(size_t)iw * k + c] = row_prev;
-          const double r                = (double)s_ratio; // log_value += log(curRatio), DiracDeterminantBatched.cpp:501
-          Dacc.logdet[2 * (size_t)iw] += log(fabs(r));
-          if (r < 0)
-            Dacc.logdet[2 * (size_t)iw + 1] += 3.14159265358979323846;
+          logdet_accumulate(Dacc.logdet + 2 * (size_t)iw, s_ratio); // log_value += log(curRatio)
         }
       }
       else
@@ -446,19 +457,19 @@ __global__ void __launch_bounds__(MB_TPB, 4)
         // pseudo-accept: detail/OMPTarget/AccelMatrixUpdateOMPTarget.hpp:139-160
         if (tid < c)
         {
-          Bs[c * kb + tid] = T(0);
-          Bs[tid * kb + c] = T(0);
+          Bs[c * kb + tid] = V(0);
+          Bs[tid * kb + c] = V(0);
         }
         if (tid == 0)
         {
-          Bs[c * kb + c]                = T(1);
+          Bs[c * kb + c]                = V(1);
           Dacc.list[(size_t)iw * k + c] = -1;
         }
       }
       cN = c + 1;
       gd.sync();
       // write the updated core back (rows/columns < cN)
-      T* B = Dacc.Binv + (size_t)iw * k * k;
+      V* B = Dacc.Binv + (size_t)iw * k * k;
       for (int e = tid; e < cN * k; e += gd.n)
       {
         const int a = e / k, b = e - a * k;
@@ -470,12 +481,12 @@ __global__ void __launch_bounds__(MB_TPB, 4)
     {
       // p'[a] = U[a].x : rows < cB from phase A; the appended row is phi.x on accept and 0 for a pseudo-accept
       if (same_det && tid == 0)
-        pB[c_prev] = s_acc != 0 ? pB[cB] : T(0);
+        pB[c_prev] = s_acc != 0 ? pB[cB] : V(0);
       gd.sync();
       // w = -Binv^T p'  (DelayedUpdate.h:100-101), kept for the accept of this electron
       if (tid < cN)
       {
-        T sacc(0);
+        V sacc(0);
         for (int a = 0; a < cN; ++a)
           sacc += Bs[a * kb + tid] * pB[a];
         w[tid]                            = -sacc;
@@ -483,17 +494,17 @@ __global__ void __launch_bounds__(MB_TPB, 4)
       }
       gd.sync();
       // x += V^T w : rows < cB from HBM/L2, the row appended by part 1 from shared memory
-      const T* V = Dprep.V + (size_t)iw * k * nB;
-      T acc3[3]  = {T(0), T(0), T(0)};
-      T* out     = Dprep.invRow + (size_t)iw * nB;
+      const V* Vm = Dprep.V + (size_t)iw * k * nB;
+      V acc3[3]   = {V(0), V(0), V(0)};
+      V* out      = Dprep.invRow + (size_t)iw * nB;
       for (int j = tid; j < nB; j += gd.n)
       {
-        T sacc(0);
+        V sacc(0);
         for (int a = 0; a < cB; ++a)
-          sacc += V[(size_t)a * nB + j] * w[a];
+          sacc += Vm[(size_t)a * nB + j] * w[a];
         if (same_det)
           sacc += vrow[j] * w[c_prev];
-        const T xv = x[j] + sacc;
+        const V xv = x[j] + sacc;
         out[j]     = xv;
         acc3[0] += xv * glrow[j];
         acc3[1] += xv * glrow[nB + j];
@@ -501,7 +512,7 @@ __global__ void __launch_bounds__(MB_TPB, 4)
       }
       if (Dr.use_drift)
       {
-        group_sum<T, 3>(gd, acc3, red);
+        group_sum<V, 3>(gd, acc3, red);
         g[0] = acc3[0];
         g[1] = acc3[1];
         g[2] = acc3[2];
@@ -517,11 +528,11 @@ __global__ void __launch_bounds__(MB_TPB, 4)
     // host-driven mode: TrialWaveFunction::mw_evalGrad = determinant + J2 + J1 gradients of electron iat_next
     if (tid < 3)
     {
-      T gd = tid == 0 ? g[0] : (tid == 1 ? g[1] : g[2]);
+      V gd = tid == 0 ? g[0] : (tid == 1 ? g[1] : g[2]);
       if (J.has_j2)
-        gd += J.dUat[((size_t)iw * 3 + tid) * J.npad + iat_next];
+        gd += V(J.dUat[((size_t)iw * 3 + tid) * J.npad + iat_next]);
       if (J.has_j1)
-        gd += J.Grad1[((size_t)iw * 3 + tid) * J.N + iat_next];
+        gd += V(J.Grad1[((size_t)iw * 3 + tid) * J.N + iat_next]);
       twf_grads_out[3 * iw + tid] = gd;
     }
   }
@@ -535,9 +546,10 @@ __global__ void __launch_bounds__(MB_TPB, 4)
     if (Dr.use_drift)
     {
       // thread 0 holds the determinant gradient (every thread of the determinant group does after group_sum)
-      T gd = d == 0 ? g[0] : (d == 1 ? g[1] : g[2]);
+      const V gdet = d == 0 ? g[0] : (d == 1 ? g[1] : g[2]);
       if (det_grads_out && lane < 3)
-        det_grads_out[3 * iw + d] = gd;
+        det_grads_out[3 * iw + d] = gdet;
+      T gd = real_part(gdet); // convertToReal of the complex gradient (DriftModifierUNR.cpp:20-23)
       if (J.has_j2)
         gd += J.dUat[((size_t)iw * 3 + d) * J.npad + iat_next];
       if (J.has_j1)
@@ -559,26 +571,44 @@ __global__ void __launch_bounds__(MB_TPB, 4)
 }
 
 // kinetic energy and log psi per walker: ke = -1/2 sum_i (L_i + G_i.G_i)
+// complex G, L: real(CplxDot(G,G) + CplxSum(L)) = sum(re^2 - im^2) + sum(re L)  (BareKineticEnergy.cpp:114)
+__device__ __forceinline__ double ke_term(const float l, const float* g)
+{
+  return (double)l + (double)g[0] * g[0] + (double)g[1] * g[1] + (double)g[2] * g[2];
+}
+__device__ __forceinline__ double ke_term(const double l, const double* g)
+{
+  return l + g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+}
 template<typename T>
-__global__ void __launch_bounds__(256) ke_kernel(int N, const T* Gd, const T* Ld, double* ke)
+__device__ __forceinline__ double ke_term(const cx<T>& l, const cx<T>* g)
+{
+  double s = (double)l.re;
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    s += (double)g[d].re * g[d].re - (double)g[d].im * g[d].im;
+  return s;
+}
+template<typename V>
+__global__ void __launch_bounds__(256) ke_kernel(int N, const V* Gd, const V* Ld, double* ke)
 {
   __shared__ double red[32];
   const int iw = blockIdx.x, tid = threadIdx.x;
   double acc[1] = {0.0};
   for (int i = tid; i < N; i += blockDim.x)
-  {
-    const T* g = Gd + ((size_t)iw * N + i) * 3;
-    acc[0] += (double)Ld[(size_t)iw * N + i] + (double)g[0] * g[0] + (double)g[1] * g[1] + (double)g[2] * g[2];
-  }
+    acc[0] += ke_term(Ld[(size_t)iw * N + i], Gd + ((size_t)iw * N + i) * 3);
   block_sum<double, 1>(acc, red);
   if (tid == 0)
     ke[iw] = -0.5 * acc[0];
 }
 
 // ------------------------------------------------------------------------------------------------------------
-template<typename T>
+template<typename T, typename V>
 struct Crowd : CrowdBase
 {
+  using DV                      = typename value_traits<V>::dbl_t; // FP64 counterpart of the determinant value type
+  static constexpr bool cplx    = value_traits<V>::is_complex;
+  static constexpr int ncomp    = value_traits<V>::ncomp;
   qmcb_system sys;
   int nw = 0, N = 0, k = 1;
   int nel[2], first[2], lda[2];
@@ -590,8 +620,8 @@ struct Crowd : CrowdBase
   cublasHandle_t blas = nullptr;
 
   // determinants
-  DetDev<T> det[2];
-  DevBuf<T> Ainv[2], GL[2], U[2], V[2], Binv[2], wvec[2], invRow[2], tempMat[2], Up[2];
+  DetDev<V> det[2];
+  DevBuf<V> Ainv[2], GL[2], U[2], Vb[2], Binv[2], wvec[2], invRow[2], tempMat[2], Up[2];
   DevBuf<int> list[2];
   DevBuf<double> logdet[2];
   int rg_cap = 1, rg_nparts = 1; // slots per walker in `rg` / slots filled by the last evaluation
@@ -603,12 +633,14 @@ struct Crowd : CrowdBase
   DevBuf<int> ion_grp;
   DevBuf<double> j2_log, j1_log;
   // shared scratch
-  DevBuf<T> phi_vgl, rg, det_grads, grads_tmp, displ, Gd, Ld;
-  DevBuf<double> ratios_d, ke_d;
+  DevBuf<V> phi_vgl, rg, det_grads, grads_tmp, Gd, Ld;
+  DevBuf<T> displ;
+  DevBuf<DV> ratios_d;
+  DevBuf<double> ke_d;
   DevBuf<unsigned char> accepted;
   PinBuf<unsigned char> h_acc;
-  PinBuf<T> h_t;
-  PinBuf<double> h_d;
+  PinBuf<V> h_t;  // gradients / displacements staging (displacements use the second half, as T)
+  PinBuf<DV> h_d;
   // driver
   DriverDev<T> drv;
   RngDev rng;
@@ -672,8 +704,9 @@ struct Crowd : CrowdBase
       QMCB_CUDA(cudaGetDevice(&dev_now));
       if (spo[i]->device != dev_now)
         throw std::runtime_error("crowd: the SPOSet lives on another CUDA device (tables are replicated per GPU)");
-      if (spo[i]->precision != sys.precision || spo[i]->kind != QMCB_R2R)
-        throw std::runtime_error("crowd: SPOSet precision/kind mismatch (real determinants need SplineR2R tables)");
+      if (spo[i]->precision != sys.precision || spo[i]->kind != (cplx ? QMCB_C2C : QMCB_R2R))
+        throw std::runtime_error("crowd: SPOSet precision/kind mismatch (both determinants need tables of one kind: "
+                                 "SplineR2R for real, SplineC2C for complex orbitals)");
       if (spo[i]->n_orb != nel[i])
         throw std::runtime_error("crowd: the SPOSet of each determinant must hold exactly n_el orbitals");
       if (k > std::max(1, nel[i]) && nel[i] > 0)
@@ -692,11 +725,11 @@ struct Crowd : CrowdBase
     for (int s2 = 0; s2 < 2; ++s2)
     {
       const int n = nel[s2];
-      lda[s2]     = (int)aligned_size<T>(n);
+      lda[s2]     = (int)aligned_size<V>(n);
       A(Ainv[s2], (size_t)nw * n * lda[s2]);
       A(GL[s2], (size_t)nw * n * 4 * n);
       A(U[s2], (size_t)nw * k * n);
-      A(V[s2], (size_t)nw * k * n);
+      A(Vb[s2], (size_t)nw * k * n);
       A(Binv[s2], (size_t)nw * k * k);
       A(wvec[s2], (size_t)nw * k);
       A(list[s2], (size_t)nw * k);
@@ -704,9 +737,9 @@ struct Crowd : CrowdBase
       A(tempMat[s2], (size_t)nw * n * k);
       A(Up[s2], (size_t)nw * k * n);
       A(logdet[s2], (size_t)nw * 2);
-      DetDev<T>& D = det[s2];
+      DetDev<V>& D = det[s2];
       D.n = n, D.lda = lda[s2], D.k = k, D.nw = nw;
-      D.Ainv = Ainv[s2].p, D.GL = GL[s2].p, D.U = U[s2].p, D.V = V[s2].p, D.Binv = Binv[s2].p, D.wvec = wvec[s2].p;
+      D.Ainv = Ainv[s2].p, D.GL = GL[s2].p, D.U = U[s2].p, D.V = Vb[s2].p, D.Binv = Binv[s2].p, D.wvec = wvec[s2].p;
       D.list = list[s2].p, D.invRow = invRow[s2].p, D.tempMat = tempMat[s2].p, D.Up = Up[s2].p, D.logdet = logdet[s2].p;
     }
     A(phi_vgl, (size_t)5 * nw * nmax);
@@ -857,6 +890,7 @@ struct Crowd : CrowdBase
   cudaStream_t stream() override { return st; }
   void sync() override { QMCB_CUDA(cudaStreamSynchronize(st)); }
   size_t device_bytes() const override { return dev_bytes; }
+  bool is_complex() const override { return cplx; }
   int spin_of(int iat) const { return iat < sys.n_up ? 0 : 1; }
   static int blocks(int n, int tpb) { return (n + tpb - 1) / tpb; }
   void check_iat(int iat) const
@@ -895,11 +929,11 @@ struct Crowd : CrowdBase
   }
 
   // ---------------------------------------------------------------- determinant engine
-  void launch_prepare(int spin, int row, T* grads)
+  void launch_prepare(int spin, int row, V* grads)
   {
-    const DetDev<T>& D = det[spin];
-    const size_t smem  = (size_t)(D.n + 2 * D.k) * sizeof(T);
-    det_prepare_row_kernel<T><<<nw, DET_TPB, smem, st>>>(D, row, delay_count[spin], grads);
+    const DetDev<V>& D = det[spin];
+    const size_t smem  = (size_t)(D.n + 2 * D.k) * sizeof(V);
+    det_prepare_row_kernel<V><<<nw, DET_TPB, smem, st>>>(D, row, delay_count[spin], grads);
     QMCB_LAUNCH_CHECK();
     invrow_id[spin] = row;
   }
@@ -913,9 +947,9 @@ struct Crowd : CrowdBase
     const int c = delay_count[spin];
     if (c == 0)
       return;
-    const DetDev<T>& D = det[spin];
+    const DetDev<V>& D = det[spin];
     const int n        = D.n;
-    if constexpr (std::is_same<T, float>::value)
+    if constexpr (std::is_same<V, float>::value)
     {
       // one-pass tensor-core flush (woodbury.cuh) whenever U, U' and a 64-row tile of Ainv fit in shared memory
       const size_t smem = wb::smem_bytes_f32(n);
@@ -938,27 +972,27 @@ struct Crowd : CrowdBase
       }
     }
     // tempMat[n x c] = Ainv[n x n] * U^T, with the -1 fix-up (applyW) fused
-    gemm_batched_kernel<T, true, true><<<dim3(blocks(c, 64), blocks(n, 64), nw), 256, 0, st>>>(
-        n, c, n, T(1), D.Ainv, D.lda, (size_t)n * D.lda, D.U, n, (size_t)D.k * n, T(0), D.tempMat, D.k, (size_t)n * D.k,
+    gemm_batched_kernel<V, true, true><<<dim3(blocks(c, 64), blocks(n, 64), nw), 256, 0, st>>>(
+        n, c, n, V(1), D.Ainv, D.lda, (size_t)n * D.lda, D.U, n, (size_t)D.k * n, V(0), D.tempMat, D.k, (size_t)n * D.k,
         D.list, D.k);
     QMCB_LAUNCH_CHECK();
     // Up[c x n] = Binv[c x c] * V[c x n]
-    gemm_batched_kernel<T, false, false><<<dim3(blocks(n, 64), blocks(c, 64), nw), 256, 0, st>>>(
-        c, n, c, T(1), D.Binv, D.k, (size_t)D.k * D.k, D.V, n, (size_t)D.k * n, T(0), D.Up, n, (size_t)D.k * n, nullptr, 0);
+    gemm_batched_kernel<V, false, false><<<dim3(blocks(n, 64), blocks(c, 64), nw), 256, 0, st>>>(
+        c, n, c, V(1), D.Binv, D.k, (size_t)D.k * D.k, D.V, n, (size_t)D.k * n, V(0), D.Up, n, (size_t)D.k * n, nullptr, 0);
     QMCB_LAUNCH_CHECK();
     // Ainv -= tempMat * Up
-    gemm_batched_kernel<T, false, false><<<dim3(blocks(n, 64), blocks(n, 64), nw), 256, 0, st>>>(
-        n, n, c, T(-1), D.tempMat, D.k, (size_t)n * D.k, D.Up, n, (size_t)D.k * n, T(1), D.Ainv, D.lda, (size_t)n * D.lda,
+    gemm_batched_kernel<V, false, false><<<dim3(blocks(n, 64), blocks(n, 64), nw), 256, 0, st>>>(
+        n, n, c, V(-1), D.tempMat, D.k, (size_t)n * D.k, D.Up, n, (size_t)D.k * n, V(1), D.Ainv, D.lda, (size_t)n * D.lda,
         nullptr, 0);
     QMCB_LAUNCH_CHECK();
     delay_count[spin] = 0;
     invrow_id[spin]   = -1;
   }
-  void launch_accept(int spin, int row, const unsigned char* acc_dev, const T* rg_dev, const T* phi_dev)
+  void launch_accept(int spin, int row, const unsigned char* acc_dev, const V* rg_dev, const V* phi_dev)
   {
-    const DetDev<T>& D = det[spin];
-    const size_t smem  = (size_t)(D.n + 2 * D.k) * sizeof(T);
-    det_accept_kernel<T><<<nw, DET_TPB, smem, st>>>(D, row, delay_count[spin], acc_dev, rg_dev, rg_nparts, phi_dev);
+    const DetDev<V>& D = det[spin];
+    const size_t smem  = (size_t)(D.n + 2 * D.k) * sizeof(V);
+    det_accept_kernel<V><<<nw, DET_TPB, smem, st>>>(D, row, delay_count[spin], acc_dev, rg_dev, rg_nparts, phi_dev);
     QMCB_LAUNCH_CHECK();
     delay_count[spin]++;
     invrow_id[spin] = -1;
@@ -977,9 +1011,9 @@ struct Crowd : CrowdBase
     flush_pending();
     check_row(spin, row);
     launch_prepare(spin, row, det_grads.p);
-    QMCB_CUDA(cudaMemcpyAsync(h_t.p, det_grads.p, (size_t)nw * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    QMCB_CUDA(cudaMemcpyAsync(h_t.p, det_grads.p, (size_t)nw * 3 * sizeof(V), cudaMemcpyDeviceToHost, st));
     sync();
-    std::memcpy(grads, h_t.p, (size_t)nw * 3 * sizeof(T));
+    std::memcpy(grads, h_t.p, (size_t)nw * 3 * sizeof(V));
   }
   void det_get_inv_row(int spin, int row, const void** dev, size_t* ld, void* host) override
   {
@@ -992,7 +1026,7 @@ struct Crowd : CrowdBase
       *ld = det[spin].n;
     if (host)
     {
-      QMCB_CUDA(cudaMemcpyAsync(host, invRow[spin].p, (size_t)nw * det[spin].n * sizeof(T), cudaMemcpyDeviceToHost, st));
+      QMCB_CUDA(cudaMemcpyAsync(host, invRow[spin].p, (size_t)nw * det[spin].n * sizeof(V), cudaMemcpyDeviceToHost, st));
       sync();
     }
   }
@@ -1003,21 +1037,21 @@ struct Crowd : CrowdBase
     ensure_row(spin, row);
     if (from_phi)
     {
-      det_ratio_from_phi_kernel<T><<<nw, DET_TPB, 0, st>>>(det[spin], phi_vgl.p, rg.p);
+      det_ratio_from_phi_kernel<V><<<nw, DET_TPB, 0, st>>>(det[spin], phi_vgl.p, rg.p);
       QMCB_LAUNCH_CHECK();
       rg_nparts = 1;
     }
     else
       launch_spline(spin, MODE_VGL, invRow[spin].p, det[spin].n, phi_vgl.p, rg.p, st);
-    std::vector<T> parts((size_t)nw * rg_nparts * 4);
-    QMCB_CUDA(cudaMemcpyAsync(parts.data(), rg.p, parts.size() * sizeof(T), cudaMemcpyDeviceToHost, st));
+    std::vector<V> parts((size_t)nw * rg_nparts * 4);
+    QMCB_CUDA(cudaMemcpyAsync(parts.data(), rg.p, parts.size() * sizeof(V), cudaMemcpyDeviceToHost, st));
     sync();
-    T* r = static_cast<T*>(ratios);
-    T* g = static_cast<T*>(grads);
+    V* r = static_cast<V*>(ratios);
+    V* g = static_cast<V*>(grads);
     for (int iw = 0; iw < nw; ++iw)
     {
-      T q[4];
-      sum_rg_parts<T, 4>(parts.data(), iw, rg_nparts, q);
+      V q[4];
+      sum_rg_parts<V, 4>(parts.data(), iw, rg_nparts, q);
       r[iw] = q[0];
       if (g)
         for (int d = 0; d < 3; ++d)
@@ -1049,8 +1083,8 @@ struct Crowd : CrowdBase
     launch_flush(spin);
     const int n = nel[spin];
     if (psiMinv)
-      QMCB_CUDA(cudaMemcpy2DAsync(psiMinv, (size_t)n * sizeof(T), Ainv[spin].p, (size_t)lda[spin] * sizeof(T),
-                                  (size_t)n * sizeof(T), (size_t)nw * n, cudaMemcpyDeviceToHost, st));
+      QMCB_CUDA(cudaMemcpy2DAsync(psiMinv, (size_t)n * sizeof(V), Ainv[spin].p, (size_t)lda[spin] * sizeof(V),
+                                  (size_t)n * sizeof(V), (size_t)nw * n, cudaMemcpyDeviceToHost, st));
     if (logdet_h)
       QMCB_CUDA(cudaMemcpyAsync(logdet_h, logdet[spin].p, (size_t)nw * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     sync();
@@ -1060,35 +1094,43 @@ struct Crowd : CrowdBase
   {
     const int n = nel[spin];
     // host layout [5][nw][n] -> device layout [5][nw][n] with the same n (phi_vgl is sized for nmax but indexed with D.n)
-    QMCB_CUDA(cudaMemcpyAsync(phi_vgl.p, phi, (size_t)5 * nw * n * sizeof(T), cudaMemcpyHostToDevice, st));
+    QMCB_CUDA(cudaMemcpyAsync(phi_vgl.p, phi, (size_t)5 * nw * n * sizeof(V), cudaMemcpyHostToDevice, st));
     sync();
   }
 
   // FP64 inversion of the transposed matrices in AT (column-major psiM), result into Ainv, log-determinants
-  void invert_from_AT(int spin, DevBuf<double>& AT)
+  // (always FullPrecValueType like DiracMatrixInverterCUDA::mw_invertTranspose, DiracMatrixInverterCUDA.hpp:306-369)
+  void invert_from_AT(int spin, DevBuf<DV>& AT)
   {
     const int n = nel[spin];
-    DevBuf<double> inv;
+    DevBuf<DV> inv;
     DevBuf<int> piv, info;
-    DevBuf<double*> ptrs;
+    DevBuf<DV*> ptrs;
     inv.alloc((size_t)nw * n * n, false);
     piv.alloc((size_t)nw * n);
     info.alloc(nw);
     ptrs.alloc(2 * (size_t)nw);
-    std::vector<double*> hp(2 * (size_t)nw);
+    std::vector<DV*> hp(2 * (size_t)nw);
     for (int iw = 0; iw < nw; ++iw)
     {
       hp[iw]      = AT.p + (size_t)iw * n * n;
       hp[nw + iw] = inv.p + (size_t)iw * n * n;
     }
-    QMCB_CUDA(cudaMemcpyAsync(ptrs.p, hp.data(), hp.size() * sizeof(double*), cudaMemcpyHostToDevice, st));
-    QMCB_CUBLAS(cublasDgetrfBatched(blas, n, ptrs.p, n, piv.p, info.p, nw));
+    QMCB_CUDA(cudaMemcpyAsync(ptrs.p, hp.data(), hp.size() * sizeof(DV*), cudaMemcpyHostToDevice, st));
+    if constexpr (cplx)
+      QMCB_CUBLAS(cublasZgetrfBatched(blas, n, reinterpret_cast<cuDoubleComplex**>(ptrs.p), n, piv.p, info.p, nw));
+    else
+      QMCB_CUBLAS(cublasDgetrfBatched(blas, n, ptrs.p, n, piv.p, info.p, nw));
     g_launch_count.fetch_add(1);
-    det_logdet_kernel<<<nw, 128, 0, st>>>(AT.p, piv.p, n, logdet[spin].p);
+    det_logdet_kernel<DV><<<nw, 128, 0, st>>>(AT.p, piv.p, n, logdet[spin].p);
     QMCB_LAUNCH_CHECK();
-    QMCB_CUBLAS(cublasDgetriBatched(blas, n, ptrs.p, n, piv.p, ptrs.p + nw, n, info.p, nw));
+    if constexpr (cplx)
+      QMCB_CUBLAS(cublasZgetriBatched(blas, n, reinterpret_cast<cuDoubleComplex**>(ptrs.p), n, piv.p,
+                                      reinterpret_cast<cuDoubleComplex**>(ptrs.p + nw), n, info.p, nw));
+    else
+      QMCB_CUBLAS(cublasDgetriBatched(blas, n, ptrs.p, n, piv.p, ptrs.p + nw, n, info.p, nw));
     g_launch_count.fetch_add(1);
-    det_store_inverse_kernel<T><<<dim3(blocks(n, 128), n, nw), 128, 0, st>>>(det[spin], inv.p);
+    det_store_inverse_kernel<V><<<dim3(blocks(n, 128), n, nw), 128, 0, st>>>(det[spin], inv.p);
     QMCB_LAUNCH_CHECK();
     std::vector<int> hinfo(nw);
     QMCB_CUDA(cudaMemcpyAsync(hinfo.data(), info.p, nw * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1103,27 +1145,27 @@ struct Crowd : CrowdBase
   void det_recompute_from_matrices(int spin, const void* psiM, const void* dpsiM, const void* d2psiM) override
   {
     const int n = nel[spin];
-    const T* pm = static_cast<const T*>(psiM);
-    const T* dp = static_cast<const T*>(dpsiM);
-    const T* d2 = static_cast<const T*>(d2psiM);
-    std::vector<double> at((size_t)nw * n * n);
-    std::vector<T> gl((size_t)nw * n * 4 * n, T(0));
+    const V* pm = static_cast<const V*>(psiM);
+    const V* dp = static_cast<const V*>(dpsiM);
+    const V* d2 = static_cast<const V*>(d2psiM);
+    std::vector<DV> at((size_t)nw * n * n);
+    std::vector<V> gl((size_t)nw * n * 4 * n, V(0));
     for (int iw = 0; iw < nw; ++iw)
       for (int e = 0; e < n; ++e)
         for (int j = 0; j < n; ++j)
         {
-          at[((size_t)iw * n + j) * n + e] = (double)pm[((size_t)iw * n + e) * n + j];
-          T* g                             = &gl[((size_t)iw * n + e) * 4 * n];
+          at[((size_t)iw * n + j) * n + e] = to_dbl(pm[((size_t)iw * n + e) * n + j]);
+          V* g                             = &gl[((size_t)iw * n + e) * 4 * n];
           if (dp)
             for (int d = 0; d < 3; ++d)
               g[(size_t)d * n + j] = dp[(((size_t)iw * n + e) * n + j) * 3 + d];
           if (d2)
             g[(size_t)3 * n + j] = d2[((size_t)iw * n + e) * n + j];
         }
-    DevBuf<double> AT;
+    DevBuf<DV> AT;
     AT.alloc(at.size(), false);
-    QMCB_CUDA(cudaMemcpyAsync(AT.p, at.data(), at.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    QMCB_CUDA(cudaMemcpyAsync(GL[spin].p, gl.data(), gl.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    QMCB_CUDA(cudaMemcpyAsync(AT.p, at.data(), at.size() * sizeof(DV), cudaMemcpyHostToDevice, st));
+    QMCB_CUDA(cudaMemcpyAsync(GL[spin].p, gl.data(), gl.size() * sizeof(V), cudaMemcpyHostToDevice, st));
     invert_from_AT(spin, AT);
   }
 
@@ -1136,7 +1178,7 @@ struct Crowd : CrowdBase
       const int n = nel[spin];
       if (n == 0)
         continue;
-      DevBuf<double> AT;
+      DevBuf<DV> AT;
       AT.alloc((size_t)nw * n * n, false);
       // SPOSet::mw_evaluate_notranspose for splines = loop over electrons calling mw_evaluateVGL (BsplineSet.h:142-189)
       for (int e = 0; e < n; ++e)
@@ -1145,7 +1187,7 @@ struct Crowd : CrowdBase
         make_move_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, displ_zero());
         QMCB_LAUNCH_CHECK();
         launch_spline(spin, MODE_VGL, nullptr, 0, phi_vgl.p, nullptr, st);
-        det_scatter_row_kernel<T><<<dim3(blocks(n, 128), nw), 128, 0, st>>>(det[spin], e, phi_vgl.p, AT.p);
+        det_scatter_row_kernel<V><<<dim3(blocks(n, 128), nw), 128, 0, st>>>(det[spin], e, phi_vgl.p, AT.p);
         QMCB_LAUNCH_CHECK();
       }
       invert_from_AT(spin, AT);
@@ -1169,17 +1211,23 @@ struct Crowd : CrowdBase
     // [accept of the previous electron, if one is pending] + inverse row + component-summed gradient: one launch
     join_jastrow();
     apply_pending(iat, grads_tmp.p);
-    QMCB_CUDA(cudaMemcpyAsync(h_t.p, grads_tmp.p, (size_t)nw * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    QMCB_CUDA(cudaMemcpyAsync(h_t.p, grads_tmp.p, (size_t)nw * 3 * sizeof(V), cudaMemcpyDeviceToHost, st));
     sync();
-    for (int i = 0; i < 3 * nw; ++i)
-      grads[i] = (double)h_t.p[i];
+    widen(grads, h_t.p, 3 * (size_t)nw);
+  }
+  // staged values -> the caller's doubles (complex values stay interleaved re, im)
+  static void widen(double* out, const V* in, size_t count)
+  {
+    const T* src = reinterpret_cast<const T*>(in);
+    for (size_t i = 0; i < count * ncomp; ++i)
+      out[i] = (double)src[i];
   }
 
   void ps_make_move(int iat, const double* dsp) override
   {
     check_iat(iat);
     flush_pending();
-    T* h = h_t.p + 4 * (size_t)nw; // second half of the staging buffer
+    T* h = reinterpret_cast<T*>(h_t.p + 4 * (size_t)nw); // second half of the staging buffer
     for (int i = 0; i < 3 * nw; ++i)
       h[i] = (T)dsp[i];
     QMCB_CUDA(cudaMemcpyAsync(displ.p, h, (size_t)nw * 3 * sizeof(T), cudaMemcpyHostToDevice, st));
@@ -1214,14 +1262,13 @@ struct Crowd : CrowdBase
     ensure_row(spin, row);
     launch_spline(spin, MODE_VGL, invRow[spin].p, det[spin].n, phi_vgl.p, rg.p, st);
     join_jastrow();
-    twf_ratio_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, rg.p, rg_nparts, ratios_d.p, grads_tmp.p);
+    twf_ratio_kernel<T, V><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, rg.p, rg_nparts, ratios_d.p, grads_tmp.p);
     QMCB_LAUNCH_CHECK();
-    QMCB_CUDA(cudaMemcpyAsync(h_d.p, ratios_d.p, (size_t)nw * sizeof(double), cudaMemcpyDeviceToHost, st));
-    QMCB_CUDA(cudaMemcpyAsync(h_t.p, grads_tmp.p, (size_t)nw * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    QMCB_CUDA(cudaMemcpyAsync(h_d.p, ratios_d.p, (size_t)nw * sizeof(DV), cudaMemcpyDeviceToHost, st));
+    QMCB_CUDA(cudaMemcpyAsync(h_t.p, grads_tmp.p, (size_t)nw * 3 * sizeof(V), cudaMemcpyDeviceToHost, st));
     sync();
-    std::memcpy(ratios, h_d.p, (size_t)nw * sizeof(double));
-    for (int i = 0; i < 3 * nw; ++i)
-      grads[i] = (double)h_t.p[i];
+    std::memcpy(ratios, h_d.p, (size_t)nw * sizeof(DV));
+    widen(grads, h_t.p, 3 * (size_t)nw);
   }
 
   void twf_accept_reject(int iat, const uint8_t* acc, int safe_to_delay) override
@@ -1254,27 +1301,28 @@ struct Crowd : CrowdBase
     for (int spin = 0; spin < 2; ++spin)
       if (nel[spin] > 0)
       {
-        det_compute_gl_kernel<T, T><<<dim3(nel[spin], nw), 128, 0, st>>>(det[spin], first[spin], N, Gd.p, Ld.p);
+        det_compute_gl_kernel<V, V><<<dim3(nel[spin], nw), 128, 0, st>>>(det[spin], first[spin], N, Gd.p, Ld.p);
         QMCB_LAUNCH_CHECK();
       }
     if (jas.has_j2 || jas.has_j1)
     {
-      jastrow_add_gl_kernel<T><<<dim3(blocks(N, 256), nw), 256, 0, st>>>(jas, Gd.p, Ld.p);
+      jastrow_add_gl_kernel<T><<<dim3(blocks(N, 256), nw), 256, 0, st>>>(jas, reinterpret_cast<T*>(Gd.p),
+                                                                         reinterpret_cast<T*>(Ld.p), ncomp);
       QMCB_LAUNCH_CHECK();
     }
-    ke_kernel<T><<<nw, 256, 0, st>>>(N, Gd.p, Ld.p, ke_d.p);
+    ke_kernel<V><<<nw, 256, 0, st>>>(N, Gd.p, Ld.p, ke_d.p);
     QMCB_LAUNCH_CHECK();
-    std::vector<T> hg, hl;
+    std::vector<V> hg, hl;
     std::vector<double> hk(nw), l0(2 * (size_t)nw), l1(2 * (size_t)nw), lj2(nw, 0.0), lj1(nw, 0.0);
     if (G)
     {
       hg.resize((size_t)nw * N * 3);
-      QMCB_CUDA(cudaMemcpyAsync(hg.data(), Gd.p, hg.size() * sizeof(T), cudaMemcpyDeviceToHost, st));
+      QMCB_CUDA(cudaMemcpyAsync(hg.data(), Gd.p, hg.size() * sizeof(V), cudaMemcpyDeviceToHost, st));
     }
     if (L)
     {
       hl.resize((size_t)nw * N);
-      QMCB_CUDA(cudaMemcpyAsync(hl.data(), Ld.p, hl.size() * sizeof(T), cudaMemcpyDeviceToHost, st));
+      QMCB_CUDA(cudaMemcpyAsync(hl.data(), Ld.p, hl.size() * sizeof(V), cudaMemcpyDeviceToHost, st));
     }
     QMCB_CUDA(cudaMemcpyAsync(hk.data(), ke_d.p, nw * sizeof(double), cudaMemcpyDeviceToHost, st));
     QMCB_CUDA(cudaMemcpyAsync(l0.data(), logdet[0].p, l0.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1285,11 +1333,9 @@ struct Crowd : CrowdBase
       QMCB_CUDA(cudaMemcpyAsync(lj1.data(), j1_log.p, nw * sizeof(double), cudaMemcpyDeviceToHost, st));
     sync();
     if (G)
-      for (size_t i = 0; i < hg.size(); ++i)
-        G[i] = (double)hg[i];
+      widen(G, hg.data(), hg.size());
     if (L)
-      for (size_t i = 0; i < hl.size(); ++i)
-        L[i] = (double)hl[i];
+      widen(L, hl.data(), hl.size());
     for (int iw = 0; iw < nw; ++iw)
     {
       if (ke)
@@ -1316,11 +1362,11 @@ struct Crowd : CrowdBase
     check_iat(iat);
     if (!jas.has_j2)
       throw std::runtime_error("no two-body Jastrow in this crowd");
-    j2_ratio_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, ratios_d.p, grads_tmp.p);
+    j2_ratio_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, ke_d.p, displ.p); // (real scratch buffers)
     QMCB_LAUNCH_CHECK();
-    QMCB_CUDA(cudaMemcpyAsync(ratios, ratios_d.p, (size_t)nw * sizeof(double), cudaMemcpyDeviceToHost, st));
+    QMCB_CUDA(cudaMemcpyAsync(ratios, ke_d.p, (size_t)nw * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (grads)
-      QMCB_CUDA(cudaMemcpyAsync(grads, grads_tmp.p, (size_t)nw * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
+      QMCB_CUDA(cudaMemcpyAsync(grads, displ.p, (size_t)nw * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
     sync();
   }
   void j2_accept_reject(int iat, const uint8_t* acc) override
@@ -1373,7 +1419,7 @@ struct Crowd : CrowdBase
     A(n_acc, nw);
     A(n_rej, nw);
     A(accept_log, (size_t)N * nw);
-    drv.deltas = deltas.p, drv.drifts = drifts.p, drv.delta_cur = delta_cur.p, drv.grads_now = grads_tmp.p;
+    drv.deltas = deltas.p, drv.drifts = drifts.p, drv.delta_cur = delta_cur.p, drv.grads_now = nullptr;
     drv.accepted = accepted.p, drv.n_accept = n_acc.p, drv.n_reject = n_rej.p, drv.accept_log = nullptr;
     // raw stream: one sweep consumes at most 2*ceil(3*nw*N/2) (Box-Muller) + nw*N (accept tests) outputs
     const unsigned long long gcount = 3ull * nw * N;
@@ -1398,7 +1444,7 @@ struct Crowd : CrowdBase
 
   // one launch of move_boundary_kernel: accept of electron iat_prev (or -1) and row preparation of iat_next (or -1).
   // ext_flags / twf_grads_out select the host-driven mode (Metropolis test done by the caller).
-  void launch_boundary(const DriverDev<T>& dr, int iat_prev, int iat_next, const unsigned char* ext_flags, T* twf_grads_out)
+  void launch_boundary(const DriverDev<T>& dr, int iat_prev, int iat_next, const unsigned char* ext_flags, V* twf_grads_out)
   {
     int igp = 0, rp = 0, ign = 0, rn = 0;
     if (iat_prev >= 0)
@@ -1418,13 +1464,15 @@ struct Crowd : CrowdBase
     if (iat_prev >= 0 && iat_next >= 0)
       cn = cp + 1; // the slot appended by part 1 of this very launch
     const int nmx     = std::max(iat_prev >= 0 ? det[igp].n : 0, iat_next >= 0 ? det[ign].n : 0);
-    const size_t smem = (size_t)(10 * nmx + k * (k + 1) + 5 * k) * sizeof(T);
+    const size_t smem = (size_t)(10 * nmx + k * (k + 1) + 5 * k) * sizeof(V);
+    if (smem > 200 * 1024)
+      throw std::runtime_error("determinant too wide for the boundary kernel's shared-memory staging");
     if (smem > 48 * 1024 && !mb_attr_set)
     {
-      QMCB_CUDA(cudaFuncSetAttribute(move_boundary_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      QMCB_CUDA(cudaFuncSetAttribute(move_boundary_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       mb_attr_set = true;
     }
-    move_boundary_kernel<T><<<nw, MB_TPB, smem, st>>>(dr, jas, rng, det[igp], iat_prev, rp, cp, rg.p, rg_nparts, phi_vgl.p,
+    move_boundary_kernel<T, V><<<nw, MB_TPB, smem, st>>>(dr, jas, rng, det[igp], iat_prev, rp, cp, rg.p, rg_nparts, phi_vgl.p,
                                                       det[ign], iat_next, rn, cn, det_grads.p, ext_flags, twf_grads_out);
     QMCB_LAUNCH_CHECK();
     if (iat_prev >= 0)
@@ -1440,7 +1488,7 @@ struct Crowd : CrowdBase
   // accept(iat) + evalGrad(iat+1) -- two consecutive calls of the reference's driver loop -- become ONE launch
   int pending_iat = -1;
   DriverDev<T> drv_host{};
-  void apply_pending(int iat_next, T* twf_grads_out)
+  void apply_pending(int iat_next, V* twf_grads_out)
   {
     if (pending_iat < 0)
     {
@@ -1588,10 +1636,12 @@ struct Crowd : CrowdBase
 
 CrowdBase* make_crowd(const qmcb_system* sys, int nw)
 {
+  // complex orbitals (SplineC2C tables) select the complex determinant engine, as QMC_COMPLEX does in the reference
+  const bool cplx = sys->spo[0] && sys->spo[0]->impl && sys->spo[0]->impl->kind == QMCB_C2C;
   if (sys->precision == QMCB_MIXED)
-    return new Crowd<float>(sys, nw);
+    return cplx ? static_cast<CrowdBase*>(new Crowd<float, cx<float>>(sys, nw)) : new Crowd<float, float>(sys, nw);
   if (sys->precision == QMCB_FULL)
-    return new Crowd<double>(sys, nw);
+    return cplx ? static_cast<CrowdBase*>(new Crowd<double, cx<double>>(sys, nw)) : new Crowd<double, double>(sys, nw);
   throw std::runtime_error("unknown precision code");
 }
 

@@ -41,6 +41,22 @@ struct DetDev
 #ifdef __CUDACC__
 constexpr int DET_TPB = 256;
 
+// log_value += log(curRatio) as a complex logarithm (DiracDeterminantBatched.cpp:501): ld = {log|r|, arg r}
+__device__ __forceinline__ void logdet_accumulate(double* ld, const double r)
+{
+  ld[0] += log(fabs(r));
+  if (r < 0)
+    ld[1] += 3.14159265358979323846;
+}
+__device__ __forceinline__ void logdet_accumulate(double* ld, const float r) { logdet_accumulate(ld, (double)r); }
+template<typename T>
+__device__ __forceinline__ void logdet_accumulate(double* ld, const cx<T>& r)
+{
+  const double re = (double)r.re, im = (double)r.im;
+  ld[0] += 0.5 * log(re * re + im * im);
+  ld[1] += atan2(im, re);
+}
+
 // invRow = Ainv[row] - V^T (Binv^T (U Ainv[row]))  and  grad_now = invRow . dpsiM[row]   (walker iw, thread group g)
 // x[n], p[k], w[k] shared scratch; red >= 3*32.  On return every thread of the group holds grad_now in gout (if asked).
 // x_ready: x[] already holds Ainv[row]; p_ready: p[0..p_ready) = U[a].x already computed by the caller
@@ -219,11 +235,7 @@ __device__ __forceinline__ void det_accept_body(const Group& g, const DetDev<T>&
     {
       B[c * k + c]               = sigma;
       D.list[(size_t)iw * k + c] = row;
-      // log_value += log(curRatio) (complex log), DiracDeterminantBatched.cpp:501
-      const double r = (double)ratio;
-      D.logdet[2 * (size_t)iw] += log(fabs(r));
-      if (r < 0)
-        D.logdet[2 * (size_t)iw + 1] += 3.14159265358979323846;
+      logdet_accumulate(D.logdet + 2 * (size_t)iw, ratio);
     }
   }
   else
@@ -353,7 +365,8 @@ __global__ void __launch_bounds__(256)
 // psiM scatter for the from-scratch path: phi_vgl [5][nw][n] of electron `e` -> transposed FP64 matrix
 // AT[iw][j][e] = phi_j (so that the column-major LU of AT is the LU of psiM) and GL[iw][e][4][n]
 template<typename T>
-__global__ void det_scatter_row_kernel(const DetDev<T> D, const int e, const T* phi_vgl, double* AT)
+__global__ void det_scatter_row_kernel(const DetDev<T> D, const int e, const T* phi_vgl,
+                                       typename value_traits<T>::dbl_t* AT)
 {
   const int iw = blockIdx.y, n = D.n;
   const int j  = blockIdx.x * blockDim.x + threadIdx.x;
@@ -361,7 +374,7 @@ __global__ void det_scatter_row_kernel(const DetDev<T> D, const int e, const T* 
     return;
   const size_t fs = (size_t)D.nw * n;
   const T* ph     = phi_vgl + (size_t)iw * n;
-  AT[((size_t)iw * n + j) * n + e] = (double)ph[j];
+  AT[((size_t)iw * n + j) * n + e] = to_dbl(ph[j]);
   T* gl                            = D.GL + ((size_t)iw * n + e) * 4 * n;
   gl[j]                            = ph[fs + j];
   gl[n + j]                        = ph[2 * fs + j];
@@ -371,19 +384,18 @@ __global__ void det_scatter_row_kernel(const DetDev<T> D, const int e, const T* 
 
 // log-determinant from the LU factors (DiracMatrix.h:100-107 / detail/CUDA/cuBLAS_LU.cu:61-110):
 // sum_i log(complex(pivot[i]==i+1 ? diag : -diag)); LU is column-major [n][n] per walker
-__global__ void det_logdet_kernel(const double* LU, const int* piv, int n, double* logdet)
+template<typename DT /* double or cx<double> */>
+__global__ void det_logdet_kernel(const DT* LU, const int* piv, int n, double* logdet)
 {
   __shared__ double red[2 * 32];
   const int iw = blockIdx.x, tid = threadIdx.x;
   double acc[2] = {0.0, 0.0};
   for (int i = tid; i < n; i += blockDim.x)
   {
-    double d = LU[((size_t)iw * n + i) * n + i];
+    DT d = LU[((size_t)iw * n + i) * n + i];
     if (piv[(size_t)iw * n + i] != i + 1)
       d = -d;
-    acc[0] += log(fabs(d));
-    if (d < 0)
-      acc[1] += 3.14159265358979323846;
+    logdet_accumulate(acc, d);
   }
   block_sum<double, 2>(acc, red);
   if (tid == 0)
@@ -395,12 +407,12 @@ __global__ void det_logdet_kernel(const double* LU, const int* piv, int n, doubl
 
 // inverse (column-major X^-1 == row-major (X^-1)^T) cast into Ainv [nw][n][lda]
 template<typename T>
-__global__ void det_store_inverse_kernel(const DetDev<T> D, const double* inv)
+__global__ void det_store_inverse_kernel(const DetDev<T> D, const typename value_traits<T>::dbl_t* inv)
 {
   const int iw = blockIdx.z, i = blockIdx.y, n = D.n;
   const int j  = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n)
-    D.Ainv[((size_t)iw * n + i) * D.lda + j] = (T)inv[((size_t)iw * n + i) * n + j];
+    D.Ainv[((size_t)iw * n + i) * D.lda + j] = from_dbl<T>(inv[((size_t)iw * n + i) * n + j]);
 }
 
 // G, L of every electron of this determinant (DiracDeterminantBatched.cpp:594-604 computeGL):

@@ -46,6 +46,7 @@ struct CrowdBase
   virtual ~CrowdBase() {}
   virtual void sync()                                                                                       = 0;
   virtual size_t device_bytes() const                                                                       = 0;
+  virtual bool is_complex() const                                                                           = 0;
   virtual void set_positions(const double* R)                                                               = 0;
   virtual void get_positions(double* R)                                                                     = 0;
   virtual void twf_recompute()                                                                              = 0;

@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(JAS_TPB) jastrow_recompute_kernel(const Jastro
 
 // G += dUat, L += d2Uat (J2);  G += Grad, L -= Lap (J1).   grid = (ceil(N/256), nw)
 template<typename RT>
-__global__ void jastrow_add_gl_kernel(const JastrowDev<RT> J, RT* Gd, RT* Ld)
+__global__ void jastrow_add_gl_kernel(const JastrowDev<RT> J, RT* Gd, RT* Ld, const int cs /* 1 real, 2 complex (re,im) */)
 {
   const int iw = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x, N = J.N, np = J.npad;
   if (i >= N)
@@ -455,11 +455,12 @@ __global__ void jastrow_add_gl_kernel(const JastrowDev<RT> J, RT* Gd, RT* Ld)
     g[2] += J.Grad1[((size_t)iw * 3 + 2) * N + i];
     l -= J.Lap1[(size_t)iw * N + i];
   }
-  RT* go = Gd + ((size_t)iw * N + i) * 3;
+  // the Jastrows are real: with complex G, L (cs == 2) only the real parts receive a contribution
+  RT* go = Gd + ((size_t)iw * N + i) * 3 * cs;
   go[0] += g[0];
-  go[1] += g[1];
-  go[2] += g[2];
-  Ld[(size_t)iw * N + i] += l;
+  go[cs] += g[1];
+  go[2 * cs] += g[2];
+  Ld[((size_t)iw * N + i) * cs] += l;
 }
 #endif
 

@@ -84,7 +84,10 @@ void advance_crowd(CrowdCtx& cx, int N, double tau, bool use_drift, uint8_t* log
   const RT sqrttau     = std::sqrt(tauovermass);
   std::vector<RT> walker_deltas(3 * (size_t)nw * N), deltas(3 * (size_t)nw), drifts(3 * (size_t)nw), log_gf(nw, RT(0)),
       log_gb(nw, RT(0)), prob(nw);
-  std::vector<double> grads(3 * (size_t)nw), displ(3 * (size_t)nw), ratios(nw);
+  // complex orbitals: ratios [nw][2] and grads [nw][3][2] arrive as interleaved (re, im) doubles; the drift takes the
+  // real part of the gradient (DriftModifierUNR.cpp:20-23) and prob = std::norm(ratio) (VMCBatched.cpp:152)
+  const int cs = qmcb_crowd_is_complex(cx.crowd) ? 2 : 1;
+  std::vector<double> grads(3 * (size_t)nw * cs), displ(3 * (size_t)nw), ratios((size_t)nw * cs);
   std::vector<uint8_t> accepted(nw);
   assignGaussRand(walker_deltas.data(), (unsigned)walker_deltas.size(), cx.rng);
   for (int iat = 0; iat < N; ++iat)
@@ -97,7 +100,7 @@ void advance_crowd(CrowdCtx& cx, int N, double tau, bool use_drift, uint8_t* log
       chk(qmcb_twf_mw_eval_grad(cx.crowd, iat, grads.data()));
       for (int i = 0; i < nw; ++i)
       {
-        const RT g[3] = {(RT)grads[3 * i], (RT)grads[3 * i + 1], (RT)grads[3 * i + 2]};
+        const RT g[3] = {(RT)grads[(3 * i) * cs], (RT)grads[(3 * i + 1) * cs], (RT)grads[(3 * i + 2) * cs]};
         RT dr[3];
         getDrift<RT>(tauovermass, g, dr);
         for (int d = 0; d < 3; ++d)
@@ -115,7 +118,7 @@ void advance_crowd(CrowdCtx& cx, int N, double tau, bool use_drift, uint8_t* log
       {
         const RT* dl = &deltas[3 * i];
         log_gf[i]    = -oneover2tau * (dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
-        const RT g[3] = {(RT)grads[3 * i], (RT)grads[3 * i + 1], (RT)grads[3 * i + 2]};
+        const RT g[3] = {(RT)grads[(3 * i) * cs], (RT)grads[(3 * i + 1) * cs], (RT)grads[(3 * i + 2) * cs]};
         RT dr[3];
         getDrift<RT>(tauovermass, g, dr);
         for (int d = 0; d < 3; ++d)
@@ -123,7 +126,7 @@ void advance_crowd(CrowdCtx& cx, int N, double tau, bool use_drift, uint8_t* log
         log_gb[i] = -oneover2tau * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
       }
     for (int i = 0; i < nw; ++i)
-      prob[i] = (RT)(ratios[i] * ratios[i]);
+      prob[i] = cs == 2 ? (RT)(ratios[2 * i] * ratios[2 * i] + ratios[2 * i + 1] * ratios[2 * i + 1]) : (RT)(ratios[i] * ratios[i]);
     for (int i = 0; i < nw; ++i)
     {
       // the uniform is drawn only when the move is valid and prob >= eps (VMCBatched.cpp:156-158)
@@ -251,8 +254,9 @@ int qmcb_host_vmc_bytes_per_sweep(qmcb_host_vmc* d, long long* h2d, long long* d
   for (auto& c : d->crowds)
   {
     // per move: displacement [nw][3] T + accept flags [nw] up; grads_now [nw][3] T (drift only) + ratios [nw] f64 + grads_new [nw][3] T down
+    const long long cs = qmcb_crowd_is_complex(c.crowd) ? 2 : 1; // complex gradients / ratios are (re, im) pairs
     up += (long long)d->N * ((long long)c.nw * 3 * T + c.nw);
-    down += (long long)d->N * ((d->use_drift ? (long long)c.nw * 3 * T : 0) + (long long)c.nw * 8 + (long long)c.nw * 3 * T);
+    down += (long long)d->N * ((d->use_drift ? (long long)c.nw * 3 * T * cs : 0) + (long long)c.nw * 8 * cs + (long long)c.nw * 3 * T * cs);
   }
   *h2d = up;
   *d2h = down;

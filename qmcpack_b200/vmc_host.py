@@ -36,7 +36,7 @@ def advance_walkers(crowd, rng, tau=0.3, use_drift=True, log_accept=None, log_ra
     for iat in range(N):
         deltas = (walker_deltas[iat] * sqrttau).astype(RT)
         if use_drift:
-            grads_now = crowd.mw_evalGrad(iat).astype(RT)
+            grads_now = np.real(crowd.mw_evalGrad(iat)).astype(RT)  # convertToReal of a complex gradient
             drifts = (get_drift(tauovermass, grads_now, RT) + deltas).astype(RT)
         else:
             drifts = deltas
@@ -46,9 +46,9 @@ def advance_walkers(crowd, rng, tau=0.3, use_drift=True, log_accept=None, log_ra
         log_gb = np.zeros(nw, RT)
         if use_drift:
             log_gf = (-oneover2tau * (deltas * deltas).sum(axis=1, dtype=RT)).astype(RT)
-            rev = (get_drift(tauovermass, grads_new.astype(RT), RT) + drifts).astype(RT)
+            rev = (get_drift(tauovermass, np.real(grads_new).astype(RT), RT) + drifts).astype(RT)
             log_gb = (-oneover2tau * (rev * rev).sum(axis=1, dtype=RT)).astype(RT)
-        prob = (ratios * ratios).astype(RT)
+        prob = (np.abs(ratios) ** 2 if np.iscomplexobj(ratios) else ratios * ratios).astype(RT)  # std::norm
         accepted = np.zeros(nw, np.uint8)
         for iw in range(nw):  # the uniform is drawn only when prob >= eps (VMCBatched.cpp:156-158)
             if prob[iw] >= eps and rng.uniform() < np.float64(RT(prob[iw] * np.exp(RT(log_gb[iw] - log_gf[iw])))):

@@ -101,19 +101,54 @@ def pw_table(M, n_spl, dtype, seed):
     return c
 
 
+def pw_table_complex(M, n_orb, dtype, seed):
+    """Complex analogue of pw_table for SplineC2C: orbital j = sum_G Q[G, j] exp(i G.r) with Q a seeded random UNITARY
+    matrix over the n_orb lowest reciprocal vectors; real and imaginary parts are stored as the component pair
+    (2j, 2j+1) of a [M+3]^3 x npad(2 n_orb) real table (SplineC2C.h: "the internal storage is real type arrays")."""
+    if np.isscalar(M):
+        M = (M, M, M)
+    npad = aligned_size(dtype, 2 * n_orb)
+    rng = np.random.default_rng(seed)
+    gmax = 1
+    while (2 * gmax + 1) ** 3 < n_orb + 8:
+        gmax += 1
+    g = [(i, j, k) for i in range(-gmax, gmax + 1) for j in range(-gmax, gmax + 1) for k in range(-gmax, gmax + 1)]
+    g.sort(key=lambda t: (t[0] ** 2 + t[1] ** 2 + t[2] ** 2, t))
+    gv = np.array(g[:n_orb], np.float64)
+    Q, _ = np.linalg.qr(rng.normal(size=(n_orb, n_orb)) + 1j * rng.normal(size=(n_orb, n_orb)))
+    c = aligned_zeros((M[0] + 3, M[1] + 3, M[2] + 3, npad), dtype)
+    ys, zs = np.meshgrid(np.arange(M[1] + 3) / M[1], np.arange(M[2] + 3) / M[2], indexing="ij")
+    pyz = 2 * np.pi * (ys.reshape(-1, 1) * gv[None, :, 1] + zs.reshape(-1, 1) * gv[None, :, 2])
+    for ix in range(M[0]):
+        ph = pyz + 2 * np.pi * (ix / M[0]) * gv[None, :, 0]
+        u = (np.exp(1j * ph) @ Q).reshape(M[1] + 3, M[2] + 3, n_orb)
+        c[ix, :, :, 0:2 * n_orb:2] = u.real
+        c[ix, :, :, 1:2 * n_orb:2] = u.imag
+    c[M[0]:, :, :, :] = c[:3, :, :, :]
+    return c
+
+
 def make_system(N=768, M=60, dtype=np.float32, L=None, seed=20240, with_j1=True, with_j2=True, lattice=None,
-                same_table=False, table="pw"):
+                same_table=False, table="pw", complex_orbitals=False, twist=(0.25, 0.25, 0.25)):
     """A synthetic NiO-like system: cubic cell scaled so the electron density matches a64, two spin tables.
-    table = "pw" (random orthogonal plane-wave mixtures, default) or "iid" (i.i.d. uniform coefficients)."""
+    table = "pw" (random orthogonal plane-wave mixtures, default) or "iid" (i.i.d. uniform coefficients).
+    complex_orbitals: SplineC2C tables (2n real components per spin) + one twist vector k = 2 pi G.twist for every
+    orbital (system["kpts"], Cartesian) -- the NiO-a128 class of BASELINE.json."""
     n_up = N // 2
     n_dn = N - n_up
     if L is None:
         L = L_A64 * (N / 768.0) ** (1.0 / 3.0)
     lat = np.asarray(lattice, np.float64).reshape(3, 3) if lattice is not None else np.eye(3) * L
-    mk = pw_table if table == "pw" else random_table
+    if complex_orbitals:
+        mk = pw_table_complex if table == "pw" else (lambda M_, n_, dt_, sd_: random_table(M_, 2 * n_, dt_, sd_))
+    else:
+        mk = pw_table if table == "pw" else random_table
     t_up = mk(M, n_up, dtype, seed)
     t_dn = t_up if same_table else mk(M, n_dn, dtype, seed + 1)
     s = dict(n_up=n_up, n_dn=n_dn, lattice=lat, coefs=[t_up, t_dn], grid=(M, M, M) if np.isscalar(M) else tuple(M))
+    if complex_orbitals:
+        kc = 2 * np.pi * (np.linalg.inv(lat) @ np.asarray(twist, np.float64))
+        s["kpts"] = [np.tile(kc, (n_up, 1)), np.tile(kc, (n_dn, 1))]
     if with_j2:
         s["j2"] = dict(uu=J2_UU, ud=J2_UD, rcut=min(J2_RCUT, 0.4999 * L_wigner_seitz(lat)))
     if with_j1:

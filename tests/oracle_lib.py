@@ -40,6 +40,7 @@ class VMCParams(C.Structure):
         ("n_j1", C.c_int), ("j1_params", c_dp), ("j1_rcut", c_dp),
         ("nw", C.c_int), ("ncrowds", C.c_int), ("seeds", C.POINTER(C.c_uint32)),
         ("tau", C.c_double), ("use_drift", C.c_int), ("delay_rank", C.c_int), ("batched_engine", C.c_int),
+        ("complex_orbitals", C.c_int), ("kpts", c_dp * 2),
     ]
 
 
@@ -93,10 +94,13 @@ class Oracle:
 
     @staticmethod
     def suf(dtype):
-        return "f" if np.dtype(dtype) == np.float32 else "d"
+        return {np.dtype(np.float32): "f", np.dtype(np.float64): "d", np.dtype(np.complex64): "c",
+                np.dtype(np.complex128): "z"}[np.dtype(dtype)]
 
     def aligned_size(self, dtype, n):
-        return int(self.lib.orc_aligned_size(1 if np.dtype(dtype) == np.float32 else 0, n))
+        """getAlignedSize<T>(n): 64-byte rows (aligned_allocator.hpp:41-47)"""
+        per = 64 // np.dtype(dtype).itemsize
+        return ((int(n) + per - 1) // per) * per
 
     # -- golden-vector pieces
     def symtrace(self, h, gg):
@@ -322,8 +326,9 @@ class DelayedUpdateHandle:
 
     def accept_row(self, Ainv, row, psiV, ratio):
         psiV = _np(psiV, self.dt)
+        ratio = complex(ratio)
         getattr(self.o.lib, "orc_du_accept_row_" + self.s)(self.h, _p(Ainv), C.c_int(Ainv.shape[1]), C.c_int(row),
-                                                          _p(psiV), C.c_double(ratio))
+                                                          _p(psiV), C.c_double(ratio.real), C.c_double(ratio.imag))
 
     def pseudo_accept_row(self, Ainv, row):
         getattr(self.o.lib, "orc_du_pseudo_accept_row_" + self.s)(self.h, _p(Ainv), C.c_int(Ainv.shape[1]), C.c_int(row))
@@ -377,6 +382,15 @@ class OracleVMC:
         p.seeds = sd.ctypes.data_as(C.POINTER(C.c_uint32))
         p.tau, p.use_drift, p.delay_rank = tau, int(use_drift), delay_rank
         p.batched_engine = int(batched_engine and not orc.is_reference)
+        # complex orbitals (SplineC2C): system["kpts"] = per-spin [n][3] Cartesian twist vectors, tables hold 2n components
+        kp = s.get("kpts")
+        self.cplx = kp is not None
+        p.complex_orbitals = int(self.cplx)
+        if self.cplx:
+            for i in range(2):
+                k = _np(kp[i], np.float64)
+                self._keep.append(k)
+                p.kpts[i] = k.ctypes.data_as(c_dp)
         self.p = p
         self.N = p.n_up + p.n_dn
         self.nw = nw
@@ -409,7 +423,7 @@ class OracleVMC:
         forced = _np(forced, np.uint8)
         nsteps = forced.shape[0]
         assert forced.shape == (nsteps, self.N, self.nw)
-        ratios = np.zeros((nsteps, self.N, self.nw), np.float64) if want_ratios else None
+        ratios = np.zeros((nsteps, self.N, self.nw), np.complex128 if self.cplx else np.float64) if want_ratios else None
         self.o._chk(self.o.lib.orc_vmc_sweep_forced(self.h, C.c_int(nsteps), _p(forced),
                                                     _p(ratios) if want_ratios else None))
         return ratios
@@ -421,7 +435,8 @@ class OracleVMC:
 
     def evaluate_gl(self):
         logpsi, ke = np.zeros(self.nw), np.zeros(self.nw)
-        G, L = np.zeros((self.nw, self.N, 3)), np.zeros((self.nw, self.N))
+        dt = np.complex128 if self.cplx else np.float64
+        G, L = np.zeros((self.nw, self.N, 3), dt), np.zeros((self.nw, self.N), dt)
         self.o._chk(self.o.lib.orc_vmc_evaluate_gl(self.h, _p(logpsi), _p(ke), _p(G), _p(L)))
         return logpsi, ke, G, L
 
@@ -432,7 +447,7 @@ class OracleVMC:
 
     def psiminv(self, iw, s):
         n = self.p.n_up if s == 0 else self.p.n_dn
-        out = np.zeros((n, n))
+        out = np.zeros((n, n), np.complex128 if self.cplx else np.float64)
         ld = C.c_double(0)
         self.o._chk(self.o.lib.orc_vmc_get_psiminv(self.h, C.c_int(iw), C.c_int(s), _p(out), C.byref(ld)))
         return out, ld.value

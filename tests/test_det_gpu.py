@@ -17,8 +17,21 @@ def api():
 def tiny_system(n, dt):
     """a crowd needs an SPOSet handle per determinant; the determinant tests feed orbital rows directly"""
     from qmcpack_b200.workload import random_table
+    dt = np.dtype(dt)
+    if dt.kind == "c":  # complex determinants sit on SplineC2C tables (2n real components + twist vectors)
+        t = random_table((4, 4, 4), 2 * n, np.float32 if dt == np.complex64 else np.float64, seed=1)
+        k = np.tile([0.1, 0.2, 0.3], (n, 1))
+        return dict(n_up=n, n_dn=n, lattice=np.eye(3) * 4.0, coefs=[t, t], kpts=[k, k])
     t = random_table((4, 4, 4), n, dt, seed=1)
     return dict(n_up=n, n_dn=n, lattice=np.eye(3) * 4.0, coefs=[t, t])
+
+
+def normal(rng, shape, dt):
+    """standard normal samples of a real or complex dtype"""
+    dt = np.dtype(dt)
+    if dt.kind == "c":
+        return (rng.normal(size=shape) + 1j * rng.normal(size=shape)).astype(dt)
+    return rng.normal(size=shape).astype(dt)
 
 
 def test_reference_3x3_literals(api):
@@ -46,7 +59,7 @@ def test_reference_3x3_literals(api):
     assert inv[1] == pytest.approx(b, rel=1e-8)  # rejected walker untouched
 
 
-@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("dt", [np.float64, np.float32, np.complex128, np.complex64])
 @pytest.mark.parametrize("n,k", [(24, 1), (24, 2), (24, 8), (70, 16), (192, 32), (130, 64)])
 def test_delayed_update_sequence_matches_oracle(api, orc, dt, n, k):
     """random accept/reject sequence, every walker with its own flags: inverse rows, ratios, gradients at every move and
@@ -56,9 +69,10 @@ def test_delayed_update_sequence_matches_oracle(api, orc, dt, n, k):
     rng = np.random.default_rng(100 + n + k)
     crowd = api.Crowd(tiny_system(n, dt), nw=nw, delay_rank=k)
     amp = 0.5 / np.sqrt(n)  # keeps the matrices well conditioned so that only rounding separates GPU and CPU
-    psiM = (2 * np.eye(n) + amp * rng.normal(size=(nw, n, n))).astype(dt)
-    dpsiM = rng.normal(size=(nw, n, n, 3)).astype(dt)
-    d2psiM = rng.normal(size=(nw, n, n)).astype(dt)
+    psiM = (2 * np.eye(n) + amp * normal(rng, (nw, n, n), dt)).astype(dt)
+    dpsiM = normal(rng, (nw, n, n, 3), dt)
+    d2psiM = normal(rng, (nw, n, n), dt)
+    wide = np.complex128 if np.dtype(dt).kind == "c" else np.float64
     crowd.det_recompute_from_matrices(1, psiM, dpsiM, d2psiM)
     lda = orc.aligned_size(dt, n)
     ainv, logdet, eng = [], [], []
@@ -68,7 +82,8 @@ def test_delayed_update_sequence_matches_oracle(api, orc, dt, n, k):
         logdet.append(ld.real)
         eng.append(orc.du(n, k, dt))
     inv0, ld0 = crowd.det_mw_completeUpdates(1)
-    tol = 1e-8 if dt == np.float64 else 2e-4
+    tol = 1e-8 if np.dtype(dt).itemsize // (2 if np.dtype(dt).kind == 'c' else 1) == 8 else 2e-4
+    fp64 = tol == 1e-8
     for iw in range(nw):
         assert np.abs(inv0[iw] - ainv[iw][:, :n]).max() < tol * np.abs(ainv[iw]).max()
         assert ld0[iw, 0] == pytest.approx(logdet[iw], rel=1e-10)
@@ -79,25 +94,25 @@ def test_delayed_update_sequence_matches_oracle(api, orc, dt, n, k):
         grads_now = crowd.det_mw_evalGrad(1, row)
         rows_gpu = crowd.det_mw_getInvRow(1, row)
         phi = np.zeros((5, nw, n), dt)
-        phi[0] = (2 * np.eye(n)[row] + amp * rng.normal(size=(nw, n))).astype(dt)
-        phi[1:] = rng.normal(size=(4, nw, n)).astype(dt)
+        phi[0] = (2 * np.eye(n)[row] + amp * normal(rng, (nw, n), dt)).astype(dt)
+        phi[1:] = normal(rng, (4, nw, n), dt)
         crowd.det_set_phi_vgl(1, phi)
         ratios, grads = crowd.det_mw_ratioGrad(1, row, from_phi=True)
         acc = (rng.random(nw) < 0.6).astype(np.uint8)
         for iw in range(nw):
             r = eng[iw].get_inv_row(ainv[iw], row)
             assert np.abs(rows_gpu[iw] - r).max() < tol * max(1.0, np.abs(r).max())
-            g_ref = r.astype(np.float64) @ cur_dpsiM[iw, row].astype(np.float64)
+            g_ref = r.astype(wide) @ cur_dpsiM[iw, row].astype(wide)  # plain (unconjugated) dots, SPOSet.cpp:166-171
             assert np.abs(grads_now[iw] - g_ref).max() < tol * 50 * max(1.0, np.abs(g_ref).max())
-            ratio_ref = float(r.astype(np.float64) @ phi[0, iw].astype(np.float64))
-            assert ratios[iw] == pytest.approx(ratio_ref, rel=tol * 10, abs=tol * 10)
-            gn_ref = (r.astype(np.float64) @ phi[1:4, iw].astype(np.float64).T) / ratio_ref
+            ratio_ref = (r.astype(wide) @ phi[0, iw].astype(wide)).item()
+            assert abs(ratios[iw] - ratio_ref) < tol * 10 * max(1.0, abs(ratio_ref))
+            gn_ref = (r.astype(wide) @ phi[1:4, iw].astype(wide).T) / ratio_ref
             assert np.abs(grads[iw] - gn_ref).max() < tol * 100 * max(1.0, np.abs(gn_ref).max())
             if acc[iw]:
-                eng[iw].accept_row(ainv[iw], row, phi[0, iw], float(ratios[iw]))
+                eng[iw].accept_row(ainv[iw], row, phi[0, iw], ratios[iw].item())
                 psiM[iw, row] = phi[0, iw]
                 cur_dpsiM[iw, row] = phi[1:4, iw].T
-                logdet[iw] += np.log(abs(float(ratios[iw])))
+                logdet[iw] += np.log(abs(ratios[iw].item()))
             elif k > 1:
                 eng[iw].pseudo_accept_row(ainv[iw], row)
         crowd.det_mw_accept_rejectRow(1, row, acc)
@@ -108,8 +123,11 @@ def test_delayed_update_sequence_matches_oracle(api, orc, dt, n, k):
         scale = np.abs(ainv[iw]).max()
         assert np.abs(inv[iw] - ainv[iw][:, :n]).max() < tol * scale
         fresh, fld = orc.invert_transpose(psiM[iw], lda=lda)
-        assert np.abs(inv[iw] - fresh[:, :n]).max() < (1e-8 if dt == np.float64 else 5e-3) * scale
-        assert ld[iw, 0] == pytest.approx(fld.real, rel=1e-9 if dt == np.float64 else 1e-4, abs=1e-5)
+        assert np.abs(inv[iw] - fresh[:, :n]).max() < (1e-8 if fp64 else 5e-3) * scale
+        assert ld[iw, 0] == pytest.approx(fld.real, rel=1e-9 if fp64 else 1e-4, abs=1e-5)
+        # phase of the determinant (imaginary part of the complex log) modulo 2 pi
+        dphase = (ld[iw, 1] - fld.imag + np.pi) % (2 * np.pi) - np.pi
+        assert abs(dphase) < (1e-8 if fp64 else 1e-3)
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])

@@ -259,3 +259,64 @@ def test_port_matches_reference_delayed_update(orc, orc_ref, dt, k):
     e2.update_inv_mat(a2)
     scale = float(np.abs(a2).max())
     assert a1 == approx(a2, rel=tol["rel"], abs=tol["abs"] * max(1.0, scale))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# complex value types: restatement vs the reference-compiled kernels (DelayedUpdate<std::complex<T>>, DiracMatrix, zgetrf)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.complex128, np.complex64])
+@pytest.mark.parametrize("k", [1, 4, 8])
+def test_complex_delayed_update_port_matches_reference(orc, orc_ref, dt, k):
+    if orc_ref is None:
+        pytest.skip("oracle/_ref not built")
+    n = 24
+    rng = np.random.default_rng(5 + k)
+    a = (2 * np.eye(n) + 0.1 * (rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n)))).astype(dt)
+    invs, engs, lds = [], [], []
+    for o in (orc, orc_ref):
+        inv, ld = o.invert_transpose(a)
+        invs.append(inv)
+        lds.append(ld)
+        engs.append(o.du(n, k, dt))
+    tol = 1e-12 if dt == np.complex128 else 1e-4
+    assert np.abs(invs[0] - invs[1]).max() < tol
+    assert abs(lds[0] - lds[1]) < 1e-10
+    # (A^-1)^T A^T = 1 for the complex inverse
+    assert np.abs(invs[0].T.astype(np.complex128) @ a.astype(np.complex128) - np.eye(n)).max() < (1e-12 if dt == np.complex128 else 1e-4)
+    for move in range(2 * k + 3):
+        row = (3 * move) % n
+        v = (2 * np.eye(n)[row] + 0.1 * (rng.normal(size=n) + 1j * rng.normal(size=n))).astype(dt)
+        rows = [e.get_inv_row(inv, row) for e, inv in zip(engs, invs)]
+        assert np.abs(rows[0] - rows[1]).max() < tol * 10
+        ratio = (rows[0].astype(np.complex128) @ v.astype(np.complex128)).item()
+        for e, inv in zip(engs, invs):
+            e.accept_row(inv, row, v, ratio)
+        a[row] = v
+    for e, inv in zip(engs, invs):
+        e.update_inv_mat(inv)
+    assert np.abs(invs[0] - invs[1]).max() < tol * 100
+    fresh, _ = orc.invert_transpose(a)
+    assert np.abs(invs[0] - fresh).max() < (1e-9 if dt == np.complex128 else 5e-3)
+
+
+def test_complex_vmc_port_matches_reference(orc, orc_ref):
+    """the oracle's complex-orbital VMC sweep on the reference's compiled DelayedUpdate<complex<double>>, DiracMatrix and
+    spline VGH kernels: identical acceptance sequence, G/L to rounding"""
+    if orc_ref is None:
+        pytest.skip("oracle/_ref not built")
+    import oracle_lib
+    from qmcpack_b200.workload import make_system, initial_positions
+    s = make_system(N=24, M=8, dtype=np.float64, L=6.0, complex_orbitals=True)
+    R = initial_positions(s, 4)
+    out = []
+    for o in (orc, orc_ref):
+        v = oracle_lib.OracleVMC(o, s, nw=4, ncrowds=2, seeds=[3, 4], tau=0.1, delay_rank=4, batched_engine=False)
+        v.set_positions(R)
+        v.recompute()
+        log = v.sweep(3, log_accept=True)
+        out.append((log,) + v.evaluate_gl())
+    assert 0.2 < out[0][0].mean() < 0.98
+    assert np.array_equal(out[0][0], out[1][0])
+    for a, b in zip(out[0][1:], out[1][1:]):
+        assert np.abs(a - b).max() < 1e-9 * max(1.0, np.abs(b).max())
+    assert np.abs(out[0][3].imag).max() > 1e-3

@@ -270,3 +270,119 @@ def test_nio_a32_shape_mixed_precision_every_move(api, orc):
     lp2, ke2, _, _ = crowd.mw_evaluateGL()
     assert lp2 == pytest.approx(lp, rel=1e-5, abs=2e-2)
     assert ke2 == pytest.approx(ke, rel=5e-3)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# complex orbitals (SplineC2C tables, complex determinants): the NiO-a128 class of BASELINE.json at test size
+# ---------------------------------------------------------------------------------------------------------------------
+def complex_system(dt, lattice=None, N=24, M=8):
+    from qmcpack_b200.workload import make_system
+    return make_system(N=N, M=M, dtype=dt, L=6.0, lattice=lattice, complex_orbitals=True)
+
+
+@pytest.mark.parametrize("lattice", [None, LAT_GENERAL], ids=["ortho", "general"])
+@pytest.mark.parametrize("k", [1, 4])
+def test_complex_orbitals_host_driven_identical_acceptance_fp64(api, orc, lattice, k):
+    """complex determinants, FP64: prob = |ratio|^2 and the real part of the complex gradient drive the same decisions
+    as the oracle; complex G, L and the kinetic energy real(G.G + sum L) agree to rounding"""
+    s = complex_system(np.float64, lattice)
+    crowd, ov, log, olog = host_sweeps(api, orc, s, nw=6, k=k, nsteps=3, tau=0.1)
+    assert crowd.cplx and 0.2 < olog.mean() < 0.98
+    assert np.array_equal(log, olog)
+    assert crowd.positions() == pytest.approx(ov.positions(), rel=1e-9, abs=1e-9)
+    lp, ke, G, L = crowd.mw_evaluateGL()
+    olp, oke, oG, oL = ov.evaluate_gl()
+    assert np.iscomplexobj(G) and np.abs(G.imag).max() > 1e-3  # genuinely complex wavefunction
+    assert lp == pytest.approx(olp, rel=1e-8, abs=1e-8)
+    assert ke == pytest.approx(oke, rel=1e-6, abs=1e-6)
+    assert np.abs(G - oG).max() < 1e-6 * max(1.0, np.abs(oG).max())
+    assert np.abs(L - oL).max() < 1e-6 * max(1.0, np.abs(oL).max())
+    for spin in (0, 1):
+        inv, ld = crowd.det_mw_completeUpdates(spin)
+        for iw in range(2):
+            oinv, old = ov.psiminv(iw, spin)
+            assert np.abs(inv[iw] - oinv).max() < 1e-8 * max(1.0, np.abs(oinv).max())
+            assert ld[iw, 0] == pytest.approx(old, rel=1e-9, abs=1e-9)
+    crowd.mw_recompute()
+    lp2, ke2, _, _ = crowd.mw_evaluateGL()
+    assert lp2 == pytest.approx(lp, rel=1e-9, abs=1e-9)
+    assert ke2 == pytest.approx(ke, rel=1e-7, abs=1e-7)
+
+
+def test_complex_orbitals_device_driver_identical_acceptance_fp64(api, orc):
+    """device-resident sweep with complex determinants (with and without CUDA graph replay) against the oracle"""
+    from qmcpack_b200.workload import initial_positions
+    import oracle_lib
+    s = complex_system(np.float64)
+    nw, k, nsteps, tau, seed = 7, 4, 3, 0.1, 4243
+    R = initial_positions(s, nw)
+    ov = oracle_lib.OracleVMC(orc, s, nw=nw, ncrowds=1, seeds=[seed], tau=tau, delay_rank=k)
+    ov.set_positions(R)
+    ov.recompute()
+    olog = ov.sweep(nsteps, log_accept=True)
+    for graph in (False, True):
+        crowd = api.Crowd(s, nw=nw, delay_rank=k)
+        crowd.set_positions(R)
+        crowd.mw_recompute()
+        crowd.vmc_init(tau=tau, use_drift=True, seed=seed, use_cuda_graph=graph)
+        log = crowd.vmc_sweep(nsteps, log_accept=True)
+        assert np.array_equal(log, olog), f"graph={graph}: {np.argwhere(log != olog)[:5]}"
+        assert crowd.positions() == pytest.approx(ov.positions(), rel=1e-9, abs=1e-9)
+
+
+def test_complex_orbitals_compiled_host_driver(api, orc):
+    """the C++ host driver above the C ABI with complex ratios / gradients (interleaved doubles), two crowds"""
+    from qmcpack_b200.workload import initial_positions
+    import oracle_lib
+    s = complex_system(np.float64)
+    nw, k, nsteps, tau, ncrowds = 6, 4, 2, 0.1, 2
+    seeds = [21, 26]
+    R = initial_positions(s, nw)
+    ov = oracle_lib.OracleVMC(orc, s, nw=nw, ncrowds=ncrowds, seeds=seeds, tau=tau, delay_rank=k)
+    ov.set_positions(R)
+    ov.recompute()
+    olog = ov.sweep(nsteps, log_accept=True)
+    crowds, spo = [], None
+    for c in range(ncrowds):
+        cr = api.Crowd(s, nw=3, delay_rank=k, spo=spo)
+        spo = cr.spo
+        cr.set_positions(R[3 * c:3 * c + 3])
+        cr.mw_recompute()
+        crowds.append(cr)
+    drv = api.HostVMC(crowds, seeds, tau=tau, use_drift=True)
+    log = drv.run(nsteps, log_accept=True)
+    assert np.array_equal(log, olog)
+    got = np.concatenate([c.positions() for c in crowds])
+    assert got == pytest.approx(ov.positions(), rel=1e-9, abs=1e-9)
+
+
+def test_complex_orbitals_mixed_precision_every_move(api, orc):
+    """complex<float> determinants on float tables: the oracle is teacher-forced with the product's decisions and every
+    move's complex ratio is compared; then delayed updates against a from-scratch recompute"""
+    from qmcpack_b200.workload import initial_positions
+    from qmcpack_b200 import vmc_host
+    import oracle_lib
+    N, nw, k, tau, seed = 48, 6, 8, 0.2, 91
+    s = complex_system(np.float32, N=N, M=10)
+    R = initial_positions(s, nw)
+    crowd = api.Crowd(s, nw=nw, delay_rank=k)
+    crowd.set_positions(R)
+    crowd.mw_recompute()
+    rng = orc.rng(seed)
+    log = np.zeros((2, N, nw), np.uint8)
+    ratios = np.zeros((2, N, nw), np.complex128)
+    for step in range(2):
+        vmc_host.advance_walkers(crowd, rng, tau=tau, log_accept=log[step], log_ratio=ratios[step])
+    ov = oracle_lib.OracleVMC(orc, s, nw=nw, ncrowds=1, seeds=[seed], tau=tau, delay_rank=k)
+    ov.set_positions(R)
+    ov.recompute()
+    oratios = ov.sweep_forced(log)
+    rel = np.abs(ratios - oratios) / np.maximum(np.abs(oratios), 0.1)
+    assert np.median(rel) < 1e-4 and rel.max() < 5e-2, (np.median(rel), rel.max())
+    lp, ke, _, _ = crowd.mw_evaluateGL()
+    olp, oke, _, _ = ov.evaluate_gl()
+    assert lp == pytest.approx(olp, rel=1e-4, abs=2e-2)
+    assert ke == pytest.approx(oke, rel=2e-2)
+    crowd.mw_recompute()
+    lp2, _, _, _ = crowd.mw_evaluateGL()
+    assert lp2 == pytest.approx(lp, rel=2e-4, abs=5e-3)
