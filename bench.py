@@ -61,9 +61,10 @@ def workload_desc(cfg, args):
     from qmcpack_b200 import workload
     c = workload.CONFIGS[cfg]
     n = c["N"] // 2
-    npad = workload.aligned_size(c["dtype"], n)
+    cplx = bool(c.get("complex_orbitals"))
+    npad = workload.aligned_size(c["dtype"], n * (2 if cplx else 1))
     tab_mb = (c["M"] + 3) ** 3 * npad * np.dtype(c["dtype"]).itemsize / 1e6
-    return (f"{cfg} synthetic: {c['N']} electrons, {n} orbitals/spin, {c['M']}^3 spline grid "
+    return (f"{cfg} synthetic: {c['N']} electrons, {n} {'complex (SplineC2C) ' if cplx else ''}orbitals/spin, {c['M']}^3 spline grid "
             f"({tab_mb:.0f} MB/spin, {np.dtype(c['dtype']).name}), J1+J2 B-spline Jastrows, batched VMC with drift "
             f"(tau={args.tau}), delay_rank {c['k']}, {args.walkers} walkers/GPU")
 
@@ -162,7 +163,7 @@ def cpu_reference_run(cfg, args, steps, warmup, nw_cpu=None):
     nw = nw_cpu or args.cpu_walkers or 8 * cores
     ncrowds = min(cores, nw)
     orc.lib.orc_set_threads(ncrowds)  # torchrun exports OMP_NUM_THREADS=1: the CPU arm must use every host core
-    s = workload.make_system(N=c["N"], M=c["M"], dtype=c["dtype"])
+    s = workload.make_system(N=c["N"], M=c["M"], dtype=c["dtype"], complex_orbitals=bool(c.get("complex_orbitals")))
     v = orc.vmc(s, nw=nw, ncrowds=ncrowds, seeds=[1000 + i for i in range(ncrowds)], tau=args.tau, use_drift=True,
                 delay_rank=c["k"], batched_engine=False)
     v.set_positions(workload.initial_positions(s, nw))
@@ -185,7 +186,7 @@ def run_reference(args, rank, world):
         return
     res = cpu_reference_run(args.config, args, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
-        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC.replace("NiO-a64", args.config), "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_desc(args.config, args), "cpu_sample": res["sample"]},
@@ -210,13 +211,19 @@ def run_b200(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     c = workload.CONFIGS[args.config]
     N, k, nw = c["N"], c["k"], args.walkers
-    s = workload.make_system(N=N, M=c["M"], dtype=c["dtype"])
+    cplx = bool(c.get("complex_orbitals"))
+    s = workload.make_system(N=N, M=c["M"], dtype=c["dtype"], complex_orbitals=cplx)
     lat = np.asarray(s["lattice"])
     G = np.linalg.inv(lat)
     n = N // 2
-    up = api.SplineSPOSet(s["coefs"][0], n, G)
-    dn = api.SplineSPOSet(s["coefs"][1], n, G)
+    if cplx:
+        up = api.SplineSPOSet(s["coefs"][0], n, G, kind=api.C2C, kcart=s["kpts"][0])
+        dn = api.SplineSPOSet(s["coefs"][1], n, G, kind=api.C2C, kcart=s["kpts"][1])
+    else:
+        up = api.SplineSPOSet(s["coefs"][0], n, G)
+        dn = api.SplineSPOSet(s["coefs"][1], n, G)
     spo = (up, dn)
+    nc = 2 if cplx else 1  # real components per orbital value
     R = workload.initial_positions(s, nw, seed=7 + 100003 * rank)  # every rank owns its own walkers (weak scaling)
 
     # ---------------- device-resident sweep (value)
@@ -232,6 +239,7 @@ def run_b200(args, rank, local_rank, world):
         streams.append(torch.cuda.ExternalStream(cr.stream, device=torch.device("cuda", local_rank)))
         off += dsizes[i]
     crowd = dcrowds[0]
+    state_bytes = sum(cr.device_bytes for cr in dcrowds)
 
     def counts():
         a = np.concatenate([cr.vmc_counts()[0] for cr in dcrowds])
@@ -286,9 +294,9 @@ def run_b200(args, rank, local_rank, world):
     gen = torch.Generator(device="cuda").manual_seed(5 + rank)
     pos = (torch.rand((nsets, nw, 3), generator=gen, device="cuda", dtype=torch.float64) @
            torch.tensor(lat, device="cuda")).to(tdt).contiguous()
-    inv = torch.randn((nw, n), generator=gen, device="cuda", dtype=tdt).contiguous()
-    phi = torch.empty((5, nw, n), device="cuda", dtype=tdt)
-    rg = torch.empty((nw, up.rg_parts, 4), device="cuda", dtype=tdt)
+    inv = torch.randn((nw, n * nc), generator=gen, device="cuda", dtype=tdt).contiguous()
+    phi = torch.empty((5, nw, n * nc), device="cuda", dtype=tdt)
+    rg = torch.empty((nw, up.rg_parts, 4 * nc), device="cuda", dtype=tdt)
     ts = torch.cuda.Stream()
     lib = api.lib()
 
@@ -308,9 +316,9 @@ def run_b200(args, rank, local_rank, world):
     s1.record(ts)
     ts.synchronize()
     t_spl = s0.elapsed_time(s1) * 1e-3 / nrep
-    npad = workload.aligned_size(T, n)
+    npad = workload.aligned_size(T, n * nc)
     esz = np.dtype(T).itemsize
-    b_spl = 64 * npad * esz + 5 * n * esz + n * esz  # stencil + phi_vgl write + inverse-row read
+    b_spl = 64 * npad * esz + 5 * n * esz * nc + n * esz * nc  # stencil + phi_vgl write + inverse-row read
     achieved = b_spl * nw / t_spl / 1e9
     pk = peaks()
     peak = pk["hbm_gbs"] if pk else 6650.0
@@ -362,13 +370,13 @@ def run_b200(args, rank, local_rank, world):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC.replace("NiO-a64", args.config), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if T == np.float32 else "f64", "data": "synthetic",
             "config": {"workload": workload_desc(args.config, args), "walkers_per_gpu": nw, "device_crowds": ndc, "electrons": N,
                        "delay_rank": k, "table": "random orthogonal mixtures of the lowest plane waves (workload.pw_table)",
-                       "l2": "inputs larger than L2: 2 x 384 MB spline tables + %.1f GB walker state vs 126 MB L2"
-                             % (3.1 * nw / 512),
+                       "l2": "inputs larger than L2: 2 x %.0f MB spline tables + %.1f GB walker state vs 126 MB L2"
+                             % (up.table_bytes / 1e6, state_bytes / 1e9),
                        "parallelism": f"walkers sharded over {world} GPU(s), no data-path collective; one all-reduce per block",
                        "acceptance": acc_rate, "ke_mean_hartree": ke_mean, "finite": sane},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,

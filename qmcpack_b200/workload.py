@@ -24,7 +24,7 @@ L_A64 = 15.7622  # cubic cell edge (bohr) of the a64 input
 CONFIGS = {
     "NiO-a32": dict(N=384, M=48, k=32, dtype=np.float32),
     "NiO-a64": dict(N=768, M=60, k=32, dtype=np.float32),
-    "NiO-a128": dict(N=1536, M=76, k=64, dtype=np.float64),
+    "NiO-a128": dict(N=1536, M=76, k=64, dtype=np.float64, complex_orbitals=True),  # full precision, SplineC2C
     "NiO-a256": dict(N=3072, M=96, k=32, dtype=np.float32),
 }
 
