@@ -10,6 +10,11 @@
 namespace qmcb
 {
 extern std::atomic<unsigned long long> g_launch_count;
+// programmatic dependent launch between the kernels of a sweep (env QMCB_PDL): 0 = off, 1 = boundary -> spline gather,
+// 2 = also spline gather -> boundary; +4 = the primary also signals at its START that dependents may become resident
+// (otherwise they follow its CTAs out as those exit).  The dependent kernel's CTAs run their prologue while the previous
+// kernel drains; every global access of a dependent sits behind pdl_wait().
+extern int g_pdl_mode;
 
 struct CudaError : std::runtime_error
 {
@@ -219,6 +224,30 @@ QMCB_HD double norm2(double v) { return v * v; }
 QMCB_HD double norm2(const cx<double>& v) { return v.re * v.re + v.im * v.im; }
 
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// kernel launch with (optionally) the programmatic-stream-serialization attribute
+template<typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                          Args&&... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim            = grid;
+  cfg.blockDim           = block;
+  cfg.dynamicSmemBytes   = smem;
+  cfg.stream             = st;
+  cudaLaunchAttribute attr[1];
+  if (pdl)
+  {
+    attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs                                          = attr;
+    cfg.numAttrs                                       = 1;
+  }
+  QMCB_CUDA(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+}
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll

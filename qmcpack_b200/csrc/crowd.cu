@@ -281,6 +281,9 @@ __global__ void __launch_bounds__(MB_TPB, (sizeof(V) > 8 ? 2 : 4))
   const int cB = part2 ? (same_det ? c_prev : c_next) : 0;    // rows of U that are final before this kernel
   const DetDev<V>& Dm = part1 ? Dacc : Dprep;                 // determinant whose Binv is staged
   const int cM        = part1 ? c_prev : c_next;              // its pending count before this kernel
+  if (Dr.pdl_early)
+    pdl_launch_dependents();
+  pdl_wait(); // (no-op unless launched as a programmatic dependent of the spline gather)
 
   if (warp == 7)
   {
@@ -822,6 +825,7 @@ struct Crowd : CrowdBase
     }
     std::memset(&drv_host, 0, sizeof(drv_host));
     drv_host.nw = nw, drv_host.N = N, drv_host.use_drift = 1, drv_host.accepted = accepted.p;
+    drv_host.pdl_early = (g_pdl_mode & 4) ? 1 : 0;
     std::memset(&rng, 0, sizeof(rng));
     QMCB_CUDA(cudaDeviceSynchronize());
   }
@@ -1412,6 +1416,7 @@ struct Crowd : CrowdBase
     drv.oneover2tau = (T)(0.5 / drv.tauovermass);
     drv.sqrttau     = (T)std::sqrt(drv.tauovermass);
     drv.use_drift   = p->use_drift;
+    drv.pdl_early   = (g_pdl_mode & 4) ? 1 : 0;
     use_graph       = p->use_cuda_graph != 0;
     A(deltas, (size_t)N * nw * 3);
     A(drifts, (size_t)nw * 3);
@@ -1472,8 +1477,9 @@ struct Crowd : CrowdBase
       QMCB_CUDA(cudaFuncSetAttribute(move_boundary_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       mb_attr_set = true;
     }
-    move_boundary_kernel<T, V><<<nw, MB_TPB, smem, st>>>(dr, jas, rng, det[igp], iat_prev, rp, cp, rg.p, rg_nparts, phi_vgl.p,
-                                                      det[ign], iat_next, rn, cn, det_grads.p, ext_flags, twf_grads_out);
+    launch_kernel(move_boundary_kernel<T, V>, dim3(nw), dim3(MB_TPB), smem, st, (g_pdl_mode & 3) >= 2, dr, jas, rng, det[igp],
+                  iat_prev, rp, cp, rg.p, rg_nparts, phi_vgl.p, det[ign], iat_next, rn, cn, det_grads.p, ext_flags,
+                  twf_grads_out);
     QMCB_LAUNCH_CHECK();
     if (iat_prev >= 0)
     {

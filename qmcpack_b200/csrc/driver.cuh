@@ -31,6 +31,7 @@ struct DriverDev
   int nw, N;
   RT tauovermass, oneover2tau, sqrttau;
   int use_drift;
+  int pdl_early;   // signal programmatic dependents at kernel start
   RT* deltas;      // [N][nw][3] Gaussians of the current sweep (walker_deltas, VMCBatched.cpp:109,122)
   RT* drifts;      // [nw][3]   displacement actually proposed (drift + delta)
   RT* delta_cur;   // [nw][3]

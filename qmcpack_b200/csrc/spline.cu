@@ -1,11 +1,18 @@
 // qmcpack_b200/csrc/spline.cu -- host side of the spline SPOSet: table upload, launch configuration.
 #include "internal.h"
+#include <cstdlib>
 #include "spline.cuh"
 #include <cstring>
 
 namespace qmcb
 {
 std::atomic<unsigned long long> g_launch_count{0};
+static int pdl_mode_from_env()
+{
+  const char* e = std::getenv("QMCB_PDL");
+  return e ? std::atoi(e) : 2;
+}
+int g_pdl_mode = pdl_mode_from_env();
 
 namespace
 {
@@ -197,6 +204,7 @@ struct SplineSPO : SplineSPOBase
     A.phi_vgl    = static_cast<ST*>(phi_dev);
     A.rg_partial = static_cast<ST*>(rg_dev);
     A.nparts     = ntiles * (TILE / VEC / 32);
+    A.pdl_early  = (g_pdl_mode & 4) ? 1 : 0;
     auto kern            = spline_gather_kernel<ST, ST, TILE, STAGES, VEC, MODE, C2C, MINB>;
     constexpr size_t smem = SplineSmem<ST, TILE, STAGES, VEC>::BYTES;
     static bool attr_set = false;
@@ -209,7 +217,7 @@ struct SplineSPO : SplineSPOBase
     if (nunits == 0)
       return;
     const int grid_x = std::min(nunits, MINB * sm_count());
-    kern<<<grid_x, TILE / VEC + 32, smem, st>>>(tmap, dev, A, ntiles);
+    launch_kernel(kern, dim3(grid_x), dim3(TILE / VEC + 32), smem, st, (g_pdl_mode & 3) >= 1, tmap, dev, A, ntiles);
     QMCB_LAUNCH_CHECK();
   }
 

@@ -57,6 +57,7 @@ struct SplineArgs
 {
   int nw;              // number of positions
   const RT* r;         // [nw][3] Cartesian
+  int pdl_early;       // signal programmatic dependents at kernel start
   const ST* invrow;    // [n_rows][ld_inv] (VT == ST; complex interleaved for C2C) or nullptr
   const int* ref;      // optional [nw] row index into invrow (virtual-particle ratios); nullptr -> iw
   long long ld_inv;    // in VT elements
@@ -249,6 +250,11 @@ __global__ void __launch_bounds__(TILE / VEC + 32, MINB)
     ptx::fence_barrier_init();
   }
   __syncthreads();
+  // programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream; the
+  // positions and inverse rows it produced are read only from here on
+  if (A.pdl_early)
+    pdl_launch_dependents();
+  pdl_wait();
 
   if (producer)
   {
