@@ -7,8 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libqmcb.so")
 SOURCES = ["spline.cu", "crowd.cu", "api.cu", "vmc_host.cpp"]
-HEADERS = ["common.cuh", "spline.cuh", "det.cuh", "jastrow.cuh", "driver.cuh", "internal.h",
-           os.path.join("..", "..", "include", "qmcb.h"), os.path.join("..", "..", "include", "qmcb_driver.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))) + [
+    os.path.join("..", "..", "include", "qmcb.h"), os.path.join("..", "..", "include", "qmcb_driver.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-ccbin", "/usr/bin/g++"]

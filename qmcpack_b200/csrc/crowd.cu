@@ -6,6 +6,8 @@
 #include "jastrow.cuh"
 #include "driver.cuh"
 #include "woodbury.cuh"
+#include "woodbury_tc5.cuh"
+#include <cstdlib>
 #include <type_traits>
 #include <cublas_v2.h>
 #include <cmath>
@@ -955,6 +957,29 @@ struct Crowd : CrowdBase
     const int n        = D.n;
     if constexpr (std::is_same<V, float>::value)
     {
+      // tcgen05 / TMEM flush (woodbury_tc5.cuh); QMCB_FLUSH=mma or simt selects the older paths
+      static const int flush_mode = [] {
+        const char* e = std::getenv("QMCB_FLUSH");
+        return !e ? 0 : (std::string(e) == "tc5" ? 0 : (std::string(e) == "mma" ? 1 : 2));
+      }();
+      if (flush_mode == 0 && wb5::eligible(n, D.k, c))
+      {
+        static bool attr5_set = false;
+        const size_t smem5    = wb5::smem_bytes(n);
+        if (!attr5_set)
+        {
+          QMCB_CUDA(cudaFuncSetAttribute(wb5::woodbury_flush_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(200 * 1024)));
+          attr5_set = true;
+        }
+        wb5::woodbury_flush_tc5_kernel<<<dim3(nw, (n + wb5::TM - 1) / wb5::TM), wb5::TPB, smem5, st>>>(D, c);
+        QMCB_LAUNCH_CHECK();
+        delay_count[spin] = 0;
+        invrow_id[spin]   = -1;
+        return;
+      }
+      if (flush_mode <= 1)
+      {
       // one-pass tensor-core flush (woodbury.cuh) whenever U, U' and a 64-row tile of Ainv fit in shared memory
       const size_t smem = wb::smem_bytes_f32(n);
       if (c <= wb::KD && n % 4 == 0 && smem <= 227 * 1024)
@@ -973,6 +998,7 @@ struct Crowd : CrowdBase
         delay_count[spin] = 0;
         invrow_id[spin]   = -1;
         return;
+      }
       }
     }
     // tempMat[n x c] = Ainv[n x n] * U^T, with the -1 fix-up (applyW) fused
