@@ -28,12 +28,13 @@ constexpr int KC  = 32;  // K chunk = one 128-byte swizzle row of floats
 constexpr int KD  = 32;  // delay slots handled (c <= KD)
 constexpr int TPB = 256;
 
-// dynamic shared memory: B operands (U, later U'^T) hi+lo, two A stages (hi+lo each); +1024 for manual alignment
-inline size_t smem_bytes(int n) { return (size_t)2 * n * KC * 4 + (size_t)2 * 2 * TM * KC * 4 + 1024; }
+// dynamic shared memory: two stages of {A_hi, A_lo [128][32], U_hi, U_lo [32][32]}; +1024 for manual alignment
+constexpr int STAGE_FLOATS = 2 * TM * KC + 2 * KD * KC;
+inline size_t smem_bytes(int) { return (size_t)2 * STAGE_FLOATS * 4 + 1024; }
 // n must be a multiple of 32 (K chunks) and the accumulators must fit the 512 TMEM columns
 // n: multiple of 64 (K chunks of 32; each half of the second product's N in 32-column epilogue pieces); the accumulators
 // (32 + n columns) must fit the 512 TMEM columns
-inline bool eligible(int n, int k, int c) { return n % 64 == 0 && n >= 64 && KD + n <= 512 && k <= KD && c <= KD; }
+inline bool eligible(int n, int k, int c) { return n % 64 == 0 && n >= 64 && k <= KD && c <= KD; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
@@ -115,8 +116,10 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo)
   lo   = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
 }
 
-// grid = (nw, ceil(n / 128)); c <= 32 pending delays; n % 32 == 0
-__global__ void __launch_bounds__(TPB, 1) woodbury_flush_tc5_kernel(const DetDev<float> D, const int c)
+// grid = (nw, ceil(n / 128)); c <= 32 pending delays; n % 64 == 0.  Two CTAs per SM (85 KB of shared memory, 256 of the
+// 512 TMEM columns and <= 128 registers each): the phases of one CTA are chains of memory latencies, the second CTA on
+// the SM fills them.
+__global__ void __launch_bounds__(TPB, 2) woodbury_flush_tc5_kernel(const DetDev<float> D, const int c)
 {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(16) float BinvT[KD][KD + 4]; // BinvT[b][a] = Binv[a][b] (float4 reads over a)
@@ -129,22 +132,57 @@ __global__ void __launch_bounds__(TPB, 1) woodbury_flush_tc5_kernel(const DetDev
   const int iw = blockIdx.x, m0 = blockIdx.y * TM;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nchunks = n / KC;
-  // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 bytes)
+  // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 bytes).  One stage = A_hi, A_lo [128][32] + U_hi, U_lo [32][32]
   unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  float* Bhi = reinterpret_cast<float*>(base);           // [nchunks][32 rows][32]  (U)   later [n rows][32] (U'^T)
-  float* Blo = Bhi + (size_t)n * KC;
-  float* Ast = Blo + (size_t)n * KC;                     // [stage][hi/lo][128 rows][32]
-  auto Aptr = [&](int stage, int part) { return Ast + ((size_t)stage * 2 + part) * TM * KC; };
+  float* S0 = reinterpret_cast<float*>(base);
+  auto Aptr = [&](int stage, int part) { return S0 + (size_t)stage * STAGE_FLOATS + (size_t)part * TM * KC; };
+  auto Uptr = [&](int stage, int part) { return S0 + (size_t)stage * STAGE_FLOATS + (size_t)2 * TM * KC + (size_t)part * KD * KC; };
 
   const float* U = D.U + (size_t)iw * k * n;
   const float* V = D.V + (size_t)iw * k * n;
   const float* B = D.Binv + (size_t)iw * k * k;
   float* Ainv    = D.Ainv + (size_t)iw * n * lda;
 
-  // ---- set-up: TMEM allocation (512 columns, one CTA per SM by shared-memory footprint), barriers
+  // ---- operand loaders.  A chunk [128 x 32]: thread -> rows tid/8 + 32 i (i < 4), 16-byte piece tid % 8 of the 128-byte
+  //      row; U chunk [32 x 32]: thread -> row tid/8, piece tid % 8.  Two chunks stay in flight in registers.
+  const int ar = tid >> 3, akq = tid & 7;
+  float4 areg[2][4], ureg[2];
+  auto load_chunk = [&](int kc, float4 (&dst)[4], float4& du) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+      const int row = m0 + ar + 32 * i;
+      dst[i] = row < n ? *reinterpret_cast<const float4*>(Ainv + (size_t)row * lda + kc * KC + akq * 4)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    du = ar < c ? __ldg(reinterpret_cast<const float4*>(U + (size_t)ar * n + kc * KC + akq * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto store_chunk = [&](int stage, const float4 (&src)[4], const float4& su) {
+    float* hi_t = Aptr(stage, 0);
+    float* lo_t = Aptr(stage, 1);
+    float4 hi, lo;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+      const int r = ar + 32 * i;
+      split4(src[i], hi, lo);
+      const int off = r * KC + ((akq ^ (r & 7)) << 2);
+      *reinterpret_cast<float4*>(hi_t + off) = hi;
+      *reinterpret_cast<float4*>(lo_t + off) = lo;
+    }
+    split4(su, hi, lo);
+    const int off = ar * KC + ((akq ^ (ar & 7)) << 2);
+    *reinterpret_cast<float4*>(Uptr(stage, 0) + off) = hi;
+    *reinterpret_cast<float4*>(Uptr(stage, 1) + off) = lo;
+  };
+  load_chunk(0, areg[0], ureg[0]);
+  if (nchunks > 1)
+    load_chunk(1, areg[1], ureg[1]);
+
+  // ---- set-up: TMEM allocation (256 columns: D1 in [0,32), one 128-column piece of D2 in [32,160)), barriers
   if (warp == 0)
   {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 32)
@@ -158,75 +196,10 @@ __global__ void __launch_bounds__(TPB, 1) woodbury_flush_tc5_kernel(const DetDev
   for (int e = tid; e < KD * KD; e += TPB)
   {
     const int a = e / KD, b = e - a * KD;
-    BinvT[b][a] = (a < c && b < c) ? B[a * k + b] : 0.f;
+    BinvT[b][a] = (a < c && b < c) ? __ldg(B + a * k + b) : 0.f;
   }
   if (tid < KD)
     lst[tid] = tid < c ? D.list[(size_t)iw * k + tid] : -1;
-
-  // ---- A chunk loader: thread handles rows r = tid/8 + 32*i (i < 4), 16-byte piece kq = tid % 8 of the 128-byte row
-  //      two chunks (32 KB per CTA) are kept in flight in registers: the loop below is bound by HBM latency, not by the MMAs
-  const int ar = tid >> 3, akq = tid & 7;
-  float4 areg[2][4];
-  auto load_chunk = [&](int kc, float4 (&dst)[4]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-    {
-      const int row = m0 + ar + 32 * i;
-      dst[i] = row < n ? __ldcs(reinterpret_cast<const float4*>(Ainv + (size_t)row * lda + kc * KC + akq * 4))
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  auto store_chunk = [&](int stage, const float4 (&src)[4]) {
-    float* hi_t = Aptr(stage, 0);
-    float* lo_t = Aptr(stage, 1);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-    {
-      const int r = ar + 32 * i;
-      float4 hi, lo;
-      split4(src[i], hi, lo);
-      const int off = r * KC + ((akq ^ (r & 7)) << 2);
-      *reinterpret_cast<float4*>(hi_t + off) = hi;
-      *reinterpret_cast<float4*>(lo_t + off) = lo;
-    }
-  };
-  load_chunk(0, areg[0]);
-  if (nchunks > 1)
-    load_chunk(1, areg[1]);
-
-  // ---- U -> B operand: chunk j holds U[0..31][32 j .. 32 j + 31] as a 32-row tile; rows >= c are zero
-  //      (loads batched four deep: a store to shared memory may not overtake a global load the compiler cannot prove
-  //      independent, so an unbatched loop pays one memory latency per element)
-  {
-    const int total = KD * (n / 4);
-    for (int e0 = tid; e0 < total; e0 += 4 * TPB)
-    {
-      float4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-      {
-        const int e = e0 + u * TPB;
-        const int a = e / (n / 4), j4 = e - a * (n / 4);
-        v[u] = (e < total && a < c) ? __ldg(reinterpret_cast<const float4*>(U + (size_t)a * n + j4 * 4))
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-      {
-        const int e = e0 + u * TPB;
-        if (e < total)
-        {
-          const int a = e / (n / 4), j4 = e - a * (n / 4);
-          float4 hi, lo;
-          split4(v[u], hi, lo);
-          const int chunk = j4 >> 3, kq = j4 & 7;
-          const int off   = chunk * (KD * KC) + a * KC + ((kq ^ (a & 7)) << 2);
-          *reinterpret_cast<float4*>(Bhi + off) = hi;
-          *reinterpret_cast<float4*>(Blo + off) = lo;
-        }
-      }
-    }
-  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -242,15 +215,15 @@ __global__ void __launch_bounds__(TPB, 1) woodbury_flush_tc5_kernel(const DetDev
       mbar_wait(&bar_stage[stage], (unsigned)(((kc >> 1) - 1) & 1)); // the MMAs that read this stage have retired
     if (stage == 0)
     {
-      store_chunk(0, areg[0]);
+      store_chunk(0, areg[0], ureg[0]);
       if (kc + 2 < nchunks)
-        load_chunk(kc + 2, areg[0]);
+        load_chunk(kc + 2, areg[0], ureg[0]);
     }
     else
     {
-      store_chunk(1, areg[1]);
+      store_chunk(1, areg[1], ureg[1]);
       if (kc + 2 < nchunks)
-        load_chunk(kc + 2, areg[1]);
+        load_chunk(kc + 2, areg[1], ureg[1]);
     }
     fence_async_smem();
     __syncthreads();
@@ -258,7 +231,7 @@ __global__ void __launch_bounds__(TPB, 1) woodbury_flush_tc5_kernel(const DetDev
     {
       fence_after_sync();
       const uint64_t a_hi = make_desc(Aptr(stage, 0)), a_lo = make_desc(Aptr(stage, 1));
-      const uint64_t b_hi = make_desc(Bhi + (size_t)kc * KD * KC), b_lo = make_desc(Blo + (size_t)kc * KD * KC);
+      const uint64_t b_hi = make_desc(Uptr(stage, 0)), b_lo = make_desc(Uptr(stage, 1));
 #pragma unroll
       for (int ks = 0; ks < KC / 8; ++ks)
       {
@@ -272,11 +245,13 @@ __global__ void __launch_bounds__(TPB, 1) woodbury_flush_tc5_kernel(const DetDev
         mma_commit(&bar_done);
     }
   }
-  mbar_wait(&bar_done, 0u);
+  unsigned done_parity = 0;
+  mbar_wait(&bar_done, done_parity);
+  done_parity ^= 1u;
   fence_after_sync();
 
   // ---- T epilogue (warps 0-3: one TMEM lane = one row each): -T with the list fix-up, split, stored as the A operand
-  //      of the second product in stage 0.  Meanwhile warps 4-7 start on U'.
+  //      of the second product over stage 0's A tiles
   if (warp < 4)
   {
     float t[32];
@@ -299,101 +274,112 @@ __global__ void __launch_bounds__(TPB, 1) woodbury_flush_tc5_kernel(const DetDev
       *reinterpret_cast<float4*>(lo_t + off) = lo;
     }
   }
-  // ---- U'^T -> B operand (the U chunks are dead: every MMA of the first product has retired): row j = column j of U'
-  for (int j = tid; j < n; j += TPB)
+
+  // ---- GEMM 2 in pieces of 128 columns: D2 = (-T)[128 x 32] * U'[32 x piece]; the U'^T piece (B operand, hi + lo) and
+  //      later the epilogue's transpose patches live in stage 1
+  float* Bp_hi = Aptr(1, 0);
+  float* Bp_lo = Aptr(1, 1);
+  float* patch = Aptr(1, 0) + (size_t)warp * 16 * 33; // 8 x 2.1 KB
+  for (int j0 = 0; j0 < n; j0 += 128)
   {
-    float acc[KD];
-#pragma unroll
-    for (int a = 0; a < KD; ++a)
-      acc[a] = 0.f;
-    float vv[KD]; // the whole column of V in flight at once
-#pragma unroll
-    for (int b = 0; b < KD; ++b)
-      vv[b] = b < c ? __ldg(V + (size_t)b * n + j) : 0.f;
-#pragma unroll
-    for (int b = 0; b < KD; ++b)
+    const int np = (n - j0) < 128 ? (n - j0) : 128; // columns in this piece (multiple of 64)
+    // U'[a][j] = sum_b Binv[a][b] V[b][j]: thread -> column jj = tid % 128, slots 16 (tid / 128) .. +15
     {
-      const float v = vv[b];
-#pragma unroll
-      for (int q = 0; q < KD / 4; ++q)
+      const int jj = tid & 127, a0 = (tid >> 7) * 16;
+      if (jj < np)
       {
-        const float4 bb = *reinterpret_cast<const float4*>(&BinvT[b][4 * q]);
-        acc[4 * q] += bb.x * v;
-        acc[4 * q + 1] += bb.y * v;
-        acc[4 * q + 2] += bb.z * v;
-        acc[4 * q + 3] += bb.w * v;
+        float vv[KD]; // the whole column of V in flight at once
+#pragma unroll
+        for (int b = 0; b < KD; ++b)
+          vv[b] = b < c ? __ldg(V + (size_t)b * n + j0 + jj) : 0.f;
+        float acc[16];
+#pragma unroll
+        for (int a = 0; a < 16; ++a)
+          acc[a] = 0.f;
+#pragma unroll
+        for (int b = 0; b < KD; ++b)
+        {
+          const float v = vv[b];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+          {
+            const float4 bb = *reinterpret_cast<const float4*>(&BinvT[b][a0 + 4 * q]);
+            acc[4 * q] += bb.x * v;
+            acc[4 * q + 1] += bb.y * v;
+            acc[4 * q + 2] += bb.z * v;
+            acc[4 * q + 3] += bb.w * v;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+          float4 hi, lo;
+          split4(make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]), hi, lo);
+          const int off = jj * KC + ((((a0 >> 2) + q) ^ (jj & 7)) << 2);
+          *reinterpret_cast<float4*>(Bp_hi + off) = hi;
+          *reinterpret_cast<float4*>(Bp_lo + off) = lo;
+        }
       }
     }
-#pragma unroll
-    for (int q = 0; q < KD / 4; ++q)
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0)
     {
-      float4 hi, lo;
-      split4(make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]), hi, lo);
-      const int off = j * KC + ((q ^ (j & 7)) << 2);
-      *reinterpret_cast<float4*>(Bhi + off) = hi;
-      *reinterpret_cast<float4*>(Blo + off) = lo;
-    }
-  }
-  fence_async_smem();
-  fence_before_sync();
-  __syncthreads();
-
-  // ---- GEMM 2: D2[128 x n] = (-T)[128 x 32] * U'[32 x n]; N split in two halves (N <= 256 per instruction)
-  if (tid == 0)
-  {
-    fence_after_sync();
-    const int nh          = n / 2;
-    const uint32_t idesc2 = make_idesc(TM, nh);
-    const uint64_t a_hi = make_desc(Aptr(0, 0)), a_lo = make_desc(Aptr(0, 1));
-    for (int h = 0; h < 2; ++h)
-    {
-      const uint64_t b_hi = make_desc(Bhi + (size_t)h * nh * KC), b_lo = make_desc(Blo + (size_t)h * nh * KC);
-      const uint32_t d    = tmemD2 + (uint32_t)(h * nh);
+      fence_after_sync();
+      const uint32_t idesc2 = make_idesc(TM, np);
+      const uint64_t a_hi = make_desc(Aptr(0, 0)), a_lo = make_desc(Aptr(0, 1));
+      const uint64_t b_hi = make_desc(Bp_hi), b_lo = make_desc(Bp_lo);
 #pragma unroll
       for (int ks = 0; ks < KC / 8; ++ks)
       {
         const uint64_t adv = (uint64_t)(ks * 2);
-        mma_tf32_ss(d, a_lo + adv, b_hi + adv, idesc2, ks != 0);
-        mma_tf32_ss(d, a_hi + adv, b_lo + adv, idesc2, 1u);
-        mma_tf32_ss(d, a_hi + adv, b_hi + adv, idesc2, 1u);
+        mma_tf32_ss(tmemD2, a_lo + adv, b_hi + adv, idesc2, ks != 0);
+        mma_tf32_ss(tmemD2, a_hi + adv, b_lo + adv, idesc2, 1u);
+        mma_tf32_ss(tmemD2, a_hi + adv, b_hi + adv, idesc2, 1u);
+      }
+      mma_commit(&bar_done);
+    }
+    mbar_wait(&bar_done, done_parity);
+    done_parity ^= 1u;
+    fence_after_sync();
+
+    // epilogue of the piece: Ainv tile += D2.  Warp w reads TMEM lanes 32 (w % 4) .. +31 (its quarter) and the 32-column
+    // slices w / 4, w / 4 + 2, ... of the piece, transposes 16 rows at a time through its padded patch (the U' piece is
+    // dead) and updates the rows (L2 hits: this CTA streamed them a moment ago) with coalesced 128-byte accesses
+    {
+      const int q = warp & 3;
+      for (int c0 = (warp >> 2) * 32; c0 < np; c0 += 64)
+      {
+        float v[32];
+        tmem_ld32(tmemD2 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow)
+        {
+          if ((lane >> 4) == hrow)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              patch[(lane & 15) * 33 + i] = v[i];
+          __syncwarp();
+          float gv[16];
+          float* g0 = Ainv + (size_t)(m0 + q * 32 + hrow * 16) * lda + j0 + c0 + lane;
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr)
+            gv[rr] = (m0 + q * 32 + hrow * 16 + rr < n) ? __ldcg(g0 + (size_t)rr * lda) : 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr)
+            if (m0 + q * 32 + hrow * 16 + rr < n)
+              __stcs(g0 + (size_t)rr * lda, gv[rr] + patch[rr * 33 + lane]);
+          __syncwarp();
+        }
       }
     }
-    mma_commit(&bar_done);
+    fence_before_sync();
+    __syncthreads(); // patches (and D2) are free for the next piece
+    fence_after_sync();
   }
-  mbar_wait(&bar_done, 1u);
-  fence_after_sync();
-
-  // ---- epilogue: Ainv tile += D2.  Warp w reads TMEM lanes 32 (w % 4) .. +31 (its quarter) and the column half w / 4 in
-  //      pieces of 32 columns, transposes each piece through its own padded shared-memory patch and
-  //      updates 32 rows x 128 bytes with coalesced accesses
-  {
-    float* patch  = Ast + (size_t)warp * 32 * 33; // (both A stages are free: 8 x 4.2 KB of the 64 KB)
-    const int q   = warp & 3, half = warp >> 2;
-    const int nh  = n / 2;
-    for (int c0 = half * nh; c0 < (half + 1) * nh; c0 += 32)
-    {
-      float v[32];
-      tmem_ld32(tmemD2 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        patch[lane * 33 + i] = v[i];
-      __syncwarp();
-      float gv[32]; // 32 rows x 128 bytes of the tile in flight (L2 hits: this CTA streamed them a moment ago)
-      float* g0 = Ainv + (size_t)(m0 + q * 32) * lda + c0 + lane;
-#pragma unroll
-      for (int rr = 0; rr < 32; ++rr)
-        gv[rr] = (m0 + q * 32 + rr < n) ? __ldcg(g0 + (size_t)rr * lda) : 0.f;
-#pragma unroll
-      for (int rr = 0; rr < 32; ++rr)
-        if (m0 + q * 32 + rr < n)
-          __stcs(g0 + (size_t)rr * lda, gv[rr] + patch[rr * 33 + lane]);
-      __syncwarp();
-    }
-  }
-  fence_before_sync();
-  __syncthreads();
   if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 } // namespace wb5
 #endif
