@@ -179,12 +179,37 @@ typedef struct qmcb_vmc_params
   int use_drift;
   uint32_t seed;      /* the crowd's std::mt19937 seed */
   int use_cuda_graph; /* capture one sweep into a CUDA graph and replay it */
+  /* 1: the move loop of DMCBatched::advanceWalkers (QMCDrivers/DMC/DMCBatched.cpp:142-262) instead of VMCBatched's:
+   * a move is rejected when the ratio is zero or changes the phase (SFNBranch::phaseChanged, SFNBranch.h:161-169: real
+   * wavefunctions reject a node crossing, complex ones never), prob = |ratio|^2 exp(log_gb - log_gf) is tested as a whole
+   * against eps and the uniform, and tau |delta|^2 is accumulated per walker for proposed and accepted moves.          */
+  int dmc;
 } qmcb_vmc_params;
 int qmcb_vmc_init(qmcb_crowd* c, const qmcb_vmc_params* p);
 int qmcb_vmc_sweep(qmcb_crowd* c, int nsteps, uint8_t* accept_log_host);
 /* asynchronous launch of one sweep on the crowd's stream (bench.py brackets it with CUDA events) */
 int qmcb_vmc_sweep_async(qmcb_crowd* c);
 int qmcb_vmc_counts(qmcb_crowd* c, long long* n_accept, long long* n_reject);
+/* DMC: per-walker rr_accepted / rr_proposed of the LAST sweep (walker Properties R2ACCEPTED / R2PROPOSED,
+ * DMCBatched.cpp:139-140,191-222), [nw] doubles each.                                                                 */
+int qmcb_dmc_get_rr(qmcb_crowd* c, double* rr_accepted_host, double* rr_proposed_host);
+
+/* ---- walker state for branching and load balancing (WalkerControl::branch, QMCDrivers/DMC/WalkerControl.cpp:151-240;
+ * MCPopulation::fissionHighMultiplicityWalkers; swapWalkersSimple :312-500 ships the walker's buffers between ranks).
+ * The packed state is device resident: positions, both inverse matrices with their gradient/Laplacian rows and
+ * log-determinants, the Jastrow sums -- what the reference keeps in the walker's DataSet so that the receiver does not
+ * recompute.  Pending delayed updates are flushed first.  dev_buf must hold qmcb_crowd_walker_bytes() bytes.           */
+size_t qmcb_crowd_walker_bytes(const qmcb_crowd* c);
+int qmcb_crowd_pack_walker(qmcb_crowd* c, int iw, void* dev_buf);
+int qmcb_crowd_unpack_walker(qmcb_crowd* c, int iw, const void* dev_buf);
+/* duplicate walker src over walker dst inside the crowd (a copy made by branching) */
+int qmcb_crowd_copy_walker(qmcb_crowd* c, int src, int dst);
+/* live walker count of the crowd (1 <= n <= capacity = the nw given at creation): branching kills and spawns walkers
+ * (MCPopulation::killWalker / spawnWalker); walkers [0, n) take part in every mw_* call and in the sweep.  The walker
+ * indices of pack/unpack/copy address the whole capacity so that a spawned walker can be filled before it goes live.  */
+int qmcb_crowd_set_num_walkers(qmcb_crowd* c, int n);
+int qmcb_crowd_num_walkers(const qmcb_crowd* c);
+int qmcb_crowd_capacity(const qmcb_crowd* c);
 /* the crowd's cudaStream_t as void* so callers can record events on the launching stream */
 void* qmcb_crowd_stream(qmcb_crowd* c);
 

@@ -530,6 +530,27 @@ int orc_vmc_get_psiminv(void* hv, int iw, int s, double* out, double* logdet)
                  if (logdet) *logdet = d.log_value.real());
   });
 }
+int orc_vmc_set_num_walkers(void* hv, int n)
+{
+  auto* h = static_cast<VMCHandle*>(hv);
+  return guarded([&] { VMC_DISPATCH(h, v.setNumWalkers(n)); });
+}
+int orc_vmc_copy_walker(void* hv, int src, int dst)
+{
+  auto* h = static_cast<VMCHandle*>(hv);
+  return guarded([&] { VMC_DISPATCH(h, v.copyWalker(src, dst)); });
+}
+// DMC: per-walker rr_accepted / rr_proposed of the last sweep
+int orc_vmc_get_rr(void* hv, double* rr_accepted, double* rr_proposed)
+{
+  auto* h = static_cast<VMCHandle*>(hv);
+  return guarded([&] {
+    VMC_DISPATCH(h, for (int iw = 0; iw < v.nw; ++iw) {
+      rr_accepted[iw] = v.walkers[iw].rr_accepted;
+      rr_proposed[iw] = v.walkers[iw].rr_proposed;
+    });
+  });
+}
 int orc_vmc_get_j2(void* hv, int iw, double* Uat, double* dUat /*[3][N]*/, double* d2Uat)
 {
   auto* h = static_cast<VMCHandle*>(hv);

@@ -56,6 +56,8 @@ struct VMCParams
   // complex orbitals (SplineC2C): tables hold 2*n real components per spin, kpts[s] = [n][3] Cartesian twist vectors
   int complex_orbitals;
   const double* kpts[2];
+  // 1: the move loop of DMCBatched::advanceWalkers (DMC/DMCBatched.cpp:142-262) instead of VMCBatched's
+  int dmc;
 };
 
 #ifndef QMC_ORACLE_USE_REFERENCE
@@ -114,6 +116,7 @@ struct VMC
     std::vector<VT> phi_vgl;            // [5][n] of the proposed move
     double weight = 1.0;
     long n_accept = 0, n_reject = 0;
+    RT rr_accepted = 0, rr_proposed = 0; // DMC: sums of tau |delta|^2 over the last sweep (DMCBatched.cpp:139-140)
   };
 
   struct Crowd
@@ -225,17 +228,38 @@ struct VMC
       w.phi_vgl.assign(5 * (size_t)std::max(p.n_up, p.n_dn), VT(0));
     }
     crowds.resize(p.ncrowds);
-    // walkers are dealt to crowds in contiguous blocks (MCPopulation::redistributeWalkers / fairDivide:
-    // the first (nw % ncrowds) crowds get one extra walker; QMCDrivers/MCPopulation.h + QMCDriverNew.cpp)
-    int base = nw / p.ncrowds, extra = nw % p.ncrowds, w0 = 0;
     for (int c = 0; c < p.ncrowds; ++c)
+      crowds[c].rng = StdRandom(p.seeds[c]);
+    dealWalkers();
+  }
+
+  // walkers are dealt to crowds in contiguous blocks (MCPopulation::redistributeWalkers / fairDivide:
+  // the first (nw % ncrowds) crowds get one extra walker; QMCDrivers/MCPopulation.h + QMCDriverNew.cpp)
+  void dealWalkers()
+  {
+    const int nc = (int)crowds.size();
+    int base = nw / nc, extra = nw % nc, w0 = 0;
+    for (int c = 0; c < nc; ++c)
     {
       const int cnt = base + (c < extra ? 1 : 0);
       crowds[c].w0  = w0;
       crowds[c].w1  = w0 + cnt;
-      crowds[c].rng = StdRandom(p.seeds[c]);
       w0 += cnt;
     }
+  }
+  // DMC branching (MCPopulation::spawnWalker / killWalker + Walker copy): the walker array keeps its capacity, the first
+  // nw walkers are alive
+  void setNumWalkers(int n_active)
+  {
+    if (n_active < 1 || n_active > (int)walkers.size())
+      throw std::runtime_error("oracle VMC: live walker count out of range");
+    nw = n_active;
+    dealWalkers();
+  }
+  void copyWalker(int src, int dst)
+  {
+    if (src != dst)
+      walkers[dst] = walkers[src];
   }
 
   void setPositions(const double* R /*[nw][N][3]*/)
@@ -352,6 +376,8 @@ struct VMC
     }
   }
 
+  RT& w_rr_prop(Crowd& cr, int i) { return walkers[cr.w0 + i].rr_proposed; }
+
   // one sweep step for one crowd
   // forced (optional, [N][nw]): accept flags imposed from outside ("teacher forcing" for mixed-precision parity: the
   // uniform is still drawn under the reference's rule so that the stream stays aligned); ratio_log (optional, [N][nw]):
@@ -372,6 +398,11 @@ struct VMC
     // makeGaussRandomWithEngine(walker_deltas, rng): nw*N*3 Gaussians in one go (VMCBatched.cpp:109)
     cr.walker_deltas.resize(3 * (size_t)cw * N);
     assignGaussRand(cr.walker_deltas.data(), (unsigned)cr.walker_deltas.size(), cr.rng);
+    const bool dmc = prm.dmc != 0;
+    if (dmc)
+      for (int i = 0; i < cw; ++i)
+        walkers[cr.w0 + i].rr_accepted = walkers[cr.w0 + i].rr_proposed = RT(0);
+    std::vector<RT> rr(cw, RT(0));
 
     for (int ig = 0; ig < 2; ++ig)
     {
@@ -384,8 +415,16 @@ struct VMC
         const int row = iat - first_of(ig);
         // deltas for this particle: walker_deltas[iat*cw + iw] (VMCBatched.cpp:122), scaled by sqrt(tau)
         for (int i = 0; i < cw; ++i)
+        {
+          if (dmc)
+          {
+            // rr = tauovermass * dot(delta_r, delta_r) of the raw Gaussians (DMCBatched.cpp:163-167)
+            const RT* dr = &cr.walker_deltas[3 * ((size_t)iat * cw + i)];
+            rr[i]        = tauovermass * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
+          }
           for (int d = 0; d < 3; ++d)
             deltas[3 * i + d] = cr.walker_deltas[3 * ((size_t)iat * cw + i) + d] * sqrttau;
+        }
 
         if (use_drift)
         {
@@ -498,8 +537,25 @@ struct VMC
         for (int i = 0; i < cw; ++i)
         {
           const bool valid = true; // periodic cell: every move is valid
-          if (valid && prob[i] >= std::numeric_limits<RT>::epsilon() &&
-              cr.rng() < prob[i] * std::exp(log_gb[i] - log_gf[i]))
+          if (dmc)
+          {
+            // DMCBatched.cpp:188-222: checkPhaseChanged (ratio == 0 or SFNBranch::phaseChanged(arg ratio): real
+            // wavefunctions reject when cos(arg) < eps, complex builds never), prob = norm(ratio) exp(log_gb - log_gf)
+            bool reject = ratios[i] == PsiV(0);
+            if constexpr (!is_cplx)
+              reject = reject || std::cos(std::arg(ratios[i])) < std::numeric_limits<RT>::epsilon();
+            w_rr_prop(cr, i) += rr[i];
+            const RT pdmc = (RT)(std::norm(ratios[i]) * std::exp(log_gb[i] - log_gf[i]));
+            if (valid && !reject && pdmc >= std::numeric_limits<RT>::epsilon() && cr.rng() < pdmc)
+            {
+              isAccepted[i] = 1;
+              walkers[cr.w0 + i].rr_accepted += rr[i];
+            }
+            else
+              isAccepted[i] = 0;
+          }
+          else if (valid && prob[i] >= std::numeric_limits<RT>::epsilon() &&
+                   cr.rng() < prob[i] * std::exp(log_gb[i] - log_gf[i]))
             isAccepted[i] = 1;
           else
             isAccepted[i] = 0;

@@ -41,7 +41,8 @@ class QmcbSystem(C.Structure):
 
 
 class QmcbVmcParams(C.Structure):
-    _fields_ = [("tau", C.c_double), ("use_drift", C.c_int), ("seed", C.c_uint32), ("use_cuda_graph", C.c_int)]
+    _fields_ = [("tau", C.c_double), ("use_drift", C.c_int), ("seed", C.c_uint32), ("use_cuda_graph", C.c_int),
+                ("dmc", C.c_int)]
 
 
 _lib = None
@@ -61,6 +62,8 @@ SYMBOLS = [
     "qmcb_det_mw_ratio_grad_from_phi", "qmcb_det_delay_count",
     "qmcb_dtaa_get_temp_rows", "qmcb_j2_mw_ratio_grad", "qmcb_j2_mw_accept_reject", "qmcb_j2_get_state",
     "qmcb_vmc_init", "qmcb_vmc_sweep", "qmcb_vmc_sweep_async", "qmcb_vmc_counts", "qmcb_crowd_stream",
+    "qmcb_dmc_get_rr", "qmcb_crowd_walker_bytes", "qmcb_crowd_pack_walker", "qmcb_crowd_unpack_walker",
+    "qmcb_crowd_copy_walker", "qmcb_crowd_set_num_walkers", "qmcb_crowd_num_walkers", "qmcb_crowd_capacity",
 ]
 
 
@@ -82,6 +85,8 @@ def lib():
         L.qmcb_kernel_launch_count.restype = C.c_ulonglong
         L.qmcb_spline_table_bytes.restype = C.c_size_t
         L.qmcb_spline_table_bytes.argtypes = [vp]
+        L.qmcb_crowd_walker_bytes.restype = C.c_size_t
+        L.qmcb_crowd_walker_bytes.argtypes = [vp]
         L.qmcb_crowd_device_bytes.restype = C.c_size_t
         L.qmcb_crowd_device_bytes.argtypes = [vp]
         L.qmcb_crowd_stream.restype = vp
@@ -383,9 +388,49 @@ class Crowd:
         return U, dU, d2U
 
     # ---- device-resident VMC driver
-    def vmc_init(self, tau=0.3, use_drift=True, seed=1000, use_cuda_graph=True):
-        p = QmcbVmcParams(tau, int(use_drift), seed, int(use_cuda_graph))
+    def vmc_init(self, tau=0.3, use_drift=True, seed=1000, use_cuda_graph=True, dmc=False):
+        """dmc=True: the move loop of DMCBatched::advanceWalkers (phase rejection, rr accumulators)"""
+        p = QmcbVmcParams(tau, int(use_drift), seed, int(use_cuda_graph), int(dmc))
         _chk(lib().qmcb_vmc_init(self.h, C.byref(p)))
+
+    # ---- the engine interface of qmcpack_b200.dmc.DMC
+    def dmc_sweep(self):
+        self.last_log = self.vmc_sweep(1, log_accept=True)
+
+    def local_energies(self):
+        return self.mw_evaluateGL()[1]
+
+    def rr(self):
+        return self.dmc_rr()
+
+    def dmc_rr(self):
+        a, p = np.zeros(self.nw), np.zeros(self.nw)
+        _chk(lib().qmcb_dmc_get_rr(self.h, _p(a), _p(p)))
+        return a, p
+
+    # ---- walker state for branching / load balancing (device-resident packed buffers: pass raw device pointers,
+    #      e.g. torch_tensor.data_ptr() of a uint8 tensor of walker_bytes elements)
+    @property
+    def walker_bytes(self):
+        return int(lib().qmcb_crowd_walker_bytes(self.h))
+
+    def pack_walker(self, iw, dev_ptr):
+        _chk(lib().qmcb_crowd_pack_walker(self.h, C.c_int(iw), C.c_void_p(dev_ptr)))
+
+    def unpack_walker(self, iw, dev_ptr):
+        _chk(lib().qmcb_crowd_unpack_walker(self.h, C.c_int(iw), C.c_void_p(dev_ptr)))
+
+    def copy_walker(self, src, dst):
+        _chk(lib().qmcb_crowd_copy_walker(self.h, C.c_int(src), C.c_int(dst)))
+
+    def set_num_walkers(self, n):
+        """live walkers [0, n) of the capacity given at creation (DMC population changes)"""
+        _chk(lib().qmcb_crowd_set_num_walkers(self.h, C.c_int(n)))
+        self.nw = int(n)
+
+    @property
+    def capacity(self):
+        return int(lib().qmcb_crowd_capacity(self.h))
 
     def vmc_sweep(self, nsteps=1, log_accept=False):
         log = np.zeros((nsteps, self.N, self.nw), np.uint8) if log_accept else None

@@ -143,6 +143,10 @@ __device__ __forceinline__ cx<T> shfl_value(const cx<T>& v, const int src)
   return cx<T>(__shfl_sync(0xffffffffu, v.re, src), __shfl_sync(0xffffffffu, v.im, src));
 }
 
+// SFNBranch::phaseChanged(std::arg(ratio)) || ratio == 0  (DMCBatched.cpp:188-193, SFNBranch.h:161-169)
+__device__ __forceinline__ bool phase_rejects(const double ratio) { return !(ratio > 0.0); }
+__device__ __forceinline__ bool phase_rejects(const cx<double>& ratio) { return ratio.re == 0.0 && ratio.im == 0.0; }
+
 template<typename T, typename V>
 __device__ __forceinline__ bool metropolis_warp(const DriverDev<T>& Dr, const JastrowDev<T>& J, const RngDev& R, const int iw,
                                                 const int iat_prev, const V* rg, const int rg_nparts, V& rdet_out)
@@ -200,9 +204,21 @@ __device__ __forceinline__ bool metropolis_warp(const DriverDev<T>& Dr, const Ja
     dr[2] += Dr.drifts[3 * iw + 2];
     log_gb = -Dr.oneover2tau * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
   }
-  const T eps     = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
-  const T prob    = (T)norm2(ratio); // std::norm(ratio), VMCBatched.cpp:152
-  const bool need = prob >= eps; // periodic cell: every move is valid
+  const T eps = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
+  T prob      = (T)norm2(ratio); // std::norm(ratio), VMCBatched.cpp:152
+  bool need   = prob >= eps;     // periodic cell: every move is valid
+  T rr        = T(0);
+  if (Dr.dmc)
+  {
+    // DMCBatched.cpp:188-250: rr = tau |delta|^2 of the raw Gaussian; reject on a zero ratio or a phase change
+    // (SFNBranch::phaseChanged: cos(arg ratio) < eps for real wavefunctions = node crossing; never for complex ones);
+    // prob = |ratio|^2 exp(log_gb - log_gf) as a whole against eps and the uniform
+    const T* dr = Dr.deltas + ((size_t)iat_prev * Dr.nw + iw) * 3;
+    rr          = Dr.tauovermass * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
+    const bool reject = phase_rejects(ratio);
+    prob              = (T)(norm2(ratio) * (double)exp(log_gb - log_gf));
+    need              = !reject && prob >= eps;
+  }
   // ---- position of this walker's draw in the crowd's stream: look back over the lower-index walkers
   const unsigned epoch = sweep * (unsigned)(Dr.N + 1) + (unsigned)iat_prev + 1u;
   if (lane == 0)
@@ -226,11 +242,17 @@ __device__ __forceinline__ bool metropolis_warp(const DriverDev<T>& Dr, const Ja
     if (need)
     {
       const double u = rng_uniform(R, base + cnt);
-      acc            = u < (double)(prob * exp(log_gb - log_gf));
+      acc            = Dr.dmc ? (u < (double)prob) : (u < (double)(prob * exp(log_gb - log_gf)));
     }
     if (iw == Dr.nw - 1)
       R.pos[(iat_prev + 1) & 1] = base + cnt + (need ? 1u : 0u);
     Dr.accepted[iw] = acc ? 1 : 0;
+    if (Dr.dmc)
+    {
+      Dr.rr_proposed[iw] += rr;
+      if (acc)
+        Dr.rr_accepted[iw] += rr;
+    }
     if (acc)
       Dr.n_accept[iw] += 1;
     else
@@ -616,6 +638,7 @@ struct Crowd : CrowdBase
   static constexpr int ncomp    = value_traits<V>::ncomp;
   qmcb_system sys;
   int nw = 0, N = 0, k = 1;
+  int cap = 0; // walkers the buffers were sized for; nw (<= cap) is the number of live walkers (DMC population)
   int nel[2], first[2], lda[2];
   int nmax = 0;
   size_t npad = 0;
@@ -649,7 +672,7 @@ struct Crowd : CrowdBase
   // driver
   DriverDev<T> drv;
   RngDev rng;
-  DevBuf<T> deltas, drifts, delta_cur;
+  DevBuf<T> deltas, drifts, delta_cur, rr_acc, rr_prop;
   DevBuf<uint32_t> rng_state, rng_ring;
   DevBuf<unsigned long long> rng_cnt, n_acc, n_rej;
   DevBuf<unsigned> rng_flags;
@@ -692,6 +715,7 @@ struct Crowd : CrowdBase
   {
     if (nw <= 0)
       throw std::runtime_error("crowd: nw must be positive");
+    cap = nw;
     N        = sys.n_up + sys.n_dn;
     k        = std::max(1, sys.delay_rank);
     nel[0]   = sys.n_up;
@@ -1443,27 +1467,32 @@ struct Crowd : CrowdBase
     drv.sqrttau     = (T)std::sqrt(drv.tauovermass);
     drv.use_drift   = p->use_drift;
     drv.pdl_early   = (g_pdl_mode & 4) ? 1 : 0;
+    drv.dmc         = p->dmc;
+    A(rr_acc, cap);
+    A(rr_prop, cap);
+    drv.rr_accepted = rr_acc.p, drv.rr_proposed = rr_prop.p;
     use_graph       = p->use_cuda_graph != 0;
-    A(deltas, (size_t)N * nw * 3);
-    A(drifts, (size_t)nw * 3);
-    A(delta_cur, (size_t)nw * 3);
-    A(n_acc, nw);
-    A(n_rej, nw);
-    A(accept_log, (size_t)N * nw);
+    A(deltas, (size_t)N * cap * 3);
+    A(drifts, (size_t)cap * 3);
+    A(delta_cur, (size_t)cap * 3);
+    A(n_acc, cap);
+    A(n_rej, cap);
+    A(accept_log, (size_t)N * cap);
     drv.deltas = deltas.p, drv.drifts = drifts.p, drv.delta_cur = delta_cur.p, drv.grads_now = nullptr;
     drv.accepted = accepted.p, drv.n_accept = n_acc.p, drv.n_reject = n_rej.p, drv.accept_log = nullptr;
     // raw stream: one sweep consumes at most 2*ceil(3*nw*N/2) (Box-Muller) + nw*N (accept tests) outputs
-    const unsigned long long gcount = 3ull * nw * N;
-    sweep_backlog                   = 2 * ((gcount + 1) / 2) + (unsigned long long)nw * N;
+    const unsigned long long gcap = 3ull * cap * N;
+    const unsigned long long bcap = 2 * ((gcap + 1) / 2) + (unsigned long long)cap * N;
+    set_backlog();
     unsigned long long ring = 1;
-    while (ring < 3 * sweep_backlog + 2 * 624)
+    while (ring < 3 * bcap + 2 * 624)
       ring <<= 1;
     A(rng_state, 624);
     A(rng_ring, ring);
     A(rng_cnt, 4);
-    A(rng_flags, (size_t)nw + 1);
+    A(rng_flags, (size_t)cap + 1);
     rng.state = rng_state.p, rng.ring = rng_ring.p, rng.gen = rng_cnt.p, rng.pos = rng_cnt.p + 1;
-    rng.sweep = rng_flags.p + nw, rng.flags = rng_flags.p;
+    rng.sweep = rng_flags.p + cap, rng.flags = rng_flags.p;
     rng.ring_mask = (unsigned)(ring - 1);
     mt19937_seed_kernel<<<1, 32, 0, st>>>(rng, p->seed);
     QMCB_LAUNCH_CHECK();
@@ -1552,6 +1581,11 @@ struct Crowd : CrowdBase
   void enqueue_sweep(bool log_accept)
   {
     drv.accept_log = log_accept ? accept_log.p : nullptr;
+    if (drv.dmc)
+    {
+      QMCB_CUDA(cudaMemsetAsync(rr_acc.p, 0, rr_acc.bytes(), st));
+      QMCB_CUDA(cudaMemsetAsync(rr_prop.p, 0, rr_prop.bytes(), st));
+    }
     // fork: top the raw stream up for the NEXT sweep on a side stream while this sweep runs.  The fill kernel may read a
     // stale (smaller) consumption counter: it then generates less, but the invariant "at least one sweep's worth is
     // available at sweep start" holds because it tops up to TWO sweeps' worth and a sweep consumes at most one.
@@ -1662,6 +1696,142 @@ struct Crowd : CrowdBase
   {
     QMCB_CUDA(cudaMemcpyAsync(na, n_acc.p, nw * sizeof(long long), cudaMemcpyDeviceToHost, st));
     QMCB_CUDA(cudaMemcpyAsync(nr, n_rej.p, nw * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    sync();
+  }
+  void dmc_get_rr(double* a, double* p) override
+  {
+    if (!vmc_ready || !drv.dmc)
+      throw std::runtime_error("qmcb_dmc_get_rr: the driver was not initialised with dmc = 1");
+    std::vector<T> ha(nw), hp(nw);
+    QMCB_CUDA(cudaMemcpyAsync(ha.data(), rr_acc.p, nw * sizeof(T), cudaMemcpyDeviceToHost, st));
+    QMCB_CUDA(cudaMemcpyAsync(hp.data(), rr_prop.p, nw * sizeof(T), cudaMemcpyDeviceToHost, st));
+    sync();
+    for (int i = 0; i < nw; ++i)
+    {
+      a[i] = (double)ha[i];
+      p[i] = (double)hp[i];
+    }
+  }
+
+  // ---------------------------------------------------------------- walker state (branching / load balancing)
+  // every per-walker array is walker-major and contiguous: a walker's state is a list of (base, bytes per walker) segments
+  struct Segment
+  {
+    unsigned char* base;
+    size_t bytes;
+  };
+  std::vector<Segment> segments()
+  {
+    std::vector<Segment> sg;
+    auto add = [&](void* p, size_t bytes) {
+      if (p && bytes)
+        sg.push_back({static_cast<unsigned char*>(p), bytes});
+    };
+    add(rsoa.p, 3 * npad * sizeof(T));
+    for (int s2 = 0; s2 < 2; ++s2)
+    {
+      const size_t n = (size_t)nel[s2];
+      add(Ainv[s2].p, n * lda[s2] * sizeof(V));
+      add(GL[s2].p, n * 4 * n * sizeof(V));
+      add(logdet[s2].p, 2 * sizeof(double));
+    }
+    if (jas.has_j2)
+    {
+      add(Uat.p, npad * sizeof(T));
+      add(dUat.p, 3 * npad * sizeof(T));
+      add(d2Uat.p, npad * sizeof(T));
+      add(j2_log.p, sizeof(double));
+    }
+    if (jas.has_j1)
+    {
+      add(Vat.p, (size_t)N * sizeof(T));
+      add(Grad1.p, 3 * (size_t)N * sizeof(T));
+      add(Lap1.p, (size_t)N * sizeof(T));
+      add(j1_log.p, sizeof(double));
+    }
+    return sg;
+  }
+  size_t walker_bytes() const override
+  {
+    size_t b = 0;
+    for (auto& s2 : const_cast<Crowd*>(this)->segments())
+      b += (s2.bytes + 15) & ~size_t(15);
+    return b;
+  }
+  void set_backlog()
+  {
+    const unsigned long long gcount = 3ull * nw * N;
+    sweep_backlog                   = 2 * ((gcount + 1) / 2) + (unsigned long long)nw * N;
+  }
+  // DMC population change: the buffers keep their capacity, every kernel and stride follows the live count
+  void set_num_walkers(int n_active) override
+  {
+    if (n_active < 1 || n_active > cap)
+      throw std::runtime_error("qmcb_crowd_set_num_walkers: count must be in [1, capacity]");
+    settle();
+    sync();
+    nw = n_active;
+    det[0].nw = det[1].nw = nw;
+    jas.nw = nw, drv_host.nw = nw;
+    if (vmc_ready)
+    {
+      drv.nw = nw;
+      set_backlog();
+    }
+    if (graph_exec)
+    {
+      cudaGraphExecDestroy(graph_exec);
+      graph_exec = nullptr;
+    }
+  }
+  int num_walkers() const override { return nw; }
+  int capacity() const override { return cap; }
+  void check_walker(int iw) const
+  {
+    if (iw < 0 || iw >= cap)
+      throw std::runtime_error("walker index out of range");
+  }
+  void settle()
+  {
+    flush_pending();
+    if (delay_count[0] != 0 || delay_count[1] != 0)
+      twf_complete_updates();
+    invrow_id[0] = invrow_id[1] = -1;
+  }
+  void pack_walker(int iw, void* dev_buf) override
+  {
+    check_walker(iw);
+    settle();
+    unsigned char* out = static_cast<unsigned char*>(dev_buf);
+    for (auto& s2 : segments())
+    {
+      QMCB_CUDA(cudaMemcpyAsync(out, s2.base + (size_t)iw * s2.bytes, s2.bytes, cudaMemcpyDeviceToDevice, st));
+      out += (s2.bytes + 15) & ~size_t(15);
+    }
+    sync();
+  }
+  void unpack_walker(int iw, const void* dev_buf) override
+  {
+    check_walker(iw);
+    settle();
+    const unsigned char* in = static_cast<const unsigned char*>(dev_buf);
+    for (auto& s2 : segments())
+    {
+      QMCB_CUDA(cudaMemcpyAsync(s2.base + (size_t)iw * s2.bytes, in, s2.bytes, cudaMemcpyDeviceToDevice, st));
+      in += (s2.bytes + 15) & ~size_t(15);
+    }
+    sync();
+  }
+  void copy_walker(int src, int dst) override
+  {
+    check_walker(src);
+    check_walker(dst);
+    if (src == dst)
+      return;
+    settle();
+    for (auto& s2 : segments())
+      QMCB_CUDA(cudaMemcpyAsync(s2.base + (size_t)dst * s2.bytes, s2.base + (size_t)src * s2.bytes, s2.bytes,
+                                cudaMemcpyDeviceToDevice, st));
     sync();
   }
 };

@@ -32,6 +32,9 @@ struct DriverDev
   RT tauovermass, oneover2tau, sqrttau;
   int use_drift;
   int pdl_early;   // signal programmatic dependents at kernel start
+  int dmc;         // DMCBatched acceptance rule + rr accumulators (DMCBatched.cpp:188-250)
+  RT* rr_accepted; // [nw] sum over accepted moves of tau |delta|^2 (this sweep)
+  RT* rr_proposed; // [nw] the same over all proposed moves
   RT* deltas;      // [N][nw][3] Gaussians of the current sweep (walker_deltas, VMCBatched.cpp:109,122)
   RT* drifts;      // [nw][3]   displacement actually proposed (drift + delta)
   RT* delta_cur;   // [nw][3]

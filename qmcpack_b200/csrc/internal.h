@@ -72,6 +72,14 @@ struct CrowdBase
   virtual void vmc_sweep(int nsteps, uint8_t* accept_log)                                                   = 0;
   virtual void vmc_sweep_async()                                                                            = 0;
   virtual void vmc_counts(long long* na, long long* nr)                                                     = 0;
+  virtual void dmc_get_rr(double* rr_acc, double* rr_prop)                                                  = 0;
+  virtual size_t walker_bytes() const                                                                       = 0;
+  virtual void pack_walker(int iw, void* dev_buf)                                                           = 0;
+  virtual void unpack_walker(int iw, const void* dev_buf)                                                   = 0;
+  virtual void copy_walker(int src, int dst)                                                                = 0;
+  virtual void set_num_walkers(int n_active)                                                                = 0;
+  virtual int num_walkers() const                                                                           = 0;
+  virtual int capacity() const                                                                              = 0;
   virtual cudaStream_t stream()                                                                             = 0;
 };
 

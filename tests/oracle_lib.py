@@ -40,7 +40,7 @@ class VMCParams(C.Structure):
         ("n_j1", C.c_int), ("j1_params", c_dp), ("j1_rcut", c_dp),
         ("nw", C.c_int), ("ncrowds", C.c_int), ("seeds", C.POINTER(C.c_uint32)),
         ("tau", C.c_double), ("use_drift", C.c_int), ("delay_rank", C.c_int), ("batched_engine", C.c_int),
-        ("complex_orbitals", C.c_int), ("kpts", c_dp * 2),
+        ("complex_orbitals", C.c_int), ("kpts", c_dp * 2), ("dmc", C.c_int),
     ]
 
 
@@ -345,7 +345,7 @@ class OracleVMC:
     """The oracle's restatement of VMCBatched::advanceWalkers over a synthetic system (see qmcpack_b200.workload)."""
 
     def __init__(self, orc, system, nw, ncrowds=1, seeds=None, tau=0.3, use_drift=True, delay_rank=32,
-                 batched_engine=True, precision=None):
+                 batched_engine=True, precision=None, dmc=False):
         self.o = orc
         s = system
         prec = precision if precision is not None else (1 if s["coefs"][0].dtype == np.float32 else 0)
@@ -386,6 +386,7 @@ class OracleVMC:
         kp = s.get("kpts")
         self.cplx = kp is not None
         p.complex_orbitals = int(self.cplx)
+        p.dmc = int(dmc)
         if self.cplx:
             for i in range(2):
                 k = _np(kp[i], np.float64)
@@ -439,6 +440,18 @@ class OracleVMC:
         G, L = np.zeros((self.nw, self.N, 3), dt), np.zeros((self.nw, self.N), dt)
         self.o._chk(self.o.lib.orc_vmc_evaluate_gl(self.h, _p(logpsi), _p(ke), _p(G), _p(L)))
         return logpsi, ke, G, L
+
+    def set_num_walkers(self, n):
+        self.o._chk(self.o.lib.orc_vmc_set_num_walkers(self.h, C.c_int(n)))
+        self.nw = int(n)
+
+    def copy_walker(self, src, dst):
+        self.o._chk(self.o.lib.orc_vmc_copy_walker(self.h, C.c_int(src), C.c_int(dst)))
+
+    def rr(self):
+        a, p = np.zeros(self.nw), np.zeros(self.nw)
+        self.o._chk(self.o.lib.orc_vmc_get_rr(self.h, _p(a), _p(p)))
+        return a, p
 
     def counts(self):
         a, r = np.zeros(self.nw, np.int64), np.zeros(self.nw, np.int64)

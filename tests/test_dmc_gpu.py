@@ -1,0 +1,154 @@
+"""GPU parity of the DMC layer: the device move loop of DMCBatched::advanceWalkers (phase rejection, rr accumulators),
+walker duplication / packed transfer, and a branching run whose population follows the oracle's step for step."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from qmcpack_b200 import api as a, build
+    build.build()
+    a.init(0)
+    return a
+
+
+def small_system(dt=np.float64, complex_orbitals=False):
+    from qmcpack_b200.workload import make_system
+    return make_system(N=24, M=8, dtype=dt, L=6.0, complex_orbitals=complex_orbitals)
+
+
+class OracleEngine:
+    """adapter: the oracle's VMC object behind the engine interface of qmcpack_b200.dmc.DMC"""
+
+    def __init__(self, ov, capacity):
+        self.ov, self.capacity = ov, capacity
+
+    nw = property(lambda self: self.ov.nw)
+
+    def dmc_sweep(self):
+        self.last_log = self.ov.sweep(1, log_accept=True)
+
+    def local_energies(self):
+        return self.ov.evaluate_gl()[1]
+
+    def rr(self):
+        return self.ov.rr()
+
+    def copy_walker(self, src, dst):
+        self.ov.copy_walker(src, dst)
+
+    def set_num_walkers(self, n):
+        self.ov.set_num_walkers(n)
+
+
+@pytest.mark.parametrize("cplx", [False, True], ids=["real", "complex"])
+def test_dmc_move_loop_identical_acceptance_fp64(api, orc, cplx):
+    """node crossings are rejected for real wavefunctions (and only there), prob is tested as a whole, rr sums agree"""
+    from qmcpack_b200.workload import initial_positions
+    import oracle_lib
+    s = small_system(np.float64, cplx)
+    nw, k, nsteps, tau, seed = 9, 4, 3, 0.3, 515
+    R = initial_positions(s, nw)
+    ov = oracle_lib.OracleVMC(orc, s, nw=nw, ncrowds=1, seeds=[seed], tau=tau, delay_rank=k, dmc=True)
+    ov.set_positions(R)
+    ov.recompute()
+    crowd = api.Crowd(s, nw=nw, delay_rank=k)
+    crowd.set_positions(R)
+    crowd.mw_recompute()
+    crowd.vmc_init(tau=tau, use_drift=True, seed=seed, use_cuda_graph=False, dmc=True)
+    for step in range(nsteps):
+        olog = ov.sweep(1, log_accept=True)
+        log = crowd.vmc_sweep(1, log_accept=True)
+        assert np.array_equal(log, olog), f"step {step}: {np.argwhere(log != olog)[:5]}"
+        a, p = crowd.dmc_rr()
+        oa, op = ov.rr()
+        assert a == pytest.approx(oa, rel=1e-10) and p == pytest.approx(op, rel=1e-10)
+        assert (p >= a).all() and p.min() > 0
+    assert crowd.positions() == pytest.approx(ov.positions(), rel=1e-9, abs=1e-9)
+
+
+def test_walker_copy_and_packed_transfer(api, orc):
+    """a duplicated walker and a walker shipped as a packed device buffer into ANOTHER crowd carry the complete state:
+    the sweeps that follow match the oracle's, whose walkers were duplicated the same way"""
+    import torch
+    from qmcpack_b200.workload import initial_positions
+    import oracle_lib
+    s = small_system()
+    nw, k, tau, seed = 6, 4, 0.2, 99
+    R = initial_positions(s, nw)
+    ov = oracle_lib.OracleVMC(orc, s, nw=nw, ncrowds=1, seeds=[seed], tau=tau, delay_rank=k)
+    ov.set_positions(R)
+    ov.recompute()
+    crowd = api.Crowd(s, nw=nw, delay_rank=k)
+    crowd.set_positions(R)
+    crowd.mw_recompute()
+    crowd.vmc_init(tau=tau, seed=seed, use_cuda_graph=False)
+    assert np.array_equal(crowd.vmc_sweep(1, log_accept=True), ov.sweep(1, log_accept=True))
+    # duplicate walker 1 over walker 4, then ship walker 2 through a second crowd and back into slot 0
+    crowd.copy_walker(1, 4)
+    ov.copy_walker(1, 4)
+    other = api.Crowd(s, nw=2, delay_rank=k, spo=crowd.spo)
+    other.set_positions(R[:2])
+    other.mw_recompute()
+    buf = torch.empty(crowd.walker_bytes, dtype=torch.uint8, device="cuda")
+    assert other.walker_bytes == crowd.walker_bytes
+    crowd.pack_walker(2, buf.data_ptr())
+    other.unpack_walker(1, buf.data_ptr())
+    buf2 = torch.empty_like(buf)
+    other.pack_walker(1, buf2.data_ptr())
+    assert torch.equal(buf, buf2)
+    crowd.unpack_walker(0, buf2.data_ptr())
+    ov.copy_walker(2, 0)
+    log, olog = crowd.vmc_sweep(2, log_accept=True), ov.sweep(2, log_accept=True)
+    assert np.array_equal(log, olog)
+    lp, ke, _, _ = crowd.mw_evaluateGL()
+    olp, oke, _, _ = ov.evaluate_gl()
+    assert lp == pytest.approx(olp, rel=1e-9, abs=1e-9) and ke == pytest.approx(oke, rel=1e-7)
+    # the live count can shrink and grow inside the capacity
+    crowd.set_num_walkers(4)
+    ov.set_num_walkers(4)
+    assert np.array_equal(crowd.vmc_sweep(1, log_accept=True), ov.sweep(1, log_accept=True))
+    crowd.set_num_walkers(6)
+    ov.set_num_walkers(6)
+    assert np.array_equal(crowd.vmc_sweep(1, log_accept=True), ov.sweep(1, log_accept=True))
+
+
+def test_dmc_branching_run_follows_oracle(api, orc):
+    """six DMC generations with branching (dynamic population inside a capacity of 16): the product on the GPU and the
+    oracle, both steered by qmcpack_b200.dmc.DMC with the same branching stream, keep identical populations,
+    acceptance logs, weights and energies"""
+    from qmcpack_b200.workload import initial_positions
+    from qmcpack_b200 import dmc
+    import oracle_lib
+    s = small_system()
+    cap, n0, k, tau, seed = 16, 8, 4, 0.05, 2024
+    R = initial_positions(s, cap)
+    ov = oracle_lib.OracleVMC(orc, s, nw=cap, ncrowds=1, seeds=[seed], tau=tau, delay_rank=k, dmc=True)
+    ov.set_positions(R)
+    ov.recompute()
+    ov.set_num_walkers(n0)
+    crowd = api.Crowd(s, nw=cap, delay_rank=k)
+    crowd.set_positions(R)
+    crowd.mw_recompute()
+    crowd.vmc_init(tau=tau, seed=seed, use_cuda_graph=True, dmc=True)
+    crowd.set_num_walkers(n0)
+    rng_a, rng_b = orc.rng(7), orc.rng(7)
+    da = dmc.DMC(crowd, tau, n0, rng_a.uniform)
+    db = dmc.DMC(OracleEngine(ov, cap), tau, n0, rng_b.uniform)
+    pops = []
+    for gen in range(6):
+        da.advance()
+        db.advance()
+        assert np.array_equal(crowd.last_log, db.eng.last_log), f"generation {gen}"
+        assert da.weights == pytest.approx(db.weights, rel=1e-7)
+        assert da.energies == pytest.approx(db.energies, rel=1e-7)
+        ea = da.branch_step(do_not_branch=(gen == 0))
+        eb = db.branch_step(do_not_branch=(gen == 0))
+        assert crowd.nw == ov.nw
+        assert ea["energy"] == pytest.approx(eb["energy"], rel=1e-7)
+        assert da.branch.e_trial == pytest.approx(db.branch.e_trial, rel=1e-7, abs=1e-7)
+        pops.append(crowd.nw)
+    assert len(set(pops)) > 1, pops  # the population really changed
+    assert crowd.positions() == pytest.approx(ov.positions()[:crowd.nw], rel=1e-9, abs=1e-9)
