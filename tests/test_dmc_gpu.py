@@ -152,3 +152,69 @@ def test_dmc_branching_run_follows_oracle(api, orc):
         pops.append(crowd.nw)
     assert len(set(pops)) > 1, pops  # the population really changed
     assert crowd.positions() == pytest.approx(ov.positions()[:crowd.nw], rel=1e-9, abs=1e-9)
+
+
+def _two_gpu_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from qmcpack_b200 import api, dmc, build
+    from qmcpack_b200.workload import initial_positions
+    build.build()
+    api.init(rank)
+    s = small_system()
+    cap, n0, k, tau = 24, 8, 4, 0.05
+    R = initial_positions(s, cap, seed=7 + 1000 * rank)
+    crowd = api.Crowd(s, nw=cap, delay_rank=k)
+    crowd.set_positions(R)
+    crowd.mw_recompute()
+    crowd.vmc_init(tau=tau, seed=100 + rank, use_cuda_graph=False, dmc=True)
+    crowd.set_num_walkers(n0)
+    rng = np.random.default_rng(5 + rank)
+    d = dmc.DMC(crowd, tau, world * n0, rng.random, dist=dist, device=torch.device("cuda", rank))
+    # make rank 0 heavy and rank 1 light so that walkers must cross NVLink
+    pops, sent = [], 0
+    for gen in range(5):
+        d.advance()
+        if gen == 1:
+            d.weights = d.weights * (2.5 if rank == 0 else 0.3)
+        before = crowd.nw
+        ens = d.branch_step(do_not_branch=(gen == 0))
+        pops.append(crowd.nw)
+    lp, ke, _, _ = crowd.mw_evaluateGL()
+    crowd.mw_recompute()  # delayed-update state of received / copied walkers == from-scratch state
+    lp2, ke2, _, _ = crowd.mw_evaluateGL()
+    q.put((rank, pops, bool(np.isfinite(ke).all()), float(np.abs(lp - lp2).max()), float(np.abs(ke - ke2).max()),
+           [h["population"] for h in d.history]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_walker_exchange_over_nccl(api):
+    """WalkerControl::branch across two GPUs: the per-rank populations stay within one walker of each other after every
+    branch, the global population is what the all-reduced multiplicities say, and walkers that crossed NVLink as packed
+    device buffers carry a state identical to a from-scratch recompute"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_two_gpu_worker, args=(r, 2, 29741, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, pops0, fin0, dlp0, dke0, glob0), (_, pops1, fin1, dlp1, dke1, glob1) = out
+    assert fin0 and fin1
+    assert glob0 == glob1
+    for a, b, g in zip(pops0, pops1, glob0):
+        assert abs(a - b) <= 1 and a + b == min(g, 48)
+    assert pops0[2] != 8 or pops1[2] != 8  # the imbalance of generation 1 really moved walkers
+    assert max(dlp0, dlp1) < 1e-8 and max(dke0, dke1) < 1e-6
