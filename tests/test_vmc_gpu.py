@@ -424,6 +424,16 @@ def test_nio_a256_orbital_count_every_move(api, orc, dt):
         assert early.max() < 1e-7, early.max()
         assert np.median(rel) < 1e-4
         assert crowd.positions() == pytest.approx(ov.positions(), rel=1e-12, abs=1e-12)
+        # the device-resident driver at this width (48 partial-dot slots > one warp of them): same stream, same decisions
+        # as the host-driven loop over the span where rounding has not been amplified yet
+        dev = api.Crowd(s, nw=nw, delay_rank=k, spo=crowd.spo)
+        dev.set_positions(R)
+        dev.mw_recompute()
+        dev.vmc_init(tau=tau, use_drift=False, seed=seed, use_cuda_graph=False)
+        dlog = dev.vmc_sweep(1, log_accept=True)
+        assert np.array_equal(dlog[0, :512], log[0, :512])
+        assert np.array_equal(dlog[0, n:n + 256], log[0, n:n + 256])
+        assert abs(dlog.mean() - log.mean()) < 0.02
     else:
         first = np.concatenate([rel[0, :32], rel[0, n:n + 32]])  # before the first flush of each determinant
         assert np.median(first) < 1e-3 and first.max() < 0.2, (np.median(first), first.max())
