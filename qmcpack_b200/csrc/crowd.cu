@@ -285,6 +285,8 @@ __global__ void __launch_bounds__(MB_TPB, (sizeof(V) > 8 ? 2 : 4))
   __shared__ V red[3 * 32];
   __shared__ int s_acc;
   __shared__ V s_ratio;
+  __shared__ T jred[10 * 32];
+  __shared__ T s_newpos[3];
   const int iw = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool part1 = iat_prev >= 0, part2 = iat_next >= 0;
   const int nA = part1 ? Dacc.n : 0, nB = part2 ? Dprep.n : 0, k = part1 ? Dacc.k : Dprep.k;
@@ -593,7 +595,17 @@ __global__ void __launch_bounds__(MB_TPB, (sizeof(V) > 8 ? 2 : 4))
       Dr.drifts[3 * iw + d]    = disp;
       Dr.delta_cur[3 * iw + d] = delta;
       J.newpos[3 * iw + d]     = rold + disp;
+      s_newpos[d]              = rold + disp;
     }
+  }
+  // Jastrow sums at the proposed position (TwoBodyJastrow::mw_ratioGrad, J1 ratioGrad), fused into the tail of the
+  // boundary: a separate kernel beside the spline gather is starved by the gather's register footprint and costs more
+  // than these few microseconds of the whole CTA
+  if (Dr.fuse_jastrow && part2 && !twf_grads_out && (J.has_j2 || J.has_j1))
+  {
+    __syncthreads();
+    const T pos[3] = {s_newpos[0], s_newpos[1], s_newpos[2]};
+    jastrow_move_body<T, false>(J, iw, iat_next, pos, jred);
   }
 }
 
@@ -798,13 +810,12 @@ struct Crowd : CrowdBase
     if (jas.has_j2)
     {
       A(rows, (size_t)2 * nw * 4 * npad);
-      A(cur_allu, (size_t)nw * 3 * npad);
       A(j2_vgl, (size_t)nw * 5);
       A(Uat, (size_t)nw * npad);
       A(dUat, (size_t)nw * 3 * npad);
       A(d2Uat, (size_t)nw * npad);
       A(j2_log, nw);
-      jas.rows = rows.p, jas.cur_allu = cur_allu.p, jas.j2_vgl = j2_vgl.p, jas.Uat = Uat.p, jas.dUat = dUat.p;
+      jas.rows = rows.p, jas.cur_allu = nullptr, jas.j2_vgl = j2_vgl.p, jas.Uat = Uat.p, jas.dUat = dUat.p;
       jas.d2Uat = d2Uat.p, jas.j2_log = j2_log.p;
       // cusp -1/4 like spin, -1/2 unlike spin (Jastrow/RadialJastrowBuilder.cpp:200-208)
       fill_functor(jas.F2[0], pool, sys.j2_uu, sys.n_j2, sys.j2_rcut, -0.25);
@@ -1292,13 +1303,15 @@ struct Crowd : CrowdBase
       // distance rows + Jastrow sums run on the side stream, beside the spline gather of the coming ratio call
       QMCB_CUDA(cudaEventRecord(ev_fork, st));
       QMCB_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
-      jastrow_move_kernel<T><<<nw, JAS_TPB, 0, st2>>>(jas, iat);
+      jastrow_move_kernel<T, false><<<nw, JAS_TPB, 0, st2>>>(jas, iat);
       QMCB_LAUNCH_CHECK();
       QMCB_CUDA(cudaEventRecord(ev_join, st2));
       jastrow_inflight = true;
+      last_move_iat    = iat;
     }
   }
   bool jastrow_inflight = false;
+  int last_move_iat     = -1;
   void join_jastrow()
   {
     if (jastrow_inflight)
@@ -1405,6 +1418,11 @@ struct Crowd : CrowdBase
     flush_pending();
     if (!jas.has_j2)
       throw std::runtime_error("distance rows are only kept when a two-body Jastrow is present");
+    if (last_move_iat < 0)
+      throw std::runtime_error("qmcb_dtaa_get_temp_rows: no move has been proposed yet");
+    // the rows are not materialised on the move path (jastrow.cuh); store them now for the last proposed move
+    jastrow_move_kernel<T, true><<<nw, JAS_TPB, 0, st>>>(jas, last_move_iat);
+    QMCB_LAUNCH_CHECK();
     // device [2][nw][4][npad] -> host [2][nw][4][N]
     QMCB_CUDA(cudaMemcpy2DAsync(out, (size_t)N * sizeof(T), rows.p, npad * sizeof(T), (size_t)N * sizeof(T),
                                 (size_t)2 * nw * 4, cudaMemcpyDeviceToHost, st));
@@ -1468,6 +1486,10 @@ struct Crowd : CrowdBase
     drv.use_drift   = p->use_drift;
     drv.pdl_early   = (g_pdl_mode & 4) ? 1 : 0;
     drv.dmc         = p->dmc;
+    {
+      const char* e    = std::getenv("QMCB_FUSE_J");
+      drv.fuse_jastrow = e ? std::atoi(e) : 1;
+    }
     A(rr_acc, cap);
     A(rr_prop, cap);
     drv.rr_accepted = rr_acc.p, drv.rr_proposed = rr_prop.p;
@@ -1606,12 +1628,12 @@ struct Crowd : CrowdBase
     for (int iat = 0; iat < N; ++iat)
     {
       const int ig = spin_of(iat);
-      const bool jast = jas.has_j2 || jas.has_j1;
+      const bool jast = (jas.has_j2 || jas.has_j1) && !drv.fuse_jastrow;
       if (jast)
       {
         QMCB_CUDA(cudaEventRecord(ev_fork, st));
         QMCB_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
-        jastrow_move_kernel<T><<<nw, JAS_TPB, 0, st2>>>(jas, iat);
+        jastrow_move_kernel<T, false><<<nw, JAS_TPB, 0, st2>>>(jas, iat);
         QMCB_LAUNCH_CHECK();
         QMCB_CUDA(cudaEventRecord(ev_join, st2));
       }

@@ -183,44 +183,49 @@ __device__ __forceinline__ void j1_sums(const JastrowDev<RT>& J, const RT pos[3]
     out[e] = acc[e];
 }
 
-// ---- proposed move: temp + old distance rows, J2 cur_allu / vgl, J1 current sums.  grid = nw
-template<typename RT>
-__global__ void __launch_bounds__(JAS_TPB) jastrow_move_kernel(const JastrowDev<RT> J, const int iat)
+// ---- proposed move: J2 sums over the temporary distance row and J1 sums at the proposed position.
+// The reference materialises the new AND the old distance row (mw_new_old_dist_displ) and the per-pair functor values
+// (mw_cur_allu) in device memory and reads them back in the accept kernel: 54 KB written + 45 KB read per walker per
+// move at NiO-a64.  Here the rows are a by-product that is only stored on request (STORE, for qmcb_dtaa_get_temp_rows);
+// the accept recomputes the two rows from the positions (9 KB) -- identical arithmetic, so identical values -- and the
+// J1 and J2 sums share one pass and one block reduction.
+// Body for one walker, executed by ALL threads of the CTA (blockDim.x threads; red >= 10 * 32).
+template<typename RT, bool STORE>
+__device__ __forceinline__ void jastrow_move_body(const JastrowDev<RT>& J, const int iw, const int iat, const RT pos[3], RT* red)
 {
-  __shared__ RT red[5 * 32];
-  const int iw = blockIdx.x, tid = threadIdx.x, N = J.N, np = J.npad;
+  const int tid = threadIdx.x, N = J.N, np = J.npad, JAS_STEP = blockDim.x;
   const RT* rs = J.rsoa + (size_t)iw * 3 * np;
-  RT pos[3]    = {J.newpos[3 * iw], J.newpos[3 * iw + 1], J.newpos[3 * iw + 2]};
+  RT acc[10]   = {RT(0), RT(0), RT(0), RT(0), RT(0), RT(0), RT(0), RT(0), RT(0), RT(0)};
   if (J.has_j2)
   {
-    RT old[3]   = {rs[iat], rs[np + iat], rs[2 * np + iat]};
+    RT old[3]   = {RT(0), RT(0), RT(0)};
     RT* rnew    = J.rows + (size_t)iw * 4 * np;
     RT* rold    = J.rows + ((size_t)J.nw + iw) * 4 * np;
-    RT* cur     = J.cur_allu + (size_t)iw * 3 * np;
+    if (STORE)
+      old[0] = rs[iat], old[1] = rs[np + iat], old[2] = rs[2 * np + iat];
     const int gi = (iat < J.n_up ? 0 : 1) * 2;
-    RT acc[5]   = {RT(0), RT(0), RT(0), RT(0), RT(0)};
-    for (int j = tid; j < N; j += JAS_TPB)
+    for (int j = tid; j < N; j += JAS_STEP)
     {
       const RT px = rs[j], py = rs[np + j], pz = rs[2 * np + j];
       RT r, dx, dy, dz;
       min_image(J.cell, pos, px, py, pz, j, iat, r, dx, dy, dz);
-      rnew[j]          = r;
-      rnew[np + j]     = dx;
-      rnew[2 * np + j] = dy;
-      rnew[3 * np + j] = dz;
-      RT ro, ox, oy, oz;
-      min_image(J.cell, old, px, py, pz, j, iat, ro, ox, oy, oz);
-      rold[j]          = (j == iat) ? (sizeof(RT) == 4 ? RT(3.402823466e+38f) : RT(1.7976931348623157e+308)) : ro;
-      rold[np + j]     = ox;
-      rold[2 * np + j] = oy;
-      rold[3 * np + j] = oz;
+      if (STORE)
+      {
+        rnew[j]          = r;
+        rnew[np + j]     = dx;
+        rnew[2 * np + j] = dy;
+        rnew[3 * np + j] = dz;
+        RT ro, ox, oy, oz;
+        min_image(J.cell, old, px, py, pz, j, iat, ro, ox, oy, oz);
+        rold[j]          = (j == iat) ? (sizeof(RT) == 4 ? RT(3.402823466e+38f) : RT(1.7976931348623157e+308)) : ro;
+        rold[np + j]     = ox;
+        rold[2 * np + j] = oy;
+        rold[3 * np + j] = oz;
+      }
       if (j != iat)
       {
         RT du, d2u;
-        const RT u      = functor_eval(J.F2[gi + (j < J.n_up ? 0 : 1)], r, du, d2u);
-        cur[j]          = u;
-        cur[np + j]     = du;
-        cur[2 * np + j] = d2u;
+        const RT u = functor_eval(J.F2[gi + (j < J.n_up ? 0 : 1)], r, du, d2u);
         acc[0] += u;
         acc[1] += du * dx;
         acc[2] += du * dy;
@@ -228,24 +233,44 @@ __global__ void __launch_bounds__(JAS_TPB) jastrow_move_kernel(const JastrowDev<
         acc[4] += d2u + RT(2) * du;
       }
     }
-    block_sum<RT, 5>(acc, red);
-    if (tid == 0)
-    {
-      RT* vgl = J.j2_vgl + (size_t)iw * 5;
-      vgl[0]  = acc[0];
-      vgl[1]  = acc[1];
-      vgl[2]  = acc[2];
-      vgl[3]  = acc[3];
-      vgl[4]  = -acc[4];
-    }
   }
   if (J.has_j1)
   {
-    RT o[5];
-    j1_sums(J, pos, o, red);
-    if (tid < 5)
-      J.j1_cur[(size_t)iw * 5 + tid] = o[tid];
+    // one-body sums at the proposed position (J1OrbitalSoA.h:136-185)
+    for (int j = tid; j < J.nions; j += JAS_STEP)
+    {
+      RT r, dx, dy, dz, du, d2u;
+      min_image(J.cell, pos, J.ion_rsoa[j], J.ion_rsoa[J.npad_ion + j], J.ion_rsoa[2 * J.npad_ion + j], j, 0, r, dx, dy, dz);
+      const RT u = functor_eval(J.F1[J.ion_grp[j]], r, du, d2u);
+      acc[5] += u;
+      acc[6] += du * dx;
+      acc[7] += du * dy;
+      acc[8] += du * dz;
+      acc[9] += d2u + RT(2) * du;
+    }
   }
+  block_sum<RT, 10>(acc, red);
+  if (J.has_j2 && tid == 0)
+  {
+    RT* vgl = J.j2_vgl + (size_t)iw * 5;
+    vgl[0]  = acc[0];
+    vgl[1]  = acc[1];
+    vgl[2]  = acc[2];
+    vgl[3]  = acc[3];
+    vgl[4]  = -acc[4];
+  }
+  if (J.has_j1 && tid < 5)
+    J.j1_cur[(size_t)iw * 5 + tid] = acc[5 + tid];
+}
+
+// grid = nw
+template<typename RT, bool STORE>
+__global__ void __launch_bounds__(JAS_TPB) jastrow_move_kernel(const JastrowDev<RT> J, const int iat)
+{
+  __shared__ RT red[10 * 32];
+  const int iw    = blockIdx.x;
+  const RT pos[3] = {J.newpos[3 * iw], J.newpos[3 * iw + 1], J.newpos[3 * iw + 2]};
+  jastrow_move_body<RT, STORE>(J, iw, iat, pos, red);
 }
 
 // ---- accept (walker iw, thread group g): J2 per-particle sums (BsplineFunctor.cpp:262-324), J1 commit, position commit
@@ -255,9 +280,9 @@ __device__ __forceinline__ void jastrow_accept_body(const Group& g, const Jastro
   const int tid = g.tid, N = J.N, np = J.npad;
   if (J.has_j2)
   {
-    const RT* rnew = J.rows + (size_t)iw * 4 * np;
-    const RT* rold = J.rows + ((size_t)J.nw + iw) * 4 * np;
-    const RT* cur  = J.cur_allu + (size_t)iw * 3 * np;
+    const RT* rs   = J.rsoa + (size_t)iw * 3 * np;
+    const RT pnew[3] = {J.newpos[3 * iw], J.newpos[3 * iw + 1], J.newpos[3 * iw + 2]};
+    const RT pold[3] = {rs[iat], rs[np + iat], rs[2 * np + iat]}; // (the commit below waits behind the group barrier)
     RT* Uat        = J.Uat + (size_t)iw * np;
     RT* dU         = J.dUat + (size_t)iw * 3 * np;
     RT* d2U        = J.d2Uat + (size_t)iw * np;
@@ -270,8 +295,7 @@ __device__ __forceinline__ void jastrow_accept_body(const Group& g, const Jastro
     constexpr int CH = 2;
     for (int j0 = tid; j0 < N; j0 += CH * g.n)
     {
-      RT ro[CH], ox[CH], oy[CH], oz[CH], nx[CH], ny[CH], nz[CH], cu[CH], cdu[CH], cd2[CH], ua[CH], da[CH], db[CH], dc[CH],
-          l2[CH];
+      RT px[CH], py[CH], pz[CH], ua[CH], da[CH], db[CH], dc[CH], l2[CH];
       bool on[CH];
 #pragma unroll
       for (int q = 0; q < CH; ++q)
@@ -280,16 +304,9 @@ __device__ __forceinline__ void jastrow_accept_body(const Group& g, const Jastro
         on[q]       = j < N && j != iat;
         if (on[q])
         {
-          ro[q]  = rold[j];
-          ox[q]  = rold[np + j];
-          oy[q]  = rold[2 * np + j];
-          oz[q]  = rold[3 * np + j];
-          nx[q]  = rnew[np + j];
-          ny[q]  = rnew[2 * np + j];
-          nz[q]  = rnew[3 * np + j];
-          cu[q]  = cur[j];
-          cdu[q] = cur[np + j];
-          cd2[q] = cur[2 * np + j];
+          px[q]  = rs[j];
+          py[q]  = rs[np + j];
+          pz[q]  = rs[2 * np + j];
           ua[q]  = Uat[j];
           da[q]  = dU[j];
           db[q]  = dU[np + j];
@@ -303,13 +320,18 @@ __device__ __forceinline__ void jastrow_accept_body(const Group& g, const Jastro
         const int j = j0 + q * g.n;
         if (on[q])
         {
-          RT du, d2u;
-          const RT u = functor_eval(J.F2[gi + (j < J.n_up ? 0 : 1)], ro[q], du, d2u);
-          Uat[j]         = ua[q] + (cu[q] - u);
-          dU[j]          = da[q] - (nx[q] * cdu[q] - ox[q] * du);
-          dU[np + j]     = db[q] - (ny[q] * cdu[q] - oy[q] * du);
-          dU[2 * np + j] = dc[q] - (nz[q] * cdu[q] - oz[q] * du);
-          d2U[j]         = l2[q] - (cd2[q] + RT(2) * cdu[q] - (d2u + RT(2) * du));
+          // both distance rows and both functor evaluations are recomputed from the positions (see jastrow_move_body)
+          RT rn, nx, ny, nz, ro, ox, oy, oz, cdu, cd2, du, d2u;
+          min_image(J.cell, pnew, px[q], py[q], pz[q], j, iat, rn, nx, ny, nz);
+          min_image(J.cell, pold, px[q], py[q], pz[q], j, iat, ro, ox, oy, oz);
+          const FunctorDev<RT>& F = J.F2[gi + (j < J.n_up ? 0 : 1)];
+          const RT cu = functor_eval(F, rn, cdu, cd2);
+          const RT u  = functor_eval(F, ro, du, d2u);
+          Uat[j]         = ua[q] + (cu - u);
+          dU[j]          = da[q] - (nx * cdu - ox * du);
+          dU[np + j]     = db[q] - (ny * cdu - oy * du);
+          dU[2 * np + j] = dc[q] - (nz * cdu - oz * du);
+          d2U[j]         = l2[q] - (cd2 + RT(2) * cdu - (d2u + RT(2) * du));
         }
       }
     }
