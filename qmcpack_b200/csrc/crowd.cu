@@ -930,6 +930,16 @@ struct Crowd : CrowdBase
 
   cudaStream_t stream() override { return st; }
   void sync() override { QMCB_CUDA(cudaStreamSynchronize(st)); }
+  // host-driven move loop: two device round trips per move, so the wake-up latency of a blocking synchronize matters;
+  // poll the stream instead (one host thread per crowd, VMCBatched.cpp:348)
+  void spin_sync()
+  {
+    cudaError_t e;
+    while ((e = cudaStreamQuery(st)) == cudaErrorNotReady)
+    {
+    }
+    QMCB_CUDA(e);
+  }
   size_t device_bytes() const override { return dev_bytes; }
   bool is_complex() const override { return cplx; }
   int spin_of(int iat) const { return iat < sys.n_up ? 0 : 1; }
@@ -1275,9 +1285,10 @@ struct Crowd : CrowdBase
     check_iat(iat);
     // [accept of the previous electron, if one is pending] + inverse row + component-summed gradient: one launch
     join_jastrow();
-    apply_pending(iat, grads_tmp.p);
-    QMCB_CUDA(cudaMemcpyAsync(h_t.p, grads_tmp.p, (size_t)nw * 3 * sizeof(V), cudaMemcpyDeviceToHost, st));
-    sync();
+    // the kernel stores the gradients straight into the pinned host buffer (unified addressing: pinned allocations are
+    // device-accessible): the device->host transfer needs no separate copy launch
+    apply_pending(iat, h_t.p);
+    spin_sync();
     widen(grads, h_t.p, 3 * (size_t)nw);
   }
   // staged values -> the caller's doubles (complex values stay interleaved re, im)
@@ -1329,11 +1340,9 @@ struct Crowd : CrowdBase
     ensure_row(spin, row);
     launch_spline(spin, MODE_VGL, invRow[spin].p, det[spin].n, phi_vgl.p, rg.p, st);
     join_jastrow();
-    twf_ratio_kernel<T, V><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, rg.p, rg_nparts, ratios_d.p, grads_tmp.p);
+    twf_ratio_kernel<T, V><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, rg.p, rg_nparts, h_d.p, h_t.p); // (pinned host)
     QMCB_LAUNCH_CHECK();
-    QMCB_CUDA(cudaMemcpyAsync(h_d.p, ratios_d.p, (size_t)nw * sizeof(DV), cudaMemcpyDeviceToHost, st));
-    QMCB_CUDA(cudaMemcpyAsync(h_t.p, grads_tmp.p, (size_t)nw * 3 * sizeof(V), cudaMemcpyDeviceToHost, st));
-    sync();
+    spin_sync();
     std::memcpy(ratios, h_d.p, (size_t)nw * sizeof(DV));
     widen(grads, h_t.p, 3 * (size_t)nw);
   }
