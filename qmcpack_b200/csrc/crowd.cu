@@ -1136,9 +1136,18 @@ struct Crowd : CrowdBase
   // pinned staging rotates over 4 slots: every move contains at least one stream sync after its accept call
   // (calc_ratio_grad / eval_grad of the next electron), so a slot is long drained when it comes round again
   int acc_slot = 0;
+  // host-driven trial-wavefunction path: the boundary kernel reads the flags straight from the pinned staging slot
+  // (a few hundred bytes over PCIe inside the kernel instead of a separate copy operation in front of it)
+  const unsigned char* pending_flags = nullptr;
+  void stage_flags(const uint8_t* acc)
+  {
+    unsigned char* h = h_acc.p + (size_t)(acc_slot++ & 3) * cap;
+    std::memcpy(h, acc, nw);
+    pending_flags = h;
+  }
   void upload_flags(const uint8_t* acc)
   {
-    unsigned char* h = h_acc.p + (size_t)(acc_slot++ & 3) * nw;
+    unsigned char* h = h_acc.p + (size_t)(acc_slot++ & 3) * cap;
     std::memcpy(h, acc, nw);
     QMCB_CUDA(cudaMemcpyAsync(accepted.p, h, nw, cudaMemcpyHostToDevice, st));
   }
@@ -1306,8 +1315,7 @@ struct Crowd : CrowdBase
     T* h = reinterpret_cast<T*>(h_t.p + 4 * (size_t)nw); // second half of the staging buffer
     for (int i = 0; i < 3 * nw; ++i)
       h[i] = (T)dsp[i];
-    QMCB_CUDA(cudaMemcpyAsync(displ.p, h, (size_t)nw * 3 * sizeof(T), cudaMemcpyHostToDevice, st));
-    make_move_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, displ.p);
+    make_move_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, h); // (reads the pinned host buffer: no copy launch)
     QMCB_LAUNCH_CHECK();
     if (jas.has_j2 || jas.has_j1)
     {
@@ -1351,7 +1359,7 @@ struct Crowd : CrowdBase
   {
     check_iat(iat);
     flush_pending();
-    upload_flags(acc);
+    stage_flags(acc);
     // deferred: applied together with whatever the driver asks next (normally the gradient of the next electron);
     // asynchronous like the reference's mw_accept_rejectMove ("this call may go asynchronous", TwoBodyJastrow.cpp:661)
     pending_iat = iat;
@@ -1588,15 +1596,16 @@ struct Crowd : CrowdBase
         launch_boundary(drv_host, -1, iat_next, accepted.p, twf_grads_out);
       return;
     }
+    const unsigned char* flags = pending_flags ? pending_flags : accepted.p;
     const int prev = pending_iat, ig = spin_of(prev);
     pending_iat    = -1;
     const bool split = iat_next < 0 || spin_of(iat_next) != ig || delay_count[ig] + 1 == k;
     if (!split)
     {
-      launch_boundary(drv_host, prev, iat_next, accepted.p, twf_grads_out);
+      launch_boundary(drv_host, prev, iat_next, flags, twf_grads_out);
       return;
     }
-    launch_boundary(drv_host, prev, -1, accepted.p, nullptr);
+    launch_boundary(drv_host, prev, -1, flags, nullptr);
     if (delay_count[ig] == k)
       launch_flush(ig);
     if (iat_next >= 0)
