@@ -158,6 +158,11 @@ int qmcb_det_mw_recompute_from_matrices(qmcb_crowd* c, int spin, const void* psi
 int qmcb_det_set_phi_vgl(qmcb_crowd* c, int spin, const void* phi_vgl_host);
 int qmcb_det_mw_ratio_grad_from_phi(qmcb_crowd* c, int spin, int row, void* ratios_host, void* grads_host);
 int qmcb_det_delay_count(qmcb_crowd* c, int spin);
+/* measurement hook for bench.py / scripts: runs `reps` back-to-back DelayedUpdateBatched::mw_updateInvMat launches
+ * (Fermion/DelayedUpdateBatched.h:675-738) of determinant `spin` with `delay_count` pending slots and returns the mean
+ * time of one flush in microseconds (CUDA events on the crowd's stream).  The slots hold whatever the last sweep left, so
+ * the inverse is NOT meaningful afterwards: call qmcb_twf_mw_recompute before using the crowd again.                    */
+int qmcb_det_time_update_inv_mat(qmcb_crowd* c, int spin, int delay_count, int reps, double* us_per_flush);
 
 /* ---- component level: distance rows + two-body Jastrow -------------------------------------------- */
 /* SoaDistanceTableAAOMPTarget::mw_move temp/old rows after qmcb_ps_mw_make_move: [2][nw][4][N] RT (r,dx,dy,dz; new then old) */

@@ -7,6 +7,7 @@
 #include "driver.cuh"
 #include "woodbury.cuh"
 #include "woodbury_tc5.cuh"
+#include "woodbury_dmma.cuh"
 #include <cstdlib>
 #include <type_traits>
 #include <cublas_v2.h>
@@ -993,6 +994,56 @@ struct Crowd : CrowdBase
     if (invrow_id[spin] != row)
       launch_prepare(spin, row, nullptr);
   }
+  template<int KD, int KC, int STAGES>
+  void launch_flush_dmma_as(const DetDev<V>& D, int c)
+  {
+    constexpr size_t smem = wb64::smem_bytes<V, KD, KC, STAGES>();
+    static bool attr_set  = false;
+    if (!attr_set)
+    {
+      QMCB_CUDA(cudaFuncSetAttribute(wb64::woodbury_flush_dmma_kernel<V, KD, KC, STAGES>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    const int n = D.n;
+    // U'[c x n] = Binv[c x c] * V[c x n]  (0.8 MFLOP per walker at a64; the fused kernel reads it back from L2)
+    gemm_batched_kernel<V, false, false><<<dim3(blocks(n, 64), blocks(c, 64), nw), 256, 0, st>>>(
+        c, n, c, V(1), D.Binv, D.k, (size_t)D.k * D.k, D.V, n, (size_t)D.k * n, V(0), D.Up, n, (size_t)D.k * n, nullptr, 0);
+    QMCB_LAUNCH_CHECK();
+    static const int split_env = [] {
+      const char* e = std::getenv("QMCB_DMMA_SPLIT");
+      return e ? std::atoi(e) : 0;
+    }();
+    const int ntiles = (n + wb64::RT - 1) / wb64::RT;
+    const int split  = split_env > 0 ? std::min(split_env, ntiles) : ntiles;
+    wb64::woodbury_flush_dmma_kernel<V, KD, KC, STAGES><<<dim3(nw, split), wb64::TPB, smem, st>>>(D, c);
+    QMCB_LAUNCH_CHECK();
+  }
+  bool launch_flush_dmma(const DetDev<V>& D, int c)
+  {
+    if constexpr (std::is_same<V, double>::value)
+    {
+      if (wb64::eligible<V>(D.n, D.k, c, 32))
+        launch_flush_dmma_as<32, 32, 4>(D, c);
+      else if (wb64::eligible<V>(D.n, D.k, c, 64))
+        launch_flush_dmma_as<64, 32, 4>(D, c);
+      else
+        return false;
+      return true;
+    }
+    else if constexpr (std::is_same<V, cx<double>>::value)
+    {
+      if (wb64::eligible<V>(D.n, D.k, c, 32))
+        launch_flush_dmma_as<32, 16, 4>(D, c);
+      else if (wb64::eligible<V>(D.n, D.k, c, 64))
+        launch_flush_dmma_as<64, 16, 4>(D, c);
+      else
+        return false;
+      return true;
+    }
+    else
+      return false;
+  }
   void launch_flush(int spin)
   {
     const int c = delay_count[spin];
@@ -1044,6 +1095,20 @@ struct Crowd : CrowdBase
         invrow_id[spin]   = -1;
         return;
       }
+      }
+    }
+    if constexpr (std::is_same<V, double>::value || std::is_same<V, cx<double>>::value)
+    {
+      // full precision: one pass over Ainv on the FP64 tensor pipe (woodbury_dmma.cuh); QMCB_FLUSH=simt keeps the GEMMs
+      static const bool use_dmma = [] {
+        const char* e = std::getenv("QMCB_FLUSH");
+        return !e || std::string(e) != "simt";
+      }();
+      if (use_dmma && launch_flush_dmma(D, c))
+      {
+        delay_count[spin] = 0;
+        invrow_id[spin]   = -1;
+        return;
       }
     }
     // tempMat[n x c] = Ainv[n x n] * U^T, with the -1 fix-up (applyW) fused
@@ -1174,6 +1239,31 @@ struct Crowd : CrowdBase
     sync();
   }
   int det_delay_count(int spin) override { return delay_count[spin]; }
+  // measurement hook: `reps` back-to-back mw_updateInvMat launches with `c` pending slots, CUDA events on the crowd stream
+  void det_time_update_inv_mat(int spin, int c, int reps, double* us_per_call) override
+  {
+    flush_pending();
+    if (c < 1 || c > k || reps < 1)
+      throw std::runtime_error("det_time_update_inv_mat: need 1 <= delay_count <= delay_rank and reps >= 1");
+    cudaEvent_t e0, e1;
+    QMCB_CUDA(cudaEventCreate(&e0));
+    QMCB_CUDA(cudaEventCreate(&e1));
+    delay_count[spin] = c;
+    launch_flush(spin); // warm-up (first-use attribute calls, instruction cache)
+    QMCB_CUDA(cudaEventRecord(e0, st));
+    for (int i = 0; i < reps; ++i)
+    {
+      delay_count[spin] = c;
+      launch_flush(spin);
+    }
+    QMCB_CUDA(cudaEventRecord(e1, st));
+    QMCB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    QMCB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *us_per_call = 1e3 * ms / reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
   void det_set_phi_vgl(int spin, const void* phi) override
   {
     const int n = nel[spin];

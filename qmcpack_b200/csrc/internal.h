@@ -64,6 +64,7 @@ struct CrowdBase
   virtual void det_recompute_from_matrices(int spin, const void* psiM, const void* dpsiM, const void* d2psiM) = 0;
   virtual void det_set_phi_vgl(int spin, const void* phi)                                                   = 0;
   virtual int det_delay_count(int spin)                                                                     = 0;
+  virtual void det_time_update_inv_mat(int spin, int c, int reps, double* us_per_call)                      = 0;
   virtual void dtaa_get_temp_rows(void* rows)                                                               = 0;
   virtual void j2_ratio_grad(int iat, double* ratios, void* grads)                                          = 0;
   virtual void j2_accept_reject(int iat, const uint8_t* acc)                                                = 0;

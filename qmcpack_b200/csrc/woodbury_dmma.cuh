@@ -1,0 +1,361 @@
+// qmcpack_b200/csrc/woodbury_dmma.cuh -- rank-k Woodbury flush in FULL precision on the FP64 tensor pipe (sm_100a).
+//
+// Same contraction as woodbury.cuh / woodbury_tc5.cuh (DelayedUpdateBatched::mw_updateInvMat,
+// Fermion/DelayedUpdateBatched.h:675-738; CPU form Fermion/DelayedUpdate.h:145-217), for double and complex<double>
+// inverses (the reference's full-precision and QMC_COMPLEX builds, the NiO-a128 class):
+//     T[m][a]  = sum_j Ainv[m][j] U[a][j]  - (m == list[a])        (n x c)
+//     U'[a][j] = sum_b Binv[a][b] V[b][j]                           (c x n)   <- small SIMT GEMM, launched before
+//     Ainv[m][j] -= sum_a T[m][a] U'[a][j]
+// The reference streams Ainv three times through cuBLAS gemmBatched.  Here ONE pass with mma.sync.m8n8k4.f64 (SASS DMMA):
+//   * a CTA (8 warps) owns 64-row tiles of one walker's Ainv.  The tile itself is never staged in shared memory: the A
+//     fragments of the first product (8 rows x 4 consecutive columns per warp load = full 32-byte sectors) go from global
+//     memory straight into registers one K chunk ahead, and in the second product the tile is the ACCUMULATOR, loaded
+//     from L2 one chunk ahead and stored back from the fragments (64-byte row segments).
+//   * U and U' stream through a cp.async ring of K chunks (STAGES deep) as one continuous sequence over both products and
+//     all tiles of the CTA, so the pipeline never drains between the products; one __syncthreads per chunk.
+//   * warp w owns rows 8w..8w+7 of the tile in the first product (all KD slots: one A fragment feeds KD/8 DMMAs) and
+//     writes -T, with the `-1` fix-up of applyW_batched, to shared memory; in the second product a warp owns a
+//     16 x (KC/2) block (2 row tiles x KC/16 column tiles).
+//   * complex: every thread holds the (re, im) pair of its fragment element, so one complex product is four DMMAs on the
+//     same fragment layout (re*re, -im*im -> real accumulator; re*im, im*re -> imaginary accumulator); plain (unconjugated)
+//     products exactly as the reference's gemm('T','N').
+// Shared-memory row strides are chosen so that every fragment load is bank-conflict free (64-bit accesses are served per
+// half warp, 128-bit accesses per quarter warp).
+#pragma once
+#include "common.cuh"
+#include "det.cuh"
+
+namespace qmcb
+{
+#ifdef __CUDACC__
+namespace wb64
+{
+constexpr int RT  = 64;  // Ainv rows per tile (8 warps x 8 rows)
+constexpr int TPB = 256;
+
+__device__ __forceinline__ void dmma(double (&d)[2], const double a, const double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d[0]), "+d"(d[1])
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// one 8 x 8 accumulator tile of the m8n8k4 shape: the thread (g = lane / 4, t = lane % 4) holds (g, 2t) and (g, 2t + 1)
+template<typename V>
+struct Acc;
+template<>
+struct Acc<double>
+{
+  double d[2];
+  __device__ __forceinline__ void zero() { d[0] = d[1] = 0.0; }
+  __device__ __forceinline__ void mma(const double a, const double b) { dmma(d, a, b); }
+  __device__ __forceinline__ double get(int i) const { return d[i]; }
+  __device__ __forceinline__ void set(int i, const double v) { d[i] = v; }
+};
+template<>
+struct Acc<cx<double>>
+{
+  double re[2], im[2];
+  __device__ __forceinline__ void zero() { re[0] = re[1] = im[0] = im[1] = 0.0; }
+  __device__ __forceinline__ void mma(const cx<double>& a, const cx<double>& b)
+  {
+    dmma(re, a.re, b.re);
+    dmma(re, -a.im, b.im);
+    dmma(im, a.re, b.im);
+    dmma(im, a.im, b.re);
+  }
+  __device__ __forceinline__ cx<double> get(int i) const { return cx<double>(re[i], im[i]); }
+  __device__ __forceinline__ void set(int i, const cx<double>& v)
+  {
+    re[i] = v.re;
+    im[i] = v.im;
+  }
+};
+
+template<typename V>
+__device__ __forceinline__ V zero_v();
+template<>
+__device__ __forceinline__ double zero_v<double>()
+{
+  return 0.0;
+}
+template<>
+__device__ __forceinline__ cx<double> zero_v<cx<double>>()
+{
+  return cx<double>(0.0, 0.0);
+}
+__device__ __forceinline__ double ldg_v(const double* p) { return __ldg(p); }
+__device__ __forceinline__ cx<double> ldg_v(const cx<double>* p)
+{
+  const double2 v = *reinterpret_cast<const double2*>(p);
+  return cx<double>(v.x, v.y);
+}
+__device__ __forceinline__ double lds_v(const double* p) { return *p; }
+__device__ __forceinline__ cx<double> lds_v(const cx<double>* p)
+{
+  const double2 v = *reinterpret_cast<const double2*>(p);
+  return cx<double>(v.x, v.y);
+}
+
+template<typename V>
+struct Cfg
+{
+  static constexpr bool CPLX = value_traits<V>::is_complex;
+  static constexpr int EPP   = CPLX ? 1 : 2; // elements per 16-byte cp.async piece
+  // row strides (in elements) of the shared-memory chunks; see the header comment
+  __host__ __device__ static constexpr int su(int KC) { return KC + 4; }                // A-type access  M[g][t]
+  __host__ __device__ static constexpr int sp(int KC) { return CPLX ? KC + 2 : KC + 4; } // B-type access  M[t][g]
+  __host__ __device__ static constexpr int st(int KD) { return KD + 4; }                // -T, A-type access
+};
+
+template<typename V, int KD, int KC, int STAGES>
+constexpr size_t smem_bytes()
+{
+  return sizeof(V) * ((size_t)STAGES * KD * Cfg<V>::su(KC) + (size_t)RT * Cfg<V>::st(KD)) + KD * sizeof(int);
+}
+
+// real: rows of U, U' (stride n) must be 16-byte aligned for cp.async, i.e. n even
+template<typename V>
+inline bool eligible(int n, int k, int c, int KD)
+{
+  return k <= KD && c <= KD && n >= 8 && (value_traits<V>::is_complex || n % 2 == 0);
+}
+
+// grid = (nw, S): CTA (iw, s) updates row tiles s, s+S, ... of walker iw.  c <= KD pending delays; D.Up holds U' = Binv*V.
+template<typename V, int KD, int KC, int STAGES>
+__global__ void __launch_bounds__(TPB, value_traits<V>::is_complex ? 1 : 2)
+    woodbury_flush_dmma_kernel(const DetDev<V> D, const int c)
+{
+  using C = Cfg<V>;
+  static_assert(KC % 16 == 0 && KD % 8 == 0, "chunk shapes");
+  constexpr int SU = C::su(KC), SP = C::sp(KC), ST = C::st(KD);
+  constexpr int STAGE_ELEMS = KD * SU; // SP <= SU
+  constexpr int NT1 = KD / 8;          // slot tiles of the first product
+  constexpr int KS1 = KC / 4;          // k-steps per chunk, first product
+  constexpr int KS2 = KD / 4;          // k-steps, second product
+  constexpr int JT  = KC / 16;         // column tiles per warp and chunk, second product
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  V* ring  = reinterpret_cast<V*>(smem_raw);
+  V* Ts    = ring + (size_t)STAGES * STAGE_ELEMS;
+  int* lst = reinterpret_cast<int*>(Ts + (size_t)RT * ST);
+
+  const int n = D.n, lda = D.lda, k = D.k;
+  const int iw = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const V* U  = D.U + (size_t)iw * k * n;
+  const V* Up = D.Up + (size_t)iw * k * n;
+  V* Ainv     = D.Ainv + (size_t)iw * n * lda;
+  const int ntiles = (n + RT - 1) / RT;
+  const int nch    = (n + KC - 1) / KC;
+  const int niter  = (int)blockIdx.y < ntiles ? (ntiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y : 0;
+  const int total  = niter * 2 * nch;
+  if (total == 0)
+    return;
+  if (tid == 0)
+  {
+    const int m0 = blockIdx.y * RT;
+    prefetch_l2_bulk(Ainv + (size_t)m0 * lda, (unsigned)(min(RT, n - m0) * lda * sizeof(V)));
+  }
+  if (tid < KD)
+    lst[tid] = tid < c ? D.list[(size_t)iw * k + tid] : -1;
+
+  // chunk s of the stream: first product chunks (U columns) then second product chunks (U' columns) of every tile
+  auto stage = [&](const int s) {
+    const int q     = s % (2 * nch);
+    const bool sec  = q >= nch;
+    const int col0  = (sec ? q - nch : q) * KC;
+    const V* src    = sec ? Up : U;
+    const int ss    = sec ? SP : SU;
+    V* dst          = ring + (size_t)(s % STAGES) * STAGE_ELEMS;
+    constexpr int P = KC / C::EPP; // pieces per row
+    for (int e = tid; e < KD * P; e += TPB)
+    {
+      const int a = e / P, j = (e - a * P) * C::EPP;
+      V* d = dst + a * ss + j;
+      if (a < c && col0 + j < n)
+        cp_async16(d, src + (size_t)a * n + col0 + j);
+      else
+        *reinterpret_cast<double2*>(d) = make_double2(0.0, 0.0);
+    }
+  };
+
+  // A fragments of the first product for chunk q of the tile starting at row m0: element (m0 + 8*warp + g, q*KC + 4*ks + t)
+  V anext[KS1];
+  auto load_a = [&](const int m0, const int q) {
+    const int row = m0 + warp * 8 + g;
+    const V* p    = Ainv + (size_t)row * lda + q * KC + t;
+#pragma unroll
+    for (int ks = 0; ks < KS1; ++ks)
+      anext[ks] = (row < n && q * KC + ks * 4 + t < n) ? ldg_v(p + ks * 4) : zero_v<V>();
+  };
+  // accumulator fragments of the second product: warp block = row tiles 2*rp + {0,1}, column tiles cp*JT + {0..JT-1}
+  const int rp = warp & 3, cp = warp >> 2;
+  V cnext[2][JT][2];
+  auto load_c = [&](const int m0, const int j0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < JT; ++j)
+      {
+        const int row = m0 + (2 * rp + i) * 8 + g, col = j0 + (cp * JT + j) * 8 + 2 * t;
+        const V* p    = Ainv + (size_t)row * lda + col;
+        if (row < n && col + 1 < n)
+        {
+          if constexpr (C::CPLX)
+          {
+            cnext[i][j][0] = lds_v(p);
+            cnext[i][j][1] = lds_v(p + 1);
+          }
+          else
+          {
+            const double2 v = *reinterpret_cast<const double2*>(p);
+            cnext[i][j][0]  = v.x;
+            cnext[i][j][1]  = v.y;
+          }
+        }
+        else
+        {
+          cnext[i][j][0] = (row < n && col < n) ? lds_v(p) : zero_v<V>();
+          cnext[i][j][1] = zero_v<V>();
+        }
+      }
+  };
+
+  for (int s = 0; s < STAGES - 1; ++s)
+  {
+    if (s < total)
+      stage(s);
+    cp_async_commit();
+  }
+  load_a(blockIdx.y * RT, 0);
+
+  Acc<V> acc1[NT1];
+  for (int s = 0; s < total; ++s)
+  {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    if (s + STAGES - 1 < total)
+      stage(s + STAGES - 1);
+    cp_async_commit();
+
+    const int it = s / (2 * nch), q = s - it * 2 * nch;
+    const int m0 = ((int)blockIdx.y + it * (int)gridDim.y) * RT;
+    const V* buf = ring + (size_t)(s % STAGES) * STAGE_ELEMS;
+    if (q < nch)
+    {
+      // ---- first product: -T[8 rows of this warp][KD] accumulates over the K chunk
+      V acur[KS1];
+#pragma unroll
+      for (int ks = 0; ks < KS1; ++ks)
+        acur[ks] = anext[ks];
+      if (q == 0)
+      {
+#pragma unroll
+        for (int nt = 0; nt < NT1; ++nt)
+          acc1[nt].zero();
+        const int m0n = m0 + (int)gridDim.y * RT;
+        if (tid == 0 && m0n < n)
+          prefetch_l2_bulk(Ainv + (size_t)m0n * lda, (unsigned)(min(RT, n - m0n) * lda * sizeof(V)));
+      }
+      if (q + 1 < nch)
+        load_a(m0, q + 1);
+      else
+        load_c(m0, 0);
+#pragma unroll
+      for (int ks = 0; ks < KS1; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < NT1; ++nt)
+          acc1[nt].mma(acur[ks], lds_v(buf + (nt * 8 + g) * SU + ks * 4 + t));
+      if (q == nch - 1)
+      {
+        // store -T with the applyW fix-up ( T[list[a]][a] -= 1  ->  (-T) += 1 ); pseudo-accepted slots carry -1
+        const int row = m0 + warp * 8 + g;
+#pragma unroll
+        for (int nt = 0; nt < NT1; ++nt)
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+          {
+            const int a = nt * 8 + 2 * t + i;
+            V v         = -acc1[nt].get(i);
+            if (lst[a] == row)
+              v += V(1.0);
+            Ts[(warp * 8 + g) * ST + a] = v;
+          }
+      }
+    }
+    else
+    {
+      // ---- second product: tile[:, chunk] += (-T) * U'[:, chunk]
+      const int j0 = (q - nch) * KC;
+      Acc<V> acc[2][JT];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < JT; ++j)
+        {
+          acc[i][j].set(0, cnext[i][j][0]);
+          acc[i][j].set(1, cnext[i][j][1]);
+        }
+      if (q + 1 < 2 * nch)
+        load_c(m0, j0 + KC);
+      else if (it + 1 < niter)
+        load_a(m0 + (int)gridDim.y * RT, 0);
+#pragma unroll
+      for (int ks = 0; ks < KS2; ++ks)
+      {
+        V a[2], b[JT];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          a[i] = lds_v(Ts + ((2 * rp + i) * 8 + g) * ST + ks * 4 + t);
+#pragma unroll
+        for (int j = 0; j < JT; ++j)
+          b[j] = lds_v(buf + (ks * 4 + t) * SP + (cp * JT + j) * 8 + g);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < JT; ++j)
+            acc[i][j].mma(a[i], b[j]);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < JT; ++j)
+        {
+          const int row = m0 + (2 * rp + i) * 8 + g, col = j0 + (cp * JT + j) * 8 + 2 * t;
+          V* p          = Ainv + (size_t)row * lda + col;
+          if (row < n && col + 1 < n)
+          {
+            if constexpr (C::CPLX)
+            {
+              const cx<double> v0 = acc[i][j].get(0), v1 = acc[i][j].get(1);
+              reinterpret_cast<double2*>(p)[0] = make_double2(v0.re, v0.im);
+              reinterpret_cast<double2*>(p)[1] = make_double2(v1.re, v1.im);
+            }
+            else
+              *reinterpret_cast<double2*>(p) = make_double2(acc[i][j].get(0), acc[i][j].get(1));
+          }
+          else if (row < n && col < n)
+            p[0] = acc[i][j].get(0);
+        }
+    }
+  }
+  cp_async_wait<0>();
+}
+} // namespace wb64
+#endif
+} // namespace qmcb
