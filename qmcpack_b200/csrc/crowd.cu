@@ -1007,8 +1007,7 @@ struct Crowd : CrowdBase
     }
     const int n = D.n;
     // U'[c x n] = Binv[c x c] * V[c x n]  (0.8 MFLOP per walker at a64; the fused kernel reads it back from L2)
-    gemm_batched_kernel<V, false, false><<<dim3(blocks(n, 64), blocks(c, 64), nw), 256, 0, st>>>(
-        c, n, c, V(1), D.Binv, D.k, (size_t)D.k * D.k, D.V, n, (size_t)D.k * n, V(0), D.Up, n, (size_t)D.k * n, nullptr, 0);
+    wb64::binv_v_kernel<V><<<dim3(blocks(n, 128), nw, blocks(c, 8)), 128, 0, st>>>(D, c);
     QMCB_LAUNCH_CHECK();
     static const int split_env = [] {
       const char* e = std::getenv("QMCB_DMMA_SPLIT");
@@ -1016,7 +1015,7 @@ struct Crowd : CrowdBase
     }();
     const int ntiles = (n + wb64::RT - 1) / wb64::RT;
     const int split  = split_env > 0 ? std::min(split_env, ntiles) : ntiles;
-    wb64::woodbury_flush_dmma_kernel<V, KD, KC, STAGES><<<dim3(nw, split), wb64::TPB, smem, st>>>(D, c);
+    wb64::woodbury_flush_dmma_kernel<V, KD, KC, STAGES><<<dim3(split, nw), wb64::TPB, smem, st>>>(D, c);
     QMCB_LAUNCH_CHECK();
   }
   bool launch_flush_dmma(const DetDev<V>& D, int c)

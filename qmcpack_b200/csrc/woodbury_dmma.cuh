@@ -50,9 +50,47 @@ __device__ __forceinline__ void cp_async_wait()
 {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes)
+
+// L2 eviction policies: the tile is read twice (A operand of the first product, accumulator of the second) about twelve
+// chunk steps apart with ~50 MB of other traffic in between -- ncu showed the second read going back to DRAM.  The first
+// read marks the lines evict_last, the second read and the write-back mark them evict_first.
+__device__ __forceinline__ uint64_t policy_evict_last()
 {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double ld_hint(const double* p, const uint64_t pol)
+{
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ cx<double> ld_hint(const cx<double>* p, const uint64_t pol)
+{
+  double x, y;
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(x), "=d"(y) : "l"(p), "l"(pol));
+  return cx<double>(x, y);
+}
+__device__ __forceinline__ double2 ld_hint2(const double* p, const uint64_t pol)
+{
+  double2 v;
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_hint2(double* p, const double x, const double y, const uint64_t pol)
+{
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(x), "d"(y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_bulk_hint(const void* p, unsigned bytes, const uint64_t pol)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(pol) : "memory");
 }
 
 // one 8 x 8 accumulator tile of the m8n8k4 shape: the thread (g = lane / 4, t = lane % 4) holds (g, 2t) and (g, 2t + 1)
@@ -99,12 +137,6 @@ __device__ __forceinline__ cx<double> zero_v<cx<double>>()
 {
   return cx<double>(0.0, 0.0);
 }
-__device__ __forceinline__ double ldg_v(const double* p) { return __ldg(p); }
-__device__ __forceinline__ cx<double> ldg_v(const cx<double>* p)
-{
-  const double2 v = *reinterpret_cast<const double2*>(p);
-  return cx<double>(v.x, v.y);
-}
 __device__ __forceinline__ double lds_v(const double* p) { return *p; }
 __device__ __forceinline__ cx<double> lds_v(const cx<double>* p)
 {
@@ -129,6 +161,45 @@ constexpr size_t smem_bytes()
   return sizeof(V) * ((size_t)STAGES * KD * Cfg<V>::su(KC) + (size_t)RT * Cfg<V>::st(KD)) + KD * sizeof(int);
 }
 
+// U'[a][j] = sum_b Binv[a][b] V[b][j]  (c x n, K = c): one thread per column j and block of eight slots a
+// (grid = (ceil(n / 128), nw, ceil(c / 8)), 128 threads); the eight Binv rows sit transposed in shared memory so that the
+// factors of one b are broadcast 16-byte loads; V is read coalesced, eight loads in flight per thread.
+// 0.8 MFLOP per walker at a64: this kernel only has to stay out of the way.
+template<typename V>
+__global__ void __launch_bounds__(128) binv_v_kernel(const DetDev<V> D, const int c)
+{
+  __shared__ __align__(16) V Bt[64 * 8]; // Bt[b][q] = Binv[a0 + q][b]
+  const int n = D.n, k = D.k, iw = blockIdx.y, a0 = blockIdx.z * 8;
+  const V* B = D.Binv + (size_t)iw * k * k;
+  for (int e = threadIdx.x; e < 8 * c; e += blockDim.x)
+  {
+    const int q = e / c, b = e - q * c;
+    Bt[b * 8 + q] = a0 + q < c ? B[(size_t)(a0 + q) * k + b] : zero_v<V>();
+  }
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n)
+    return;
+  const V* Vw = D.V + (size_t)iw * k * n + j;
+  V* Uw       = D.Up + (size_t)iw * k * n + j;
+  V acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    acc[q] = zero_v<V>();
+#pragma unroll 8
+  for (int b = 0; b < c; ++b)
+  {
+    const V v = Vw[(size_t)b * n];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      acc[q] += Bt[b * 8 + q] * v;
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (a0 + q < c)
+      Uw[(size_t)(a0 + q) * n] = acc[q];
+}
+
 // real: rows of U, U' (stride n) must be 16-byte aligned for cp.async, i.e. n even
 template<typename V>
 inline bool eligible(int n, int k, int c, int KD)
@@ -136,7 +207,8 @@ inline bool eligible(int n, int k, int c, int KD)
   return k <= KD && c <= KD && n >= 8 && (value_traits<V>::is_complex || n % 2 == 0);
 }
 
-// grid = (nw, S): CTA (iw, s) updates row tiles s, s+S, ... of walker iw.  c <= KD pending delays; D.Up holds U' = Binv*V.
+// grid = (S, nw): CTA (s, iw) updates row tiles s, s+S, ... of walker iw (tile index fastest, so that the CTAs resident at
+// any time belong to few walkers and share their U, U' chunks in L2).  c <= KD pending delays; D.Up holds U' = Binv*V.
 template<typename V, int KD, int KC, int STAGES>
 __global__ void __launch_bounds__(TPB, value_traits<V>::is_complex ? 1 : 2)
     woodbury_flush_dmma_kernel(const DetDev<V> D, const int c)
@@ -155,21 +227,22 @@ __global__ void __launch_bounds__(TPB, value_traits<V>::is_complex ? 1 : 2)
   int* lst = reinterpret_cast<int*>(Ts + (size_t)RT * ST);
 
   const int n = D.n, lda = D.lda, k = D.k;
-  const int iw = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int iw = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const V* U  = D.U + (size_t)iw * k * n;
   const V* Up = D.Up + (size_t)iw * k * n;
   V* Ainv     = D.Ainv + (size_t)iw * n * lda;
   const int ntiles = (n + RT - 1) / RT;
   const int nch    = (n + KC - 1) / KC;
-  const int niter  = (int)blockIdx.y < ntiles ? (ntiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y : 0;
+  const int niter  = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int total  = niter * 2 * nch;
   if (total == 0)
     return;
+  const uint64_t pol_keep = policy_evict_last(), pol_drop = policy_evict_first();
   if (tid == 0)
   {
-    const int m0 = blockIdx.y * RT;
-    prefetch_l2_bulk(Ainv + (size_t)m0 * lda, (unsigned)(min(RT, n - m0) * lda * sizeof(V)));
+    const int m0 = blockIdx.x * RT;
+    prefetch_l2_bulk_hint(Ainv + (size_t)m0 * lda, (unsigned)(min(RT, n - m0) * lda * sizeof(V)), pol_keep);
   }
   if (tid < KD)
     lst[tid] = tid < c ? D.list[(size_t)iw * k + tid] : -1;
@@ -201,7 +274,7 @@ __global__ void __launch_bounds__(TPB, value_traits<V>::is_complex ? 1 : 2)
     const V* p    = Ainv + (size_t)row * lda + q * KC + t;
 #pragma unroll
     for (int ks = 0; ks < KS1; ++ks)
-      anext[ks] = (row < n && q * KC + ks * 4 + t < n) ? ldg_v(p + ks * 4) : zero_v<V>();
+      anext[ks] = (row < n && q * KC + ks * 4 + t < n) ? ld_hint(p + ks * 4, pol_keep) : zero_v<V>();
   };
   // accumulator fragments of the second product: warp block = row tiles 2*rp + {0,1}, column tiles cp*JT + {0..JT-1}
   const int rp = warp & 3, cp = warp >> 2;
@@ -218,12 +291,12 @@ __global__ void __launch_bounds__(TPB, value_traits<V>::is_complex ? 1 : 2)
         {
           if constexpr (C::CPLX)
           {
-            cnext[i][j][0] = lds_v(p);
-            cnext[i][j][1] = lds_v(p + 1);
+            cnext[i][j][0] = ld_hint(p, pol_drop);
+            cnext[i][j][1] = ld_hint(p + 1, pol_drop);
           }
           else
           {
-            const double2 v = *reinterpret_cast<const double2*>(p);
+            const double2 v = ld_hint2(p, pol_drop);
             cnext[i][j][0]  = v.x;
             cnext[i][j][1]  = v.y;
           }
@@ -242,7 +315,7 @@ __global__ void __launch_bounds__(TPB, value_traits<V>::is_complex ? 1 : 2)
       stage(s);
     cp_async_commit();
   }
-  load_a(blockIdx.y * RT, 0);
+  load_a(blockIdx.x * RT, 0);
 
   Acc<V> acc1[NT1];
   for (int s = 0; s < total; ++s)
@@ -254,7 +327,7 @@ __global__ void __launch_bounds__(TPB, value_traits<V>::is_complex ? 1 : 2)
     cp_async_commit();
 
     const int it = s / (2 * nch), q = s - it * 2 * nch;
-    const int m0 = ((int)blockIdx.y + it * (int)gridDim.y) * RT;
+    const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * RT;
     const V* buf = ring + (size_t)(s % STAGES) * STAGE_ELEMS;
     if (q < nch)
     {
@@ -268,9 +341,9 @@ __global__ void __launch_bounds__(TPB, value_traits<V>::is_complex ? 1 : 2)
 #pragma unroll
         for (int nt = 0; nt < NT1; ++nt)
           acc1[nt].zero();
-        const int m0n = m0 + (int)gridDim.y * RT;
+        const int m0n = m0 + (int)gridDim.x * RT;
         if (tid == 0 && m0n < n)
-          prefetch_l2_bulk(Ainv + (size_t)m0n * lda, (unsigned)(min(RT, n - m0n) * lda * sizeof(V)));
+          prefetch_l2_bulk_hint(Ainv + (size_t)m0n * lda, (unsigned)(min(RT, n - m0n) * lda * sizeof(V)), pol_keep);
       }
       if (q + 1 < nch)
         load_a(m0, q + 1);
@@ -314,7 +387,7 @@ __global__ void __launch_bounds__(TPB, value_traits<V>::is_complex ? 1 : 2)
       if (q + 1 < 2 * nch)
         load_c(m0, j0 + KC);
       else if (it + 1 < niter)
-        load_a(m0 + (int)gridDim.y * RT, 0);
+        load_a(m0 + (int)gridDim.x * RT, 0);
 #pragma unroll
       for (int ks = 0; ks < KS2; ++ks)
       {
@@ -343,11 +416,11 @@ __global__ void __launch_bounds__(TPB, value_traits<V>::is_complex ? 1 : 2)
             if constexpr (C::CPLX)
             {
               const cx<double> v0 = acc[i][j].get(0), v1 = acc[i][j].get(1);
-              reinterpret_cast<double2*>(p)[0] = make_double2(v0.re, v0.im);
-              reinterpret_cast<double2*>(p)[1] = make_double2(v1.re, v1.im);
+              st_hint2(reinterpret_cast<double*>(p), v0.re, v0.im, pol_drop);
+              st_hint2(reinterpret_cast<double*>(p + 1), v1.re, v1.im, pol_drop);
             }
             else
-              *reinterpret_cast<double2*>(p) = make_double2(acc[i][j].get(0), acc[i][j].get(1));
+              st_hint2(p, acc[i][j].get(0), acc[i][j].get(1), pol_drop);
           }
           else if (row < n && col < n)
             p[0] = acc[i][j].get(0);
