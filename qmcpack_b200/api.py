@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libqmcb.so")
+LIB_PATH = os.environ.get("QMCB_LIB") or os.path.join(HERE, "libqmcb.so")  # QMCB_LIB: tuning variants (scripts/)
 FULL, MIXED = 0, 1
 R2R, C2C = 0, 1
 

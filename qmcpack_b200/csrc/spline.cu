@@ -35,7 +35,12 @@ struct Shape;
 template<>
 struct Shape<float, false>
 {
-  static constexpr int TILE = 192, STAGES = 2, VEC = 1, MINB = 2;
+#ifndef QMCB_SPL_TILE // tuning experiments: -DQMCB_SPL_TILE=.. -DQMCB_SPL_STAGES=.. -DQMCB_SPL_MINB=..
+#define QMCB_SPL_TILE 192
+#define QMCB_SPL_STAGES 2
+#define QMCB_SPL_MINB 2
+#endif
+  static constexpr int TILE = QMCB_SPL_TILE, STAGES = QMCB_SPL_STAGES, VEC = 1, MINB = QMCB_SPL_MINB;
 }; // 48 KB / stage, 2 CTAs/SM
 template<>
 struct Shape<double, false>

@@ -214,13 +214,37 @@ __device__ __forceinline__ void locate(const SplineDev<ST>& S, const ST ru[3], i
     get_spline_bound<ST>((double)ru[d] * S.delta_inv[d], S.M[d] - 1, ind[d], t[d]);
 }
 
+// per-stage unit header written by the producer warp (in ST): pre[16][8] = for every (i, j) the prefactor products
+// {d2a_i b_j, da_i b_j, da_i db_j, a_i db_j, a_i d2b_j, a_i b_j, 0, 0}, then c[4], dc[4], d2c[4], then the bc sign (int)
+constexpr int SPL_HDR     = 16 * 8 + 16;
+constexpr int SPL_HDR_C   = 16 * 8;      // offset of c, dc, d2c
+constexpr int SPL_HDR_SGN = 16 * 8 + 12; // offset of the sign word
+constexpr int SPL_SCRATCH = 36;          // producer scratch: a, da, d2a, b, db, d2b, c, dc, d2c
+
 template<typename ST, int TILE, int STAGES, int VEC>
 struct SplineSmem
 {
   static constexpr int ROWS        = 64;
   static constexpr size_t STAGE_B  = (size_t)ROWS * TILE * sizeof(ST);
-  static constexpr size_t BYTES    = STAGES * STAGE_B + 2 * STAGES * sizeof(uint64_t) + 64;
+  static constexpr size_t BAR_OFF  = STAGES * STAGE_B;
+  static constexpr size_t HDR_OFF  = BAR_OFF + ((2 * STAGES * sizeof(uint64_t) + 15) / 16) * 16;
+  static constexpr size_t BYTES    = HDR_OFF + (STAGES * SPL_HDR + SPL_SCRATCH + 4) * sizeof(ST) + 64;
 };
+
+template<typename ST>
+__device__ __forceinline__ void load4(const ST* p, ST (&o)[4]);
+template<>
+__device__ __forceinline__ void load4<float>(const float* p, float (&o)[4])
+{
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x, o[1] = v.y, o[2] = v.z, o[3] = v.w;
+}
+template<>
+__device__ __forceinline__ void load4<double>(const double* p, double (&o)[4])
+{
+  const double2 v0 = reinterpret_cast<const double2*>(p)[0], v1 = reinterpret_cast<const double2*>(p)[1];
+  o[0] = v0.x, o[1] = v0.y, o[2] = v1.x, o[3] = v1.y;
+}
 
 // MODE: SplineMode.  C2C: complex orbitals from pairs of components (VEC == 2), otherwise VEC == 1.
 template<typename ST, typename RT, int TILE, int STAGES, int VEC, int MODE, bool C2C, int MINB>
@@ -233,8 +257,10 @@ __global__ void __launch_bounds__(TILE / VEC + 32, MINB)
   constexpr int NRED  = C2C ? 8 : 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ST* stage_base     = reinterpret_cast<ST*>(smem_raw);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * ROWS * TILE * sizeof(ST));
+  using SM = SplineSmem<ST, TILE, STAGES, VEC>;
+  uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem_raw + SM::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
+  ST* hdr_base        = reinterpret_cast<ST*>(smem_raw + SM::HDR_OFF);
 
   const int tid       = threadIdx.x;
   const int nunits    = A.nw * ntiles;
@@ -258,25 +284,87 @@ __global__ void __launch_bounds__(TILE / VEC + 32, MINB)
 
   if (producer)
   {
-    // ===== producer warp: ONE tensor-TMA request per unit, issued by one elected lane =====
-    if (tid == NCONS)
-    {
+    // ===== producer warp: everything that is uniform over the unit -- cell location, the 36 basis values and the 96
+    // prefactor products -- is computed ONCE here (spread over the lanes) instead of by every consumer thread, parked
+    // in the stage's header, and the stencil is requested with ONE tensor-TMA request issued by lane 0.  The
+    // arithmetic is the consumers' former prologue verbatim, so results are bit-identical.
+    const int pl = tid - NCONS;
+    ST* scratch  = hdr_base + STAGES * SPL_HDR;
+    if (pl == 0)
       ptx::prefetch_tensormap(&tmap);
-      int q = 0;
-      for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++q)
+    int q = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++q)
+    {
+      const int stage   = q % STAGES;
+      const unsigned ph = (q / STAGES) & 1;
+      const int iw = u / ntiles, tile = u - iw * ntiles;
+      ST ru[3];
+      const int bc_sign = convert_pos<ST, RT>(S, A.r + 3 * (size_t)iw, ru);
+      int my_ind        = 0;
+      if (pl < 3)
       {
-        const int stage   = q % STAGES;
-        const unsigned ph = (q / STAGES) & 1;
-        const int iw = u / ntiles, tile = u - iw * ntiles;
-        ST ru[3], t[3];
-        int ind[3];
-        convert_pos<ST, RT>(S, A.r + 3 * (size_t)iw, ru);
-        locate(S, ru, ind, t);
-        ptx::mbar_wait(&empty_bar[stage], ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], (unsigned)(ROWS * TILE * sizeof(ST)));
-        ptx::tma_load_4d(stage_base + (size_t)stage * ROWS * TILE, &tmap, tile * TILE, ind[2], ind[1], ind[0],
-                         &full_bar[stage]);
+        const ST rud     = pl == 0 ? ru[0] : (pl == 1 ? ru[1] : ru[2]);
+        const double di  = pl == 0 ? S.delta_inv[0] : (pl == 1 ? S.delta_inv[1] : S.delta_inv[2]);
+        const int nmax   = (pl == 0 ? S.M[0] : (pl == 1 ? S.M[1] : S.M[2])) - 1;
+        ST t, p0[4], p1[4], p2[4];
+        get_spline_bound<ST>((double)rud * di, nmax, my_ind, t);
+        prefactors(p0, p1, p2, t);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+        {
+          scratch[pl * 12 + e]     = p0[e];
+          scratch[pl * 12 + 4 + e] = p1[e];
+          scratch[pl * 12 + 8 + e] = p2[e];
+        }
       }
+      __syncwarp();
+      const int i0 = __shfl_sync(0xffffffffu, my_ind, 0), i1 = __shfl_sync(0xffffffffu, my_ind, 1),
+                i2 = __shfl_sync(0xffffffffu, my_ind, 2);
+      ST o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        o[e] = ST(0);
+      if (pl < 16)
+      {
+        const int i = pl >> 2, j = pl & 3;
+        const ST ai = scratch[i], dai = scratch[4 + i], d2ai = scratch[8 + i];
+        const ST bj = scratch[12 + j], dbj = scratch[16 + j], d2bj = scratch[20 + j];
+        o[0] = d2ai * bj; // pre20
+        o[1] = dai * bj;  // pre10
+        o[2] = dai * dbj; // pre11
+        o[3] = ai * dbj;  // pre01
+        o[4] = ai * d2bj; // pre02
+        o[5] = ai * bj;   // pre00
+      }
+      else if (pl < 19)
+      {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          o[e] = scratch[24 + (pl - 16) * 4 + e];
+      }
+      ptx::mbar_wait(&empty_bar[stage], ph ^ 1u);
+      ST* hd = hdr_base + stage * SPL_HDR;
+      if (pl < 16)
+      {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          hd[pl * 8 + e] = o[e];
+      }
+      else if (pl < 19)
+      {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          hd[SPL_HDR_C + (pl - 16) * 4 + e] = o[e];
+      }
+      else if (pl == 19)
+        *reinterpret_cast<int*>(hd + SPL_HDR_SGN) = bc_sign;
+      __syncwarp();
+      if (pl == 0)
+      {
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], (unsigned)(ROWS * TILE * sizeof(ST)));
+        ptx::tma_load_4d(stage_base + (size_t)stage * ROWS * TILE, &tmap, tile * TILE, i2, i1, i0, &full_bar[stage]);
+      }
+      __syncwarp();
     }
     return;
   }
@@ -289,15 +377,7 @@ __global__ void __launch_bounds__(TILE / VEC + 32, MINB)
     const int stage = q % STAGES;
     const unsigned ph = (q / STAGES) & 1;
     const int iw = u / ntiles, tile = u - iw * ntiles;
-    ST ru[3], t[3];
-    int ind[3];
-    const RT* rpos    = A.r + 3 * (size_t)iw;
-    const int bc_sign = convert_pos<ST, RT>(S, rpos, ru);
-    locate(S, ru, ind, t);
-    ST a[4], b[4], c[4], da[4], db[4], dc[4], d2a[4], d2b[4], d2c[4];
-    prefactors(a, da, d2a, t[0]);
-    prefactors(b, db, d2b, t[1]);
-    prefactors(c, dc, d2c, t[2]);
+    const RT* rpos = A.r + 3 * (size_t)iw;
 
     ST v[VEC], gx[VEC], gy[VEC], gz[VEC], hxx[VEC], hxy[VEC], hxz[VEC], hyy[VEC], hyz[VEC], hzz[VEC];
 #pragma unroll
@@ -327,13 +407,24 @@ __global__ void __launch_bounds__(TILE / VEC + 32, MINB)
     }
     ptx::mbar_wait(&full_bar[stage], ph);
     const ST* sm = stage_base + (size_t)stage * ROWS * TILE + tid * VEC;
+    const ST* hd = hdr_base + stage * SPL_HDR;
+    ST c[4], dc[4], d2c[4];
+    load4<ST>(hd + SPL_HDR_C, c);
+    if (MODE != MODE_V)
+    {
+      load4<ST>(hd + SPL_HDR_C + 4, dc);
+      load4<ST>(hd + SPL_HDR_C + 8, d2c);
+    }
+    const int bc_sign = *reinterpret_cast<const int*>(hd + SPL_HDR_SGN);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
       {
-        const ST* p0   = sm + (size_t)((i * 4 + j) * 4) * TILE;
-        const ST pre00 = a[i] * b[j];
+        const ST* p0 = sm + (size_t)((i * 4 + j) * 4) * TILE;
+        ST pa[4], pb[4];
+        load4<ST>(hd + (i * 4 + j) * 8 + 4, pb);
+        const ST pre00 = pb[1];
         if (MODE == MODE_V)
         {
 #pragma unroll
@@ -342,8 +433,8 @@ __global__ void __launch_bounds__(TILE / VEC + 32, MINB)
         }
         else
         {
-          const ST pre20 = d2a[i] * b[j], pre10 = da[i] * b[j], pre11 = da[i] * db[j], pre01 = a[i] * db[j],
-                   pre02 = a[i] * d2b[j];
+          load4<ST>(hd + (i * 4 + j) * 8, pa);
+          const ST pre20 = pa[0], pre10 = pa[1], pre11 = pa[2], pre01 = pa[3], pre02 = pb[0];
 #pragma unroll
           for (int e = 0; e < VEC; ++e)
           {
