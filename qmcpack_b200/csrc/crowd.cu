@@ -9,6 +9,7 @@
 #include "woodbury_tc5.cuh"
 #include "woodbury_dmma.cuh"
 #include <cstdlib>
+#include <cuda.h>
 #include <type_traits>
 #include <cublas_v2.h>
 #include <cmath>
@@ -58,6 +59,27 @@ __global__ void make_move_kernel(const JastrowDev<T> J, const int iat, const T* 
 #pragma unroll
   for (int d = 0; d < 3; ++d)
     J.newpos[3 * iw + d] = J.rsoa[((size_t)iw * 3 + d) * J.npad + iat] + displ[3 * iw + d];
+}
+
+// host-driven path: ParticleSet::mw_makeMove and the proposed move's Jastrow sums in ONE launch on the crowd stream (one
+// CTA per walker).  The alternative -- make_move_kernel, then jastrow_move_kernel on a side stream beside the spline
+// gather -- costs one more launch and four event operations per move, and the driver calls, not the GPU, bound that path.
+template<typename T>
+__global__ void __launch_bounds__(JAS_TPB) make_move_jastrow_kernel(const JastrowDev<T> J, const int iat, const T* displ)
+{
+  __shared__ T red[10 * 32];
+  __shared__ unsigned short jl[JAS_LIST];
+  __shared__ T s_pos[3];
+  const int iw = blockIdx.x;
+  if (threadIdx.x < 3)
+  {
+    const T p = J.rsoa[((size_t)iw * 3 + threadIdx.x) * J.npad + iat] + displ[3 * iw + threadIdx.x];
+    J.newpos[3 * iw + threadIdx.x] = p;
+    s_pos[threadIdx.x]             = p;
+  }
+  __syncthreads();
+  const T pos[3] = {s_pos[0], s_pos[1], s_pos[2]};
+  jastrow_move_body<T, false>(J, iw, iat, pos, red, jl);
 }
 
 // TrialWaveFunction::mw_calcRatioGrad combination for one walker
@@ -287,6 +309,7 @@ __global__ void __launch_bounds__(MB_TPB, (sizeof(V) > 8 ? 2 : 4))
   __shared__ int s_acc;
   __shared__ V s_ratio;
   __shared__ T jred[10 * 32];
+  __shared__ unsigned short jlist[JAS_LIST]; // cutoff lists of the Jastrow passes (jastrow.cuh)
   __shared__ T s_newpos[3];
   const int iw = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool part1 = iat_prev >= 0, part2 = iat_next >= 0;
@@ -311,6 +334,29 @@ __global__ void __launch_bounds__(MB_TPB, (sizeof(V) > 8 ? 2 : 4))
   if (Dr.pdl_early)
     pdl_launch_dependents();
   pdl_wait(); // (no-op unless launched as a programmatic dependent of the spline gather)
+
+  // The Jastrow passes of phase B and of the tail start chains of dependent global loads (positions -> per-particle
+  // sums -> functor tables) long after the kernel began; their inputs are known now, so the lines are pulled into L1
+  // while phase A runs (one prefetch per 128-byte line, no registers held)
+  if (Dr.l1_prefetch && (J.has_j2 || J.has_j1))
+  {
+    const int lines_row = (J.npad * (int)sizeof(T) + 127) / 128;
+    const char* rs = reinterpret_cast<const char*>(J.rsoa + (size_t)iw * 3 * J.npad);
+    for (int l = tid; l < 3 * lines_row; l += MB_TPB)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(rs + (size_t)l * 128));
+    if (part1 && J.has_j2)
+    {
+      const char* ua = reinterpret_cast<const char*>(J.Uat + (size_t)iw * J.npad);
+      const char* du = reinterpret_cast<const char*>(J.dUat + (size_t)iw * 3 * J.npad);
+      const char* d2 = reinterpret_cast<const char*>(J.d2Uat + (size_t)iw * J.npad);
+      for (int l = tid; l < 5 * lines_row; l += MB_TPB)
+      {
+        const char* p = l < lines_row ? ua + (size_t)l * 128
+                                      : (l < 4 * lines_row ? du + (size_t)(l - lines_row) * 128 : d2 + (size_t)(l - 4 * lines_row) * 128);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+      }
+    }
+  }
 
   if (warp == 7)
   {
@@ -401,12 +447,28 @@ __global__ void __launch_bounds__(MB_TPB, (sizeof(V) > 8 ? 2 : 4))
         pick(t1, r1, v1, n1);
       V s0(0), s1(0);
       const int nmax = n0 > n1 ? n0 : n1;
-      for (int j = lane; j < nmax; j += 32)
+      // DOT_B elements of both rows are requested before the first multiply: 2 * DOT_B loads in flight per lane, one
+      // memory round trip per 32 * DOT_B columns instead of one per unrolled group (same accumulation order)
+      constexpr int DOT_B = sizeof(V) > 8 ? 4 : (sizeof(V) > 4 ? 6 : 12);
+      for (int jb = lane; jb < nmax; jb += 32 * DOT_B)
       {
-        if (j < n0)
-          s0 += r0[j] * v0[j];
-        if (j < n1)
-          s1 += r1[j] * v1[j];
+        V a0[DOT_B], a1[DOT_B];
+#pragma unroll
+        for (int q = 0; q < DOT_B; ++q)
+        {
+          const int j = jb + 32 * q;
+          a0[q]       = j < n0 ? r0[j] : V(0);
+          a1[q]       = j < n1 ? r1[j] : V(0);
+        }
+#pragma unroll
+        for (int q = 0; q < DOT_B; ++q)
+        {
+          const int j = jb + 32 * q;
+          if (j < n0)
+            s0 += a0[q] * v0[j];
+          if (j < n1)
+            s1 += a1[q] * v1[j];
+        }
       }
       s0 = warp_sum(s0);
       s1 = warp_sum(s1);
@@ -527,18 +589,43 @@ __global__ void __launch_bounds__(MB_TPB, (sizeof(V) > 8 ? 2 : 4))
       const V* Vm = Dprep.V + (size_t)iw * k * nB;
       V acc3[3]   = {V(0), V(0), V(0)};
       V* out      = Dprep.invRow + (size_t)iw * nB;
-      for (int j = tid; j < nB; j += gd.n)
+      // XC columns per thread side by side: the a-loop then carries XC independent load streams (the stores to out[]
+      // would otherwise keep the compiler from overlapping the columns); same per-column accumulation order
+      constexpr int XC = sizeof(V) > 8 ? 2 : 3;
+      for (int jb = tid; jb < nB; jb += XC * gd.n)
       {
-        V sacc(0);
+        V sacc[XC];
+#pragma unroll
+        for (int q = 0; q < XC; ++q)
+          sacc[q] = V(0);
+#pragma unroll 4
         for (int a = 0; a < cB; ++a)
-          sacc += Vm[(size_t)a * nB + j] * w[a];
-        if (same_det)
-          sacc += vrow[j] * w[c_prev];
-        const V xv = x[j] + sacc;
-        out[j]     = xv;
-        acc3[0] += xv * glrow[j];
-        acc3[1] += xv * glrow[nB + j];
-        acc3[2] += xv * glrow[2 * nB + j];
+        {
+          const V wa = w[a];
+#pragma unroll
+          for (int q = 0; q < XC; ++q)
+          {
+            const int j = jb + q * gd.n;
+            if (j < nB)
+              sacc[q] += Vm[(size_t)a * nB + j] * wa;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < XC; ++q)
+        {
+          const int j = jb + q * gd.n;
+          if (j < nB)
+          {
+            V sq = sacc[q];
+            if (same_det)
+              sq += vrow[j] * w[c_prev];
+            const V xv = x[j] + sq;
+            out[j]     = xv;
+            acc3[0] += xv * glrow[j];
+            acc3[1] += xv * glrow[nB + j];
+            acc3[2] += xv * glrow[2 * nB + j];
+          }
+        }
       }
       if (Dr.use_drift)
       {
@@ -550,7 +637,7 @@ __global__ void __launch_bounds__(MB_TPB, (sizeof(V) > 8 ? 2 : 4))
     }
   }
   else if (part1 && s_acc != 0)
-    jastrow_accept_body<T>(Group{tid - MB_TPB / 2, MB_TPB / 2, 2}, J, iw, iat_prev);
+    jastrow_accept_body<T>(Group{tid - MB_TPB / 2, MB_TPB / 2, 2}, J, iw, iat_prev, jlist);
   __syncthreads();
 
   if (part2 && twf_grads_out)
@@ -606,7 +693,7 @@ __global__ void __launch_bounds__(MB_TPB, (sizeof(V) > 8 ? 2 : 4))
   {
     __syncthreads();
     const T pos[3] = {s_newpos[0], s_newpos[1], s_newpos[2]};
-    jastrow_move_body<T, false>(J, iw, iat_next, pos, jred);
+    jastrow_move_body<T, false>(J, iw, iat_next, pos, jred, jlist);
   }
 }
 
@@ -643,6 +730,12 @@ __global__ void __launch_bounds__(256) ke_kernel(int N, const V* Gd, const V* Ld
 }
 
 // ------------------------------------------------------------------------------------------------------------
+static int env_flag(const char* name, int dflt)
+{
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+
 template<typename T, typename V>
 struct Crowd : CrowdBase
 {
@@ -864,6 +957,7 @@ struct Crowd : CrowdBase
     std::memset(&drv_host, 0, sizeof(drv_host));
     drv_host.nw = nw, drv_host.N = N, drv_host.use_drift = 1, drv_host.accepted = accepted.p;
     drv_host.pdl_early = (g_pdl_mode & 4) ? 1 : 0;
+    drv_host.l1_prefetch = env_flag("QMCB_L1PF", 1);
     std::memset(&rng, 0, sizeof(rng));
     QMCB_CUDA(cudaDeviceSynchronize());
   }
@@ -933,8 +1027,60 @@ struct Crowd : CrowdBase
   void sync() override { QMCB_CUDA(cudaStreamSynchronize(st)); }
   // host-driven move loop: two device round trips per move, so the wake-up latency of a blocking synchronize matters;
   // poll the stream instead (one host thread per crowd, VMCBatched.cpp:348)
+  // Polling with cudaStreamQuery takes the driver's context lock on every call: with one polling thread per crowd the
+  // launches of the other crowds queue behind the pollers (measured: 2 crowds overlap, 4 and 8 do not).  Default: a
+  // stream memory operation (cuStreamWriteValue32) publishes a sequence number in pinned host memory when the stream
+  // reaches it and the host thread spins on that word -- one driver call per round trip, none while waiting.
+  // QMCB_SYNC=query keeps the stream-query poll.
+  typedef CUresult (*StreamWriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+  static StreamWriteValue32Fn stream_write_fn()
+  {
+    static StreamWriteValue32Fn fn = [] {
+      const char* e = std::getenv("QMCB_SYNC");
+      if (e && std::string(e) == "query")
+        return (StreamWriteValue32Fn) nullptr;
+      void* p = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &qres) != cudaSuccess || !p ||
+          qres != cudaDriverEntryPointSuccess)
+        return (StreamWriteValue32Fn) nullptr;
+      return reinterpret_cast<StreamWriteValue32Fn>(p);
+    }();
+    return fn;
+  }
+  PinBuf<uint32_t> sync_word;
+  uint32_t sync_seq = 0;
   void spin_sync()
   {
+    StreamWriteValue32Fn wr = stream_write_fn();
+    if (wr)
+    {
+      if (!sync_word.p)
+      {
+        sync_word.alloc(16);
+        sync_word.p[0] = 0;
+      }
+      ++sync_seq;
+      if (wr((CUstream)st, (CUdeviceptr)(uintptr_t)sync_word.p, sync_seq, 0) == CUDA_SUCCESS)
+      {
+        volatile uint32_t* w = sync_word.p;
+        unsigned long long spins = 0;
+        while (*w != sync_seq)
+        {
+#if defined(__x86_64__)
+          __builtin_ia32_pause();
+#endif
+          if ((++spins & 0xfffffull) == 0) // every ~million spins: surface a sticky device error instead of hanging
+          {
+            const cudaError_t e = cudaStreamQuery(st);
+            if (e != cudaSuccess && e != cudaErrorNotReady)
+              QMCB_CUDA(e);
+          }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        return;
+      }
+    }
     cudaError_t e;
     while ((e = cudaStreamQuery(st)) == cudaErrorNotReady)
     {
@@ -1404,7 +1550,15 @@ struct Crowd : CrowdBase
     T* h = reinterpret_cast<T*>(h_t.p + 4 * (size_t)nw); // second half of the staging buffer
     for (int i = 0; i < 3 * nw; ++i)
       h[i] = (T)dsp[i];
-    make_move_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, h); // (reads the pinned host buffer: no copy launch)
+    static const int host_fuse = env_flag("QMCB_HOST_FUSE", 1);
+    if (host_fuse && (jas.has_j2 || jas.has_j1))
+    {
+      make_move_jastrow_kernel<T><<<nw, JAS_TPB, 0, st>>>(jas, iat, h); // (reads the pinned host buffer: no copy launch)
+      QMCB_LAUNCH_CHECK();
+      last_move_iat = iat;
+      return;
+    }
+    make_move_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, h);
     QMCB_LAUNCH_CHECK();
     if (jas.has_j2 || jas.has_j1)
     {
@@ -1591,6 +1745,7 @@ struct Crowd : CrowdBase
     drv.sqrttau     = (T)std::sqrt(drv.tauovermass);
     drv.use_drift   = p->use_drift;
     drv.pdl_early   = (g_pdl_mode & 4) ? 1 : 0;
+    drv.l1_prefetch = env_flag("QMCB_L1PF", 1);
     drv.dmc         = p->dmc;
     {
       const char* e    = std::getenv("QMCB_FUSE_J");

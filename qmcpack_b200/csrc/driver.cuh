@@ -32,6 +32,7 @@ struct DriverDev
   RT tauovermass, oneover2tau, sqrttau;
   int use_drift;
   int pdl_early;   // signal programmatic dependents at kernel start
+  int l1_prefetch; // boundary kernel pulls the Jastrow inputs into L1 at its start (env QMCB_L1PF, default on)
   int fuse_jastrow; // device sweep: the proposed move's Jastrow sums run in the boundary kernel's tail
   int dmc;         // DMCBatched acceptance rule + rr accumulators (DMCBatched.cpp:188-250)
   RT* rr_accepted; // [nw] sum over accepted moves of tau |delta|^2 (this sweep)

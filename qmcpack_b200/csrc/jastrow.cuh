@@ -183,31 +183,50 @@ __device__ __forceinline__ void j1_sums(const JastrowDev<RT>& J, const RT pos[3]
     out[e] = acc[e];
 }
 
+// ---- cutoff lists.  The functors vanish beyond rcut (5.57 bohr in a 15.76 bohr cell at NiO-a64: 18 % of the pairs are
+// inside), so evaluating every pair keeps 4 of 5 lanes busy with zeros and the accept rewrites 15 KB of unchanged sums.
+// Pass 1 computes the distances of all pairs and every WARP compacts the indices of its in-range pairs (ballot + popc)
+// into its own segment of a shared-memory list; pass 2 evaluates the functors with full warps over the list.  Skipped
+// pairs contribute exact zeros, the list order is fixed by (iteration, lane), and no atomics are involved, so the sums
+// stay deterministic.  JAS_LIST entries are enough for N + N_ion <= 4096 - (threads); larger systems take the direct path.
+constexpr int JAS_LIST = 4608;
+
 // ---- proposed move: J2 sums over the temporary distance row and J1 sums at the proposed position.
 // The reference materialises the new AND the old distance row (mw_new_old_dist_displ) and the per-pair functor values
 // (mw_cur_allu) in device memory and reads them back in the accept kernel: 54 KB written + 45 KB read per walker per
 // move at NiO-a64.  Here the rows are a by-product that is only stored on request (STORE, for qmcb_dtaa_get_temp_rows);
 // the accept recomputes the two rows from the positions (9 KB) -- identical arithmetic, so identical values -- and the
 // J1 and J2 sums share one pass and one block reduction.
-// Body for one walker, executed by ALL threads of the CTA (blockDim.x threads; red >= 10 * 32).
+// Body for one walker, executed by ALL threads of the CTA (blockDim.x threads; red >= 10 * 32; jl = JAS_LIST entries).
 template<typename RT, bool STORE>
-__device__ __forceinline__ void jastrow_move_body(const JastrowDev<RT>& J, const int iw, const int iat, const RT pos[3], RT* red)
+__device__ __forceinline__ void jastrow_move_body(const JastrowDev<RT>& J, const int iw, const int iat, const RT pos[3], RT* red,
+                                                  unsigned short* jl)
 {
   const int tid = threadIdx.x, N = J.N, np = J.npad, JAS_STEP = blockDim.x;
+  const int lane = tid & 31, wg = tid >> 5, nwg = JAS_STEP >> 5;
   const RT* rs = J.rsoa + (size_t)iw * 3 * np;
   RT acc[10]   = {RT(0), RT(0), RT(0), RT(0), RT(0), RT(0), RT(0), RT(0), RT(0), RT(0)};
-  if (J.has_j2)
+  const int n2 = J.has_j2 ? N : 0, n1 = J.has_j1 ? J.nions : 0; // combined index space: electrons then ions
+  const int gi = (iat < J.n_up ? 0 : 1) * 2;
+  RT old[3]    = {RT(0), RT(0), RT(0)};
+  RT* rnew     = J.rows + (size_t)iw * 4 * np;
+  RT* rold     = J.rows + ((size_t)J.nw + iw) * 4 * np;
+  if (STORE && J.has_j2)
+    old[0] = rs[iat], old[1] = rs[np + iat], old[2] = rs[2 * np + iat];
+  const int iters  = (n2 + n1 + JAS_STEP - 1) / JAS_STEP;
+  const int segcap = iters * 32;
+  const bool listed = segcap * nwg <= JAS_LIST && n2 + n1 < 65536;
+  unsigned short* seg = jl + wg * segcap;
+  int cnt = 0;
+  for (int it = 0; it < iters; ++it)
   {
-    RT old[3]   = {RT(0), RT(0), RT(0)};
-    RT* rnew    = J.rows + (size_t)iw * 4 * np;
-    RT* rold    = J.rows + ((size_t)J.nw + iw) * 4 * np;
-    if (STORE)
-      old[0] = rs[iat], old[1] = rs[np + iat], old[2] = rs[2 * np + iat];
-    const int gi = (iat < J.n_up ? 0 : 1) * 2;
-    for (int j = tid; j < N; j += JAS_STEP)
+    const int idx = it * JAS_STEP + tid;
+    bool need     = false;
+    RT r = RT(0), dx = RT(0), dy = RT(0), dz = RT(0);
+    if (idx < n2)
     {
+      const int j = idx;
       const RT px = rs[j], py = rs[np + j], pz = rs[2 * np + j];
-      RT r, dx, dy, dz;
       min_image(J.cell, pos, px, py, pz, j, iat, r, dx, dy, dz);
       if (STORE)
       {
@@ -222,31 +241,74 @@ __device__ __forceinline__ void jastrow_move_body(const JastrowDev<RT>& J, const
         rold[2 * np + j] = oy;
         rold[3 * np + j] = oz;
       }
-      if (j != iat)
+      const FunctorDev<RT>& F = J.F2[gi + (j < J.n_up ? 0 : 1)];
+      need                    = j != iat && F.coefs != nullptr && r < F.rcut;
+    }
+    else if (idx < n2 + n1)
+    {
+      const int j = idx - n2;
+      min_image(J.cell, pos, J.ion_rsoa[j], J.ion_rsoa[J.npad_ion + j], J.ion_rsoa[2 * J.npad_ion + j], j, 0, r, dx, dy, dz);
+      const FunctorDev<RT>& F = J.F1[J.ion_grp[j]];
+      need                    = F.coefs != nullptr && r < F.rcut;
+    }
+    if (listed)
+    {
+      const unsigned m = __ballot_sync(0xffffffffu, need);
+      if (need)
+        seg[cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)idx;
+      cnt += __popc(m);
+    }
+    else if (need)
+    {
+      RT du, d2u;
+      if (idx < n2)
       {
-        RT du, d2u;
-        const RT u = functor_eval(J.F2[gi + (j < J.n_up ? 0 : 1)], r, du, d2u);
+        const RT u = functor_eval(J.F2[gi + (idx < J.n_up ? 0 : 1)], r, du, d2u);
         acc[0] += u;
         acc[1] += du * dx;
         acc[2] += du * dy;
         acc[3] += du * dz;
         acc[4] += d2u + RT(2) * du;
       }
+      else
+      {
+        const RT u = functor_eval(J.F1[J.ion_grp[idx - n2]], r, du, d2u);
+        acc[5] += u;
+        acc[6] += du * dx;
+        acc[7] += du * dy;
+        acc[8] += du * dz;
+        acc[9] += d2u + RT(2) * du;
+      }
     }
   }
-  if (J.has_j1)
+  if (listed)
   {
-    // one-body sums at the proposed position (J1OrbitalSoA.h:136-185)
-    for (int j = tid; j < J.nions; j += JAS_STEP)
+    __syncwarp();
+    for (int e = lane; e < cnt; e += 32)
     {
+      const int idx = seg[e];
       RT r, dx, dy, dz, du, d2u;
-      min_image(J.cell, pos, J.ion_rsoa[j], J.ion_rsoa[J.npad_ion + j], J.ion_rsoa[2 * J.npad_ion + j], j, 0, r, dx, dy, dz);
-      const RT u = functor_eval(J.F1[J.ion_grp[j]], r, du, d2u);
-      acc[5] += u;
-      acc[6] += du * dx;
-      acc[7] += du * dy;
-      acc[8] += du * dz;
-      acc[9] += d2u + RT(2) * du;
+      if (idx < n2)
+      {
+        min_image(J.cell, pos, rs[idx], rs[np + idx], rs[2 * np + idx], idx, iat, r, dx, dy, dz);
+        const RT u = functor_eval(J.F2[gi + (idx < J.n_up ? 0 : 1)], r, du, d2u);
+        acc[0] += u;
+        acc[1] += du * dx;
+        acc[2] += du * dy;
+        acc[3] += du * dz;
+        acc[4] += d2u + RT(2) * du;
+      }
+      else
+      {
+        const int j = idx - n2;
+        min_image(J.cell, pos, J.ion_rsoa[j], J.ion_rsoa[J.npad_ion + j], J.ion_rsoa[2 * J.npad_ion + j], j, 0, r, dx, dy, dz);
+        const RT u = functor_eval(J.F1[J.ion_grp[j]], r, du, d2u);
+        acc[5] += u;
+        acc[6] += du * dx;
+        acc[7] += du * dy;
+        acc[8] += du * dz;
+        acc[9] += d2u + RT(2) * du;
+      }
     }
   }
   block_sum<RT, 10>(acc, red);
@@ -268,16 +330,28 @@ template<typename RT, bool STORE>
 __global__ void __launch_bounds__(JAS_TPB) jastrow_move_kernel(const JastrowDev<RT> J, const int iat)
 {
   __shared__ RT red[10 * 32];
+  __shared__ unsigned short jl[JAS_LIST];
   const int iw    = blockIdx.x;
   const RT pos[3] = {J.newpos[3 * iw], J.newpos[3 * iw + 1], J.newpos[3 * iw + 2]};
-  jastrow_move_body<RT, STORE>(J, iw, iat, pos, red);
+  jastrow_move_body<RT, STORE>(J, iw, iat, pos, red, jl);
 }
 
-// ---- accept (walker iw, thread group g): J2 per-particle sums (BsplineFunctor.cpp:262-324), J1 commit, position commit
+// one pair of the accept: both distance rows and both functor evaluations are recomputed from the positions (see
+// jastrow_move_body); BsplineFunctor.cpp:262-324
 template<typename RT>
-__device__ __forceinline__ void jastrow_accept_body(const Group& g, const JastrowDev<RT>& J, const int iw, const int iat)
+struct J2Pair
+{
+  RT px, py, pz, ua, da, db, dc, l2;
+};
+
+// ---- accept (walker iw, thread group g): J2 per-particle sums (BsplineFunctor.cpp:262-324), J1 commit, position commit
+// jl: JAS_LIST entries of shared memory for the group
+template<typename RT>
+__device__ __forceinline__ void jastrow_accept_body(const Group& g, const JastrowDev<RT>& J, const int iw, const int iat,
+                                                    unsigned short* jl)
 {
   const int tid = g.tid, N = J.N, np = J.npad;
+  const int lane = tid & 31, wg = tid >> 5, nwg = g.n >> 5;
   if (J.has_j2)
   {
     const RT* rs   = J.rsoa + (size_t)iw * 3 * np;
@@ -290,49 +364,96 @@ __device__ __forceinline__ void jastrow_accept_body(const Group& g, const Jastro
     const int gi   = (iat < J.n_up ? 0 : 1) * 2;
     const RT Uold_iat = Uat[iat];
     g.sync();
+    auto update = [&](const int j, const J2Pair<RT>& q) {
+      RT rn, nx, ny, nz, ro, ox, oy, oz, cdu, cd2, du, d2u;
+      min_image(J.cell, pnew, q.px, q.py, q.pz, j, iat, rn, nx, ny, nz);
+      min_image(J.cell, pold, q.px, q.py, q.pz, j, iat, ro, ox, oy, oz);
+      const FunctorDev<RT>& F = J.F2[gi + (j < J.n_up ? 0 : 1)];
+      const RT cu = functor_eval(F, rn, cdu, cd2);
+      const RT u  = functor_eval(F, ro, du, d2u);
+      Uat[j]         = q.ua + (cu - u);
+      dU[j]          = q.da - (nx * cdu - ox * du);
+      dU[np + j]     = q.db - (ny * cdu - oy * du);
+      dU[2 * np + j] = q.dc - (nz * cdu - oz * du);
+      d2U[j]         = q.l2 - (cd2 + RT(2) * cdu - (d2u + RT(2) * du));
+    };
+    auto fetch = [&](const int j, J2Pair<RT>& q) {
+      q.px = rs[j];
+      q.py = rs[np + j];
+      q.pz = rs[2 * np + j];
+      q.ua = Uat[j];
+      q.da = dU[j];
+      q.db = dU[np + j];
+      q.dc = dU[2 * np + j];
+      q.l2 = d2U[j];
+    };
+    const int iters  = (N + g.n - 1) / g.n;
+    const int segcap = iters * 32;
+    const bool listed = segcap * nwg <= JAS_LIST && N < 65536;
     // two elements per thread at a time: every load of a chunk is issued before the first store, so the HBM round trips
     // overlap instead of queueing behind the read-modify-write stores (which the compiler must assume may alias)
     constexpr int CH = 2;
-    for (int j0 = tid; j0 < N; j0 += CH * g.n)
+    if (listed)
     {
-      RT px[CH], py[CH], pz[CH], ua[CH], da[CH], db[CH], dc[CH], l2[CH];
-      bool on[CH];
-#pragma unroll
-      for (int q = 0; q < CH; ++q)
+      // pass 1: pairs whose old OR new distance is inside the cutoff (the others add exact zeros to every sum)
+      unsigned short* seg = jl + wg * segcap;
+      int cnt = 0;
+      for (int it = 0; it < iters; ++it)
       {
-        const int j = j0 + q * g.n;
-        on[q]       = j < N && j != iat;
-        if (on[q])
+        const int j = it * g.n + tid;
+        bool need   = false;
+        if (j < N && j != iat)
         {
-          px[q]  = rs[j];
-          py[q]  = rs[np + j];
-          pz[q]  = rs[2 * np + j];
-          ua[q]  = Uat[j];
-          da[q]  = dU[j];
-          db[q]  = dU[np + j];
-          dc[q]  = dU[2 * np + j];
-          l2[q]  = d2U[j];
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < CH; ++q)
-      {
-        const int j = j0 + q * g.n;
-        if (on[q])
-        {
-          // both distance rows and both functor evaluations are recomputed from the positions (see jastrow_move_body)
-          RT rn, nx, ny, nz, ro, ox, oy, oz, cdu, cd2, du, d2u;
-          min_image(J.cell, pnew, px[q], py[q], pz[q], j, iat, rn, nx, ny, nz);
-          min_image(J.cell, pold, px[q], py[q], pz[q], j, iat, ro, ox, oy, oz);
+          const RT px = rs[j], py = rs[np + j], pz = rs[2 * np + j];
+          RT rn, ro, t0, t1, t2;
+          min_image(J.cell, pnew, px, py, pz, j, iat, rn, t0, t1, t2);
+          min_image(J.cell, pold, px, py, pz, j, iat, ro, t0, t1, t2);
           const FunctorDev<RT>& F = J.F2[gi + (j < J.n_up ? 0 : 1)];
-          const RT cu = functor_eval(F, rn, cdu, cd2);
-          const RT u  = functor_eval(F, ro, du, d2u);
-          Uat[j]         = ua[q] + (cu - u);
-          dU[j]          = da[q] - (nx * cdu - ox * du);
-          dU[np + j]     = db[q] - (ny * cdu - oy * du);
-          dU[2 * np + j] = dc[q] - (nz * cdu - oz * du);
-          d2U[j]         = l2[q] - (cd2 + RT(2) * cdu - (d2u + RT(2) * du));
+          need                    = F.coefs != nullptr && (rn < F.rcut || ro < F.rcut);
         }
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        if (need)
+          seg[cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
+        cnt += __popc(m);
+      }
+      __syncwarp();
+      // pass 2: full warps over the list
+      for (int e0 = lane; e0 < cnt; e0 += CH * 32)
+      {
+        J2Pair<RT> q[CH];
+        int jj[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+        {
+          const int e = e0 + c * 32;
+          jj[c]       = e < cnt ? (int)seg[e] : -1;
+          if (jj[c] >= 0)
+            fetch(jj[c], q[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+          if (jj[c] >= 0)
+            update(jj[c], q[c]);
+      }
+    }
+    else
+    {
+      for (int j0 = tid; j0 < N; j0 += CH * g.n)
+      {
+        J2Pair<RT> q[CH];
+        bool on[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+        {
+          const int j = j0 + c * g.n;
+          on[c]       = j < N && j != iat;
+          if (on[c])
+            fetch(j, q[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+          if (on[c])
+            update(j0 + c * g.n, q[c]);
       }
     }
     if (tid == 0)
@@ -365,9 +486,10 @@ template<typename RT>
 __global__ void __launch_bounds__(JAS_TPB)
     jastrow_accept_kernel(const JastrowDev<RT> J, const int iat, const unsigned char* accepted)
 {
+  __shared__ unsigned short jl[JAS_LIST];
   if (!accepted[blockIdx.x])
     return;
-  jastrow_accept_body<RT>(cta_group(), J, blockIdx.x, iat);
+  jastrow_accept_body<RT>(cta_group(), J, blockIdx.x, iat, jl);
 }
 
 // ---- from scratch (TwoBodyJastrow.cpp:667-713 lower-triangle form; J1OrbitalSoA.h:237-250).  grid = nw.
