@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--config", default="NiO-a64")
     ap.add_argument("--walkers", type=int, default=512, help="walkers per GPU")
     ap.add_argument("--crowds", type=int, default=4, help="crowds (host threads / streams) of the e2e host driver")
-    ap.add_argument("--device-crowds", type=int, default=4,
+    ap.add_argument("--device-crowds", type=int, default=2,
                     help="crowds of the device-resident sweep: walkers/GPU are split over this many crowds, each with its own "
                          "RNG stream and CUDA graph on its own stream (QMCDriverNew gives every crowd its own generator)")
     ap.add_argument("--tau", type=float, default=0.3)
@@ -307,6 +307,30 @@ def run_b200(args, rank, local_rank, world):
               "path": "qmcb_vmc_sweep (device-resident Metropolis loop) + per-sweep read-back of kinetic energy, log psi and "
                       "positions; informational, the contract's e2e is the host-driven path"}
 
+    # ---------------- rank-k Woodbury flush alone (the dense contraction; informational second roofline object).
+    # Executed flops per flush and walker: 4 k n^2 + 2 n k^2 (x4 complex); one-pass bytes 2 n^2 sizeof(VT).
+    # Full precision runs on the FP64 tensor pipe (DMMA; measured peak 37.0 TF/s, scripts/micro/mma_rate.cu), mixed
+    # precision on tcgen05 TF32 with the 3-product split (3x the algorithmic flops executed).
+    flush = None
+    try:
+        us_f = dcrowds[0].det_time_update_inv_mat(0, k, 8)
+        nwf = dsizes[0]
+        vt_bytes = (4 if c["dtype"] == np.float32 else 8) * (2 if cplx else 1)
+        fl = (4 if cplx else 1) * (4.0 * k * n * n + 2.0 * n * k * k) * nwf
+        by = 2.0 * n * n * vt_bytes * nwf
+        full = c["dtype"] != np.float32
+        flush = {"kernel": "wb64::woodbury_flush_dmma_kernel (DMMA m8n8k4, one pass)" if full else
+                 "wb5::woodbury_flush_tc5_kernel (tcgen05 TF32 x3 split, one pass)",
+                 "walkers": nwf, "delay_rank": k, "us_per_flush": us_f, "tflops_algorithmic": fl / us_f * 1e-6,
+                 "one_pass_GBps": by / us_f * 1e-3, "frac_hbm": by / us_f * 1e-3 / (peaks() or {"hbm_gbs": 6650.0})["hbm_gbs"]}
+        if full:
+            flush["frac_fp64_tensor_peak"] = fl / us_f * 1e-6 / 37.0
+            flush["fp64_tensor_peak_source"] = "37.0 TF/s measured with scripts/micro/mma_rate.cu (DMMA m8n8k4, all SMs)"
+        for cr in dcrowds:  # the hook leaves the inverse meaningless
+            cr.mw_recompute()
+    except Exception as ex:  # measurement hook only
+        flush = {"error": str(ex)}
+
     # ---------------- spline gather kernel alone (roofline)
     T = np.float32 if c["dtype"] == np.float32 else np.float64
     tdt = torch.float32 if T == np.float32 else torch.float64
@@ -401,7 +425,7 @@ def run_b200(args, rank, local_rank, world):
                        "parallelism": f"walkers sharded over {world} GPU(s), no data-path collective; one all-reduce per block",
                        "acceptance": acc_rate, "ke_mean_hartree": ke_mean, "finite": sane},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu,
+            "flush": flush, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if dist:

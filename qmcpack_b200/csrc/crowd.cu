@@ -1213,7 +1213,7 @@ struct Crowd : CrowdBase
                                          (int)(200 * 1024)));
           attr5_set = true;
         }
-        wb5::woodbury_flush_tc5_kernel<<<dim3(nw, (n + wb5::TM - 1) / wb5::TM), wb5::TPB, smem5, st>>>(D, c);
+        wb5::woodbury_flush_tc5_kernel<<<dim3((n + wb5::TM - 1) / wb5::TM, nw), wb5::TPB, smem5, st>>>(D, c);
         QMCB_LAUNCH_CHECK();
         delay_count[spin] = 0;
         invrow_id[spin]   = -1;

@@ -116,7 +116,7 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo)
   lo   = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
 }
 
-// grid = (nw, ceil(n / 128)); c <= 32 pending delays; n % 64 == 0.  Two CTAs per SM (85 KB of shared memory, 256 of the
+// grid = (ceil(n / 128), nw); c <= 32 pending delays; n % 64 == 0.  Two CTAs per SM (85 KB of shared memory, 256 of the
 // 512 TMEM columns and <= 128 registers each): the phases of one CTA are chains of memory latencies, the second CTA on
 // the SM fills them.
 __global__ void __launch_bounds__(TPB, 2) woodbury_flush_tc5_kernel(const DetDev<float> D, const int c)
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(TPB, 2) woodbury_flush_tc5_kernel(const DetDev
   __shared__ uint32_t tmem_base_s;
 
   const int n = D.n, lda = D.lda, k = D.k;
-  const int iw = blockIdx.x, m0 = blockIdx.y * TM;
+  const int iw = blockIdx.y, m0 = blockIdx.x * TM; // tile index fastest: a walker's CTAs run together and share U, V in L2
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nchunks = n / KC;
   // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 bytes).  One stage = A_hi, A_lo [128][32] + U_hi, U_lo [32][32]
