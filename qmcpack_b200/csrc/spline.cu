@@ -210,6 +210,11 @@ struct SplineSPO : SplineSPOBase
     A.rg_partial = static_cast<ST*>(rg_dev);
     A.nparts     = ntiles * (TILE / VEC / 32);
     A.pdl_early  = (g_pdl_mode & 4) ? 1 : 0;
+    static const int evict = [] {
+      const char* e = std::getenv("QMCB_SPL_EVICT");
+      return e ? std::atoi(e) : 1; // measured: device sweep 54.3 -> 51.2 us per move (the boundary kernel's rows stay in L2)
+    }();
+    A.l2_evict_first = evict;
     auto kern            = spline_gather_kernel<ST, ST, TILE, STAGES, VEC, MODE, C2C, MINB>;
     constexpr size_t smem = SplineSmem<ST, TILE, STAGES, VEC>::BYTES;
     static bool attr_set = false;

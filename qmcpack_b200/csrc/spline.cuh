@@ -58,6 +58,7 @@ struct SplineArgs
   int nw;              // number of positions
   const RT* r;         // [nw][3] Cartesian
   int pdl_early;       // signal programmatic dependents at kernel start
+  int l2_evict_first;  // stencil requests carry an evict_first L2 policy (env QMCB_SPL_EVICT)
   const ST* invrow;    // [n_rows][ld_inv] (VT == ST; complex interleaved for C2C) or nullptr
   const int* ref;      // optional [nw] row index into invrow (virtual-particle ratios); nullptr -> iw
   long long ld_inv;    // in VT elements
@@ -126,6 +127,22 @@ __device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* t
                "%5, %6}], [%2];" ::"r"(smem_u32(dst_smem)),
                "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
+}
+// the same request with an L2 eviction policy: the stencil stream is read once per evaluation, the walkers' delayed-update
+// rows (U, V, Binv, inverse rows) are read again by the next boundary kernel -- evict_first on the stream keeps them in L2
+__device__ __forceinline__ void tma_load_4d_hint(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, int c3,
+                                                 uint64_t* bar, uint64_t policy)
+{
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, "
+               "{%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(dst_smem)),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tmap)
 {
@@ -362,7 +379,11 @@ __global__ void __launch_bounds__(TILE / VEC + 32, MINB)
       if (pl == 0)
       {
         ptx::mbar_arrive_expect_tx(&full_bar[stage], (unsigned)(ROWS * TILE * sizeof(ST)));
-        ptx::tma_load_4d(stage_base + (size_t)stage * ROWS * TILE, &tmap, tile * TILE, i2, i1, i0, &full_bar[stage]);
+        if (A.l2_evict_first)
+          ptx::tma_load_4d_hint(stage_base + (size_t)stage * ROWS * TILE, &tmap, tile * TILE, i2, i1, i0, &full_bar[stage],
+                                ptx::policy_evict_first());
+        else
+          ptx::tma_load_4d(stage_base + (size_t)stage * ROWS * TILE, &tmap, tile * TILE, i2, i1, i0, &full_bar[stage]);
       }
       __syncwarp();
     }
