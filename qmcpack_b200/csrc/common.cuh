@@ -248,6 +248,32 @@ inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t 
   QMCB_CUDA(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
 }
 
+// streaming (read-once / write-once) global accesses: ld.global.cs / st.global.cs mark the line evict-first in L2, so
+// one-shot data (the proposed move's orbital rows, the gradient rows written by an accept) does not push the walkers'
+// recurring working set (delayed-update rows, Jastrow sums, positions) out of L2
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ cx<float> ld_stream(const cx<float>* p)
+{
+  const float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+  return cx<float>(v.x, v.y);
+}
+__device__ __forceinline__ cx<double> ld_stream(const cx<double>* p)
+{
+  const double2 v = __ldcs(reinterpret_cast<const double2*>(p));
+  return cx<double>(v.x, v.y);
+}
+__device__ __forceinline__ void st_stream(float* p, const float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(double* p, const double v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(cx<float>* p, const cx<float>& v)
+{
+  __stcs(reinterpret_cast<float2*>(p), make_float2(v.re, v.im));
+}
+__device__ __forceinline__ void st_stream(cx<double>* p, const cx<double>& v)
+{
+  __stcs(reinterpret_cast<double2*>(p), make_double2(v.re, v.im));
+}
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll

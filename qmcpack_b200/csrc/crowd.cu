@@ -391,11 +391,11 @@ __global__ void __launch_bounds__(MB_TPB, (sizeof(V) > 8 ? 2 : 4))
       const V* arow   = Dacc.Ainv + ((size_t)iw * nA + row_prev) * Dacc.lda;
       for (int j = tid; j < nA; j += ga.n)
       {
-        phi[j]          = ph[j];
-        phi[nA + j]     = ph[fs + j];
-        phi[2 * nA + j] = ph[2 * fs + j];
-        phi[3 * nA + j] = ph[3 * fs + j];
-        phi[4 * nA + j] = ph[4 * fs + j];
+        phi[j]          = ld_stream(ph + j); // read once: streaming loads (common.cuh)
+        phi[nA + j]     = ld_stream(ph + fs + j);
+        phi[2 * nA + j] = ld_stream(ph + 2 * fs + j);
+        phi[3 * nA + j] = ld_stream(ph + 3 * fs + j);
+        phi[4 * nA + j] = ld_stream(ph + 4 * fs + j);
         vrow[j]         = arow[j];
       }
       const V* wv = Dacc.wvec + (size_t)iw * k;
@@ -509,10 +509,10 @@ __global__ void __launch_bounds__(MB_TPB, (sizeof(V) > 8 ? 2 : 4))
         U[(size_t)c * nA + j]  = acc ? phi[j] : V(0);
         if (acc)
         {
-          gl[j]          = phi[nA + j];
-          gl[nA + j]     = phi[2 * nA + j];
-          gl[2 * nA + j] = phi[3 * nA + j];
-          gl[3 * nA + j] = phi[4 * nA + j];
+          st_stream(gl + j, phi[nA + j]); // next read a whole sweep later: streaming stores
+          st_stream(gl + nA + j, phi[2 * nA + j]);
+          st_stream(gl + 2 * nA + j, phi[3 * nA + j]);
+          st_stream(gl + 3 * nA + j, phi[4 * nA + j]);
         }
       }
       if (acc)
