@@ -6,6 +6,9 @@
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 #include <atomic>
@@ -74,9 +77,36 @@ struct CrowdCtx
   CrowdCtx(qmcb_crowd* c, int n, int off, uint32_t seed) : crowd(c), nw(n), w0(off), rng(seed) {}
 };
 
+// QMCB_HOST_PROFILE=1: wall-clock attribution of the host-driven loop (crowd 0 prints microseconds per move spent in
+// each C-ABI call and in the host arithmetic between them) -- where a round trip goes when no timeline tool is at hand
+struct PhaseClock
+{
+  bool on;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  std::chrono::steady_clock::time_point t;
+  explicit PhaseClock(bool enable) : on(enable)
+  {
+    if (on)
+      t = std::chrono::steady_clock::now();
+  }
+  void lap(int phase)
+  {
+    if (!on)
+      return;
+    const auto n = std::chrono::steady_clock::now();
+    acc[phase] += std::chrono::duration<double, std::micro>(n - t).count();
+    t = n;
+  }
+};
+
 template<typename RT>
 void advance_crowd(CrowdCtx& cx, int N, double tau, bool use_drift, uint8_t* log, int nw_total)
 {
+  static const bool profile = [] {
+    const char* e = std::getenv("QMCB_HOST_PROFILE");
+    return e && std::atoi(e) != 0;
+  }();
+  PhaseClock pc(profile && cx.w0 == 0);
   const int nw = cx.nw;
   // TauParams.hpp:29-40, unit mass
   const RT tauovermass = RT(tau) * RT(1.0);
@@ -95,9 +125,11 @@ void advance_crowd(CrowdCtx& cx, int N, double tau, bool use_drift, uint8_t* log
     for (int i = 0; i < nw; ++i)
       for (int d = 0; d < 3; ++d)
         deltas[3 * i + d] = walker_deltas[3 * ((size_t)iat * nw + i) + d] * sqrttau;
+    pc.lap(0);
     if (use_drift)
     {
       chk(qmcb_twf_mw_eval_grad(cx.crowd, iat, grads.data()));
+      pc.lap(1);
       for (int i = 0; i < nw; ++i)
       {
         const RT g[3] = {(RT)grads[(3 * i) * cs], (RT)grads[(3 * i + 1) * cs], (RT)grads[(3 * i + 2) * cs]};
@@ -111,8 +143,11 @@ void advance_crowd(CrowdCtx& cx, int N, double tau, bool use_drift, uint8_t* log
       drifts = deltas;
     for (size_t i = 0; i < displ.size(); ++i)
       displ[i] = drifts[i];
+    pc.lap(0);
     chk(qmcb_ps_mw_make_move(cx.crowd, iat, displ.data()));
+    pc.lap(2);
     chk(qmcb_twf_mw_calc_ratio_grad(cx.crowd, iat, ratios.data(), grads.data()));
+    pc.lap(3);
     if (use_drift)
       for (int i = 0; i < nw; ++i)
       {
@@ -143,8 +178,15 @@ void advance_crowd(CrowdCtx& cx, int N, double tau, bool use_drift, uint8_t* log
       if (log)
         log[(size_t)iat * nw_total + cx.w0 + i] = accepted[i];
     }
+    pc.lap(0);
     chk(qmcb_twf_mw_accept_reject(cx.crowd, iat, accepted.data(), 1));
+    pc.lap(4);
   }
+  if (pc.on)
+    std::fprintf(stderr,
+                 "[host profile] crowd 0 (%d walkers), us per move: host arithmetic %.1f | eval_grad %.1f | make_move %.1f | "
+                 "calc_ratio_grad %.1f | accept_reject %.1f\n",
+                 nw, pc.acc[0] / N, pc.acc[1] / N, pc.acc[2] / N, pc.acc[3] / N, pc.acc[4] / N);
   chk(qmcb_twf_mw_complete_updates(cx.crowd));
   chk(qmcb_crowd_sync(cx.crowd));
 }
