@@ -33,3 +33,21 @@ np.savez_compressed(out,
                     psi_g=psi_g.astype(np.complex128),
                     version=f.read("/version"))
 print(out, os.path.getsize(out), "bytes;", nstates, "states,", psi_g.shape[1], "G-vectors")
+
+
+# ---- the 2x1x1 tiling of the same test set: two primitive-cell twists, (0,0,0) and (1/2,0,0); only the five lowest bands
+# over both twists (what test_einset_diamondC.cpp:374-376 asks for) are kept, with their (twist, band) labels
+SRC2 = "/root/reference/tests/solids/diamondC_2x1x1_pp/pwscf.pwscf.h5"
+f2 = H5File(SRC2)
+nk = int(f2.read("/electrons/number_of_kpoints").ravel()[0])
+twists = np.stack([f2.read("/electrons/kpoint_%d/reduced_k" % k) for k in range(nk)])
+eig = np.stack([f2.read("/electrons/kpoint_%d/spin_0/eigenvalues" % k) for k in range(nk)])
+gv2 = f2.read("/electrons/kpoint_0/gvectors").astype(np.int32)
+assert all(np.array_equal(gv2, f2.read("/electrons/kpoint_%d/gvectors" % k)) for k in range(nk))
+order = sorted((round(float(eig[k][b]) / 1e-6) * 1e-6, k, b) for k in range(nk) for b in range(eig.shape[1]))[:5]
+labels = np.array([(k, b) for _, k, b in order], np.int32)
+pg = np.stack([f2.read("/electrons/kpoint_%d/spin_0/state_%d/psi_g" % (k, b)) for k, b in labels])
+out2 = os.path.join(ROOT, "tests", "golden", "diamondC_2x1x1_eshdf.npz")
+np.savez_compressed(out2, primitive_vectors=f2.read("/supercell/primitive_vectors"), gvectors=gv2, reduced_k=twists,
+                    eigenvalues=eig, band_labels=labels, psi_g=(pg[..., 0] + 1j * pg[..., 1]).astype(np.complex128))
+print(out2, os.path.getsize(out2), "bytes; bands (twist, band):", labels.tolist())

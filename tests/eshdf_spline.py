@@ -71,3 +71,31 @@ def build_table(orc, psi_g, gvecs, twist, eigenvalues, norb, dtype, complex_orbi
         else:
             coefs[..., o] = orc.create_periodic_coefs(rotate_c2r(box, twist)).astype(dtype)
     return coefs
+
+
+def band_order(eigenvalues, norb):
+    """(twist, band) of the `norb` lowest states over all twists: BandInfo::operator< (energy within 1e-6, then twist,
+    then band index), EinsplineSetBuilderCommon.cpp OccupyBands"""
+    eig = np.atleast_2d(eigenvalues)
+    keys = sorted((round(float(eig[k][b]) / 1e-6) * 1e-6, k, b) for k in range(eig.shape[0]) for b in range(eig.shape[1]))
+    return [(k, b) for _, k, b in keys[:norb]]
+
+
+def k_cart(G, twist):
+    """BsplineSet::kPoints = PrimLattice.k_cart(-twist): the orbital is u(r) exp(+i k.r) and SplineC2C multiplies by
+    exp(-i kPoint.r) (SplineC2C.cpp:146-168); G = inverse primitive vectors (ru = r G)"""
+    return -2.0 * np.pi * (np.asarray(G) @ np.asarray(twist, np.float64))
+
+
+def build_table_c2c_twists(orc, psi_g, band_twist, twists, gvecs, dtype, meshfactor=1.0):
+    """complex (SplineC2C) table of orbitals that come from several primitive-cell twists: psi_g[o] belongs to twist
+    band_twist[o]; returns (table, kcart [norb][3] in reduced-to-Cartesian form still to be multiplied by G)"""
+    mesh = mesh_size(gvecs, meshfactor)
+    norb = len(psi_g)
+    npad = orc.aligned_size(dtype, 2 * norb)
+    coefs = np.zeros((mesh[0] + 3, mesh[1] + 3, mesh[2] + 3, npad), dtype)
+    for o in range(norb):
+        z = rotate_c2c(fft_box(psi_g[o], gvecs, mesh), twists[band_twist[o]])
+        coefs[..., 2 * o] = orc.create_periodic_coefs(z.real).astype(dtype)
+        coefs[..., 2 * o + 1] = orc.create_periodic_coefs(z.imag).astype(dtype)
+    return coefs

@@ -3,7 +3,8 @@
 the B-spline table exactly as EinsplineSetBuilder does (tests/eshdf_spline.py) and evaluated at the positions of
 QMCWaveFunctions/tests/test_einset_diamondC.cpp:58-62 in the fcc primitive cell (a general, non-orthorhombic lattice).
 Expected values are that test's literals: :98-113 (value, gradient, Laplacian), :128-136 (Hessian), :232-235 (batched
-evaluate) and :249-268 (mw_evaluateVGLandDetRatioGrads with inv_row = {0.1..0.5}, real build and QMC_COMPLEX build).
+evaluate), :249-268 (mw_evaluateVGLandDetRatioGrads with inv_row = {0.1..0.5}, real build and QMC_COMPLEX build) and
+:392-419 (the 2x1x1 tiling: SplineC2C orbitals from two primitive-cell twists, diamondC_2x1x1_eshdf.npz).
 The reference checks with Catch's Approx (relative 100 * float epsilon ~ 1.2e-5 scaled by the value).
 CPU tests run the oracle; the gpu tests run the CUDA kernels through the C ABI on the same table."""
 import os
@@ -141,6 +142,52 @@ def test_reference_compiled_kernels_on_the_real_table(orc, table_real):
             assert np.allclose(x, y, rtol=1e-6, atol=1e-6)
 
 
+# ---------------------------------------------------------------- 2x1x1 tiling: orbitals from two primitive-cell twists
+R_PRIM = R_LAT  # the spline lives on the primitive cell (BsplineSet::PrimLattice); the supercell only tiles it
+
+
+@pytest.fixture(scope="module")
+def data2():
+    return np.load(os.path.join(HERE, "golden", "diamondC_2x1x1_eshdf.npz"))
+
+
+@pytest.fixture(scope="module")
+def table_2x1x1(orc, data2):
+    labels = [tuple(x) for x in data2["band_labels"]]
+    assert eshdf_spline.band_order(data2["eigenvalues"], 5) == labels == [(0, 0), (1, 0), (1, 1), (1, 2), (1, 3)]
+    assert eshdf_spline.mesh_size(data2["gvectors"]) == [44, 40, 40]
+    tw = [k for k, _ in labels]
+    coefs = eshdf_spline.build_table_c2c_twists(orc, data2["psi_g"], tw, data2["reduced_k"], data2["gvectors"], np.float32)
+    G = np.linalg.inv(R_PRIM)
+    kcart = np.stack([eshdf_spline.k_cart(G, data2["reduced_k"][k]) for k in tw])
+    return coefs, kcart
+
+
+def check_2x1x1(psi, dpsi, d2psi):
+    # test_einset_diamondC.cpp:392-419 (QMC_COMPLEX build: real and imaginary parts), electron 1 at (0, 1, 0)
+    def c(re, im):
+        return pytest.approx(complex(re, im), rel=2e-5, abs=2e-5)
+    assert psi[1][0] == c(0.9008999467, 0.9008999467)
+    assert psi[1][1] == c(1.2383049726, 1.2383049726)
+    assert dpsi[1][0][0] == c(0.0025820041, 0.0025820041)
+    assert dpsi[1][0][1] == c(-0.1880052537, -0.1880052537)
+    assert dpsi[1][0][2] == c(-0.0025404284, -0.0025404284)
+    assert dpsi[1][1][0] == c(0.1069662273, 0.1069453433)
+    assert dpsi[1][1][1] == c(-0.4364597797, -0.43649593)
+    assert dpsi[1][1][2] == c(-0.106951952, -0.1069145575)
+    assert d2psi[1][0] == c(-1.3757134676, -1.3757134676)
+    assert d2psi[1][1] == c(-2.4803137779, -2.4919104576)
+
+
+POS5 = np.array([[0.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 1.1, 0.0], [0.0, 1.2, 0.0], [0.0, 1.3, 0.0]])
+
+
+def test_oracle_two_twists_complex(orc, table_2x1x1):
+    coefs, kcart = table_2x1x1
+    psi, dpsi, d2psi = orc.c2c_vgl(coefs, np.linalg.inv(R_PRIM), kcart, 5, POS5)
+    check_2x1x1(psi, dpsi, d2psi)
+
+
 # ---------------------------------------------------------------- CUDA kernels through the C ABI
 @pytest.fixture(scope="module")
 def api():
@@ -181,3 +228,15 @@ def test_gpu_ratio_grads_complex(api, table_cplx):
     out = spo.mw_evaluateVGLandDetRatioGrads(POS, inv)
     ratios, grads = out[-2], out[-1]
     check_ratio_grads_cplx(ratios, grads)
+
+
+@pytest.mark.gpu
+def test_gpu_two_twists_complex(api, orc, table_2x1x1):
+    coefs, kcart = table_2x1x1
+    G = np.linalg.inv(R_PRIM)
+    spo = api.SplineSPOSet(coefs, 5, G, kind=api.C2C, kcart=kcart)
+    psi, dpsi, d2psi = spo.mw_evaluateVGL(POS5)
+    check_2x1x1(psi, dpsi, d2psi)
+    opsi, odpsi, od2psi = orc.c2c_vgl(coefs, G, kcart, 5, POS5)
+    for a, b in ((psi, opsi), (dpsi, odpsi), (d2psi, od2psi)):
+        assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max()
