@@ -1153,7 +1153,21 @@ struct Crowd : CrowdBase
     }
     const int n = D.n;
     // U'[c x n] = Binv[c x c] * V[c x n]  (0.8 MFLOP per walker at a64; the fused kernel reads it back from L2)
-    wb64::binv_v_kernel<V><<<dim3(blocks(n, 128), nw, blocks(c, 8)), 128, 0, st>>>(D, c);
+    static const int up_simt = env_flag("QMCB_UP_SIMT", 0);
+    if (up_simt)
+      wb64::binv_v_kernel<V><<<dim3(blocks(n, 128), nw, blocks(c, 8)), 128, 0, st>>>(D, c);
+    else
+    {
+      constexpr size_t smem_b = (size_t)KD * (KD + 4) * sizeof(V);
+      static bool attr_b_set  = false;
+      if (!attr_b_set)
+      {
+        QMCB_CUDA(cudaFuncSetAttribute(wb64::binv_v_dmma_kernel<V, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_b));
+        attr_b_set = true;
+      }
+      wb64::binv_v_dmma_kernel<V, KD><<<nw, wb64::TPB, smem_b, st>>>(D, c);
+    }
     QMCB_LAUNCH_CHECK();
     static const int split_env = [] {
       const char* e = std::getenv("QMCB_DMMA_SPLIT");

@@ -200,6 +200,67 @@ __global__ void __launch_bounds__(128) binv_v_kernel(const DetDev<V> D, const in
       Uw[(size_t)(a0 + q) * n] = acc[q];
 }
 
+// The same product on the FP64 tensor pipe: one CTA (8 warps) per walker, Binv staged once in shared memory (A operand,
+// row stride = 4 mod 16 doubles), the B fragments of a column tile (4 rows x 8 consecutive columns of V = 64-byte
+// segments) straight from global memory one tile ahead, U' stored from the accumulator fragments.  No shared memory for V.
+// grid = nw, 256 threads, KD * (KD + 4) * sizeof(V) bytes of dynamic shared memory.
+template<typename V, int KD>
+__global__ void __launch_bounds__(TPB) binv_v_dmma_kernel(const DetDev<V> D, const int c)
+{
+  constexpr int SB = KD + 4, NR = KD / 8, KS = KD / 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  V* Bs = reinterpret_cast<V*>(smem_raw);
+  const int n = D.n, k = D.k, iw = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const V* B  = D.Binv + (size_t)iw * k * k;
+  const V* Vw = D.V + (size_t)iw * k * n;
+  V* Uw       = D.Up + (size_t)iw * k * n;
+  for (int e = tid; e < KD * KD; e += TPB)
+  {
+    const int a = e / KD, b = e - a * KD;
+    Bs[a * SB + b] = (a < c && b < c) ? B[(size_t)a * k + b] : zero_v<V>();
+  }
+  const int ntile = (n + 7) / 8;
+  auto load_b = [&](const int ct, V (&b)[KS]) {
+    const int col = ct * 8 + g;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+    {
+      const int row = ks * 4 + t;
+      b[ks]         = (ct < ntile && row < c && col < n) ? Vw[(size_t)row * n + col] : zero_v<V>();
+    }
+  };
+  V bcur[KS], bnext[KS];
+  load_b(warp, bnext);
+  __syncthreads();
+  for (int ct = warp; ct < ntile; ct += TPB / 32)
+  {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+      bcur[ks] = bnext[ks];
+    load_b(ct + TPB / 32, bnext);
+#pragma unroll
+    for (int rt = 0; rt < NR; ++rt)
+    {
+      if (rt * 8 >= c)
+        break;
+      Acc<V> acc;
+      acc.zero();
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+        acc.mma(lds_v(Bs + (rt * 8 + g) * SB + ks * 4 + t), bcur[ks]);
+      const int row = rt * 8 + g, col = ct * 8 + 2 * t;
+      if (row < c)
+      {
+        if (col < n)
+          Uw[(size_t)row * n + col] = acc.get(0);
+        if (col + 1 < n)
+          Uw[(size_t)row * n + col + 1] = acc.get(1);
+      }
+    }
+  }
+}
+
 // real: rows of U, U' (stride n) must be 16-byte aligned for cp.async, i.e. n even
 template<typename V>
 inline bool eligible(int n, int k, int c, int KD)
