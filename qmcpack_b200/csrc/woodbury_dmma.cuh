@@ -378,114 +378,139 @@ __global__ void __launch_bounds__(TPB, value_traits<V>::is_complex ? 1 : 2)
   }
   load_a(blockIdx.x * RT, 0);
 
-  Acc<V> acc1[NT1];
-  for (int s = 0; s < total; ++s)
-  {
+  // one pipeline step: chunk s has landed and is visible, the buffer consumed at step s - 1 is refilled
+  auto step = [&](const int s) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
     if (s + STAGES - 1 < total)
       stage(s + STAGES - 1);
     cp_async_commit();
-
-    const int it = s / (2 * nch), q = s - it * 2 * nch;
+  };
+  // real, k <= 32: the -T fragments of the second product (2 row tiles x 8 k-steps = 16 doubles) stay in registers for
+  // the whole tile; otherwise they are re-read from shared memory per chunk (complex: four DMMAs per fragment pair)
+  constexpr bool HOIST = !C::CPLX && KD <= 32;
+  int s = 0;
+  for (int it = 0; it < niter; ++it)
+  {
     const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * RT;
-    const V* buf = ring + (size_t)(s % STAGES) * STAGE_ELEMS;
-    if (q < nch)
     {
-      // ---- first product: -T[8 rows of this warp][KD] accumulates over the K chunk
-      V acur[KS1];
-#pragma unroll
-      for (int ks = 0; ks < KS1; ++ks)
-        acur[ks] = anext[ks];
-      if (q == 0)
-      {
-#pragma unroll
-        for (int nt = 0; nt < NT1; ++nt)
-          acc1[nt].zero();
-        const int m0n = m0 + (int)gridDim.x * RT;
-        if (tid == 0 && m0n < n)
-          prefetch_l2_bulk_hint(Ainv + (size_t)m0n * lda, (unsigned)(min(RT, n - m0n) * lda * sizeof(V)), pol_keep);
-      }
-      if (q + 1 < nch)
-        load_a(m0, q + 1);
-      else
-        load_c(m0, 0);
-#pragma unroll
-      for (int ks = 0; ks < KS1; ++ks)
-#pragma unroll
-        for (int nt = 0; nt < NT1; ++nt)
-          acc1[nt].mma(acur[ks], lds_v(buf + (nt * 8 + g) * SU + ks * 4 + t));
-      if (q == nch - 1)
-      {
-        // store -T with the applyW fix-up ( T[list[a]][a] -= 1  ->  (-T) += 1 ); pseudo-accepted slots carry -1
-        const int row = m0 + warp * 8 + g;
-#pragma unroll
-        for (int nt = 0; nt < NT1; ++nt)
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-          {
-            const int a = nt * 8 + 2 * t + i;
-            V v         = -acc1[nt].get(i);
-            if (lst[a] == row)
-              v += V(1.0);
-            Ts[(warp * 8 + g) * ST + a] = v;
-          }
-      }
+      const int m0n = m0 + (int)gridDim.x * RT;
+      if (tid == 0 && m0n < n)
+        prefetch_l2_bulk_hint(Ainv + (size_t)m0n * lda, (unsigned)(min(RT, n - m0n) * lda * sizeof(V)), pol_keep);
     }
-    else
+    // ---- first product: -T[8 rows of this warp][KD] accumulates over the K chunks
     {
-      // ---- second product: tile[:, chunk] += (-T) * U'[:, chunk]
-      const int j0 = (q - nch) * KC;
-      Acc<V> acc[2][JT];
+      Acc<V> acc1[NT1];
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < JT; ++j)
-        {
-          acc[i][j].set(0, cnext[i][j][0]);
-          acc[i][j].set(1, cnext[i][j][1]);
-        }
-      if (q + 1 < 2 * nch)
-        load_c(m0, j0 + KC);
-      else if (it + 1 < niter)
-        load_a(m0 + (int)gridDim.x * RT, 0);
-#pragma unroll
-      for (int ks = 0; ks < KS2; ++ks)
+      for (int nt = 0; nt < NT1; ++nt)
+        acc1[nt].zero();
+      for (int q = 0; q < nch; ++q, ++s)
       {
-        V a[2], b[JT];
+        step(s);
+        const V* buf = ring + (size_t)(s % STAGES) * STAGE_ELEMS;
+        V acur[KS1];
+#pragma unroll
+        for (int ks = 0; ks < KS1; ++ks)
+          acur[ks] = anext[ks];
+        if (q + 1 < nch)
+          load_a(m0, q + 1);
+        else
+          load_c(m0, 0);
+#pragma unroll
+        for (int ks = 0; ks < KS1; ++ks)
+#pragma unroll
+          for (int nt = 0; nt < NT1; ++nt)
+            acc1[nt].mma(acur[ks], lds_v(buf + (nt * 8 + g) * SU + ks * 4 + t));
+      }
+      // store -T with the applyW fix-up ( T[list[a]][a] -= 1  ->  (-T) += 1 ); pseudo-accepted slots carry -1
+      const int row = m0 + warp * 8 + g;
+#pragma unroll
+      for (int nt = 0; nt < NT1; ++nt)
 #pragma unroll
         for (int i = 0; i < 2; ++i)
-          a[i] = lds_v(Ts + ((2 * rp + i) * 8 + g) * ST + ks * 4 + t);
+        {
+          const int a = nt * 8 + 2 * t + i;
+          V v         = -acc1[nt].get(i);
+          if (lst[a] == row)
+            v += V(1.0);
+          Ts[(warp * 8 + g) * ST + a] = v;
+        }
+    }
+    // ---- second product: tile[:, chunk] += (-T) * U'[:, chunk]
+    {
+      V th[HOIST ? 2 : 1][HOIST ? KS2 : 1];
+      for (int q = 0; q < nch; ++q, ++s)
+      {
+        step(s); // (its barrier also publishes -T)
+        const V* buf = ring + (size_t)(s % STAGES) * STAGE_ELEMS;
+        if constexpr (HOIST)
+        {
+          if (q == 0)
+          {
 #pragma unroll
-        for (int j = 0; j < JT; ++j)
-          b[j] = lds_v(buf + (ks * 4 + t) * SP + (cp * JT + j) * 8 + g);
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int ks = 0; ks < KS2; ++ks)
+                th[i][ks] = lds_v(Ts + ((2 * rp + i) * 8 + g) * ST + ks * 4 + t);
+          }
+        }
+        const int j0 = q * KC;
+        Acc<V> acc[2][JT];
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int j = 0; j < JT; ++j)
-            acc[i][j].mma(a[i], b[j]);
-      }
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < JT; ++j)
-        {
-          const int row = m0 + (2 * rp + i) * 8 + g, col = j0 + (cp * JT + j) * 8 + 2 * t;
-          V* p          = Ainv + (size_t)row * lda + col;
-          if (row < n && col + 1 < n)
           {
-            if constexpr (C::CPLX)
-            {
-              const cx<double> v0 = acc[i][j].get(0), v1 = acc[i][j].get(1);
-              st_hint2(reinterpret_cast<double*>(p), v0.re, v0.im, pol_drop);
-              st_hint2(reinterpret_cast<double*>(p + 1), v1.re, v1.im, pol_drop);
-            }
-            else
-              st_hint2(p, acc[i][j].get(0), acc[i][j].get(1), pol_drop);
+            acc[i][j].set(0, cnext[i][j][0]);
+            acc[i][j].set(1, cnext[i][j][1]);
           }
-          else if (row < n && col < n)
-            p[0] = acc[i][j].get(0);
+        if (q + 1 < nch)
+          load_c(m0, j0 + KC);
+        else if (it + 1 < niter)
+          load_a(m0 + (int)gridDim.x * RT, 0);
+#pragma unroll
+        for (int ks = 0; ks < KS2; ++ks)
+        {
+          V a[2], b[JT];
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+          {
+            if constexpr (HOIST)
+              a[i] = th[i][ks];
+            else
+              a[i] = lds_v(Ts + ((2 * rp + i) * 8 + g) * ST + ks * 4 + t);
+          }
+#pragma unroll
+          for (int j = 0; j < JT; ++j)
+            b[j] = lds_v(buf + (ks * 4 + t) * SP + (cp * JT + j) * 8 + g);
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < JT; ++j)
+              acc[i][j].mma(a[i], b[j]);
         }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < JT; ++j)
+          {
+            const int row = m0 + (2 * rp + i) * 8 + g, col = j0 + (cp * JT + j) * 8 + 2 * t;
+            V* p          = Ainv + (size_t)row * lda + col;
+            if (row < n && col + 1 < n)
+            {
+              if constexpr (C::CPLX)
+              {
+                const cx<double> v0 = acc[i][j].get(0), v1 = acc[i][j].get(1);
+                st_hint2(reinterpret_cast<double*>(p), v0.re, v0.im, pol_drop);
+                st_hint2(reinterpret_cast<double*>(p + 1), v1.re, v1.im, pol_drop);
+              }
+              else
+                st_hint2(p, acc[i][j].get(0), acc[i][j].get(1), pol_drop);
+            }
+            else if (row < n && col < n)
+              p[0] = acc[i][j].get(0);
+          }
+      }
     }
   }
   cp_async_wait<0>();
