@@ -59,6 +59,25 @@ def test_reference_3x3_literals(api):
     assert inv[1] == pytest.approx(b, rel=1e-8)  # rejected walker untouched
 
 
+def test_invert_transpose_4x4_literals(api):
+    """mw_invertTranspose literals of test_DiracMatrixInverterCUDA.cpp:63-132 (batch sizes 1, 2, 3 give the same result):
+    inverse transpose and log value (5.267858159063328, 2 pi) through mw_recompute's FP64 LU"""
+    a = np.array([2, 5, 8, 7, 5, 2, 2, 8, 7, 5, 6, 6, 5, 4, 4, 8], float).reshape(4, 4)
+    want = np.array([-0.08247423, -0.26804124, 0.26804124, 0.05154639, 0.18556701, -0.89690722, 0.39690722, 0.13402062,
+                     0.24742268, -0.19587629, 0.19587629, -0.15463918, -0.29896907, 1.27835052, -0.77835052,
+                     0.06185567]).reshape(4, 4)
+    for nw in (1, 2, 3):
+        crowd = api.Crowd(tiny_system(4, np.float64), nw=nw, delay_rank=2)
+        crowd.det_recompute_from_matrices(0, np.stack([a] * nw))
+        inv, logdet = crowd.det_mw_completeUpdates(0)
+        for iw in range(nw):
+            assert inv[iw][:, :4] == pytest.approx(want, abs=2e-8)
+            assert logdet[iw, 0] == pytest.approx(5.267858159063328, rel=1e-12)
+            # the reference accumulates pi per negative pivot without reducing the phase; any representative of the
+            # same phase modulo 2 pi is the same determinant sign
+            assert np.cos(logdet[iw, 1]) == pytest.approx(1.0, abs=1e-12)
+
+
 @pytest.mark.parametrize("dt", [np.float64, np.float32, np.complex128, np.complex64])
 @pytest.mark.parametrize("n,k", [(24, 1), (24, 2), (24, 8), (70, 16), (192, 32), (130, 64)])
 def test_delayed_update_sequence_matches_oracle(api, orc, dt, n, k):

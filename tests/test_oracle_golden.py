@@ -91,6 +91,21 @@ def test_dirac_matrix_inverse(orc):
     assert abs(logdet) == approx(0.0, abs=1e-14)
 
 
+INV_A = np.array([2, 5, 8, 7, 5, 2, 2, 8, 7, 5, 6, 6, 5, 4, 4, 8], float).reshape(4, 4)
+INV_A_LITERAL = np.array([-0.08247423, -0.26804124, 0.26804124, 0.05154639, 0.18556701, -0.89690722, 0.39690722, 0.13402062,
+                          0.24742268, -0.19587629, 0.19587629, -0.15463918, -0.29896907, 1.27835052, -0.77835052,
+                          0.06185567]).reshape(4, 4)
+
+
+def test_invert_transpose_4x4_literals(orc):
+    """test_DiracMatrixInverterCUDA.cpp:63-110 (same matrix and values as test_cuBLAS_LU.cpp:67-110,460-520): inverse
+    transpose and the complex log value, whose phase counts pi per negative pivot WITHOUT reduction (2 pi here)"""
+    inv, logdet = orc.invert_transpose(INV_A, lda=4)
+    assert inv[:, :4] == pytest.approx(INV_A_LITERAL, abs=2e-8)
+    assert logdet.real == pytest.approx(5.267858159063328, rel=1e-12)
+    assert logdet.imag == pytest.approx(6.283185307179586, rel=1e-12)
+
+
 def test_dirac_matrix_update_row(orc):
     """test_DiracMatrix.cpp:315-366 with delay rank 1."""
     a = np.array([[2.3, 4.5, 2.6], [0.5, 8.5, 3.3], [1.8, 4.4, 4.9]])
