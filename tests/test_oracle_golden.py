@@ -172,6 +172,40 @@ def test_bspline_functor_table(orc):
     assert d2u == approx([v[3] for v in J2_VALS], rel=1e-6, abs=1e-9)
 
 
+J1_C_TEST = [-0.2032153051, -0.1625595974, -0.143124599, -0.1216434956, -0.09919771951, -0.07111729038, -0.04445345869,
+             -0.02135082917]
+J1_VALS = [(0.00, -0.1896634025, 0, 0.06586224647), (0.60, -0.1804990512, 0.02606308248, 0.02101469513),
+           (1.20, -0.1637586749, 0.0255799351, -0.01568108497), (1.80, -0.1506226948, 0.01922435549, -0.005504180392),
+           (2.40, -0.1394848415, 0.01869442683, 0.001517191423), (3.00, -0.128023472, 0.01946283614, 0.00104417293),
+           (3.60, -0.1161729491, 0.02009651096, 0.001689229059), (4.20, -0.1036884223, 0.02172284322, 0.003731878464),
+           (4.80, -0.08992443283, 0.0240346508, 0.002736384838), (5.40, -0.07519614609, 0.02475121662, -0.000347832122),
+           (6.00, -0.06054074137, 0.02397053075, -0.001842295859), (6.60, -0.04654631918, 0.0225837382, -0.002780345968),
+           (7.20, -0.03347994129, 0.02104406699, -0.00218107833), (7.80, -0.0211986378, 0.01996899618, -0.00173646255),
+           (8.40, -0.01004416026, 0.01635533409, -0.01030907776), (9.00, -0.002594125744, 0.007782377232, -0.01556475446),
+           (9.60, -0.0001660240476, 0.001245180357, -0.006225901786), (10.20, 0, 0, 0), (10.80, 0, 0, 0), (11.40, 0, 0, 0)]
+
+
+def test_j1_functor_table_logpsi_and_ratios(orc):
+    """test_J1_bspline.cpp: the electron-ion functor (8 coefficients, rcut 10, cusp 0) table :213-243; log psi =
+    0.3160552244 for one ion at (2,0,0) and electrons at (1,0,0), (0,0,0) (:131-132, J1 = exp(-sum u)); the ratios of moving
+    either electron to (0.3, 0.2, 0.5), 0.9819208747 and 1.0040884258 (:282-292).  Open boundaries: plain distances."""
+    r = np.array([v[0] for v in J1_VALS])
+    u, du, d2u = orc.functor_eval(J1_C_TEST, 10.0, 0.0, r)
+    assert u == approx([v[1] for v in J1_VALS], rel=1e-6, abs=1e-9)
+    assert du == approx([v[2] for v in J1_VALS], rel=1e-6, abs=1e-9)
+    assert d2u == approx([v[3] for v in J1_VALS], rel=1e-6, abs=1e-9)
+    ion = np.array([2.0, 0.0, 0.0])
+    elec = np.array([[1.0, 0.0, 0.0], [0.0, 0.0, 0.0]])
+    newpos = np.array([0.3, 0.2, 0.5])
+    d_old = np.linalg.norm(elec - ion, axis=1)
+    d_new = np.linalg.norm(newpos - ion)
+    u_old, _, _ = orc.functor_eval(J1_C_TEST, 10.0, 0.0, d_old)
+    u_new, _, _ = orc.functor_eval(J1_C_TEST, 10.0, 0.0, np.array([d_new]))
+    assert -u_old.sum() == approx(0.3160552244, rel=1e-6)
+    assert np.exp(u_old[0] - u_new[0]) == approx(0.9819208747, rel=1e-6)
+    assert np.exp(u_old[1] - u_new[0]) == approx(1.0040884258, rel=1e-6)
+
+
 def _two_electron_system():
     # open-boundary test geometry emulated by a huge cubic cell (rcut = 10 << L/2)
     L = 400.0
