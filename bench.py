@@ -17,6 +17,8 @@ move, distance rows, spline SPO evaluation, determinant ratio/gradient, J1/J2, M
   roofline  the spline gather kernel timed alone (CUDA events on its stream): algorithmic bytes per launch
             (64*Npad*4 stencil + 5*n*4 phi_vgl write + n*4 inverse-row read per walker) / average duration, against
             the measured HBM copy bandwidth of MEASURED_PEAKS.json (burst figure).
+  flush     the rank-k Woodbury flush (mw_updateInvMat) timed alone through the qmcb_det_time_update_inv_mat hook:
+            algorithmic TF/s, one-pass GB/s and, in full precision, the fraction of the measured FP64 tensor peak.
   cpu_baseline  the reference's CPU path (oracle/_ref: spline2::evaluate_vgh_impl + DelayedUpdate<T> + DiracMatrix compiled
             from /root/reference, else the oracle port) on the host cores, on a bounded sample of the same workload.
 """
