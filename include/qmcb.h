@@ -87,7 +87,7 @@ typedef struct qmcb_system
   /* two-body Jastrow, B-spline functors uu (= dd) and ud; n_j2 = 0 disables (Jastrow/TwoBodyJastrow.h:57) */
   int n_j2;
   const double* j2_uu;
-  const double* j2_ud;
+  const double* j2_ud; /* NULL: the like-spin functor (cusp -1/4 included) serves every pair, as TwoBodyJastrow::addFunc does */
   double j2_rcut;
   /* one-body Jastrow (Jastrow/J1OrbitalSoA.h); nions = 0 disables */
   int nions;

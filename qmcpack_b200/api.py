@@ -241,9 +241,13 @@ class Crowd:
         self._keep = []
         j2 = s.get("j2")
         if j2:
-            uu, ud = np.ascontiguousarray(j2["uu"], np.float64), np.ascontiguousarray(j2["ud"], np.float64)
+            uu = np.ascontiguousarray(j2["uu"], np.float64)
+            # ud = None: only the like-spin correlation was given and serves every pair (TwoBodyJastrow::addFunc)
+            ud = None if j2.get("ud") is None else np.ascontiguousarray(j2["ud"], np.float64)
             self._keep += [uu, ud]
-            q.n_j2, q.j2_uu, q.j2_ud, q.j2_rcut = len(uu), uu.ctypes.data_as(c_dp), ud.ctypes.data_as(c_dp), j2["rcut"]
+            q.n_j2, q.j2_uu, q.j2_rcut = len(uu), uu.ctypes.data_as(c_dp), j2["rcut"]
+            if ud is not None:
+                q.j2_ud = ud.ctypes.data_as(c_dp)
         j1 = s.get("j1")
         if j1:
             ip = np.ascontiguousarray(j1["ion_pos"], np.float64)

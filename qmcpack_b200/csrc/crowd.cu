@@ -911,10 +911,14 @@ struct Crowd : CrowdBase
       A(j2_log, nw);
       jas.rows = rows.p, jas.cur_allu = nullptr, jas.j2_vgl = j2_vgl.p, jas.Uat = Uat.p, jas.dUat = dUat.p;
       jas.d2Uat = d2Uat.p, jas.j2_log = j2_log.p;
-      // cusp -1/4 like spin, -1/2 unlike spin (Jastrow/RadialJastrowBuilder.cpp:200-208)
+      // cusp -1/4 like spin, -1/2 unlike spin (Jastrow/RadialJastrowBuilder.cpp:200-208).  An input that only gives the
+      // like-spin correlation (j2_ud == NULL) uses that functor, cusp included, for every pair: TwoBodyJastrow::addFunc
+      // fills all pair slots when the first (u, u) functor is added (Jastrow/TwoBodyJastrow.cpp, addFunc).
+      const double* ud     = sys.j2_ud ? sys.j2_ud : sys.j2_uu;
+      const double cusp_ud = sys.j2_ud ? -0.5 : -0.25;
       fill_functor(jas.F2[0], pool, sys.j2_uu, sys.n_j2, sys.j2_rcut, -0.25);
-      fill_functor(jas.F2[1], pool, sys.j2_ud, sys.n_j2, sys.j2_rcut, -0.5);
-      fill_functor(jas.F2[2], pool, sys.j2_ud, sys.n_j2, sys.j2_rcut, -0.5);
+      fill_functor(jas.F2[1], pool, ud, sys.n_j2, sys.j2_rcut, cusp_ud);
+      fill_functor(jas.F2[2], pool, ud, sys.n_j2, sys.j2_rcut, cusp_ud);
       fill_functor(jas.F2[3], pool, sys.j2_uu, sys.n_j2, sys.j2_rcut, -0.25);
     }
     jas.has_j1 = sys.nions > 0;
