@@ -5,6 +5,9 @@ SplineC2C orbitals from two primitive-cell twists, complex determinants, meshfac
 the supercell's Wigner-Seitz radius).  The test drives two walkers through mw_evaluateLog, mw_evalGrad, mw_makeMove,
 mw_calcRatioGrad and mw_accept_rejectMove (:259-405) -- exactly the calls of the C ABI.
 
+The same sequence on the 1x1x1 primitive cell, test_TrialWaveFunction.cpp:56-360, pins the REAL branch (SplineR2R, real
+determinants, precision="float" table, Gamma point).
+
 CPU: the wavefunction is restated with numpy on top of the oracle's spline and functor primitives (explicit 2x2
 determinants), which pins those primitives AND documents what the literals mean.  GPU: the same sequence through
 qmcb_twf_mw_* on a two-walker crowd."""
@@ -157,3 +160,96 @@ def test_gpu_twf_sequence_matches_the_reference_literals(orc, spo_data):
     crowd.mw_completeUpdates()
     lp = crowd.mw_evaluateGL()[0]
     assert lp[0] == pytest.approx(LOGPSI_MOVED, rel=1e-8) and lp[1] == pytest.approx(LOGPSI_MOVED, rel=1e-8)
+
+
+# ---------------------------------------------------------------- real orbitals: test_TrialWaveFunction.cpp (1x1x1 cell)
+R_PRIM = np.array([[3.37316115, 3.37316115, 0.0], [0.0, 3.37316115, 3.37316115], [3.37316115, 0.0, 3.37316115]])
+SHIFTS1 = np.array([np.array(c) @ R_PRIM for c in itertools.product(range(-2, 3), repeat=3)])
+WS1 = min(np.linalg.norm(s) for s in SHIFTS1 if np.any(s)) / 2
+# literals of the non-complex branch
+RL_LOGPSI_0, RL_LOGPSI_MOVED = -1.471840358291562, -0.6365029797784554     # :157, :197
+RL_RATIO_ALL, RL_RATIO_FERMI = 2.305591774210242, 2.515045914101833         # :187-188
+RL_GRAD_OLD = [[14.77249702264, -20.385235323777, 4.8529516184558], [47.38770710732, -63.361119579044, 15.318325284049]]
+RL_R_SIGN = [-0.4138835449, -2.5974770159]                                  # :284-285
+RL_GRAD_SIGN_1 = [-17.865723259764, 19.854257889369, -2.9669578650441]      # :286-288
+
+
+class NumpyTWFReal(NumpyTWF):
+    def __init__(self, orc, coefs, G):
+        self.orc, self.coefs, self.G = orc, coefs, G
+
+    def spo(self, r):
+        psi, dpsi, _ = self.orc.r2r_vgl(self.coefs, self.G, 2, np.atleast_2d(r))
+        return psi.astype(np.float64), dpsi.astype(np.float64)
+
+    def u(self, r):
+        return [x[0] for x in self.orc.functor_eval(UU, WS1, -0.25, np.array([r]))]
+
+    @staticmethod
+    def min_image(dv):
+        c = dv + SHIFTS1
+        return c[np.argmin((c**2).sum(1))]
+
+
+def real_table(orc, dtype):
+    d = np.load(os.path.join(HERE, "golden", "diamondC_1x1x1_eshdf.npz"))
+    return eshdf_spline.build_table(orc, d["psi_g"], d["gvectors"], d["reduced_k"], d["eigenvalues"], 2, dtype)
+
+
+def test_numpy_restatement_real_branch(orc):
+    """precision="float" table, double determinant arithmetic: what the reference's full-precision build runs.  Catch's
+    Approx is 1.2e-5 relative; the walker that never moved agrees to 1e-10, the moved one to 1e-7 (FFT library rounding
+    in the float table)."""
+    w = NumpyTWFReal(orc, real_table(orc, np.float32), np.linalg.inv(R_PRIM))
+    l0 = w.logpsi(R0)
+    assert l0.real == pytest.approx(RL_LOGPSI_0, rel=1e-6) and abs(l0.imag) == pytest.approx(np.pi)  # :235-237
+    R1 = R0.copy()
+    R1[0] += DELTA
+    l1 = w.logpsi(R1)
+    assert l1.real == pytest.approx(RL_LOGPSI_MOVED, rel=1e-6)
+    assert np.exp(l1 - l0).real == pytest.approx(RL_RATIO_ALL, rel=1e-6)
+    assert np.exp(w.log_det(R1) - w.log_det(R0)).real == pytest.approx(RL_RATIO_FERMI, rel=1e-6)
+    assert w.grad(R1, 0) == pytest.approx(RL_GRAD_OLD[0], rel=1e-6)
+    assert w.grad(R0, 0) == pytest.approx(RL_GRAD_OLD[1], rel=1e-9)
+    R1s, R0s = R1.copy(), R0.copy()
+    R1s[0] += DELTA_SIGN
+    R0s[0] += DELTA_SIGN
+    assert np.exp(w.logpsi(R1s) - l1).real == pytest.approx(RL_R_SIGN[0], rel=1e-6)
+    assert np.exp(w.logpsi(R0s) - l0).real == pytest.approx(RL_R_SIGN[1], rel=1e-9)
+    assert w.grad(R0s, 0) == pytest.approx(RL_GRAD_SIGN_1, rel=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt,rel", [(np.float64, 1.2e-5), (np.float32, 1e-3)])
+def test_gpu_twf_sequence_real_branch(orc, dt, rel):
+    """full precision (double table; the reference's own Approx tolerance) and mixed precision (float table, float
+    inverse; the reference's MIXED_PRECISION tolerances are 1e-3 on gradients and 2e-4 on ratios)"""
+    from qmcpack_b200 import api, build
+    build.build()
+    api.init(0)
+    coefs = real_table(orc, dt)
+    system = dict(n_up=2, n_dn=2, lattice=R_PRIM, coefs=[coefs, coefs], j2=dict(uu=UU, ud=None, rcut=WS1))
+    crowd = api.Crowd(system, nw=2, delay_rank=2)
+    R1 = R0.copy()
+    R1[0] += DELTA
+    crowd.set_positions(np.stack([R1, R0]))
+    crowd.mw_recompute()
+    lp = crowd.mw_evaluateGL()[0]
+    assert lp[0] == pytest.approx(RL_LOGPSI_MOVED, rel=rel) and lp[1] == pytest.approx(RL_LOGPSI_0, rel=rel)
+    g = np.asarray(crowd.mw_evalGrad(0)).reshape(2, 3)
+    assert g[0] == pytest.approx(RL_GRAD_OLD[0], rel=rel) and g[1] == pytest.approx(RL_GRAD_OLD[1], rel=rel)
+    crowd.mw_makeMove(0, np.stack([DELTA_SIGN, DELTA_SIGN]))
+    ratios, grads = crowd.mw_calcRatioGrad(0)
+    assert ratios[0] == pytest.approx(RL_R_SIGN[0], rel=rel) and ratios[1] == pytest.approx(RL_R_SIGN[1], rel=rel)
+    assert np.asarray(grads).reshape(2, 3)[1] == pytest.approx(RL_GRAD_SIGN_1, rel=rel)
+    crowd.mw_accept_rejectMove(0, [0, 0])
+    crowd.mw_evalGrad(0)
+    crowd.mw_makeMove(0, np.stack([np.zeros(3), DELTA]))
+    ratios, grads = crowd.mw_calcRatioGrad(0)
+    grads = np.asarray(grads).reshape(2, 3)
+    assert ratios[0] == pytest.approx(1.0, rel=rel) and ratios[1] == pytest.approx(RL_RATIO_ALL, rel=rel)
+    assert grads[0] == pytest.approx(RL_GRAD_OLD[0], rel=rel) and grads[1] == pytest.approx(RL_GRAD_OLD[0], rel=rel)
+    crowd.mw_accept_rejectMove(0, [1, 1])
+    crowd.mw_completeUpdates()
+    lp = crowd.mw_evaluateGL()[0]
+    assert lp[0] == pytest.approx(RL_LOGPSI_MOVED, rel=rel) and lp[1] == pytest.approx(RL_LOGPSI_MOVED, rel=rel)
