@@ -58,6 +58,10 @@ struct VMCParams
   const double* kpts[2];
   // 1: the move loop of DMCBatched::advanceWalkers (DMC/DMCBatched.cpp:142-262) instead of VMCBatched's
   int dmc;
+  // optional (0 = the spline lives on `lattice`): the PRIMITIVE cell of the spline table when the simulation cell is a
+  // tiling of it (BsplineSet::PrimLattice, test_TrialWaveFunction_diamondC_2x1x1.cpp)
+  int has_spline_lattice;
+  double spline_lattice[9];
 };
 
 #ifndef QMC_ORACLE_USE_REFERENCE
@@ -153,7 +157,7 @@ struct VMC
     // G = inverse(R) (CrystalLattice.cpp:63)
     const double* R = p.lattice;
     MinImage<double> tmp;
-    tmp.set(R);
+    tmp.set(p.has_spline_lattice ? p.spline_lattice : R);
     double G[9];
     for (int i = 0; i < 9; ++i)
       G[i] = tmp.g[i];
@@ -186,8 +190,11 @@ struct VMC
       // cusp: -1/4 like spin, -1/2 unlike spin (Jastrow/RadialJastrowBuilder.cpp:200-208)
       j2.F[0].set(p.j2_uu, p.n_j2, p.j2_rcut, -0.25);
       j2.F[3].set(p.j2_uu, p.n_j2, p.j2_rcut, -0.25);
-      j2.F[1].set(p.j2_ud, p.n_j2, p.j2_rcut, -0.5);
-      j2.F[2].set(p.j2_ud, p.n_j2, p.j2_rcut, -0.5);
+      // only the like-spin correlation given: TwoBodyJastrow::addFunc fills every pair slot with it (cusp included)
+      const double* ud     = p.j2_ud ? p.j2_ud : p.j2_uu;
+      const double cusp_ud = p.j2_ud ? -0.5 : -0.25;
+      j2.F[1].set(ud, p.n_j2, p.j2_rcut, cusp_ud);
+      j2.F[2].set(ud, p.n_j2, p.j2_rcut, cusp_ud);
     }
     has_j1 = p.nions > 0;
     if (has_j1)

@@ -41,6 +41,7 @@ class VMCParams(C.Structure):
         ("nw", C.c_int), ("ncrowds", C.c_int), ("seeds", C.POINTER(C.c_uint32)),
         ("tau", C.c_double), ("use_drift", C.c_int), ("delay_rank", C.c_int), ("batched_engine", C.c_int),
         ("complex_orbitals", C.c_int), ("kpts", c_dp * 2), ("dmc", C.c_int),
+        ("has_spline_lattice", C.c_int), ("spline_lattice", C.c_double * 9),
     ]
 
 
@@ -353,6 +354,9 @@ class OracleVMC:
         p.precision = prec
         p.n_up, p.n_dn = s["n_up"], s["n_dn"]
         p.lattice[:] = list(np.asarray(s["lattice"], np.float64).ravel())
+        if s.get("spline_lattice") is not None:  # the primitive cell of the table inside a tiled simulation cell
+            p.has_spline_lattice = 1
+            p.spline_lattice[:] = list(np.asarray(s["spline_lattice"], np.float64).ravel())
         self._keep = []
         for i in range(2):
             c = s["coefs"][i]
@@ -363,9 +367,12 @@ class OracleVMC:
         p.npad = int(s["coefs"][0].shape[3])
         j2 = s.get("j2")
         if j2:
-            uu, ud = _np(j2["uu"], np.float64), _np(j2["ud"], np.float64)
+            uu = _np(j2["uu"], np.float64)
+            ud = None if j2.get("ud") is None else _np(j2["ud"], np.float64)  # None: the uu functor serves every pair
             self._keep += [uu, ud]
-            p.n_j2, p.j2_uu, p.j2_ud, p.j2_rcut = len(uu), uu.ctypes.data_as(c_dp), ud.ctypes.data_as(c_dp), j2["rcut"]
+            p.n_j2, p.j2_uu, p.j2_rcut = len(uu), uu.ctypes.data_as(c_dp), j2["rcut"]
+            if ud is not None:
+                p.j2_ud = ud.ctypes.data_as(c_dp)
         j1 = s.get("j1")
         if j1:
             ip = _np(j1["ion_pos"], np.float64)

@@ -253,3 +253,31 @@ def test_gpu_twf_sequence_real_branch(orc, dt, rel):
     crowd.mw_completeUpdates()
     lp = crowd.mw_evaluateGL()[0]
     assert lp[0] == pytest.approx(RL_LOGPSI_MOVED, rel=rel) and lp[1] == pytest.approx(RL_LOGPSI_MOVED, rel=rel)
+
+
+# ---------------------------------------------------------------- the oracle DRIVER itself on the same literals
+def test_oracle_driver_logpsi_on_reference_data(orc, spo_data):
+    """OracleVMC (the checker of the GPU VMC tests) from-scratch evaluation -- spline rows, LU inverse + log-determinant,
+    J2 sums -- gives the reference's log psi for both cells: complex orbitals in the 2x1x1 tiling (spline on the primitive
+    cell) and real orbitals on the 1x1x1 cell."""
+    coefs, Gp, kc = spo_data
+    d2 = np.load(os.path.join(HERE, "golden", "diamondC_2x1x1_eshdf.npz"))
+    sys_c = dict(n_up=2, n_dn=2, lattice=R_SUPER, spline_lattice=d2["primitive_vectors"], coefs=[coefs, coefs],
+                 kpts=[kc, kc], j2=dict(uu=UU, ud=None, rcut=WS_RADIUS))
+    R1 = R0.copy()
+    R1[0] += DELTA
+    ov = oracle_lib.OracleVMC(orc, sys_c, nw=2, ncrowds=1, seeds=[1], delay_rank=2)
+    ov.set_positions(np.stack([R1, R0]))
+    ov.recompute()
+    lp = ov.evaluate_gl()[0]
+    assert lp[0] == pytest.approx(LOGPSI_MOVED, rel=1e-9) and lp[1] == pytest.approx(LOGPSI_0, rel=1e-9)
+    # (the reference's literals come from a float table under double determinants; the oracle driver is all-double or
+    # all-float, so the double table is checked within the reference's own Approx and the float one within 1e-4)
+    for dt, rel in ((np.float64, 1.2e-5), (np.float32, 1e-4)):
+        tab = real_table(orc, dt)
+        sys_r = dict(n_up=2, n_dn=2, lattice=R_PRIM, coefs=[tab, tab], j2=dict(uu=UU, ud=None, rcut=WS1))
+        ov = oracle_lib.OracleVMC(orc, sys_r, nw=2, ncrowds=1, seeds=[1], delay_rank=2)
+        ov.set_positions(np.stack([R1, R0]))
+        ov.recompute()
+        lp = ov.evaluate_gl()[0]
+        assert lp[0] == pytest.approx(RL_LOGPSI_MOVED, rel=rel) and lp[1] == pytest.approx(RL_LOGPSI_0, rel=rel)
