@@ -106,6 +106,17 @@ def test_invert_transpose_4x4_literals(orc):
     assert logdet.imag == pytest.approx(6.283185307179586, rel=1e-12)
 
 
+def test_complex_log_determinant_literal(orc):
+    """test_cuBLAS_LU.cpp:112-166 (log value of the LU factors) for the matrix of :295-310: log|det| = 5.603777579195571 and
+    a phase of -6.1586603331188225, i.e. +0.1245249740607652 modulo 2 pi (the reference does not reduce the phase)"""
+    m = np.array([2.0 + 0.1j, 5.0 + 0.1j, 8.0 + 0.5j, 7.0 + 1.0j, 5.0 + 0.1j, 2.0 + 0.2j, 2.0 + 0.1j, 8.0 + 0.5j, 7.0 + 0.2j,
+                  5.0 + 1.0j, 6.0 - 0.2j, 6.0 - 0.2j, 5.0 + 0.0j, 4.0 - 0.1j, 4.0 - 0.6j, 8.0 - 2.0j]).reshape(4, 4)
+    inv, logdet = orc.invert_transpose(m, lda=4)
+    assert logdet.real == pytest.approx(5.603777579195571, rel=1e-13)
+    assert np.exp(1j * logdet.imag) == pytest.approx(np.exp(-6.1586603331188225j), abs=1e-12)
+    assert inv[:, :4] == pytest.approx(np.linalg.inv(m).T, abs=1e-13)
+
+
 def test_dirac_matrix_update_row(orc):
     """test_DiracMatrix.cpp:315-366 with delay rank 1."""
     a = np.array([[2.3, 4.5, 2.6], [0.5, 8.5, 3.3], [1.8, 4.4, 4.9]])
