@@ -217,6 +217,21 @@ def test_j1_functor_table_logpsi_and_ratios(orc):
     assert np.exp(u_old[1] - u_new[0]) == approx(1.0040884258, rel=1e-6)
 
 
+def test_j2_move_ratios_and_accept(orc):
+    """test_J2_bspline.cpp:213-246: electrons (up, down) at (1,0,0), (0,0,0), open boundaries; moving either to
+    (0.3, 0.2, 0.5) gives the ratios 0.9522052017 / 0.9871985577, a virtual move of electron 1 to (0.2, 0.5, 0.3) gives
+    0.9989268241, and after accepting the move of electron 1 the log value is 0.0883791773"""
+    def u(r):
+        return orc.functor_eval(J2_UD_TEST, 10.0, -0.5, np.array([r]))[0][0]
+    r0, r1 = np.array([1.0, 0.0, 0.0]), np.zeros(3)
+    new, new2 = np.array([0.3, 0.2, 0.5]), np.array([0.2, 0.5, 0.3])
+    d01 = np.linalg.norm(r0 - r1)
+    assert np.exp(u(d01) - u(np.linalg.norm(new - r1))) == approx(0.9522052017, rel=1e-6)
+    assert np.exp(u(d01) - u(np.linalg.norm(new - r0))) == approx(0.9871985577, rel=1e-6)
+    assert np.exp(u(d01) - u(np.linalg.norm(new2 - r0))) == approx(0.9989268241, rel=1e-6)
+    assert -u(np.linalg.norm(new - r0)) == approx(0.0883791773, rel=1e-6)
+
+
 def _two_electron_system():
     # open-boundary test geometry emulated by a huge cubic cell (rcut = 10 << L/2)
     L = 400.0
