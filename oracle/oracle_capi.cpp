@@ -458,6 +458,22 @@ int orc_vmc_set_positions(void* hv, const double* R)
   auto* h = static_cast<VMCHandle*>(hv);
   return guarded([&] { VMC_DISPATCH(h, v.setPositions(R)); });
 }
+// TrialWaveFunction evalGrad / makeMove / calcRatioGrad of walker iw for a prescribed displacement (no accept);
+// ratio [2], grad_old [3][2], grad_new [3][2] as (re, im) doubles
+int orc_vmc_probe_move(void* hv, int iw, int iat, const double* displ, double* ratio, double* grad_old, double* grad_new)
+{
+  auto* h = static_cast<VMCHandle*>(hv);
+  return guarded([&] {
+    std::complex<double> r, go[3], gn[3];
+    VMC_DISPATCH(h, v.probeMove(iw, iat, displ, r, go, gn));
+    ratio[0] = r.real(), ratio[1] = r.imag();
+    for (int d = 0; d < 3; ++d)
+    {
+      grad_old[2 * d] = go[d].real(), grad_old[2 * d + 1] = go[d].imag();
+      grad_new[2 * d] = gn[d].real(), grad_new[2 * d + 1] = gn[d].imag();
+    }
+  });
+}
 int orc_vmc_recompute(void* hv)
 {
   auto* h = static_cast<VMCHandle*>(hv);

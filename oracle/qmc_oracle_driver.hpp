@@ -385,6 +385,62 @@ struct VMC
 
   RT& w_rr_prop(Crowd& cr, int i) { return walkers[cr.w0 + i].rr_proposed; }
 
+  // TrialWaveFunction::evalGrad + ParticleSet::makeMove + TrialWaveFunction::calcRatioGrad for ONE walker and a given
+  // displacement, without accepting (TrialWaveFunction.cpp:568-833 in the order SlaterDet, J2, J1) -- the same blocks
+  // advanceCrowd strings together, exposed so that the reference's own TrialWaveFunction tests (which prescribe the
+  // displacement) can be replayed.  Gradients keep their complex value (the drift only uses the real part).
+  void probeMove(int iw, int iat, const double displ[3], std::complex<double>& ratio_out, std::complex<double> grad_old[3],
+                 std::complex<double> grad_new[3])
+  {
+    Walker& w     = walkers[iw];
+    const int ig  = group_of(iat);
+    const int row = iat - first_of(ig);
+    Det& d        = w.det[ig];
+    const int n   = d.n;
+    prepareInvRow(d, row);
+    VT g[3]      = {VT(0), VT(0), VT(0)};
+    const VT* dp = &d.dpsiM[(size_t)row * n * 3];
+    for (int j = 0; j < n; ++j)
+      for (int dd = 0; dd < 3; ++dd)
+        g[dd] += d.invRow[j] * dp[3 * j + dd];
+    for (int dd = 0; dd < 3; ++dd)
+    {
+      std::complex<double> t = std::complex<double>(g[dd]);
+      if (has_j2)
+        t += (double)w.j2.dUat[dd * j2.npad + iat];
+      if (has_j1)
+        t += (double)w.j1.Grad[3 * iat + dd];
+      grad_old[dd] = t;
+    }
+    for (int dd = 0; dd < 3; ++dd)
+      w.newpos[dd] = w.R[3 * iat + dd] + (RT)displ[dd];
+    if (has_j2)
+    {
+      mi.row(w.newpos, w.rsoa.data(), npad_pos, N, iat, w.dist_new.data());
+      RT oldpos[3] = {w.rsoa[iat], w.rsoa[npad_pos + iat], w.rsoa[2 * npad_pos + iat]};
+      mi.row(oldpos, w.rsoa.data(), npad_pos, N, iat, w.dist_old.data());
+      w.dist_old[iat] = std::numeric_limits<RT>::max();
+    }
+    std::vector<VT> psi(n), dpsi(3 * (size_t)n), d2psi(n);
+    spoVGL(w, ig, w.newpos, psi.data(), dpsi.data(), d2psi.data());
+    VT ratio(0), gn[3] = {VT(0), VT(0), VT(0)};
+    for (int j = 0; j < n; ++j)
+    {
+      ratio += d.invRow[j] * psi[j];
+      for (int dd = 0; dd < 3; ++dd)
+        gn[dd] += d.invRow[j] * dpsi[3 * j + dd];
+    }
+    std::complex<double> r = std::complex<double>(static_cast<PsiV>(ratio));
+    RT gj[3]               = {RT(0), RT(0), RT(0)};
+    if (has_j2)
+      r *= (double)j2.ratioGrad(w.j2, iat, w.dist_new.data(), gj);
+    if (has_j1)
+      r *= (double)j1.ratioGrad(w.j1, mi, iat, w.newpos, gj);
+    ratio_out = r;
+    for (int dd = 0; dd < 3; ++dd)
+      grad_new[dd] = std::complex<double>(gn[dd] / ratio) + (double)gj[dd];
+  }
+
   // one sweep step for one crowd
   // forced (optional, [N][nw]): accept flags imposed from outside ("teacher forcing" for mixed-precision parity: the
   // uniform is still drawn under the reference's rule so that the stream stays aligned); ratio_log (optional, [N][nw]):

@@ -420,6 +420,14 @@ class OracleVMC:
     def recompute(self):
         self.o._chk(self.o.lib.orc_vmc_recompute(self.h))
 
+    def probe_move(self, iw, iat, displ):
+        """evalGrad, makeMove by `displ`, calcRatioGrad of walker iw (nothing accepted): (ratio, grad_old[3], grad_new[3])
+        as complex numbers (zero imaginary parts for real orbitals)"""
+        d = _np(displ, np.float64)
+        r, go, gn = np.zeros(2), np.zeros(6), np.zeros(6)
+        self.o._chk(self.o.lib.orc_vmc_probe_move(self.h, C.c_int(iw), C.c_int(iat), _p(d), _p(r), _p(go), _p(gn)))
+        return complex(r[0], r[1]), go[0::2] + 1j * go[1::2], gn[0::2] + 1j * gn[1::2]
+
     def sweep(self, nsteps=1, log_accept=False):
         log = np.zeros((nsteps, self.N, self.nw), np.uint8) if log_accept else None
         sec = C.c_double(0)

@@ -256,9 +256,10 @@ def test_gpu_twf_sequence_real_branch(orc, dt, rel):
 
 
 # ---------------------------------------------------------------- the oracle DRIVER itself on the same literals
-def test_oracle_driver_logpsi_on_reference_data(orc, spo_data):
-    """OracleVMC (the checker of the GPU VMC tests) from-scratch evaluation -- spline rows, LU inverse + log-determinant,
-    J2 sums -- gives the reference's log psi for both cells: complex orbitals in the 2x1x1 tiling (spline on the primitive
+def test_oracle_driver_on_reference_data(orc, spo_data):
+    """OracleVMC (the checker of the GPU VMC tests): its from-scratch evaluation -- spline rows, LU inverse +
+    log-determinant, J2 sums -- and the evalGrad / makeMove / calcRatioGrad blocks of its move loop reproduce the reference's
+    literals for both cells: complex orbitals in the 2x1x1 tiling (spline on the primitive
     cell) and real orbitals on the 1x1x1 cell."""
     coefs, Gp, kc = spo_data
     d2 = np.load(os.path.join(HERE, "golden", "diamondC_2x1x1_eshdf.npz"))
@@ -271,6 +272,16 @@ def test_oracle_driver_logpsi_on_reference_data(orc, spo_data):
     ov.recompute()
     lp = ov.evaluate_gl()[0]
     assert lp[0] == pytest.approx(LOGPSI_MOVED, rel=1e-9) and lp[1] == pytest.approx(LOGPSI_0, rel=1e-9)
+    # the move path of the driver (evalGrad / makeMove / calcRatioGrad blocks of advanceCrowd) on the prescribed moves
+    r0, go0, _ = ov.probe_move(0, 0, DELTA_SIGN)
+    r1, go1, gn1 = ov.probe_move(1, 0, DELTA_SIGN)
+    assert go0 == pytest.approx(GRAD_OLD[0], rel=1e-8) and go1 == pytest.approx(GRAD_OLD[1], rel=1e-8)
+    assert r0 == pytest.approx(R_SIGN[0], rel=1e-8) and r1 == pytest.approx(R_SIGN[1], rel=1e-8)
+    assert gn1 == pytest.approx(GRAD_SIGN_1, rel=1e-7)
+    r1, _, gn1 = ov.probe_move(1, 0, DELTA)
+    assert r1 == pytest.approx(RATIO_ALL, rel=1e-9) and gn1 == pytest.approx(GRAD_OLD[0], rel=1e-8)
+    r0, _, gn0 = ov.probe_move(0, 0, np.zeros(3))
+    assert r0 == pytest.approx(1.0, rel=1e-12) and gn0 == pytest.approx(GRAD_OLD[0], rel=1e-8)
     # (the reference's literals come from a float table under double determinants; the oracle driver is all-double or
     # all-float, so the double table is checked within the reference's own Approx and the float one within 1e-4)
     for dt, rel in ((np.float64, 1.2e-5), (np.float32, 1e-4)):
@@ -281,3 +292,10 @@ def test_oracle_driver_logpsi_on_reference_data(orc, spo_data):
         ov.recompute()
         lp = ov.evaluate_gl()[0]
         assert lp[0] == pytest.approx(RL_LOGPSI_MOVED, rel=rel) and lp[1] == pytest.approx(RL_LOGPSI_0, rel=rel)
+        r0, go0, _ = ov.probe_move(0, 0, DELTA_SIGN)
+        r1, go1, gn1 = ov.probe_move(1, 0, DELTA_SIGN)
+        assert go0.real == pytest.approx(RL_GRAD_OLD[0], rel=rel) and go1.real == pytest.approx(RL_GRAD_OLD[1], rel=rel)
+        assert r0.real == pytest.approx(RL_R_SIGN[0], rel=rel) and r1.real == pytest.approx(RL_R_SIGN[1], rel=rel)
+        assert gn1.real == pytest.approx(RL_GRAD_SIGN_1, rel=rel)
+        r1, _, gn1 = ov.probe_move(1, 0, DELTA)
+        assert r1.real == pytest.approx(RL_RATIO_ALL, rel=rel) and gn1.real == pytest.approx(RL_GRAD_OLD[0], rel=rel)
