@@ -282,6 +282,26 @@ def test_oracle_driver_on_reference_data(orc, spo_data):
     assert r1 == pytest.approx(RATIO_ALL, rel=1e-9) and gn1 == pytest.approx(GRAD_OLD[0], rel=1e-8)
     r0, _, gn0 = ov.probe_move(0, 0, np.zeros(3))
     assert r0 == pytest.approx(1.0, rel=1e-12) and gn0 == pytest.approx(GRAD_OLD[0], rel=1e-8)
+    # second half of the reference test (:426-505): both walkers at the accepted position, electron 1 next
+    DISPL_NEXT = np.array([0.1, 0.2, 0.3])
+    ov.set_positions(np.stack([R1, R1]))
+    ov.recompute()
+    grad_next = [complex(-114.82740072726, -7.605305979232e-05), complex(-93.980772428401, -7.605302517238e-05),
+                 complex(64.050803536571, 7.6052975324197e-05)]          # :436-447
+    grad_next_new = [complex(9.6073058494562, -1.4375146770852e-05), complex(6.3111018321898, -1.4375146510386e-05),
+                     complex(-3.2027658046121, 1.4375146020225e-05)]     # :466-477
+    for iw in (0, 1):
+        _, go, gn = ov.probe_move(iw, 1, DISPL_NEXT)
+        assert go == pytest.approx(grad_next, rel=1e-7) and gn == pytest.approx(grad_next_new, rel=1e-7)
+    # walker 0 accepts that move; the inverse of its up determinant after the update (:499-502, psiMinv = (psiM^-1)^T)
+    R2 = R1.copy()
+    R2[1] += DISPL_NEXT
+    ov.set_positions(np.stack([R2, R1]))
+    ov.recompute()
+    minv = ov.psiminv(0, 0)[0]
+    want = np.array([[complex(38.503358805635, -38.503358805645), complex(-31.465077529568, 31.465077529576)],
+                     [complex(-27.188228530061, 27.188228530068), complex(22.759962501254, -22.75996250126)]])
+    assert minv == pytest.approx(want, rel=1e-7)
     # (the reference's literals come from a float table under double determinants; the oracle driver is all-double or
     # all-float, so the double table is checked within the reference's own Approx and the float one within 1e-4)
     for dt, rel in ((np.float64, 1.2e-5), (np.float32, 1e-4)):
