@@ -978,37 +978,106 @@ struct MinImage
   T r[9], g[9];     // general cell: R rows, G = inverse(R)
   T corners[3][8];  // corners[idim][c]
 
+  // ref: Particle/Lattice/LatticeAnalyzer.h:213-246 found_shorter_base
+  static bool found_shorter_base(T rb[3][3])
+  {
+    const T eps = T(10) * std::numeric_limits<T>::epsilon();
+    auto dot3   = [](const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    int imax    = 0;
+    T r2max     = dot3(rb[0], rb[0]);
+    for (int i = 1; i < 3; i++)
+    {
+      T r2 = dot3(rb[i], rb[i]);
+      if ((r2 - r2max) > eps)
+      {
+        r2max = r2;
+        imax  = i;
+      }
+    }
+    T rmax = std::sqrt(r2max);
+    T tol  = T(4.0) * rmax * eps;
+    T rb_new[4][3];
+    for (int d = 0; d < 3; ++d)
+    {
+      rb_new[0][d] = rb[0][d] + rb[1][d] - rb[2][d];
+      rb_new[1][d] = rb[0][d] + rb[2][d] - rb[1][d];
+      rb_new[2][d] = rb[1][d] + rb[2][d] - rb[0][d];
+      rb_new[3][d] = rb[0][d] + rb[1][d] + rb[2][d];
+    }
+    for (int i = 0; i < 4; ++i)
+    {
+      T r2 = dot3(rb_new[i], rb_new[i]);
+      if ((r2 - r2max) < -tol)
+      {
+        for (int d = 0; d < 3; ++d)
+          rb[imax][d] = rb_new[i][d];
+        return true;
+      }
+    }
+    return false;
+  }
+  // ref: LatticeAnalyzer.h:247-272 find_reduced_basis
+  static void find_reduced_basis(T rb[3][3])
+  {
+    const int maxIter = 10000;
+    for (int count = 0; count < maxIter; count++)
+    {
+      T saved[3][3];
+      for (int i = 0; i < 3; ++i)
+        for (int d = 0; d < 3; ++d)
+          saved[i][d] = rb[i][d];
+      bool changed = false;
+      for (int i = 0; i < 3; ++i)
+      {
+        rb[i][0] = rb[i][1] = rb[i][2] = T(0);
+        changed                        = found_shorter_base(rb);
+        for (int d = 0; d < 3; ++d)
+          rb[i][d] = saved[i][d];
+        if (changed)
+          break;
+      }
+      if (!changed && !found_shorter_base(rb))
+        return;
+    }
+    throw std::runtime_error("Reduced basis not found in allowed number of iterations.");
+  }
+
+  // ref: ParticleBConds3DSoa.h:339-386 (DTD_BConds<T,3,PPPG+SOA_OFFSET> constructor: reduced basis rb in T, g = inverse(rb)
+  // in T, corners from rb) and :111-128 (PPPO: box lengths)
   void set(const double R[9])
   {
     ortho = (R[1] == 0 && R[2] == 0 && R[3] == 0 && R[5] == 0 && R[6] == 0 && R[7] == 0);
-    double G[9];
-    // inverse of 3x3
-    const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) +
-        R[2] * (R[3] * R[7] - R[4] * R[6]);
-    G[0] = (R[4] * R[8] - R[5] * R[7]) / det;
-    G[1] = (R[2] * R[7] - R[1] * R[8]) / det;
-    G[2] = (R[1] * R[5] - R[2] * R[4]) / det;
-    G[3] = (R[5] * R[6] - R[3] * R[8]) / det;
-    G[4] = (R[0] * R[8] - R[2] * R[6]) / det;
-    G[5] = (R[2] * R[3] - R[0] * R[5]) / det;
-    G[6] = (R[3] * R[7] - R[4] * R[6]) / det;
-    G[7] = (R[1] * R[6] - R[0] * R[7]) / det;
-    G[8] = (R[0] * R[4] - R[1] * R[3]) / det;
+    T rb[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int d = 0; d < 3; ++d)
+        rb[i][d] = (T)R[3 * i + d];
+    if (!ortho)
+      find_reduced_basis(rb);
+    const T* a = &rb[0][0];
+    // ref: OhmmsPETE/TensorOps.h:906-923 inverse(Tensor<T,3>)
+    const T det  = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+    const T vinv = T(1) / det;
+    g[0]         = vinv * (a[4] * a[8] - a[5] * a[7]);
+    g[1]         = vinv * (a[7] * a[2] - a[8] * a[1]);
+    g[2]         = vinv * (a[1] * a[5] - a[2] * a[4]);
+    g[3]         = vinv * (a[5] * a[6] - a[3] * a[8]);
+    g[4]         = vinv * (a[8] * a[0] - a[6] * a[2]);
+    g[5]         = vinv * (a[2] * a[3] - a[0] * a[5]);
+    g[6]         = vinv * (a[3] * a[7] - a[4] * a[6]);
+    g[7]         = vinv * (a[6] * a[1] - a[7] * a[0]);
+    g[8]         = vinv * (a[0] * a[4] - a[1] * a[3]);
     for (int i = 0; i < 9; ++i)
-    {
-      r[i] = (T)R[i];
-      g[i] = (T)G[i];
-    }
+      r[i] = a[i];
     for (int d = 0; d < 3; ++d)
     {
       const double len = std::sqrt(R[3 * d] * R[3 * d] + R[3 * d + 1] * R[3 * d + 1] + R[3 * d + 2] * R[3 * d + 2]);
       L[d]             = (T)len;
       Linv[d]          = (T)(1.0 / len);
     }
-    // ref :405-420 corners: 0, -a0, -a1, -a2, -(a0+a1), -(a0+a2), -(a1+a2), -(a0+a1+a2)
+    // ref :371-385 corners: 0, -a0, -a1, -a2, -(a0+a1), -(a0+a2), -(a1+a2), -(a0+a1+a2) of the reduced basis
     for (int d = 0; d < 3; ++d)
     {
-      const T a0 = (T)R[0 + d], a1 = (T)R[3 + d], a2 = (T)R[6 + d];
+      const T a0 = rb[0][d], a1 = rb[1][d], a2 = rb[2][d];
       corners[d][0] = T(0);
       corners[d][1] = T(-1) * a0;
       corners[d][2] = T(-1) * a1;

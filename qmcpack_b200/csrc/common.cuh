@@ -6,6 +6,9 @@
 #include <stdexcept>
 #include <string>
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace qmcb
 {
@@ -36,6 +39,25 @@ struct CudaError : std::runtime_error
     qmcb::g_launch_count.fetch_add(1, std::memory_order_relaxed); \
     QMCB_CUDA(cudaPeekAtLastError());                      \
   } while (0)
+
+// Opt a kernel in to `bytes` of dynamic shared memory.  The attribute is per DEVICE (and per kernel), and crowds of one
+// process may live on several GPUs and call in from concurrent host threads: the record is keyed by (kernel, device)
+// and guarded by a mutex -- a process-wide "done once" flag would leave every launch above 48 KB failing on the second GPU.
+template<typename K>
+inline void ensure_dynamic_smem(K kern, size_t bytes)
+{
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> granted;
+  int dev = 0;
+  QMCB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = granted[std::make_pair(reinterpret_cast<const void*>(kern), dev)];
+  if (have < bytes)
+  {
+    QMCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
+}
 
 // getAlignedSize<T> of the reference (Platforms/CPU/SIMD/aligned_allocator.hpp:41-47): 64-byte rows
 template<typename T>

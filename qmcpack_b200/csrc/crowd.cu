@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstring>
 #include <algorithm>
+#include <limits>
 
 namespace qmcb
 {
@@ -243,7 +244,7 @@ __device__ __forceinline__ bool metropolis_warp(const DriverDev<T>& Dr, const Ja
     need              = !reject && prob >= eps;
   }
   // ---- position of this walker's draw in the crowd's stream: look back over the lower-index walkers
-  const unsigned epoch = sweep * (unsigned)(Dr.N + 1) + (unsigned)iat_prev + 1u;
+  const unsigned epoch = (sweep * (unsigned)(Dr.N + 1) + (unsigned)iat_prev + 1u) & 0x7fffffffu; // 31 bits: the flag word keeps bit 0 for `need`
   if (lane == 0)
     *((volatile unsigned*)(R.flags + iw)) = (epoch << 1) | (need ? 1u : 0u);
   unsigned cnt = 0;
@@ -783,7 +784,7 @@ struct Crowd : CrowdBase
   DevBuf<unsigned long long> rng_cnt, n_acc, n_rej;
   DevBuf<unsigned> rng_flags;
   DevBuf<unsigned char> accept_log;
-  bool vmc_ready = false, use_graph = false, mb_attr_set = false;
+  bool vmc_ready = false, use_graph = false;
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_logs = false;
   unsigned long long sweep_backlog = 0;
@@ -988,6 +989,68 @@ struct Crowd : CrowdBase
       cudaEventDestroy(ev_rng_done);
   }
 
+  // LatticeAnalyzer.h:213-275: shortest equivalent basis.  One vector at a time is replaced by the shortest of the four
+  // combinations a+b-c, a+c-b, b+c-a, a+b+c (and, with one vector zeroed, the pairwise sums/differences) until nothing
+  // shrinks.  Done in T like DTD_BConds<T, 3, PPPG + SOA_OFFSET> (ParticleBConds3DSoa.h:339-347).
+  static bool found_shorter_base(T rb[3][3])
+  {
+    const T eps = T(10) * std::numeric_limits<T>::epsilon();
+    auto dot3   = [](const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    int imax    = 0;
+    T r2max     = dot3(rb[0], rb[0]);
+    for (int i = 1; i < 3; ++i)
+    {
+      const T r2 = dot3(rb[i], rb[i]);
+      if ((r2 - r2max) > eps)
+      {
+        r2max = r2;
+        imax  = i;
+      }
+    }
+    const T rmax = std::sqrt(r2max);
+    const T tol  = T(4) * rmax * eps;
+    T cand[4][3];
+    for (int d = 0; d < 3; ++d)
+    {
+      cand[0][d] = rb[0][d] + rb[1][d] - rb[2][d];
+      cand[1][d] = rb[0][d] + rb[2][d] - rb[1][d];
+      cand[2][d] = rb[1][d] + rb[2][d] - rb[0][d];
+      cand[3][d] = rb[0][d] + rb[1][d] + rb[2][d];
+    }
+    for (int i = 0; i < 4; ++i)
+      if ((dot3(cand[i], cand[i]) - r2max) < -tol)
+      {
+        for (int d = 0; d < 3; ++d)
+          rb[imax][d] = cand[i][d];
+        return true;
+      }
+    return false;
+  }
+  static void find_reduced_basis(T rb[3][3])
+  {
+    for (int count = 0; count < 10000; ++count)
+    {
+      T saved[3][3];
+      std::memcpy(saved, rb, sizeof(saved));
+      bool changed = false;
+      for (int i = 0; i < 3; ++i)
+      {
+        rb[i][0] = rb[i][1] = rb[i][2] = T(0);
+        changed                        = found_shorter_base(rb);
+        for (int d = 0; d < 3; ++d)
+          rb[i][d] = saved[i][d];
+        if (changed)
+          break;
+      }
+      if (!changed && !found_shorter_base(rb))
+        return;
+    }
+    throw std::runtime_error("crowd: reduced basis not found in the allowed number of iterations; check the unit cell");
+  }
+
+  // minimum-image data of the cell.  Orthorhombic cells: box lengths (DTD_BConds PPPO, ParticleBConds3DSoa.h:111-139).
+  // General cells: rows, inverse and the 8 corner shifts are all taken from the REDUCED basis (:339-386) -- with the raw
+  // rows of a skewed cell the floor + 8-corner search can miss the nearest image.
   static void set_cell(CellDev<T>& C, const double R[9])
   {
     C.ortho = (R[1] == 0 && R[2] == 0 && R[3] == 0 && R[5] == 0 && R[6] == 0 && R[7] == 0) ? 1 : 0;
@@ -995,27 +1058,33 @@ struct Crowd : CrowdBase
         R[2] * (R[3] * R[7] - R[4] * R[6]);
     if (det == 0)
       throw std::runtime_error("crowd: singular lattice");
-    double G[9];
-    G[0] = (R[4] * R[8] - R[5] * R[7]) / det;
-    G[1] = (R[2] * R[7] - R[1] * R[8]) / det;
-    G[2] = (R[1] * R[5] - R[2] * R[4]) / det;
-    G[3] = (R[5] * R[6] - R[3] * R[8]) / det;
-    G[4] = (R[0] * R[8] - R[2] * R[6]) / det;
-    G[5] = (R[2] * R[3] - R[0] * R[5]) / det;
-    G[6] = (R[3] * R[7] - R[4] * R[6]) / det;
-    G[7] = (R[1] * R[6] - R[0] * R[7]) / det;
-    G[8] = (R[0] * R[4] - R[1] * R[3]) / det;
+    T rb[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int d = 0; d < 3; ++d)
+        rb[i][d] = (T)R[3 * i + d];
+    if (!C.ortho)
+      find_reduced_basis(rb);
+    // inverse(Tensor<T, 3>) in T (OhmmsPETE/TensorOps.h:906-923)
+    const T* a   = &rb[0][0];
+    const T detT = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+    const T vinv = T(1) / detT;
+    C.g[0] = vinv * (a[4] * a[8] - a[5] * a[7]);
+    C.g[1] = vinv * (a[7] * a[2] - a[8] * a[1]);
+    C.g[2] = vinv * (a[1] * a[5] - a[2] * a[4]);
+    C.g[3] = vinv * (a[5] * a[6] - a[3] * a[8]);
+    C.g[4] = vinv * (a[8] * a[0] - a[6] * a[2]);
+    C.g[5] = vinv * (a[2] * a[3] - a[0] * a[5]);
+    C.g[6] = vinv * (a[3] * a[7] - a[4] * a[6]);
+    C.g[7] = vinv * (a[6] * a[1] - a[7] * a[0]);
+    C.g[8] = vinv * (a[0] * a[4] - a[1] * a[3]);
     for (int i = 0; i < 9; ++i)
-    {
-      C.r[i] = (T)R[i];
-      C.g[i] = (T)G[i];
-    }
+      C.r[i] = a[i];
     for (int d = 0; d < 3; ++d)
     {
       const double len = std::sqrt(R[3 * d] * R[3 * d] + R[3 * d + 1] * R[3 * d + 1] + R[3 * d + 2] * R[3 * d + 2]);
       C.L[d]           = (T)len;
       C.Linv[d]        = (T)(1.0 / len);
-      const T a0 = (T)R[0 + d], a1 = (T)R[3 + d], a2 = (T)R[6 + d];
+      const T a0 = rb[0][d], a1 = rb[1][d], a2 = rb[2][d];
       C.corners[d][0] = T(0);
       C.corners[d][1] = T(-1) * a0;
       C.corners[d][2] = T(-1) * a1;
@@ -1148,13 +1217,7 @@ struct Crowd : CrowdBase
   void launch_flush_dmma_as(const DetDev<V>& D, int c)
   {
     constexpr size_t smem = wb64::smem_bytes<V, KD, KC, STAGES>();
-    static bool attr_set  = false;
-    if (!attr_set)
-    {
-      QMCB_CUDA(cudaFuncSetAttribute(wb64::woodbury_flush_dmma_kernel<V, KD, KC, STAGES>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
+    ensure_dynamic_smem(wb64::woodbury_flush_dmma_kernel<V, KD, KC, STAGES>, smem);
     const int n = D.n;
     // U'[c x n] = Binv[c x c] * V[c x n]  (0.8 MFLOP per walker at a64; the fused kernel reads it back from L2)
     static const int up_simt = env_flag("QMCB_UP_SIMT", 0);
@@ -1163,13 +1226,7 @@ struct Crowd : CrowdBase
     else
     {
       constexpr size_t smem_b = (size_t)KD * (KD + 4) * sizeof(V);
-      static bool attr_b_set  = false;
-      if (!attr_b_set)
-      {
-        QMCB_CUDA(cudaFuncSetAttribute(wb64::binv_v_dmma_kernel<V, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_b));
-        attr_b_set = true;
-      }
+      ensure_dynamic_smem(wb64::binv_v_dmma_kernel<V, KD>, smem_b);
       wb64::binv_v_dmma_kernel<V, KD><<<nw, wb64::TPB, smem_b, st>>>(D, c);
     }
     QMCB_LAUNCH_CHECK();
@@ -1223,14 +1280,8 @@ struct Crowd : CrowdBase
       }();
       if (flush_mode == 0 && wb5::eligible(n, D.k, c))
       {
-        static bool attr5_set = false;
-        const size_t smem5    = wb5::smem_bytes(n);
-        if (!attr5_set)
-        {
-          QMCB_CUDA(cudaFuncSetAttribute(wb5::woodbury_flush_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(200 * 1024)));
-          attr5_set = true;
-        }
+        const size_t smem5 = wb5::smem_bytes(n);
+        ensure_dynamic_smem(wb5::woodbury_flush_tc5_kernel, 200 * 1024);
         wb5::woodbury_flush_tc5_kernel<<<dim3((n + wb5::TM - 1) / wb5::TM, nw), wb5::TPB, smem5, st>>>(D, c);
         QMCB_LAUNCH_CHECK();
         delay_count[spin] = 0;
@@ -1243,13 +1294,7 @@ struct Crowd : CrowdBase
       const size_t smem = wb::smem_bytes_f32(n);
       if (c <= wb::KD && n % 4 == 0 && smem <= 227 * 1024)
       {
-        static bool attr_set = false;
-        if (!attr_set)
-        {
-          QMCB_CUDA(cudaFuncSetAttribute(wb::woodbury_flush_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024));
-          attr_set = true;
-        }
+        ensure_dynamic_smem(wb::woodbury_flush_tf32_kernel, 227 * 1024);
         const int ntiles = (n + wb::RT - 1) / wb::RT;
         const int split  = std::min(ntiles, 2);
         wb::woodbury_flush_tf32_kernel<<<dim3(nw, split), wb::TPB, smem, st>>>(D, c);
@@ -1828,11 +1873,8 @@ struct Crowd : CrowdBase
     const size_t smem = (size_t)(10 * nmx + k * (k + 1) + 5 * k) * sizeof(V);
     if (smem > 200 * 1024)
       throw std::runtime_error("determinant too wide for the boundary kernel's shared-memory staging");
-    if (smem > 48 * 1024 && !mb_attr_set)
-    {
-      QMCB_CUDA(cudaFuncSetAttribute(move_boundary_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      mb_attr_set = true;
-    }
+    if (smem > 48 * 1024)
+      ensure_dynamic_smem(move_boundary_kernel<T, V>, 200 * 1024);
     launch_kernel(move_boundary_kernel<T, V>, dim3(nw), dim3(MB_TPB), smem, st, (g_pdl_mode & 3) >= 2, dr, jas, rng, det[igp],
                   iat_prev, rp, cp, rg.p, rg_nparts, phi_vgl.p, det[ign], iat_next, rn, cn, det_grads.p, ext_flags,
                   twf_grads_out);

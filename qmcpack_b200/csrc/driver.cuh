@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(256) mt19937_fill_kernel(RngDev R, unsigned lo
   if (tid == 0)
     s_gen = *R.gen;
   __syncthreads();
-  const unsigned long long pos = R.pos[0]; // possibly stale (smaller): see the fork comment in enqueue_sweep
+  // consumption counter: the two parity slots leapfrog (driver.cuh RngDev::pos), the larger one is the more recent;
+  // possibly stale (smaller): see the fork comment in enqueue_sweep
+  const unsigned long long pos = R.pos[0] > R.pos[1] ? R.pos[0] : R.pos[1];
   unsigned long long gen       = s_gen;
   auto twist = [](uint32_t xi, uint32_t xi1, uint32_t xm) {
     const uint32_t y = (xi & 0x80000000u) | (xi1 & 0x7fffffffu);

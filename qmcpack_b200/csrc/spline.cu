@@ -18,13 +18,9 @@ namespace
 {
 int sm_count()
 {
-  static int n = 0;
-  if (!n)
-  {
-    int dev = 0;
-    QMCB_CUDA(cudaGetDevice(&dev));
-    QMCB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int dev = 0, n = 0;
+  QMCB_CUDA(cudaGetDevice(&dev));
+  QMCB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
   return n;
 }
 
@@ -217,12 +213,7 @@ struct SplineSPO : SplineSPOBase
     A.l2_evict_first = evict;
     auto kern            = spline_gather_kernel<ST, ST, TILE, STAGES, VEC, MODE, C2C, MINB>;
     constexpr size_t smem = SplineSmem<ST, TILE, STAGES, VEC>::BYTES;
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-      QMCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
+    ensure_dynamic_smem(kern, smem);
     const int nunits = nw * ntiles;
     if (nunits == 0)
       return;

@@ -84,7 +84,22 @@ def test_delayed_update_sequence_matches_oracle(api, orc, dt, n, k):
     """random accept/reject sequence, every walker with its own flags: inverse rows, ratios, gradients at every move and
     the flushed inverse / log-determinant at the end must match the oracle's batched engine (pseudo-accepts included)
     and a fresh inverse of the explicitly updated matrix."""
-    nw = 5
+    run_delayed_update_sequence(api, orc, dt, n, k, nmoves=2 * n + 3)
+
+
+# the shapes bench.py runs: NiO-a64 (n = 384, k = 32: three 128-row tiles x three column pieces of the tcgen05 flush, six
+# 64-row tiles of the DMMA flush), NiO-a256 (n = 1536, k = 32) and NiO-a128 (n = 768 complex double, k = 64).  Four full
+# flushes plus a partial one, every move checked.
+@pytest.mark.parametrize("dt,n,k", [(np.float32, 384, 32), (np.float64, 384, 32), (np.complex64, 384, 32),
+                                    (np.complex128, 384, 32), (np.float32, 1536, 32), (np.float64, 1536, 32),
+                                    (np.complex128, 768, 64), (np.float32, 192, 32), (np.float32, 384, 64)],
+                         ids=["a64-f32", "a64-f64", "a64-c64", "a64-c128", "a256-f32", "a256-f64", "a128-c128", "a32-f32",
+                              "a64-f32-k64"])
+def test_delayed_update_benchmarked_shapes(api, orc, dt, n, k):
+    run_delayed_update_sequence(api, orc, dt, n, k, nmoves=4 * k + 5, nw=3)
+
+
+def run_delayed_update_sequence(api, orc, dt, n, k, nmoves, nw=5):
     rng = np.random.default_rng(100 + n + k)
     crowd = api.Crowd(tiny_system(n, dt), nw=nw, delay_rank=k)
     amp = 0.5 / np.sqrt(n)  # keeps the matrices well conditioned so that only rounding separates GPU and CPU
@@ -107,7 +122,6 @@ def test_delayed_update_sequence_matches_oracle(api, orc, dt, n, k):
         assert np.abs(inv0[iw] - ainv[iw][:, :n]).max() < tol * np.abs(ainv[iw]).max()
         assert ld0[iw, 0] == pytest.approx(logdet[iw], rel=1e-10)
     cur_dpsiM = dpsiM.copy()
-    nmoves = 2 * n + 3
     for move in range(nmoves):
         row = move % n
         grads_now = crowd.det_mw_evalGrad(1, row)

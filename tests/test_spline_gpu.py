@@ -136,6 +136,31 @@ def test_det_ratios_virtual_positions(api, orc, dt):
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_c2c_det_ratios_virtual_positions(api, orc, dt):
+    """SPOSet::mw_evaluateDetRatios with complex orbitals (SplineC2COMPTarget.cpp:230-352): twisted V-only evaluation at
+    the quadrature points, plain (unconjugated) complex dot with the reference walker's inverse row"""
+    from qmcpack_b200.workload import random_table
+    from qmcpack_b200.api import C2C
+    lat = LATTICES["general"]
+    G = np.linalg.inv(lat)
+    norb, nw, nvp = 150, 4, 50
+    coefs = random_table((6, 5, 7), 2 * norb, dt, seed=21)
+    rng = np.random.default_rng(22)
+    kcart = rng.normal(size=(norb, 3)) * 0.4
+    spo = api.SplineSPOSet(coefs, norb, G, kind=C2C, kcart=kcart)
+    r_vp = (rng.random((nvp, 3)) * 2 - 0.5) @ lat
+    ref = rng.integers(0, nw, nvp)
+    cdt = np.complex64 if dt == np.float32 else np.complex128
+    invrow = (rng.normal(size=(nw, norb)) + 1j * rng.normal(size=(nw, norb))).astype(cdt)
+    ratios = spo.mw_evaluateDetRatios(r_vp, ref, invrow)
+    psi = orc.c2c_vgl(coefs, G, kcart, norb, r_vp, value_only=True)[0]
+    expect = np.einsum("ij,ij->i", psi.astype(np.complex128), invrow[ref].astype(np.complex128))
+    scale = np.abs(invrow).max() * np.abs(psi).max() * np.sqrt(norb)
+    tol = TOL[np.dtype(dt)] * (4 if dt == np.float32 else 1)
+    assert np.abs(ratios - expect).max() / scale < tol
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("norb", [12, 130, 384])
 def test_c2c_matches_oracle(api, orc, dt, norb):
     """complex orbitals with a twist (SplineC2C.cpp:200-277 / ApplyPhaseC2C.hpp)"""

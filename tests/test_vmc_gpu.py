@@ -15,6 +15,9 @@ def api():
 
 
 LAT_GENERAL = np.array([[6.0, 0.4, 0.0], [0.3, 6.5, -0.2], [0.1, -0.3, 7.0]])
+# the same lattice described by a NON-reduced basis (a1 -> a1 + 2 a0, a2 -> a2 + a0 - a1): the minimum image must come from
+# the reduced basis (find_reduced_basis, LatticeAnalyzer.h:213-272; ParticleBConds3DSoa.h:339-386)
+LAT_SHEARED = np.array([[1, 0, 0], [2, 1, 0], [1, -1, 1]], float) @ LAT_GENERAL
 
 
 def small_system(dt, lattice=None, N=24, M=8):
@@ -22,7 +25,7 @@ def small_system(dt, lattice=None, N=24, M=8):
     return make_system(N=N, M=M, dtype=dt, L=6.0, lattice=lattice)
 
 
-@pytest.mark.parametrize("lattice", [None, LAT_GENERAL], ids=["ortho", "general"])
+@pytest.mark.parametrize("lattice", [None, LAT_GENERAL, LAT_SHEARED], ids=["ortho", "general", "non_reduced"])
 def test_distance_rows_and_j2_ratio(api, orc, lattice):
     """SoaDistanceTableAA temp/old rows and TwoBodyJastrow::mw_ratioGrad against the oracle (orthorhombic and general cell)"""
     from qmcpack_b200.workload import initial_positions
@@ -78,7 +81,7 @@ def host_sweeps(api, orc, s, nw, k, nsteps, tau, seed=1000, use_drift=True):
     return crowd, ov, log, olog
 
 
-@pytest.mark.parametrize("lattice", [None, LAT_GENERAL], ids=["ortho", "general"])
+@pytest.mark.parametrize("lattice", [None, LAT_GENERAL, LAT_SHEARED], ids=["ortho", "general", "non_reduced"])
 @pytest.mark.parametrize("k", [1, 4])
 def test_host_driven_sweep_identical_acceptance_fp64(api, orc, lattice, k):
     """FP64: acceptance sequences identical; positions, log psi, kinetic energy, G and L agree to rounding"""
@@ -218,6 +221,31 @@ def _a32_forced(api, orc, dt, tau=0.3, nw=4, seed=31):
     return s, R, crowd, ov, log, ratios, oratios
 
 
+def _double_twin_ratios(orc, s, R, log, nw, seed, tau, k, use_drift=True):
+    """the oracle in FULL precision on the same table values (the float coefficients widened exactly), teacher-forced with
+    the same accept flags: the yardstick that tells how far a float32 implementation of this path may legitimately be
+    from the exact ratios"""
+    import oracle_lib
+    sd = dict(s)
+    sd["coefs"] = [np.ascontiguousarray(c.astype(np.float64)) for c in s["coefs"]]
+    ovd = oracle_lib.OracleVMC(orc, sd, nw=nw, ncrowds=1, seeds=[seed], tau=tau, use_drift=use_drift, delay_rank=k)
+    ovd.set_positions(R)
+    ovd.recompute()
+    return ovd.sweep_forced(log)
+
+
+def _same_size_as_reference_float(ratios, oratios_f, oratios_d, sel=slice(None), factor=4.0):
+    """product(float) vs exact and oracle(float) vs exact must be errors of the same size: median and 95th percentile of
+    the product's relative error within `factor` of the float oracle's"""
+    den = np.maximum(np.abs(oratios_d), 0.1)
+    e_prod = (np.abs(ratios - oratios_d) / den)[0, sel].ravel()
+    e_orc = (np.abs(oratios_f - oratios_d) / den)[0, sel].ravel()
+    for q in (50, 95):
+        assert np.percentile(e_prod, q) <= factor * np.percentile(e_orc, q) + 1e-6, (q, np.percentile(e_prod, q),
+                                                                                    np.percentile(e_orc, q))
+    return e_prod, e_orc
+
+
 def test_nio_a32_shape_fp64_every_move(api, orc):
     """BASELINE config 2 shape (384 electrons, 192 orbitals/spin, 48^3 grid, delay rank 32) in full precision: every
     move's total wavefunction ratio within 1e-8 relative of the oracle, and the free-running oracle takes the same
@@ -251,6 +279,12 @@ def test_nio_a32_shape_mixed_precision_every_move(api, orc):
     assert rel.max() < 5e-2, rel.max()
     assert np.percentile(rel, 95) < 5e-3
     assert np.median(rel) < 1e-4
+    # anchor of those tolerances: against the FP64 oracle on the same table values the product's float error is the size
+    # of the reference float path's own error (a kernel bug at the 1e-3 level, e.g. in the TF32x3 split, would not be)
+    oratios_d = _double_twin_ratios(orc, s, R, log, nw, 31, 0.3, 32)
+    e_prod, e_orc = _same_size_as_reference_float(ratios, oratios, oratios_d)
+    post_flush = slice(32, None)  # every move after the first Woodbury flush of the first determinant
+    _same_size_as_reference_float(ratios, oratios, oratios_d, sel=post_flush)
     lp, ke, _, _ = crowd.mw_evaluateGL()
     olp, oke, _, _ = ov.evaluate_gl()
     assert lp == pytest.approx(olp, rel=1e-5, abs=2e-2)
@@ -437,6 +471,11 @@ def test_nio_a256_orbital_count_every_move(api, orc, dt):
     else:
         first = np.concatenate([rel[0, :32], rel[0, n:n + 32]])  # before the first flush of each determinant
         assert np.median(first) < 1e-3 and first.max() < 0.2, (np.median(first), first.max())
+        # AFTER the flushes (moves 32..255 of each determinant: seven tcgen05 flushes at n = 1536): the product's error
+        # against the FP64 oracle is the size of the float oracle's own error against it
+        oratios_d = _double_twin_ratios(orc, s, R, log, nw, seed, tau, k, use_drift=False)
+        for lo in (0, n):
+            _same_size_as_reference_float(ratios, oratios, oratios_d, sel=slice(lo + 32, lo + 256))
     # the product's own delayed-update state against ITS from-scratch recompute (checkGL_after_moves of the reference)
     lp, ke, _, _ = crowd.mw_evaluateGL()
     crowd.mw_recompute()
