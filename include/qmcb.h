@@ -189,12 +189,21 @@ typedef struct qmcb_vmc_params
    * wavefunctions reject a node crossing, complex ones never), prob = |ratio|^2 exp(log_gb - log_gf) is tested as a whole
    * against eps and the uniform, and tau |delta|^2 is accumulated per walker for proposed and accepted moves.          */
   int dmc;
+  /* which kernels run the sweep.  0: automatic -- the persistent walker-segment kernel (one CTA per walker for the moves
+   * between two Woodbury flushes: proposal, spline gather, ratio, Metropolis test, accept and next-row preparation in one
+   * launch; csrc/segment.cuh) whenever the wavefunction is eligible (real orbitals, at most 384 per spin) and every
+   * walker's CTA can be resident at once, otherwise the two-kernel path (boundary kernel + spline gather per move).
+   * 1: always the two-kernel path.  2: the segment kernel or an error.  Both give the same acceptance sequence.           */
+  int sweep_kernel;
 } qmcb_vmc_params;
 int qmcb_vmc_init(qmcb_crowd* c, const qmcb_vmc_params* p);
 int qmcb_vmc_sweep(qmcb_crowd* c, int nsteps, uint8_t* accept_log_host);
 /* asynchronous launch of one sweep on the crowd's stream (bench.py brackets it with CUDA events) */
 int qmcb_vmc_sweep_async(qmcb_crowd* c);
 int qmcb_vmc_counts(qmcb_crowd* c, long long* n_accept, long long* n_reject);
+/* 2 when the sweeps of this crowd run on the persistent walker-segment kernel, 1 on the two-kernel path, 0 before
+ * qmcb_vmc_init                                                                                                          */
+int qmcb_vmc_sweep_kernel(qmcb_crowd* c);
 /* DMC: per-walker rr_accepted / rr_proposed of the LAST sweep (walker Properties R2ACCEPTED / R2PROPOSED,
  * DMCBatched.cpp:139-140,191-222), [nw] doubles each.                                                                 */
 int qmcb_dmc_get_rr(qmcb_crowd* c, double* rr_accepted_host, double* rr_proposed_host);

@@ -42,7 +42,7 @@ class QmcbSystem(C.Structure):
 
 class QmcbVmcParams(C.Structure):
     _fields_ = [("tau", C.c_double), ("use_drift", C.c_int), ("seed", C.c_uint32), ("use_cuda_graph", C.c_int),
-                ("dmc", C.c_int)]
+                ("dmc", C.c_int), ("sweep_kernel", C.c_int)]
 
 
 _lib = None
@@ -61,7 +61,7 @@ SYMBOLS = [
     "qmcb_det_mw_complete_updates", "qmcb_det_mw_recompute_from_matrices", "qmcb_det_set_phi_vgl",
     "qmcb_det_mw_ratio_grad_from_phi", "qmcb_det_delay_count", "qmcb_det_time_update_inv_mat",
     "qmcb_dtaa_get_temp_rows", "qmcb_j2_mw_ratio_grad", "qmcb_j2_mw_accept_reject", "qmcb_j2_get_state",
-    "qmcb_vmc_init", "qmcb_vmc_sweep", "qmcb_vmc_sweep_async", "qmcb_vmc_counts", "qmcb_crowd_stream",
+    "qmcb_vmc_init", "qmcb_vmc_sweep", "qmcb_vmc_sweep_async", "qmcb_vmc_counts", "qmcb_vmc_sweep_kernel", "qmcb_crowd_stream",
     "qmcb_dmc_get_rr", "qmcb_crowd_walker_bytes", "qmcb_crowd_pack_walker", "qmcb_crowd_unpack_walker",
     "qmcb_crowd_copy_walker", "qmcb_crowd_set_num_walkers", "qmcb_crowd_num_walkers", "qmcb_crowd_capacity",
 ]
@@ -398,10 +398,16 @@ class Crowd:
         return U, dU, d2U
 
     # ---- device-resident VMC driver
-    def vmc_init(self, tau=0.3, use_drift=True, seed=1000, use_cuda_graph=True, dmc=False):
-        """dmc=True: the move loop of DMCBatched::advanceWalkers (phase rejection, rr accumulators)"""
-        p = QmcbVmcParams(tau, int(use_drift), seed, int(use_cuda_graph), int(dmc))
+    def vmc_init(self, tau=0.3, use_drift=True, seed=1000, use_cuda_graph=True, dmc=False, sweep_kernel=0):
+        """dmc=True: the move loop of DMCBatched::advanceWalkers (phase rejection, rr accumulators).
+        sweep_kernel: 0 automatic, 1 two-kernel path, 2 persistent walker-segment kernel (error if not eligible)"""
+        p = QmcbVmcParams(tau, int(use_drift), seed, int(use_cuda_graph), int(dmc), int(sweep_kernel))
         _chk(lib().qmcb_vmc_init(self.h, C.byref(p)))
+
+    @property
+    def sweep_kernel(self):
+        """2: persistent walker-segment kernel, 1: boundary + gather kernels per move, 0: driver not initialised"""
+        return int(lib().qmcb_vmc_sweep_kernel(self.h))
 
     # ---- the engine interface of qmcpack_b200.dmc.DMC
     def dmc_sweep(self):

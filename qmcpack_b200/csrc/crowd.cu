@@ -5,6 +5,7 @@
 #include "det.cuh"
 #include "jastrow.cuh"
 #include "driver.cuh"
+#include "segment.cuh"
 #include "woodbury.cuh"
 #include "woodbury_tc5.cuh"
 #include "woodbury_dmma.cuh"
@@ -16,6 +17,8 @@
 #include <cstring>
 #include <algorithm>
 #include <limits>
+#include <map>
+#include <mutex>
 
 namespace qmcb
 {
@@ -737,6 +740,40 @@ static int env_flag(const char* name, int dflt)
   return e ? std::atoi(e) : dflt;
 }
 
+// ---- residency budget of the persistent walker-segment kernel (segment.cuh).  Its CTAs wait on one another (RNG order),
+// so every CTA of a launch must be resident, and crowds of one device launch concurrently from their own streams: two
+// half-resident launches would wait on each other's slots for ever.  Every crowd therefore reserves, per device, the SM
+// share of ALL its walkers (walkers / CTAs-per-SM) when its driver is initialised; a crowd that does not fit any more
+// runs the two-kernel path.
+struct SegBudget
+{
+  static std::mutex& mu()
+  {
+    static std::mutex m;
+    return m;
+  }
+  static std::map<int, double>& used()
+  {
+    static std::map<int, double> u;
+    return u;
+  }
+  static bool reserve(int dev, double sms, int sm_count)
+  {
+    std::lock_guard<std::mutex> lock(mu());
+    double& u = used()[dev];
+    if (u + sms > (double)sm_count + 1e-9)
+      return false;
+    u += sms;
+    return true;
+  }
+  static void release(int dev, double sms)
+  {
+    std::lock_guard<std::mutex> lock(mu());
+    double& u = used()[dev];
+    u         = std::max(0.0, u - sms);
+  }
+};
+
 template<typename T, typename V>
 struct Crowd : CrowdBase
 {
@@ -785,6 +822,12 @@ struct Crowd : CrowdBase
   DevBuf<unsigned> rng_flags;
   DevBuf<unsigned char> accept_log;
   bool vmc_ready = false, use_graph = false;
+  // persistent walker-segment kernel (segment.cuh)
+  bool fused = false;
+  double seg_reserved_sms = 0.0;
+  SegRng segrng{};
+  DevBuf<unsigned> seg_flags, seg_tot_tag;
+  DevBuf<unsigned long long> seg_tot_val;
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_logs = false;
   unsigned long long sweep_backlog = 0;
@@ -969,6 +1012,7 @@ struct Crowd : CrowdBase
 
   ~Crowd() override
   {
+    release_segment_slots();
     if (graph_exec)
       cudaGraphExecDestroy(graph_exec);
     if (blas)
@@ -1840,12 +1884,121 @@ struct Crowd : CrowdBase
     rng.state = rng_state.p, rng.ring = rng_ring.p, rng.gen = rng_cnt.p, rng.pos = rng_cnt.p + 1;
     rng.sweep = rng_flags.p + cap, rng.flags = rng_flags.p;
     rng.ring_mask = (unsigned)(ring - 1);
+    setup_segment_kernel(p->sweep_kernel);
     mt19937_seed_kernel<<<1, 32, 0, st>>>(rng, p->seed);
     QMCB_LAUNCH_CHECK();
     mt19937_fill_kernel<<<1, 256, 0, st>>>(rng, 2 * sweep_backlog);
     QMCB_LAUNCH_CHECK();
     sync();
     vmc_ready = true;
+  }
+
+  // ---------------------------------------------------------------- persistent walker-segment kernel (segment.cuh)
+  void release_segment_slots()
+  {
+    if (seg_reserved_sms > 0)
+      SegBudget::release(device, seg_reserved_sms);
+    seg_reserved_sms = 0;
+    fused            = false;
+  }
+  template<int CPT>
+  int segment_occupancy(int spin, size_t& smem)
+  {
+    if constexpr (std::is_same<T, V>::value)
+    {
+      const SegLayout L = seg_layout<T, CPT>(det[spin].n, k, N, jas.has_j1 ? jas.nions : 0);
+      smem              = L.total;
+      if (smem > 227 * 1024)
+        return 0;
+      ensure_dynamic_smem(walker_segment_kernel<T, CPT>, smem);
+      int occ = 0;
+      QMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walker_segment_kernel<T, CPT>, SEG_TPB, smem));
+      return occ;
+    }
+    else
+      return 0;
+  }
+  // mode: qmcb_vmc_params.sweep_kernel (0 automatic, 1 two-kernel path, 2 segment kernel required)
+  void setup_segment_kernel(int mode)
+  {
+    release_segment_slots();
+    {
+      const char* e = std::getenv("QMCB_SWEEP_KERNEL");
+      if (e && mode == 0)
+        mode = std::atoi(e);
+    }
+    if (mode == 1)
+      return;
+    std::string why;
+    if (!std::is_same<T, V>::value)
+      why = "complex orbitals";
+    else if (nmax > 2 * SEG_BOXW)
+      why = "more than 384 orbitals per spin";
+    else if (N + (jas.has_j1 ? jas.nions : 0) + 128 > 65535)
+      why = "too many particles for the 16-bit cutoff lists";
+    int occ = 1 << 30;
+    if (why.empty())
+      for (int spin = 0; spin < 2; ++spin)
+        if (nel[spin] > 0)
+        {
+          size_t smem = 0;
+          const int o = nel[spin] <= SEG_BOXW ? segment_occupancy<1>(spin, smem) : segment_occupancy<2>(spin, smem);
+          occ         = std::min(occ, o);
+        }
+    if (why.empty() && occ <= 0)
+      why = "the walker's working set does not fit in shared memory";
+    if (why.empty())
+    {
+      int sms = 0;
+      QMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+      const double want = (double)cap / (double)occ;
+      if (SegBudget::reserve(device, want, sms))
+        seg_reserved_sms = want;
+      else
+        why = "not every walker's CTA can be resident at once (" + std::to_string(cap) + " walkers, " + std::to_string(occ) +
+            " CTAs per SM, " + std::to_string(sms) + " SMs shared with the other crowds of this device)";
+    }
+    if (!why.empty())
+    {
+      if (mode == 2)
+        throw std::runtime_error("qmcb_vmc_init: the walker-segment kernel was requested but is not available: " + why);
+      return;
+    }
+    fused = true;
+    A(seg_flags, (size_t)N * cap);
+    A(seg_tot_val, (size_t)N + 1);
+    A(seg_tot_tag, (size_t)N + 1);
+    segrng.flags = seg_flags.p, segrng.tot_val = seg_tot_val.p, segrng.tot_tag = seg_tot_tag.p, segrng.stride = cap;
+  }
+  int vmc_sweep_kernel() const override { return vmc_ready ? (fused ? 2 : 1) : 0; }
+  // moves e0 .. e0 + nm - 1 of determinant `spin` in ONE launch (no flush inside: delay_count + nm <= k)
+  void launch_segment(int spin, int e0, int nm)
+  {
+    if constexpr (std::is_same<T, V>::value)
+    {
+      const DetDev<V>& D = det[spin];
+      if (delay_count[spin] + nm > k || e0 + nm > D.n)
+        throw std::runtime_error("launch_segment: the segment crosses a flush or the end of the determinant");
+      const SplineDev<T>& S  = *static_cast<const SplineDev<T>*>(spo[spin]->dev_desc());
+      const CUtensorMap& tm = *static_cast<const CUtensorMap*>(spo[spin]->seg_tensor_map());
+      if (D.n <= SEG_BOXW)
+      {
+        const SegLayout L = seg_layout<T, 1>(D.n, k, N, jas.has_j1 ? jas.nions : 0);
+        walker_segment_kernel<T, 1><<<nw, SEG_TPB, L.total, st>>>(tm, S, drv, jas, rng, segrng, D, first[spin] + e0, e0, nm,
+                                                                    delay_count[spin]);
+      }
+      else
+      {
+        const SegLayout L = seg_layout<T, 2>(D.n, k, N, jas.has_j1 ? jas.nions : 0);
+        walker_segment_kernel<T, 2><<<nw, SEG_TPB, L.total, st>>>(tm, S, drv, jas, rng, segrng, D, first[spin] + e0, e0, nm,
+                                                                    delay_count[spin]);
+      }
+      QMCB_LAUNCH_CHECK();
+      delay_count[spin] += nm;
+      invrow_id[spin] = -1;
+    }
+    else
+      throw std::runtime_error("launch_segment: real orbitals only");
   }
 
   // one launch of move_boundary_kernel: accept of electron iat_prev (or -1) and row preparation of iat_next (or -1).
@@ -1943,6 +2096,19 @@ struct Crowd : CrowdBase
     QMCB_LAUNCH_CHECK();
     rng_advance_kernel<<<1, 32, 0, st>>>(rng, 2 * ((gcount + 1) / 2), N & 1);
     QMCB_LAUNCH_CHECK();
+    if (fused)
+    {
+      // one launch per segment of <= delay_rank moves, then the flush: 2 launches per k moves instead of 2 per move
+      for (int spin = 0; spin < 2; ++spin)
+        for (int e0 = 0; e0 < nel[spin]; e0 += k)
+        {
+          launch_segment(spin, e0, std::min(k, nel[spin] - e0));
+          launch_flush(spin);
+        }
+      twf_complete_updates();
+      QMCB_CUDA(cudaStreamWaitEvent(st, ev_rng_done, 0));
+      return;
+    }
     // per electron: [accept(iat-1) + prepare/propose(iat)] -> {spline gather || Jastrow rows}; the boundary kernel is
     // split in two around a Woodbury flush
     auto boundary = [&](int iat_prev, int iat_next) { launch_boundary(drv, iat_prev, iat_next, nullptr, nullptr); };

@@ -32,6 +32,10 @@ struct SplineSPOBase
   // dots to be added in index order (may be null)
   virtual void evaluate_dev(int mode, int nw, const void* r_dev, const void* invrow_dev, size_t ld_inv,
                             const int* ref_dev, void* phi_dev, void* rg_dev, cudaStream_t st) = 0;
+  // for the fused walker-segment kernel (segment.cuh): the device-side table descriptor (SplineDev<ST>) and the tensor
+  // map whose box is one 8-row slab of the stencil (192 components x 4 z x 2 y x 1 x); CUtensorMap*, R2R tables only
+  virtual const void* dev_desc() const       = 0;
+  virtual const void* seg_tensor_map() const = 0;
 };
 
 SplineSPOBase* make_spline(int precision, int kind, const int grid[3], int n_orb, int n_spl, size_t npad,
@@ -73,6 +77,7 @@ struct CrowdBase
   virtual void vmc_sweep(int nsteps, uint8_t* accept_log)                                                   = 0;
   virtual void vmc_sweep_async()                                                                            = 0;
   virtual void vmc_counts(long long* na, long long* nr)                                                     = 0;
+  virtual int vmc_sweep_kernel() const                                                                      = 0;
   virtual void dmc_get_rr(double* rr_acc, double* rr_prop)                                                  = 0;
   virtual size_t walker_bytes() const                                                                       = 0;
   virtual void pack_walker(int iw, void* dev_buf)                                                           = 0;

@@ -325,6 +325,117 @@ __device__ __forceinline__ void jastrow_move_body(const JastrowDev<RT>& J, const
     J.j1_cur[(size_t)iw * 5 + tid] = acc[5 + tid];
 }
 
+// ---- the same sums by ONE warp (fused walker-segment kernel, segment.cuh: the warp works beside the spline gather of
+// the same move, so no CTA barrier may appear here).  jl: (N + nions) rounded up to 32 entries of shared memory owned by
+// the warp.  All 32 lanes call it; on return every lane holds the ten sums {J2: u, gx, gy, gz, lap; J1: the same} and
+// lane 0 has stored j2_vgl / j1_cur for the accept (jastrow_accept_body) and for API readers.
+template<typename RT>
+__device__ __forceinline__ void jastrow_move_warp(const JastrowDev<RT>& J, const int iw, const int iat, const RT pos[3],
+                                                  unsigned short* jl, RT acc[10])
+{
+  const int lane = threadIdx.x & 31, N = J.N, np = J.npad;
+  const RT* rs = J.rsoa + (size_t)iw * 3 * np;
+#pragma unroll
+  for (int e = 0; e < 10; ++e)
+    acc[e] = RT(0);
+  const int n2 = J.has_j2 ? N : 0, n1 = J.has_j1 ? J.nions : 0;
+  const int gi = (iat < J.n_up ? 0 : 1) * 2;
+  int cnt      = 0;
+  // pass 1: all distances, indices of the in-range pairs compacted in (iteration, lane) order
+  for (int base = 0; base < n2 + n1; base += 64)
+  {
+    // two candidates per lane per trip: the position loads of both are in flight together
+    int idx[2];
+    RT px[2], py[2], pz[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+    {
+      idx[h] = base + 32 * h + lane;
+      px[h] = py[h] = pz[h] = RT(0);
+      if (idx[h] < n2)
+        px[h] = rs[idx[h]], py[h] = rs[np + idx[h]], pz[h] = rs[2 * np + idx[h]];
+      else if (idx[h] < n2 + n1)
+      {
+        const int j = idx[h] - n2;
+        px[h] = J.ion_rsoa[j], py[h] = J.ion_rsoa[J.npad_ion + j], pz[h] = J.ion_rsoa[2 * J.npad_ion + j];
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+    {
+      bool need = false;
+      RT r, dx, dy, dz;
+      if (idx[h] < n2)
+      {
+        min_image(J.cell, pos, px[h], py[h], pz[h], idx[h], iat, r, dx, dy, dz);
+        const FunctorDev<RT>& F = J.F2[gi + (idx[h] < J.n_up ? 0 : 1)];
+        need                    = idx[h] != iat && F.coefs != nullptr && r < F.rcut;
+      }
+      else if (idx[h] < n2 + n1)
+      {
+        min_image(J.cell, pos, px[h], py[h], pz[h], idx[h] - n2, 0, r, dx, dy, dz);
+        const FunctorDev<RT>& F = J.F1[J.ion_grp[idx[h] - n2]];
+        need                    = F.coefs != nullptr && r < F.rcut;
+      }
+      const unsigned mk = __ballot_sync(0xffffffffu, need);
+      if (need)
+        jl[cnt + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)idx[h];
+      cnt += __popc(mk);
+    }
+  }
+  __syncwarp();
+  // pass 2: functors over the list with full warps
+  for (int e = lane; e < cnt; e += 32)
+  {
+    const int idx = jl[e];
+    RT r, dx, dy, dz, du, d2u;
+    if (idx < n2)
+    {
+      min_image(J.cell, pos, rs[idx], rs[np + idx], rs[2 * np + idx], idx, iat, r, dx, dy, dz);
+      const RT u = functor_eval(J.F2[gi + (idx < J.n_up ? 0 : 1)], r, du, d2u);
+      acc[0] += u;
+      acc[1] += du * dx;
+      acc[2] += du * dy;
+      acc[3] += du * dz;
+      acc[4] += d2u + RT(2) * du;
+    }
+    else
+    {
+      const int j = idx - n2;
+      min_image(J.cell, pos, J.ion_rsoa[j], J.ion_rsoa[J.npad_ion + j], J.ion_rsoa[2 * J.npad_ion + j], j, 0, r, dx, dy, dz);
+      const RT u = functor_eval(J.F1[J.ion_grp[j]], r, du, d2u);
+      acc[5] += u;
+      acc[6] += du * dx;
+      acc[7] += du * dy;
+      acc[8] += du * dz;
+      acc[9] += d2u + RT(2) * du;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 10; ++e)
+    acc[e] = warp_sum(acc[e]);
+  if (lane == 0)
+  {
+    if (J.has_j2)
+    {
+      RT* vgl = J.j2_vgl + (size_t)iw * 5;
+      vgl[0]  = acc[0];
+      vgl[1]  = acc[1];
+      vgl[2]  = acc[2];
+      vgl[3]  = acc[3];
+      vgl[4]  = -acc[4];
+    }
+    if (J.has_j1)
+    {
+      RT* cur = J.j1_cur + (size_t)iw * 5;
+#pragma unroll
+      for (int e = 0; e < 5; ++e)
+        cur[e] = acc[5 + e];
+    }
+  }
+  __syncwarp();
+}
+
 // grid = nw
 template<typename RT, bool STORE>
 __global__ void __launch_bounds__(JAS_TPB) jastrow_move_kernel(const JastrowDev<RT> J, const int iat)

@@ -1,0 +1,779 @@
+// qmcpack_b200/csrc/segment.cuh -- the persistent walker-segment kernel of the device-resident sweep (sm_100a).
+//
+// One CTA owns ONE walker for a whole segment of the particle-by-particle loop (the <= delay_rank electron moves between
+// two Woodbury flushes) and runs, per move, everything the reference spreads over TrialWaveFunction::mw_evalGrad /
+// mw_calcRatioGrad / mw_accept_rejectMove and VMCBatched::advanceWalkers (QMCDrivers/VMC/VMCBatched.cpp:106-176):
+//
+//   propose (UNR drift + Gaussian)                                          DriftModifierUNR.cpp:20-31, ParticleSet::mw_makeMove
+//   spline gather of the 4x4x4 stencil + VGL + det ratio / gradient dots     SplineR2R.cpp:414-582 (mw_evaluateVGLandDetRatioGrads)
+//   J1 / J2 sums at the proposed position                                    TwoBodyJastrow.cpp:542-578, J1OrbitalSoA ratioGrad
+//   Metropolis test in the crowd's RNG order                                 VMCBatched.cpp:139-167 (DMC rule DMCBatched.cpp:188-250)
+//   determinant accept / pseudo-accept, Jastrow accept, position commit      DelayedUpdateBatched.h:542-670, TwoBodyJastrow.cpp:631-664
+//   inverse row of the next electron incl. pending delays + old gradient     DelayedUpdateBatched.h:174-235, :354-400
+//
+// Why one kernel: with one launch per step (move_boundary_kernel + spline_gather_kernel, crowd.cu / spline.cuh) every
+// move pays two launch ramps and all walkers march in lock step -- the HBM stream of the gather idles while the
+// boundary's chain of dependent L2 round trips runs and vice versa.  Here every walker's CTA is resident for the whole
+// segment (4 CTAs per SM at NiO-a64 in mixed precision = 592 slots for 512 walkers), walkers drift apart by up to one
+// move, and one walker's stencil streams from HBM while its SM neighbours sit in their boundary chains.  Binv, w, the
+// proposed orbital rows and the partial dots never leave shared memory.
+//
+// Stencil staging: the table is the same 4-D TMA tensor (component, z, y, x) as in spline.cuh, but a stage is a SLAB of
+// the stencil -- all components x 4 z x 2 y x 1 x = 8 rows -- so that the 64 rows of an evaluation stream through a
+// 3-stage ring of 8-row slabs (36 KB at 384 float components) in the reference's accumulation order (x index outer, y
+// index inner, MultiBsplineVGLH.hpp:164-202); the accumulators stay in registers across the slabs.
+//
+// Cross-walker order: the reference draws the uniform of a move only when prob >= eps, walkers in index order, moves in
+// electron order (VMCBatched.cpp:156-158).  Walker iw's stream position at move m is
+//     tot[m] + #{ j < iw : need[m][j] },      tot[m + 1] = tot[m] + #{ all j : need[m][j] }.
+// Every CTA publishes need[m][iw] (tagged with the sweep number) before it looks back, the CTA of the last walker
+// publishes tot[m + 1]; nobody waits for a Metropolis DECISION of another walker.  All CTAs of the launch must be
+// co-resident (the host checks the occupancy and reserves the slots per device, crowd.cu).
+#pragma once
+#include "spline.cuh"
+#include "det.cuh"
+#include "jastrow.cuh"
+#include "driver.cuh"
+
+namespace qmcb
+{
+constexpr int SEG_TPB    = 256; // warps 0-5: spline consumers; warp 6: TMA producer; warp 7: Jastrow sums + Metropolis
+constexpr int SEG_NCONS  = 192;
+constexpr int SEG_NSTAGE = 3;
+constexpr int SEG_ROWS   = 8;   // stencil rows per stage
+constexpr int SEG_BOXW   = 192; // components per TMA box (two boxes per stage at CPT = 2)
+constexpr int SEG_NQ     = 8;   // stages per evaluation
+
+// per-sweep arrays of the cross-walker RNG order (zero-initialised once; entries are tagged with the sweep number)
+struct SegRng
+{
+  unsigned* flags;             // [N][stride]  (tag << 1) | needs_draw
+  unsigned long long* tot_val; // [N + 1] raw outputs consumed before move m
+  unsigned* tot_tag;           // [N + 1]
+  int stride;                  // walker capacity of the crowd
+};
+
+struct SegLayout
+{
+  unsigned ring, phi, x, Bs, vec, red, rgp, sg, hdr, bars, jl, total;
+  int jl_entries;
+};
+
+// shared-memory carve-up (bytes).  CPT = components per consumer thread (1: n <= 192, 2: n <= 384)
+template<typename T, int CPT>
+__host__ __device__ inline SegLayout seg_layout(int n, int k, int N, int nions)
+{
+  auto up = [](unsigned v, unsigned a) { return (v + a - 1) / a * a; };
+  SegLayout L;
+  unsigned o = 0;
+  L.ring = o, o += SEG_NSTAGE * SEG_ROWS * CPT * SEG_BOXW * (unsigned)sizeof(T);
+  L.phi = o, o += up(5 * n * (unsigned)sizeof(T), 16);
+  L.x = o, o += up(n * (unsigned)sizeof(T), 16);
+  L.Bs = o, o += up(k * (k + 1) * (unsigned)sizeof(T), 16);
+  L.vec = o, o += up(4 * k * (unsigned)sizeof(T), 16); // pA, pB, y, w
+  L.red = o, o += 96 * (unsigned)sizeof(T);
+  L.rgp = o, o += 32 * (unsigned)sizeof(T);
+  L.sg = o, o += 8 * (unsigned)sizeof(T);
+  L.hdr = o, o += up((SPL_HDR + SPL_SCRATCH + 4) * (unsigned)sizeof(T), 16);
+  L.bars = o, o += 64;
+  L.jl_entries = (int)up((unsigned)(N + nions + 128), 32);
+  L.jl = o, o += up(2u * (unsigned)L.jl_entries, 16);
+  L.total = o;
+  return L;
+}
+
+#ifdef __CUDACC__
+namespace ptx
+{
+__device__ __forceinline__ void fence_proxy_async()
+{
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+} // namespace ptx
+
+template<typename T, int CPT>
+struct SegVec;
+template<typename T>
+struct SegVec<T, 1>
+{
+  static __device__ __forceinline__ void load(const T* p, T (&o)[1]) { o[0] = p[0]; }
+};
+template<>
+struct SegVec<float, 2>
+{
+  static __device__ __forceinline__ void load(const float* p, float (&o)[2])
+  {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    o[0] = v.x, o[1] = v.y;
+  }
+};
+template<>
+struct SegVec<double, 2>
+{
+  static __device__ __forceinline__ void load(const double* p, double (&o)[2])
+  {
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    o[0] = v.x, o[1] = v.y;
+  }
+};
+
+// proposal of electron iat for walker iw by one warp: lanes 0-2 own one Cartesian component each; every lane returns
+// the proposed position.  g_det: determinant gradient of the prepared row (shared memory).  STORE: publish the
+// displacement, the Gaussian part and the position (Metropolis test, Jastrow accept and API readers take them from memory)
+template<typename T, bool STORE>
+__device__ __forceinline__ void seg_propose(const DriverDev<T>& Dr, const JastrowDev<T>& J, const int iw, const int iat,
+                                            const T* g_det, T newpos[3])
+{
+  const int lane = threadIdx.x & 31;
+  const int d    = lane < 3 ? lane : 0;
+  const T delta  = Dr.deltas[((size_t)iat * Dr.nw + iw) * 3 + d] * Dr.sqrttau;
+  const T rold   = J.rsoa[((size_t)iw * 3 + d) * J.npad + iat];
+  T disp         = delta;
+  if (Dr.use_drift)
+  {
+    T gd = g_det[d];
+    if (J.has_j2)
+      gd += J.dUat[((size_t)iw * 3 + d) * J.npad + iat];
+    if (J.has_j1)
+      gd += J.Grad1[((size_t)iw * 3 + d) * J.N + iat];
+    const T gv[3] = {__shfl_sync(0xffffffffu, gd, 0), __shfl_sync(0xffffffffu, gd, 1), __shfl_sync(0xffffffffu, gd, 2)};
+    T dr[3];
+    get_drift<T>(Dr.tauovermass, gv, dr);
+    disp = (d == 0 ? dr[0] : (d == 1 ? dr[1] : dr[2])) + delta;
+  }
+  const T p = rold + disp;
+  if (STORE && lane < 3)
+  {
+    Dr.drifts[3 * iw + d]    = disp;
+    Dr.delta_cur[3 * iw + d] = delta;
+    J.newpos[3 * iw + d]     = p;
+  }
+  newpos[0] = __shfl_sync(0xffffffffu, p, 0);
+  newpos[1] = __shfl_sync(0xffffffffu, p, 1);
+  newpos[2] = __shfl_sync(0xffffffffu, p, 2);
+}
+
+// Metropolis test of (walker iw, electron iat) by one warp.  q[4]: determinant ratio and gradient dots (undivided).
+// Returns the decision in every lane; rdet_out = determinant ratio.
+template<typename T>
+__device__ __forceinline__ bool seg_metropolis(const DriverDev<T>& Dr, const JastrowDev<T>& J, const RngDev& R, const SegRng& SR,
+                                               const int iw, const int iat, const T q[4], T& rdet_out)
+{
+  const int lane = threadIdx.x & 31;
+  const T rdet   = q[0];
+  double ratio   = (double)rdet;
+  T gn[3]        = {q[1] / rdet, q[2] / rdet, q[3] / rdet};
+  if (J.has_j2)
+  {
+    const T* vgl = J.j2_vgl + (size_t)iw * 5;
+    ratio        = ratio * exp((double)(J.Uat[(size_t)iw * J.npad + iat] - vgl[0]));
+    gn[0] += vgl[1];
+    gn[1] += vgl[2];
+    gn[2] += vgl[3];
+  }
+  if (J.has_j1)
+  {
+    const T* cur = J.j1_cur + (size_t)iw * 5;
+    ratio        = ratio * exp((double)(J.Vat[(size_t)iw * J.N + iat] - cur[0]));
+    gn[0] += cur[1];
+    gn[1] += cur[2];
+    gn[2] += cur[3];
+  }
+  T log_gf = T(0), log_gb = T(0);
+  if (Dr.use_drift)
+  {
+    const T* dl = Dr.delta_cur + 3 * iw;
+    log_gf      = -Dr.oneover2tau * (dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
+    T dr[3];
+    get_drift<T>(Dr.tauovermass, gn, dr);
+    dr[0] += Dr.drifts[3 * iw];
+    dr[1] += Dr.drifts[3 * iw + 1];
+    dr[2] += Dr.drifts[3 * iw + 2];
+    log_gb = -Dr.oneover2tau * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
+  }
+  const T eps = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
+  T prob      = (T)(ratio * ratio); // std::norm(ratio), VMCBatched.cpp:152
+  bool need   = prob >= eps;
+  T rr        = T(0);
+  if (Dr.dmc)
+  {
+    // DMCBatched.cpp:188-250 (see metropolis_warp in crowd.cu)
+    const T* dr       = Dr.deltas + ((size_t)iat * Dr.nw + iw) * 3;
+    rr                = Dr.tauovermass * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
+    const bool reject = !(ratio > 0.0);
+    prob              = (T)(ratio * ratio * (double)exp(log_gb - log_gf));
+    need              = !reject && prob >= eps;
+  }
+  // ---- position of this walker's draw in the crowd's stream
+  const unsigned tag = ((*R.sweep) & 0x3fffffffu) + 1u;
+  volatile unsigned* fl = SR.flags + (size_t)iat * SR.stride;
+  if (lane == 0)
+    fl[iw] = (tag << 1) | (need ? 1u : 0u);
+  unsigned long long base;
+  if (iat == 0)
+    base = R.pos[0]; // left by the sweep prologue (rng_advance_kernel)
+  else
+  {
+    volatile unsigned* tt = SR.tot_tag + iat;
+    while (*tt != tag)
+      __nanosleep(40);
+    __threadfence();
+    base = *((volatile unsigned long long*)(SR.tot_val + iat));
+  }
+  unsigned cnt = 0;
+  for (int j = lane; j < iw; j += 32)
+  {
+    unsigned f;
+    while (((f = fl[j]) >> 1) != tag)
+      __nanosleep(40);
+    cnt += f & 1u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  bool acc = false;
+  if (lane == 0)
+  {
+    if (iw == Dr.nw - 1)
+    {
+      const unsigned long long next = base + cnt + (need ? 1u : 0u);
+      *((volatile unsigned long long*)(SR.tot_val + iat + 1)) = next;
+      __threadfence();
+      *((volatile unsigned*)(SR.tot_tag + iat + 1)) = tag;
+      if (iat == Dr.N - 1)
+        R.pos[(iat + 1) & 1] = next; // where the next sweep's Gaussians start (gauss_kernel reads pos[N & 1])
+    }
+    if (need)
+    {
+      const double u = rng_uniform(R, base + cnt);
+      acc            = Dr.dmc ? (u < (double)prob) : (u < (double)(prob * exp(log_gb - log_gf)));
+    }
+    Dr.accepted[iw] = acc ? 1 : 0;
+    if (Dr.dmc)
+    {
+      Dr.rr_proposed[iw] += rr;
+      if (acc)
+        Dr.rr_accepted[iw] += rr;
+    }
+    if (acc)
+      Dr.n_accept[iw] += 1;
+    else
+      Dr.n_reject[iw] += 1;
+    if (Dr.accept_log)
+      Dr.accept_log[(size_t)iat * Dr.nw + iw] = acc ? 1 : 0;
+  }
+  rdet_out = rdet;
+  return __shfl_sync(0xffffffffu, acc ? 1 : 0, 0) != 0;
+}
+
+// grid = live walkers of the crowd (all co-resident); block = SEG_TPB; dynamic smem = seg_layout(...).total
+// Moves iat0 .. iat0 + nmoves - 1 of one determinant (rows row0 ..), c0 delays pending at entry, no flush inside.
+template<typename T, int CPT>
+__global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
+    walker_segment_kernel(const __grid_constant__ CUtensorMap tmap, const SplineDev<T> S, const DriverDev<T> Dr,
+                          const JastrowDev<T> J, const RngDev R, const SegRng SR, const DetDev<T> D, const int iat0,
+                          const int row0, const int nmoves, const int c0)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ int s_acc;
+  __shared__ T s_ratio;
+  const int n = D.n, k = D.k, kb = k + 1;
+  const int iw = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const SegLayout L = seg_layout<T, CPT>(n, k, J.N, J.has_j1 ? J.nions : 0);
+  constexpr int STAGE_ELEMS = SEG_ROWS * CPT * SEG_BOXW;
+  T* ring   = reinterpret_cast<T*>(smem_raw + L.ring);
+  T* vrow   = ring;     // [n]    Ainv[row]      } live only between two gathers, when the ring is idle
+  T* glrow  = ring + n; // [3][n] gradient rows  }
+  T* phi    = reinterpret_cast<T*>(smem_raw + L.phi); // [5][n] value, gx, gy, gz, lap of the proposed move
+  T* x      = reinterpret_cast<T*>(smem_raw + L.x);   // [n] Ainv[row_next] -> inverse row of the move in flight
+  T* Bs     = reinterpret_cast<T*>(smem_raw + L.Bs);  // [k][k+1] Woodbury core, resident for the whole segment
+  T* pA     = reinterpret_cast<T*>(smem_raw + L.vec); // [k] -V.phi
+  T* pB     = pA + k;                                 // [k] U.x
+  T* y      = pB + k;
+  T* w      = y + k;                                  // [k] w of the prepared row (the accept's bordered update reads it)
+  T* red    = reinterpret_cast<T*>(smem_raw + L.red);
+  T* rgp    = reinterpret_cast<T*>(smem_raw + L.rgp); // [6][4] per-consumer-warp partial dots
+  T* sg     = reinterpret_cast<T*>(smem_raw + L.sg);  // [3] determinant gradient of the prepared row
+  T* hdr    = reinterpret_cast<T*>(smem_raw + L.hdr); // unit header of the evaluation (spline.cuh)
+  uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
+  uint64_t* empty_bar = full_bar + SEG_NSTAGE;
+  unsigned short* jl  = reinterpret_cast<unsigned short*>(smem_raw + L.jl);
+
+  if (tid == 0)
+  {
+    for (int s = 0; s < SEG_NSTAGE; ++s)
+    {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], SEG_NCONS / 32);
+    }
+    ptx::fence_barrier_init();
+    if (nmoves > 0)
+      ptx::prefetch_tensormap(&tmap);
+  }
+  if (tid < 3)
+    sg[tid] = T(0);
+  __syncthreads();
+
+  unsigned gq = 0; // ring position; consumers and producer advance it in lock step (SEG_NQ per evaluation)
+
+  for (int m = -1; m < nmoves; ++m)
+  {
+    const bool part1 = m >= 0, part2 = m + 1 < nmoves;
+    const int iat = iat0 + m, row = row0 + m, c = c0 + m; // the move being decided (part1); c = slot it appends
+    const int cn = c + 1;                                   // pending delays when the next row is prepared
+
+    if (part1)
+    {
+      // ======================= gather phase =======================
+      if (warp < SEG_NCONS / 32)
+      {
+        T v[CPT], gx[CPT], gy[CPT], gz[CPT], hxx[CPT], hxy[CPT], hxz[CPT], hyy[CPT], hyz[CPT], hzz[CPT];
+#pragma unroll
+        for (int e = 0; e < CPT; ++e)
+          v[e] = gx[e] = gy[e] = gz[e] = hxx[e] = hxy[e] = hxz[e] = hyy[e] = hyz[e] = hzz[e] = T(0);
+        const int cfirst = tid * CPT;
+        const int blk = cfirst / SEG_BOXW, loc = cfirst - blk * SEG_BOXW;
+        T cz[4], dcz[4], d2cz[4];
+#pragma unroll
+        for (int qq = 0; qq < SEG_NQ; ++qq)
+        {
+          const unsigned g    = gq + qq;
+          const int stage     = g % SEG_NSTAGE;
+          const unsigned ph   = (g / SEG_NSTAGE) & 1u;
+          ptx::mbar_wait(&full_bar[stage], ph);
+          if (qq == 0)
+          {
+            load4<T>(hdr + SPL_HDR_C, cz);
+            load4<T>(hdr + SPL_HDR_C + 4, dcz);
+            load4<T>(hdr + SPL_HDR_C + 8, d2cz);
+          }
+          const T* sp = ring + stage * STAGE_ELEMS + blk * (SEG_ROWS * SEG_BOXW) + loc;
+          const int i = qq >> 1, j0 = (qq & 1) * 2;
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)
+          {
+            T pa[4], pb[4];
+            load4<T>(hdr + (i * 4 + j0 + jj) * 8, pa);
+            load4<T>(hdr + (i * 4 + j0 + jj) * 8 + 4, pb);
+            const T pre20 = pa[0], pre10 = pa[1], pre11 = pa[2], pre01 = pa[3], pre02 = pb[0], pre00 = pb[1];
+            const T* p0 = sp + jj * 4 * SEG_BOXW;
+            T k0[CPT], k1[CPT], k2[CPT], k3[CPT];
+            SegVec<T, CPT>::load(p0, k0);
+            SegVec<T, CPT>::load(p0 + SEG_BOXW, k1);
+            SegVec<T, CPT>::load(p0 + 2 * SEG_BOXW, k2);
+            SegVec<T, CPT>::load(p0 + 3 * SEG_BOXW, k3);
+#pragma unroll
+            for (int e = 0; e < CPT; ++e)
+            {
+              const T sum0 = cz[0] * k0[e] + cz[1] * k1[e] + cz[2] * k2[e] + cz[3] * k3[e];
+              const T sum1 = dcz[0] * k0[e] + dcz[1] * k1[e] + dcz[2] * k2[e] + dcz[3] * k3[e];
+              const T sum2 = d2cz[0] * k0[e] + d2cz[1] * k1[e] + d2cz[2] * k2[e] + d2cz[3] * k3[e];
+              hxx[e] += pre20 * sum0;
+              hxy[e] += pre11 * sum0;
+              hxz[e] += pre10 * sum1;
+              hyy[e] += pre02 * sum0;
+              hyz[e] += pre01 * sum1;
+              hzz[e] += pre00 * sum2;
+              gx[e] += pre10 * sum0;
+              gy[e] += pre01 * sum0;
+              gz[e] += pre00 * sum1;
+              v[e] += pre00 * sum0;
+            }
+          }
+          __syncwarp();
+          if (lane == 0)
+            ptx::mbar_arrive(&empty_bar[stage]);
+        }
+        // epilogue: lattice units -> Cartesian, sign, rows into shared memory, dots with the inverse row
+        const int bc_sign = *reinterpret_cast<const int*>(hdr + SPL_HDR_SGN);
+        const T sgn   = (bc_sign & 1) ? T(-1) : T(1);
+        const T dxInv = (T)S.delta_inv[0], dyInv = (T)S.delta_inv[1], dzInv = (T)S.delta_inv[2];
+        T acc[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+        for (int e = 0; e < CPT; ++e)
+        {
+          const int mo = cfirst + e;
+          if (mo < n)
+          {
+            const T g0 = gx[e] * dxInv, g1 = gy[e] * dyInv, g2 = gz[e] * dzInv;
+            const T h00 = hxx[e] * (dxInv * dxInv), h11 = hyy[e] * (dyInv * dyInv), h22 = hzz[e] * (dzInv * dzInv);
+            const T h01 = hxy[e] * (dxInv * dyInv), h02 = hxz[e] * (dxInv * dzInv), h12 = hyz[e] * (dyInv * dzInv);
+            const T psi = sgn * v[e];
+            const T dx  = sgn * (S.G[0] * g0 + S.G[1] * g1 + S.G[2] * g2);
+            const T dy  = sgn * (S.G[3] * g0 + S.G[4] * g1 + S.G[5] * g2);
+            const T dz  = sgn * (S.G[6] * g0 + S.G[7] * g1 + S.G[8] * g2);
+            const T lap = sgn *
+                (h00 * S.symGG[0] + h01 * S.symGG[1] + h02 * S.symGG[2] + h11 * S.symGG[3] + h12 * S.symGG[4] +
+                 h22 * S.symGG[5]);
+            phi[mo]         = psi;
+            phi[n + mo]     = dx;
+            phi[2 * n + mo] = dy;
+            phi[3 * n + mo] = dz;
+            phi[4 * n + mo] = lap;
+            const T wr = x[mo];
+            acc[0] += psi * wr;
+            acc[1] += dx * wr;
+            acc[2] += dy * wr;
+            acc[3] += dz * wr;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          acc[e] = warp_sum(acc[e]);
+        if (lane < 4)
+          rgp[warp * 4 + lane] = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+      }
+      else if (warp == 6)
+      {
+        // ---- producer: proposal, unit header (spline.cuh producer warp), one TMA request (CPT boxes) per stage
+        T np3[3];
+        seg_propose<T, true>(Dr, J, iw, iat, sg, np3);
+        T* scratch = hdr + SPL_HDR;
+        T ru[3];
+        const int bc_sign = convert_pos<T, T>(S, np3, ru);
+        int my_ind        = 0;
+        if (lane < 3)
+        {
+          const T rud     = lane == 0 ? ru[0] : (lane == 1 ? ru[1] : ru[2]);
+          const double di = lane == 0 ? S.delta_inv[0] : (lane == 1 ? S.delta_inv[1] : S.delta_inv[2]);
+          const int nmax  = (lane == 0 ? S.M[0] : (lane == 1 ? S.M[1] : S.M[2])) - 1;
+          T t, p0[4], p1[4], p2[4];
+          get_spline_bound<T>((double)rud * di, nmax, my_ind, t);
+          prefactors(p0, p1, p2, t);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+          {
+            scratch[lane * 12 + e]     = p0[e];
+            scratch[lane * 12 + 4 + e] = p1[e];
+            scratch[lane * 12 + 8 + e] = p2[e];
+          }
+        }
+        __syncwarp();
+        const int i0 = __shfl_sync(0xffffffffu, my_ind, 0), i1 = __shfl_sync(0xffffffffu, my_ind, 1),
+                  i2 = __shfl_sync(0xffffffffu, my_ind, 2);
+        if (lane < 16)
+        {
+          const int i = lane >> 2, j = lane & 3;
+          const T ai = scratch[i], dai = scratch[4 + i], d2ai = scratch[8 + i];
+          const T bj = scratch[12 + j], dbj = scratch[16 + j], d2bj = scratch[20 + j];
+          T* hd = hdr + lane * 8;
+          hd[0] = d2ai * bj; // pre20
+          hd[1] = dai * bj;  // pre10
+          hd[2] = dai * dbj; // pre11
+          hd[3] = ai * dbj;  // pre01
+          hd[4] = ai * d2bj; // pre02
+          hd[5] = ai * bj;   // pre00
+          hd[6] = T(0);
+          hd[7] = T(0);
+        }
+        else if (lane < 19)
+        {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            hdr[SPL_HDR_C + (lane - 16) * 4 + e] = scratch[24 + (lane - 16) * 4 + e];
+        }
+        else if (lane == 19)
+          *reinterpret_cast<int*>(hdr + SPL_HDR_SGN) = bc_sign;
+        __syncwarp();
+        const uint64_t pol = ptx::policy_evict_first();
+        for (int qq = 0; qq < SEG_NQ; ++qq)
+        {
+          const unsigned g  = gq + qq;
+          const int stage   = g % SEG_NSTAGE;
+          const unsigned ph = (g / SEG_NSTAGE) & 1u;
+          ptx::mbar_wait(&empty_bar[stage], ph ^ 1u);
+          if (lane == 0)
+          {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], (unsigned)(STAGE_ELEMS * sizeof(T)));
+#pragma unroll
+            for (int b = 0; b < CPT; ++b)
+              ptx::tma_load_4d_hint(ring + stage * STAGE_ELEMS + b * (SEG_ROWS * SEG_BOXW), &tmap, b * SEG_BOXW, i2,
+                                    i1 + (qq & 1) * 2, i0 + (qq >> 1), &full_bar[stage], pol);
+          }
+          __syncwarp();
+        }
+      }
+      else
+      {
+        // ---- warp 7: Jastrow sums at the proposed position (stored for the Metropolis test and the accept)
+        T np3[3];
+        seg_propose<T, false>(Dr, J, iw, iat, sg, np3);
+        if (J.has_j2 || J.has_j1)
+        {
+          T js[10];
+          jastrow_move_warp<T>(J, iw, iat, np3, jl, js);
+        }
+      }
+      gq += SEG_NQ;
+      __syncthreads(); // B1: orbital rows and partial dots in shared memory, Jastrow sums and the proposal in memory
+    }
+
+    // ======================= Metropolis test (warp 7) || accept-independent staging and dots (warps 0-6) =======================
+    const int cA = part1 ? c : 0;                   // rows of V final before this step
+    const int cB = part2 ? (part1 ? c : cn) : 0;    // rows of U final before this step
+    if (warp == 7)
+    {
+      if (part1)
+      {
+        T q[4] = {T(0), T(0), T(0), T(0)};
+        for (int pw = 0; pw < SEG_NCONS / 32; ++pw)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            q[e] += rgp[pw * 4 + e];
+        T rdet;
+        const bool acc = seg_metropolis<T>(Dr, J, R, SR, iw, iat, q, rdet);
+        if (lane == 0)
+        {
+          s_acc   = acc ? 1 : 0;
+          s_ratio = rdet;
+        }
+      }
+    }
+    else
+    {
+      const Group ga{tid, 7 * 32, 1};
+      if (part1)
+      {
+        const T* arow = D.Ainv + ((size_t)iw * n + row) * D.lda;
+        for (int j = tid; j < n; j += ga.n)
+          vrow[j] = arow[j];
+      }
+      if (part2)
+      {
+        const T* arow = D.Ainv + ((size_t)iw * n + row + 1) * D.lda;
+        const T* gl   = D.GL + ((size_t)iw * n + row + 1) * 4 * n;
+        for (int j = tid; j < n; j += ga.n)
+        {
+          x[j]             = arow[j];
+          glrow[j]         = gl[j];
+          glrow[n + j]     = gl[n + j];
+          glrow[2 * n + j] = gl[2 * n + j];
+        }
+      }
+      ptx::fence_proxy_async(); // vrow / glrow live in the ring region: generic writes before the next TMA requests
+      if (!part1 && c0 > 0)
+      {
+        // segment entered with pending delays: the core comes from memory once
+        const T* B = D.Binv + (size_t)iw * k * k;
+        for (int e = tid; e < c0 * k; e += ga.n)
+        {
+          const int a = e / k, b = e - a * k;
+          if (b < c0)
+            Bs[a * kb + b] = B[a * k + b];
+        }
+      }
+      ga.sync();
+      const T* Va     = D.V + (size_t)iw * k * n;
+      const T* Ub     = D.U + (size_t)iw * k * n;
+      const int nspec = (part1 && part2) ? 1 : 0; // phi.x for the slot this move may append
+      const int ntask = cA + cB + nspec;
+      for (int t0 = warp; t0 < ntask; t0 += 14)
+      {
+        const int t1 = t0 + 7;
+        const T *r0, *v0, *r1, *v1;
+        auto pick = [&](int t, const T*& r, const T*& v) {
+          if (t < cA)
+            r = Va + (size_t)t * n, v = phi;
+          else if (t < cA + cB)
+            r = Ub + (size_t)(t - cA) * n, v = x;
+          else
+            r = phi, v = x;
+        };
+        pick(t0, r0, v0);
+        r1 = r0, v1 = v0;
+        const bool two = t1 < ntask;
+        if (two)
+          pick(t1, r1, v1);
+        T s0(0), s1(0);
+        constexpr int DOT_B = sizeof(T) > 4 ? 6 : 12;
+        for (int jb = lane; jb < n; jb += 32 * DOT_B)
+        {
+          T a0[DOT_B], a1[DOT_B];
+#pragma unroll
+          for (int qd = 0; qd < DOT_B; ++qd)
+          {
+            const int j = jb + 32 * qd;
+            a0[qd]      = j < n ? r0[j] : T(0);
+            a1[qd]      = (two && j < n) ? r1[j] : T(0);
+          }
+#pragma unroll
+          for (int qd = 0; qd < DOT_B; ++qd)
+          {
+            const int j = jb + 32 * qd;
+            if (j < n)
+            {
+              s0 += a0[qd] * v0[j];
+              if (two)
+                s1 += a1[qd] * v1[j];
+            }
+          }
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        if (lane == 0)
+        {
+          if (t0 < cA)
+            pA[t0] = -s0;
+          else
+            pB[t0 - cA] = s0;
+          if (two)
+          {
+            if (t1 < cA)
+              pA[t1] = -s1;
+            else
+              pB[t1 - cA] = s1;
+          }
+        }
+      }
+    }
+    __syncthreads(); // B2
+
+    // ======================= determinant accept + next row (threads 0-127) || Jastrow accept (threads 128-255) =======================
+    if (tid < SEG_TPB / 2)
+    {
+      const Group gd{tid, SEG_TPB / 2, 1};
+      if (part1)
+      {
+        const bool acc = s_acc != 0;
+        T* U           = D.U + (size_t)iw * k * n;
+        T* Vm          = D.V + (size_t)iw * k * n;
+        T* gl          = D.GL + ((size_t)iw * n + row) * 4 * n;
+        // rows: V[c] = Ainv[row] for every walker (DelayedUpdateBatched.h:646); U[c] and the G/L rows on accept
+        for (int j = tid; j < n; j += gd.n)
+        {
+          Vm[(size_t)c * n + j] = vrow[j];
+          U[(size_t)c * n + j]  = acc ? phi[j] : T(0);
+          if (acc)
+          {
+            st_stream(gl + j, phi[n + j]);
+            st_stream(gl + n + j, phi[2 * n + j]);
+            st_stream(gl + 2 * n + j, phi[3 * n + j]);
+            st_stream(gl + 3 * n + j, phi[4 * n + j]);
+          }
+        }
+        if (acc)
+        {
+          // bordered update of Binv (DelayedUpdate.h:113-141) in shared memory; w is the one left by this row's preparation
+          const T sigma = T(1) / s_ratio;
+          if (tid < c)
+          {
+            T sacc(0);
+            for (int b = 0; b < c; ++b)
+              sacc += Bs[tid * kb + b] * pA[b];
+            y[tid] = sigma * sacc;
+          }
+          gd.sync();
+          for (int e = tid; e < c * c; e += gd.n)
+          {
+            const int a = e / c, b = e - a * c;
+            Bs[a * kb + b] += y[a] * w[b];
+          }
+          if (tid < c)
+          {
+            Bs[tid * kb + c] = y[tid];
+            Bs[c * kb + tid] = sigma * w[tid];
+          }
+          if (tid == 0)
+          {
+            Bs[c * kb + c]             = sigma;
+            D.list[(size_t)iw * k + c] = row;
+            logdet_accumulate(D.logdet + 2 * (size_t)iw, s_ratio); // log_value += log(curRatio)
+          }
+        }
+        else
+        {
+          // pseudo-accept: detail/OMPTarget/AccelMatrixUpdateOMPTarget.hpp:139-160
+          if (tid < c)
+          {
+            Bs[c * kb + tid] = T(0);
+            Bs[tid * kb + c] = T(0);
+          }
+          if (tid == 0)
+          {
+            Bs[c * kb + c]             = T(1);
+            D.list[(size_t)iw * k + c] = -1;
+          }
+        }
+        gd.sync();
+      }
+      if (part2)
+      {
+        // p'[a] = U[a].x : rows < cB from the staging phase; the appended row is phi.x on accept, 0 for a pseudo-accept
+        if (part1 && tid == 0)
+          pB[c] = s_acc != 0 ? pB[cB] : T(0);
+        gd.sync();
+        if (tid < cn)
+        {
+          T sacc(0);
+          for (int a = 0; a < cn; ++a)
+            sacc += Bs[a * kb + tid] * pB[a];
+          w[tid] = -sacc; // w = -Binv^T p'  (DelayedUpdate.h:100-101)
+        }
+        gd.sync();
+        // x += V^T w : rows < cB from L2, the row appended by this move from shared memory
+        const T* Vm = D.V + (size_t)iw * k * n;
+        T acc3[3]   = {T(0), T(0), T(0)};
+        constexpr int XC = sizeof(T) > 4 ? 2 : 3;
+        for (int jb = tid; jb < n; jb += XC * gd.n)
+        {
+          T sacc[XC];
+#pragma unroll
+          for (int qx = 0; qx < XC; ++qx)
+            sacc[qx] = T(0);
+#pragma unroll 4
+          for (int a = 0; a < cB; ++a)
+          {
+            const T wa = w[a];
+#pragma unroll
+            for (int qx = 0; qx < XC; ++qx)
+            {
+              const int j = jb + qx * gd.n;
+              if (j < n)
+                sacc[qx] += Vm[(size_t)a * n + j] * wa;
+            }
+          }
+#pragma unroll
+          for (int qx = 0; qx < XC; ++qx)
+          {
+            const int j = jb + qx * gd.n;
+            if (j < n)
+            {
+              T sq = sacc[qx];
+              if (part1)
+                sq += vrow[j] * w[c];
+              const T xv = x[j] + sq;
+              x[j]       = xv;
+              acc3[0] += xv * glrow[j];
+              acc3[1] += xv * glrow[n + j];
+              acc3[2] += xv * glrow[2 * n + j];
+            }
+          }
+        }
+        group_sum<T, 3>(gd, acc3, red);
+        if (tid < 3)
+          sg[tid] = tid == 0 ? acc3[0] : (tid == 1 ? acc3[1] : acc3[2]);
+      }
+      // the ring region (vrow, glrow) goes back to the TMA engine
+      ptx::fence_proxy_async();
+    }
+    else if (part1 && s_acc != 0)
+      jastrow_accept_body<T>(Group{tid - SEG_TPB / 2, SEG_TPB / 2, 2}, J, iw, iat, jl);
+    __syncthreads(); // B3
+  }
+
+  // the flush (and any later API call) finds the core and w in memory
+  const int cF = c0 + nmoves;
+  {
+    T* B = D.Binv + (size_t)iw * k * k;
+    for (int e = tid; e < cF * cF; e += SEG_TPB)
+    {
+      const int a = e / cF, b = e - a * cF;
+      B[a * k + b] = Bs[a * kb + b];
+    }
+    if (tid < cF)
+      D.wvec[(size_t)iw * k + tid] = w[tid];
+  }
+}
+#endif // __CUDACC__
+
+} // namespace qmcb

@@ -74,14 +74,14 @@ EncodeTiledFn encode_tiled()
 
 // the table as a 4-D tensor (component fastest, then z, y, x); box = TILE components x 4 x 4 x 4 grid planes
 template<typename ST>
-CUtensorMap make_tensor_map(const ST* coefs, const int grid[3], size_t npad, int tile)
+CUtensorMap make_tensor_map(const ST* coefs, const int grid[3], size_t npad, int tile, int bz = 4, int by = 4, int bx = 4)
 {
   CUtensorMap m;
   const cuuint64_t dims[4]    = {(cuuint64_t)npad, (cuuint64_t)(grid[2] + 3), (cuuint64_t)(grid[1] + 3),
                                  (cuuint64_t)(grid[0] + 3)};
   const cuuint64_t strides[3] = {(cuuint64_t)npad * sizeof(ST), (cuuint64_t)npad * sizeof(ST) * (grid[2] + 3),
                                  (cuuint64_t)npad * sizeof(ST) * (grid[2] + 3) * (grid[1] + 3)};
-  const cuuint32_t box[4]     = {(cuuint32_t)tile, 4, 4, 4};
+  const cuuint32_t box[4]     = {(cuuint32_t)tile, (cuuint32_t)bz, (cuuint32_t)by, (cuuint32_t)bx};
   const cuuint32_t estr[4]    = {1, 1, 1, 1};
   const CUresult r = encode_tiled()(&m, sizeof(ST) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4,
                                     const_cast<ST*>(coefs), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -99,7 +99,10 @@ struct SplineSPO : SplineSPOBase
   DevBuf<ST> coefs, kc, mkk;
   SplineDev<ST> dev;
   CUtensorMap tmap; // box shape follows Shape<ST, kind == C2C>
+  CUtensorMap tmap_seg; // 192 components x 4 z x 2 y x 1 x: one slab of the stencil (segment.cuh)
   size_t table_bytes() const override { return coefs.bytes(); }
+  const void* dev_desc() const override { return &dev; }
+  const void* seg_tensor_map() const override { return &tmap_seg; }
 
   SplineSPO(int prec, int kind_, const int g[3], int norb, int nspl, size_t npad_, const void* host, const double G_[9],
             const int hG[3], const double* kcart)
@@ -156,6 +159,7 @@ struct SplineSPO : SplineSPOBase
     dev.kcart    = nullptr;
     dev.mKK      = nullptr;
     tmap = make_tensor_map<ST>(coefs.p, grid, npad, kind == QMCB_C2C ? Shape<ST, true>::TILE : Shape<ST, false>::TILE);
+    tmap_seg = make_tensor_map<ST>(coefs.p, grid, npad, 192, 4, 2, 1);
     if (kind == QMCB_C2C)
     {
       if (!kcart)

@@ -102,12 +102,19 @@ def test_host_driven_sweep_identical_acceptance_fp64(api, orc, lattice, k):
     assert ke2 == pytest.approx(ke, rel=1e-7, abs=1e-7)
 
 
-def test_device_driver_identical_acceptance_fp64(api, orc):
+# the two implementations of the device-resident sweep (qmcb_vmc_params.sweep_kernel): 1 = boundary kernel + spline gather
+# per move, 2 = the persistent walker-segment kernel (csrc/segment.cuh).  Same random stream, same decisions.
+SWEEP_KERNELS = pytest.mark.parametrize("sweep_kernel", [1, 2], ids=["two_kernel", "segment_kernel"])
+
+
+@SWEEP_KERNELS
+@pytest.mark.parametrize("lattice", [None, LAT_GENERAL], ids=["ortho", "general"])
+def test_device_driver_identical_acceptance_fp64(api, orc, sweep_kernel, lattice):
     """the device-resident sweep (on-device mt19937, Box-Muller, Metropolis test) reproduces the oracle's acceptance
     sequence in FP64 with drift, J1 and J2, delay rank 4, with and without CUDA graph replay"""
     from qmcpack_b200.workload import initial_positions
     import oracle_lib
-    s = small_system(np.float64)
+    s = small_system(np.float64, lattice)
     nw, k, nsteps, tau, seed = 7, 4, 3, 0.1, 4242
     R = initial_positions(s, nw)
     ov = oracle_lib.OracleVMC(orc, s, nw=nw, ncrowds=1, seeds=[seed], tau=tau, delay_rank=k)
@@ -118,15 +125,69 @@ def test_device_driver_identical_acceptance_fp64(api, orc):
         crowd = api.Crowd(s, nw=nw, delay_rank=k)
         crowd.set_positions(R)
         crowd.mw_recompute()
-        crowd.vmc_init(tau=tau, use_drift=True, seed=seed, use_cuda_graph=graph)
+        crowd.vmc_init(tau=tau, use_drift=True, seed=seed, use_cuda_graph=graph, sweep_kernel=sweep_kernel)
+        assert crowd.sweep_kernel == sweep_kernel
         log = crowd.vmc_sweep(nsteps, log_accept=True)
         assert np.array_equal(log, olog), f"graph={graph}: {np.argwhere(log != olog)[:5]}"
         assert crowd.positions() == pytest.approx(ov.positions(), rel=1e-8, abs=1e-8)
-        lp, ke, _, _ = crowd.mw_evaluateGL()
-        olp, oke, _, _ = ov.evaluate_gl()
+        lp, ke, G, L = crowd.mw_evaluateGL()
+        olp, oke, oG, oL = ov.evaluate_gl()
         assert lp == pytest.approx(olp, rel=1e-8, abs=1e-8)
+        assert ke == pytest.approx(oke, rel=1e-6, abs=1e-6)
+        assert G == pytest.approx(oG, rel=1e-6, abs=1e-6)
         na, nr = crowd.vmc_counts()
         assert (na + nr == nsteps * 24).all() and na.sum() == olog.sum()
+        # delayed-update state == from-scratch recompute (checkGL_after_moves of the reference)
+        crowd.mw_recompute()
+        lp2, ke2, _, _ = crowd.mw_evaluateGL()
+        assert lp2 == pytest.approx(lp, rel=1e-9, abs=1e-9)
+        assert ke2 == pytest.approx(ke, rel=1e-7, abs=1e-7)
+
+
+@pytest.mark.parametrize("N,k,nw", [(24, 1, 5), (24, 12, 5), (26, 5, 33), (40, 32, 70), (400, 32, 3), (768, 32, 2)],
+                         ids=["k1", "k_eq_n", "odd_k_33w", "k_gt_n_70w", "one_box_wide", "two_boxes_a64_width"])
+def test_segment_kernel_shapes_fp64(api, orc, N, k, nw):
+    """the persistent walker-segment kernel over the shapes that exercise its corners: delay rank 1 (every segment is one
+    move), delay rank = determinant size, segments that do not divide the determinant, more walkers than one look-back
+    warp covers, a determinant wider than one TMA box (200 > 192 orbitals: two components per consumer thread) and the
+    NiO-a64 width (384).  FP64: acceptance identical to the oracle, delayed-update state == recompute."""
+    from qmcpack_b200.workload import make_system, initial_positions
+    import oracle_lib
+    kk = min(k, N // 2)
+    s = make_system(N=N, M=8 if N <= 40 else 12, dtype=np.float64, L=6.0 if N <= 40 else None)
+    nsteps, tau, seed = 2, 0.1, 99 + N
+    R = initial_positions(s, nw)
+    ov = oracle_lib.OracleVMC(orc, s, nw=nw, ncrowds=1, seeds=[seed], tau=tau, delay_rank=kk)
+    ov.set_positions(R)
+    ov.recompute()
+    olog = ov.sweep(nsteps, log_accept=True)
+    crowd = api.Crowd(s, nw=nw, delay_rank=kk)
+    crowd.set_positions(R)
+    crowd.mw_recompute()
+    crowd.vmc_init(tau=tau, use_drift=True, seed=seed, use_cuda_graph=True, sweep_kernel=2)
+    log = crowd.vmc_sweep(nsteps, log_accept=True)
+    assert np.array_equal(log, olog), np.argwhere(log != olog)[:5]
+    assert crowd.positions() == pytest.approx(ov.positions(), rel=1e-8, abs=1e-8)
+    lp, ke, _, _ = crowd.mw_evaluateGL()
+    olp, oke, _, _ = ov.evaluate_gl()
+    assert lp == pytest.approx(olp, rel=1e-8, abs=1e-7)
+    crowd.mw_recompute()
+    lp2, ke2, _, _ = crowd.mw_evaluateGL()
+    assert lp2 == pytest.approx(lp, rel=1e-9, abs=1e-7)
+
+
+def test_segment_kernel_refused_for_complex_orbitals(api):
+    """complex determinants run the two-kernel path; asking for the segment kernel explicitly is an error, automatic
+    selection falls back silently"""
+    from qmcpack_b200.workload import make_system, initial_positions
+    s = make_system(N=24, M=8, dtype=np.float64, L=6.0, complex_orbitals=True)
+    crowd = api.Crowd(s, nw=3, delay_rank=4)
+    crowd.set_positions(initial_positions(s, 3))
+    crowd.mw_recompute()
+    with pytest.raises(RuntimeError, match="complex orbitals"):
+        crowd.vmc_init(tau=0.1, seed=1, sweep_kernel=2)
+    crowd.vmc_init(tau=0.1, seed=1, sweep_kernel=0)
+    assert crowd.sweep_kernel == 1
 
 
 @pytest.mark.parametrize("ncrowds", [1, 3])
@@ -166,7 +227,8 @@ def test_compiled_host_driver_matches_oracle_multi_crowd(api, orc, ncrowds):
     assert up == 24 * (nw * 3 * 8 + nw) and down == 24 * (nw * 3 * 8 * 2 + nw * 8)
 
 
-def test_device_driver_no_drift(api, orc):
+@SWEEP_KERNELS
+def test_device_driver_no_drift(api, orc, sweep_kernel):
     from qmcpack_b200.workload import initial_positions
     import oracle_lib
     s = small_system(np.float64)
@@ -179,7 +241,7 @@ def test_device_driver_no_drift(api, orc):
     crowd = api.Crowd(s, nw=nw, delay_rank=2)
     crowd.set_positions(R)
     crowd.mw_recompute()
-    crowd.vmc_init(tau=0.2, use_drift=False, seed=seed, use_cuda_graph=False)
+    crowd.vmc_init(tau=0.2, use_drift=False, seed=seed, use_cuda_graph=False, sweep_kernel=sweep_kernel)
     assert np.array_equal(crowd.vmc_sweep(2, log_accept=True), olog)
 
 
@@ -293,17 +355,18 @@ def test_nio_a32_shape_mixed_precision_every_move(api, orc):
     ov2.set_positions(R)
     ov2.recompute()
     olog = ov2.sweep(1, log_accept=True)
-    crowd.set_positions(R)
-    crowd.mw_recompute()
-    crowd.vmc_init(tau=0.3, use_drift=True, seed=31, use_cuda_graph=True)
-    dlog = crowd.vmc_sweep(1, log_accept=True)
-    assert abs(dlog.mean() - olog.mean()) < 0.03
-    assert (dlog == olog).mean() > 0.9
-    lp, ke, _, _ = crowd.mw_evaluateGL()
-    crowd.mw_recompute()
-    lp2, ke2, _, _ = crowd.mw_evaluateGL()
-    assert lp2 == pytest.approx(lp, rel=1e-5, abs=2e-2)
-    assert ke2 == pytest.approx(ke, rel=5e-3)
+    for sweep_kernel in (1, 2):
+        crowd.set_positions(R)
+        crowd.mw_recompute()
+        crowd.vmc_init(tau=0.3, use_drift=True, seed=31, use_cuda_graph=True, sweep_kernel=sweep_kernel)
+        dlog = crowd.vmc_sweep(1, log_accept=True)
+        assert abs(dlog.mean() - olog.mean()) < 0.03
+        assert (dlog == olog).mean() > 0.9
+        lp, ke, _, _ = crowd.mw_evaluateGL()
+        crowd.mw_recompute()
+        lp2, ke2, _, _ = crowd.mw_evaluateGL()
+        assert lp2 == pytest.approx(lp, rel=1e-5, abs=2e-2)
+        assert ke2 == pytest.approx(ke, rel=5e-3)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
