@@ -68,7 +68,10 @@ SYMBOLS = [
 
 
 DRIVER_SYMBOLS = ["qmcb_host_vmc_last_error", "qmcb_host_vmc_create", "qmcb_host_vmc_destroy", "qmcb_host_vmc_run",
-                  "qmcb_host_vmc_counts", "qmcb_host_vmc_bytes_per_sweep"]
+                  "qmcb_host_vmc_counts", "qmcb_host_vmc_bytes_per_sweep",
+                  "qmcb_dmc_last_error", "qmcb_dmc_create", "qmcb_dmc_create_with_engine", "qmcb_dmc_destroy", "qmcb_dmc_step",
+                  "qmcb_dmc_advance", "qmcb_dmc_branch", "qmcb_dmc_get_walkers", "qmcb_dmc_set_weights",
+                  "qmcb_dmc_branch_weight"]
 
 
 def lib():
@@ -99,6 +102,9 @@ def lib():
         L.qmcb_crowd_create.argtypes = [C.POINTER(vp), C.POINTER(QmcbSystem), C.c_int]
         L.qmcb_det_mw_get_inv_row.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), vp]
         L.qmcb_host_vmc_last_error.restype = C.c_char_p
+        L.qmcb_dmc_last_error.restype = C.c_char_p
+        L.qmcb_dmc_branch_weight.restype = C.c_double
+        L.qmcb_dmc_branch_weight.argtypes = [vp, C.c_double, C.c_double]
         _lib = L
     return _lib
 
@@ -214,7 +220,7 @@ class Crowd:
         self.T = np.float32 if self.precision == MIXED else np.float64
         self.n_up, self.n_dn = int(s["n_up"]), int(s["n_dn"])
         self.N = self.n_up + self.n_dn
-        self.nw = int(nw)
+        self._nw0 = int(nw)
         self.k = int(delay_rank)
         lat = np.ascontiguousarray(s["lattice"], np.float64).reshape(3, 3)
         G = np.linalg.inv(lat)  # CrystalLattice: G = inverse(R), ru = r . G
@@ -259,7 +265,7 @@ class Crowd:
             q.n_ion_groups, q.n_j1 = prm.shape[0], prm.shape[1]
             q.j1_params, q.j1_rcut = prm.ctypes.data_as(c_dp), rc.ctypes.data_as(c_dp)
         self.h = vp()
-        _chk(lib().qmcb_crowd_create(C.byref(self.h), C.byref(q), self.nw))
+        _chk(lib().qmcb_crowd_create(C.byref(self.h), C.byref(q), self._nw0))
 
     def __del__(self):
         try:
@@ -442,7 +448,12 @@ class Crowd:
     def set_num_walkers(self, n):
         """live walkers [0, n) of the capacity given at creation (DMC population changes)"""
         _chk(lib().qmcb_crowd_set_num_walkers(self.h, C.c_int(n)))
-        self.nw = int(n)
+
+    @property
+    def nw(self):
+        """live walkers (the C++ DMC layer changes the count behind this wrapper's back)"""
+        h = getattr(self, "h", None)
+        return int(lib().qmcb_crowd_num_walkers(h)) if h else self._nw0
 
     @property
     def capacity(self):
@@ -505,3 +516,195 @@ class HostVMC:
         a, r = C.c_longlong(), C.c_longlong()
         lib().qmcb_host_vmc_bytes_per_sweep(self.h, C.byref(a), C.byref(r))
         return a.value, r.value
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# DMC layer (include/qmcb_driver.h, csrc/dmc_host.cpp): DMCBatched::advanceWalkers + WalkerControl::branch + SFNBranch in
+# C++; this class only marshals the communicator (torch.distributed) and, for tests, a duck-typed engine
+# ---------------------------------------------------------------------------------------------------------------------
+_ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, vp, c_dp, C.c_int)
+_SEND_FN = C.CFUNCTYPE(C.c_int, vp, C.c_int, c_dp)
+_RECV_FN = C.CFUNCTYPE(C.c_int, vp, C.c_int, c_dp)
+
+
+class QmcbComm(C.Structure):
+    _fields_ = [("rank", C.c_int), ("size", C.c_int), ("ctx", vp), ("allreduce_sum", _ALLREDUCE_FN), ("send", _SEND_FN),
+                ("recv", _RECV_FN), ("send_buf", vp), ("recv_buf", vp)]
+
+
+_E_INT = C.CFUNCTYPE(C.c_int, vp)
+_E_DP = C.CFUNCTYPE(C.c_int, vp, c_dp)
+_E_DP2 = C.CFUNCTYPE(C.c_int, vp, c_dp, c_dp)
+_E_II = C.CFUNCTYPE(C.c_int, vp, C.c_int, C.c_int)
+_E_I = C.CFUNCTYPE(C.c_int, vp, C.c_int)
+_E_IP = C.CFUNCTYPE(C.c_int, vp, C.c_int, vp)
+
+
+class QmcbDmcEngine(C.Structure):
+    _fields_ = [("ctx", vp), ("num_walkers", _E_INT), ("capacity", _E_INT), ("sweep", _E_INT), ("local_energies", _E_DP),
+                ("get_rr", _E_DP2), ("copy_walker", _E_II), ("set_num_walkers", _E_I), ("pack_walker", _E_IP),
+                ("unpack_walker", _E_IP)]
+
+
+class QmcbDmcParams(C.Structure):
+    _fields_ = [("tau", C.c_double), ("target_walkers", C.c_int), ("branch_seed", C.c_uint32), ("sigma2", C.c_double),
+                ("sigma_bound", C.c_double), ("feedback", C.c_double), ("warmup_steps", C.c_int),
+                ("energy_update_interval", C.c_int), ("use_tau_eff", C.c_int)]
+
+
+class QmcbDmcEnsemble(C.Structure):
+    _fields_ = [("energy", C.c_double), ("variance", C.c_double), ("weight", C.c_double), ("num_samples", C.c_double),
+                ("r2_accepted", C.c_double), ("r2_proposed", C.c_double), ("living_fraction", C.c_double),
+                ("e_trial", C.c_double), ("e_ref", C.c_double), ("tau_eff", C.c_double), ("branch_cutoff", C.c_double),
+                ("population", C.c_int), ("local", C.c_int), ("walkers_sent", C.c_longlong),
+                ("walkers_received", C.c_longlong), ("bytes_sent", C.c_longlong), ("bytes_received", C.c_longlong)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class TorchComm:
+    """qmcb_comm over torch.distributed: NCCL on the GPU box (all-reduce of curData, ncclSend / ncclRecv of the packed
+    device-resident walker), gloo in the CPU tests.  Owns the two transfer buffers."""
+
+    def __init__(self, dist, walker_bytes, device):
+        import torch
+        self.dist, self.device = dist, device
+        self.rank, self.size = dist.get_rank(), dist.get_world_size()
+        self.send_buf = torch.empty(max(16, walker_bytes), dtype=torch.uint8, device=device)
+        self.recv_buf = torch.empty_like(self.send_buf)
+        self.bytes_sent = self.bytes_received = 0
+        self.messages = 0
+
+        def allreduce(ctx, buf, n):
+            try:
+                a = np.ctypeslib.as_array(buf, shape=(n,))
+                t = torch.as_tensor(a.copy(), dtype=torch.float64, device=device)
+                dist.all_reduce(t)
+                a[:] = t.cpu().numpy()
+                return 0
+            except Exception:  # surfaced as "allreduce failed" by the C++ side
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        def send(ctx, dst, header):
+            try:
+                h = torch.as_tensor(np.ctypeslib.as_array(header, shape=(4,)).copy(), dtype=torch.float64, device=device)
+                dist.send(h, dst=dst)
+                dist.send(self.send_buf, dst=dst)
+                self.bytes_sent += self.send_buf.numel() + 32
+                self.messages += 1
+                return 0
+            except Exception:
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        def recv(ctx, src, header):
+            try:
+                h = torch.empty(4, dtype=torch.float64, device=device)
+                dist.recv(h, src=src)
+                dist.recv(self.recv_buf, src=src)
+                np.ctypeslib.as_array(header, shape=(4,))[:] = h.cpu().numpy()
+                self.bytes_received += self.recv_buf.numel() + 32
+                return 0
+            except Exception:
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        self._cb = (_ALLREDUCE_FN(allreduce), _SEND_FN(send), _RECV_FN(recv))
+        self.c = QmcbComm(self.rank, self.size, None, self._cb[0], self._cb[1], self._cb[2], self.send_buf.data_ptr(),
+                          self.recv_buf.data_ptr())
+
+
+class DMCDriver:
+    """The C++ DMC layer on one crowd per rank (or, for tests, on a duck-typed engine with nw, capacity, dmc_sweep(),
+    local_energies(), rr(), copy_walker(), set_num_walkers(), pack_walker(), unpack_walker())."""
+
+    def __init__(self, engine, tau, target_walkers=0, branch_seed=7, comm=None, warmup_steps=1 << 30,
+                 energy_update_interval=1, sigma2=10.0, sigma_bound=10.0, feedback=1.0, use_tau_eff=True):
+        self.engine, self.comm = engine, comm
+        self.p = QmcbDmcParams(tau, int(target_walkers), int(branch_seed), sigma2, sigma_bound, feedback, int(warmup_steps),
+                               int(energy_update_interval), int(use_tau_eff))
+        self.h = vp()
+        cp = C.byref(comm.c) if comm is not None else None
+        if isinstance(engine, Crowd):
+            rc = lib().qmcb_dmc_create(C.byref(self.h), engine.h, C.byref(self.p), cp)
+        else:
+            self._eng_c = self._wrap_engine(engine)
+            rc = lib().qmcb_dmc_create_with_engine(C.byref(self.h), C.byref(self._eng_c), C.byref(self.p), cp)
+        if rc:
+            raise RuntimeError(lib().qmcb_dmc_last_error().decode())
+        self.history = []
+
+    def _wrap_engine(self, e):
+        def guard(f):
+            def g(*a):
+                try:
+                    f(*a)
+                    return 0
+                except Exception:
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            return g
+
+        def energies(ctx, out):
+            np.ctypeslib.as_array(out, shape=(e.nw,))[:] = np.asarray(e.local_energies(), np.float64)
+
+        def rr(ctx, a, p):
+            ra, rp = e.rr()
+            np.ctypeslib.as_array(a, shape=(e.nw,))[:] = np.asarray(ra, np.float64)
+            np.ctypeslib.as_array(p, shape=(e.nw,))[:] = np.asarray(rp, np.float64)
+
+        self._eng_cb = (_E_INT(lambda ctx: int(e.nw)), _E_INT(lambda ctx: int(e.capacity)),
+                        _E_INT(guard(lambda ctx: e.dmc_sweep())), _E_DP(guard(energies)), _E_DP2(guard(rr)),
+                        _E_II(guard(lambda ctx, s, d: e.copy_walker(s, d))),
+                        _E_I(guard(lambda ctx, n: e.set_num_walkers(n))),
+                        _E_IP(guard(lambda ctx, iw, buf: e.pack_walker(iw, buf))),
+                        _E_IP(guard(lambda ctx, iw, buf: e.unpack_walker(iw, buf))))
+        return QmcbDmcEngine(None, *self._eng_cb)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().qmcb_dmc_destroy(self.h)
+        except Exception:
+            pass
+
+    def _ens(self, rc, ens):
+        if rc:
+            raise RuntimeError(lib().qmcb_dmc_last_error().decode())
+        d = ens.as_dict()
+        self.history.append(d)
+        return d
+
+    def step(self, it):
+        """one generation: advance + branch(iter, do_not_branch = (iter == 0)) + updateParamAfterPopControl"""
+        ens = QmcbDmcEnsemble()
+        return self._ens(lib().qmcb_dmc_step(self.h, C.c_int(it), C.byref(ens)), ens)
+
+    def advance(self):
+        if lib().qmcb_dmc_advance(self.h):
+            raise RuntimeError(lib().qmcb_dmc_last_error().decode())
+
+    def branch_step(self, it=1, do_not_branch=False):
+        ens = QmcbDmcEnsemble()
+        return self._ens(lib().qmcb_dmc_branch(self.h, C.c_int(it), C.c_int(int(do_not_branch)), C.byref(ens)), ens)
+
+    def walkers(self):
+        """(weights, energies, ages) of the live walkers"""
+        cap = 1 << 16
+        w, e, a = np.zeros(cap), np.zeros(cap), np.zeros(cap, np.int64)
+        n = lib().qmcb_dmc_get_walkers(self.h, _p(w), _p(e), _p(a), C.c_int(cap))
+        return w[:n].copy(), e[:n].copy(), a[:n].copy()
+
+    def set_weights(self, w):
+        w = np.ascontiguousarray(w, np.float64)
+        if lib().qmcb_dmc_set_weights(self.h, _p(w), C.c_int(len(w))):
+            raise RuntimeError(lib().qmcb_dmc_last_error().decode())
+
+    def branch_weight(self, enew, eold):
+        return float(lib().qmcb_dmc_branch_weight(self.h, C.c_double(enew), C.c_double(eold)))

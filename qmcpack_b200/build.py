@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libqmcb.so")
-SOURCES = ["spline.cu", "crowd.cu", "api.cu", "vmc_host.cpp"]
+SOURCES = ["spline.cu", "crowd.cu", "api.cu", "vmc_host.cpp", "dmc_host.cpp"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))) + [
     os.path.join("..", "..", "include", "qmcb.h"), os.path.join("..", "..", "include", "qmcb_driver.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -274,9 +274,9 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
                           const JastrowDev<T> J, const RngDev R, const SegRng SR, const DetDev<T> D, const int iat0,
                           const int row0, const int nmoves, const int c0)
 {
+  // (no static __shared__ variables in this kernel: the ring must sit at a 128-byte aligned shared-memory address for the
+  // TMA engine, and the dynamic segment is only guaranteed to start aligned when nothing precedes it)
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ int s_acc;
-  __shared__ T s_ratio;
   const int n = D.n, k = D.k, kb = k + 1;
   const int iw = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SegLayout L = seg_layout<T, CPT>(n, k, J.N, J.has_j1 ? J.nions : 0);
@@ -294,6 +294,8 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
   T* red    = reinterpret_cast<T*>(smem_raw + L.red);
   T* rgp    = reinterpret_cast<T*>(smem_raw + L.rgp); // [6][4] per-consumer-warp partial dots
   T* sg     = reinterpret_cast<T*>(smem_raw + L.sg);  // [3] determinant gradient of the prepared row
+  T& s_ratio = sg[4];                                 // determinant ratio of the move being decided
+  int& s_acc = *reinterpret_cast<int*>(sg + 5);       // its Metropolis decision
   T* hdr    = reinterpret_cast<T*>(smem_raw + L.hdr); // unit header of the evaluation (spline.cuh)
   uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
   uint64_t* empty_bar = full_bar + SEG_NSTAGE;

@@ -1,5 +1,6 @@
-"""Host-side DMC layer above the device-resident sweep: branch weights, population control and walker
-exchange, restating
+"""Python MIRROR of the DMC layer (the product is C++: csrc/dmc_host.cpp behind include/qmcb_driver.h, bound as
+qmcpack_b200.api.DMCDriver).  The tests drive the oracle with this file and the GPU crowd with the C++ layer, so the two
+restatements check each other.  Branch weights, population control and walker exchange, restating
 
   * DMCBatched::advanceWalkers, the part after the move loop   QMCDrivers/DMC/DMCBatched.cpp:264-292
   * SFNBranch::branchWeight / setBranchCutoff / warm-up E_trial QMCDrivers/SFNBranch.h:199-208, SFNBranch.cpp:133-199,290-320
@@ -162,47 +163,43 @@ class DMC:
             mult, incoming = self._swap(mult, num_per_rank)
         mult = list(int(m) for m in mult)
         # killDeadWalkersOnRank: survivors keep their order and close the gaps (vector erase); received walkers were
-        # appended by spawnWalker; fissionHighMultiplicityWalkers appends the copies parent by parent
+        # appended by spawnWalker during the swap; fissionHighMultiplicityWalkers then walks the whole list once and
+        # appends the copies parent by parent (survivors' copies first, then the copies of received walkers)
         survivors = [i for i in range(len(mult)) if mult[i] > 0]
-        new_e, new_age = [], []
+        new_w, new_e, new_age, new_mult = [], [], [], []
         for dst, src in enumerate(survivors):
             eng.copy_walker(src, dst)
+            new_w.append(self.weights[src])
             new_e.append(self.energies[src])
             new_age.append(self.ages[src])
+            new_mult.append(mult[src])
         nlive = len(survivors)
-        for buf, e_in, age_in, extra in incoming:
+        for buf, w_in, e_in, age_in, extra in incoming:
             if nlive >= eng.capacity:
-                break
+                raise RuntimeError("DMC population exceeds the crowd's capacity on rank %d" % self.rank)
             eng.unpack_walker(nlive, buf.data_ptr())
-            mult.append(0)
-            survivors.append(None)
+            new_w.append(w_in)
             new_e.append(e_in)
             new_age.append(age_in)
-            parent = nlive
+            new_mult.append(extra + 1)
             nlive += 1
-            for _ in range(extra):
+        for parent in range(len(new_mult)):
+            for _ in range(new_mult[parent] - 1):
                 if nlive >= eng.capacity:
-                    break
+                    raise RuntimeError("DMC population exceeds the crowd's capacity on rank %d" % self.rank)
                 eng.copy_walker(parent, nlive)
-                new_e.append(e_in)
-                new_age.append(age_in)
-                nlive += 1
-        for dst, src in enumerate(survivors):
-            if src is None:
-                continue
-            for _ in range(mult[src] - 1):
-                if nlive >= eng.capacity:
-                    break  # walker-count ceiling (n_max): surplus copies are dropped
-                eng.copy_walker(dst, nlive)
-                new_e.append(self.energies[src])
-                new_age.append(self.ages[src])
+                new_w.append(new_w[parent])
+                new_e.append(new_e[parent])
+                new_age.append(new_age[parent])
                 nlive += 1
         if nlive == 0:
             raise RuntimeError("DMC population died out on rank %d" % self.rank)
         eng.set_num_walkers(nlive)
         self.energies = np.asarray(new_e, np.float64)
         self.ages = np.asarray(new_age, np.int64)
-        self.weights = np.ones(nlive)  # WalkerControl.cpp:226-233
+        # WalkerControl.cpp:226-233: Weight and Multiplicity go back to 1 only `if (!do_not_branch)`; on iteration 0 the
+        # branch weights of the first step carry into the second
+        self.weights = np.asarray(new_w, np.float64) if do_not_branch else np.ones(nlive)
         self.rr_acc = np.zeros(nlive)
         self.rr_prop = np.zeros(nlive)
         self.branch.update_after_pop_control(ens)
@@ -210,7 +207,8 @@ class DMC:
         return ens
 
     def _swap(self, mult, num_per_rank):
-        """swapWalkersSimple: packed device buffers over point-to-point messages; header = (extra copies, energy, age)"""
+        """swapWalkersSimple: packed device buffers over point-to-point messages; header = (extra copies, weight, energy,
+        age) -- Weight, Age and the Properties travel inside Walker::DataSet in the reference"""
         import torch
         dist, eng = self.dist, self.eng
         _, minus, plus = sharding.determine_new_walker_population(num_per_rank)
@@ -224,20 +222,20 @@ class DMC:
             nsent = 0
             if plus[ic] == self.rank:
                 widx, target, nsent = next(send_iter)
-                head = torch.tensor([float(nsent), float(self.energies[widx]), float(self.ages[widx])], dtype=torch.float64,
-                                    device=dev)
+                head = torch.tensor([float(nsent), float(self.weights[widx]), float(self.energies[widx]),
+                                     float(self.ages[widx])], dtype=torch.float64, device=dev)
                 buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
                 eng.pack_walker(widx, buf.data_ptr())
                 dist.send(head, dst=target)
                 dist.send(buf, dst=target)
             elif minus[ic] == self.rank:
-                head = torch.empty(3, dtype=torch.float64, device=dev)
+                head = torch.empty(4, dtype=torch.float64, device=dev)
                 buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
                 dist.recv(head, src=plus[ic])
                 dist.recv(buf, src=plus[ic])
                 h = head.cpu().numpy()
                 nsent = int(h[0])
-                incoming.append((buf, float(h[1]), int(h[2]), nsent))
+                incoming.append((buf, float(h[1]), float(h[2]), int(h[3]), nsent))
             else:
                 # a third rank must skip the folded entries too: the fold count is (pairs with the same endpoints that
                 # follow) limited by the sender's copies; it is broadcast implicitly by advancing one entry at a time,

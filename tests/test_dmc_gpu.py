@@ -116,9 +116,10 @@ def test_walker_copy_and_packed_transfer(api, orc):
 
 
 def test_dmc_branching_run_follows_oracle(api, orc):
-    """six DMC generations with branching (dynamic population inside a capacity of 16): the product on the GPU and the
-    oracle, both steered by qmcpack_b200.dmc.DMC with the same branching stream, keep identical populations,
-    acceptance logs, weights and energies"""
+    """eight DMC generations with branching (dynamic population inside a capacity of 16): the product -- GPU crowd steered
+    by the C++ DMC layer (csrc/dmc_host.cpp) -- and the checker -- the oracle's CPU walkers steered by the Python mirror
+    (qmcpack_b200/dmc.py) -- share one branching stream and keep identical populations, acceptance logs, weights and
+    energies"""
     from qmcpack_b200.workload import initial_positions
     from qmcpack_b200 import dmc
     import oracle_lib
@@ -134,21 +135,22 @@ def test_dmc_branching_run_follows_oracle(api, orc):
     crowd.mw_recompute()
     crowd.vmc_init(tau=tau, seed=seed, use_cuda_graph=True, dmc=True)
     crowd.set_num_walkers(n0)
-    rng_a, rng_b = orc.rng(7), orc.rng(7)
-    da = dmc.DMC(crowd, tau, n0, rng_a.uniform)
-    db = dmc.DMC(OracleEngine(ov, cap), tau, n0, rng_b.uniform)
+    da = api.DMCDriver(crowd, tau, n0, branch_seed=7)
+    db = dmc.DMC(OracleEngine(ov, cap), tau, n0, orc.rng(7).uniform)
     pops = []
-    for gen in range(6):
+    for gen in range(8):
         da.advance()
         db.advance()
-        assert np.array_equal(crowd.last_log, db.eng.last_log), f"generation {gen}"
-        assert da.weights == pytest.approx(db.weights, rel=1e-7)
-        assert da.energies == pytest.approx(db.energies, rel=1e-7)
-        ea = da.branch_step(do_not_branch=(gen == 0))
+        wa, ena, agea = da.walkers()
+        assert wa == pytest.approx(db.weights, rel=1e-7)
+        assert ena == pytest.approx(db.energies, rel=1e-7)
+        assert np.array_equal(agea, db.ages)
+        ea = da.branch_step(gen, do_not_branch=(gen == 0))
         eb = db.branch_step(do_not_branch=(gen == 0))
-        assert crowd.nw == ov.nw
+        assert ea["local"] == ov.nw == ea["population"]
         assert ea["energy"] == pytest.approx(eb["energy"], rel=1e-7)
-        assert da.branch.e_trial == pytest.approx(db.branch.e_trial, rel=1e-7, abs=1e-7)
+        assert ea["e_trial"] == pytest.approx(db.branch.e_trial, rel=1e-7, abs=1e-7)
+        assert crowd.positions() == pytest.approx(ov.positions()[:crowd.nw], rel=1e-9, abs=1e-9), f"generation {gen}"
         pops.append(crowd.nw)
     assert len(set(pops)) > 1, pops  # the population really changed
     assert crowd.positions() == pytest.approx(ov.positions()[:crowd.nw], rel=1e-9, abs=1e-9)
@@ -162,7 +164,7 @@ def _two_gpu_worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    from qmcpack_b200 import api, dmc, build
+    from qmcpack_b200 import api, build
     from qmcpack_b200.workload import initial_positions
     build.build()
     api.init(rank)
@@ -174,17 +176,19 @@ def _two_gpu_worker(rank, world, port, q):
     crowd.mw_recompute()
     crowd.vmc_init(tau=tau, seed=100 + rank, use_cuda_graph=False, dmc=True)
     crowd.set_num_walkers(n0)
-    rng = np.random.default_rng(5 + rank)
-    d = dmc.DMC(crowd, tau, world * n0, rng.random, dist=dist, device=torch.device("cuda", rank))
+    comm = api.TorchComm(dist, crowd.walker_bytes, torch.device("cuda", rank))
+    d = api.DMCDriver(crowd, tau, world * n0, branch_seed=5 + rank, comm=comm)
     # make rank 0 heavy and rank 1 light so that walkers must cross NVLink
     pops, sent = [], 0
     for gen in range(5):
         d.advance()
         if gen == 1:
-            d.weights = d.weights * (2.5 if rank == 0 else 0.3)
-        before = crowd.nw
-        ens = d.branch_step(do_not_branch=(gen == 0))
+            w, _, _ = d.walkers()
+            d.set_weights(w * (2.5 if rank == 0 else 0.3))
+        ens = d.branch_step(gen, do_not_branch=(gen == 0))
+        sent += ens["walkers_sent"]
         pops.append(crowd.nw)
+    print("rank %d: populations %s, messages sent %d, %d bytes over NCCL p2p" % (rank, pops, sent, comm.bytes_sent), flush=True)
     lp, ke, _, _ = crowd.mw_evaluateGL()
     crowd.mw_recompute()  # delayed-update state of received / copied walkers == from-scratch state
     lp2, ke2, _, _ = crowd.mw_evaluateGL()
