@@ -161,7 +161,8 @@ int qmcb_det_delay_count(qmcb_crowd* c, int spin);
 /* measurement hook for bench.py / scripts: runs `reps` back-to-back DelayedUpdateBatched::mw_updateInvMat launches
  * (Fermion/DelayedUpdateBatched.h:675-738) of determinant `spin` with `delay_count` pending slots and returns the mean
  * time of one flush in microseconds (CUDA events on the crowd's stream).  The slots hold whatever the last sweep left, so
- * the inverse is NOT meaningful afterwards: call qmcb_twf_mw_recompute before using the crowd again.                    */
+ * the flushes are arithmetic on stale data; the inverse is saved before and restored afterwards, so the crowd is left as
+ * qmcb_twf_mw_complete_updates leaves it.                                                                               */
 int qmcb_det_time_update_inv_mat(qmcb_crowd* c, int spin, int delay_count, int reps, double* us_per_flush);
 
 /* ---- component level: distance rows + two-body Jastrow -------------------------------------------- */
@@ -204,6 +205,10 @@ int qmcb_vmc_counts(qmcb_crowd* c, long long* n_accept, long long* n_reject);
 /* 2 when the sweeps of this crowd run on the persistent walker-segment kernel, 1 on the two-kernel path, 0 before
  * qmcb_vmc_init                                                                                                          */
 int qmcb_vmc_sweep_kernel(qmcb_crowd* c);
+/* measurement hook: one sweep outside the CUDA graph with an event pair around every launch.  out9[0] = sweep time (us);
+ * out9[1..4] = summed time of the walker-segment kernel, the boundary kernel, the spline gather and the Woodbury flush;
+ * out9[5..8] = their launch counts.                                                                                     */
+int qmcb_vmc_profile_sweep(qmcb_crowd* c, double* out9);
 /* DMC: per-walker rr_accepted / rr_proposed of the LAST sweep (walker Properties R2ACCEPTED / R2PROPOSED,
  * DMCBatched.cpp:139-140,191-222), [nw] doubles each.                                                                 */
 int qmcb_dmc_get_rr(qmcb_crowd* c, double* rr_accepted_host, double* rr_proposed_host);

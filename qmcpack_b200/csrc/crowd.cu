@@ -1491,12 +1491,18 @@ struct Crowd : CrowdBase
     sync();
   }
   int det_delay_count(int spin) override { return delay_count[spin]; }
-  // measurement hook: `reps` back-to-back mw_updateInvMat launches with `c` pending slots, CUDA events on the crowd stream
+  // measurement hook: `reps` back-to-back mw_updateInvMat launches with `c` pending slots, CUDA events on the crowd stream.
+  // The delay buffers hold whatever the last moves left there, so the flushes are arithmetic on stale data: the inverse
+  // is saved before and restored afterwards and the crowd is left exactly as a qmcb_twf_mw_complete_updates call leaves it.
   void det_time_update_inv_mat(int spin, int c, int reps, double* us_per_call) override
   {
     flush_pending();
-    if (c < 1 || c > k || reps < 1)
-      throw std::runtime_error("det_time_update_inv_mat: need 1 <= delay_count <= delay_rank and reps >= 1");
+    if (spin < 0 || spin > 1 || c < 1 || c > k || reps < 1)
+      throw std::runtime_error("det_time_update_inv_mat: need spin in {0, 1}, 1 <= delay_count <= delay_rank and reps >= 1");
+    twf_complete_updates();
+    DevBuf<V> saved;
+    saved.alloc(Ainv[spin].n, false);
+    QMCB_CUDA(cudaMemcpyAsync(saved.p, Ainv[spin].p, Ainv[spin].bytes(), cudaMemcpyDeviceToDevice, st));
     cudaEvent_t e0, e1;
     QMCB_CUDA(cudaEventCreate(&e0));
     QMCB_CUDA(cudaEventCreate(&e1));
@@ -1509,12 +1515,16 @@ struct Crowd : CrowdBase
       launch_flush(spin);
     }
     QMCB_CUDA(cudaEventRecord(e1, st));
+    QMCB_CUDA(cudaMemcpyAsync(Ainv[spin].p, saved.p, Ainv[spin].bytes(), cudaMemcpyDeviceToDevice, st));
     QMCB_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;
     QMCB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     *us_per_call = 1e3 * ms / reps;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    delay_count[spin] = 0;
+    invrow_id[spin]   = -1;
+    sync();
   }
   void det_set_phi_vgl(int spin, const void* phi) override
   {
@@ -1893,6 +1903,73 @@ struct Crowd : CrowdBase
     vmc_ready = true;
   }
 
+  // ---------------------------------------------------------------- per-kernel attribution of one sweep (measurement)
+  struct ProfRec
+  {
+    int kind; // 0 walker-segment kernel, 1 boundary kernel, 2 spline gather, 3 Woodbury flush
+    cudaEvent_t a, b;
+  };
+  std::vector<ProfRec>* prof = nullptr;
+  void prof_begin(int kind)
+  {
+    if (!prof)
+      return;
+    ProfRec r;
+    r.kind = kind;
+    QMCB_CUDA(cudaEventCreate(&r.a));
+    QMCB_CUDA(cudaEventCreate(&r.b));
+    QMCB_CUDA(cudaEventRecord(r.a, st));
+    prof->push_back(r);
+  }
+  void prof_end()
+  {
+    if (prof)
+      QMCB_CUDA(cudaEventRecord(prof->back().b, st));
+  }
+  // out[0] sweep time (us), out[1 + kind] summed kernel time per kind, out[5 + kind] launches per kind
+  void vmc_profile_sweep(double* out) override
+  {
+    flush_pending();
+    if (!vmc_ready)
+      throw std::runtime_error("qmcb_vmc_init has not been called");
+    if (delay_count[0] != 0 || delay_count[1] != 0)
+      twf_complete_updates();
+    std::vector<ProfRec> recs;
+    cudaEvent_t t0, t1;
+    QMCB_CUDA(cudaEventCreate(&t0));
+    QMCB_CUDA(cudaEventCreate(&t1));
+    sync();
+    prof = &recs;
+    QMCB_CUDA(cudaEventRecord(t0, st));
+    try
+    {
+      enqueue_sweep(false);
+    }
+    catch (...)
+    {
+      prof = nullptr;
+      throw;
+    }
+    prof = nullptr;
+    QMCB_CUDA(cudaEventRecord(t1, st));
+    sync();
+    for (int i = 0; i < 9; ++i)
+      out[i] = 0.0;
+    float ms = 0.f;
+    QMCB_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+    out[0] = 1e3 * ms;
+    for (auto& r : recs)
+    {
+      QMCB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+      out[1 + r.kind] += 1e3 * ms;
+      out[5 + r.kind] += 1.0;
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+  }
+
   // ---------------------------------------------------------------- persistent walker-segment kernel (segment.cuh)
   void release_segment_slots()
   {
@@ -2102,8 +2179,12 @@ struct Crowd : CrowdBase
       for (int spin = 0; spin < 2; ++spin)
         for (int e0 = 0; e0 < nel[spin]; e0 += k)
         {
+          prof_begin(0);
           launch_segment(spin, e0, std::min(k, nel[spin] - e0));
+          prof_end();
+          prof_begin(3);
           launch_flush(spin);
+          prof_end();
         }
       twf_complete_updates();
       QMCB_CUDA(cudaStreamWaitEvent(st, ev_rng_done, 0));
@@ -2111,7 +2192,11 @@ struct Crowd : CrowdBase
     }
     // per electron: [accept(iat-1) + prepare/propose(iat)] -> {spline gather || Jastrow rows}; the boundary kernel is
     // split in two around a Woodbury flush
-    auto boundary = [&](int iat_prev, int iat_next) { launch_boundary(drv, iat_prev, iat_next, nullptr, nullptr); };
+    auto boundary = [&](int iat_prev, int iat_next) {
+      prof_begin(1);
+      launch_boundary(drv, iat_prev, iat_next, nullptr, nullptr);
+      prof_end();
+    };
     boundary(-1, 0);
     for (int iat = 0; iat < N; ++iat)
     {
@@ -2125,7 +2210,9 @@ struct Crowd : CrowdBase
         QMCB_LAUNCH_CHECK();
         QMCB_CUDA(cudaEventRecord(ev_join, st2));
       }
+      prof_begin(2);
       launch_spline(ig, MODE_VGL, invRow[ig].p, det[ig].n, phi_vgl.p, rg.p, st);
+      prof_end();
       if (jast)
         QMCB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
       const int next = iat + 1 < N ? iat + 1 : -1;
@@ -2133,7 +2220,9 @@ struct Crowd : CrowdBase
       if (flush_after || next < 0)
       {
         boundary(iat, -1);
+        prof_begin(3);
         launch_flush(ig);
+        prof_end();
         if (next >= 0)
           boundary(-1, next);
       }

@@ -55,7 +55,7 @@ struct SegRng
 
 struct SegLayout
 {
-  unsigned ring, phi, x, Bs, vec, red, rgp, sg, hdr, bars, jl, total;
+  unsigned ring, phi, x, Bs, vec, red, rgp, sg, hdr, bars, jred, jsum, jl, total;
   int jl_entries;
 };
 
@@ -76,7 +76,9 @@ __host__ __device__ inline SegLayout seg_layout(int n, int k, int N, int nions)
   L.sg = o, o += 8 * (unsigned)sizeof(T);
   L.hdr = o, o += up((SPL_HDR + SPL_SCRATCH + 4) * (unsigned)sizeof(T), 16);
   L.bars = o, o += 64;
-  L.jl_entries = (int)up((unsigned)(N + nions + 128), 32);
+  L.jred = o, o += 320 * (unsigned)sizeof(T); // group reduction of the ten Jastrow sums
+  L.jsum = o, o += 16 * (unsigned)sizeof(T);  // the sums of the move being decided
+  L.jl_entries = (int)up((unsigned)(N + nions + 256), 32);
   L.jl = o, o += up(2u * (unsigned)L.jl_entries, 16);
   L.total = o;
   return L;
@@ -122,7 +124,7 @@ struct SegVec<double, 2>
 // displacement, the Gaussian part and the position (Metropolis test, Jastrow accept and API readers take them from memory)
 template<typename T, bool STORE>
 __device__ __forceinline__ void seg_propose(const DriverDev<T>& Dr, const JastrowDev<T>& J, const int iw, const int iat,
-                                            const T* g_det, T newpos[3])
+                                            const T* g_det, T newpos[3], T* disp_out = nullptr, T* delta_out = nullptr)
 {
   const int lane = threadIdx.x & 31;
   const int d    = lane < 3 ? lane : 0;
@@ -151,13 +153,65 @@ __device__ __forceinline__ void seg_propose(const DriverDev<T>& Dr, const Jastro
   newpos[0] = __shfl_sync(0xffffffffu, p, 0);
   newpos[1] = __shfl_sync(0xffffffffu, p, 1);
   newpos[2] = __shfl_sync(0xffffffffu, p, 2);
+  if (disp_out)
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+    {
+      disp_out[e]  = __shfl_sync(0xffffffffu, disp, e);
+      delta_out[e] = __shfl_sync(0xffffffffu, delta, e);
+    }
 }
 
-// Metropolis test of (walker iw, electron iat) by one warp.  q[4]: determinant ratio and gradient dots (undivided).
-// Returns the decision in every lane; rdet_out = determinant ratio.
+// what the Metropolis test of (iw, iat) needs from memory besides the orbital dots: fetched by the Metropolis warp WHILE
+// the spline gather of the same move runs, so that the test itself is arithmetic plus the cross-walker look-back
+template<typename T>
+struct SegMetroPre
+{
+  T uat_old, vat_old;          // Uat[iat], Vat[iat] of the committed configuration
+  T disp[3], delta[3];         // proposed displacement and its Gaussian part
+  T rr;                        // DMC: tau |Gaussian|^2
+  unsigned tag;                // sweep tag of the look-back arrays
+  unsigned long long base;     // raw outputs consumed before this move
+  uint32_t raw_spec;           // ring word at base + iw (the draw of this walker when every lower walker draws)
+};
+
+template<typename T>
+__device__ __forceinline__ SegMetroPre<T> seg_metro_prefetch(const DriverDev<T>& Dr, const JastrowDev<T>& J, const RngDev& R,
+                                                             const SegRng& SR, const int iw, const int iat, const T* g_det)
+{
+  SegMetroPre<T> P;
+  T np3[3];
+  seg_propose<T, false>(Dr, J, iw, iat, g_det, np3, P.disp, P.delta);
+  P.uat_old = J.has_j2 ? J.Uat[(size_t)iw * J.npad + iat] : T(0);
+  P.vat_old = J.has_j1 ? J.Vat[(size_t)iw * J.N + iat] : T(0);
+  P.rr      = T(0);
+  if (Dr.dmc)
+  {
+    const T* dr = Dr.deltas + ((size_t)iat * Dr.nw + iw) * 3;
+    P.rr        = Dr.tauovermass * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
+  }
+  P.tag = ((*R.sweep) & 0x3fffffffu) + 1u;
+  if (iat == 0)
+    P.base = R.pos[0]; // left by the sweep prologue (rng_advance_kernel)
+  else
+  {
+    volatile unsigned* tt = SR.tot_tag + iat;
+    while (*tt != P.tag)
+      __nanosleep(64);
+    __threadfence();
+    P.base = *((volatile unsigned long long*)(SR.tot_val + iat));
+  }
+  P.raw_spec = R.ring[(unsigned)((P.base + (unsigned long long)iw) & R.ring_mask)];
+  return P;
+}
+
+// Metropolis test of (walker iw, electron iat) by one warp.  q[4]: determinant ratio and gradient dots (undivided);
+// js[10]: Jastrow sums at the proposed position (shared memory); P: seg_metro_prefetch.  Returns the decision in every
+// lane; rdet_out = determinant ratio.
 template<typename T>
 __device__ __forceinline__ bool seg_metropolis(const DriverDev<T>& Dr, const JastrowDev<T>& J, const RngDev& R, const SegRng& SR,
-                                               const int iw, const int iat, const T q[4], T& rdet_out)
+                                               const int iw, const int iat, const T q[4], const T* js, const SegMetroPre<T>& P,
+                                               T& rdet_out)
 {
   const int lane = threadIdx.x & 31;
   const T rdet   = q[0];
@@ -165,62 +219,46 @@ __device__ __forceinline__ bool seg_metropolis(const DriverDev<T>& Dr, const Jas
   T gn[3]        = {q[1] / rdet, q[2] / rdet, q[3] / rdet};
   if (J.has_j2)
   {
-    const T* vgl = J.j2_vgl + (size_t)iw * 5;
-    ratio        = ratio * exp((double)(J.Uat[(size_t)iw * J.npad + iat] - vgl[0]));
-    gn[0] += vgl[1];
-    gn[1] += vgl[2];
-    gn[2] += vgl[3];
+    ratio = ratio * exp((double)(P.uat_old - js[0]));
+    gn[0] += js[1];
+    gn[1] += js[2];
+    gn[2] += js[3];
   }
   if (J.has_j1)
   {
-    const T* cur = J.j1_cur + (size_t)iw * 5;
-    ratio        = ratio * exp((double)(J.Vat[(size_t)iw * J.N + iat] - cur[0]));
-    gn[0] += cur[1];
-    gn[1] += cur[2];
-    gn[2] += cur[3];
+    ratio = ratio * exp((double)(P.vat_old - js[5]));
+    gn[0] += js[6];
+    gn[1] += js[7];
+    gn[2] += js[8];
   }
   T log_gf = T(0), log_gb = T(0);
   if (Dr.use_drift)
   {
-    const T* dl = Dr.delta_cur + 3 * iw;
-    log_gf      = -Dr.oneover2tau * (dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
+    log_gf = -Dr.oneover2tau * (P.delta[0] * P.delta[0] + P.delta[1] * P.delta[1] + P.delta[2] * P.delta[2]);
     T dr[3];
     get_drift<T>(Dr.tauovermass, gn, dr);
-    dr[0] += Dr.drifts[3 * iw];
-    dr[1] += Dr.drifts[3 * iw + 1];
-    dr[2] += Dr.drifts[3 * iw + 2];
+    dr[0] += P.disp[0];
+    dr[1] += P.disp[1];
+    dr[2] += P.disp[2];
     log_gb = -Dr.oneover2tau * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
   }
   const T eps = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
   T prob      = (T)(ratio * ratio); // std::norm(ratio), VMCBatched.cpp:152
   bool need   = prob >= eps;
-  T rr        = T(0);
   if (Dr.dmc)
   {
     // DMCBatched.cpp:188-250 (see metropolis_warp in crowd.cu)
-    const T* dr       = Dr.deltas + ((size_t)iat * Dr.nw + iw) * 3;
-    rr                = Dr.tauovermass * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
     const bool reject = !(ratio > 0.0);
     prob              = (T)(ratio * ratio * (double)exp(log_gb - log_gf));
     need              = !reject && prob >= eps;
   }
   // ---- position of this walker's draw in the crowd's stream
-  const unsigned tag = ((*R.sweep) & 0x3fffffffu) + 1u;
+  const unsigned tag    = P.tag;
   volatile unsigned* fl = SR.flags + (size_t)iat * SR.stride;
   if (lane == 0)
     fl[iw] = (tag << 1) | (need ? 1u : 0u);
-  unsigned long long base;
-  if (iat == 0)
-    base = R.pos[0]; // left by the sweep prologue (rng_advance_kernel)
-  else
-  {
-    volatile unsigned* tt = SR.tot_tag + iat;
-    while (*tt != tag)
-      __nanosleep(40);
-    __threadfence();
-    base = *((volatile unsigned long long*)(SR.tot_val + iat));
-  }
-  unsigned cnt = 0;
+  const unsigned long long base = P.base;
+  unsigned cnt                  = 0;
   for (int j = lane; j < iw; j += 32)
   {
     unsigned f;
@@ -245,15 +283,16 @@ __device__ __forceinline__ bool seg_metropolis(const DriverDev<T>& Dr, const Jas
     }
     if (need)
     {
-      const double u = rng_uniform(R, base + cnt);
-      acc            = Dr.dmc ? (u < (double)prob) : (u < (double)(prob * exp(log_gb - log_gf)));
+      const uint32_t raw = cnt == (unsigned)iw ? P.raw_spec : R.ring[(unsigned)((base + cnt) & R.ring_mask)];
+      const double u     = (double)raw / 4294967296.0;
+      acc                = Dr.dmc ? (u < (double)prob) : (u < (double)(prob * exp(log_gb - log_gf)));
     }
     Dr.accepted[iw] = acc ? 1 : 0;
     if (Dr.dmc)
     {
-      Dr.rr_proposed[iw] += rr;
+      Dr.rr_proposed[iw] += P.rr;
       if (acc)
-        Dr.rr_accepted[iw] += rr;
+        Dr.rr_accepted[iw] += P.rr;
     }
     if (acc)
       Dr.n_accept[iw] += 1;
@@ -299,7 +338,18 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
   T* hdr    = reinterpret_cast<T*>(smem_raw + L.hdr); // unit header of the evaluation (spline.cuh)
   uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
   uint64_t* empty_bar = full_bar + SEG_NSTAGE;
+  uint64_t* v_bar     = empty_bar + SEG_NSTAGE;
+  // Between two gathers the ring is idle: the pending rows of V (the stale inverse rows of the delayed electrons) are
+  // pulled into it by ONE bulk copy (they are contiguous per walker), and both passes over V -- the accept's -V.phi dots
+  // and the next row's x += V^T w -- read shared memory instead of making c dependent trips to L2.
+  T* vs                = ring + 4 * n;                                  // behind vrow and glrow
+  const int v_cap      = (SEG_NSTAGE * STAGE_ELEMS - 4 * n) / n;         // rows that fit
+  const bool v_bulk    = ((size_t)n * sizeof(T)) % 16 == 0;              // bulk copies move multiples of 16 bytes
+  unsigned v_phase     = 0;
+  T* jred             = reinterpret_cast<T*>(smem_raw + L.jred);
+  T* jsum             = reinterpret_cast<T*>(smem_raw + L.jsum);
   unsigned short* jl  = reinterpret_cast<unsigned short*>(smem_raw + L.jl);
+  SegMetroPre<T> mpre; // (warp 7)
 
   if (tid == 0)
   {
@@ -308,6 +358,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], SEG_NCONS / 32);
     }
+    ptx::mbar_init(v_bar, 1);
     ptx::fence_barrier_init();
     if (nmoves > 0)
       ptx::prefetch_tensormap(&tmap);
@@ -335,6 +386,22 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           v[e] = gx[e] = gy[e] = gz[e] = hxx[e] = hxy[e] = hxz[e] = hyy[e] = hyz[e] = hzz[e] = T(0);
         const int cfirst = tid * CPT;
         const int blk = cfirst / SEG_BOXW, loc = cfirst - blk * SEG_BOXW;
+        // Jastrow sums at the proposed position while the first slabs are in flight (every warp derives the proposal
+        // itself: a handful of L1/L2 hits and shuffles, no barrier)
+        if (J.has_j2 || J.has_j1)
+        {
+          T np3[3], js[10];
+          seg_propose<T, false>(Dr, J, iw, iat, sg, np3);
+          jastrow_move_group<T>(Group{tid, SEG_NCONS, 3}, J, iw, iat, np3, jred, jl, js);
+          if (tid < 10)
+          {
+            T mine = js[0];
+#pragma unroll
+            for (int e = 1; e < 10; ++e)
+              mine = tid == e ? js[e] : mine;
+            jsum[tid] = mine;
+          }
+        }
         T cz[4], dcz[4], d2cz[4];
 #pragma unroll
         for (int qq = 0; qq < SEG_NQ; ++qq)
@@ -497,14 +564,8 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
       }
       else
       {
-        // ---- warp 7: Jastrow sums at the proposed position (stored for the Metropolis test and the accept)
-        T np3[3];
-        seg_propose<T, false>(Dr, J, iw, iat, sg, np3);
-        if (J.has_j2 || J.has_j1)
-        {
-          T js[10];
-          jastrow_move_warp<T>(J, iw, iat, np3, jl, js);
-        }
+        // ---- warp 7: everything the Metropolis test needs from memory, fetched under the gather
+        mpre = seg_metro_prefetch<T>(Dr, J, R, SR, iw, iat, sg);
       }
       gq += SEG_NQ;
       __syncthreads(); // B1: orbital rows and partial dots in shared memory, Jastrow sums and the proposal in memory
@@ -513,6 +574,14 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
     // ======================= Metropolis test (warp 7) || accept-independent staging and dots (warps 0-6) =======================
     const int cA = part1 ? c : 0;                   // rows of V final before this step
     const int cB = part2 ? (part1 ? c : cn) : 0;    // rows of U final before this step
+    const int nv  = part1 ? c : (part2 ? cn : 0);          // rows of V this step reads
+    const int nvs = v_bulk ? (nv < v_cap ? nv : v_cap) : 0; // ... of which staged in shared memory
+    if (tid == 0 && nvs > 0)
+    {
+      const unsigned bytes = (unsigned)((size_t)nvs * n * sizeof(T));
+      ptx::mbar_arrive_expect_tx(v_bar, bytes);
+      ptx::bulk_g2s(vs, D.V + (size_t)iw * k * n, bytes, v_bar);
+    }
     if (warp == 7)
     {
       if (part1)
@@ -523,7 +592,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           for (int e = 0; e < 4; ++e)
             q[e] += rgp[pw * 4 + e];
         T rdet;
-        const bool acc = seg_metropolis<T>(Dr, J, R, SR, iw, iat, q, rdet);
+        const bool acc = seg_metropolis<T>(Dr, J, R, SR, iw, iat, q, jsum, mpre, rdet);
         if (lane == 0)
         {
           s_acc   = acc ? 1 : 0;
@@ -569,17 +638,29 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
       const T* Ub     = D.U + (size_t)iw * k * n;
       const int nspec = (part1 && part2) ? 1 : 0; // phi.x for the slot this move may append
       const int ntask = cA + cB + nspec;
+      // task order: rows of U (memory) and the speculative dot first, rows of V last -- those come from the staged copy,
+      // which lands while the U rows are read
+      const int nU = cB + nspec;
+      bool v_waited = false;
       for (int t0 = warp; t0 < ntask; t0 += 14)
       {
         const int t1 = t0 + 7;
         const T *r0, *v0, *r1, *v1;
         auto pick = [&](int t, const T*& r, const T*& v) {
-          if (t < cA)
-            r = Va + (size_t)t * n, v = phi;
-          else if (t < cA + cB)
-            r = Ub + (size_t)(t - cA) * n, v = x;
-          else
+          if (t < cB)
+            r = Ub + (size_t)t * n, v = x;
+          else if (t < nU)
             r = phi, v = x;
+          else
+          {
+            const int a = t - nU;
+            r = a < nvs ? vs + (size_t)a * n : Va + (size_t)a * n, v = phi;
+            if (a < nvs && !v_waited)
+            {
+              ptx::mbar_wait(v_bar, v_phase);
+              v_waited = true;
+            }
+          }
         };
         pick(t0, r0, v0);
         r1 = r0, v1 = v0;
@@ -614,16 +695,16 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         s1 = warp_sum(s1);
         if (lane == 0)
         {
-          if (t0 < cA)
-            pA[t0] = -s0;
+          if (t0 < nU)
+            pB[t0] = s0;
           else
-            pB[t0 - cA] = s0;
+            pA[t0 - nU] = -s0;
           if (two)
           {
-            if (t1 < cA)
-              pA[t1] = -s1;
+            if (t1 < nU)
+              pB[t1] = s1;
             else
-              pB[t1 - cA] = s1;
+              pA[t1 - nU] = -s1;
           }
         }
       }
@@ -712,10 +793,14 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           w[tid] = -sacc; // w = -Binv^T p'  (DelayedUpdate.h:100-101)
         }
         gd.sync();
-        // x += V^T w : rows < cB from L2, the row appended by this move from shared memory
+        // x += V^T w : the staged rows from shared memory, rows beyond the staging capacity from L2, the row appended
+        // by this move from vrow
         const T* Vm = D.V + (size_t)iw * k * n;
         T acc3[3]   = {T(0), T(0), T(0)};
         constexpr int XC = sizeof(T) > 4 ? 2 : 3;
+        if (nvs > 0)
+          ptx::mbar_wait(v_bar, v_phase); // (warps that read no V row in the staging phase have not observed it yet)
+        const int cS = cB < nvs ? cB : nvs;
         for (int jb = tid; jb < n; jb += XC * gd.n)
         {
           T sacc[XC];
@@ -723,7 +808,19 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           for (int qx = 0; qx < XC; ++qx)
             sacc[qx] = T(0);
 #pragma unroll 4
-          for (int a = 0; a < cB; ++a)
+          for (int a = 0; a < cS; ++a)
+          {
+            const T wa = w[a];
+#pragma unroll
+            for (int qx = 0; qx < XC; ++qx)
+            {
+              const int j = jb + qx * gd.n;
+              if (j < n)
+                sacc[qx] += vs[(size_t)a * n + j] * wa;
+            }
+          }
+#pragma unroll 4
+          for (int a = cS; a < cB; ++a)
           {
             const T wa = w[a];
 #pragma unroll
@@ -760,6 +857,8 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
     }
     else if (part1 && s_acc != 0)
       jastrow_accept_body<T>(Group{tid - SEG_TPB / 2, SEG_TPB / 2, 2}, J, iw, iat, jl);
+    if (nvs > 0)
+      v_phase ^= 1u;
     __syncthreads(); // B3
   }
 
