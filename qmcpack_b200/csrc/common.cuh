@@ -317,6 +317,33 @@ __device__ __forceinline__ cx<T> warp_sum(cx<T> v)
   return cx<T>(warp_sum(v.re), warp_sum(v.im));
 }
 
+// warp-wide sums of NV (4 or 16) values per lane with the recursive-halving exchange: at every step a lane hands half of
+// its values to its partner and keeps the other half, so NV values cost NV - 1 + log2(32 / NV) shuffles instead of
+// 5 NV.  On return lane l holds, in v[0], the total of value number l / (32 / NV) (l >> 1 for NV = 16, l >> 3 for NV = 4);
+// the order in which a total is added up is fixed (it depends on the lane numbers only).
+template<typename T, int NV>
+__device__ __forceinline__ void warp_fold(T (&v)[NV])
+{
+  static_assert(NV == 4 || NV == 16, "warp_fold handles 4 or 16 values");
+  const int lane = threadIdx.x & 31;
+  int off        = 16;
+#pragma unroll
+  for (int m = NV / 2; m >= 1; m /= 2, off /= 2)
+  {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < m; ++i)
+    {
+      const T send = upper ? v[i] : v[i + m];
+      const T keep = upper ? v[i + m] : v[i];
+      v[i]         = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off >= 1; off /= 2)
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+}
+
 // a group of threads of one CTA that synchronise on their own named barrier (bar 0 with the full CTA == __syncthreads)
 struct Group
 {

@@ -1258,22 +1258,25 @@ struct Crowd : CrowdBase
       launch_prepare(spin, row, nullptr);
   }
   template<int KD, int KC, int STAGES>
-  void launch_flush_dmma_as(const DetDev<V>& D, int c)
+  void launch_flush_dmma_as(const DetDev<V>& D, int c, bool up_ready)
   {
     constexpr size_t smem = wb64::smem_bytes<V, KD, KC, STAGES>();
     ensure_dynamic_smem(wb64::woodbury_flush_dmma_kernel<V, KD, KC, STAGES>, smem);
     const int n = D.n;
     // U'[c x n] = Binv[c x c] * V[c x n]  (0.8 MFLOP per walker at a64; the fused kernel reads it back from L2)
     static const int up_simt = env_flag("QMCB_UP_SIMT", 0);
-    if (up_simt)
-      wb64::binv_v_kernel<V><<<dim3(blocks(n, 128), nw, blocks(c, 8)), 128, 0, st>>>(D, c);
-    else
+    if (!up_ready)
     {
-      constexpr size_t smem_b = (size_t)KD * (KD + 4) * sizeof(V);
-      ensure_dynamic_smem(wb64::binv_v_dmma_kernel<V, KD>, smem_b);
-      wb64::binv_v_dmma_kernel<V, KD><<<nw, wb64::TPB, smem_b, st>>>(D, c);
+      if (up_simt)
+        wb64::binv_v_kernel<V><<<dim3(blocks(n, 128), nw, blocks(c, 8)), 128, 0, st>>>(D, c);
+      else
+      {
+        constexpr size_t smem_b = (size_t)KD * (KD + 4) * sizeof(V);
+        ensure_dynamic_smem(wb64::binv_v_dmma_kernel<V, KD>, smem_b);
+        wb64::binv_v_dmma_kernel<V, KD><<<nw, wb64::TPB, smem_b, st>>>(D, c);
+      }
+      QMCB_LAUNCH_CHECK();
     }
-    QMCB_LAUNCH_CHECK();
     static const int split_env = [] {
       const char* e = std::getenv("QMCB_DMMA_SPLIT");
       return e ? std::atoi(e) : 0;
@@ -1283,14 +1286,14 @@ struct Crowd : CrowdBase
     wb64::woodbury_flush_dmma_kernel<V, KD, KC, STAGES><<<dim3(split, nw), wb64::TPB, smem, st>>>(D, c);
     QMCB_LAUNCH_CHECK();
   }
-  bool launch_flush_dmma(const DetDev<V>& D, int c)
+  bool launch_flush_dmma(const DetDev<V>& D, int c, bool up_ready)
   {
     if constexpr (std::is_same<V, double>::value)
     {
       if (wb64::eligible<V>(D.n, D.k, c, 32))
-        launch_flush_dmma_as<32, 32, 4>(D, c);
+        launch_flush_dmma_as<32, 32, 4>(D, c, up_ready);
       else if (wb64::eligible<V>(D.n, D.k, c, 64))
-        launch_flush_dmma_as<64, 32, 4>(D, c);
+        launch_flush_dmma_as<64, 32, 4>(D, c, up_ready);
       else
         return false;
       return true;
@@ -1298,9 +1301,9 @@ struct Crowd : CrowdBase
     else if constexpr (std::is_same<V, cx<double>>::value)
     {
       if (wb64::eligible<V>(D.n, D.k, c, 32))
-        launch_flush_dmma_as<32, 16, 4>(D, c);
+        launch_flush_dmma_as<32, 16, 4>(D, c, up_ready);
       else if (wb64::eligible<V>(D.n, D.k, c, 64))
-        launch_flush_dmma_as<64, 16, 4>(D, c);
+        launch_flush_dmma_as<64, 16, 4>(D, c, up_ready);
       else
         return false;
       return true;
@@ -1308,7 +1311,8 @@ struct Crowd : CrowdBase
     else
       return false;
   }
-  void launch_flush(int spin)
+  // up_ready: U' = Binv V is already in D.Up (written by the walker-segment kernel)
+  void launch_flush(int spin, bool up_ready = false)
   {
     const int c = delay_count[spin];
     if (c == 0)
@@ -1326,7 +1330,7 @@ struct Crowd : CrowdBase
       {
         const size_t smem5 = wb5::smem_bytes(n);
         ensure_dynamic_smem(wb5::woodbury_flush_tc5_kernel, 200 * 1024);
-        wb5::woodbury_flush_tc5_kernel<<<dim3((n + wb5::TM - 1) / wb5::TM, nw), wb5::TPB, smem5, st>>>(D, c);
+        wb5::woodbury_flush_tc5_kernel<<<dim3((n + wb5::TM - 1) / wb5::TM, nw), wb5::TPB, smem5, st>>>(D, c, up_ready ? 1 : 0);
         QMCB_LAUNCH_CHECK();
         delay_count[spin] = 0;
         invrow_id[spin]   = -1;
@@ -1356,7 +1360,7 @@ struct Crowd : CrowdBase
         const char* e = std::getenv("QMCB_FLUSH");
         return !e || std::string(e) != "simt";
       }();
-      if (use_dmma && launch_flush_dmma(D, c))
+      if (use_dmma && launch_flush_dmma(D, c, up_ready))
       {
         delay_count[spin] = 0;
         invrow_id[spin]   = -1;
@@ -2183,7 +2187,7 @@ struct Crowd : CrowdBase
           launch_segment(spin, e0, std::min(k, nel[spin] - e0));
           prof_end();
           prof_begin(3);
-          launch_flush(spin);
+          launch_flush(spin, true);
           prof_end();
         }
       twf_complete_updates();

@@ -325,25 +325,25 @@ __device__ __forceinline__ void jastrow_move_body(const JastrowDev<RT>& J, const
     J.j1_cur[(size_t)iw * 5 + tid] = acc[5 + tid];
 }
 
-// ---- the same sums by a thread GROUP with its own named barrier (walker-segment kernel, segment.cuh: the spline consumer
-// warps run them while the first stencil slabs are in flight).  red >= 10 * 32 RT, jl >= ceil((N + nions) / g.n) * g.n
-// entries.  On return every thread of the group holds the ten sums {J2: u, gx, gy, gz, lap; J1: the same}; thread 0 has
-// stored j2_vgl / j1_cur for the accept and for API readers.
+// ---- the same sums by `nwarps` warps of a CTA WITHOUT any barrier (walker-segment kernel, segment.cuh: the spline
+// consumer warps run them while the first stencil slabs are in flight).  Warp `wg` of the set takes the candidates
+// it * 32 nwarps + 32 wg + lane, compacts its in-range pairs into its own list segment and leaves its ten partial sums
+// {J2: u, gx, gy, gz, lap; J1: the same} in part[0..10) (shared memory, 16 entries per warp); whoever consumes the sums
+// adds the warps' partials in index order.  jl: >= ceil((N + nions) / (32 nwarps)) * 32 nwarps entries.
 template<typename RT>
-__device__ __forceinline__ void jastrow_move_group(const Group& g, const JastrowDev<RT>& J, const int iw, const int iat,
-                                                   const RT pos[3], RT* red, unsigned short* jl, RT (&acc)[10])
+__device__ __forceinline__ void jastrow_move_warps(const int wg, const int nwarps, const JastrowDev<RT>& J, const int iw,
+                                                   const int iat, const RT pos[3], unsigned short* jl, RT* part)
 {
-  const int tid = g.tid, N = J.N, np = J.npad, STEP = g.n;
-  const int lane = tid & 31, wg = tid >> 5;
+  const int lane = threadIdx.x & 31, N = J.N, np = J.npad, STEP = 32 * nwarps, tid = 32 * wg + lane;
   const RT* rs = J.rsoa + (size_t)iw * 3 * np;
+  RT acc[16];
 #pragma unroll
-  for (int e = 0; e < 10; ++e)
+  for (int e = 0; e < 16; ++e)
     acc[e] = RT(0);
   const int n2 = J.has_j2 ? N : 0, n1 = J.has_j1 ? J.nions : 0;
   const int gi = (iat < J.n_up ? 0 : 1) * 2;
   const int iters  = (n2 + n1 + STEP - 1) / STEP;
-  const int segcap = iters * 32;
-  unsigned short* seg = jl + wg * segcap;
+  unsigned short* seg = jl + wg * iters * 32;
   int cnt = 0;
   // pass 1: every distance; the loads of two iterations are in flight together
   for (int it = 0; it < iters; it += 2)
@@ -353,10 +353,8 @@ __device__ __forceinline__ void jastrow_move_group(const Group& g, const Jastrow
 #pragma unroll
     for (int h = 0; h < 2; ++h)
     {
-      idx[h] = (it + h) * STEP + tid;
+      idx[h] = (it + h < iters) ? (it + h) * STEP + tid : n2 + n1;
       px[h] = py[h] = pz[h] = RT(0);
-      if (it + h >= iters)
-        idx[h] = n2 + n1; // nothing
       if (idx[h] < n2)
         px[h] = rs[idx[h]], py[h] = rs[np + idx[h]], pz[h] = rs[2 * np + idx[h]];
       else if (idx[h] < n2 + n1)
@@ -418,137 +416,9 @@ __device__ __forceinline__ void jastrow_move_group(const Group& g, const Jastrow
       acc[9] += d2u + RT(2) * du;
     }
   }
-  group_sum<RT, 10>(g, acc, red);
-  if (tid == 0)
-  {
-    if (J.has_j2)
-    {
-      RT* vgl = J.j2_vgl + (size_t)iw * 5;
-      vgl[0]  = acc[0];
-      vgl[1]  = acc[1];
-      vgl[2]  = acc[2];
-      vgl[3]  = acc[3];
-      vgl[4]  = -acc[4];
-    }
-    if (J.has_j1)
-    {
-      RT* cur = J.j1_cur + (size_t)iw * 5;
-#pragma unroll
-      for (int e = 0; e < 5; ++e)
-        cur[e] = acc[5 + e];
-    }
-  }
-}
-
-// ---- the same sums by ONE warp (fused walker-segment kernel, segment.cuh: the warp works beside the spline gather of
-// the same move, so no CTA barrier may appear here).  jl: (N + nions) rounded up to 32 entries of shared memory owned by
-// the warp.  All 32 lanes call it; on return every lane holds the ten sums {J2: u, gx, gy, gz, lap; J1: the same} and
-// lane 0 has stored j2_vgl / j1_cur for the accept (jastrow_accept_body) and for API readers.
-template<typename RT>
-__device__ __forceinline__ void jastrow_move_warp(const JastrowDev<RT>& J, const int iw, const int iat, const RT pos[3],
-                                                  unsigned short* jl, RT acc[10])
-{
-  const int lane = threadIdx.x & 31, N = J.N, np = J.npad;
-  const RT* rs = J.rsoa + (size_t)iw * 3 * np;
-#pragma unroll
-  for (int e = 0; e < 10; ++e)
-    acc[e] = RT(0);
-  const int n2 = J.has_j2 ? N : 0, n1 = J.has_j1 ? J.nions : 0;
-  const int gi = (iat < J.n_up ? 0 : 1) * 2;
-  int cnt      = 0;
-  // pass 1: all distances, indices of the in-range pairs compacted in (iteration, lane) order
-  for (int base = 0; base < n2 + n1; base += 64)
-  {
-    // two candidates per lane per trip: the position loads of both are in flight together
-    int idx[2];
-    RT px[2], py[2], pz[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-    {
-      idx[h] = base + 32 * h + lane;
-      px[h] = py[h] = pz[h] = RT(0);
-      if (idx[h] < n2)
-        px[h] = rs[idx[h]], py[h] = rs[np + idx[h]], pz[h] = rs[2 * np + idx[h]];
-      else if (idx[h] < n2 + n1)
-      {
-        const int j = idx[h] - n2;
-        px[h] = J.ion_rsoa[j], py[h] = J.ion_rsoa[J.npad_ion + j], pz[h] = J.ion_rsoa[2 * J.npad_ion + j];
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-    {
-      bool need = false;
-      RT r, dx, dy, dz;
-      if (idx[h] < n2)
-      {
-        min_image(J.cell, pos, px[h], py[h], pz[h], idx[h], iat, r, dx, dy, dz);
-        const FunctorDev<RT>& F = J.F2[gi + (idx[h] < J.n_up ? 0 : 1)];
-        need                    = idx[h] != iat && F.coefs != nullptr && r < F.rcut;
-      }
-      else if (idx[h] < n2 + n1)
-      {
-        min_image(J.cell, pos, px[h], py[h], pz[h], idx[h] - n2, 0, r, dx, dy, dz);
-        const FunctorDev<RT>& F = J.F1[J.ion_grp[idx[h] - n2]];
-        need                    = F.coefs != nullptr && r < F.rcut;
-      }
-      const unsigned mk = __ballot_sync(0xffffffffu, need);
-      if (need)
-        jl[cnt + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)idx[h];
-      cnt += __popc(mk);
-    }
-  }
-  __syncwarp();
-  // pass 2: functors over the list with full warps
-  for (int e = lane; e < cnt; e += 32)
-  {
-    const int idx = jl[e];
-    RT r, dx, dy, dz, du, d2u;
-    if (idx < n2)
-    {
-      min_image(J.cell, pos, rs[idx], rs[np + idx], rs[2 * np + idx], idx, iat, r, dx, dy, dz);
-      const RT u = functor_eval(J.F2[gi + (idx < J.n_up ? 0 : 1)], r, du, d2u);
-      acc[0] += u;
-      acc[1] += du * dx;
-      acc[2] += du * dy;
-      acc[3] += du * dz;
-      acc[4] += d2u + RT(2) * du;
-    }
-    else
-    {
-      const int j = idx - n2;
-      min_image(J.cell, pos, J.ion_rsoa[j], J.ion_rsoa[J.npad_ion + j], J.ion_rsoa[2 * J.npad_ion + j], j, 0, r, dx, dy, dz);
-      const RT u = functor_eval(J.F1[J.ion_grp[j]], r, du, d2u);
-      acc[5] += u;
-      acc[6] += du * dx;
-      acc[7] += du * dy;
-      acc[8] += du * dz;
-      acc[9] += d2u + RT(2) * du;
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < 10; ++e)
-    acc[e] = warp_sum(acc[e]);
-  if (lane == 0)
-  {
-    if (J.has_j2)
-    {
-      RT* vgl = J.j2_vgl + (size_t)iw * 5;
-      vgl[0]  = acc[0];
-      vgl[1]  = acc[1];
-      vgl[2]  = acc[2];
-      vgl[3]  = acc[3];
-      vgl[4]  = -acc[4];
-    }
-    if (J.has_j1)
-    {
-      RT* cur = J.j1_cur + (size_t)iw * 5;
-#pragma unroll
-      for (int e = 0; e < 5; ++e)
-        cur[e] = acc[5 + e];
-    }
-  }
-  __syncwarp();
+  warp_fold<RT, 16>(acc); // lane l holds the total of value l >> 1
+  if ((lane & 1) == 0 && (lane >> 1) < 10)
+    part[lane >> 1] = acc[0];
 }
 
 // grid = nw

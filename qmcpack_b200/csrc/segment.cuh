@@ -76,8 +76,8 @@ __host__ __device__ inline SegLayout seg_layout(int n, int k, int N, int nions)
   L.sg = o, o += 8 * (unsigned)sizeof(T);
   L.hdr = o, o += up((SPL_HDR + SPL_SCRATCH + 4) * (unsigned)sizeof(T), 16);
   L.bars = o, o += 64;
-  L.jred = o, o += 320 * (unsigned)sizeof(T); // group reduction of the ten Jastrow sums
-  L.jsum = o, o += 16 * (unsigned)sizeof(T);  // the sums of the move being decided
+  L.jred = o, o += 96 * (unsigned)sizeof(T); // per-consumer-warp partials of the ten Jastrow sums [6][16]
+  L.jsum = o, o += 16 * (unsigned)sizeof(T); // the sums of the move being decided
   L.jl_entries = (int)up((unsigned)(N + nions + 256), 32);
   L.jl = o, o += up(2u * (unsigned)L.jl_entries, 16);
   L.total = o;
@@ -118,6 +118,28 @@ struct SegVec<double, 2>
     o[0] = v.x, o[1] = v.y;
   }
 };
+
+// four consecutive values with 16-byte loads (rows whose byte length is a multiple of 16)
+template<typename T>
+struct V4
+{
+  T x, y, z, w;
+};
+__device__ __forceinline__ V4<float> ld4(const float* p)
+{
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  return V4<float>{v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ V4<double> ld4(const double* p)
+{
+  const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+  return V4<double>{a.x, a.y, b.x, b.y};
+}
+template<typename T>
+__device__ __forceinline__ T dot4(const V4<T>& a, const V4<T>& b)
+{
+  return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+}
 
 // proposal of electron iat for walker iw by one warp: lanes 0-2 own one Cartesian component each; every lane returns
 // the proposed position.  g_det: determinant gradient of the prepared row (shared memory).  STORE: publish the
@@ -197,7 +219,7 @@ __device__ __forceinline__ SegMetroPre<T> seg_metro_prefetch(const DriverDev<T>&
   {
     volatile unsigned* tt = SR.tot_tag + iat;
     while (*tt != P.tag)
-      __nanosleep(64);
+      __nanosleep(100);
     __threadfence();
     P.base = *((volatile unsigned long long*)(SR.tot_val + iat));
   }
@@ -263,7 +285,7 @@ __device__ __forceinline__ bool seg_metropolis(const DriverDev<T>& Dr, const Jas
   {
     unsigned f;
     while (((f = fl[j]) >> 1) != tag)
-      __nanosleep(40);
+      __nanosleep(100);
     cnt += f & 1u;
   }
 #pragma unroll
@@ -390,17 +412,9 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         // itself: a handful of L1/L2 hits and shuffles, no barrier)
         if (J.has_j2 || J.has_j1)
         {
-          T np3[3], js[10];
+          T np3[3];
           seg_propose<T, false>(Dr, J, iw, iat, sg, np3);
-          jastrow_move_group<T>(Group{tid, SEG_NCONS, 3}, J, iw, iat, np3, jred, jl, js);
-          if (tid < 10)
-          {
-            T mine = js[0];
-#pragma unroll
-            for (int e = 1; e < 10; ++e)
-              mine = tid == e ? js[e] : mine;
-            jsum[tid] = mine;
-          }
+          jastrow_move_warps<T>(warp, SEG_NCONS / 32, J, iw, iat, np3, jl, jred + warp * 16);
         }
         T cz[4], dcz[4], d2cz[4];
 #pragma unroll
@@ -486,11 +500,9 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
             acc[3] += dz * wr;
           }
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          acc[e] = warp_sum(acc[e]);
-        if (lane < 4)
-          rgp[warp * 4 + lane] = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+        warp_fold<T, 4>(acc); // lane l holds the total of value l >> 3
+        if ((lane & 7) == 0)
+          rgp[warp * 4 + (lane >> 3)] = acc[0];
       }
       else if (warp == 6)
       {
@@ -591,6 +603,22 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
 #pragma unroll
           for (int e = 0; e < 4; ++e)
             q[e] += rgp[pw * 4 + e];
+        if (J.has_j2 || J.has_j1)
+        {
+          // the consumer warps' partial Jastrow sums in warp order; stored for the accept (jastrow_accept_body) and API readers
+          if (lane < 10)
+          {
+            T t = T(0);
+            for (int pw = 0; pw < SEG_NCONS / 32; ++pw)
+              t += jred[pw * 16 + lane];
+            jsum[lane] = t;
+            if (lane < 5 && J.has_j2)
+              J.j2_vgl[(size_t)iw * 5 + lane] = lane == 4 ? -t : t;
+            if (lane >= 5 && J.has_j1)
+              J.j1_cur[(size_t)iw * 5 + lane - 5] = t;
+          }
+          __syncwarp();
+        }
         T rdet;
         const bool acc = seg_metropolis<T>(Dr, J, R, SR, iw, iat, q, jsum, mpre, rdet);
         if (lane == 0)
@@ -637,74 +665,121 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
       const T* Va     = D.V + (size_t)iw * k * n;
       const T* Ub     = D.U + (size_t)iw * k * n;
       const int nspec = (part1 && part2) ? 1 : 0; // phi.x for the slot this move may append
-      const int ntask = cA + cB + nspec;
-      // task order: rows of U (memory) and the speculative dot first, rows of V last -- those come from the staged copy,
-      // which lands while the U rows are read
       const int nU = cB + nspec;
-      bool v_waited = false;
-      for (int t0 = warp; t0 < ntask; t0 += 14)
+      if (v_bulk)
       {
-        const int t1 = t0 + 7;
-        const T *r0, *v0, *r1, *v1;
-        auto pick = [&](int t, const T*& r, const T*& v) {
-          if (t < cB)
-            r = Ub + (size_t)t * n, v = x;
-          else if (t < nU)
-            r = phi, v = x;
-          else
-          {
-            const int a = t - nU;
-            r = a < nvs ? vs + (size_t)a * n : Va + (size_t)a * n, v = phi;
-            if (a < nvs && !v_waited)
-            {
-              ptx::mbar_wait(v_bar, v_phase);
-              v_waited = true;
-            }
-          }
-        };
-        pick(t0, r0, v0);
-        r1 = r0, v1 = v0;
-        const bool two = t1 < ntask;
-        if (two)
-          pick(t1, r1, v1);
-        T s0(0), s1(0);
-        constexpr int DOT_B = sizeof(T) > 4 ? 6 : 12;
-        for (int jb = lane; jb < n; jb += 32 * DOT_B)
+        // rows are multiples of 16 bytes: every lane keeps its slice of x and of phi in registers for the whole task
+        // loop and reads two rows at a time with 16-byte loads.  Rows of U (memory) and the speculative dot first, rows
+        // of V last -- those come from the staged copy, which lands while the U rows are read.
+        constexpr int NV4 = (CPT * SEG_BOXW / 4 + 31) / 32;
+        const V4<T> zero4{T(0), T(0), T(0), T(0)};
+        V4<T> xr[NV4], pr[NV4];
+#pragma unroll
+        for (int i = 0; i < NV4; ++i)
         {
-          T a0[DOT_B], a1[DOT_B];
+          const int j4 = 4 * (lane + 32 * i);
+          xr[i] = (part2 && j4 < n) ? ld4(x + j4) : zero4;
+          pr[i] = (part1 && j4 < n) ? ld4(phi + j4) : zero4;
+        }
+        auto two_rows = [&](const T* r0, const T* r1, const bool two, const V4<T> (&vec)[NV4], T& s0, T& s1) {
+          V4<T> a0[NV4], a1[NV4];
 #pragma unroll
-          for (int qd = 0; qd < DOT_B; ++qd)
+          for (int i = 0; i < NV4; ++i)
           {
-            const int j = jb + 32 * qd;
-            a0[qd]      = j < n ? r0[j] : T(0);
-            a1[qd]      = (two && j < n) ? r1[j] : T(0);
+            const int j4 = 4 * (lane + 32 * i);
+            a0[i] = j4 < n ? ld4(r0 + j4) : zero4;
+            a1[i] = (two && j4 < n) ? ld4(r1 + j4) : zero4;
           }
+          s0 = T(0), s1 = T(0);
 #pragma unroll
-          for (int qd = 0; qd < DOT_B; ++qd)
+          for (int i = 0; i < NV4; ++i)
           {
-            const int j = jb + 32 * qd;
-            if (j < n)
+            s0 += dot4(a0[i], vec[i]);
+            s1 += dot4(a1[i], vec[i]);
+          }
+          s0 = warp_sum(s0);
+          s1 = warp_sum(s1);
+        };
+        for (int u0 = warp; u0 < nU; u0 += 14)
+        {
+          const int u1   = u0 + 7;
+          const bool two = u1 < nU;
+          const T* r0    = u0 < cB ? Ub + (size_t)u0 * n : phi;
+          const T* r1    = two ? (u1 < cB ? Ub + (size_t)u1 * n : phi) : r0;
+          T s0, s1;
+          two_rows(r0, r1, two, xr, s0, s1);
+          if (lane == 0)
+          {
+            pB[u0] = s0;
+            if (two)
+              pB[u1] = s1;
+          }
+        }
+        if (cA > 0)
+        {
+          if (nvs > 0)
+            ptx::mbar_wait(v_bar, v_phase);
+          // (the warps take the V rows in reverse order of the U rows so that the work evens out)
+          for (int a0i = 6 - warp; a0i < cA; a0i += 14)
+          {
+            const int a1i  = a0i + 7;
+            const bool two = a1i < cA;
+            const T* r0    = a0i < nvs ? vs + (size_t)a0i * n : Va + (size_t)a0i * n;
+            const T* r1    = two ? (a1i < nvs ? vs + (size_t)a1i * n : Va + (size_t)a1i * n) : r0;
+            T s0, s1;
+            two_rows(r0, r1, two, pr, s0, s1);
+            if (lane == 0)
             {
-              s0 += a0[qd] * v0[j];
+              pA[a0i] = -s0;
               if (two)
-                s1 += a1[qd] * v1[j];
+                pA[a1i] = -s1;
             }
           }
         }
-        s0 = warp_sum(s0);
-        s1 = warp_sum(s1);
-        if (lane == 0)
+      }
+      else
+      {
+        // generic rows (length not a multiple of 16 bytes): scalar loads, everything from memory
+        const int ntask = cA + cB + nspec;
+        for (int t0 = warp; t0 < ntask; t0 += 14)
         {
-          if (t0 < nU)
-            pB[t0] = s0;
-          else
-            pA[t0 - nU] = -s0;
-          if (two)
-          {
-            if (t1 < nU)
-              pB[t1] = s1;
+          const int t1 = t0 + 7;
+          const T *r0, *v0, *r1, *v1;
+          auto pick = [&](int t, const T*& r, const T*& v) {
+            if (t < cB)
+              r = Ub + (size_t)t * n, v = x;
+            else if (t < nU)
+              r = phi, v = x;
             else
-              pA[t1 - nU] = -s1;
+              r = Va + (size_t)(t - nU) * n, v = phi;
+          };
+          pick(t0, r0, v0);
+          r1 = r0, v1 = v0;
+          const bool two = t1 < ntask;
+          if (two)
+            pick(t1, r1, v1);
+          T s0(0), s1(0);
+          for (int j = lane; j < n; j += 32)
+          {
+            s0 += r0[j] * v0[j];
+            if (two)
+              s1 += r1[j] * v1[j];
+          }
+          s0 = warp_sum(s0);
+          s1 = warp_sum(s1);
+          if (lane == 0)
+          {
+            if (t0 < nU)
+              pB[t0] = s0;
+            else
+              pA[t0 - nU] = -s0;
+            if (two)
+            {
+              if (t1 < nU)
+                pB[t1] = s1;
+              else
+                pA[t1 - nU] = -s1;
+            }
           }
         }
       }
@@ -794,58 +869,60 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         }
         gd.sync();
         // x += V^T w : the staged rows from shared memory, rows beyond the staging capacity from L2, the row appended
-        // by this move from vrow
+        // by this move from vrow; then the gradient dots with the staged gradient rows
         const T* Vm = D.V + (size_t)iw * k * n;
         T acc3[3]   = {T(0), T(0), T(0)};
-        constexpr int XC = sizeof(T) > 4 ? 2 : 3;
         if (nvs > 0)
           ptx::mbar_wait(v_bar, v_phase); // (warps that read no V row in the staging phase have not observed it yet)
         const int cS = cB < nvs ? cB : nvs;
-        for (int jb = tid; jb < n; jb += XC * gd.n)
+        if (v_bulk)
         {
-          T sacc[XC];
-#pragma unroll
-          for (int qx = 0; qx < XC; ++qx)
-            sacc[qx] = T(0);
+          // four consecutive columns per thread, 16-byte accesses
+          for (int j4 = 4 * tid; j4 < n; j4 += 4 * gd.n)
+          {
+            V4<T> sacc{T(0), T(0), T(0), T(0)};
 #pragma unroll 4
-          for (int a = 0; a < cS; ++a)
-          {
-            const T wa = w[a];
-#pragma unroll
-            for (int qx = 0; qx < XC; ++qx)
+            for (int a = 0; a < cS; ++a)
             {
-              const int j = jb + qx * gd.n;
-              if (j < n)
-                sacc[qx] += vs[(size_t)a * n + j] * wa;
+              const T wa    = w[a];
+              const V4<T> v = ld4(vs + (size_t)a * n + j4);
+              sacc.x += v.x * wa, sacc.y += v.y * wa, sacc.z += v.z * wa, sacc.w += v.w * wa;
             }
-          }
 #pragma unroll 4
-          for (int a = cS; a < cB; ++a)
-          {
-            const T wa = w[a];
-#pragma unroll
-            for (int qx = 0; qx < XC; ++qx)
+            for (int a = cS; a < cB; ++a)
             {
-              const int j = jb + qx * gd.n;
-              if (j < n)
-                sacc[qx] += Vm[(size_t)a * n + j] * wa;
+              const T wa    = w[a];
+              const V4<T> v = ld4(Vm + (size_t)a * n + j4);
+              sacc.x += v.x * wa, sacc.y += v.y * wa, sacc.z += v.z * wa, sacc.w += v.w * wa;
             }
+            if (part1)
+            {
+              const T wc     = w[c];
+              const V4<T> vr = ld4(vrow + j4);
+              sacc.x += vr.x * wc, sacc.y += vr.y * wc, sacc.z += vr.z * wc, sacc.w += vr.w * wc;
+            }
+            const V4<T> x0 = ld4(x + j4);
+            const V4<T> xv{x0.x + sacc.x, x0.y + sacc.y, x0.z + sacc.z, x0.w + sacc.w};
+            x[j4] = xv.x, x[j4 + 1] = xv.y, x[j4 + 2] = xv.z, x[j4 + 3] = xv.w;
+            acc3[0] += dot4(xv, ld4(glrow + j4));
+            acc3[1] += dot4(xv, ld4(glrow + n + j4));
+            acc3[2] += dot4(xv, ld4(glrow + 2 * n + j4));
           }
-#pragma unroll
-          for (int qx = 0; qx < XC; ++qx)
+        }
+        else
+        {
+          for (int j = tid; j < n; j += gd.n)
           {
-            const int j = jb + qx * gd.n;
-            if (j < n)
-            {
-              T sq = sacc[qx];
-              if (part1)
-                sq += vrow[j] * w[c];
-              const T xv = x[j] + sq;
-              x[j]       = xv;
-              acc3[0] += xv * glrow[j];
-              acc3[1] += xv * glrow[n + j];
-              acc3[2] += xv * glrow[2 * n + j];
-            }
+            T sq(0);
+            for (int a = 0; a < cB; ++a)
+              sq += Vm[(size_t)a * n + j] * w[a];
+            if (part1)
+              sq += vrow[j] * w[c];
+            const T xv = x[j] + sq;
+            x[j]       = xv;
+            acc3[0] += xv * glrow[j];
+            acc3[1] += xv * glrow[n + j];
+            acc3[2] += xv * glrow[2 * n + j];
           }
         }
         group_sum<T, 3>(gd, acc3, red);
@@ -873,6 +950,34 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
     }
     if (tid < cF)
       D.wvec[(size_t)iw * k + tid] = w[tid];
+  }
+  // U'[a][j] = sum_b Binv[a][b] V[b][j] for the flush that follows (DelayedUpdateBatched.h:716-722, the second of the
+  // three products): the core is in shared memory here and the rows of V are L2-hot, so the flush kernel finds U' ready
+  // in memory instead of every one of its CTAs re-deriving it.  Thread -> (column j, sixteen slots a).
+  {
+    const T* Vg = D.V + (size_t)iw * k * n;
+    T* Upg      = D.Up + (size_t)iw * k * n;
+    const int nh = (cF + 15) / 16;
+    for (int item = tid; item < n * nh; item += SEG_TPB)
+    {
+      const int h = item / n, j = item - h * n, a0 = 16 * h;
+      T acc[16];
+#pragma unroll
+      for (int a = 0; a < 16; ++a)
+        acc[a] = T(0);
+      for (int b = 0; b < cF; ++b)
+      {
+        const T v = Vg[(size_t)b * n + j];
+#pragma unroll
+        for (int a = 0; a < 16; ++a)
+          if (a0 + a < cF)
+            acc[a] += Bs[(a0 + a) * kb + b] * v;
+      }
+#pragma unroll
+      for (int a = 0; a < 16; ++a)
+        if (a0 + a < cF)
+          Upg[(size_t)(a0 + a) * n + j] = acc[a];
+    }
   }
 }
 #endif // __CUDACC__

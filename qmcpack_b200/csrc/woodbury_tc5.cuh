@@ -119,7 +119,8 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo)
 // grid = (ceil(n / 128), nw); c <= 32 pending delays; n % 64 == 0.  Two CTAs per SM (85 KB of shared memory, 256 of the
 // 512 TMEM columns and <= 128 registers each): the phases of one CTA are chains of memory latencies, the second CTA on
 // the SM fills them.
-__global__ void __launch_bounds__(TPB, 2) woodbury_flush_tc5_kernel(const DetDev<float> D, const int c)
+// up_ready: D.Up already holds U' = Binv V (left there by the walker-segment kernel, segment.cuh)
+__global__ void __launch_bounds__(TPB, 2) woodbury_flush_tc5_kernel(const DetDev<float> D, const int c, const int up_ready)
 {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(16) float BinvT[KD][KD + 4]; // BinvT[b][a] = Binv[a][b] (float4 reads over a)
@@ -286,7 +287,25 @@ __global__ void __launch_bounds__(TPB, 2) woodbury_flush_tc5_kernel(const DetDev
     // U'[a][j] = sum_b Binv[a][b] V[b][j]: thread -> column jj = tid % 128, slots 16 (tid / 128) .. +15
     {
       const int jj = tid & 127, a0 = (tid >> 7) * 16;
-      if (jj < np)
+      if (jj < np && up_ready)
+      {
+        // U' comes from memory: sixteen coalesced loads per thread, split, stored as the B operand
+        const float* Up = D.Up + (size_t)iw * k * n + j0 + jj;
+        float acc[16];
+#pragma unroll
+        for (int a = 0; a < 16; ++a)
+          acc[a] = a0 + a < c ? __ldg(Up + (size_t)(a0 + a) * n) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+          float4 hi, lo;
+          split4(make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]), hi, lo);
+          const int off = jj * KC + ((((a0 >> 2) + q) ^ (jj & 7)) << 2);
+          *reinterpret_cast<float4*>(Bp_hi + off) = hi;
+          *reinterpret_cast<float4*>(Bp_lo + off) = lo;
+        }
+      }
+      else if (jj < np)
       {
         float vv[KD]; // the whole column of V in flight at once
 #pragma unroll
