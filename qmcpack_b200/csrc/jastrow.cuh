@@ -345,13 +345,15 @@ __device__ __forceinline__ void jastrow_move_warps(const int wg, const int nwarp
   const int iters  = (n2 + n1 + STEP - 1) / STEP;
   unsigned short* seg = jl + wg * iters * 32;
   int cnt = 0;
-  // pass 1: every distance; the loads of two iterations are in flight together
-  for (int it = 0; it < iters; it += 2)
+  // pass 1: every distance; the position loads of up to JB iterations are requested before the first is used (one
+  // memory round trip per JB * 32 nwarps candidates)
+  constexpr int JB = 3;
+  for (int it = 0; it < iters; it += JB)
   {
-    int idx[2];
-    RT px[2], py[2], pz[2];
+    int idx[JB];
+    RT px[JB], py[JB], pz[JB];
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+    for (int h = 0; h < JB; ++h)
     {
       idx[h] = (it + h < iters) ? (it + h) * STEP + tid : n2 + n1;
       px[h] = py[h] = pz[h] = RT(0);
@@ -364,7 +366,7 @@ __device__ __forceinline__ void jastrow_move_warps(const int wg, const int nwarp
       }
     }
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+    for (int h = 0; h < JB; ++h)
     {
       if (it + h >= iters)
         break;
@@ -494,23 +496,39 @@ __device__ __forceinline__ void jastrow_accept_body(const Group& g, const Jastro
       // pass 1: pairs whose old OR new distance is inside the cutoff (the others add exact zeros to every sum)
       unsigned short* seg = jl + wg * segcap;
       int cnt = 0;
-      for (int it = 0; it < iters; ++it)
+      // (the position loads of up to three iterations are requested before the first is used)
+      constexpr int JB = 3;
+      for (int it0 = 0; it0 < iters; it0 += JB)
       {
-        const int j = it * g.n + tid;
-        bool need   = false;
-        if (j < N && j != iat)
+        RT px[JB], py[JB], pz[JB];
+#pragma unroll
+        for (int h = 0; h < JB; ++h)
         {
-          const RT px = rs[j], py = rs[np + j], pz = rs[2 * np + j];
-          RT rn, ro, t0, t1, t2;
-          min_image(J.cell, pnew, px, py, pz, j, iat, rn, t0, t1, t2);
-          min_image(J.cell, pold, px, py, pz, j, iat, ro, t0, t1, t2);
-          const FunctorDev<RT>& F = J.F2[gi + (j < J.n_up ? 0 : 1)];
-          need                    = F.coefs != nullptr && (rn < F.rcut || ro < F.rcut);
+          const int j = (it0 + h) * g.n + tid;
+          px[h] = py[h] = pz[h] = RT(0);
+          if (it0 + h < iters && j < N)
+            px[h] = rs[j], py[h] = rs[np + j], pz[h] = rs[2 * np + j];
         }
-        const unsigned m = __ballot_sync(0xffffffffu, need);
-        if (need)
-          seg[cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
-        cnt += __popc(m);
+#pragma unroll
+        for (int h = 0; h < JB; ++h)
+        {
+          if (it0 + h >= iters)
+            break;
+          const int j = (it0 + h) * g.n + tid;
+          bool need   = false;
+          if (j < N && j != iat)
+          {
+            RT rn, ro, t0, t1, t2;
+            min_image(J.cell, pnew, px[h], py[h], pz[h], j, iat, rn, t0, t1, t2);
+            min_image(J.cell, pold, px[h], py[h], pz[h], j, iat, ro, t0, t1, t2);
+            const FunctorDev<RT>& F = J.F2[gi + (j < J.n_up ? 0 : 1)];
+            need                    = F.coefs != nullptr && (rn < F.rcut || ro < F.rcut);
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, need);
+          if (need)
+            seg[cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
+          cnt += __popc(m);
+        }
       }
       __syncwarp();
       // pass 2: full warps over the list

@@ -55,7 +55,7 @@ struct SegRng
 
 struct SegLayout
 {
-  unsigned ring, phi, x, Bs, vec, red, rgp, sg, hdr, bars, jred, jsum, jl, total;
+  unsigned ring, phi, x, Bs, vec, red, rgp, sg, hdr, bars, jred, jsum, tim, jl, total;
   int jl_entries;
 };
 
@@ -78,6 +78,7 @@ __host__ __device__ inline SegLayout seg_layout(int n, int k, int N, int nions)
   L.bars = o, o += 64;
   L.jred = o, o += 96 * (unsigned)sizeof(T); // per-consumer-warp partials of the ten Jastrow sums [6][16]
   L.jsum = o, o += 16 * (unsigned)sizeof(T); // the sums of the move being decided
+  L.tim = o = up(o, 16), o += 192 + 16;      // cycle stamps of the timing build; the last 16 bytes: log|det|, phase
   L.jl_entries = (int)up((unsigned)(N + nions + 256), 32);
   L.jl = o, o += up(2u * (unsigned)L.jl_entries, 16);
   L.total = o;
@@ -85,6 +86,24 @@ __host__ __device__ inline SegLayout seg_layout(int n, int k, int N, int nions)
 }
 
 #ifdef __CUDACC__
+// per-phase cycle stamps of the walker-segment kernel (debug builds only: scripts/build_variant.sh -DQMCB_SEG_TIMING)
+#ifdef QMCB_SEG_TIMING
+#define SEG_STAMP(slot, who)                                             \
+  do                                                                     \
+  {                                                                      \
+    if (threadIdx.x == (who))                                            \
+    {                                                                    \
+      const long long now__ = clock64();                                 \
+      seg_tim[slot] += now__ - seg_tim[16 + ((who) >> 5)];               \
+      seg_tim[16 + ((who) >> 5)] = now__;                                \
+    }                                                                    \
+  } while (0)
+#else
+#define SEG_STAMP(slot, who) \
+  do                         \
+  {                          \
+  } while (0)
+#endif
 namespace ptx
 {
 __device__ __forceinline__ void fence_proxy_async()
@@ -372,6 +391,16 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
   T* jsum             = reinterpret_cast<T*>(smem_raw + L.jsum);
   unsigned short* jl  = reinterpret_cast<unsigned short*>(smem_raw + L.jl);
   SegMetroPre<T> mpre; // (warp 7)
+  // log-determinant increments of the accepted moves: summed here, added to memory once at the end of the segment (a
+  // read-modify-write of global memory per accept would put a memory round trip into the accept's critical path)
+  double* ld_acc = reinterpret_cast<double*>(smem_raw + L.tim + 192);
+  if (tid < 2)
+    ld_acc[tid] = 0.0;
+#ifdef QMCB_SEG_TIMING
+  long long* seg_tim = reinterpret_cast<long long*>(smem_raw + L.tim); // [0,16): cycles per stamp, [16,24): last stamp per warp
+  if (threadIdx.x < 24)
+    seg_tim[threadIdx.x] = threadIdx.x < 16 ? 0 : clock64();
+#endif
 
   if (tid == 0)
   {
@@ -414,7 +443,9 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         {
           T np3[3];
           seg_propose<T, false>(Dr, J, iw, iat, sg, np3);
+          SEG_STAMP(0, 0); // barrier wake-up + proposal
           jastrow_move_warps<T>(warp, SEG_NCONS / 32, J, iw, iat, np3, jl, jred + warp * 16);
+          SEG_STAMP(1, 0); // Jastrow sums
         }
         T cz[4], dcz[4], d2cz[4];
 #pragma unroll
@@ -467,6 +498,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           if (lane == 0)
             ptx::mbar_arrive(&empty_bar[stage]);
         }
+        SEG_STAMP(2, 0); // eight slabs
         // epilogue: lattice units -> Cartesian, sign, rows into shared memory, dots with the inverse row
         const int bc_sign = *reinterpret_cast<const int*>(hdr + SPL_HDR_SGN);
         const T sgn   = (bc_sign & 1) ? T(-1) : T(1);
@@ -576,11 +608,31 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
       }
       else
       {
-        // ---- warp 7: everything the Metropolis test needs from memory, fetched under the gather
+        // ---- warp 7: everything the Metropolis test needs from memory, fetched under the gather; and the rows the NEXT
+        // move's preparation reads for the first time since the last flush (the stale inverse row, the gradient rows of
+        // that electron, its Gaussians) are pulled into L2 now -- their addresses are known a whole move ahead, and a
+        // cold DRAM access inside the boundary chain costs microseconds while the stencil stream keeps HBM busy
+        if (part2)
+        {
+          const char* ar = reinterpret_cast<const char*>(D.Ainv + ((size_t)iw * n + row + 1) * D.lda);
+          const char* gr = reinterpret_cast<const char*>(D.GL + ((size_t)iw * n + row + 1) * 4 * n);
+          const int la = (int)(((size_t)n * sizeof(T) + 127) / 128), lg = (int)(((size_t)3 * n * sizeof(T) + 127) / 128);
+          for (int l = lane; l < la + lg; l += 32)
+          {
+            const char* pf = l < la ? ar + (size_t)l * 128 : gr + (size_t)(l - la) * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+          }
+          if (lane == 0)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Dr.deltas + ((size_t)(iat + 1) * Dr.nw + iw) * 3));
+        }
         mpre = seg_metro_prefetch<T>(Dr, J, R, SR, iw, iat, sg);
+        SEG_STAMP(8, 224); // Metropolis prefetch incl. the wait for the previous move's total
       }
       gq += SEG_NQ;
-      __syncthreads(); // B1: orbital rows and partial dots in shared memory, Jastrow sums and the proposal in memory
+      SEG_STAMP(3, 0); // epilogue
+      __syncthreads(); // B1
+      SEG_STAMP(4, 0);   // wait at B1
+      SEG_STAMP(9, 224); // wait at B1 (Metropolis warp): orbital rows and partial dots in shared memory, Jastrow sums and the proposal in memory
     }
 
     // ======================= Metropolis test (warp 7) || accept-independent staging and dots (warps 0-6) =======================
@@ -626,6 +678,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           s_acc   = acc ? 1 : 0;
           s_ratio = rdet;
         }
+        SEG_STAMP(10, 224); // Metropolis test
       }
     }
     else
@@ -662,6 +715,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         }
       }
       ga.sync();
+      SEG_STAMP(5, 0); // staging of the next row
       const T* Va     = D.V + (size_t)iw * k * n;
       const T* Ub     = D.U + (size_t)iw * k * n;
       const int nspec = (part1 && part2) ? 1 : 0; // phi.x for the slot this move may append
@@ -784,7 +838,10 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         }
       }
     }
+    SEG_STAMP(6, 0); // dots
     __syncthreads(); // B2
+    SEG_STAMP(7, 0);    // wait at B2
+    SEG_STAMP(11, 224); // wait at B2 (Metropolis warp)
 
     // ======================= determinant accept + next row (threads 0-127) || Jastrow accept (threads 128-255) =======================
     if (tid < SEG_TPB / 2)
@@ -835,7 +892,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           {
             Bs[c * kb + c]             = sigma;
             D.list[(size_t)iw * k + c] = row;
-            logdet_accumulate(D.logdet + 2 * (size_t)iw, s_ratio); // log_value += log(curRatio)
+            logdet_accumulate(ld_acc, s_ratio); // log_value += log(curRatio)
           }
         }
         else
@@ -931,14 +988,27 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
       }
       // the ring region (vrow, glrow) goes back to the TMA engine
       ptx::fence_proxy_async();
+      SEG_STAMP(12, 0); // determinant accept + next row
     }
     else if (part1 && s_acc != 0)
       jastrow_accept_body<T>(Group{tid - SEG_TPB / 2, SEG_TPB / 2, 2}, J, iw, iat, jl);
+    SEG_STAMP(13, 224); // Jastrow accept
     if (nvs > 0)
       v_phase ^= 1u;
     __syncthreads(); // B3
+    SEG_STAMP(14, 0);   // wait at B3 (determinant group)
+    SEG_STAMP(15, 224); // wait at B3 (Jastrow group)
   }
 
+#ifdef QMCB_SEG_TIMING
+  if (tid == 0 && (iw % 97) == 0 && iat0 == 32)
+    printf("seg_timing iw %d moves %d | propose %lld Jsums %lld slabs %lld epi %lld waitB1 %lld stage %lld dots %lld waitB2 %lld "
+           "detacc+prep %lld waitB3 %lld || w7: prefetch %lld waitB1 %lld metro %lld waitB2 %lld Jacc %lld waitB3 %lld\n",
+           iw, nmoves, seg_tim[0] / nmoves, seg_tim[1] / nmoves, seg_tim[2] / nmoves, seg_tim[3] / nmoves, seg_tim[4] / nmoves,
+           seg_tim[5] / nmoves, seg_tim[6] / nmoves, seg_tim[7] / nmoves, seg_tim[12] / nmoves, seg_tim[14] / nmoves,
+           seg_tim[8] / nmoves, seg_tim[9] / nmoves, seg_tim[10] / nmoves, seg_tim[11] / nmoves, seg_tim[13] / nmoves,
+           seg_tim[15] / nmoves);
+#endif
   // the flush (and any later API call) finds the core and w in memory
   const int cF = c0 + nmoves;
   {
@@ -950,6 +1020,8 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
     }
     if (tid < cF)
       D.wvec[(size_t)iw * k + tid] = w[tid];
+    if (tid < 2)
+      D.logdet[2 * (size_t)iw + tid] += ld_acc[tid];
   }
   // U'[a][j] = sum_b Binv[a][b] V[b][j] for the flush that follows (DelayedUpdateBatched.h:716-722, the second of the
   // three products): the core is in shared memory here and the rows of V are L2-hot, so the flush kernel finds U' ready
