@@ -205,6 +205,12 @@ int qmcb_vmc_counts(qmcb_crowd* c, long long* n_accept, long long* n_reject);
 /* 2 when the sweeps of this crowd run on the persistent walker-segment kernel, 1 on the two-kernel path, 0 before
  * qmcb_vmc_init                                                                                                          */
 int qmcb_vmc_sweep_kernel(qmcb_crowd* c);
+/* how the per-electron calls (qmcb_twf_mw_eval_grad / qmcb_ps_mw_make_move / qmcb_twf_mw_calc_ratio_grad /
+ * qmcb_twf_mw_accept_reject) of this crowd are served: 2 = by a resident walker-segment kernel through host mailboxes
+ * (one launch per segment of <= delay_rank moves; engaged when the calls arrive in the driver loop's order, real
+ * orbitals, <= 384 per spin; environment QMCB_HOST_KERNEL=launch disables it), 1 = one or two launches per call,
+ * 0 = no per-electron call has been made yet.  Both give the same results.                                              */
+int qmcb_crowd_host_kernel(qmcb_crowd* c);
 /* measurement hook: one sweep outside the CUDA graph with an event pair around every launch.  out9[0] = sweep time (us);
  * out9[1..4] = summed time of the walker-segment kernel, the boundary kernel, the spline gather and the Woodbury flush;
  * out9[5..8] = their launch counts.                                                                                     */

@@ -61,7 +61,7 @@ SYMBOLS = [
     "qmcb_det_mw_complete_updates", "qmcb_det_mw_recompute_from_matrices", "qmcb_det_set_phi_vgl",
     "qmcb_det_mw_ratio_grad_from_phi", "qmcb_det_delay_count", "qmcb_det_time_update_inv_mat",
     "qmcb_dtaa_get_temp_rows", "qmcb_j2_mw_ratio_grad", "qmcb_j2_mw_accept_reject", "qmcb_j2_get_state",
-    "qmcb_vmc_init", "qmcb_vmc_sweep", "qmcb_vmc_sweep_async", "qmcb_vmc_counts", "qmcb_vmc_sweep_kernel", "qmcb_vmc_profile_sweep", "qmcb_crowd_stream",
+    "qmcb_vmc_init", "qmcb_vmc_sweep", "qmcb_vmc_sweep_async", "qmcb_vmc_counts", "qmcb_vmc_sweep_kernel", "qmcb_vmc_profile_sweep", "qmcb_crowd_host_kernel", "qmcb_crowd_stream",
     "qmcb_dmc_get_rr", "qmcb_crowd_walker_bytes", "qmcb_crowd_pack_walker", "qmcb_crowd_unpack_walker",
     "qmcb_crowd_copy_walker", "qmcb_crowd_set_num_walkers", "qmcb_crowd_num_walkers", "qmcb_crowd_capacity",
 ]
@@ -409,6 +409,11 @@ class Crowd:
         sweep_kernel: 0 automatic, 1 two-kernel path, 2 persistent walker-segment kernel (error if not eligible)"""
         p = QmcbVmcParams(tau, int(use_drift), seed, int(use_cuda_graph), int(dmc), int(sweep_kernel))
         _chk(lib().qmcb_vmc_init(self.h, C.byref(p)))
+
+    @property
+    def host_kernel(self):
+        """2: per-electron calls served by a resident walker-segment kernel (mailboxes), 1: launches per call, 0: none yet"""
+        return int(lib().qmcb_crowd_host_kernel(self.h))
 
     def vmc_profile_sweep(self):
         """one sweep with an event pair around every launch: dict of sweep time and per-kernel sums (us) and launch counts"""

@@ -374,6 +374,7 @@ int qmcb_vmc_sweep(qmcb_crowd* c, int nsteps, uint8_t* log) { CROWD_CALL(vmc_swe
 int qmcb_vmc_sweep_async(qmcb_crowd* c) { CROWD_CALL(vmc_sweep_async()); }
 int qmcb_vmc_counts(qmcb_crowd* c, long long* a, long long* r) { CROWD_CALL(vmc_counts(a, r)); }
 int qmcb_vmc_sweep_kernel(qmcb_crowd* c) { return (c && c->impl) ? c->impl->vmc_sweep_kernel() : 0; }
+int qmcb_crowd_host_kernel(qmcb_crowd* c) { return (c && c->impl) ? c->impl->host_kernel() : 0; }
 int qmcb_vmc_profile_sweep(qmcb_crowd* c, double* out9) { CROWD_CALL(vmc_profile_sweep(out9)); }
 int qmcb_dmc_get_rr(qmcb_crowd* c, double* a, double* p) { CROWD_CALL(dmc_get_rr(a, p)); }
 size_t qmcb_crowd_walker_bytes(const qmcb_crowd* c) { return c ? c->impl->walker_bytes() : 0; }

@@ -1012,6 +1012,13 @@ struct Crowd : CrowdBase
 
   ~Crowd() override
   {
+    try
+    {
+      hd_abort();
+    }
+    catch (...)
+    {
+    }
     release_segment_slots();
     if (graph_exec)
       cudaGraphExecDestroy(graph_exec);
@@ -1141,7 +1148,11 @@ struct Crowd : CrowdBase
   }
 
   cudaStream_t stream() override { return st; }
-  void sync() override { QMCB_CUDA(cudaStreamSynchronize(st)); }
+  void sync() override
+  {
+    hd_abort(); // (a resident kernel waiting for the host would never let the stream drain)
+    QMCB_CUDA(cudaStreamSynchronize(st));
+  }
   // host-driven move loop: two device round trips per move, so the wake-up latency of a blocking synchronize matters;
   // poll the stream instead (one host thread per crowd, VMCBatched.cpp:348)
   // Polling with cudaStreamQuery takes the driver's context lock on every call: with one polling thread per crowd the
@@ -1494,7 +1505,12 @@ struct Crowd : CrowdBase
       QMCB_CUDA(cudaMemcpyAsync(logdet_h, logdet[spin].p, (size_t)nw * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     sync();
   }
-  int det_delay_count(int spin) override { return delay_count[spin]; }
+  int det_delay_count(int spin) override
+  {
+    if (hd.active && spin == hd.spin)
+      return hd.c0 + (hd.iat - hd.iat0); // (moves the resident kernel has been told to apply)
+    return delay_count[spin];
+  }
   // measurement hook: `reps` back-to-back mw_updateInvMat launches with `c` pending slots, CUDA events on the crowd stream.
   // The delay buffers hold whatever the last moves left there, so the flushes are arithmetic on stale data: the inverse
   // is saved before and restored afterwards and the crowd is left exactly as a qmcb_twf_mw_complete_updates call leaves it.
@@ -1648,6 +1664,8 @@ struct Crowd : CrowdBase
   void twf_eval_grad(int iat, double* grads) override
   {
     check_iat(iat);
+    if (hd_eval_grad(iat, grads))
+      return;
     // [accept of the previous electron, if one is pending] + inverse row + component-summed gradient: one launch
     join_jastrow();
     // the kernel stores the gradients straight into the pinned host buffer (unified addressing: pinned allocations are
@@ -1667,6 +1685,8 @@ struct Crowd : CrowdBase
   void ps_make_move(int iat, const double* dsp) override
   {
     check_iat(iat);
+    if (hd.active && hd_make_move(iat, dsp)) // (a resident kernel is started by mw_evalGrad; loops without drift launch per call)
+      return;
     flush_pending();
     T* h = reinterpret_cast<T*>(h_t.p + 4 * (size_t)nw); // second half of the staging buffer
     for (int i = 0; i < 3 * nw; ++i)
@@ -1707,6 +1727,8 @@ struct Crowd : CrowdBase
   void twf_calc_ratio_grad(int iat, double* ratios, double* grads) override
   {
     check_iat(iat);
+    if (hd_calc_ratio_grad(iat, ratios, grads))
+      return;
     apply_pending(-1, nullptr); // (make_move already applied it; the Jastrow rows keep running beside the gather below)
     const int spin = spin_of(iat), row = iat - first[spin];
     ensure_row(spin, row);
@@ -1722,6 +1744,8 @@ struct Crowd : CrowdBase
   void twf_accept_reject(int iat, const uint8_t* acc, int safe_to_delay) override
   {
     check_iat(iat);
+    if (hd_accept_reject(iat, acc, safe_to_delay))
+      return;
     flush_pending();
     stage_flags(acc);
     // deferred: applied together with whatever the driver asks next (normally the gradient of the next electron);
@@ -1898,6 +1922,7 @@ struct Crowd : CrowdBase
     rng.state = rng_state.p, rng.ring = rng_ring.p, rng.gen = rng_cnt.p, rng.pos = rng_cnt.p + 1;
     rng.sweep = rng_flags.p + cap, rng.flags = rng_flags.p;
     rng.ring_mask = (unsigned)(ring - 1);
+    hd_abort();
     setup_segment_kernel(p->sweep_kernel);
     mt19937_seed_kernel<<<1, 32, 0, st>>>(rng, p->seed);
     QMCB_LAUNCH_CHECK();
@@ -1981,8 +2006,10 @@ struct Crowd : CrowdBase
       SegBudget::release(device, seg_reserved_sms);
     seg_reserved_sms = 0;
     fused            = false;
+    hd.enabled       = false;
+    hd.tried         = false;
   }
-  template<int CPT>
+  template<int CPT, bool HD>
   int segment_occupancy(int spin, size_t& smem)
   {
     if constexpr (std::is_same<T, V>::value)
@@ -1991,13 +2018,50 @@ struct Crowd : CrowdBase
       smem              = L.total;
       if (smem > 227 * 1024)
         return 0;
-      ensure_dynamic_smem(walker_segment_kernel<T, CPT>, smem);
+      ensure_dynamic_smem(walker_segment_kernel<T, CPT, HD>, smem);
       int occ = 0;
-      QMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walker_segment_kernel<T, CPT>, SEG_TPB, smem));
+      QMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walker_segment_kernel<T, CPT, HD>, SEG_TPB, smem));
       return occ;
     }
     else
       return 0;
+  }
+  // can this crowd run the walker-segment kernel (device-driven, and host-driven when `host_mode`), with every CTA
+  // resident?  Reserves the SM share once per crowd.  Returns "" or the reason why not.
+  std::string acquire_segment_kernel(bool host_mode)
+  {
+    std::string why;
+    if (!std::is_same<T, V>::value)
+      why = "complex orbitals";
+    else if (nmax > 2 * SEG_BOXW)
+      why = "more than 384 orbitals per spin";
+    else if (N + (jas.has_j1 ? jas.nions : 0) + 256 > 65535)
+      why = "too many particles for the 16-bit cutoff lists";
+    int occ = 1 << 30;
+    if (why.empty())
+      for (int spin = 0; spin < 2; ++spin)
+        if (nel[spin] > 0)
+        {
+          size_t smem = 0;
+          int o       = nel[spin] <= SEG_BOXW ? segment_occupancy<1, false>(spin, smem) : segment_occupancy<2, false>(spin, smem);
+          if (host_mode)
+            o = std::min(o, nel[spin] <= SEG_BOXW ? segment_occupancy<1, true>(spin, smem) : segment_occupancy<2, true>(spin, smem));
+          occ = std::min(occ, o);
+        }
+    if (why.empty() && occ <= 0)
+      why = "the walker's working set does not fit in shared memory";
+    if (why.empty() && seg_reserved_sms <= 0)
+    {
+      int sms = 0;
+      QMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+      const double want = (double)cap / (double)occ;
+      if (SegBudget::reserve(device, want, sms))
+        seg_reserved_sms = want;
+      else
+        why = "not every walker's CTA can be resident at once (" + std::to_string(cap) + " walkers, " + std::to_string(occ) +
+            " CTAs per SM, " + std::to_string(sms) + " SMs shared with the other crowds of this device)";
+    }
+    return why;
   }
   // mode: qmcb_vmc_params.sweep_kernel (0 automatic, 1 two-kernel path, 2 segment kernel required)
   void setup_segment_kernel(int mode)
@@ -2010,35 +2074,7 @@ struct Crowd : CrowdBase
     }
     if (mode == 1)
       return;
-    std::string why;
-    if (!std::is_same<T, V>::value)
-      why = "complex orbitals";
-    else if (nmax > 2 * SEG_BOXW)
-      why = "more than 384 orbitals per spin";
-    else if (N + (jas.has_j1 ? jas.nions : 0) + 128 > 65535)
-      why = "too many particles for the 16-bit cutoff lists";
-    int occ = 1 << 30;
-    if (why.empty())
-      for (int spin = 0; spin < 2; ++spin)
-        if (nel[spin] > 0)
-        {
-          size_t smem = 0;
-          const int o = nel[spin] <= SEG_BOXW ? segment_occupancy<1>(spin, smem) : segment_occupancy<2>(spin, smem);
-          occ         = std::min(occ, o);
-        }
-    if (why.empty() && occ <= 0)
-      why = "the walker's working set does not fit in shared memory";
-    if (why.empty())
-    {
-      int sms = 0;
-      QMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-      const double want = (double)cap / (double)occ;
-      if (SegBudget::reserve(device, want, sms))
-        seg_reserved_sms = want;
-      else
-        why = "not every walker's CTA can be resident at once (" + std::to_string(cap) + " walkers, " + std::to_string(occ) +
-            " CTAs per SM, " + std::to_string(sms) + " SMs shared with the other crowds of this device)";
-    }
+    const std::string why = acquire_segment_kernel(false);
     if (!why.empty())
     {
       if (mode == 2)
@@ -2052,6 +2088,7 @@ struct Crowd : CrowdBase
     segrng.flags = seg_flags.p, segrng.tot_val = seg_tot_val.p, segrng.tot_tag = seg_tot_tag.p, segrng.stride = cap;
   }
   int vmc_sweep_kernel() const override { return vmc_ready ? (fused ? 2 : 1) : 0; }
+  int host_kernel() const override { return hd.tried ? (hd.enabled ? 2 : 1) : 0; }
   // moves e0 .. e0 + nm - 1 of determinant `spin` in ONE launch (no flush inside: delay_count + nm <= k)
   void launch_segment(int spin, int e0, int nm)
   {
@@ -2062,17 +2099,18 @@ struct Crowd : CrowdBase
         throw std::runtime_error("launch_segment: the segment crosses a flush or the end of the determinant");
       const SplineDev<T>& S  = *static_cast<const SplineDev<T>*>(spo[spin]->dev_desc());
       const CUtensorMap& tm = *static_cast<const CUtensorMap*>(spo[spin]->seg_tensor_map());
+      const SegHost<T> noH{};
       if (D.n <= SEG_BOXW)
       {
         const SegLayout L = seg_layout<T, 1>(D.n, k, N, jas.has_j1 ? jas.nions : 0);
-        walker_segment_kernel<T, 1><<<nw, SEG_TPB, L.total, st>>>(tm, S, drv, jas, rng, segrng, D, first[spin] + e0, e0, nm,
-                                                                    delay_count[spin]);
+        walker_segment_kernel<T, 1, false><<<nw, SEG_TPB, L.total, st>>>(tm, S, drv, jas, rng, segrng, D, first[spin] + e0, e0, nm,
+                                                                           delay_count[spin], noH);
       }
       else
       {
         const SegLayout L = seg_layout<T, 2>(D.n, k, N, jas.has_j1 ? jas.nions : 0);
-        walker_segment_kernel<T, 2><<<nw, SEG_TPB, L.total, st>>>(tm, S, drv, jas, rng, segrng, D, first[spin] + e0, e0, nm,
-                                                                    delay_count[spin]);
+        walker_segment_kernel<T, 2, false><<<nw, SEG_TPB, L.total, st>>>(tm, S, drv, jas, rng, segrng, D, first[spin] + e0, e0, nm,
+                                                                           delay_count[spin], noH);
       }
       QMCB_LAUNCH_CHECK();
       delay_count[spin] += nm;
@@ -2080,6 +2118,248 @@ struct Crowd : CrowdBase
     }
     else
       throw std::runtime_error("launch_segment: real orbitals only");
+  }
+
+  // ---------------------------------------------------------------- host-driven persistent segment (mailboxes, segment.cuh)
+  // The per-electron calls of the reference's driver loop (mw_evalGrad, mw_makeMove, mw_calcRatioGrad,
+  // mw_accept_rejectMove) normally cost one or two kernel launches and a stream round trip each.  When the calls arrive in
+  // the loop's order, ONE resident kernel serves a whole segment (the moves up to the next flush) and every call becomes
+  // a mailbox exchange in pinned host memory.  Any other call aborts the kernel and continues on the launch-per-call path.
+  struct HostDrive
+  {
+    bool enabled = false, tried = false, active = false, grad_seen = false;
+    PinBuf<unsigned char> pin;
+    DevBuf<unsigned char> dev;
+    SegHost<T> H{};
+    unsigned seq = 0;   // last sequence number handed out
+    unsigned seq0 = 0;  // first exchange of the active launch
+    int iat0 = 0, iat = -1, iat_end = -1, spin = 0, c0 = 0;
+    int stage = 0; // 0: gradient posted by the kernel / displacement expected, 1: ratio expected, 2: accept flags expected
+  } hd;
+  void hd_setup()
+  {
+    hd.tried = true;
+    {
+      const char* e = std::getenv("QMCB_HOST_KERNEL");
+      if (e && std::string(e) == "launch")
+        return;
+    }
+    if (!acquire_segment_kernel(true).empty())
+      return;
+    // pinned block: h_grad [3 cap] T | h_gradnew [3 cap] T | h_displ [3 cap] T | h_ratio [cap] f64 | h_ready [cap] u32 |
+    //               h_cmd [4] u32 | h_acc [cap]
+    auto up16 = [](size_t v) { return (v + 15) & ~size_t(15); };
+    size_t o = 0;
+    const size_t o_grad = o;
+    o += up16(3 * (size_t)cap * sizeof(T));
+    const size_t o_gnew = o;
+    o += up16(3 * (size_t)cap * sizeof(T));
+    const size_t o_dis = o;
+    o += up16(3 * (size_t)cap * sizeof(T));
+    const size_t o_rat = o;
+    o += up16((size_t)cap * sizeof(double));
+    const size_t o_rdy = o;
+    o += up16((size_t)cap * sizeof(unsigned));
+    const size_t o_cmd = o;
+    o += 64;
+    const size_t o_acc = o;
+    o += up16((size_t)cap);
+    hd.pin.alloc(o);
+    std::memset(hd.pin.p, 0, o);
+    hd.H.h_grad    = reinterpret_cast<T*>(hd.pin.p + o_grad);
+    hd.H.h_gradnew = reinterpret_cast<T*>(hd.pin.p + o_gnew);
+    hd.H.h_displ   = reinterpret_cast<const T*>(hd.pin.p + o_dis);
+    hd.H.h_ratio   = reinterpret_cast<double*>(hd.pin.p + o_rat);
+    hd.H.h_ready   = reinterpret_cast<volatile unsigned*>(hd.pin.p + o_rdy);
+    hd.H.h_cmd     = reinterpret_cast<volatile unsigned*>(hd.pin.p + o_cmd);
+    hd.H.h_acc     = hd.pin.p + o_acc;
+    // device block: d_displ [3 cap] T | d_cmd [4] u32 | d_acc [cap]
+    size_t d = 0;
+    const size_t d_dis = d;
+    d += up16(3 * (size_t)cap * sizeof(T));
+    const size_t d_cmd = d;
+    d += 64;
+    const size_t d_acc = d;
+    d += up16((size_t)cap);
+    hd.dev.alloc(d);
+    dev_bytes += hd.dev.bytes();
+    hd.H.d_displ = reinterpret_cast<T*>(hd.dev.p + d_dis);
+    hd.H.d_cmd   = reinterpret_cast<volatile unsigned*>(hd.dev.p + d_cmd);
+    hd.H.d_acc   = hd.dev.p + d_acc;
+    hd.enabled   = true;
+  }
+  // start a resident kernel for the moves iat .. end of the segment; false: not possible, use the launch-per-call path
+  bool hd_begin(int iat)
+  {
+    if constexpr (std::is_same<T, V>::value)
+    {
+      if (!hd.tried)
+        hd_setup();
+      if (!hd.enabled)
+        return false;
+      join_jastrow();
+      apply_pending(-1, nullptr); // an accept deferred by the launch-per-call path
+      const int spin = spin_of(iat), row = iat - first[spin];
+      const int nm   = std::min(k - delay_count[spin], nel[spin] - row);
+      if (nm <= 0)
+        return false;
+      const DetDev<V>& D   = det[spin];
+      const SplineDev<T>& S = *static_cast<const SplineDev<T>*>(spo[spin]->dev_desc());
+      const CUtensorMap& tm = *static_cast<const CUtensorMap*>(spo[spin]->seg_tensor_map());
+      hd.seq0   = hd.seq + 1;
+      hd.H.seq0 = hd.seq0;
+      hd.seq += 2u * (unsigned)nm;
+      const_cast<volatile unsigned*>(hd.H.h_cmd)[0] = hd.seq0 - 1u;
+      const_cast<volatile unsigned*>(hd.H.h_cmd)[1] = 0u;
+      const unsigned init[2] = {hd.seq0 - 1u, 0u};
+      QMCB_CUDA(cudaMemcpyAsync(const_cast<unsigned*>(hd.H.d_cmd), init, sizeof(init), cudaMemcpyHostToDevice, st));
+      drv_host.nw = nw;
+      if (D.n <= SEG_BOXW)
+      {
+        const SegLayout L = seg_layout<T, 1>(D.n, k, N, jas.has_j1 ? jas.nions : 0);
+        walker_segment_kernel<T, 1, true><<<nw, SEG_TPB, L.total, st>>>(tm, S, drv_host, jas, rng, segrng, D, iat, row, nm,
+                                                                          delay_count[spin], hd.H);
+      }
+      else
+      {
+        const SegLayout L = seg_layout<T, 2>(D.n, k, N, jas.has_j1 ? jas.nions : 0);
+        walker_segment_kernel<T, 2, true><<<nw, SEG_TPB, L.total, st>>>(tm, S, drv_host, jas, rng, segrng, D, iat, row, nm,
+                                                                          delay_count[spin], hd.H);
+      }
+      QMCB_LAUNCH_CHECK();
+      hd.active = true, hd.grad_seen = false;
+      hd.iat0 = hd.iat = iat, hd.iat_end = iat + nm, hd.spin = spin, hd.c0 = delay_count[spin], hd.stage = 0;
+      invrow_id[spin] = -1;
+      return true;
+    }
+    else
+      return false;
+  }
+  unsigned hd_seq(int iat, int second) const { return hd.seq0 + 2u * (unsigned)(iat - hd.iat0) + (unsigned)second; }
+  // every live walker has posted exchange `seq`
+  void hd_wait_ready(unsigned seq)
+  {
+    volatile unsigned* r = hd.H.h_ready;
+    unsigned long long spins = 0;
+    for (int iw = 0; iw < nw; ++iw)
+      while (r[iw] != seq)
+      {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((++spins & 0x3fffffull) == 0)
+        {
+          const cudaError_t e = cudaStreamQuery(st);
+          if (e != cudaErrorNotReady)
+          {
+            hd.active = false;
+            QMCB_CUDA(e);
+            throw std::runtime_error("the resident walker-segment kernel ended before answering (time-out inside the kernel?)");
+          }
+        }
+      }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
+  void hd_post(unsigned seq)
+  {
+    std::atomic_thread_fence(std::memory_order_release);
+    const_cast<volatile unsigned*>(hd.H.h_cmd)[0] = seq;
+  }
+  // leave the resident kernel (no-op when none is active): the completed moves stay applied, a proposed but undecided
+  // move is dropped exactly as if its accept had never been called
+  void hd_abort()
+  {
+    if (!hd.active)
+      return;
+    hd_post(SEG_ABORT);
+    QMCB_CUDA(cudaStreamSynchronize(st));
+    unsigned done[2] = {0, 0};
+    QMCB_CUDA(cudaMemcpy(done, const_cast<unsigned*>(hd.H.d_cmd), sizeof(done), cudaMemcpyDeviceToHost));
+    hd.active              = false;
+    delay_count[hd.spin]   = hd.c0 + (int)done[1];
+    invrow_id[hd.spin]     = -1;
+    const_cast<volatile unsigned*>(hd.H.h_cmd)[0] = hd.seq;
+  }
+  // the four calls of the move loop; each returns false when the call has to take the launch-per-call path
+  bool hd_eval_grad(int iat, double* grads)
+  {
+    if (!hd.active && !hd_begin(iat))
+      return false;
+    if (hd.stage != 0 || iat != hd.iat)
+    {
+      hd_abort();
+      return false;
+    }
+    hd_wait_ready(hd_seq(iat, 0));
+    hd.grad_seen = true;
+    for (size_t i = 0; i < 3 * (size_t)nw; ++i)
+      grads[i] = (double)hd.H.h_grad[i];
+    return true;
+  }
+  bool hd_make_move(int iat, const double* dsp)
+  {
+    if (!hd.active && !hd_begin(iat))
+      return false;
+    if (hd.stage != 0 || iat != hd.iat)
+    {
+      hd_abort();
+      return false;
+    }
+    if (!hd.grad_seen)
+      hd_wait_ready(hd_seq(iat, 0)); // (the mailboxes of this exchange must have been written before they are reused)
+    T* h = const_cast<T*>(hd.H.h_displ);
+    for (int i = 0; i < 3 * nw; ++i)
+      h[i] = (T)dsp[i];
+    hd_post(hd_seq(iat, 0));
+    hd.stage      = 1;
+    last_move_iat = iat;
+    return true;
+  }
+  bool hd_calc_ratio_grad(int iat, double* ratios, double* grads)
+  {
+    if (!hd.active)
+      return false;
+    if (hd.stage != 1 || iat != hd.iat)
+    {
+      hd_abort();
+      return false;
+    }
+    hd_wait_ready(hd_seq(iat, 1));
+    std::memcpy(ratios, hd.H.h_ratio, (size_t)nw * sizeof(double));
+    for (size_t i = 0; i < 3 * (size_t)nw; ++i)
+      grads[i] = (double)hd.H.h_gradnew[i];
+    hd.stage = 2;
+    return true;
+  }
+  bool hd_accept_reject(int iat, const uint8_t* acc, int safe_to_delay)
+  {
+    if (!hd.active)
+      return false;
+    if (hd.stage != 2 || iat != hd.iat)
+    {
+      hd_abort();
+      return false;
+    }
+    std::memcpy(const_cast<unsigned char*>(hd.H.h_acc), acc, nw);
+    hd_post(hd_seq(iat, 1));
+    hd.iat++;
+    hd.stage     = 0;
+    hd.grad_seen = false;
+    if (hd.iat == hd.iat_end)
+    {
+      // the kernel applies this accept and ends by itself; whatever is launched next queues behind it on the stream
+      hd.active            = false;
+      delay_count[hd.spin] = hd.c0 + (hd.iat_end - hd.iat0);
+      invrow_id[hd.spin]   = -1;
+      if (delay_count[hd.spin] == k || !safe_to_delay)
+        launch_flush(hd.spin, true);
+    }
+    else if (!safe_to_delay)
+    {
+      hd_abort();
+      launch_flush(hd.spin);
+    }
+    return true;
   }
 
   // one launch of move_boundary_kernel: accept of electron iat_prev (or -1) and row preparation of iat_next (or -1).
@@ -2151,6 +2431,7 @@ struct Crowd : CrowdBase
   }
   void flush_pending()
   {
+    hd_abort();
     join_jastrow();
     apply_pending(-1, nullptr);
   }

@@ -78,6 +78,7 @@ struct CrowdBase
   virtual void vmc_sweep_async()                                                                            = 0;
   virtual void vmc_counts(long long* na, long long* nr)                                                     = 0;
   virtual int vmc_sweep_kernel() const                                                                      = 0;
+  virtual int host_kernel() const                                                                           = 0;
   virtual void vmc_profile_sweep(double* out9)                                                              = 0;
   virtual void dmc_get_rr(double* rr_acc, double* rr_prop)                                                  = 0;
   virtual size_t walker_bytes() const                                                                       = 0;

@@ -73,7 +73,7 @@ __host__ __device__ inline SegLayout seg_layout(int n, int k, int N, int nions)
   L.vec = o, o += up(4 * k * (unsigned)sizeof(T), 16); // pA, pB, y, w
   L.red = o, o += 96 * (unsigned)sizeof(T);
   L.rgp = o, o += 32 * (unsigned)sizeof(T);
-  L.sg = o, o += 8 * (unsigned)sizeof(T);
+  L.sg = o, o += 16 * (unsigned)sizeof(T);
   L.hdr = o, o += up((SPL_HDR + SPL_SCRATCH + 4) * (unsigned)sizeof(T), 16);
   L.bars = o, o += 64;
   L.jred = o, o += 96 * (unsigned)sizeof(T); // per-consumer-warp partials of the ten Jastrow sums [6][16]
@@ -346,13 +346,104 @@ __device__ __forceinline__ bool seg_metropolis(const DriverDev<T>& Dr, const Jas
   return __shfl_sync(0xffffffffu, acc ? 1 : 0, 0) != 0;
 }
 
+// ---- host-driven mode (template parameter HD): the Metropolis test and the drift stay with the CALLER (QMCPACK's batched
+// driver calling TrialWaveFunction::mw_evalGrad / mw_calcRatioGrad / mw_accept_rejectMove per electron), but the kernel
+// stays resident for the whole segment and talks to the host thread through mailboxes in pinned host memory instead of
+// being launched four times per move:
+//     kernel: gradient of the prepared electron -> h_grad, h_ready[iw] = seq        (qmcb_twf_mw_eval_grad reads it)
+//     host:   displacements -> h_displ, h_cmd = seq                                  (qmcb_ps_mw_make_move)
+//     kernel: ratio, new gradient -> h_ratio, h_gradnew, h_ready[iw] = seq + 1       (qmcb_twf_mw_calc_ratio_grad)
+//     host:   accept flags -> h_acc, h_cmd = seq + 1                                 (qmcb_twf_mw_accept_reject)
+// Only the CTA of walker 0 polls the host word over PCIe; it copies the host's reply into device memory and republishes
+// the sequence number there for the other CTAs.  h_cmd = SEG_ABORT makes every CTA leave at its next wait with the
+// state of the completed moves written back (the host falls back to the launch-per-call path, e.g. for an API call
+// that is not part of the move loop).
+constexpr unsigned SEG_ABORT = 0xffffffffu;
+template<typename T>
+struct SegHost
+{
+  T* h_grad;                    // [nw][3] pinned host
+  double* h_ratio;              // [nw]
+  T* h_gradnew;                 // [nw][3]
+  volatile unsigned* h_ready;   // [nw]
+  const T* h_displ;             // [nw][3]
+  const unsigned char* h_acc;   // [nw]
+  volatile unsigned* h_cmd;     // [1] (+ [1]: error word written by the kernel)
+  T* d_displ;                   // [nw][3] device copies published by walker 0's CTA
+  unsigned char* d_acc;         // [nw]
+  volatile unsigned* d_cmd;     // [1] last sequence number republished on the device, [1] moves completed by this launch
+  unsigned seq0;                // sequence number of the first exchange of this launch
+};
+
+// one warp waits until the host has answered exchange `seq`; the warp of walker 0 fetches the answer (count bytes from
+// src_host to dst_dev) and republishes.  Returns false on abort / time-out.
+template<typename T>
+__device__ __forceinline__ bool seg_host_wait(const SegHost<T>& H, const int iw, const unsigned seq, const void* src_host,
+                                              void* dst_dev, const int bytes)
+{
+  const int lane = threadIdx.x & 31;
+  unsigned got   = 0;
+  if (iw == 0)
+  {
+    long long spins = 0;
+    while (true)
+    {
+      got = H.h_cmd[0];
+      if (got == SEG_ABORT || (int)(got - seq) >= 0)
+        break;
+      if (++spins > (1ll << 24)) // ~ seconds: the host thread is gone
+      {
+        got = SEG_ABORT;
+        if (lane == 0)
+          H.h_cmd[1] = 1u;
+        break;
+      }
+      __nanosleep(200);
+    }
+    if (got != SEG_ABORT)
+    {
+      __threadfence_system();
+      const unsigned char* s8 = static_cast<const unsigned char*>(src_host);
+      unsigned char* d8       = static_cast<unsigned char*>(dst_dev);
+      if ((bytes & 3) == 0)
+        for (int e = lane; e < bytes / 4; e += 32)
+          reinterpret_cast<unsigned*>(d8)[e] = reinterpret_cast<const volatile unsigned*>(s8)[e];
+      else
+        for (int e = lane; e < bytes; e += 32)
+          d8[e] = reinterpret_cast<const volatile unsigned char*>(s8)[e];
+      __threadfence();
+    }
+    __syncwarp();
+    if (lane == 0)
+      H.d_cmd[0] = got == SEG_ABORT ? SEG_ABORT : seq;
+  }
+  else
+  {
+    long long spins = 0;
+    while (true)
+    {
+      got = H.d_cmd[0];
+      if (got == SEG_ABORT || (int)(got - seq) >= 0)
+        break;
+      if (++spins > (1ll << 25))
+      {
+        got = SEG_ABORT;
+        break;
+      }
+      __nanosleep(100);
+    }
+    __threadfence();
+  }
+  return got != SEG_ABORT;
+}
+
 // grid = live walkers of the crowd (all co-resident); block = SEG_TPB; dynamic smem = seg_layout(...).total
 // Moves iat0 .. iat0 + nmoves - 1 of one determinant (rows row0 ..), c0 delays pending at entry, no flush inside.
-template<typename T, int CPT>
+template<typename T, int CPT, bool HD>
 __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
     walker_segment_kernel(const __grid_constant__ CUtensorMap tmap, const SplineDev<T> S, const DriverDev<T> Dr,
                           const JastrowDev<T> J, const RngDev R, const SegRng SR, const DetDev<T> D, const int iat0,
-                          const int row0, const int nmoves, const int c0)
+                          const int row0, const int nmoves, const int c0, const SegHost<T> H)
 {
   // (no static __shared__ variables in this kernel: the ring must sit at a 128-byte aligned shared-memory address for the
   // TMA engine, and the dynamic segment is only guaranteed to start aligned when nothing precedes it)
@@ -376,6 +467,9 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
   T* sg     = reinterpret_cast<T*>(smem_raw + L.sg);  // [3] determinant gradient of the prepared row
   T& s_ratio = sg[4];                                 // determinant ratio of the move being decided
   int& s_acc = *reinterpret_cast<int*>(sg + 5);       // its Metropolis decision
+  T* s_np    = sg + 8;                                // [3] host-driven mode: the proposed position
+  int& s_abort = *reinterpret_cast<int*>(sg + 12);    // host-driven mode: leave the loop
+  int mdone  = 0;                                     // moves whose accept / pseudo-accept has been applied
   T* hdr    = reinterpret_cast<T*>(smem_raw + L.hdr); // unit header of the evaluation (spline.cuh)
   uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
   uint64_t* empty_bar = full_bar + SEG_NSTAGE;
@@ -416,6 +510,8 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
   }
   if (tid < 3)
     sg[tid] = T(0);
+  if (tid == 0)
+    s_abort = 0;
   __syncthreads();
 
   unsigned gq = 0; // ring position; consumers and producer advance it in lock step (SEG_NQ per evaluation)
@@ -428,6 +524,42 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
 
     if (part1)
     {
+      if constexpr (HD)
+      {
+        // ---- exchange 1: gradient of the prepared electron out, displacement in (warp 6; everybody else waits at B0)
+        if (warp == 6)
+        {
+          const unsigned seq = H.seq0 + 2u * (unsigned)m;
+          const int d        = lane < 3 ? lane : 0;
+          T gd               = sg[d];
+          if (J.has_j2)
+            gd += J.dUat[((size_t)iw * 3 + d) * J.npad + iat];
+          if (J.has_j1)
+            gd += J.Grad1[((size_t)iw * 3 + d) * J.N + iat];
+          const T rold = J.rsoa[((size_t)iw * 3 + d) * J.npad + iat];
+          if (lane < 3)
+            H.h_grad[3 * iw + d] = gd;
+          __threadfence_system();
+          __syncwarp();
+          if (lane == 0)
+            H.h_ready[iw] = seq;
+          const bool ok = seg_host_wait<T>(H, iw, seq, H.h_displ, H.d_displ, 3 * Dr.nw * (int)sizeof(T));
+          if (ok)
+          {
+            const T p = rold + __ldcg(H.d_displ + 3 * iw + d); // (written by another SM: not through L1)
+            if (lane < 3)
+            {
+              J.newpos[3 * iw + d] = p;
+              s_np[d]              = p;
+            }
+          }
+          else if (lane == 0)
+            s_abort = 1;
+        }
+        __syncthreads(); // B0
+        if (s_abort)
+          break;
+      }
       // ======================= gather phase =======================
       if (warp < SEG_NCONS / 32)
       {
@@ -442,7 +574,10 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         if (J.has_j2 || J.has_j1)
         {
           T np3[3];
-          seg_propose<T, false>(Dr, J, iw, iat, sg, np3);
+          if constexpr (HD)
+            np3[0] = s_np[0], np3[1] = s_np[1], np3[2] = s_np[2];
+          else
+            seg_propose<T, false>(Dr, J, iw, iat, sg, np3);
           SEG_STAMP(0, 0); // barrier wake-up + proposal
           jastrow_move_warps<T>(warp, SEG_NCONS / 32, J, iw, iat, np3, jl, jred + warp * 16);
           SEG_STAMP(1, 0); // Jastrow sums
@@ -540,7 +675,10 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
       {
         // ---- producer: proposal, unit header (spline.cuh producer warp), one TMA request (CPT boxes) per stage
         T np3[3];
-        seg_propose<T, true>(Dr, J, iw, iat, sg, np3);
+        if constexpr (HD)
+          np3[0] = s_np[0], np3[1] = s_np[1], np3[2] = s_np[2];
+        else
+          seg_propose<T, true>(Dr, J, iw, iat, sg, np3);
         T* scratch = hdr + SPL_HDR;
         T ru[3];
         const int bc_sign = convert_pos<T, T>(S, np3, ru);
@@ -625,14 +763,19 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           if (lane == 0)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(Dr.deltas + ((size_t)(iat + 1) * Dr.nw + iw) * 3));
         }
-        mpre = seg_metro_prefetch<T>(Dr, J, R, SR, iw, iat, sg);
+        if constexpr (!HD)
+          mpre = seg_metro_prefetch<T>(Dr, J, R, SR, iw, iat, sg);
         SEG_STAMP(8, 224); // Metropolis prefetch incl. the wait for the previous move's total
       }
       gq += SEG_NQ;
       SEG_STAMP(3, 0); // epilogue
       __syncthreads(); // B1
       SEG_STAMP(4, 0);   // wait at B1
-      SEG_STAMP(9, 224); // wait at B1 (Metropolis warp): orbital rows and partial dots in shared memory, Jastrow sums and the proposal in memory
+      SEG_STAMP(9, 224); // wait at B1 (Metropolis warp)
+#ifdef QMCB_SEG_TIMING
+      if (iw == 194 && iat0 == 32 && m >= 4 && m <= 6 && (tid == 0 || tid == 224 || tid == 100))
+        printf("abs iw %d m %d tid %d after B1 clock %lld\n", iw, m, tid, (long long)clock64());
+#endif: orbital rows and partial dots in shared memory, Jastrow sums and the proposal in memory
     }
 
     // ======================= Metropolis test (warp 7) || accept-independent staging and dots (warps 0-6) =======================
@@ -672,7 +815,43 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           __syncwarp();
         }
         T rdet;
-        const bool acc = seg_metropolis<T>(Dr, J, R, SR, iw, iat, q, jsum, mpre, rdet);
+        bool acc;
+        if constexpr (HD)
+        {
+          // ---- exchange 2: TrialWaveFunction::mw_calcRatioGrad out (ratio as PsiValue = double, gradient of the
+          // proposed configuration), accept flag in; the staging and the dot sweeps of warps 0-6 run under the round trip
+          const unsigned seq = H.seq0 + 2u * (unsigned)m + 1u;
+          rdet               = q[0];
+          double ratio       = (double)rdet;
+          T gn[3]            = {q[1] / rdet, q[2] / rdet, q[3] / rdet};
+          if (J.has_j2)
+          {
+            ratio = ratio * exp((double)(J.Uat[(size_t)iw * J.npad + iat] - jsum[0]));
+            gn[0] += jsum[1], gn[1] += jsum[2], gn[2] += jsum[3];
+          }
+          if (J.has_j1)
+          {
+            ratio = ratio * exp((double)(J.Vat[(size_t)iw * J.N + iat] - jsum[5]));
+            gn[0] += jsum[6], gn[1] += jsum[7], gn[2] += jsum[8];
+          }
+          if (lane == 0)
+          {
+            H.h_ratio[iw]           = ratio;
+            H.h_gradnew[3 * iw]     = gn[0];
+            H.h_gradnew[3 * iw + 1] = gn[1];
+            H.h_gradnew[3 * iw + 2] = gn[2];
+          }
+          __threadfence_system();
+          __syncwarp();
+          if (lane == 0)
+            H.h_ready[iw] = seq;
+          const bool ok = seg_host_wait<T>(H, iw, seq, H.h_acc, H.d_acc, Dr.nw);
+          acc           = ok && __ldcg(H.d_acc + iw) != 0;
+          if (!ok && lane == 0)
+            s_abort = 1;
+        }
+        else
+          acc = seg_metropolis<T>(Dr, J, R, SR, iw, iat, q, jsum, mpre, rdet);
         if (lane == 0)
         {
           s_acc   = acc ? 1 : 0;
@@ -840,8 +1019,19 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
     }
     SEG_STAMP(6, 0); // dots
     __syncthreads(); // B2
+    if constexpr (HD)
+      if (s_abort)
+      {
+        if (nvs > 0)
+          ptx::mbar_wait(v_bar, v_phase); // (no bulk copy may be in flight into this CTA's shared memory at exit)
+        break;
+      }
     SEG_STAMP(7, 0);    // wait at B2
     SEG_STAMP(11, 224); // wait at B2 (Metropolis warp)
+#ifdef QMCB_SEG_TIMING
+    if (iw == 194 && iat0 == 32 && m >= 4 && m <= 6 && (tid == 0 || tid == 224 || tid == 100))
+      printf("abs iw %d m %d tid %d after B2 clock %lld\n", iw, m, tid, (long long)clock64());
+#endif
 
     // ======================= determinant accept + next row (threads 0-127) || Jastrow accept (threads 128-255) =======================
     if (tid < SEG_TPB / 2)
@@ -995,9 +1185,15 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
     SEG_STAMP(13, 224); // Jastrow accept
     if (nvs > 0)
       v_phase ^= 1u;
+    if (part1)
+      ++mdone;
     __syncthreads(); // B3
     SEG_STAMP(14, 0);   // wait at B3 (determinant group)
     SEG_STAMP(15, 224); // wait at B3 (Jastrow group)
+#ifdef QMCB_SEG_TIMING
+    if (iw == 194 && iat0 == 32 && m >= 4 && m <= 6 && (tid == 0 || tid == 224 || tid == 100))
+      printf("abs iw %d m %d tid %d after B3 clock %lld\n", iw, m, tid, (long long)clock64());
+#endif
   }
 
 #ifdef QMCB_SEG_TIMING
@@ -1010,7 +1206,10 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
            seg_tim[15] / nmoves);
 #endif
   // the flush (and any later API call) finds the core and w in memory
-  const int cF = c0 + nmoves;
+  const int cF = c0 + mdone;
+  if constexpr (HD)
+    if (iw == 0 && tid == 0)
+      H.d_cmd[1] = (unsigned)mdone;
   {
     T* B = D.Binv + (size_t)iw * k * k;
     for (int e = tid; e < cF * cF; e += SEG_TPB)

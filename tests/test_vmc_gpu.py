@@ -81,12 +81,16 @@ def host_sweeps(api, orc, s, nw, k, nsteps, tau, seed=1000, use_drift=True):
     return crowd, ov, log, olog
 
 
+@pytest.mark.parametrize("host_kernel", ["resident", "launch"])
 @pytest.mark.parametrize("lattice", [None, LAT_GENERAL, LAT_SHEARED], ids=["ortho", "general", "non_reduced"])
 @pytest.mark.parametrize("k", [1, 4])
-def test_host_driven_sweep_identical_acceptance_fp64(api, orc, lattice, k):
-    """FP64: acceptance sequences identical; positions, log psi, kinetic energy, G and L agree to rounding"""
+def test_host_driven_sweep_identical_acceptance_fp64(api, orc, lattice, k, host_kernel, monkeypatch):
+    """FP64: acceptance sequences identical; positions, log psi, kinetic energy, G and L agree to rounding.  The
+    per-electron calls are served either by the resident walker-segment kernel (host mailboxes) or by launches per call."""
+    monkeypatch.setenv("QMCB_HOST_KERNEL", host_kernel)
     s = small_system(np.float64, lattice)
     crowd, ov, log, olog = host_sweeps(api, orc, s, nw=6, k=k, nsteps=3, tau=0.1)
+    assert crowd.host_kernel == (2 if host_kernel == "resident" else 1)
     assert 0.2 < olog.mean() < 0.98
     assert np.array_equal(log, olog)
     assert crowd.positions() == pytest.approx(ov.positions(), rel=1e-9, abs=1e-9)
