@@ -149,6 +149,22 @@ struct VMC
   int first_of(int ig) const { return ig == 0 ? 0 : prm.n_up; }
   int last_of(int ig) const { return ig == 0 ? prm.n_up : N; }
 
+  // ref: OhmmsPETE/TensorOps.h:906-923 inverse(Tensor<T,3>), row-major
+  static void inverse3(const double* a, double* g)
+  {
+    const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+    const double vinv = 1.0 / det;
+    g[0] = vinv * (a[4] * a[8] - a[5] * a[7]);
+    g[1] = vinv * (a[7] * a[2] - a[8] * a[1]);
+    g[2] = vinv * (a[1] * a[5] - a[2] * a[4]);
+    g[3] = vinv * (a[5] * a[6] - a[3] * a[8]);
+    g[4] = vinv * (a[8] * a[0] - a[6] * a[2]);
+    g[5] = vinv * (a[2] * a[3] - a[0] * a[5]);
+    g[6] = vinv * (a[3] * a[7] - a[4] * a[6]);
+    g[7] = vinv * (a[6] * a[1] - a[7] * a[0]);
+    g[8] = vinv * (a[0] * a[4] - a[1] * a[3]);
+  }
+
   explicit VMC(const VMCParams& p) : prm(p)
   {
     N        = p.n_up + p.n_dn;
@@ -156,11 +172,10 @@ struct VMC
     npad_pos = aligned_size<RT>(N);
     // G = inverse(R) (CrystalLattice.cpp:63)
     const double* R = p.lattice;
-    MinImage<double> tmp;
-    tmp.set(p.has_spline_lattice ? p.spline_lattice : R);
+    // (the inverse of the cell AS GIVEN: the minimum-image object keeps the inverse of the REDUCED basis,
+    //  ParticleBConds3DSoa.h:339-386, which is a different matrix for a non-reduced cell)
     double G[9];
-    for (int i = 0; i < 9; ++i)
-      G[i] = tmp.g[i];
+    inverse3(p.has_spline_lattice ? p.spline_lattice : R, G);
     latG.set(G, nullptr);
     mi.set(R);
     if (is_cplx != (p.complex_orbitals != 0))

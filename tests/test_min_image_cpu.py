@@ -50,3 +50,23 @@ def test_general_cell_rows_are_nearest_images(orc, name, dtype):
                 assert row[0, j] == pytest.approx(r, abs=tol), (name, j, row[0, j], r)
                 # the displacement is the nearest-image vector unless two images tie (never within tol here)
                 assert np.allclose(row[1:, j], d, atol=tol * 10)
+
+
+def test_oracle_driver_keeps_the_given_cell_for_the_orbitals(orc):
+    """the spline SPOs convert positions with the inverse of the cell AS GIVEN (CrystalLattice::toUnit); only the distance
+    tables work in the reduced basis.  For a non-reduced cell the two inverses differ: log|det| of the oracle driver must
+    equal the determinant of the orbital matrix evaluated directly."""
+    from qmcpack_b200 import workload
+    import oracle_lib
+    lat = LATS["sheared_twice"][0]
+    s = workload.make_system(N=24, M=8, dtype=np.float64, L=6.0, lattice=lat, with_j1=False, with_j2=False)
+    nw = 2
+    R = workload.initial_positions(s, nw)
+    ov = oracle_lib.OracleVMC(orc, s, nw=nw, ncrowds=1, seeds=[1], tau=0.1, delay_rank=4)
+    ov.set_positions(R)
+    ov.recompute()
+    lp = ov.evaluate_gl()[0]
+    G = np.linalg.inv(lat)
+    for iw in range(nw):
+        want = sum(np.linalg.slogdet(orc.r2r_vgl(s["coefs"][sp], G, 12, R[iw, sp * 12:(sp + 1) * 12])[0])[1] for sp in (0, 1))
+        assert lp[iw] == pytest.approx(want, rel=1e-12)
