@@ -403,14 +403,32 @@ __device__ __forceinline__ bool seg_host_wait(const SegHost<T>& H, const int iw,
     if (got != SEG_ABORT)
     {
       __threadfence_system();
-      const unsigned char* s8 = static_cast<const unsigned char*>(src_host);
-      unsigned char* d8       = static_cast<unsigned char*>(dst_dev);
-      if ((bytes & 3) == 0)
-        for (int e = lane; e < bytes / 4; e += 32)
-          reinterpret_cast<unsigned*>(d8)[e] = reinterpret_cast<const volatile unsigned*>(s8)[e];
-      else
-        for (int e = lane; e < bytes; e += 32)
-          d8[e] = reinterpret_cast<const volatile unsigned char*>(s8)[e];
+      // the reply crosses PCIe: every load is a ~2 us round trip, so ALL of a lane's loads are requested before the
+      // first store (a load/store loop would pay the round trips one after the other); 16-byte loads (the mailboxes are
+      // 16-byte aligned and padded), up to 8 per lane per pass = 4 KB per pass
+      const uint4* s16 = static_cast<const uint4*>(src_host);
+      uint4* d16       = static_cast<uint4*>(dst_dev);
+      const int n16    = (bytes + 15) / 16;
+      for (int e0 = 0; e0 < n16; e0 += 8 * 32)
+      {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+        {
+          const int e = e0 + 32 * u + lane;
+          if (e < n16)
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
+                         : "l"(s16 + e));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+        {
+          const int e = e0 + 32 * u + lane;
+          if (e < n16)
+            d16[e] = v[u];
+        }
+      }
       __threadfence();
     }
     __syncwarp();
