@@ -8,17 +8,22 @@ One "step" = one particle-by-particle VMC sweep (every electron of every walker 
 move, distance rows, spline SPO evaluation, determinant ratio/gradient, J1/J2, Metropolis test, delayed update).
 
   value     whole-job electron-moves/s with everything resident in HBM: the device-resident sweep (on-device
-            std::mt19937 + Metropolis test, one CUDA graph per sweep), timed with CUDA events on the launching stream,
-            max over ranks.
+            std::mt19937 + Metropolis test, one CUDA graph per sweep; the persistent walker-segment kernel where the
+            wavefunction is eligible), timed with CUDA events on the launching stream, max over ranks.  The timed region
+            is one VMC BLOCK: K sweeps, then the block estimator (kinetic energy per walker) and its all-reduce over
+            ranks (the path's only collective, EstimatorManagerNew.cpp:338,363).
   e2e       the same metric through the reference-facing C ABI with HOST buffers: the compiled host driver
             (include/qmcb_driver.h) issues evalGrad / makeMove / calcRatioGrad / accept_reject per electron, positions,
             gradients, ratios and accept flags cross PCIe every move, accept test on the host -- how QMCPACK's batched
             driver would call this library.
-  roofline  the spline gather kernel timed alone (CUDA events on its stream): algorithmic bytes per launch
-            (64*Npad*4 stencil + 5*n*4 phi_vgl write + n*4 inverse-row read per walker) / average duration, against
-            the measured HBM copy bandwidth of MEASURED_PEAKS.json (burst figure).
+  roofline  the dominant kernel of the sweep.  With the walker-segment kernel: its launches timed with CUDA events in
+            one profiled sweep (qmcb_vmc_profile_sweep), algorithmic bytes per launch = SURVEY 8d's per-move figure
+            (64*Npad*4 stencil + 5*n*4 + n*4) x walkers x moves per launch, against the measured HBM copy bandwidth of
+            MEASURED_PEAKS.json.  `spline_gather` carries the stand-alone gather kernel (SPOSet::mw_evaluateVGLandDetRatioGrads)
+            at the full and at the per-crowd launch size.
   flush     the rank-k Woodbury flush (mw_updateInvMat) timed alone through the qmcb_det_time_update_inv_mat hook:
-            algorithmic TF/s, one-pass GB/s and, in full precision, the fraction of the measured FP64 tensor peak.
+            algorithmic TF/s, one-pass GB/s; `flush_fp64` the same for the full-precision shapes (NiO-a64 real k = 32,
+            NiO-a128 complex k = 64) against `fp64_peak` = cublasDgemm 8192^3 measured in this run.
   cpu_baseline  the reference's CPU path (oracle/_ref: spline2::evaluate_vgh_impl + DelayedUpdate<T> + DiracMatrix compiled
             from /root/reference, else the oracle port) on the host cores, on a bounded sample of the same workload.
 """
@@ -49,12 +54,14 @@ def parse():
     ap.add_argument("--config", default="NiO-a64")
     ap.add_argument("--walkers", type=int, default=512, help="walkers per GPU")
     ap.add_argument("--crowds", type=int, default=4, help="crowds (host threads / streams) of the e2e host driver")
-    ap.add_argument("--device-crowds", type=int, default=2,
+    ap.add_argument("--device-crowds", type=int, default=1,
                     help="crowds of the device-resident sweep: walkers/GPU are split over this many crowds, each with its own "
                          "RNG stream and CUDA graph on its own stream (QMCDriverNew gives every crowd its own generator)")
     ap.add_argument("--tau", type=float, default=0.3)
     ap.add_argument("--cpu-walkers", type=int, default=0, help="walkers of the CPU sample (default 2 per core)")
+    ap.add_argument("--sweep-kernel", type=int, default=0, help="0 automatic, 1 two-kernel path, 2 walker-segment kernel")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fp64", action="store_true", help="skip the FP64 peak / full-precision flush objects")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -193,7 +200,7 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_desc(args.config, args), "cpu_sample": res["sample"]},
         "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
-                         "sample": res["sample"]},
+                         "sample": res["sample"], "acceptance": res["acceptance"]},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -236,7 +243,8 @@ def run_b200(args, rank, local_rank, world):
         cr = api.Crowd(s, nw=dsizes[i], delay_rank=k, spo=spo)
         cr.set_positions(R[off:off + dsizes[i]])
         cr.mw_recompute()
-        cr.vmc_init(tau=args.tau, use_drift=True, seed=1000 + 7919 * rank + i, use_cuda_graph=True)  # one stream per crowd
+        cr.vmc_init(tau=args.tau, use_drift=True, seed=1000 + 7919 * rank + i, use_cuda_graph=True,
+                    sweep_kernel=args.sweep_kernel)  # one stream per crowd
         dcrowds.append(cr)
         streams.append(torch.cuda.ExternalStream(cr.stream, device=torch.device("cuda", local_rank)))
         off += dsizes[i]
@@ -247,11 +255,20 @@ def run_b200(args, rank, local_rank, world):
         a = np.concatenate([cr.vmc_counts()[0] for cr in dcrowds])
         r = np.concatenate([cr.vmc_counts()[1] for cr in dcrowds])
         return a, r
+
+    from qmcpack_b200 import sharding
+
+    def block_estimator(acc, rej):
+        """kinetic energy of every walker of this rank, reduced over ranks: the block's only collective"""
+        ke_l = np.concatenate([cr.mw_block_estimators()[1] for cr in dcrowds])
+        return ke_l, sharding.reduce_block_estimator([ke_l.sum(), (ke_l * ke_l).sum(), float(nw), float(acc), float(rej)], dist,
+                                                     device="cuda")
     for _ in range(max(args.warmup, 3)):
         for cr in dcrowds:
             cr.vmc_sweep_async()
     for cr in dcrowds:
         cr.sync()
+    block_estimator(0, 0)  # (warm-up of the estimator kernels and of the NCCL communicator)
     a0, r0 = counts()
     launches0 = api.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -269,25 +286,24 @@ def run_b200(args, rank, local_rank, world):
         for ev, st_i in zip(joins, streams[1:]):
             ev.record(st_i)
             streams[0].wait_event(ev)
+        # end of the block: estimator + all-reduce, inside the timed region
+        a1, r1 = counts()
+        ke, est = block_estimator((a1 - a0).sum(), (r1 - r0).sum())
         e1.record(streams[0])
         for cr in dcrowds:
             cr.sync()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     launches = api.kernel_launch_count() - launches0
-    a1, r1 = counts()
     acc_rate = float((a1 - a0).sum() / max(1, ((a1 - a0) + (r1 - r0)).sum()))
-    # block estimator: kinetic energy of the walkers, reduced over ranks (the path's only collective: one small
-    # all-reduce per block, EstimatorManagerNew.cpp:338,363)
-    gl = [cr.mw_evaluateGL() for cr in dcrowds]
-    lp, ke = np.concatenate([g[0] for g in gl]), np.concatenate([g[1] for g in gl])
-    from qmcpack_b200 import sharding
-    est = sharding.reduce_block_estimator([ke.sum(), (ke * ke).sum(), float(nw), float((a1 - a0).sum()),
-                                           float((r1 - r0).sum())], dist, device="cuda")
+    lp = np.concatenate([cr.mw_block_estimators()[0] for cr in dcrowds])
     ms_max = sharding.max_over_ranks(ms, dist, device="cuda")
     value = world * nw * N * args.steps / (ms_max * 1e-3)
     ke_mean = float(est[0] / est[2])
     sane = bool(np.isfinite(ke).all() and np.isfinite(lp).all())
+    sweep_kernel = dcrowds[0].sweep_kernel
+    # per-kernel attribution of one sweep outside the graph (event pair around every launch)
+    prof = dcrowds[0].vmc_profile_sweep()
 
     # ---------------- the same sweep as a caller of qmcb_vmc_sweep sees it: one call per sweep, then the per-sweep
     # results an estimator needs (kinetic energy, log psi, positions) read back to host memory every step
@@ -311,29 +327,63 @@ def run_b200(args, rank, local_rank, world):
 
     # ---------------- rank-k Woodbury flush alone (the dense contraction; informational second roofline object).
     # Executed flops per flush and walker: 4 k n^2 + 2 n k^2 (x4 complex); one-pass bytes 2 n^2 sizeof(VT).
-    # Full precision runs on the FP64 tensor pipe (DMMA; measured peak 37.0 TF/s, scripts/micro/mma_rate.cu), mixed
-    # precision on tcgen05 TF32 with the 3-product split (3x the algorithmic flops executed).
+    # Full precision runs on the FP64 tensor pipe (DMMA), mixed precision on tcgen05 TF32 with the 3-product split (3x the
+    # algorithmic flops executed).
+    pk = peaks()
+    peak = pk["hbm_gbs"] if pk else 6650.0
+
+    def flush_object(cr, nwf, n_, k_, cplx_, vt_bytes, label):
+        us_f = cr.det_time_update_inv_mat(0, k_, 8)
+        fl = (4 if cplx_ else 1) * (4.0 * k_ * n_ * n_ + 2.0 * n_ * k_ * k_) * nwf
+        by = 2.0 * n_ * n_ * vt_bytes * nwf
+        return {"shape": label, "walkers": nwf, "n": n_, "delay_rank": k_, "us_per_flush": us_f,
+                "tflops_algorithmic": fl / us_f * 1e-6, "one_pass_GBps": by / us_f * 1e-3, "frac_hbm": by / us_f * 1e-3 / peak}
     flush = None
     try:
-        us_f = dcrowds[0].det_time_update_inv_mat(0, k, 8)
-        nwf = dsizes[0]
         vt_bytes = (4 if c["dtype"] == np.float32 else 8) * (2 if cplx else 1)
-        fl = (4 if cplx else 1) * (4.0 * k * n * n + 2.0 * n * k * k) * nwf
-        by = 2.0 * n * n * vt_bytes * nwf
-        full = c["dtype"] != np.float32
-        flush = {"kernel": "wb64::woodbury_flush_dmma_kernel (DMMA m8n8k4, one pass)" if full else
-                 "wb5::woodbury_flush_tc5_kernel (tcgen05 TF32 x3 split, one pass)",
-                 "walkers": nwf, "delay_rank": k, "us_per_flush": us_f, "tflops_algorithmic": fl / us_f * 1e-6,
-                 "one_pass_GBps": by / us_f * 1e-3, "frac_hbm": by / us_f * 1e-3 / (peaks() or {"hbm_gbs": 6650.0})["hbm_gbs"]}
-        if full:
-            flush["frac_fp64_tensor_peak"] = fl / us_f * 1e-6 / 37.0
-            flush["fp64_tensor_peak_source"] = "37.0 TF/s measured with scripts/micro/mma_rate.cu (DMMA m8n8k4, all SMs)"
-        for cr in dcrowds:  # the hook leaves the inverse meaningless
-            cr.mw_recompute()
+        flush = flush_object(dcrowds[0], dsizes[0], n, k, cplx, vt_bytes, args.config)
+        flush["kernel"] = ("wb64::woodbury_flush_dmma_kernel (DMMA m8n8k4, one pass)" if c["dtype"] != np.float32 else
+                           "wb5::woodbury_flush_tc5_kernel (tcgen05 TF32 x3 split, one pass)")
     except Exception as ex:  # measurement hook only
         flush = {"error": str(ex)}
 
-    # ---------------- spline gather kernel alone (roofline)
+    # ---------------- FP64 peak of this GPU (cublasDgemm 8192^3) and the full-precision flush at
+    # the NiO-a64 (real, k = 32) and NiO-a128 (complex, k = 64) determinant shapes.  Only the determinant engine is
+    # exercised: tiny tables, the benchmarked matrix sizes.
+    fp64_peak, flush_fp64 = None, None
+    if rank == 0 and not args.no_fp64:
+        try:
+            ga = torch.randn((8192, 8192), device="cuda", dtype=torch.float64)
+            gb = torch.randn((8192, 8192), device="cuda", dtype=torch.float64)
+            torch.matmul(ga, gb)
+            best = 1e9
+            for _ in range(3):
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                gc = torch.matmul(ga, gb)
+                g1.record()
+                g1.synchronize()
+                best = min(best, g0.elapsed_time(g1))
+            fp64_peak = {"tflops": 2.0 * 8192 ** 3 / (best * 1e-3) * 1e-12, "how": "torch.matmul float64 8192^3 (cublasDgemm), best of 3, CUDA events"}
+            del ga, gb, gc
+            flush_fp64 = []
+            for label, n_, k_, cplx_, nwf in (("NiO-a64 real FP64", 384, 32, False, 512), ("NiO-a128 complex FP64", 768, 64, True, 128)):
+                t = workload.random_table((4, 4, 4), n_ * (2 if cplx_ else 1), np.float64, seed=1)
+                tsys = dict(n_up=n_, n_dn=n_, lattice=np.eye(3) * 4.0, coefs=[t, t])
+                if cplx_:
+                    kp = np.tile([0.1, 0.2, 0.3], (n_, 1))
+                    tsys["kpts"] = [kp, kp]
+                crf = api.Crowd(tsys, nw=nwf, delay_rank=k_)
+                o = flush_object(crf, nwf, n_, k_, cplx_, 16 if cplx_ else 8, label)
+                o["frac_fp64_peak"] = o["tflops_algorithmic"] / fp64_peak["tflops"]
+                o["kernel"] = "wb64::woodbury_flush_dmma_kernel + binv_v_dmma_kernel (DMMA m8n8k4)"
+                flush_fp64.append(o)
+                del crf
+        except Exception as ex:
+            flush_fp64 = {"error": str(ex)}
+
+    # ---------------- spline gather kernel alone (SPOSet::mw_evaluateVGLandDetRatioGrads), at the full population and at
+    # the launch size the two-kernel sweep uses per crowd
     T = np.float32 if c["dtype"] == np.float32 else np.float64
     tdt = torch.float32 if T == np.float32 else torch.float64
     nsets = 24
@@ -346,35 +396,58 @@ def run_b200(args, rank, local_rank, world):
     ts = torch.cuda.Stream()
     lib = api.lib()
 
-    def spline_launch(i):
-        rc = lib.qmcb_spline_mw_vgl_ratio_grads_dev(up.h, nw, pos[i % nsets].data_ptr(), inv.data_ptr(), n,
-                                                    phi.data_ptr(), rg.data_ptr(), ts.cuda_stream)
-        if rc:
-            raise RuntimeError(lib.qmcb_last_error().decode())
-    for i in range(4):
-        spline_launch(i)
-    ts.synchronize()
-    nrep = 40
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record(ts)
-    for i in range(nrep):
-        spline_launch(4 + i)
-    s1.record(ts)
-    ts.synchronize()
-    t_spl = s0.elapsed_time(s1) * 1e-3 / nrep
+    def time_gather(nwl):
+        def spline_launch(i):
+            rc = lib.qmcb_spline_mw_vgl_ratio_grads_dev(up.h, nwl, pos[i % nsets].data_ptr(), inv.data_ptr(), n,
+                                                        phi.data_ptr(), rg.data_ptr(), ts.cuda_stream)
+            if rc:
+                raise RuntimeError(lib.qmcb_last_error().decode())
+        for i in range(4):
+            spline_launch(i)
+        ts.synchronize()
+        nrep = 40
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(ts)
+        for i in range(nrep):
+            spline_launch(4 + i)
+        s1.record(ts)
+        ts.synchronize()
+        return s0.elapsed_time(s1) * 1e-3 / nrep
     npad = workload.aligned_size(T, n * nc)
     esz = np.dtype(T).itemsize
     b_spl = 64 * npad * esz + 5 * n * esz * nc + n * esz * nc  # stencil + phi_vgl write + inverse-row read
-    achieved = b_spl * nw / t_spl / 1e9
-    pk = peaks()
-    peak = pk["hbm_gbs"] if pk else 6650.0
-    tr = ncu_traffic() if (args.config == "NiO-a64" and nw == 512) else None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": tr["bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None,
-                "kernel": "spline_gather_kernel (VGL + ratio/grad)",
-                "algorithmic_bytes_per_launch": b_spl * nw, "us_per_launch": t_spl * 1e6,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if pk else "fallback 6.65 TB/s",
-                "evals_per_s": nw / t_spl}
+    t_spl = time_gather(nw)
+    tr = ncu_traffic("spline_gather_kernel") if (args.config == "NiO-a64" and nw == 512) else None
+    spline_gather = {"kernel": "spline_gather_kernel (VGL + ratio/grad)", "walkers": nw, "us_per_launch": t_spl * 1e6,
+                     "achieved": b_spl * nw / t_spl / 1e9, "unit": "GB/s", "frac": b_spl * nw / t_spl / 1e9 / peak,
+                     "traffic": tr["bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None,
+                     "evals_per_s": nw / t_spl}
+    nw_crowd = max(1, nw // 2)
+    if nw_crowd < nw:
+        t_c = time_gather(nw_crowd)
+        spline_gather["per_crowd"] = {"walkers": nw_crowd, "us_per_launch": t_c * 1e6, "frac": b_spl * nw_crowd / t_c / 1e9 / peak}
+    # the roofline object = the dominant kernel of the timed sweep, measured in situ (profiled sweep, event pairs)
+    if sweep_kernel == 2 and prof["segment_launches"] > 0:
+        moves_per_launch = N * dsizes[0] / prof["segment_launches"]
+        t_k = prof["segment_us"] * 1e-6 / prof["segment_launches"]
+        alg = b_spl * moves_per_launch
+        trs = ncu_traffic("walker_segment_kernel") if (args.config == "NiO-a64" and dsizes[0] == 512) else None
+        roofline = {"bound": "hbm", "achieved": alg / t_k / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / t_k / 1e9 / peak,
+                    "traffic": trs["bytes_per_launch"] if trs else None, "traffic_source": trs["source"] if trs else None,
+                    "kernel": "walker_segment_kernel (proposal + spline gather + ratio + Metropolis test + accept + next row, "
+                              "%d walkers x %d moves per launch)" % (dsizes[0], round(moves_per_launch / dsizes[0])),
+                    "algorithmic_bytes_per_launch": alg, "us_per_launch": t_k * 1e6,
+                    "share_of_sweep": prof["segment_us"] / prof["sweep_us"],
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth; the file carries one HBM figure)" if pk else "fallback 6.65 TB/s"}
+    else:
+        roofline = {"bound": "hbm", "achieved": spline_gather["achieved"], "peak": peak, "unit": "GB/s", "frac": spline_gather["frac"],
+                    "traffic": spline_gather["traffic"], "traffic_source": spline_gather["traffic_source"],
+                    "kernel": spline_gather["kernel"], "algorithmic_bytes_per_launch": b_spl * nw,
+                    "us_per_launch": t_spl * 1e6, "share_of_sweep": prof["gather_us"] / max(prof["sweep_us"], 1e-9),
+                    "frac_in_situ": (b_spl * dsizes[0] / (prof["gather_us"] * 1e-6 / max(prof["gather_launches"], 1)) / 1e9 / peak)
+                    if prof["gather_launches"] else None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if pk else "fallback 6.65 TB/s"}
+    roofline["sweep_attribution_us"] = {kk: prof[kk] for kk in ("sweep_us", "segment_us", "boundary_us", "gather_us", "flush_us")}
 
     # ---------------- end to end through the C ABI with host buffers
     e2e = None
@@ -413,7 +486,9 @@ def run_b200(args, rank, local_rank, world):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         res = cpu_reference_run(args.config, args, steps=12, warmup=1, nw_cpu=4 * (os.cpu_count() or 1))
-        cpu = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]}
+        cpu = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"],
+               "acceptance": res["acceptance"], "acceptance_gpu": acc_rate,
+               "acceptance_agrees": bool(abs(res["acceptance"] - acc_rate) < 0.01)}
 
     if rank == 0:
         line = {
@@ -425,9 +500,12 @@ def run_b200(args, rank, local_rank, world):
                        "l2": "inputs larger than L2: 2 x %.0f MB spline tables + %.1f GB walker state vs 126 MB L2"
                              % (up.table_bytes / 1e6, state_bytes / 1e9),
                        "parallelism": f"walkers sharded over {world} GPU(s), no data-path collective; one all-reduce per block",
-                       "acceptance": acc_rate, "ke_mean_hartree": ke_mean, "finite": sane},
+                       "acceptance": acc_rate, "ke_mean_hartree": ke_mean, "finite": sane,
+                       "sweep_kernel": "walker-segment kernel (csrc/segment.cuh)" if sweep_kernel == 2 else
+                       "boundary kernel + spline gather per move",
+                       "timed_region": "one VMC block: %d sweeps + block estimator + all-reduce over ranks" % args.steps},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "flush": flush, "cpu_baseline": cpu,
+            "flush": flush, "flush_fp64": flush_fp64, "fp64_peak": fp64_peak, "spline_gather": spline_gather, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if dist:

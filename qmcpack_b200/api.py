@@ -332,6 +332,12 @@ class Crowd:
         _chk(lib().qmcb_twf_mw_evaluate_gl(self.h, _p(G), _p(L), _p(lp), _p(ke)))
         return lp, ke, G, L
 
+    def mw_block_estimators(self):
+        """(log psi, kinetic energy) per walker without shipping G and L to the host: what a block estimator needs"""
+        lp, ke = np.zeros(self.nw), np.zeros(self.nw)
+        _chk(lib().qmcb_twf_mw_evaluate_gl(self.h, None, None, _p(lp), _p(ke)))
+        return lp, ke
+
     # ---- DiracDeterminantBatched / DelayedUpdateBatched
     def det_mw_evalGrad(self, spin, row):
         g = np.zeros((self.nw, 3), self.V)

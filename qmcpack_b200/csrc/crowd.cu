@@ -13,6 +13,7 @@
 #include <cuda.h>
 #include <type_traits>
 #include <cublas_v2.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cmath>
 #include <cstring>
 #include <algorithm>
@@ -22,6 +23,15 @@
 
 namespace qmcb
 {
+// NVTX ranges named after the reference's timers (Utilities/NewTimer.cpp:48-49,94-95 pushes an NVTX range per ScopedTimer;
+// names: DiracDeterminantBase.h:42-47, TrialWaveFunction.cpp TWF_timers_): visible in Nsight Systems, free otherwise
+struct NvtxRange
+{
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define QMCB_NVTX(name) qmcb::NvtxRange nvtx_range__(name)
+
 #define QMCB_CUBLAS(call)                                                                      \
   do                                                                                           \
   {                                                                                            \
@@ -233,6 +243,8 @@ __device__ __forceinline__ bool metropolis_warp(const DriverDev<T>& Dr, const Ja
   }
   const T eps = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
   T prob      = (T)norm2(ratio); // std::norm(ratio), VMCBatched.cpp:152
+  if (isnan(norm2(ratio)) && lane == 0 && Dr.err)
+    atomicOr(Dr.err, QMCB_ERR_NAN_RATIO); // NaNguard::checkOneParticleRatio (TrialWaveFunction.cpp:549): the host throws
   bool need   = prob >= eps;     // periodic cell: every move is valid
   T rr        = T(0);
   if (Dr.dmc)
@@ -522,6 +534,8 @@ __global__ void __launch_bounds__(MB_TPB, (sizeof(V) > 8 ? 2 : 4))
       if (acc)
       {
         // bordered update of Binv (DelayedUpdate.h:113-141) on the staged copy
+        if (tid == 0 && s_ratio == V(0) && Dacc.err)
+          atomicOr(Dacc.err, QMCB_ERR_ZERO_RATIO_ACCEPTED);
         const V sigma = V(1) / s_ratio;
         if (tid < c)
         {
@@ -810,6 +824,7 @@ struct Crowd : CrowdBase
   DevBuf<DV> ratios_d;
   DevBuf<double> ke_d;
   DevBuf<unsigned char> accepted;
+  DevBuf<unsigned> err_word; // crowd-wide error bits set by the kernels (det.cuh: QMCB_ERR_*)
   PinBuf<unsigned char> h_acc;
   PinBuf<V> h_t;  // gradients / displacements staging (displacements use the second half, as T)
   PinBuf<DV> h_d;
@@ -921,6 +936,8 @@ struct Crowd : CrowdBase
       D.Ainv = Ainv[s2].p, D.GL = GL[s2].p, D.U = U[s2].p, D.V = Vb[s2].p, D.Binv = Binv[s2].p, D.wvec = wvec[s2].p;
       D.list = list[s2].p, D.invRow = invRow[s2].p, D.tempMat = tempMat[s2].p, D.Up = Up[s2].p, D.logdet = logdet[s2].p;
     }
+    A(err_word, 4);
+    det[0].err = det[1].err = err_word.p;
     A(phi_vgl, (size_t)5 * nw * nmax);
     rg_cap = std::max(1, std::max(spo[0]->rg_parts(), spo[1]->rg_parts()));
     A(rg, (size_t)nw * rg_cap * 4);
@@ -1004,6 +1021,7 @@ struct Crowd : CrowdBase
     }
     std::memset(&drv_host, 0, sizeof(drv_host));
     drv_host.nw = nw, drv_host.N = N, drv_host.use_drift = 1, drv_host.accepted = accepted.p;
+    drv_host.err = err_word.p;
     drv_host.pdl_early = (g_pdl_mode & 4) ? 1 : 0;
     drv_host.l1_prefetch = env_flag("QMCB_L1PF", 1);
     std::memset(&rng, 0, sizeof(rng));
@@ -1230,6 +1248,54 @@ struct Crowd : CrowdBase
       throw std::runtime_error("determinant row out of range");
   }
 
+  // ---------------------------------------------------------------- numerical guards
+  // The reference throws from the host the moment a ratio is NaN (NaNguard::checkOneParticleRatio, TrialWaveFunction.cpp:
+  // 473,508,549) or a move is accepted with a zero determinant ratio (DiracDeterminantBatched.cpp:494-500).  Kernels that
+  // decide on the device leave a bit in err_word instead; every synchronising entry point turns it into the same exception.
+  void check_device_errors(const char* where)
+  {
+    unsigned bits = 0;
+    QMCB_CUDA(cudaMemcpyAsync(&bits, err_word.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    QMCB_CUDA(cudaStreamSynchronize(st));
+    if (!bits)
+      return;
+    QMCB_CUDA(cudaMemsetAsync(err_word.p, 0, sizeof(unsigned), st));
+    std::string msg;
+    if (bits & QMCB_ERR_NAN_RATIO)
+      msg += std::string("NaNguard::checkOneParticleRatio error message: ") + where + ": a one-particle ratio is NaN. ";
+    if (bits & QMCB_ERR_ZERO_RATIO_ACCEPTED)
+      msg += std::string("mw_accept_rejectMove (") + where + "): det.curRatio is 0 for an accepted move! Report a bug.";
+    throw std::runtime_error(msg);
+  }
+  std::vector<unsigned char> ratio_zero; // host-driven path: walkers whose last determinant-times-Jastrow ratio was 0
+  void guard_ratios(const double* ratios, const char* where)
+  {
+    ratio_zero.assign(nw, 0);
+    for (int iw = 0; iw < nw; ++iw)
+    {
+      double nrm = 0;
+      for (int c2 = 0; c2 < ncomp; ++c2)
+        nrm += ratios[(size_t)iw * ncomp + c2] * ratios[(size_t)iw * ncomp + c2];
+      if (std::isnan(nrm))
+        throw std::runtime_error(std::string("NaNguard::checkOneParticleRatio error message: ") + where + " walker " +
+                                 std::to_string(iw) + ": ratio is NaN");
+      ratio_zero[iw] = nrm == 0.0;
+    }
+  }
+  void guard_accept(const uint8_t* acc)
+  {
+    if ((int)ratio_zero.size() != nw)
+      return;
+    for (int iw = 0; iw < nw; ++iw)
+      if (acc[iw] && ratio_zero[iw])
+      {
+        ratio_zero.clear();
+        throw std::runtime_error("mw_accept_rejectMove: curRatio is 0 for the accepted move of walker " + std::to_string(iw) +
+                                 "! Report a bug.");
+      }
+    ratio_zero.clear();
+  }
+
   // ---------------------------------------------------------------- positions
   void set_positions(const double* R) override
   {
@@ -1439,6 +1505,7 @@ struct Crowd : CrowdBase
   }
   void det_ratio_grad(int spin, int row, void* ratios, void* grads, bool from_phi) override
   {
+    QMCB_NVTX("DiracDeterminantBatched::ratio");
     flush_pending();
     check_row(spin, row);
     ensure_row(spin, row);
@@ -1485,14 +1552,17 @@ struct Crowd : CrowdBase
   }
   void det_accept_reject(int spin, int row, const uint8_t* acc) override
   {
+    QMCB_NVTX("DiracDeterminantBatched::update");
     flush_pending();
     check_row(spin, row);
     upload_flags(acc);
     launch_accept(spin, row, accepted.p, rg.p, phi_vgl.p);
     sync(); // h_acc is reused by the next call
+    check_device_errors("DiracDeterminantBatched::mw_accept_rejectMove");
   }
   void det_complete_updates(int spin, void* psiMinv, double* logdet_h) override
   {
+    QMCB_NVTX("DiracDeterminantBatched::update");
     flush_pending();
     if (spin < 0 || spin > 1)
       throw std::runtime_error("bad spin");
@@ -1558,6 +1628,7 @@ struct Crowd : CrowdBase
   // (always FullPrecValueType like DiracMatrixInverterCUDA::mw_invertTranspose, DiracMatrixInverterCUDA.hpp:306-369)
   void invert_from_AT(int spin, DevBuf<DV>& AT)
   {
+    QMCB_NVTX("DiracDeterminantBatched::inverse");
     const int n = nel[spin];
     DevBuf<DV> inv;
     DevBuf<int> piv, info;
@@ -1628,6 +1699,7 @@ struct Crowd : CrowdBase
   // ---------------------------------------------------------------- trial wavefunction level
   void twf_recompute() override
   {
+    QMCB_NVTX("TrialWaveFunction::mw_evaluateLog");
     flush_pending();
     for (int spin = 0; spin < 2; ++spin)
     {
@@ -1663,6 +1735,7 @@ struct Crowd : CrowdBase
 
   void twf_eval_grad(int iat, double* grads) override
   {
+    QMCB_NVTX("TrialWaveFunction::mw_evalGrad");
     check_iat(iat);
     if (hd_eval_grad(iat, grads))
       return;
@@ -1684,6 +1757,7 @@ struct Crowd : CrowdBase
 
   void ps_make_move(int iat, const double* dsp) override
   {
+    QMCB_NVTX("ParticleSet::mw_makeMove");
     check_iat(iat);
     if (hd.active && hd_make_move(iat, dsp)) // (a resident kernel is started by mw_evalGrad; loops without drift launch per call)
       return;
@@ -1726,9 +1800,13 @@ struct Crowd : CrowdBase
 
   void twf_calc_ratio_grad(int iat, double* ratios, double* grads) override
   {
+    QMCB_NVTX("TrialWaveFunction::mw_calcRatioGrad");
     check_iat(iat);
     if (hd_calc_ratio_grad(iat, ratios, grads))
+    {
+      guard_ratios(ratios, "TWF::mw_calcRatioGrad");
       return;
+    }
     apply_pending(-1, nullptr); // (make_move already applied it; the Jastrow rows keep running beside the gather below)
     const int spin = spin_of(iat), row = iat - first[spin];
     ensure_row(spin, row);
@@ -1739,11 +1817,14 @@ struct Crowd : CrowdBase
     spin_sync();
     std::memcpy(ratios, h_d.p, (size_t)nw * sizeof(DV));
     widen(grads, h_t.p, 3 * (size_t)nw);
+    guard_ratios(ratios, "TWF::mw_calcRatioGrad");
   }
 
   void twf_accept_reject(int iat, const uint8_t* acc, int safe_to_delay) override
   {
+    QMCB_NVTX("TrialWaveFunction::mw_accept_rejectMove");
     check_iat(iat);
+    guard_accept(acc);
     if (hd_accept_reject(iat, acc, safe_to_delay))
       return;
     flush_pending();
@@ -1760,6 +1841,7 @@ struct Crowd : CrowdBase
 
   void twf_complete_updates() override
   {
+    QMCB_NVTX("TrialWaveFunction::mw_completeUpdates");
     flush_pending();
     launch_flush(0);
     launch_flush(1);
@@ -1767,6 +1849,7 @@ struct Crowd : CrowdBase
 
   void twf_evaluate_gl(double* G, double* L, double* logpsi, double* ke) override
   {
+    QMCB_NVTX("TrialWaveFunction::mw_evaluateGL");
     twf_complete_updates();
     QMCB_CUDA(cudaMemsetAsync(Gd.p, 0, Gd.bytes(), st));
     QMCB_CUDA(cudaMemsetAsync(Ld.p, 0, Ld.bytes(), st));
@@ -1804,6 +1887,7 @@ struct Crowd : CrowdBase
     if (jas.has_j1)
       QMCB_CUDA(cudaMemcpyAsync(lj1.data(), j1_log.p, nw * sizeof(double), cudaMemcpyDeviceToHost, st));
     sync();
+    check_device_errors("TrialWaveFunction::mw_evaluateGL");
     if (G)
       widen(G, hg.data(), hg.size());
     if (L)
@@ -1884,6 +1968,7 @@ struct Crowd : CrowdBase
     }
     std::memset(&drv, 0, sizeof(drv));
     drv.nw = nw, drv.N = N;
+    drv.err = err_word.p;
     // TauParams (QMCDrivers/TauParams.hpp:29-40), unit mass
     drv.tauovermass = (T)p->tau * (T)1.0;
     drv.oneover2tau = (T)(0.5 / drv.tauovermass);
@@ -2562,6 +2647,7 @@ struct Crowd : CrowdBase
 
   void vmc_sweep(int nsteps, uint8_t* log_host) override
   {
+    QMCB_NVTX("VMCBatched::advanceWalkers");
     flush_pending();
     if (!vmc_ready)
       throw std::runtime_error("qmcb_vmc_init has not been called");
@@ -2575,6 +2661,7 @@ struct Crowd : CrowdBase
       }
     }
     sync();
+    check_device_errors("VMCBatched::advanceWalkers (device-resident sweep)");
   }
   void vmc_counts(long long* na, long long* nr) override
   {
@@ -2684,6 +2771,7 @@ struct Crowd : CrowdBase
   }
   void pack_walker(int iw, void* dev_buf) override
   {
+    QMCB_NVTX("DiracDeterminantBatched::buffer");
     check_walker(iw);
     settle();
     unsigned char* out = static_cast<unsigned char*>(dev_buf);

@@ -36,7 +36,11 @@ struct DetDev
   T* tempMat;     // [nw][n][k]
   T* Up;          // [nw][k][n]
   double* logdet; // [nw][2]
+  unsigned* err;  // crowd-wide error bits set by the kernels, read by the host at its next synchronisation:
+                  // 1 = a one-particle ratio was NaN (NaNguard::checkOneParticleRatio, TrialWaveFunction.cpp:473,508,549)
+                  // 2 = a move was accepted with a zero determinant ratio (DiracDeterminantBatched.cpp:494-500)
 };
+constexpr unsigned QMCB_ERR_NAN_RATIO = 1u, QMCB_ERR_ZERO_RATIO_ACCEPTED = 2u;
 
 #ifdef __CUDACC__
 constexpr int DET_TPB = 256;
@@ -183,6 +187,8 @@ __device__ __forceinline__ void det_accept_body(const Group& g, const DetDev<T>&
   // V[c] = Ainv[row] (stale stored row) for every walker, DelayedUpdateBatched.h:646
   for (int j = g.tid; j < n; j += g.n)
     V[(size_t)c * n + j] = arow[j];
+  if (acc && g.tid == 0 && ratio == T(0) && D.err)
+    atomicOr(D.err, QMCB_ERR_ZERO_RATIO_ACCEPTED);
   if (acc)
   {
     const T* ph = phi_vgl + (size_t)iw * n;

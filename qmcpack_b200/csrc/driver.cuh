@@ -45,6 +45,7 @@ struct DriverDev
   unsigned long long* n_accept; // [nw]
   unsigned long long* n_reject; // [nw]
   unsigned char* accept_log;    // optional [N][nw] of the current sweep
+  unsigned* err;                // crowd-wide error bits (det.cuh: QMCB_ERR_*)
 };
 
 #ifdef __CUDACC__

@@ -285,6 +285,8 @@ __device__ __forceinline__ bool seg_metropolis(const DriverDev<T>& Dr, const Jas
   }
   const T eps = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
   T prob      = (T)(ratio * ratio); // std::norm(ratio), VMCBatched.cpp:152
+  if (isnan(ratio) && lane == 0 && Dr.err)
+    atomicOr(Dr.err, QMCB_ERR_NAN_RATIO); // NaNguard::checkOneParticleRatio (TrialWaveFunction.cpp:549): the host throws
   bool need   = prob >= eps;
   if (Dr.dmc)
   {
@@ -1077,6 +1079,8 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         if (acc)
         {
           // bordered update of Binv (DelayedUpdate.h:113-141) in shared memory; w is the one left by this row's preparation
+          if (tid == 0 && s_ratio == T(0) && D.err)
+            atomicOr(D.err, QMCB_ERR_ZERO_RATIO_ACCEPTED);
           const T sigma = T(1) / s_ratio;
           if (tid < c)
           {
