@@ -474,6 +474,17 @@ int orc_vmc_probe_move(void* hv, int iw, int iat, const double* displ, double* r
     }
   });
 }
+// TrialWaveFunction::mw_evaluateRatios for one walker: nk virtual positions of electron `ref`; out [nk][2] (re, im)
+int orc_vmc_evaluate_ratios(void* hv, int iw, int ref, int nk, const double* r_vp, int ct, double* out)
+{
+  auto* h = static_cast<VMCHandle*>(hv);
+  return guarded([&] {
+    std::vector<std::complex<double>> r(nk);
+    VMC_DISPATCH(h, v.evaluateRatios(iw, ref, nk, r_vp, ct, r.data()));
+    for (int i = 0; i < nk; ++i)
+      out[2 * i] = r[i].real(), out[2 * i + 1] = r[i].imag();
+  });
+}
 int orc_vmc_recompute(void* hv)
 {
   auto* h = static_cast<VMCHandle*>(hv);

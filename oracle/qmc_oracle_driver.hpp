@@ -456,6 +456,63 @@ struct VMC
       grad_new[dd] = std::complex<double>(gn[dd] / ratio) + (double)gj[dd];
   }
 
+  // TrialWaveFunction::mw_evaluateRatios body for ONE walker (TrialWaveFunction.cpp:1079-1110): the ratios
+  // psi(R with electron `ref` at r_vp[k]) / psi(R) at the nk virtual positions of a VirtualParticleSet (the quadrature
+  // points of the non-local pseudopotential), as the product over the selected components:
+  //   determinant  DiracDeterminantBatched::evaluateRatios (DiracDeterminantBatched.cpp:790-797): psiMinv row . psi(r_vp)
+  //   J2           TwoBodyJastrow::evaluateRatios (TwoBodyJastrow.cpp:166-171): exp(Uat[ref] - computeU(dist row of r_vp))
+  //                with computeU = sum_{j != ref} F[group(ref)][group(j)].evaluate(r_j) (value only, BsplineFunctor.cpp:135-200)
+  //   J1           J1OrbitalSoA::evaluateRatios (J1OrbitalSoA.h:295-299): exp(Vat[ref] - computeU(e-ion row of r_vp))
+  // ct: 0 ALL, 1 FERMIONIC, 2 NONFERMIONIC (TrialWaveFunction::ComputeType)
+  void evaluateRatios(int iw, int ref, int nk, const double* r_vp, int ct, std::complex<double>* out)
+  {
+    Walker& w     = walkers[iw];
+    const int ig  = group_of(ref);
+    const int row = ref - first_of(ig);
+    Det& d        = w.det[ig];
+    const int n   = d.n;
+    if (ct != 2)
+      prepareInvRow(d, row); // (= the row of psiMinv once the delayed updates are complete)
+    std::vector<VT> psi(n), dpsi(3 * (size_t)n), d2psi(n);
+    std::vector<RT> dist(4 * npad_pos);
+    for (int kq = 0; kq < nk; ++kq)
+    {
+      const RT pos[3] = {(RT)r_vp[3 * kq], (RT)r_vp[3 * kq + 1], (RT)r_vp[3 * kq + 2]};
+      std::complex<double> r(1.0, 0.0);
+      if (ct != 2)
+      {
+        spoVGL(w, ig, pos, psi.data(), dpsi.data(), d2psi.data());
+        VT ratio(0);
+        for (int j = 0; j < n; ++j)
+          ratio += d.invRow[j] * psi[j];
+        r *= std::complex<double>(static_cast<PsiV>(ratio));
+      }
+      if (ct != 1 && has_j2)
+      {
+        mi.row(pos, w.rsoa.data(), npad_pos, N, ref, dist.data());
+        RT usum(0);
+        const int igt = j2.grp_ids[ref] * j2.ngroups;
+        for (int j = 0; j < N; ++j)
+        {
+          if (j == ref)
+            continue;
+          const BsplineFunctor<RT>& f = j2.F[igt + j2.grp_ids[j]];
+          RT du, d2u;
+          if (f.present && dist[j] < f.cutoff_radius)
+            usum += f.evaluate_impl(dist[j], du, d2u);
+        }
+        r *= std::exp(static_cast<double>(w.j2.Uat[ref] - usum));
+      }
+      if (ct != 1 && has_j1)
+      {
+        RT at, lap, g[3];
+        j1.compute(mi, pos, at, lap, g);
+        r *= std::exp(static_cast<double>(w.j1.Vat[ref] - at));
+      }
+      out[kq] = r;
+    }
+  }
+
   // one sweep step for one crowd
   // forced (optional, [N][nw]): accept flags imposed from outside ("teacher forcing" for mixed-precision parity: the
   // uniform is still drawn under the reference's rule so that the stream stays aligned); ratio_log (optional, [N][nw]):

@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(MB_TPB, (sizeof(V) > 8 ? 2 : 4))
       {
         Vm[(size_t)c * nA + j] = vrow[j];
         U[(size_t)c * nA + j]  = acc ? phi[j] : V(0);
-        if (acc)
+        if (acc && !Dr.value_only)
         {
           st_stream(gl + j, phi[nA + j]); // next read a whole sweep later: streaming stores
           st_stream(gl + nA + j, phi[2 * nA + j]);

@@ -388,6 +388,24 @@ __global__ void det_scatter_row_kernel(const DetDev<T> D, const int e, const T* 
   gl[3 * n + j]                    = ph[4 * fs + j];
 }
 
+// gradient / Laplacian rows of electron `e` only (psiM is not touched): refresh of dpsiM, d2psiM after ratio-only moves
+// (DiracDeterminantBatched::mw_evaluateGL with UpdateMode == ORB_PBYP_RATIO re-evaluates them, DiracDeterminantBatched.cpp:630-678)
+template<typename T>
+__global__ void det_scatter_gl_kernel(const DetDev<T> D, const int e, const T* phi_vgl)
+{
+  const int iw = blockIdx.y, n = D.n;
+  const int j  = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n)
+    return;
+  const size_t fs = (size_t)D.nw * n;
+  const T* ph     = phi_vgl + (size_t)iw * n;
+  T* gl           = D.GL + ((size_t)iw * n + e) * 4 * n;
+  gl[j]           = ph[fs + j];
+  gl[n + j]       = ph[2 * fs + j];
+  gl[2 * n + j]   = ph[3 * fs + j];
+  gl[3 * n + j]   = ph[4 * fs + j];
+}
+
 // log-determinant from the LU factors (DiracMatrix.h:100-107 / detail/CUDA/cuBLAS_LU.cu:61-110):
 // sum_i log(complex(pivot[i]==i+1 ? diag : -diag)); LU is column-major [n][n] per walker
 template<typename DT /* double or cx<double> */>

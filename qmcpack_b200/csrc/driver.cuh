@@ -46,6 +46,8 @@ struct DriverDev
   unsigned long long* n_reject; // [nw]
   unsigned char* accept_log;    // optional [N][nw] of the current sweep
   unsigned* err;                // crowd-wide error bits (det.cuh: QMCB_ERR_*)
+  int value_only;               // the proposed move's orbital rows hold VALUES only (TrialWaveFunction::mw_calcRatio):
+                                // an accept must not touch the gradient / Laplacian rows
 };
 
 #ifdef __CUDACC__

@@ -85,9 +85,14 @@ __device__ __forceinline__ void spline_bound_rt(RT x, int nmax, int& ind, RT& dx
   }
 }
 
+#ifdef QMCB_JAS_NOINLINE
+#define QMCB_JAS_INLINE __noinline__
+#else
+#define QMCB_JAS_INLINE __forceinline__
+#endif
 // ref: BsplineFunctor.h:254-285 evaluate_impl; returns u, sets du = u'/r and d2u = u'' (zero beyond the cutoff)
 template<typename RT>
-__device__ __forceinline__ RT functor_eval(const FunctorDev<RT>& f, RT r, RT& du_over_r, RT& d2u)
+__device__ QMCB_JAS_INLINE RT functor_eval(const FunctorDev<RT>& f, RT r, RT& du_over_r, RT& d2u)
 {
   RT u(0);
   du_over_r = RT(0);
@@ -116,7 +121,7 @@ __device__ __forceinline__ RT functor_eval(const FunctorDev<RT>& f, RT r, RT& du
 
 // minimum-image displacement src - pos.  ref: ParticleBConds3DSoa.h:141-168 (ortho), :452-510 (general)
 template<typename RT>
-__device__ __forceinline__ void min_image(const CellDev<RT>& C, const RT pos[3], RT px, RT py, RT pz, int iel, int flip_ind,
+__device__ QMCB_JAS_INLINE void min_image(const CellDev<RT>& C, const RT pos[3], RT px, RT py, RT pz, int iel, int flip_ind,
                                           RT& rr, RT& dx, RT& dy, RT& dz)
 {
   if (C.ortho)
@@ -347,7 +352,10 @@ __device__ __forceinline__ void jastrow_move_warps(const int wg, const int nwarp
   int cnt = 0;
   // pass 1: every distance; the position loads of up to JB iterations are requested before the first is used (one
   // memory round trip per JB * 32 nwarps candidates)
-  constexpr int JB = 3;
+#ifndef QMCB_JB
+#define QMCB_JB 1 // measured on B200 (NiO-a64, 512 walkers, segment kernel per sweep): 1 -> 32.5 ms, 2 -> 35.4 ms, 3 -> 40.0 ms
+#endif
+  constexpr int JB = QMCB_JB;
   for (int it = 0; it < iters; it += JB)
   {
     int idx[JB];
@@ -423,6 +431,54 @@ __device__ __forceinline__ void jastrow_move_warps(const int wg, const int nwarp
     part[lane >> 1] = acc[0];
 }
 
+// ---- ratios at VIRTUAL positions (non-local pseudopotential quadrature points): TwoBodyJastrow::mw_evaluateRatios
+// (Jastrow/TwoBodyJastrow.cpp:174-210) -> BsplineFunctor::mw_evaluateV (Jastrow/BsplineFunctor.cpp:135-200), and
+// J1OrbitalSoA::evaluateRatios (Jastrow/J1OrbitalSoA.h:295-299).  One warp per virtual position ivp of walker wk[ivp]
+// replacing electron ref[ivp]:  out[ivp] = exp(Uat[ref] - sum_{j != ref} u(|r_j - r_vp|)) * exp(Vat[ref] - sum_I u(|R_I - r_vp|)).
+// grid = ceil(nvp / 4), block = 128.
+template<typename RT>
+__global__ void __launch_bounds__(128)
+    jastrow_vp_ratio_kernel(const JastrowDev<RT> J, const int nvp, const int* wk, const int* ref, const RT* rvp, double* out)
+{
+  const int lane = threadIdx.x & 31, ivp = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (ivp >= nvp)
+    return;
+  const int iw = wk[ivp], iat = ref[ivp], np = J.npad;
+  const RT pos[3] = {rvp[3 * ivp], rvp[3 * ivp + 1], rvp[3 * ivp + 2]};
+  const RT* rs    = J.rsoa + (size_t)iw * 3 * np;
+  RT u2(0), u1(0);
+  if (J.has_j2)
+  {
+    const int gi = (iat < J.n_up ? 0 : 1) * 2;
+    for (int j = lane; j < J.N; j += 32)
+    {
+      if (j == iat)
+        continue;
+      RT r, dx, dy, dz, du, d2u;
+      min_image(J.cell, pos, rs[j], rs[np + j], rs[2 * np + j], j, 0, r, dx, dy, dz);
+      u2 += functor_eval(J.F2[gi + (j < J.n_up ? 0 : 1)], r, du, d2u);
+    }
+  }
+  if (J.has_j1)
+    for (int j = lane; j < J.nions; j += 32)
+    {
+      RT r, dx, dy, dz, du, d2u;
+      min_image(J.cell, pos, J.ion_rsoa[j], J.ion_rsoa[J.npad_ion + j], J.ion_rsoa[2 * J.npad_ion + j], j, 0, r, dx, dy, dz);
+      u1 += functor_eval(J.F1[J.ion_grp[j]], r, du, d2u);
+    }
+  u2 = warp_sum(u2);
+  u1 = warp_sum(u1);
+  if (lane == 0)
+  {
+    double ratio = 1.0;
+    if (J.has_j2)
+      ratio *= exp((double)(J.Uat[(size_t)iw * np + iat] - u2));
+    if (J.has_j1)
+      ratio *= exp((double)(J.Vat[(size_t)iw * J.N + iat] - u1));
+    out[ivp] = ratio;
+  }
+}
+
 // grid = nw
 template<typename RT, bool STORE>
 __global__ void __launch_bounds__(JAS_TPB) jastrow_move_kernel(const JastrowDev<RT> J, const int iat)
@@ -490,14 +546,17 @@ __device__ __forceinline__ void jastrow_accept_body(const Group& g, const Jastro
     const bool listed = segcap * nwg <= JAS_LIST && N < 65536;
     // two elements per thread at a time: every load of a chunk is issued before the first store, so the HBM round trips
     // overlap instead of queueing behind the read-modify-write stores (which the compiler must assume may alias)
-    constexpr int CH = 2;
+#ifndef QMCB_JACC_CH
+#define QMCB_JACC_CH 1 // pairs per thread per trip in the accept (B200, a64: 1 -> 31.1 ms, 2 -> 33.3 ms per sweep)
+#endif
+    constexpr int CH = QMCB_JACC_CH;
     if (listed)
     {
       // pass 1: pairs whose old OR new distance is inside the cutoff (the others add exact zeros to every sum)
       unsigned short* seg = jl + wg * segcap;
       int cnt = 0;
       // (the position loads of up to three iterations are requested before the first is used)
-      constexpr int JB = 3;
+      constexpr int JB = QMCB_JB;
       for (int it0 = 0; it0 < iters; it0 += JB)
       {
         RT px[JB], py[JB], pz[JB];

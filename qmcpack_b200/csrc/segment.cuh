@@ -583,10 +583,13 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
       // ======================= gather phase =======================
       if (warp < SEG_NCONS / 32)
       {
-        T v[CPT], gx[CPT], gy[CPT], gz[CPT], hxx[CPT], hxy[CPT], hxz[CPT], hyy[CPT], hyz[CPT], hzz[CPT];
+        // value, gradient (lattice units) and the Laplacian ALREADY contracted with G G^T: the producer folds the six
+        // Hessian prefactors of every (i, j) with the metric into three numbers (A0, A1, A2 below), so a component costs
+        // five accumulators instead of ten -- at four CTAs per SM the kernel lives on 64 registers per thread
+        T v[CPT], gx[CPT], gy[CPT], gz[CPT], lp[CPT];
 #pragma unroll
         for (int e = 0; e < CPT; ++e)
-          v[e] = gx[e] = gy[e] = gz[e] = hxx[e] = hxy[e] = hxz[e] = hyy[e] = hyz[e] = hzz[e] = T(0);
+          v[e] = gx[e] = gy[e] = gz[e] = lp[e] = T(0);
         const int cfirst = tid * CPT;
         const int blk = cfirst / SEG_BOXW, loc = cfirst - blk * SEG_BOXW;
         // Jastrow sums at the proposed position while the first slabs are in flight (every warp derives the proposal
@@ -603,7 +606,11 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           SEG_STAMP(1, 0); // Jastrow sums
         }
         T cz[4], dcz[4], d2cz[4];
+#ifdef QMCB_SEG_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int qq = 0; qq < SEG_NQ; ++qq)
         {
           const unsigned g    = gq + qq;
@@ -624,7 +631,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
             T pa[4], pb[4];
             load4<T>(hdr + (i * 4 + j0 + jj) * 8, pa);
             load4<T>(hdr + (i * 4 + j0 + jj) * 8 + 4, pb);
-            const T pre20 = pa[0], pre10 = pa[1], pre11 = pa[2], pre01 = pa[3], pre02 = pb[0], pre00 = pb[1];
+            const T pre00 = pa[0], pre10 = pa[1], pre01 = pa[2], A0 = pa[3], A1 = pb[0], A2 = pb[1];
             const T* p0 = sp + jj * 4 * SEG_BOXW;
             T k0[CPT], k1[CPT], k2[CPT], k3[CPT];
             SegVec<T, CPT>::load(p0, k0);
@@ -637,12 +644,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
               const T sum0 = cz[0] * k0[e] + cz[1] * k1[e] + cz[2] * k2[e] + cz[3] * k3[e];
               const T sum1 = dcz[0] * k0[e] + dcz[1] * k1[e] + dcz[2] * k2[e] + dcz[3] * k3[e];
               const T sum2 = d2cz[0] * k0[e] + d2cz[1] * k1[e] + d2cz[2] * k2[e] + d2cz[3] * k3[e];
-              hxx[e] += pre20 * sum0;
-              hxy[e] += pre11 * sum0;
-              hxz[e] += pre10 * sum1;
-              hyy[e] += pre02 * sum0;
-              hyz[e] += pre01 * sum1;
-              hzz[e] += pre00 * sum2;
+              lp[e] += A0 * sum0 + A1 * sum1 + A2 * sum2;
               gx[e] += pre10 * sum0;
               gy[e] += pre01 * sum0;
               gz[e] += pre00 * sum1;
@@ -666,15 +668,11 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           if (mo < n)
           {
             const T g0 = gx[e] * dxInv, g1 = gy[e] * dyInv, g2 = gz[e] * dzInv;
-            const T h00 = hxx[e] * (dxInv * dxInv), h11 = hyy[e] * (dyInv * dyInv), h22 = hzz[e] * (dzInv * dzInv);
-            const T h01 = hxy[e] * (dxInv * dyInv), h02 = hxz[e] * (dxInv * dzInv), h12 = hyz[e] * (dyInv * dzInv);
             const T psi = sgn * v[e];
             const T dx  = sgn * (S.G[0] * g0 + S.G[1] * g1 + S.G[2] * g2);
             const T dy  = sgn * (S.G[3] * g0 + S.G[4] * g1 + S.G[5] * g2);
             const T dz  = sgn * (S.G[6] * g0 + S.G[7] * g1 + S.G[8] * g2);
-            const T lap = sgn *
-                (h00 * S.symGG[0] + h01 * S.symGG[1] + h02 * S.symGG[2] + h11 * S.symGG[3] + h12 * S.symGG[4] +
-                 h22 * S.symGG[5]);
+            const T lap = sgn * lp[e];
             phi[mo]         = psi;
             phi[n + mo]     = dx;
             phi[2 * n + mo] = dy;
@@ -727,13 +725,18 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           const int i = lane >> 2, j = lane & 3;
           const T ai = scratch[i], dai = scratch[4 + i], d2ai = scratch[8 + i];
           const T bj = scratch[12 + j], dbj = scratch[16 + j], d2bj = scratch[20 + j];
+          // metric-weighted Hessian prefactors: lap = sum_ab h_ab GGt_ab with h_ab scaled by the grid spacings
+          // (SplineR2R.cpp:349-373; SymTrace, contraction_helper.hpp:47-48)
+          const T dxI = (T)S.delta_inv[0], dyI = (T)S.delta_inv[1], dzI = (T)S.delta_inv[2];
+          const T wxx = S.symGG[0] * (dxI * dxI), wxy = S.symGG[1] * (dxI * dyI), wxz = S.symGG[2] * (dxI * dzI);
+          const T wyy = S.symGG[3] * (dyI * dyI), wyz = S.symGG[4] * (dyI * dzI), wzz = S.symGG[5] * (dzI * dzI);
           T* hd = hdr + lane * 8;
-          hd[0] = d2ai * bj; // pre20
-          hd[1] = dai * bj;  // pre10
-          hd[2] = dai * dbj; // pre11
-          hd[3] = ai * dbj;  // pre01
-          hd[4] = ai * d2bj; // pre02
-          hd[5] = ai * bj;   // pre00
+          hd[0] = ai * bj;                                              // pre00: value, d/dz
+          hd[1] = dai * bj;                                             // pre10: d/dx, with sum1: d2/dxdz
+          hd[2] = ai * dbj;                                             // pre01: d/dy, with sum1: d2/dydz
+          hd[3] = (d2ai * bj) * wxx + (dai * dbj) * wxy + (ai * d2bj) * wyy; // A0 (x sum0)
+          hd[4] = (dai * bj) * wxz + (ai * dbj) * wyz;                  // A1 (x sum1)
+          hd[5] = (ai * bj) * wzz;                                      // A2 (x sum2)
           hd[6] = T(0);
           hd[7] = T(0);
         }
@@ -770,6 +773,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         // move's preparation reads for the first time since the last flush (the stale inverse row, the gradient rows of
         // that electron, its Gaussians) are pulled into L2 now -- their addresses are known a whole move ahead, and a
         // cold DRAM access inside the boundary chain costs microseconds while the stencil stream keeps HBM busy
+#ifdef QMCB_SEG_PREFETCH // (measured: no gain, slightly slower)
         if (part2)
         {
           const char* ar = reinterpret_cast<const char*>(D.Ainv + ((size_t)iw * n + row + 1) * D.lda);
@@ -783,6 +787,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           if (lane == 0)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(Dr.deltas + ((size_t)(iat + 1) * Dr.nw + iw) * 3));
         }
+#endif
         if constexpr (!HD)
           mpre = seg_metro_prefetch<T>(Dr, J, R, SR, iw, iat, sg);
         SEG_STAMP(8, 224); // Metropolis prefetch incl. the wait for the previous move's total
@@ -926,13 +931,12 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         // of V last -- those come from the staged copy, which lands while the U rows are read.
         constexpr int NV4 = (CPT * SEG_BOXW / 4 + 31) / 32;
         const V4<T> zero4{T(0), T(0), T(0), T(0)};
-        V4<T> xr[NV4], pr[NV4];
+        V4<T> xr[NV4];
 #pragma unroll
         for (int i = 0; i < NV4; ++i)
         {
           const int j4 = 4 * (lane + 32 * i);
           xr[i] = (part2 && j4 < n) ? ld4(x + j4) : zero4;
-          pr[i] = (part1 && j4 < n) ? ld4(phi + j4) : zero4;
         }
         auto two_rows = [&](const T* r0, const T* r1, const bool two, const V4<T> (&vec)[NV4], T& s0, T& s1) {
           V4<T> a0[NV4], a1[NV4];
@@ -970,6 +974,13 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         }
         if (cA > 0)
         {
+          // (the slice of phi replaces the slice of x in the same registers)
+#pragma unroll
+          for (int i = 0; i < NV4; ++i)
+          {
+            const int j4 = 4 * (lane + 32 * i);
+            xr[i] = j4 < n ? ld4(phi + j4) : zero4;
+          }
           if (nvs > 0)
             ptx::mbar_wait(v_bar, v_phase);
           // (the warps take the V rows in reverse order of the U rows so that the work evens out)
@@ -980,7 +991,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
             const T* r0    = a0i < nvs ? vs + (size_t)a0i * n : Va + (size_t)a0i * n;
             const T* r1    = two ? (a1i < nvs ? vs + (size_t)a1i * n : Va + (size_t)a1i * n) : r0;
             T s0, s1;
-            two_rows(r0, r1, two, pr, s0, s1);
+            two_rows(r0, r1, two, xr, s0, s1);
             if (lane == 0)
             {
               pA[a0i] = -s0;
@@ -1147,10 +1158,14 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         if (v_bulk)
         {
           // four consecutive columns per thread, 16-byte accesses
+#ifndef QMCB_SEG_VTW_UNROLL
+#define QMCB_SEG_VTW_UNROLL 1 // (B200, a64: 1 -> 32.7 ms, 4 -> 33.3 ms per sweep: the kernel is register-bound at 64)
+#endif
+          constexpr int VTW_UNROLL = QMCB_SEG_VTW_UNROLL;
           for (int j4 = 4 * tid; j4 < n; j4 += 4 * gd.n)
           {
             V4<T> sacc{T(0), T(0), T(0), T(0)};
-#pragma unroll 4
+#pragma unroll(VTW_UNROLL)
             for (int a = 0; a < cS; ++a)
             {
               const T wa    = w[a];

@@ -428,6 +428,15 @@ class OracleVMC:
         self.o._chk(self.o.lib.orc_vmc_probe_move(self.h, C.c_int(iw), C.c_int(iat), _p(d), _p(r), _p(go), _p(gn)))
         return complex(r[0], r[1]), go[0::2] + 1j * go[1::2], gn[0::2] + 1j * gn[1::2]
 
+    def evaluate_ratios(self, iw, ref, r_vp, ct=0):
+        """TrialWaveFunction::mw_evaluateRatios of walker iw: psi(electron ref at r_vp[k]) / psi, complex [nk];
+        ct 0 ALL, 1 FERMIONIC, 2 NONFERMIONIC"""
+        r = _np(r_vp, np.float64).reshape(-1, 3)
+        out = np.zeros(2 * len(r))
+        self.o._chk(self.o.lib.orc_vmc_evaluate_ratios(self.h, C.c_int(iw), C.c_int(ref), C.c_int(len(r)), _p(r), C.c_int(ct),
+                                                       _p(out)))
+        return out[0::2] + 1j * out[1::2]
+
     def sweep(self, nsteps=1, log_accept=False):
         log = np.zeros((nsteps, self.N, self.nw), np.uint8) if log_accept else None
         sec = C.c_double(0)
