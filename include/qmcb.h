@@ -128,6 +128,23 @@ int qmcb_twf_mw_calc_ratio_grad(qmcb_crowd* c, int iat, double* ratios_host, dou
 int qmcb_twf_mw_accept_reject(qmcb_crowd* c, int iat, const uint8_t* accepted_host, int safe_to_delay);
 /* TrialWaveFunction::mw_completeUpdates (:833): flush pending delayed updates of both determinants.               */
 int qmcb_twf_mw_complete_updates(qmcb_crowd* c);
+/* TrialWaveFunction::mw_calcRatio (TrialWaveFunction.cpp:494-510; DiracDeterminantBatched::mw_calcRatio,
+ * Fermion/DiracDeterminantBatched.cpp:742-789): the ratio of the move proposed by qmcb_ps_mw_make_move WITHOUT gradients
+ * (sweeps without drift).  Only orbital values are gathered; an accept that follows leaves the determinant's gradient and
+ * Laplacian rows stale (the reference's ORB_PBYP_RATIO mode) and they are re-evaluated from the committed positions when
+ * next needed (qmcb_twf_mw_evaluate_gl, qmcb_twf_mw_eval_grad, a device sweep).  ratios_host [nw] doubles (x2 complex).     */
+int qmcb_twf_mw_calc_ratio(qmcb_crowd* c, int iat, double* ratios_host);
+/* TrialWaveFunction::mw_evaluateRatios (TrialWaveFunction.cpp:1079-1110) for the non-local pseudopotential: nvp virtual
+ * positions; position i belongs to walker walker[i] and stands for its electron ref_ptcl[i] (VirtualParticleSet::refPtcl).
+ * ratios_host[i] = product over the selected components of psi(electron at r_vp[i]) / psi: determinants through
+ * DiracDeterminantBatched::mw_evaluateRatios (DiracDeterminantBatched.cpp:812-848; V-only spline gather dotted with the
+ * row of psiMinv), Jastrows through TwoBodyJastrow::mw_evaluateRatios (Jastrow/TwoBodyJastrow.cpp:174-210,
+ * BsplineFunctor::mw_evaluateV, Jastrow/BsplineFunctor.cpp:135-200) and J1OrbitalSoA::evaluateRatios.
+ * compute_type: 0 ALL, 1 FERMIONIC, 2 NONFERMIONIC (TrialWaveFunction::ComputeType).  Pending delayed updates are applied
+ * first (the reference evaluates the pseudopotential after mw_completeUpdates).  r_vp_host [nvp][3] Cartesian doubles;
+ * ratios_host [nvp] doubles (x2 complex).                                                                              */
+int qmcb_twf_mw_evaluate_ratios(qmcb_crowd* c, int nvp, const int* walker, const int* ref_ptcl, const double* r_vp_host,
+                                int compute_type, double* ratios_host);
 /* TrialWaveFunction::mw_evaluateGL (:869), fromscratch = false: G_host [nw][N][3], L_host [nw][N] (either may be
  * NULL), logpsi_host [nw] (real part of log psi), ke_host [nw] = -1/2 sum(L + G.G) (BareKineticEnergy).            */
 int qmcb_twf_mw_evaluate_gl(qmcb_crowd* c, double* G_host, double* L_host, double* logpsi_host, double* ke_host);

@@ -61,7 +61,8 @@ SYMBOLS = [
     "qmcb_det_mw_complete_updates", "qmcb_det_mw_recompute_from_matrices", "qmcb_det_set_phi_vgl",
     "qmcb_det_mw_ratio_grad_from_phi", "qmcb_det_delay_count", "qmcb_det_time_update_inv_mat",
     "qmcb_dtaa_get_temp_rows", "qmcb_j2_mw_ratio_grad", "qmcb_j2_mw_accept_reject", "qmcb_j2_get_state",
-    "qmcb_vmc_init", "qmcb_vmc_sweep", "qmcb_vmc_sweep_async", "qmcb_vmc_counts", "qmcb_vmc_sweep_kernel", "qmcb_vmc_profile_sweep", "qmcb_crowd_host_kernel", "qmcb_crowd_stream",
+    "qmcb_vmc_init", "qmcb_vmc_sweep", "qmcb_vmc_sweep_async", "qmcb_vmc_counts", "qmcb_vmc_sweep_kernel", "qmcb_vmc_profile_sweep", "qmcb_crowd_host_kernel", "qmcb_twf_mw_calc_ratio",
+    "qmcb_twf_mw_evaluate_ratios", "qmcb_crowd_stream",
     "qmcb_dmc_get_rr", "qmcb_crowd_walker_bytes", "qmcb_crowd_pack_walker", "qmcb_crowd_unpack_walker",
     "qmcb_crowd_copy_walker", "qmcb_crowd_set_num_walkers", "qmcb_crowd_num_walkers", "qmcb_crowd_capacity",
 ]
@@ -331,6 +332,22 @@ class Crowd:
         lp, ke = np.zeros(self.nw), np.zeros(self.nw)
         _chk(lib().qmcb_twf_mw_evaluate_gl(self.h, _p(G), _p(L), _p(lp), _p(ke)))
         return lp, ke, G, L
+
+    def mw_calcRatio(self, iat):
+        """TrialWaveFunction::mw_calcRatio: ratio of the proposed move without gradients"""
+        r = np.zeros(self.nw, self.P)
+        _chk(lib().qmcb_twf_mw_calc_ratio(self.h, C.c_int(iat), _p(r)))
+        return r
+
+    def mw_evaluateRatios(self, walker, ref_ptcl, r_vp, compute_type=0):
+        """TrialWaveFunction::mw_evaluateRatios at virtual positions (NLPP quadrature points): walker [nvp], ref_ptcl [nvp],
+        r_vp [nvp][3]; compute_type 0 ALL, 1 FERMIONIC, 2 NONFERMIONIC"""
+        wk = np.ascontiguousarray(walker, np.int32)
+        rf = np.ascontiguousarray(ref_ptcl, np.int32)
+        r = np.ascontiguousarray(r_vp, np.float64).reshape(-1, 3)
+        out = np.zeros(len(wk), self.P)
+        _chk(lib().qmcb_twf_mw_evaluate_ratios(self.h, C.c_int(len(wk)), _p(wk), _p(rf), _p(r), C.c_int(compute_type), _p(out)))
+        return out
 
     def mw_block_estimators(self):
         """(log psi, kinetic energy) per walker without shipping G and L to the host: what a block estimator needs"""

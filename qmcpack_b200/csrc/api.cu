@@ -348,6 +348,11 @@ int qmcb_ps_mw_make_move(qmcb_crowd* c, int iat, const double* d) { CROWD_CALL(p
 int qmcb_twf_mw_calc_ratio_grad(qmcb_crowd* c, int iat, double* r, double* g) { CROWD_CALL(twf_calc_ratio_grad(iat, r, g)); }
 int qmcb_twf_mw_accept_reject(qmcb_crowd* c, int iat, const uint8_t* a, int safe) { CROWD_CALL(twf_accept_reject(iat, a, safe)); }
 int qmcb_twf_mw_complete_updates(qmcb_crowd* c) { CROWD_CALL(twf_complete_updates()); }
+int qmcb_twf_mw_calc_ratio(qmcb_crowd* c, int iat, double* ratios) { CROWD_CALL(twf_calc_ratio(iat, ratios)); }
+int qmcb_twf_mw_evaluate_ratios(qmcb_crowd* c, int nvp, const int* walker, const int* ref, const double* r_vp, int ct, double* ratios)
+{
+  CROWD_CALL(twf_evaluate_ratios(nvp, walker, ref, r_vp, ct, ratios));
+}
 int qmcb_twf_mw_evaluate_gl(qmcb_crowd* c, double* G, double* L, double* lp, double* ke) { CROWD_CALL(twf_evaluate_gl(G, L, lp, ke)); }
 int qmcb_det_mw_eval_grad(qmcb_crowd* c, int spin, int row, void* g) { CROWD_CALL(det_eval_grad(spin, row, g)); }
 int qmcb_det_mw_get_inv_row(qmcb_crowd* c, int spin, int row, const void** dev, size_t* ld, void* host)

@@ -1701,6 +1701,7 @@ struct Crowd : CrowdBase
   {
     QMCB_NVTX("TrialWaveFunction::mw_evaluateLog");
     flush_pending();
+    gl_stale[0] = gl_stale[1] = false;
     for (int spin = 0; spin < 2; ++spin)
     {
       const int n = nel[spin];
@@ -1737,6 +1738,11 @@ struct Crowd : CrowdBase
   {
     QMCB_NVTX("TrialWaveFunction::mw_evalGrad");
     check_iat(iat);
+    if (gl_stale[0] || gl_stale[1])
+    {
+      flush_pending();
+      refresh_stale_gl();
+    }
     if (hd_eval_grad(iat, grads))
       return;
     // [accept of the previous electron, if one is pending] + inverse row + component-summed gradient: one launch
@@ -1828,6 +1834,10 @@ struct Crowd : CrowdBase
     if (hd_accept_reject(iat, acc, safe_to_delay))
       return;
     flush_pending();
+    pending_value_only = value_only_move;
+    if (value_only_move)
+      gl_stale[spin_of(iat)] = true;
+    value_only_move = false;
     stage_flags(acc);
     // deferred: applied together with whatever the driver asks next (normally the gradient of the next electron);
     // asynchronous like the reference's mw_accept_rejectMove ("this call may go asynchronous", TwoBodyJastrow.cpp:661)
@@ -1851,6 +1861,7 @@ struct Crowd : CrowdBase
   {
     QMCB_NVTX("TrialWaveFunction::mw_evaluateGL");
     twf_complete_updates();
+    refresh_stale_gl();
     QMCB_CUDA(cudaMemsetAsync(Gd.p, 0, Gd.bytes(), st));
     QMCB_CUDA(cudaMemsetAsync(Ld.p, 0, Ld.bytes(), st));
     for (int spin = 0; spin < 2; ++spin)
@@ -1899,6 +1910,129 @@ struct Crowd : CrowdBase
       if (logpsi)
         logpsi[iw] = l0[2 * iw] + l1[2 * iw] + lj2[iw] + lj1[iw];
     }
+  }
+
+  // ---------------------------------------------------------------- ratios at virtual positions (NLPP quadrature)
+  // TrialWaveFunction::mw_evaluateRatios (TrialWaveFunction.cpp:1079-1110): the product over the selected components
+  // of psi(R with electron ref[i] of walker wk[i] at r_vp[i]) / psi(R).  Determinants: DiracDeterminantBatched::
+  // mw_evaluateRatios (DiracDeterminantBatched.cpp:812-848) -> SPOSet::mw_evaluateDetRatios with the rows of psiMinv;
+  // Jastrows: TwoBodyJastrow::mw_evaluateRatios (TwoBodyJastrow.cpp:174-210), J1OrbitalSoA::evaluateRatios.
+  void twf_evaluate_ratios(int nvp, const int* wk, const int* ref, const double* r_vp, int ct, double* ratios) override
+  {
+    QMCB_NVTX("TrialWaveFunction::mw_evaluateRatios");
+    if (nvp < 0 || ct < 0 || ct > 2)
+      throw std::runtime_error("qmcb_twf_mw_evaluate_ratios: bad arguments");
+    twf_complete_updates(); // the reference evaluates the non-local pseudopotential after completeUpdates: psiMinv is current
+    if (nvp == 0)
+      return;
+    for (int i = 0; i < nvp; ++i)
+      if (wk[i] < 0 || wk[i] >= nw || ref[i] < 0 || ref[i] >= N)
+        throw std::runtime_error("qmcb_twf_mw_evaluate_ratios: walker or reference particle index out of range");
+    std::vector<DV> det_r(nvp, DV(1.0));
+    if (ct != 2)
+      for (int spin = 0; spin < 2; ++spin)
+      {
+        const int n = nel[spin];
+        std::vector<int> sel, rowid;
+        std::vector<T> pos;
+        for (int i = 0; i < nvp; ++i)
+          if (spin_of(ref[i]) == spin)
+          {
+            sel.push_back(i);
+            rowid.push_back(wk[i] * n + (ref[i] - first[spin]));
+            for (int d = 0; d < 3; ++d)
+              pos.push_back((T)r_vp[3 * (size_t)i + d]);
+          }
+        if (sel.empty())
+          continue;
+        const int ns = (int)sel.size(), parts = spo[spin]->rg_parts();
+        DevBuf<T> pos_d;
+        DevBuf<int> row_d;
+        DevBuf<V> rg_d;
+        pos_d.alloc(pos.size(), false);
+        row_d.alloc(ns, false);
+        rg_d.alloc((size_t)ns * parts * 4);
+        QMCB_CUDA(cudaMemcpyAsync(pos_d.p, pos.data(), pos.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+        QMCB_CUDA(cudaMemcpyAsync(row_d.p, rowid.data(), ns * sizeof(int), cudaMemcpyHostToDevice, st));
+        spo[spin]->evaluate_dev(MODE_V, ns, pos_d.p, Ainv[spin].p, lda[spin], row_d.p, nullptr, rg_d.p, st);
+        g_launch_count.fetch_add(0);
+        std::vector<V> parts_h((size_t)ns * parts * 4);
+        QMCB_CUDA(cudaMemcpyAsync(parts_h.data(), rg_d.p, parts_h.size() * sizeof(V), cudaMemcpyDeviceToHost, st));
+        sync();
+        for (int q = 0; q < ns; ++q)
+        {
+          V acc4[4];
+          sum_rg_parts<V, 4>(parts_h.data(), q, parts, acc4);
+          det_r[sel[q]] = to_dbl(acc4[0]);
+        }
+      }
+    std::vector<double> jas_r(nvp, 1.0);
+    if (ct != 1 && (jas.has_j2 || jas.has_j1))
+    {
+      std::vector<T> pos(3 * (size_t)nvp);
+      for (size_t i = 0; i < pos.size(); ++i)
+        pos[i] = (T)r_vp[i];
+      DevBuf<T> pos_d;
+      DevBuf<int> wk_d, ref_d;
+      DevBuf<double> out_d;
+      pos_d.alloc(pos.size(), false);
+      wk_d.alloc(nvp, false);
+      ref_d.alloc(nvp, false);
+      out_d.alloc(nvp, false);
+      QMCB_CUDA(cudaMemcpyAsync(pos_d.p, pos.data(), pos.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+      QMCB_CUDA(cudaMemcpyAsync(wk_d.p, wk, nvp * sizeof(int), cudaMemcpyHostToDevice, st));
+      QMCB_CUDA(cudaMemcpyAsync(ref_d.p, ref, nvp * sizeof(int), cudaMemcpyHostToDevice, st));
+      jastrow_vp_ratio_kernel<T><<<blocks(nvp, 4), 128, 0, st>>>(jas, nvp, wk_d.p, ref_d.p, pos_d.p, out_d.p);
+      QMCB_LAUNCH_CHECK();
+      QMCB_CUDA(cudaMemcpyAsync(jas_r.data(), out_d.p, nvp * sizeof(double), cudaMemcpyDeviceToHost, st));
+      sync();
+    }
+    DV* out = reinterpret_cast<DV*>(ratios);
+    for (int i = 0; i < nvp; ++i)
+      out[i] = det_r[i] * DV(jas_r[i]);
+  }
+
+  // ---------------------------------------------------------------- ratio-only moves (no drift)
+  // TrialWaveFunction::mw_calcRatio (TrialWaveFunction.cpp:494-510) -> DiracDeterminantBatched::mw_calcRatio
+  // (DiracDeterminantBatched.cpp:742-789).  The reference "temporarily" still evaluates V, G and L there; here the
+  // orbital VALUES are gathered alone.  An accept that follows stores the orbital row only, so the gradient / Laplacian
+  // rows of the determinant go stale (UpdateMode ORB_PBYP_RATIO) and are re-evaluated from the committed positions the
+  // next time they are needed, exactly as mw_evaluateGL does in that mode (DiracDeterminantBatched.cpp:630-678).
+  bool gl_stale[2] = {false, false};
+  void twf_calc_ratio(int iat, double* ratios) override
+  {
+    QMCB_NVTX("TrialWaveFunction::mw_calcRatio");
+    check_iat(iat);
+    hd_abort();
+    apply_pending(-1, nullptr);
+    const int spin = spin_of(iat), row = iat - first[spin];
+    ensure_row(spin, row);
+    launch_spline(spin, MODE_V, invRow[spin].p, det[spin].n, phi_vgl.p, rg.p, st);
+    join_jastrow();
+    twf_ratio_kernel<T, V><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, rg.p, rg_nparts, h_d.p, h_t.p); // (pinned host)
+    QMCB_LAUNCH_CHECK();
+    spin_sync();
+    std::memcpy(ratios, h_d.p, (size_t)nw * sizeof(DV));
+    guard_ratios(ratios, "TWF::mw_calcRatio");
+    value_only_move = true;
+  }
+  bool value_only_move = false; // the orbital rows of the proposed move hold values only
+  void refresh_stale_gl()
+  {
+    for (int spin = 0; spin < 2; ++spin)
+      if (gl_stale[spin])
+      {
+        const int n = nel[spin];
+        for (int e = 0; e < n; ++e)
+        {
+          make_move_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, first[spin] + e, displ_zero());
+          QMCB_LAUNCH_CHECK();
+          launch_spline(spin, MODE_VGL, nullptr, 0, phi_vgl.p, nullptr, st);
+          det_scatter_gl_kernel<V><<<dim3(blocks(n, 128), nw), 128, 0, st>>>(det[spin], e, phi_vgl.p);
+          QMCB_LAUNCH_CHECK();
+        }
+        gl_stale[spin] = false;
+      }
   }
 
   // ---------------------------------------------------------------- component level: DT rows + J2
@@ -2490,6 +2624,7 @@ struct Crowd : CrowdBase
   // ---- host-driven mode: the accept of an electron is deferred until the next call tells what follows it, so that
   // accept(iat) + evalGrad(iat+1) -- two consecutive calls of the reference's driver loop -- become ONE launch
   int pending_iat = -1;
+  bool pending_value_only = false;
   DriverDev<T> drv_host{};
   void apply_pending(int iat_next, V* twf_grads_out)
   {
@@ -2502,6 +2637,9 @@ struct Crowd : CrowdBase
     const unsigned char* flags = pending_flags ? pending_flags : accepted.p;
     const int prev = pending_iat, ig = spin_of(prev);
     pending_iat    = -1;
+    DriverDev<T> drv_host = this->drv_host; // (per-launch copy: the value-only flag belongs to this accept)
+    drv_host.value_only   = pending_value_only ? 1 : 0;
+    pending_value_only    = false;
     const bool split = iat_next < 0 || spin_of(iat_next) != ig || delay_count[ig] + 1 == k;
     if (!split)
     {
@@ -2616,6 +2754,7 @@ struct Crowd : CrowdBase
   {
     if (delay_count[0] != 0 || delay_count[1] != 0)
       twf_complete_updates();
+    refresh_stale_gl();
     if (!use_graph)
     {
       enqueue_sweep(log_accept);
@@ -2765,6 +2904,7 @@ struct Crowd : CrowdBase
   void settle()
   {
     flush_pending();
+    refresh_stale_gl();
     if (delay_count[0] != 0 || delay_count[1] != 0)
       twf_complete_updates();
     invrow_id[0] = invrow_id[1] = -1;

@@ -59,6 +59,8 @@ struct CrowdBase
   virtual void twf_calc_ratio_grad(int iat, double* ratios, double* grads)                                  = 0;
   virtual void twf_accept_reject(int iat, const uint8_t* acc, int safe_to_delay)                            = 0;
   virtual void twf_complete_updates()                                                                       = 0;
+  virtual void twf_evaluate_ratios(int nvp, const int* walker, const int* ref, const double* r_vp, int ct, double* ratios) = 0;
+  virtual void twf_calc_ratio(int iat, double* ratios)                                                      = 0;
   virtual void twf_evaluate_gl(double* G, double* L, double* logpsi, double* ke)                            = 0;
   virtual void det_eval_grad(int spin, int row, void* grads)                                                = 0;
   virtual void det_get_inv_row(int spin, int row, const void** dev, size_t* ld, void* host)                 = 0;
