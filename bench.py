@@ -62,6 +62,11 @@ def parse():
     ap.add_argument("--sweep-kernel", type=int, default=0, help="0 automatic, 1 two-kernel path, 2 walker-segment kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fp64", action="store_true", help="skip the FP64 peak / full-precision flush objects")
+    ap.add_argument("--dmc", action="store_true",
+                    help="headline = batched DMC generations (BASELINE config 5: device move loop + block of C++ WalkerControl::"
+                         "branch with the NCCL all-reduce and the packed-walker exchange inside the timed region)")
+    ap.add_argument("--no-dmc", action="store_true", help="skip the short DMC object of the default (VMC) line")
+    ap.add_argument("--dmc-tau", type=float, default=0.002)
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -208,6 +213,53 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+def run_dmc_generations(api, torch, dist, s, spo, k, N, nw, rank, local_rank, world, tau, generations, warm):
+    """Batched DMC on one crowd per rank: qmcb_vmc_sweep(dmc = 1) + the C++ DMC layer (csrc/dmc_host.cpp: branch weights,
+    WalkerControl::branch, computeCurData all-reduce over NCCL, swapWalkersSimple with packed device-resident walkers over
+    ncclSend / ncclRecv).  The local energy of the harness is the kinetic energy (the Hamiltonian is out of scope), so the
+    numbers characterise the machinery, not physics.  Returns a dict; the timed region covers `generations` generations
+    with every collective and every walker transfer inside it."""
+    from qmcpack_b200 import workload, sharding
+    cap = int(nw * 1.5) + 8
+    R = workload.initial_positions(s, cap, seed=11 + 100003 * rank)
+    cr = api.Crowd(s, nw=cap, delay_rank=k, spo=spo)
+    cr.set_positions(R)
+    cr.mw_recompute()
+    cr.vmc_init(tau=tau, use_drift=True, seed=3000 + 7919 * rank, use_cuda_graph=True, dmc=True)
+    cr.set_num_walkers(nw)
+    comm = api.TorchComm(dist, cr.walker_bytes, torch.device("cuda", local_rank)) if (dist is not None and world > 1) else None
+    drv = api.DMCDriver(cr, tau, world * nw, branch_seed=77 + rank, comm=comm, warmup_steps=1 << 30)
+    it = 0
+    for _ in range(warm):
+        drv.step(it)
+        it += 1
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sent0 = comm.bytes_sent if comm else 0
+    moves, pops, sent, t0 = 0, [], 0, time.perf_counter()
+    for _ in range(generations):
+        local_before = cr.nw
+        ens = drv.step(it)
+        it += 1
+        moves += local_before * N
+        pops.append(int(ens["population"]))
+        sent += int(ens["walkers_sent"])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    dt_max = sharding.max_over_ranks(dt, dist, device="cuda")
+    tot = sharding.reduce_block_estimator([float(moves), float(sent), float(comm.bytes_sent - sent0 if comm else 0)], dist, device="cuda")
+    ke = cr.mw_block_estimators()[1]
+    out = {"value": float(tot[0]) / dt_max, "unit": UNIT, "generations": generations, "ms_per_generation": 1e3 * dt_max / generations,
+           "tau": tau, "target_walkers": world * nw, "population": pops, "e_trial": float(drv.history[-1]["e_trial"]),
+           "walker_messages": int(tot[1]), "nccl_p2p_bytes": int(tot[2]), "walker_bytes": int(cr.walker_bytes),
+           "finite": bool(np.isfinite(ke).all()),
+           "path": "qmcb_vmc_sweep(dmc = 1) + qmcb_dmc_step (C++ WalkerControl::branch; all-reduce of curData and ncclSend / "
+                   "ncclRecv of packed device-resident walkers through torch.distributed inside the timed region)"}
+    del drv, cr
+    return out
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
     from qmcpack_b200 import api, workload, build
@@ -482,6 +534,16 @@ def run_b200(args, rank, local_rank, world):
         e2e["device_driver"] = e2e_dd
         del drv, crowds
 
+    # ---------------- batched DMC generations (BASELINE config 5 machinery at this run's shape): population control with the
+    # all-reduce and the walker exchange inside the timed region
+    dmc_obj = None
+    if args.dmc or not args.no_dmc:
+        try:
+            dmc_obj = run_dmc_generations(api, torch, dist, s, spo, k, N, nw if args.dmc else min(nw, 128), rank, local_rank, world,
+                                          args.dmc_tau, generations=max(3, args.steps if args.dmc else 3), warm=2)
+        except Exception as ex:
+            dmc_obj = {"error": str(ex)}
+
     # ---------------- CPU baseline beside it (rank 0, single-GPU run only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -506,7 +568,15 @@ def run_b200(args, rank, local_rank, world):
                        "timed_region": "one VMC block: %d sweeps + block estimator + all-reduce over ranks" % args.steps},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "flush": flush, "flush_fp64": flush_fp64, "fp64_peak": fp64_peak, "spline_gather": spline_gather, "cpu_baseline": cpu,
+            "dmc": dmc_obj,
         }
+        if args.dmc and dmc_obj and "value" in dmc_obj:
+            # --dmc: the DMC generations are the headline; the VMC sweep numbers stay in the line as `vmc`
+            line["vmc"] = {"value": value, "ms_per_step": ms_max / args.steps}
+            line["metric"] = args.config + " DMC electron-moves/s"
+            line["value"] = dmc_obj["value"]
+            line["ms_per_step"] = dmc_obj["ms_per_generation"]
+            line["config"]["timed_region"] = "%d DMC generations (device move loop, local energies, branch with all-reduce and walker exchange)" % dmc_obj["generations"]
         print(json.dumps(line))
     if dist:
         dist.barrier()
