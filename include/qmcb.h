@@ -75,6 +75,14 @@ int qmcb_spline_mw_evaluate_det_ratios(qmcb_spline* h, int nvp, const double* r_
 int qmcb_spline_mw_vgl_ratio_grads_dev(qmcb_spline* h, int nw, const void* r_dev, const void* invrow_dev, size_t ld_inv,
                                        void* phi_vgl_dev, void* rg_parts_dev, void* stream);
 int qmcb_spline_rg_parts(const qmcb_spline* h);
+/* the contract of SPOSet::mw_evaluateVGLandDetRatioGrads for an offload SPOSet as DiracDeterminantBatched::mw_ratioGrad
+ * drives it (DiracDeterminantBatched.cpp:334-346: isOMPoffload() == true): positions from the host (P_list[iw].activeR),
+ * the inverse rows as DEVICE memory [nw][ld_inv] (mw_getInvRow(..., on_host = false)), phi_vgl_dev [5][nw][n_orb] = the
+ * device copy of phi_vgl_v, current on return (may be NULL), ratios_host [nw] and grads_host [nw][3] VT on the host (grads
+ * already divided by the ratio, SPOSet.cpp:171).  Synchronises `stream` (the crowd's queue) before returning.           */
+int qmcb_spline_mw_evaluate_vgl_ratio_grads_offload(qmcb_spline* h, int nw, const double* r_host, const void* invrow_dev,
+                                                    size_t ld_inv, void* phi_vgl_dev, void* ratios_host, void* grads_host,
+                                                    void* stream);
 
 /* ---- crowd: walker batch + trial wavefunction state ---------------------------------------------- */
 typedef struct qmcb_system

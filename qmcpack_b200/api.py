@@ -52,7 +52,7 @@ SYMBOLS = [
     "qmcb_init", "qmcb_last_error", "qmcb_device_count", "qmcb_aligned_size", "qmcb_kernel_launch_count",
     "qmcb_spline_create", "qmcb_spline_destroy", "qmcb_spline_table_bytes", "qmcb_spline_mw_evaluate_value",
     "qmcb_spline_mw_evaluate_vgl", "qmcb_spline_mw_evaluate_vgl_ratio_grads", "qmcb_spline_mw_evaluate_det_ratios",
-    "qmcb_spline_mw_vgl_ratio_grads_dev", "qmcb_spline_rg_parts",
+    "qmcb_spline_mw_vgl_ratio_grads_dev", "qmcb_spline_rg_parts", "qmcb_spline_mw_evaluate_vgl_ratio_grads_offload",
     "qmcb_crowd_create", "qmcb_crowd_destroy", "qmcb_crowd_sync", "qmcb_crowd_device_bytes", "qmcb_crowd_is_complex",
     "qmcb_crowd_set_positions", "qmcb_crowd_get_positions",
     "qmcb_twf_mw_recompute", "qmcb_twf_mw_eval_grad", "qmcb_ps_mw_make_move", "qmcb_twf_mw_calc_ratio_grad",
@@ -100,6 +100,7 @@ def lib():
         L.qmcb_spline_mw_evaluate_vgl_ratio_grads.argtypes = [vp, C.c_int, vp, vp, C.c_size_t, vp, vp, vp]
         L.qmcb_spline_mw_evaluate_det_ratios.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_size_t, vp]
         L.qmcb_spline_mw_vgl_ratio_grads_dev.argtypes = [vp, C.c_int, vp, vp, C.c_size_t, vp, vp, vp]
+        L.qmcb_spline_mw_evaluate_vgl_ratio_grads_offload.argtypes = [vp, C.c_int, vp, vp, C.c_size_t, vp, vp, vp, vp]
         L.qmcb_crowd_create.argtypes = [C.POINTER(vp), C.POINTER(QmcbSystem), C.c_int]
         L.qmcb_det_mw_get_inv_row.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), vp]
         L.qmcb_host_vmc_last_error.restype = C.c_char_p
@@ -188,6 +189,19 @@ class SplineSPOSet:
         d2psi = np.zeros((nw, self.n_orb), self.vt)
         _chk(lib().qmcb_spline_mw_evaluate_vgl(self.h, C.c_int(nw), _p(r), _p(psi), _p(dpsi), _p(d2psi)))
         return psi, dpsi, d2psi
+
+    def mw_evaluateVGLandDetRatioGrads_offload(self, r, invrow_dev, ld, phi_vgl_dev=None, stream=None):
+        """SPOSet::mw_evaluateVGLandDetRatioGrads as an offload SPOSet is driven (DiracDeterminantBatched.cpp:334-346):
+        host positions, DEVICE inverse rows [nw][ld] (an address), optional device phi_vgl_v [5][nw][n_orb] (an address);
+        returns host ratios [nw] and grads [nw][3]."""
+        r = np.ascontiguousarray(r, np.float64)
+        nw = r.shape[0]
+        ratios = np.zeros(nw, self.vt)
+        grads = np.zeros((nw, 3), self.vt)
+        _chk(lib().qmcb_spline_mw_evaluate_vgl_ratio_grads_offload(self.h, nw, _p(r), vp(invrow_dev), ld,
+                                                                   vp(phi_vgl_dev) if phi_vgl_dev else None, _p(ratios),
+                                                                   _p(grads), vp(stream) if stream else None))
+        return ratios, grads
 
     def mw_evaluateVGLandDetRatioGrads(self, r, invrow):
         r = np.ascontiguousarray(r, np.float64)

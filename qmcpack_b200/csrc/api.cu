@@ -158,6 +158,44 @@ void spline_ratio_host(qmcb_spline* h, int nw, const double* r, const void* invr
         cdiv<T>(q + (1 + d) * vt, q, gr + ((size_t)iw * 3 + d) * vt, vt);
   }
 }
+
+// the reference's contract for an offload SPOSet (SPOSet.h:346-352 with isOMPoffload() == true): positions from the host,
+// inverse rows and phi_vgl_v in device memory, ratios and gradients back on the host
+template<typename T>
+void spline_ratio_offload(qmcb_spline* h, int nw, const double* r, const void* invrow_dev, size_t ld, void* phi_dev,
+                          void* ratios, void* grads, cudaStream_t st)
+{
+  SplineSPOBase& S = *h->impl;
+  const int vt = S.vt_per_orb(), np = S.rg_parts(), nred = 4 * vt;
+  Stage<T> g;
+  std::vector<T> rh(3 * (size_t)nw);
+  for (size_t i = 0; i < rh.size(); ++i)
+    rh[i] = (T)r[i];
+  g.r.alloc(rh.size(), false);
+  g.rg.alloc((size_t)nw * np * nred);
+  QMCB_CUDA(cudaMemcpyAsync(g.r.p, rh.data(), rh.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  S.evaluate_dev(MODE_VGL, nw, g.r.p, invrow_dev, ld, nullptr, phi_dev, g.rg.p, st);
+  std::vector<T> parts((size_t)nw * np * nred);
+  QMCB_CUDA(cudaMemcpyAsync(parts.data(), g.rg.p, parts.size() * sizeof(T), cudaMemcpyDeviceToHost, st));
+  QMCB_CUDA(cudaStreamSynchronize(st));
+  T* ra = static_cast<T*>(ratios);
+  T* gr = static_cast<T*>(grads);
+  std::vector<T> q(nred);
+  for (int iw = 0; iw < nw; ++iw)
+  {
+    // the per-(tile, warp) partial dots in index order (the reference's host code adds its per-team partials the same
+    // way, SplineR2R.cpp:566-581)
+    std::fill(q.begin(), q.end(), T(0));
+    for (int t = 0; t < np; ++t)
+      for (int e = 0; e < nred; ++e)
+        q[e] += parts[((size_t)iw * np + t) * nred + e];
+    for (int c = 0; c < vt; ++c)
+      ra[(size_t)iw * vt + c] = q[c];
+    if (gr)
+      for (int d = 0; d < 3; ++d)
+        cdiv<T>(q.data() + (1 + d) * vt, q.data(), gr + ((size_t)iw * 3 + d) * vt, vt);
+  }
+}
 } // namespace
 
 extern "C"
@@ -313,6 +351,27 @@ int qmcb_spline_mw_vgl_ratio_grads_dev(qmcb_spline* h, int nw, const void* r_dev
 }
 
 int qmcb_spline_rg_parts(const qmcb_spline* h) { return h ? h->impl->rg_parts() : 0; }
+
+int qmcb_spline_mw_evaluate_vgl_ratio_grads_offload(qmcb_spline* h, int nw, const double* r_host, const void* invrow_dev,
+                                                    size_t ld_inv, void* phi_vgl_dev, void* ratios_host, void* grads_host,
+                                                    void* stream)
+{
+  return guarded([&] {
+    need(h, "spline");
+    QMCB_CUDA(cudaSetDevice(h->impl->device));
+    need(r_host, "r_host");
+    need(invrow_dev, "invrow_dev");
+    need(ratios_host, "ratios_host");
+    if (nw <= 0)
+      return;
+    if (h->impl->precision == QMCB_MIXED)
+      spline_ratio_offload<float>(h, nw, r_host, invrow_dev, ld_inv, phi_vgl_dev, ratios_host, grads_host,
+                                  static_cast<cudaStream_t>(stream));
+    else
+      spline_ratio_offload<double>(h, nw, r_host, invrow_dev, ld_inv, phi_vgl_dev, ratios_host, grads_host,
+                                   static_cast<cudaStream_t>(stream));
+  });
+}
 
 // ---- crowd
 int qmcb_crowd_create(qmcb_crowd** c, const qmcb_system* sys, int nw)

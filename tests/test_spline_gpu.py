@@ -85,6 +85,40 @@ def test_r2r_vgl_ratio_grads_matches_oracle(api, orc, dt, norb):
     assert np.abs(grads - ograds).max() / gscale < (2e-3 if dt == np.float32 else 1e-9)
 
 
+@pytest.mark.parametrize("kind", ["R2R", "C2C"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_offload_contract_device_rows_host_results(api, orc, dt, kind):
+    """SPOSet::mw_evaluateVGLandDetRatioGrads as DiracDeterminantBatched::mw_ratioGrad drives an offload SPOSet
+    (DiracDeterminantBatched.cpp:334-346): host positions, DEVICE inverse rows, phi_vgl_v current on the device on
+    return, ratios / gradients on the host -- the same numbers as the host-buffer entry, bit for bit."""
+    import torch
+    from qmcpack_b200.workload import random_table
+    lat = LATTICES["general"]
+    G = np.linalg.inv(lat)
+    norb, nw, ld = 130, 9, 136
+    cplx = kind == "C2C"
+    coefs = random_table((6, 7, 5), norb * (2 if cplx else 1), dt, seed=7)
+    kc = np.random.default_rng(3).normal(size=(norb, 3)) * 0.3 if cplx else None
+    spo = api.SplineSPOSet(coefs, norb, G, kind=api.C2C if cplx else api.R2R, kcart=kc)
+    r = positions(lat, nw, seed=11)
+    rng = np.random.default_rng(2)
+    invrow = rng.normal(size=(nw, ld)).astype(dt)
+    if cplx:
+        invrow = (invrow + 1j * rng.normal(size=(nw, ld))).astype(spo.vt)
+    phi, ratios, grads = spo.mw_evaluateVGLandDetRatioGrads(r, invrow)
+    real_view = invrow.view(dt) if cplx else invrow
+    inv_dev = torch.from_numpy(np.ascontiguousarray(real_view)).cuda()
+    phi_dev = torch.zeros(phi.view(dt).shape if cplx else phi.shape, dtype=inv_dev.dtype, device="cuda")
+    torch.cuda.synchronize()
+    r2, g2 = spo.mw_evaluateVGLandDetRatioGrads_offload(r, inv_dev.data_ptr(), ld, phi_dev.data_ptr())
+    assert np.array_equal(r2, ratios) and np.array_equal(g2, grads)
+    got = phi_dev.cpu().numpy()
+    assert np.array_equal(got.view(spo.vt).reshape(phi.shape) if cplx else got, phi)
+    # and without the optional phi_vgl_v
+    r3, g3 = spo.mw_evaluateVGLandDetRatioGrads_offload(r, inv_dev.data_ptr(), ld)
+    assert np.array_equal(r3, ratios) and np.array_equal(g3, grads)
+
+
 def test_r2r_ratio_is_deterministic(api):
     """fixed-order reduction: two evaluations give bit-identical ratios/gradients"""
     from qmcpack_b200.workload import random_table
