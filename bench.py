@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--sweep-kernel", type=int, default=0, help="0 automatic, 1 two-kernel path, 2 walker-segment kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fp64", action="store_true", help="skip the FP64 peak / full-precision flush objects")
+    ap.add_argument("--no-recompute", action="store_true", help="skip the mw_recompute inverse object (own kernels vs cuBLAS)")
     ap.add_argument("--dmc", action="store_true",
                     help="headline = batched DMC generations (BASELINE config 5: device move loop + block of C++ WalkerControl::"
                          "branch with the NCCL all-reduce and the packed-walker exchange inside the timed region)")
@@ -399,6 +400,24 @@ def run_b200(args, rank, local_rank, world):
     except Exception as ex:  # measurement hook only
         flush = {"error": str(ex)}
 
+    # ---------------- mw_recompute's FP64 inverse + log-determinant (DiracMatrixInverterCUDA::mw_invertTranspose,
+    # DiracMatrixInverterCUDA.hpp:306-369) of the benchmark crowd's own Slater matrices: this library's blocked
+    # Gauss-Jordan kernels (csrc/inverse.cuh) beside cublasDgetrfBatched + getriBatched, the routines the reference calls
+    # (detail/CUDA/cuBLAS_LU.cu:61-210).  2 n^3 flops per matrix either way.
+    recompute = None
+    if rank == 0 and not args.no_recompute:
+        try:
+            cr0, nwr = dcrowds[0], dsizes[0]
+            us_own = cr0.det_time_inverse(0, 2, reps=2)
+            us_cub = cr0.det_time_inverse(0, 1, reps=1)
+            fl = (4 if cplx else 1) * 2.0 * n ** 3 * nwr
+            recompute = {"walkers": nwr, "n": n, "us_own": us_own, "us_cublas": us_cub, "speedup_vs_cublas": us_cub / us_own,
+                         "tflops_own": fl / us_own * 1e-6, "tflops_cublas": fl / us_cub * 1e-6,
+                         "kernel": "gj::gj_panel_kernel + gj::gj_update_kernel (blocked Gauss-Jordan, DMMA m8n8k4 rank-b updates)",
+                         "baseline": "cublas%sgetrfBatched + getriBatched" % ("Z" if cplx else "D")}
+        except Exception as ex:  # measurement hook only
+            recompute = {"error": str(ex)}
+
     # ---------------- FP64 peak of this GPU (cublasDgemm 8192^3) and the full-precision flush at
     # the NiO-a64 (real, k = 32) and NiO-a128 (complex, k = 64) determinant shapes.  Only the determinant engine is
     # exercised: tiny tables, the benchmarked matrix sizes.
@@ -567,7 +586,7 @@ def run_b200(args, rank, local_rank, world):
                        "boundary kernel + spline gather per move",
                        "timed_region": "one VMC block: %d sweeps + block estimator + all-reduce over ranks" % args.steps},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "flush": flush, "flush_fp64": flush_fp64, "fp64_peak": fp64_peak, "spline_gather": spline_gather, "cpu_baseline": cpu,
+            "flush": flush, "flush_fp64": flush_fp64, "recompute": recompute, "fp64_peak": fp64_peak, "spline_gather": spline_gather, "cpu_baseline": cpu,
             "dmc": dmc_obj,
         }
         if args.dmc and dmc_obj and "value" in dmc_obj:

@@ -189,6 +189,14 @@ int qmcb_det_delay_count(qmcb_crowd* c, int spin);
  * the flushes are arithmetic on stale data; the inverse is saved before and restored afterwards, so the crowd is left as
  * qmcb_twf_mw_complete_updates leaves it.                                                                               */
 int qmcb_det_time_update_inv_mat(qmcb_crowd* c, int spin, int delay_count, int reps, double* us_per_flush);
+/* measurement hook: the FP64 inverse-transpose + log-determinant of the current Slater matrices of determinant `spin`
+ * (DiracMatrixInverterCUDA::mw_invertTranspose, Fermion/DiracMatrixInverterCUDA.hpp:306-369), the step of
+ * qmcb_twf_mw_recompute after the orbital evaluation; mean time of `reps` runs in microseconds, CUDA events on the crowd's
+ * stream.  method 1: cublas<t>getrfBatched + getriBatched, the routines the reference calls
+ * (detail/CUDA/cuBLAS_LU.cu:61-210); method 2: this library's blocked Gauss-Jordan kernels (csrc/inverse.cuh), the
+ * default of qmcb_twf_mw_recompute (environment QMCB_LU=cublas selects the cuBLAS routines there).  The crowd is left
+ * recomputed.                                                                                                            */
+int qmcb_det_time_inverse(qmcb_crowd* c, int spin, int method, int reps, double* us_per_call);
 
 /* ---- component level: distance rows + two-body Jastrow -------------------------------------------- */
 /* SoaDistanceTableAAOMPTarget::mw_move temp/old rows after qmcb_ps_mw_make_move: [2][nw][4][N] RT (r,dx,dy,dz; new then old) */
@@ -226,6 +234,7 @@ int qmcb_vmc_init(qmcb_crowd* c, const qmcb_vmc_params* p);
 int qmcb_vmc_sweep(qmcb_crowd* c, int nsteps, uint8_t* accept_log_host);
 /* asynchronous launch of one sweep on the crowd's stream (bench.py brackets it with CUDA events) */
 int qmcb_vmc_sweep_async(qmcb_crowd* c);
+/* accepted / rejected moves PER WALKER since qmcb_vmc_init: n_accept [nw], n_reject [nw] */
 int qmcb_vmc_counts(qmcb_crowd* c, long long* n_accept, long long* n_reject);
 /* 2 when the sweeps of this crowd run on the persistent walker-segment kernel, 1 on the two-kernel path, 0 before
  * qmcb_vmc_init                                                                                                          */

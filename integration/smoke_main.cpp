@@ -181,8 +181,11 @@ int main()
   vp.tau = tau, vp.use_drift = 1, vp.seed = 7, vp.use_cuda_graph = 1;
   CHECK(qmcb_vmc_init(crowd, &vp));
   CHECK(qmcb_vmc_sweep(crowd, 2, nullptr));
+  std::vector<long long> nacc(nw), nrej(nw); // per walker
+  CHECK(qmcb_vmc_counts(crowd, nacc.data(), nrej.data()));
   long long na = 0, nr = 0;
-  CHECK(qmcb_vmc_counts(crowd, &na, &nr));
+  for (int iw = 0; iw < nw; ++iw)
+    na += nacc[iw], nr += nrej[iw];
   CHECK(qmcb_twf_mw_evaluate_gl(crowd, nullptr, nullptr, logpsi1.data(), ke.data()));
   CHECK(qmcb_twf_mw_recompute(crowd));
   CHECK(qmcb_twf_mw_evaluate_gl(crowd, nullptr, nullptr, logpsi2.data(), ke.data()));

@@ -59,7 +59,7 @@ SYMBOLS = [
     "qmcb_twf_mw_accept_reject", "qmcb_twf_mw_complete_updates", "qmcb_twf_mw_evaluate_gl",
     "qmcb_det_mw_eval_grad", "qmcb_det_mw_get_inv_row", "qmcb_det_mw_ratio_grad", "qmcb_det_mw_accept_reject",
     "qmcb_det_mw_complete_updates", "qmcb_det_mw_recompute_from_matrices", "qmcb_det_set_phi_vgl",
-    "qmcb_det_mw_ratio_grad_from_phi", "qmcb_det_delay_count", "qmcb_det_time_update_inv_mat",
+    "qmcb_det_mw_ratio_grad_from_phi", "qmcb_det_delay_count", "qmcb_det_time_update_inv_mat", "qmcb_det_time_inverse",
     "qmcb_dtaa_get_temp_rows", "qmcb_j2_mw_ratio_grad", "qmcb_j2_mw_accept_reject", "qmcb_j2_get_state",
     "qmcb_vmc_init", "qmcb_vmc_sweep", "qmcb_vmc_sweep_async", "qmcb_vmc_counts", "qmcb_vmc_sweep_kernel", "qmcb_vmc_profile_sweep", "qmcb_crowd_host_kernel", "qmcb_twf_mw_calc_ratio",
     "qmcb_twf_mw_evaluate_ratios", "qmcb_crowd_stream",
@@ -413,6 +413,12 @@ class Crowd:
 
     def det_delay_count(self, spin):
         return int(lib().qmcb_det_delay_count(self.h, C.c_int(spin)))
+
+    def det_time_inverse(self, spin, method, reps=3):
+        """microseconds per FP64 inverse + log-determinant of the whole batch (1: cuBLAS getrf/getriBatched, 2: own kernels)"""
+        us = C.c_double(0.0)
+        _chk(lib().qmcb_det_time_inverse(self.h, C.c_int(spin), C.c_int(method), C.c_int(reps), C.byref(us)))
+        return us.value
 
     def det_time_update_inv_mat(self, spin, delay_count, reps=10):
         """microseconds per mw_updateInvMat launch (measurement hook; recompute the crowd afterwards)"""

@@ -429,6 +429,7 @@ int qmcb_det_mw_recompute_from_matrices(qmcb_crowd* c, int spin, const void* m, 
 int qmcb_det_set_phi_vgl(qmcb_crowd* c, int spin, const void* phi) { CROWD_CALL(det_set_phi_vgl(spin, phi)); }
 int qmcb_det_delay_count(qmcb_crowd* c, int spin) { return c ? c->impl->det_delay_count(spin) : -1; }
 int qmcb_det_time_update_inv_mat(qmcb_crowd* c, int spin, int dc, int reps, double* us) { CROWD_CALL(det_time_update_inv_mat(spin, dc, reps, us)); }
+int qmcb_det_time_inverse(qmcb_crowd* c, int spin, int method, int reps, double* us) { CROWD_CALL(det_time_inverse(spin, method, reps, us)); }
 int qmcb_dtaa_get_temp_rows(qmcb_crowd* c, void* rows) { CROWD_CALL(dtaa_get_temp_rows(rows)); }
 int qmcb_j2_mw_ratio_grad(qmcb_crowd* c, int iat, double* r, void* g) { CROWD_CALL(j2_ratio_grad(iat, r, g)); }
 int qmcb_j2_mw_accept_reject(qmcb_crowd* c, int iat, const uint8_t* a) { CROWD_CALL(j2_accept_reject(iat, a)); }

@@ -9,6 +9,7 @@
 #include "woodbury.cuh"
 #include "woodbury_tc5.cuh"
 #include "woodbury_dmma.cuh"
+#include "inverse.cuh"
 #include <cstdlib>
 #include <cuda.h>
 #include <type_traits>
@@ -327,7 +328,23 @@ __global__ void __launch_bounds__(MB_TPB, (sizeof(V) > 8 ? 2 : 4))
   __shared__ T jred[10 * 32];
   __shared__ unsigned short jlist[JAS_LIST]; // cutoff lists of the Jastrow passes (jastrow.cuh)
   __shared__ T s_newpos[3];
-  const int iw = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int s_iw;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int iw = blockIdx.x;
+  if (Dr.ticket)
+  {
+    // walker index = start order of the CTA (driver.cuh: DriverDev::ticket); the CTA that draws the last ticket of the
+    // launch re-arms the counter for the next one (launches of a crowd are stream ordered)
+    if (tid == 0)
+    {
+      const unsigned t = atomicAdd(Dr.ticket, 1u);
+      if (t == gridDim.x - 1)
+        *((volatile unsigned*)Dr.ticket) = 0u;
+      s_iw = (int)t;
+    }
+    __syncthreads();
+    iw = s_iw;
+  }
   const bool part1 = iat_prev >= 0, part2 = iat_next >= 0;
   const int nA = part1 ? Dacc.n : 0, nB = part2 ? Dprep.n : 0, k = part1 ? Dacc.k : Dprep.k;
   const int kb = k + 1; // padded row stride of the staged Binv (conflict-free row AND column walks)
@@ -835,6 +852,8 @@ struct Crowd : CrowdBase
   DevBuf<uint32_t> rng_state, rng_ring;
   DevBuf<unsigned long long> rng_cnt, n_acc, n_rej;
   DevBuf<unsigned> rng_flags;
+  DevBuf<unsigned> ticket;   // dispatch-order walker tickets of oversubscribed boundary launches (driver.cuh)
+  int boundary_slots = 0;    // boundary-kernel CTAs the device holds at once
   DevBuf<unsigned char> accept_log;
   bool vmc_ready = false, use_graph = false;
   // persistent walker-segment kernel (segment.cuh)
@@ -1625,10 +1644,88 @@ struct Crowd : CrowdBase
   }
 
   // FP64 inversion of the transposed matrices in AT (column-major psiM), result into Ainv, log-determinants
-  // (always FullPrecValueType like DiracMatrixInverterCUDA::mw_invertTranspose, DiracMatrixInverterCUDA.hpp:306-369)
-  void invert_from_AT(int spin, DevBuf<DV>& AT)
+  // (always FullPrecValueType like DiracMatrixInverterCUDA::mw_invertTranspose, DiracMatrixInverterCUDA.hpp:306-369).
+  // Default: the blocked Gauss-Jordan inverse of csrc/inverse.cuh (panel kernel + DMMA rank-b updates over the whole
+  // batch).  QMCB_LU=cublas selects cublas<t>getrfBatched + getriBatched, the reference's routines
+  // (detail/CUDA/cuBLAS_LU.cu:61-210) -- kept as the baseline bench.py times beside it, and for matrices whose column
+  // panel does not fit in shared memory at the narrowest panel width.
+  static int gj_panel_width(int n)
+  {
+    int dev = 0, cap = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    for (int b : {32, 16, 8})
+      if (gj::panel_smem<DV>(n, b) <= (size_t)cap)
+        return b;
+    return 0;
+  }
+  void invert_from_AT(int spin, DevBuf<DV>& AT, int method = 0 /* 0: default, 1: cuBLAS, 2: Gauss-Jordan */)
   {
     QMCB_NVTX("DiracDeterminantBatched::inverse");
+    static const bool force_cublas = [] {
+      const char* e = std::getenv("QMCB_LU");
+      return e && std::string(e) == "cublas";
+    }();
+    const int n  = nel[spin];
+    const int BW = (method == 1 || (method == 0 && force_cublas)) ? 0 : gj_panel_width(n);
+    if (BW == 0)
+    {
+      invert_from_AT_cublas(spin, AT);
+      return;
+    }
+    DevBuf<unsigned char> used;
+    DevBuf<int> R, Rinv, info;
+    DevBuf<DV> W, Xr;
+    used.alloc((size_t)nw * n, false);
+    R.alloc((size_t)nw * n, false);
+    Rinv.alloc((size_t)nw * n, false);
+    info.alloc(nw);
+    W.alloc((size_t)nw * n * BW, false);
+    Xr.alloc((size_t)nw * BW * n, false);
+    const size_t psm = gj::panel_smem<DV>(n, BW);
+    ensure_dynamic_smem(gj::gj_panel_kernel<DV>, psm);
+    const int nt = (n + gj::TILE - 1) / gj::TILE;
+    auto update = [&](auto kern, int j0, int b) {
+      const size_t usm = (size_t)(gj::TILE * (BW + 4) + BW * (gj::TILE + 4)) * sizeof(DV);
+      ensure_dynamic_smem(kern, usm);
+      kern<<<dim3(nt, nt, nw), gj::TPB, usm, st>>>(AT.p, n, j0, b, W.p, Xr.p);
+      QMCB_LAUNCH_CHECK();
+    };
+    for (int j0 = 0; j0 < n; j0 += BW)
+    {
+      const int b = std::min(BW, n - j0);
+      gj::gj_panel_kernel<DV><<<nw, gj::TPB, gj::panel_smem<DV>(n, b), st>>>(AT.p, n, j0, b, BW, used.p, R.p, W.p, Xr.p,
+                                                                          logdet[spin].p, info.p);
+      QMCB_LAUNCH_CHECK();
+      if (n > b)
+      {
+        if (BW == 32)
+          update(gj::gj_update_kernel<DV, 32>, j0, b);
+        else if (BW == 16)
+          update(gj::gj_update_kernel<DV, 16>, j0, b);
+        else
+          update(gj::gj_update_kernel<DV, 8>, j0, b);
+      }
+    }
+    gj::gj_perm_kernel<<<nw, 128, (size_t)(n + 15) / 16 * 16, st>>>(R.p, Rinv.p, n, logdet[spin].p);
+    QMCB_LAUNCH_CHECK();
+    gj::gj_store_inverse_kernel<V><<<dim3(blocks(n, 128), n, nw), 128, 0, st>>>(det[spin], AT.p, R.p, Rinv.p);
+    QMCB_LAUNCH_CHECK();
+    finish_inversion(spin, info);
+  }
+  void finish_inversion(int spin, DevBuf<int>& info)
+  {
+    std::vector<int> hinfo(nw);
+    QMCB_CUDA(cudaMemcpyAsync(hinfo.data(), info.p, nw * sizeof(int), cudaMemcpyDeviceToHost, st));
+    sync();
+    for (int iw = 0; iw < nw; ++iw)
+      if (hinfo[iw] != 0)
+        throw std::runtime_error("matrix inversion failed (singular Slater matrix) for walker " + std::to_string(iw));
+    delay_count[spin] = 0;
+    invrow_id[spin]   = -1;
+  }
+  void invert_from_AT_cublas(int spin, DevBuf<DV>& AT)
+  {
     const int n = nel[spin];
     DevBuf<DV> inv;
     DevBuf<int> piv, info;
@@ -1659,14 +1756,7 @@ struct Crowd : CrowdBase
     g_launch_count.fetch_add(1);
     det_store_inverse_kernel<V><<<dim3(blocks(n, 128), n, nw), 128, 0, st>>>(det[spin], inv.p);
     QMCB_LAUNCH_CHECK();
-    std::vector<int> hinfo(nw);
-    QMCB_CUDA(cudaMemcpyAsync(hinfo.data(), info.p, nw * sizeof(int), cudaMemcpyDeviceToHost, st));
-    sync();
-    for (int iw = 0; iw < nw; ++iw)
-      if (hinfo[iw] != 0)
-        throw std::runtime_error("matrix inversion failed (singular Slater matrix) for walker " + std::to_string(iw));
-    delay_count[spin] = 0;
-    invrow_id[spin]   = -1;
+    finish_inversion(spin, info);
   }
 
   void det_recompute_from_matrices(int spin, const void* psiM, const void* dpsiM, const void* d2psiM) override
@@ -1708,17 +1798,7 @@ struct Crowd : CrowdBase
       if (n == 0)
         continue;
       DevBuf<DV> AT;
-      AT.alloc((size_t)nw * n * n, false);
-      // SPOSet::mw_evaluate_notranspose for splines = loop over electrons calling mw_evaluateVGL (BsplineSet.h:142-189)
-      for (int e = 0; e < n; ++e)
-      {
-        const int iat = first[spin] + e;
-        make_move_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, displ_zero());
-        QMCB_LAUNCH_CHECK();
-        launch_spline(spin, MODE_VGL, nullptr, 0, phi_vgl.p, nullptr, st);
-        det_scatter_row_kernel<V><<<dim3(blocks(n, 128), nw), 128, 0, st>>>(det[spin], e, phi_vgl.p, AT.p);
-        QMCB_LAUNCH_CHECK();
-      }
+      build_AT(spin, AT);
       invert_from_AT(spin, AT);
     }
     if (jas.has_j2 || jas.has_j1)
@@ -1727,6 +1807,54 @@ struct Crowd : CrowdBase
       QMCB_LAUNCH_CHECK();
     }
     sync();
+  }
+  // psiM of determinant `spin` at the committed positions, transposed, in double; the gradient / Laplacian rows go to GL
+  void build_AT(int spin, DevBuf<DV>& AT)
+  {
+    const int n = nel[spin];
+    AT.alloc((size_t)nw * n * n, false);
+    // SPOSet::mw_evaluate_notranspose for splines = loop over electrons calling mw_evaluateVGL (BsplineSet.h:142-189)
+    for (int e = 0; e < n; ++e)
+    {
+      const int iat = first[spin] + e;
+      make_move_kernel<T><<<blocks(nw, 128), 128, 0, st>>>(jas, iat, displ_zero());
+      QMCB_LAUNCH_CHECK();
+      launch_spline(spin, MODE_VGL, nullptr, 0, phi_vgl.p, nullptr, st);
+      det_scatter_row_kernel<V><<<dim3(blocks(n, 128), nw), 128, 0, st>>>(det[spin], e, phi_vgl.p, AT.p);
+      QMCB_LAUNCH_CHECK();
+    }
+  }
+  // measurement hook: the FP64 inversion + log-determinant of the current Slater matrices of determinant `spin`, `reps`
+  // times (each on a fresh copy of psiM; the copy is outside the timed span), method 1 = cuBLAS getrf/getriBatched,
+  // 2 = the blocked Gauss-Jordan kernels.  The crowd is left as qmcb_twf_mw_recompute leaves it.
+  void det_time_inverse(int spin, int method, int reps, double* us_per_call) override
+  {
+    if (spin < 0 || spin > 1 || nel[spin] == 0 || reps < 1 || method < 1 || method > 2)
+      throw std::runtime_error("det_time_inverse: need spin in {0, 1}, method in {1, 2}, reps >= 1");
+    flush_pending();
+    DevBuf<DV> AT, work;
+    build_AT(spin, AT);
+    work.alloc(AT.n, false);
+    cudaEvent_t e0, e1;
+    QMCB_CUDA(cudaEventCreate(&e0));
+    QMCB_CUDA(cudaEventCreate(&e1));
+    double total = 0.0;
+    for (int i = -1; i < reps; ++i) // (i = -1: warm-up, first-use attribute calls)
+    {
+      QMCB_CUDA(cudaMemcpyAsync(work.p, AT.p, AT.bytes(), cudaMemcpyDeviceToDevice, st));
+      QMCB_CUDA(cudaEventRecord(e0, st));
+      invert_from_AT(spin, work, method);
+      QMCB_CUDA(cudaEventRecord(e1, st));
+      QMCB_CUDA(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      QMCB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (i >= 0)
+        total += 1e3 * ms;
+    }
+    *us_per_call = total / reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    twf_recompute();
   }
   const T* displ_zero()
   {
@@ -2143,6 +2271,21 @@ struct Crowd : CrowdBase
     rng.ring_mask = (unsigned)(ring - 1);
     hd_abort();
     setup_segment_kernel(p->sweep_kernel);
+    // oversubscribed two-kernel sweeps: walker indices by dispatch-order ticket (driver.cuh)
+    {
+      A(ticket, 1);
+      int occ = 0, sms = 0, dev = 0;
+      const int nmx     = std::max(det[0].n, det[1].n);
+      const size_t smem = (size_t)(10 * nmx + k * (k + 1) + 5 * k) * sizeof(V);
+      if (smem > 48 * 1024 && smem <= 200 * 1024)
+        ensure_dynamic_smem(move_boundary_kernel<T, V>, 200 * 1024);
+      QMCB_CUDA(cudaGetDevice(&dev));
+      QMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      QMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, move_boundary_kernel<T, V>, MB_TPB, smem));
+      const bool over = cap > occ * sms;
+      drv.ticket      = (over || env_flag("QMCB_TICKET", 0)) ? ticket.p : nullptr;
+      boundary_slots  = occ * sms;
+    }
     mt19937_seed_kernel<<<1, 32, 0, st>>>(rng, p->seed);
     QMCB_LAUNCH_CHECK();
     mt19937_fill_kernel<<<1, 256, 0, st>>>(rng, 2 * sweep_backlog);

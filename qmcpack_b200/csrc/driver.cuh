@@ -48,6 +48,13 @@ struct DriverDev
   unsigned* err;                // crowd-wide error bits (det.cuh: QMCB_ERR_*)
   int value_only;               // the proposed move's orbital rows hold VALUES only (TrialWaveFunction::mw_calcRatio):
                                 // an accept must not touch the gradient / Laplacian rows
+  unsigned* ticket;             // not null: the boundary kernel's CTAs take their walker index from this counter in the
+                                // order they START instead of from blockIdx.x.  The Metropolis warp of walker iw waits for
+                                // the flags of the walkers below it (RNG order); when a launch has more CTAs than the
+                                // device can hold at once that is only deadlock-free if every lower-index walker is owned
+                                // by a CTA that is already running -- which the dispatch-order ticket guarantees and the
+                                // hardware's block scheduling order does not promise.  Set by the host for oversubscribed
+                                // launches only (and by QMCB_TICKET=1).
 };
 
 #ifdef __CUDACC__

@@ -71,6 +71,7 @@ struct CrowdBase
   virtual void det_set_phi_vgl(int spin, const void* phi)                                                   = 0;
   virtual int det_delay_count(int spin)                                                                     = 0;
   virtual void det_time_update_inv_mat(int spin, int c, int reps, double* us_per_call)                      = 0;
+  virtual void det_time_inverse(int spin, int method, int reps, double* us_per_call)                       = 0;
   virtual void dtaa_get_temp_rows(void* rows)                                                               = 0;
   virtual void j2_ratio_grad(int iat, double* ratios, void* grads)                                          = 0;
   virtual void j2_accept_reject(int iat, const uint8_t* acc)                                                = 0;

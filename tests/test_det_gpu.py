@@ -79,6 +79,59 @@ def test_invert_transpose_4x4_literals(api):
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32, np.complex128, np.complex64])
+@pytest.mark.parametrize("n", [1, 5, 31, 33, 70, 130, 384])
+def test_batched_inverse_and_logdet_match_lapack(api, dt, n):
+    """mw_invertTranspose (DiracMatrixInverterCUDA.hpp:306-369) on the library's own blocked Gauss-Jordan kernels
+    (csrc/inverse.cuh): inverse transpose, log|det| and the determinant's phase against LAPACK (numpy) in double, for
+    panel-aligned and ragged sizes, real and complex; rows are permuted per walker so that pivoting is exercised (a
+    different pivot order in every walker) and one walker carries a negative determinant"""
+    rng = np.random.default_rng(100 + n)
+    nw = 5 if n < 384 else 3
+    psiM = normal(rng, (nw, n, n), dt)
+    psiM += 0.5 * np.sqrt(n) * np.eye(n, dtype=dt)  # conditioned so that float results are meaningful too
+    for iw in range(nw):
+        psiM[iw] = psiM[iw][rng.permutation(n)]
+    crowd = api.Crowd(tiny_system(n, dt), nw=nw, delay_rank=1)
+    crowd.det_recompute_from_matrices(0, psiM)
+    inv, logdet = crowd.det_mw_completeUpdates(0)
+    ref = np.linalg.inv(psiM.astype(np.complex128 if np.dtype(dt).kind == "c" else np.float64)).transpose(0, 2, 1)
+    sign, logabs = np.linalg.slogdet(psiM.astype(ref.dtype))
+    single = np.dtype(dt) in (np.dtype(np.float32), np.dtype(np.complex64))
+    tol = 2e-5 if single else 1e-10  # the inversion itself is FP64; single = the cast of the result
+    for iw in range(nw):
+        assert np.abs(inv[iw][:, :n] - ref[iw]).max() <= tol * np.abs(ref[iw]).max()
+        assert logdet[iw, 0] == pytest.approx(logabs[iw], rel=1e-11, abs=1e-11)
+        assert np.exp(1j * logdet[iw, 1]) == pytest.approx(sign[iw], abs=1e-9)
+    assert (np.real(sign) < 0).any() or np.dtype(dt).kind == "c" or n == 1
+
+
+def test_singular_matrix_is_reported(api):
+    """getrf's info != 0 -> exception (DiracMatrixInverterCUDA.hpp:180-190 checks the infos and throws)"""
+    a = np.ones((2, 6, 6))
+    a[0] += np.eye(6)
+    crowd = api.Crowd(tiny_system(6, np.float64), nw=2, delay_rank=1)
+    with pytest.raises(RuntimeError, match="singular"):
+        crowd.det_recompute_from_matrices(0, a)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+def test_own_inverse_and_cublas_route_agree(api, dt):
+    """the timing hook runs both routes on the same Slater matrices and leaves the crowd recomputed"""
+    from qmcpack_b200 import workload
+    s = workload.make_system(N=48, M=8, dtype=np.float64, L=6.0, complex_orbitals=np.dtype(dt).kind == "c")
+    crowd = api.Crowd(s, nw=4, delay_rank=4)
+    crowd.set_positions(workload.initial_positions(s, 4))
+    crowd.mw_recompute()
+    a0, l0 = crowd.det_mw_completeUpdates(0)
+    for method in (1, 2):
+        assert crowd.det_time_inverse(0, method, reps=1) > 0
+        a1, l1 = crowd.det_mw_completeUpdates(0)
+        assert np.abs(a1 - a0).max() <= 1e-9 * np.abs(a0).max()
+        assert np.allclose(l1[:, 0], l0[:, 0], rtol=1e-12, atol=1e-12)
+        assert np.allclose(np.exp(1j * l1[:, 1]), np.exp(1j * l0[:, 1]), atol=1e-9)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32, np.complex128, np.complex64])
 @pytest.mark.parametrize("n,k", [(24, 1), (24, 2), (24, 8), (70, 16), (192, 32), (130, 64)])
 def test_delayed_update_sequence_matches_oracle(api, orc, dt, n, k):
     """random accept/reject sequence, every walker with its own flags: inverse rows, ratios, gradients at every move and

@@ -8,6 +8,14 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from qmcpack_b200 import api as a, build
+    build.build()
+    a.init(0)
+    return a
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 

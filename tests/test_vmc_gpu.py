@@ -552,3 +552,32 @@ def test_nio_a256_orbital_count_every_move(api, orc, dt):
         assert ke2 == pytest.approx(ke, rel=1e-5)
     else:
         assert np.isfinite(lp).all() and np.isfinite(ke).all()
+
+
+@pytest.mark.parametrize("cplx,nw,force", [(True, 2048, False), (False, 700, False), (False, 40, True)],
+                         ids=["complex_2048_walkers", "real_700_walkers", "forced_small"])
+def test_oversubscribed_crowd_look_back_by_ticket(api, orc, cplx, nw, force, monkeypatch):
+    """one crowd with more walkers than the device can hold boundary-kernel CTAs at once: the walker index of a CTA is
+    its start order (DriverDev::ticket), so the cross-CTA RNG-order wait of the Metropolis test (VMCBatched.cpp:156-158:
+    the uniform is drawn only when prob >= eps, walkers in index order) cannot wait on a CTA that has not started.
+    Identical acceptance sequence with the oracle in FP64, two sweeps, both with and without CUDA-graph replay."""
+    from qmcpack_b200.workload import initial_positions
+    import oracle_lib
+    if force:
+        monkeypatch.setenv("QMCB_TICKET", "1")
+    s = (complex_system if cplx else small_system)(np.float64, None, N=12, M=6)
+    k, nsteps, tau, seed = 3, 2, 0.15, 99
+    R = initial_positions(s, nw)
+    ov = oracle_lib.OracleVMC(orc, s, nw=nw, ncrowds=1, seeds=[seed], tau=tau, delay_rank=k)
+    ov.set_positions(R)
+    ov.recompute()
+    olog = ov.sweep(nsteps, log_accept=True)
+    for graph in (False, True):
+        crowd = api.Crowd(s, nw=nw, delay_rank=k)
+        crowd.set_positions(R)
+        crowd.mw_recompute()
+        crowd.vmc_init(tau=tau, use_drift=True, seed=seed, use_cuda_graph=graph, sweep_kernel=1)
+        assert crowd.sweep_kernel == 1
+        log = crowd.vmc_sweep(nsteps, log_accept=True)
+        assert np.array_equal(log, olog), f"graph={graph}: {np.argwhere(log != olog)[:5]}"
+        assert crowd.positions() == pytest.approx(ov.positions(), rel=1e-8, abs=1e-8)
