@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="NiO-a64")
     ap.add_argument("--walkers", type=int, default=512, help="walkers per GPU")
-    ap.add_argument("--crowds", type=int, default=4, help="crowds (host threads / streams) of the e2e host driver")
+    ap.add_argument("--crowds", type=int, default=8, help="crowds (host threads / streams) of the e2e host driver")
     ap.add_argument("--device-crowds", type=int, default=1,
                     help="crowds of the device-resident sweep: walkers/GPU are split over this many crowds, each with its own "
                          "RNG stream and CUDA graph on its own stream (QMCDriverNew gives every crowd its own generator)")

@@ -12,6 +12,9 @@
 #include "inverse.cuh"
 #include <cstdlib>
 #include <cuda.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <type_traits>
 #include <cublas_v2.h>
 #include <nvtx3/nvToolsExt.h>
@@ -852,6 +855,9 @@ struct Crowd : CrowdBase
   DevBuf<uint32_t> rng_state, rng_ring;
   DevBuf<unsigned long long> rng_cnt, n_acc, n_rej;
   DevBuf<unsigned> rng_flags;
+  DevBuf<unsigned char> gj_used; // work buffers of the blocked Gauss-Jordan inverse (inverse.cuh)
+  DevBuf<int> gj_R, gj_Rinv, gj_info;
+  DevBuf<DV> gj_W, gj_Xr;
   DevBuf<unsigned> ticket;   // dispatch-order walker tickets of oversubscribed boundary launches (driver.cuh)
   int boundary_slots = 0;    // boundary-kernel CTAs the device holds at once
   DevBuf<unsigned char> accept_log;
@@ -1673,30 +1679,42 @@ struct Crowd : CrowdBase
       invert_from_AT_cublas(spin, AT);
       return;
     }
-    DevBuf<unsigned char> used;
-    DevBuf<int> R, Rinv, info;
-    DevBuf<DV> W, Xr;
-    used.alloc((size_t)nw * n, false);
-    R.alloc((size_t)nw * n, false);
-    Rinv.alloc((size_t)nw * n, false);
-    info.alloc(nw);
-    W.alloc((size_t)nw * n * BW, false);
-    Xr.alloc((size_t)nw * BW * n, false);
+    // work buffers of the inversion: kept by the crowd (an allocation inside every recompute costs milliseconds)
+    DevBuf<unsigned char>& used = gj_used;
+    DevBuf<int>&R = gj_R, &Rinv = gj_Rinv, &info = gj_info;
+    DevBuf<DV>&W = gj_W, &Xr = gj_Xr;
+    auto fit = [](auto& b, size_t need) {
+      if (b.n < need)
+        b.alloc(need, false);
+    };
+    fit(used, (size_t)cap * n);
+    fit(R, (size_t)cap * n);
+    fit(Rinv, (size_t)cap * n);
+    fit(info, (size_t)cap);
+    fit(W, (size_t)cap * n * BW);
+    fit(Xr, (size_t)cap * BW * n);
     const size_t psm = gj::panel_smem<DV>(n, BW);
-    ensure_dynamic_smem(gj::gj_panel_kernel<DV>, psm);
     const int nt = (n + gj::TILE - 1) / gj::TILE;
     auto update = [&](auto kern, int j0, int b) {
-      const size_t usm = (size_t)(gj::TILE * (BW + 4) + BW * (gj::TILE + 4)) * sizeof(DV);
+      const size_t usm = (size_t)(gj::TILE * (BW + 4) + 2 * BW * (gj::TILE + 4)) * sizeof(DV);
       ensure_dynamic_smem(kern, usm);
-      kern<<<dim3(nt, nt, nw), gj::TPB, usm, st>>>(AT.p, n, j0, b, W.p, Xr.p);
+      kern<<<dim3(nt, nw), gj::TPB, usm, st>>>(AT.p, n, j0, b, W.p, Xr.p);
       QMCB_LAUNCH_CHECK();
     };
     for (int j0 = 0; j0 < n; j0 += BW)
     {
       const int b = std::min(BW, n - j0);
-      gj::gj_panel_kernel<DV><<<nw, gj::TPB, gj::panel_smem<DV>(n, b), st>>>(AT.p, n, j0, b, BW, used.p, R.p, W.p, Xr.p,
-                                                                          logdet[spin].p, info.p);
-      QMCB_LAUNCH_CHECK();
+      auto panel = [&](auto kern) {
+        ensure_dynamic_smem(kern, psm);
+        kern<<<nw, gj::TPB, psm, st>>>(AT.p, n, j0, b, used.p, R.p, W.p, Xr.p, logdet[spin].p, info.p);
+        QMCB_LAUNCH_CHECK();
+      };
+      if (BW == 32)
+        panel(gj::gj_panel_kernel<DV, 32>);
+      else if (BW == 16)
+        panel(gj::gj_panel_kernel<DV, 16>);
+      else
+        panel(gj::gj_panel_kernel<DV, 8>);
       if (n > b)
       {
         if (BW == 32)
@@ -2508,33 +2526,27 @@ struct Crowd : CrowdBase
     }
     if (!acquire_segment_kernel(true).empty())
       return;
-    // pinned block: h_grad [3 cap] T | h_gradnew [3 cap] T | h_displ [3 cap] T | h_ratio [cap] f64 | h_ready [cap] u32 |
-    //               h_cmd [4] u32 | h_acc [cap]
+    // pinned block of 16-byte chunks (segment.cuh, SegHost): h_out1 [cap][3] | h_out2 [cap][4] | h_in1 [cap] (float) or
+    // [cap][3] (double) | h_in2 [ceil(cap / 4)] | h_cmd [4] u32
     auto up16 = [](size_t v) { return (v + 15) & ~size_t(15); };
     size_t o = 0;
-    const size_t o_grad = o;
-    o += up16(3 * (size_t)cap * sizeof(T));
-    const size_t o_gnew = o;
-    o += up16(3 * (size_t)cap * sizeof(T));
-    const size_t o_dis = o;
-    o += up16(3 * (size_t)cap * sizeof(T));
-    const size_t o_rat = o;
-    o += up16((size_t)cap * sizeof(double));
-    const size_t o_rdy = o;
-    o += up16((size_t)cap * sizeof(unsigned));
+    const size_t o_out1 = o;
+    o += 16 * 3 * (size_t)cap;
+    const size_t o_out2 = o;
+    o += 16 * 4 * (size_t)cap;
+    const size_t o_in1 = o;
+    o += 16 * (sizeof(T) == 4 ? 1 : 3) * (size_t)cap;
+    const size_t o_in2 = o;
+    o += 16 * (((size_t)cap + 3) / 4);
     const size_t o_cmd = o;
     o += 64;
-    const size_t o_acc = o;
-    o += up16((size_t)cap);
     hd.pin.alloc(o);
     std::memset(hd.pin.p, 0, o);
-    hd.H.h_grad    = reinterpret_cast<T*>(hd.pin.p + o_grad);
-    hd.H.h_gradnew = reinterpret_cast<T*>(hd.pin.p + o_gnew);
-    hd.H.h_displ   = reinterpret_cast<const T*>(hd.pin.p + o_dis);
-    hd.H.h_ratio   = reinterpret_cast<double*>(hd.pin.p + o_rat);
-    hd.H.h_ready   = reinterpret_cast<volatile unsigned*>(hd.pin.p + o_rdy);
-    hd.H.h_cmd     = reinterpret_cast<volatile unsigned*>(hd.pin.p + o_cmd);
-    hd.H.h_acc     = hd.pin.p + o_acc;
+    hd.H.h_out1 = reinterpret_cast<uint4*>(hd.pin.p + o_out1);
+    hd.H.h_out2 = reinterpret_cast<uint4*>(hd.pin.p + o_out2);
+    hd.H.h_in1  = reinterpret_cast<const uint4*>(hd.pin.p + o_in1);
+    hd.H.h_in2  = reinterpret_cast<const uint4*>(hd.pin.p + o_in2);
+    hd.H.h_cmd  = reinterpret_cast<volatile unsigned*>(hd.pin.p + o_cmd);
     // device block: d_displ [3 cap] T | d_cmd [4] u32 | d_acc [cap]
     size_t d = 0;
     const size_t d_dis = d;
@@ -2571,7 +2583,7 @@ struct Crowd : CrowdBase
       hd.seq0   = hd.seq + 1;
       hd.H.seq0 = hd.seq0;
       hd.seq += 2u * (unsigned)nm;
-      const_cast<volatile unsigned*>(hd.H.h_cmd)[0] = hd.seq0 - 1u;
+      const_cast<volatile unsigned*>(hd.H.h_cmd)[0] = 0u; // (no abort requested)
       const_cast<volatile unsigned*>(hd.H.h_cmd)[1] = 0u;
       const unsigned init[2] = {hd.seq0 - 1u, 0u};
       QMCB_CUDA(cudaMemcpyAsync(const_cast<unsigned*>(hd.H.d_cmd), init, sizeof(init), cudaMemcpyHostToDevice, st));
@@ -2598,34 +2610,58 @@ struct Crowd : CrowdBase
       return false;
   }
   unsigned hd_seq(int iat, int second) const { return hd.seq0 + 2u * (unsigned)(iat - hd.iat0) + (unsigned)second; }
-  // every live walker has posted exchange `seq`
-  void hd_wait_ready(unsigned seq)
+  // one 16-byte chunk {lo, hi} of a mailbox written by ONE store, so that the kernel's 16-byte read sees the tag (in the
+  // high half) only together with the payload
+  static void store16(void* dst, unsigned long long lo, unsigned long long hi)
   {
-    volatile unsigned* r = hd.H.h_ready;
-    unsigned long long spins = 0;
-    for (int iw = 0; iw < nw; ++iw)
-      while (r[iw] != seq)
-      {
 #if defined(__x86_64__)
-        __builtin_ia32_pause();
+    _mm_store_si128(static_cast<__m128i*>(dst), _mm_set_epi64x((long long)hi, (long long)lo)); // (aligned: one 16-byte store)
+#else
+    volatile unsigned long long* d = static_cast<volatile unsigned long long*>(dst);
+    d[0] = lo;
+    std::atomic_thread_fence(std::memory_order_release);
+    d[1] = hi; // (the tag sits in the half written last)
 #endif
-        if ((++spins & 0x3fffffull) == 0)
+  }
+  // wait until chunk `slot` of an outgoing mailbox carries the tag of exchange `seq`; returns its 8 payload bytes
+  unsigned long long hd_wait_chunk(const uint4* slot, unsigned seq, unsigned long long& spins)
+  {
+    const volatile unsigned* w = reinterpret_cast<const volatile unsigned*>(slot);
+    while (w[2] != seq)
+    {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+      if ((++spins & 0x3fffffull) == 0)
+      {
+        const cudaError_t e = cudaStreamQuery(st);
+        if (e != cudaErrorNotReady)
         {
-          const cudaError_t e = cudaStreamQuery(st);
-          if (e != cudaErrorNotReady)
-          {
-            hd.active = false;
-            QMCB_CUDA(e);
-            throw std::runtime_error("the resident walker-segment kernel ended before answering (time-out inside the kernel?)");
-          }
+          hd.active = false;
+          QMCB_CUDA(e);
+          throw std::runtime_error("the resident walker-segment kernel ended before answering (time-out inside the kernel?)");
         }
       }
+    }
     std::atomic_thread_fence(std::memory_order_acquire);
+    // (the device wrote the chunk with one 16-byte store: tag visible => payload visible)
+    return (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
   }
-  void hd_post(unsigned seq)
+  static T bits_to_T(unsigned long long b)
   {
-    std::atomic_thread_fence(std::memory_order_release);
-    const_cast<volatile unsigned*>(hd.H.h_cmd)[0] = seq;
+    if constexpr (sizeof(T) == 4)
+    {
+      const unsigned u = (unsigned)b;
+      float f;
+      std::memcpy(&f, &u, 4);
+      return (T)f;
+    }
+    else
+    {
+      double d;
+      std::memcpy(&d, &b, 8);
+      return (T)d;
+    }
   }
   // leave the resident kernel (no-op when none is active): the completed moves stay applied, a proposed but undecided
   // move is dropped exactly as if its accept had never been called
@@ -2633,14 +2669,27 @@ struct Crowd : CrowdBase
   {
     if (!hd.active)
       return;
-    hd_post(SEG_ABORT);
+    std::atomic_thread_fence(std::memory_order_release);
+    const_cast<volatile unsigned*>(hd.H.h_cmd)[0] = SEG_ABORT;
     QMCB_CUDA(cudaStreamSynchronize(st));
     unsigned done[2] = {0, 0};
     QMCB_CUDA(cudaMemcpy(done, const_cast<unsigned*>(hd.H.d_cmd), sizeof(done), cudaMemcpyDeviceToHost));
     hd.active              = false;
     delay_count[hd.spin]   = hd.c0 + (int)done[1];
     invrow_id[hd.spin]     = -1;
-    const_cast<volatile unsigned*>(hd.H.h_cmd)[0] = hd.seq;
+    const_cast<volatile unsigned*>(hd.H.h_cmd)[0] = 0u;
+  }
+  // exchange 1, kernel -> host: the component-summed gradient of the prepared electron of every live walker
+  void hd_read_grads(unsigned seq, double* grads)
+  {
+    unsigned long long spins = 0;
+    for (int iw = 0; iw < nw; ++iw)
+      for (int d = 0; d < 3; ++d)
+      {
+        const unsigned long long b = hd_wait_chunk(hd.H.h_out1 + 3 * (size_t)iw + d, seq, spins);
+        if (grads)
+          grads[3 * (size_t)iw + d] = (double)bits_to_T(b);
+      }
   }
   // the four calls of the move loop; each returns false when the call has to take the launch-per-call path
   bool hd_eval_grad(int iat, double* grads)
@@ -2652,10 +2701,8 @@ struct Crowd : CrowdBase
       hd_abort();
       return false;
     }
-    hd_wait_ready(hd_seq(iat, 0));
+    hd_read_grads(hd_seq(iat, 0), grads);
     hd.grad_seen = true;
-    for (size_t i = 0; i < 3 * (size_t)nw; ++i)
-      grads[i] = (double)hd.H.h_grad[i];
     return true;
   }
   bool hd_make_move(int iat, const double* dsp)
@@ -2668,11 +2715,29 @@ struct Crowd : CrowdBase
       return false;
     }
     if (!hd.grad_seen)
-      hd_wait_ready(hd_seq(iat, 0)); // (the mailboxes of this exchange must have been written before they are reused)
-    T* h = const_cast<T*>(hd.H.h_displ);
-    for (int i = 0; i < 3 * nw; ++i)
-      h[i] = (T)dsp[i];
-    hd_post(hd_seq(iat, 0));
+      hd_read_grads(hd_seq(iat, 0), nullptr); // (every CTA must have consumed the previous reply before this one is written)
+    {
+      const unsigned seq = hd_seq(iat, 0);
+      unsigned char* h   = reinterpret_cast<unsigned char*>(const_cast<uint4*>(hd.H.h_in1));
+      for (int iw = 0; iw < nw; ++iw)
+      {
+        if constexpr (sizeof(T) == 4)
+        {
+          const float f[3] = {(float)dsp[3 * iw], (float)dsp[3 * iw + 1], (float)dsp[3 * iw + 2]};
+          unsigned u[3];
+          std::memcpy(u, f, 12);
+          store16(h + 16 * (size_t)iw, (unsigned long long)u[0] | ((unsigned long long)u[1] << 32),
+                  (unsigned long long)u[2] | ((unsigned long long)seq << 32));
+        }
+        else
+          for (int d = 0; d < 3; ++d)
+          {
+            unsigned long long b;
+            std::memcpy(&b, &dsp[3 * iw + d], 8);
+            store16(h + 16 * (size_t)(3 * iw + d), b, (unsigned long long)seq);
+          }
+      }
+    }
     hd.stage      = 1;
     last_move_iat = iat;
     return true;
@@ -2686,10 +2751,17 @@ struct Crowd : CrowdBase
       hd_abort();
       return false;
     }
-    hd_wait_ready(hd_seq(iat, 1));
-    std::memcpy(ratios, hd.H.h_ratio, (size_t)nw * sizeof(double));
-    for (size_t i = 0; i < 3 * (size_t)nw; ++i)
-      grads[i] = (double)hd.H.h_gradnew[i];
+    {
+      const unsigned seq       = hd_seq(iat, 1);
+      unsigned long long spins = 0;
+      for (int iw = 0; iw < nw; ++iw)
+      {
+        const unsigned long long rb = hd_wait_chunk(hd.H.h_out2 + 4 * (size_t)iw, seq, spins);
+        std::memcpy(&ratios[iw], &rb, 8);
+        for (int d = 0; d < 3; ++d)
+          grads[3 * (size_t)iw + d] = (double)bits_to_T(hd_wait_chunk(hd.H.h_out2 + 4 * (size_t)iw + 1 + d, seq, spins));
+      }
+    }
     hd.stage = 2;
     return true;
   }
@@ -2702,8 +2774,19 @@ struct Crowd : CrowdBase
       hd_abort();
       return false;
     }
-    std::memcpy(const_cast<unsigned char*>(hd.H.h_acc), acc, nw);
-    hd_post(hd_seq(iat, 1));
+    {
+      // one word per walker: (sequence number << 1) | accepted, four walkers per 16-byte chunk
+      const unsigned tag = (hd_seq(iat, 1) & 0x7fffffffu) << 1;
+      unsigned char* h   = reinterpret_cast<unsigned char*>(const_cast<uint4*>(hd.H.h_in2));
+      for (int e = 0; 4 * e < nw; ++e)
+      {
+        unsigned w4[4] = {0u, 0u, 0u, 0u};
+        for (int q = 0; q < 4 && 4 * e + q < nw; ++q)
+          w4[q] = tag | (acc[4 * e + q] ? 1u : 0u);
+        store16(h + 16 * (size_t)e, (unsigned long long)w4[0] | ((unsigned long long)w4[1] << 32),
+                (unsigned long long)w4[2] | ((unsigned long long)w4[3] << 32));
+      }
+    }
     hd.iat++;
     hd.stage     = 0;
     hd.grad_seen = false;

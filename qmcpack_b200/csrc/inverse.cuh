@@ -42,38 +42,59 @@ __device__ __forceinline__ cx<double> one_over(const cx<double>& v) { return cx<
 __device__ __forceinline__ bool is_zero(const double v) { return v == 0.0; }
 __device__ __forceinline__ bool is_zero(const cx<double>& v) { return v.re == 0.0 && v.im == 0.0; }
 
-// shared-memory bytes of the panel kernel
-template<typename V>
-inline size_t panel_smem(int n, int b)
+// two consecutive values of a 16-byte aligned shared-memory row
+__device__ __forceinline__ void ld2(const double* p, double& a, double& b)
 {
-  return (size_t)n * (b + 1) * sizeof(V) + (size_t)b * sizeof(V) + (size_t)(n + 15) / 16 * 16 + 64 * sizeof(int) +
+  const double2 v = *reinterpret_cast<const double2*>(p);
+  a = v.x, b = v.y;
+}
+__device__ __forceinline__ void st2(double* p, const double a, const double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+__device__ __forceinline__ void ld2(const cx<double>* p, cx<double>& a, cx<double>& b)
+{
+  const double2 v0 = reinterpret_cast<const double2*>(p)[0], v1 = reinterpret_cast<const double2*>(p)[1];
+  a = cx<double>(v0.x, v0.y), b = cx<double>(v1.x, v1.y);
+}
+__device__ __forceinline__ void st2(cx<double>* p, const cx<double>& a, const cx<double>& b)
+{
+  reinterpret_cast<double2*>(p)[0] = make_double2(a.re, a.im);
+  reinterpret_cast<double2*>(p)[1] = make_double2(b.re, b.im);
+}
+
+// shared-memory bytes of the panel kernel
+// (rows of BW + 2 values: 16-byte aligned for the vector accesses of the elimination, and a stride of 4 (mod 32) banks
+// per row, so that a quarter warp's 16-byte accesses to eight consecutive rows are conflict free)
+template<typename V>
+inline size_t panel_smem(int n, int BW)
+{
+  return (size_t)n * (BW + 2) * sizeof(V) + (size_t)BW * sizeof(V) + (size_t)(n + 15) / 16 * 16 + 64 * sizeof(int) +
          32 * sizeof(double) + 32 * sizeof(int);
 }
 
 // One panel step of one walker.  X [nw][n][n] row-major (in place); used [nw][n] row flags; R [nw][n] pivot row of every
 // column; W [nw][n][BW], Xr [nw][BW][n] (BW = slots allocated per panel, b <= BW used); logdet [nw][2]; info [nw].
-template<typename V>
-__global__ void __launch_bounds__(TPB) gj_panel_kernel(V* __restrict__ X, const int n, const int j0, const int b, const int BW,
+template<typename V, int BW>
+__global__ void __launch_bounds__(TPB) gj_panel_kernel(V* __restrict__ X, const int n, const int j0, const int b,
                                                        unsigned char* __restrict__ used, int* __restrict__ R,
                                                        V* __restrict__ W, V* __restrict__ Xr, double* __restrict__ logdet,
                                                        int* __restrict__ info)
 {
   extern __shared__ __align__(16) unsigned char gj_smem[];
   const int iw = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ldp = b + 1;
+  constexpr int ldp = BW + 2;
   V* Pn   = reinterpret_cast<V*>(gj_smem);
   V* prow = Pn + (size_t)n * ldp;
-  unsigned char* us = reinterpret_cast<unsigned char*>(prow + b);
+  unsigned char* us = reinterpret_cast<unsigned char*>(prow + BW);
   int* Rs           = reinterpret_cast<int*>(us + (size_t)(n + 15) / 16 * 16);
   double* rbest     = reinterpret_cast<double*>(Rs + 64);
   int* rbi          = reinterpret_cast<int*>(rbest + 32);
   V* Xw             = X + (size_t)iw * n * n;
   unsigned char* ug = used + (size_t)iw * n;
 
-  for (int e = tid; e < n * b; e += TPB)
+  // (a last, narrower panel is padded with zero columns: they stay zero through the eliminations)
+  for (int e = tid; e < n * BW; e += TPB)
   {
-    const int i = e / b, k = e - i * b;
-    Pn[(size_t)i * ldp + k] = Xw[(size_t)i * n + j0 + k];
+    const int i = e / BW, k = e - i * BW;
+    Pn[(size_t)i * ldp + k] = k < b ? Xw[(size_t)i * n + j0 + k] : V(0.0);
   }
   for (int i = tid; i < n; i += TPB)
     us[i] = j0 == 0 ? 0 : ug[i];
@@ -134,23 +155,32 @@ __global__ void __launch_bounds__(TPB) gj_panel_kernel(V* __restrict__ X, const 
         bad = j0 + k + 1; // singular (or NaN) pivot: reported like the `info` of getrf
     }
     const V rp = one_over(pv);
-    if (tid < b)
+    if (tid < BW)
       prow[tid] = tid == k ? rp : Pn[(size_t)p * ldp + tid] * rp;
     __syncthreads();
     // ---- eliminate column k from every other row; the column itself receives the new column of the inverse
+    // (row[k] <- 0 first, so that the uniform update row[c] -= f prow[c] leaves -f / pivot there); two values per access
     for (int i = tid; i < n; i += TPB)
     {
       V* row = Pn + (size_t)i * ldp;
       if (i == p)
       {
-        for (int c = 0; c < b; ++c)
-          row[c] = prow[c];
+#pragma unroll
+        for (int c = 0; c < BW; c += 2)
+          st2(row + c, prow[c], prow[c + 1]);
       }
       else
       {
         const V f = row[k];
-        for (int c = 0; c < b; ++c)
-          row[c] = c == k ? -(f * prow[k]) : row[c] - f * prow[c];
+        row[k]    = V(0.0);
+#pragma unroll
+        for (int c = 0; c < BW; c += 2)
+        {
+          V a0, a1, p0, p1;
+          ld2(row + c, a0, a1);
+          ld2(prow + c, p0, p1);
+          st2(row + c, a0 - f * p0, a1 - f * p1);
+        }
       }
     }
     __syncthreads();
@@ -199,8 +229,12 @@ __global__ void __launch_bounds__(TPB) gj_panel_kernel(V* __restrict__ X, const 
   }
 }
 
-// X[:, c] += W X[R, c] for every column outside the panel [j0, j0 + b).  grid (col tiles, row tiles, walkers); one CTA =
-// one 64 x 64 tile; warp (wr, wc) owns 16 rows x 32 columns = 2 x 4 accumulator tiles.
+// X[:, c] += W X[R, c] for every column outside the panel [j0, j0 + b).  grid (row tiles, walkers); one CTA owns a 64-row
+// block of one walker's matrix and walks over its 64-column tiles: the W block (64 x BW) is staged once, the X[R, :]
+// tiles (BW x 64) stream through a double-buffered cp.async ring, and the accumulator tile of the NEXT column tile is
+// loaded into registers while the DMMAs of the current one run -- the kernel is a stream over X (one read, one write per
+// panel step), so what matters is that every CTA always has loads in flight.  Warp (wr, wc) owns 16 rows x 32 columns
+// = 2 x 4 accumulator tiles.
 template<typename V, int BW>
 __global__ void __launch_bounds__(TPB) gj_update_kernel(V* __restrict__ X, const int n, const int j0, const int b,
                                                         const V* __restrict__ W, const V* __restrict__ Xr)
@@ -209,65 +243,124 @@ __global__ void __launch_bounds__(TPB) gj_update_kernel(V* __restrict__ X, const
   constexpr int SW = BW + 4, SX = TILE + 4; // conflict-free fragment loads (woodbury_dmma.cuh)
   extern __shared__ __align__(16) unsigned char gj_smem[];
   V* Ws = reinterpret_cast<V*>(gj_smem);
-  V* Xs = Ws + TILE * SW;
-  const int iw = blockIdx.z, r0 = blockIdx.y * TILE, c0 = blockIdx.x * TILE;
+  V* Xs = Ws + TILE * SW; // [2][BW][SX]
+  const int iw = blockIdx.y, r0 = blockIdx.x * TILE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  // a tile that lies entirely inside the panel has nothing to do
-  if (c0 >= j0 && c0 + TILE <= j0 + b)
+  const int nt = (n + TILE - 1) / TILE;
+  V* Xw        = X + (size_t)iw * n * n;
+  const V* Xrw = Xr + (size_t)iw * BW * n;
+  const int wr = warp >> 1, wc = warp & 1;
+  // a column tile that lies entirely inside the panel has nothing to do
+  auto skip = [&](int ct) { return ct * TILE >= j0 && ct * TILE + TILE <= j0 + b; };
+  auto next_tile = [&](int ct) {
+    ++ct;
+    while (ct < nt && skip(ct))
+      ++ct;
+    return ct;
+  };
+  // X[R, tile] -> shared memory (asynchronous; columns beyond n are zero)
+  auto stage_x = [&](int ct, int buf) {
+    V* dst = Xs + (size_t)buf * BW * SX;
+    for (int e = tid; e < BW * TILE; e += TPB)
+    {
+      const int k = e / TILE, c = e - k * TILE, col = ct * TILE + c;
+      if (col < n)
+      {
+        if constexpr (sizeof(V) == 8)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + k * SX + c)),
+                       "l"(Xrw + (size_t)k * n + col)
+                       : "memory");
+        else
+          cp_async16(dst + k * SX + c, Xrw + (size_t)k * n + col);
+      }
+      else
+        dst[k * SX + c] = zero_v<V>();
+    }
+    cp_async_commit();
+  };
+  // (real values: the next tile's accumulators wait in registers; complex values need twice the registers per tile
+  // and load theirs at the top of the tile's own iteration instead)
+  constexpr bool AHEAD = !value_traits<V>::is_complex;
+  Acc<V> acc[2][4], nxt[AHEAD ? 2 : 1][AHEAD ? 4 : 1];
+  auto load_c = [&](int ct, auto& dst) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+      {
+        const int row = r0 + 16 * wr + 8 * i + g, col = ct * TILE + 32 * wc + 8 * j + 2 * t;
+        dst[i][j].set(0, (row < n && col < n) ? Xw[(size_t)row * n + col] : zero_v<V>());
+        dst[i][j].set(1, (row < n && col + 1 < n) ? Xw[(size_t)row * n + col + 1] : zero_v<V>());
+      }
+  };
+
+  int ct = next_tile(-1);
+  if (ct >= nt)
     return;
+  stage_x(ct, 0);
+  if constexpr (AHEAD)
+    load_c(ct, nxt);
   for (int e = tid; e < TILE * BW; e += TPB)
   {
     const int i = e / BW, k = e - i * BW, row = r0 + i;
     Ws[i * SW + k] = row < n ? W[((size_t)iw * n + row) * BW + k] : zero_v<V>();
   }
-  for (int e = tid; e < BW * TILE; e += TPB)
+  int buf = 0;
+  while (ct < nt)
   {
-    const int k = e / TILE, c = e - k * TILE, col = c0 + c;
-    Xs[k * SX + c] = col < n ? Xr[((size_t)iw * BW + k) * n + col] : zero_v<V>();
-  }
-  V* Xw        = X + (size_t)iw * n * n;
-  const int wr = warp >> 1, wc = warp & 1;
-  Acc<V> acc[2][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
+    cp_async_wait<0>();
+    __syncthreads(); // this tile's X[R, :] (and, the first time, W) is in shared memory; the other buffer is free
+    if constexpr (AHEAD)
     {
-      const int row = r0 + 16 * wr + 8 * i + g, col = c0 + 32 * wc + 8 * j + 2 * t;
-      acc[i][j].set(0, (row < n && col < n) ? Xw[(size_t)row * n + col] : zero_v<V>());
-      acc[i][j].set(1, (row < n && col + 1 < n) ? Xw[(size_t)row * n + col + 1] : zero_v<V>());
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          acc[i][j] = nxt[i][j];
     }
-  __syncthreads();
+    else
+      load_c(ct, acc);
+    const int cn = next_tile(ct);
+    if (cn < nt)
+    {
+      stage_x(cn, buf ^ 1);
+      if constexpr (AHEAD)
+        load_c(cn, nxt);
+    }
+    const V* Xb = Xs + (size_t)buf * BW * SX;
 #pragma unroll
-  for (int ks = 0; ks < BW / 4; ++ks)
-  {
-    V a[2], bq[4];
+    for (int ks = 0; ks < BW / 4; ++ks)
+    {
+      V a[2], bq[4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
-      a[i] = lds_v(Ws + (16 * wr + 8 * i + g) * SW + 4 * ks + t);
+      for (int i = 0; i < 2; ++i)
+        a[i] = lds_v(Ws + (16 * wr + 8 * i + g) * SW + 4 * ks + t);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      bq[j] = lds_v(Xs + (4 * ks + t) * SX + 32 * wc + 8 * j + g);
+      for (int j = 0; j < 4; ++j)
+        bq[j] = lds_v(Xb + (4 * ks + t) * SX + 32 * wc + 8 * j + g);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          acc[i][j].mma(a[i], bq[j]);
+    }
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        acc[i][j].mma(a[i], bq[j]);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-    {
-      const int row = r0 + 16 * wr + 8 * i + g, col = c0 + 32 * wc + 8 * j + 2 * t;
-      if (row < n)
       {
-        if (col < n && (col < j0 || col >= j0 + b))
-          Xw[(size_t)row * n + col] = acc[i][j].get(0);
-        if (col + 1 < n && (col + 1 < j0 || col + 1 >= j0 + b))
-          Xw[(size_t)row * n + col + 1] = acc[i][j].get(1);
+        const int row = r0 + 16 * wr + 8 * i + g, col = ct * TILE + 32 * wc + 8 * j + 2 * t;
+        if (row < n)
+        {
+          if (col < n && (col < j0 || col >= j0 + b))
+            Xw[(size_t)row * n + col] = acc[i][j].get(0);
+          if (col + 1 < n && (col + 1 < j0 || col + 1 >= j0 + b))
+            Xw[(size_t)row * n + col + 1] = acc[i][j].get(1);
+        }
       }
-    }
+    ct = cn;
+    buf ^= 1;
+  }
 }
 
 // inverse of the pivot permutation and its parity (one CTA per walker): Rinv[R[c]] = c; the sign of the permutation

@@ -352,90 +352,154 @@ __device__ __forceinline__ bool seg_metropolis(const DriverDev<T>& Dr, const Jas
 // driver calling TrialWaveFunction::mw_evalGrad / mw_calcRatioGrad / mw_accept_rejectMove per electron), but the kernel
 // stays resident for the whole segment and talks to the host thread through mailboxes in pinned host memory instead of
 // being launched four times per move:
-//     kernel: gradient of the prepared electron -> h_grad, h_ready[iw] = seq        (qmcb_twf_mw_eval_grad reads it)
-//     host:   displacements -> h_displ, h_cmd = seq                                  (qmcb_ps_mw_make_move)
-//     kernel: ratio, new gradient -> h_ratio, h_gradnew, h_ready[iw] = seq + 1       (qmcb_twf_mw_calc_ratio_grad)
-//     host:   accept flags -> h_acc, h_cmd = seq + 1                                 (qmcb_twf_mw_accept_reject)
-// Only the CTA of walker 0 polls the host word over PCIe; it copies the host's reply into device memory and republishes
-// the sequence number there for the other CTAs.  h_cmd = SEG_ABORT makes every CTA leave at its next wait with the
-// state of the completed moves written back (the host falls back to the launch-per-call path, e.g. for an API call
-// that is not part of the move loop).
+//     kernel: gradient of the prepared electron -> h_out1                           (qmcb_twf_mw_eval_grad reads it)
+//     host:   displacements -> h_in1                                                 (qmcb_ps_mw_make_move)
+//     kernel: ratio, new gradient -> h_out2                                          (qmcb_twf_mw_calc_ratio_grad)
+//     host:   accept flags -> h_in2                                                  (qmcb_twf_mw_accept_reject)
+// Every message is made of 16-byte chunks that carry the sequence number of the exchange NEXT TO the payload and are
+// written with one 16-byte store, so a chunk is either old or complete: no flag word behind the data, no system-scope
+// fence between them, and the reader's polling load IS the data load (a PCIe read is a ~2 us round trip; "flag, then
+// data" would pay it twice).  Only the CTA of walker 0 polls host memory; it copies the host's reply into device memory
+// and republishes the sequence number there for the other CTAs.  h_cmd[0] = SEG_ABORT makes every CTA leave at its
+// next wait with the state of the completed moves written back (the host falls back to the launch-per-call path, e.g.
+// for an API call that is not part of the move loop).
 constexpr unsigned SEG_ABORT = 0xffffffffu;
 template<typename T>
 struct SegHost
 {
-  T* h_grad;                    // [nw][3] pinned host
-  double* h_ratio;              // [nw]
-  T* h_gradnew;                 // [nw][3]
-  volatile unsigned* h_ready;   // [nw]
-  const T* h_displ;             // [nw][3]
-  const unsigned char* h_acc;   // [nw]
-  volatile unsigned* h_cmd;     // [1] (+ [1]: error word written by the kernel)
+  uint4* h_out1;                // [nw][3]  {value (T, low bytes of 8), -, tag, -}: gradient components           pinned host
+  uint4* h_out2;                // [nw][4]  chunk 0: ratio (double); chunks 1-3: new gradient components (T); tag in .z
+  const uint4* h_in1;           // float: [nw] {dx, dy, dz, tag}; double: [nw][3] {value (8 bytes), tag, -}
+  const uint4* h_in2;           // [ceil(nw / 4)] words (seq << 1) | accepted, one per walker
+  volatile unsigned* h_cmd;     // [0] SEG_ABORT request (host -> kernel), [1] error word written by the kernel
   T* d_displ;                   // [nw][3] device copies published by walker 0's CTA
   unsigned char* d_acc;         // [nw]
   volatile unsigned* d_cmd;     // [1] last sequence number republished on the device, [1] moves completed by this launch
   unsigned seq0;                // sequence number of the first exchange of this launch
 };
 
-// one warp waits until the host has answered exchange `seq`; the warp of walker 0 fetches the answer (count bytes from
-// src_host to dst_dev) and republishes.  Returns false on abort / time-out.
-template<typename T>
-__device__ __forceinline__ bool seg_host_wait(const SegHost<T>& H, const int iw, const unsigned seq, const void* src_host,
-                                              void* dst_dev, const int bytes)
+__device__ __forceinline__ uint4 ld_sys16(const uint4* p)
+{
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_sys16(uint4* p, const uint4 v)
+{
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// one outgoing chunk: the value's bits in .x/.y, the tag in .z
+__device__ __forceinline__ void seg_post(uint4* slot, const float v, const unsigned tag)
+{
+  st_sys16(slot, make_uint4(__float_as_uint(v), 0u, tag, 0u));
+}
+__device__ __forceinline__ void seg_post(uint4* slot, const double v, const unsigned tag)
+{
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  st_sys16(slot, make_uint4((unsigned)b, (unsigned)(b >> 32), tag, 0u));
+}
+
+// One warp waits until the host has answered exchange `seq` (KIND 1: displacements, KIND 2: accept flags); the warp of
+// walker 0 polls the tagged chunks in host memory -- all loads of a pass in flight at once, up to 8 per lane -- unpacks
+// them into device memory and republishes.  Returns false on abort / time-out.
+template<typename T, int KIND>
+__device__ __forceinline__ bool seg_host_wait(const SegHost<T>& H, const int iw, const int nw, const unsigned seq)
 {
   const int lane = threadIdx.x & 31;
   unsigned got   = 0;
   if (iw == 0)
   {
-    long long spins = 0;
+    constexpr bool compact = sizeof(T) == 4;
+    const uint4* src = KIND == 1 ? H.h_in1 : H.h_in2;
+    const int n16    = KIND == 1 ? (compact ? nw : 3 * nw) : (nw + 3) / 4;
+    long long spins  = 0;
     while (true)
     {
-      got = H.h_cmd[0];
-      if (got == SEG_ABORT || (int)(got - seq) >= 0)
-        break;
-      if (++spins > (1ll << 24)) // ~ seconds: the host thread is gone
-      {
-        got = SEG_ABORT;
-        if (lane == 0)
-          H.h_cmd[1] = 1u;
-        break;
-      }
-      __nanosleep(200);
-    }
-    if (got != SEG_ABORT)
-    {
-      __threadfence_system();
-      // the reply crosses PCIe: every load is a ~2 us round trip, so ALL of a lane's loads are requested before the
-      // first store (a load/store loop would pay the round trips one after the other); 16-byte loads (the mailboxes are
-      // 16-byte aligned and padded), up to 8 per lane per pass = 4 KB per pass
-      const uint4* s16 = static_cast<const uint4*>(src_host);
-      uint4* d16       = static_cast<uint4*>(dst_dev);
-      const int n16    = (bytes + 15) / 16;
-      for (int e0 = 0; e0 < n16; e0 += 8 * 32)
+      const unsigned cmd = H.h_cmd[0];
+      bool ok            = true;
+      for (int e0 = 0; e0 < n16 && ok; e0 += 8 * 32)
       {
         uint4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
         {
           const int e = e0 + 32 * u + lane;
-          if (e < n16)
-            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
-                         : "l"(s16 + e));
+          v[u]        = e < n16 ? ld_sys16(src + e) : make_uint4(0u, 0u, 0u, 0u);
         }
+        bool mine = true;
 #pragma unroll
         for (int u = 0; u < 8; ++u)
         {
           const int e = e0 + 32 * u + lane;
           if (e < n16)
-            d16[e] = v[u];
+          {
+            if (KIND == 1)
+              mine = mine && (compact ? v[u].w : v[u].z) == seq;
+            else
+            {
+              const unsigned w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (4 * e + q < nw)
+                  mine = mine && (w4[q] >> 1) == (seq & 0x7fffffffu);
+            }
+          }
+        }
+        ok = __all_sync(0xffffffffu, mine);
+        if (ok)
+        {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+          {
+            const int e = e0 + 32 * u + lane;
+            if (e < n16)
+            {
+              if (KIND == 1)
+              {
+                if constexpr (compact)
+                {
+                  H.d_displ[3 * e]     = (T)__uint_as_float(v[u].x);
+                  H.d_displ[3 * e + 1] = (T)__uint_as_float(v[u].y);
+                  H.d_displ[3 * e + 2] = (T)__uint_as_float(v[u].z);
+                }
+                else
+                  H.d_displ[e] = (T)__longlong_as_double((long long)(((unsigned long long)v[u].y << 32) | v[u].x));
+              }
+              else
+              {
+                const unsigned w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (4 * e + q < nw)
+                    H.d_acc[4 * e + q] = (unsigned char)(w4[q] & 1u);
+              }
+            }
+          }
         }
       }
-      __threadfence();
+      if (ok)
+      {
+        got = seq;
+        break;
+      }
+      if (cmd == SEG_ABORT)
+      {
+        got = SEG_ABORT;
+        break;
+      }
+      if (++spins > (1ll << 23)) // ~ seconds: the host thread is gone
+      {
+        got = SEG_ABORT;
+        if (lane == 0)
+          H.h_cmd[1] = 1u;
+        break;
+      }
+      __nanosleep(100);
     }
+    __threadfence();
     __syncwarp();
     if (lane == 0)
-      H.d_cmd[0] = got == SEG_ABORT ? SEG_ABORT : seq;
+      H.d_cmd[0] = got;
   }
   else
   {
@@ -558,12 +622,8 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
             gd += J.Grad1[((size_t)iw * 3 + d) * J.N + iat];
           const T rold = J.rsoa[((size_t)iw * 3 + d) * J.npad + iat];
           if (lane < 3)
-            H.h_grad[3 * iw + d] = gd;
-          __threadfence_system();
-          __syncwarp();
-          if (lane == 0)
-            H.h_ready[iw] = seq;
-          const bool ok = seg_host_wait<T>(H, iw, seq, H.h_displ, H.d_displ, 3 * Dr.nw * (int)sizeof(T));
+            seg_post(H.h_out1 + 3 * iw + d, gd, seq);
+          const bool ok = seg_host_wait<T, 1>(H, iw, Dr.nw, seq);
           if (ok)
           {
             const T p = rold + __ldcg(H.d_displ + 3 * iw + d); // (written by another SM: not through L1)
@@ -860,17 +920,10 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
             gn[0] += jsum[6], gn[1] += jsum[7], gn[2] += jsum[8];
           }
           if (lane == 0)
-          {
-            H.h_ratio[iw]           = ratio;
-            H.h_gradnew[3 * iw]     = gn[0];
-            H.h_gradnew[3 * iw + 1] = gn[1];
-            H.h_gradnew[3 * iw + 2] = gn[2];
-          }
-          __threadfence_system();
-          __syncwarp();
-          if (lane == 0)
-            H.h_ready[iw] = seq;
-          const bool ok = seg_host_wait<T>(H, iw, seq, H.h_acc, H.d_acc, Dr.nw);
+            seg_post(H.h_out2 + 4 * iw, ratio, seq);
+          else if (lane < 4)
+            seg_post(H.h_out2 + 4 * iw + lane, lane == 1 ? gn[0] : (lane == 2 ? gn[1] : gn[2]), seq);
+          const bool ok = seg_host_wait<T, 2>(H, iw, Dr.nw, seq);
           acc           = ok && __ldcg(H.d_acc + iw) != 0;
           if (!ok && lane == 0)
             s_abort = 1;
@@ -1219,6 +1272,9 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
     }
     else if (part1 && s_acc != 0)
       jastrow_accept_body<T>(Group{tid - SEG_TPB / 2, SEG_TPB / 2, 2}, J, iw, iat, jl);
+    // (pulling the rows the NEXT move's staging reads cold -- stale inverse row, gradient rows, Gaussians of electron
+    // row + 2 -- into L2 from this phase was measured too: 1278 vs 1259 us per segment, i.e. slightly slower, like the
+    // prefetch under the gather (QMCB_SEG_PREFETCH above); the staging is not DRAM-latency bound)
     SEG_STAMP(13, 224); // Jastrow accept
     if (nvs > 0)
       v_phase ^= 1u;

@@ -119,12 +119,27 @@ void advance_crowd(CrowdCtx& cx, int N, double tau, bool use_drift, uint8_t* log
   const int cs = qmcb_crowd_is_complex(cx.crowd) ? 2 : 1;
   std::vector<double> grads(3 * (size_t)nw * cs), displ(3 * (size_t)nw), ratios((size_t)nw * cs);
   std::vector<uint8_t> accepted(nw);
+  std::vector<double> uni(nw);
   assignGaussRand(walker_deltas.data(), (unsigned)walker_deltas.size(), cx.rng);
   for (int iat = 0; iat < N; ++iat)
   {
+    // Everything that does not depend on the device's answers runs HERE, while the device still applies the previous
+    // accept and prepares this electron's row: the scaled Gaussians, log_gf (a function of the Gaussians only) and the
+    // uniforms of the accept tests, drawn ahead from a COPY of the crowd's engine -- the reference draws walker i's
+    // uniform only when prob[i] >= eps (VMCBatched.cpp:156-158), so the copy is committed only when every walker of the
+    // move turns out to draw; otherwise the tests are replayed from the untouched engine, walker by walker.
     for (int i = 0; i < nw; ++i)
       for (int d = 0; d < 3; ++d)
         deltas[3 * i + d] = walker_deltas[3 * ((size_t)iat * nw + i) + d] * sqrttau;
+    if (use_drift)
+      for (int i = 0; i < nw; ++i)
+      {
+        const RT* dl = &deltas[3 * i];
+        log_gf[i]    = -oneover2tau * (dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
+      }
+    StdRandom ahead = cx.rng;
+    for (int i = 0; i < nw; ++i)
+      uni[i] = ahead();
     pc.lap(0);
     if (use_drift)
     {
@@ -151,8 +166,6 @@ void advance_crowd(CrowdCtx& cx, int N, double tau, bool use_drift, uint8_t* log
     if (use_drift)
       for (int i = 0; i < nw; ++i)
       {
-        const RT* dl = &deltas[3 * i];
-        log_gf[i]    = -oneover2tau * (dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
         const RT g[3] = {(RT)grads[(3 * i) * cs], (RT)grads[(3 * i + 1) * cs], (RT)grads[(3 * i + 2) * cs]};
         RT dr[3];
         getDrift<RT>(tauovermass, g, dr);
@@ -162,10 +175,16 @@ void advance_crowd(CrowdCtx& cx, int N, double tau, bool use_drift, uint8_t* log
       }
     for (int i = 0; i < nw; ++i)
       prob[i] = cs == 2 ? (RT)(ratios[2 * i] * ratios[2 * i] + ratios[2 * i + 1] * ratios[2 * i + 1]) : (RT)(ratios[i] * ratios[i]);
+    bool all_draw = true;
+    for (int i = 0; i < nw; ++i)
+      all_draw = all_draw && prob[i] >= std::numeric_limits<RT>::epsilon();
+    if (all_draw)
+      cx.rng = ahead; // every walker consumed exactly the uniform drawn ahead for it
     for (int i = 0; i < nw; ++i)
     {
       // the uniform is drawn only when the move is valid and prob >= eps (VMCBatched.cpp:156-158)
-      if (prob[i] >= std::numeric_limits<RT>::epsilon() && cx.rng() < prob[i] * std::exp(log_gb[i] - log_gf[i]))
+      if (prob[i] >= std::numeric_limits<RT>::epsilon() &&
+          (all_draw ? uni[i] : cx.rng()) < prob[i] * std::exp(log_gb[i] - log_gf[i]))
       {
         accepted[i] = 1;
         cx.n_accept++;

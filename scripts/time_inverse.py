@@ -17,7 +17,7 @@ c = workload.CONFIGS[args.config]
 cplx = bool(c.get("complex_orbitals"))
 n = c["N"] // 2
 # only the determinant engine is exercised: a tiny table, the benchmarked matrix size
-t = workload.pw_table((6, 6, 6), n, np.float64, 3) if not cplx else workload.pw_table_complex((6, 6, 6), n, np.float64, 3)
+t = workload.pw_table((12, 12, 12), n, np.float64, 3) if not cplx else workload.pw_table_complex((12, 12, 12), n, np.float64, 3)
 s = dict(n_up=n, n_dn=n, lattice=np.eye(3) * 6.0 * (n / 12) ** (1 / 3), coefs=[t, t])
 if cplx:
     kp = np.tile([0.1, 0.2, 0.3], (n, 1))
