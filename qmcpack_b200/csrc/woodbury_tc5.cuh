@@ -193,12 +193,13 @@ __global__ void __launch_bounds__(TPB, 2) woodbury_flush_tc5_kernel(const DetDev
     mbar_init(&bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // Binv (transposed, zero beyond the c pending slots) and the delay list
-  for (int e = tid; e < KD * KD; e += TPB)
-  {
-    const int a = e / KD, b = e - a * KD;
-    BinvT[b][a] = (a < c && b < c) ? __ldg(B + a * k + b) : 0.f;
-  }
+  // Binv (transposed, zero beyond the c pending slots; only needed when U' is formed here) and the delay list
+  if (!up_ready)
+    for (int e = tid; e < KD * KD; e += TPB)
+    {
+      const int a = e / KD, b = e - a * KD;
+      BinvT[b][a] = (a < c && b < c) ? __ldg(B + a * k + b) : 0.f;
+    }
   if (tid < KD)
     lst[tid] = tid < c ? D.list[(size_t)iw * k + tid] : -1;
   fence_before_sync();
@@ -392,6 +393,8 @@ __global__ void __launch_bounds__(TPB, 2) woodbury_flush_tc5_kernel(const DetDev
           __syncwarp();
         }
       }
+      // (requesting both halves' tile rows before tcgen05.ld was measured: 270 vs 250 us per flush in the sweep -- the
+      // 32 extra live registers spill at the 128-register budget of two CTAs per SM)
     }
     fence_before_sync();
     __syncthreads(); // patches (and D2) are free for the next piece
