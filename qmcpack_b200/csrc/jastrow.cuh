@@ -335,100 +335,115 @@ __device__ __forceinline__ void jastrow_move_body(const JastrowDev<RT>& J, const
 // it * 32 nwarps + 32 wg + lane, compacts its in-range pairs into its own list segment and leaves its ten partial sums
 // {J2: u, gx, gy, gz, lap; J1: the same} in part[0..10) (shared memory, 16 entries per warp); whoever consumes the sums
 // adds the warps' partials in index order.  jl: >= ceil((N + nions) / (32 nwarps)) * 32 nwarps entries.
+#ifndef QMCB_JB
+#define QMCB_JB 1 // position loads of JB iterations in flight at once (B200, NiO-a64, 512 walkers, segment kernels per sweep:
+                  // 1 -> 32.5 ms, 2 -> 35.4 ms, 3 -> 40.0 ms: the kernel lives on 64 registers per thread)
+#endif
+// The same work as a resumable object: init(), one pass1(it) per block of 32 nwarps candidates (each a short chain of
+// dependent loads: positions -> distance -> cutoff test), finish() = functors over the compacted list + reduction.  The
+// walker-segment kernel interleaves the pass1 steps with the stencil slabs of the spline gather (segment.cuh), so that
+// the slab stream never waits for the Jastrow sums and vice versa.
+template<typename RT>
+struct JastrowMove
+{
+  int cnt, iters, n2, n1, gi, tid, STEP, np;
+  unsigned short* seg;
+  const RT* rs;
+  __device__ __forceinline__ void init(const int wg, const int nwarps, const JastrowDev<RT>& J, const int iw, const int iat,
+                                       unsigned short* jl)
+  {
+    const int lane = threadIdx.x & 31;
+    np = J.npad, STEP = 32 * nwarps, tid = 32 * wg + lane;
+    rs    = J.rsoa + (size_t)iw * 3 * np;
+    n2    = J.has_j2 ? J.N : 0;
+    n1    = J.has_j1 ? J.nions : 0;
+    gi    = (iat < J.n_up ? 0 : 1) * 2;
+    iters = (n2 + n1 + STEP - 1) / STEP;
+    seg   = jl + wg * iters * 32;
+    cnt   = 0;
+  }
+  // pass 1, iteration `it`: distance of candidate it * STEP + tid, in-range pairs compacted into the warp's list
+  __device__ __forceinline__ void pass1(const JastrowDev<RT>& J, const int iat, const RT pos[3], const int it)
+  {
+    const int lane = threadIdx.x & 31;
+    const int idx  = it * STEP + tid;
+    RT px(0), py(0), pz(0);
+    if (idx < n2)
+      px = rs[idx], py = rs[np + idx], pz = rs[2 * np + idx];
+    else if (idx < n2 + n1)
+    {
+      const int j = idx - n2;
+      px = J.ion_rsoa[j], py = J.ion_rsoa[J.npad_ion + j], pz = J.ion_rsoa[2 * J.npad_ion + j];
+    }
+    bool need = false;
+    RT r, dx, dy, dz;
+    if (idx < n2)
+    {
+      min_image(J.cell, pos, px, py, pz, idx, iat, r, dx, dy, dz);
+      const FunctorDev<RT>& F = J.F2[gi + (idx < J.n_up ? 0 : 1)];
+      need                    = idx != iat && F.coefs != nullptr && r < F.rcut;
+    }
+    else if (idx < n2 + n1)
+    {
+      min_image(J.cell, pos, px, py, pz, idx - n2, 0, r, dx, dy, dz);
+      const FunctorDev<RT>& F = J.F1[J.ion_grp[idx - n2]];
+      need                    = F.coefs != nullptr && r < F.rcut;
+    }
+    const unsigned mk = __ballot_sync(0xffffffffu, need);
+    if (need)
+      seg[cnt + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)idx;
+    cnt += __popc(mk);
+  }
+  // pass 2: functors over the warp's list; the ten partial sums go to part[0..10)
+  __device__ __forceinline__ void finish(const JastrowDev<RT>& J, const int iat, const RT pos[3], RT* part)
+  {
+    const int lane = threadIdx.x & 31;
+    RT acc[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      acc[e] = RT(0);
+    __syncwarp();
+    for (int e = lane; e < cnt; e += 32)
+    {
+      const int idx = seg[e];
+      RT r, dx, dy, dz, du, d2u;
+      if (idx < n2)
+      {
+        min_image(J.cell, pos, rs[idx], rs[np + idx], rs[2 * np + idx], idx, iat, r, dx, dy, dz);
+        const RT u = functor_eval(J.F2[gi + (idx < J.n_up ? 0 : 1)], r, du, d2u);
+        acc[0] += u;
+        acc[1] += du * dx;
+        acc[2] += du * dy;
+        acc[3] += du * dz;
+        acc[4] += d2u + RT(2) * du;
+      }
+      else
+      {
+        const int j = idx - n2;
+        min_image(J.cell, pos, J.ion_rsoa[j], J.ion_rsoa[J.npad_ion + j], J.ion_rsoa[2 * J.npad_ion + j], j, 0, r, dx, dy, dz);
+        const RT u = functor_eval(J.F1[J.ion_grp[j]], r, du, d2u);
+        acc[5] += u;
+        acc[6] += du * dx;
+        acc[7] += du * dy;
+        acc[8] += du * dz;
+        acc[9] += d2u + RT(2) * du;
+      }
+    }
+    warp_fold<RT, 16>(acc); // lane l holds the total of value l >> 1
+    if ((lane & 1) == 0 && (lane >> 1) < 10)
+      part[lane >> 1] = acc[0];
+  }
+};
+
 template<typename RT>
 __device__ __forceinline__ void jastrow_move_warps(const int wg, const int nwarps, const JastrowDev<RT>& J, const int iw,
                                                    const int iat, const RT pos[3], unsigned short* jl, RT* part)
 {
-  const int lane = threadIdx.x & 31, N = J.N, np = J.npad, STEP = 32 * nwarps, tid = 32 * wg + lane;
-  const RT* rs = J.rsoa + (size_t)iw * 3 * np;
-  RT acc[16];
-#pragma unroll
-  for (int e = 0; e < 16; ++e)
-    acc[e] = RT(0);
-  const int n2 = J.has_j2 ? N : 0, n1 = J.has_j1 ? J.nions : 0;
-  const int gi = (iat < J.n_up ? 0 : 1) * 2;
-  const int iters  = (n2 + n1 + STEP - 1) / STEP;
-  unsigned short* seg = jl + wg * iters * 32;
-  int cnt = 0;
-  // pass 1: every distance; the position loads of up to JB iterations are requested before the first is used (one
-  // memory round trip per JB * 32 nwarps candidates)
-#ifndef QMCB_JB
-#define QMCB_JB 1 // measured on B200 (NiO-a64, 512 walkers, segment kernel per sweep): 1 -> 32.5 ms, 2 -> 35.4 ms, 3 -> 40.0 ms
-#endif
-  constexpr int JB = QMCB_JB;
-  for (int it = 0; it < iters; it += JB)
-  {
-    int idx[JB];
-    RT px[JB], py[JB], pz[JB];
-#pragma unroll
-    for (int h = 0; h < JB; ++h)
-    {
-      idx[h] = (it + h < iters) ? (it + h) * STEP + tid : n2 + n1;
-      px[h] = py[h] = pz[h] = RT(0);
-      if (idx[h] < n2)
-        px[h] = rs[idx[h]], py[h] = rs[np + idx[h]], pz[h] = rs[2 * np + idx[h]];
-      else if (idx[h] < n2 + n1)
-      {
-        const int j = idx[h] - n2;
-        px[h] = J.ion_rsoa[j], py[h] = J.ion_rsoa[J.npad_ion + j], pz[h] = J.ion_rsoa[2 * J.npad_ion + j];
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < JB; ++h)
-    {
-      if (it + h >= iters)
-        break;
-      bool need = false;
-      RT r, dx, dy, dz;
-      if (idx[h] < n2)
-      {
-        min_image(J.cell, pos, px[h], py[h], pz[h], idx[h], iat, r, dx, dy, dz);
-        const FunctorDev<RT>& F = J.F2[gi + (idx[h] < J.n_up ? 0 : 1)];
-        need                    = idx[h] != iat && F.coefs != nullptr && r < F.rcut;
-      }
-      else if (idx[h] < n2 + n1)
-      {
-        min_image(J.cell, pos, px[h], py[h], pz[h], idx[h] - n2, 0, r, dx, dy, dz);
-        const FunctorDev<RT>& F = J.F1[J.ion_grp[idx[h] - n2]];
-        need                    = F.coefs != nullptr && r < F.rcut;
-      }
-      const unsigned mk = __ballot_sync(0xffffffffu, need);
-      if (need)
-        seg[cnt + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)idx[h];
-      cnt += __popc(mk);
-    }
-  }
-  __syncwarp();
-  // pass 2: functors over the warp's list
-  for (int e = lane; e < cnt; e += 32)
-  {
-    const int idx = seg[e];
-    RT r, dx, dy, dz, du, d2u;
-    if (idx < n2)
-    {
-      min_image(J.cell, pos, rs[idx], rs[np + idx], rs[2 * np + idx], idx, iat, r, dx, dy, dz);
-      const RT u = functor_eval(J.F2[gi + (idx < J.n_up ? 0 : 1)], r, du, d2u);
-      acc[0] += u;
-      acc[1] += du * dx;
-      acc[2] += du * dy;
-      acc[3] += du * dz;
-      acc[4] += d2u + RT(2) * du;
-    }
-    else
-    {
-      const int j = idx - n2;
-      min_image(J.cell, pos, J.ion_rsoa[j], J.ion_rsoa[J.npad_ion + j], J.ion_rsoa[2 * J.npad_ion + j], j, 0, r, dx, dy, dz);
-      const RT u = functor_eval(J.F1[J.ion_grp[j]], r, du, d2u);
-      acc[5] += u;
-      acc[6] += du * dx;
-      acc[7] += du * dy;
-      acc[8] += du * dz;
-      acc[9] += d2u + RT(2) * du;
-    }
-  }
-  warp_fold<RT, 16>(acc); // lane l holds the total of value l >> 1
-  if ((lane & 1) == 0 && (lane >> 1) < 10)
-    part[lane >> 1] = acc[0];
+  JastrowMove<RT> jm;
+  jm.init(wg, nwarps, J, iw, iat, jl);
+  for (int it = 0; it < jm.iters; ++it)
+    jm.pass1(J, iat, pos, it);
+  jm.finish(J, iat, pos, part);
 }
 
 // ---- ratios at VIRTUAL positions (non-local pseudopotential quadrature points): TwoBodyJastrow::mw_evaluateRatios

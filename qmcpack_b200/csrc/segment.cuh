@@ -657,6 +657,11 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         const int blk = cfirst / SEG_BOXW, loc = cfirst - blk * SEG_BOXW;
         // Jastrow sums at the proposed position while the first slabs are in flight (every warp derives the proposal
         // itself: a handful of L1/L2 hits and shuffles, no barrier)
+        // Jastrow sums at the proposed position while the first slabs are in flight (every warp derives the proposal
+        // itself: a handful of L1/L2 hits and shuffles, no barrier).  Interleaving the blocks of the distance pass with the
+        // slabs below (one block, one slab, ..., functor pass after the spline epilogue; JastrowMove in jastrow.cuh is
+        // resumable for that) was measured: 32.7 vs 30.6 ms of segment kernels per sweep -- the state carried across the
+        // slab loop spills at 64 registers per thread
         if (J.has_j2 || J.has_j1)
         {
           T np3[3];
