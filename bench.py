@@ -15,7 +15,9 @@ move, distance rows, spline SPO evaluation, determinant ratio/gradient, J1/J2, M
   e2e       the same metric through the reference-facing C ABI with HOST buffers: the compiled host driver
             (include/qmcb_driver.h) issues evalGrad / makeMove / calcRatioGrad / accept_reject per electron, positions,
             gradients, ratios and accept flags cross PCIe every move, accept test on the host -- how QMCPACK's batched
-            driver would call this library.
+            driver would call this library.  One host thread per crowd (--crowds, default 8, never more than this rank's
+            share of the cores); `host_kernel_mode` 2 = the calls were mailbox exchanges with a resident walker-segment
+            kernel, 1 = kernel launches per call.
   roofline  the dominant kernel of the sweep.  With the walker-segment kernel: its launches timed with CUDA events in
             one profiled sweep (qmcb_vmc_profile_sweep), algorithmic bytes per launch = SURVEY 8d's per-move figure
             (64*Npad*4 stencil + 5*n*4 + n*4) x walkers x moves per launch, against the measured HBM copy bandwidth of
@@ -24,6 +26,10 @@ move, distance rows, spline SPO evaluation, determinant ratio/gradient, J1/J2, M
   flush     the rank-k Woodbury flush (mw_updateInvMat) timed alone through the qmcb_det_time_update_inv_mat hook:
             algorithmic TF/s, one-pass GB/s; `flush_fp64` the same for the full-precision shapes (NiO-a64 real k = 32,
             NiO-a128 complex k = 64) against `fp64_peak` = cublasDgemm 8192^3 measured in this run.
+  recompute the FP64 inverse + log-determinant of mw_recompute on the benchmark crowd's own matrices: this library's blocked
+            Gauss-Jordan kernels beside cublas<t>getrfBatched + getriBatched, the routines the reference calls.
+  dmc       three DMC generations (device sweep with the DMC rule + C++ WalkerControl::branch) with the all-reduce and the
+            packed-walker ncclSend/Recv inside the timed region; --dmc makes it the headline.
   cpu_baseline  the reference's CPU path (oracle/_ref: spline2::evaluate_vgh_impl + DelayedUpdate<T> + DiracMatrix compiled
             from /root/reference, else the oracle port) on the host cores, on a bounded sample of the same workload.
 """
@@ -407,9 +413,9 @@ def run_b200(args, rank, local_rank, world):
     recompute = None
     if rank == 0 and not args.no_recompute:
         try:
-            cr0, nwr = dcrowds[0], dsizes[0]
-            us_own = cr0.det_time_inverse(0, 2, reps=2)
-            us_cub = cr0.det_time_inverse(0, 1, reps=1)
+            nwr = dsizes[0]
+            us_own = dcrowds[0].det_time_inverse(0, 2, reps=2)
+            us_cub = dcrowds[0].det_time_inverse(0, 1, reps=1)
             fl = (4 if cplx else 1) * 2.0 * n ** 3 * nwr
             recompute = {"walkers": nwr, "n": n, "us_own": us_own, "us_cublas": us_cub, "speedup_vs_cublas": us_cub / us_own,
                          "tflops_own": fl / us_own * 1e-6, "tflops_cublas": fl / us_cub * 1e-6,
@@ -523,7 +529,9 @@ def run_b200(args, rank, local_rank, world):
     # ---------------- end to end through the C ABI with host buffers
     e2e = None
     if not args.no_e2e:
-        ncr = max(1, min(args.crowds, nw))
+        # one spinning host thread per crowd (the mailbox exchanges are polled): never more crowds per rank than this
+        # rank's share of the box's cores (8 ranks on a 32-core box: 4 crowds each)
+        ncr = max(1, min(args.crowds, nw, max(1, (os.cpu_count() or 1) // max(world, 1))))
         base, extra = divmod(nw, ncr)
         sizes = [base + (1 if i < extra else 0) for i in range(ncr)]
         crowds, off = [], 0
@@ -548,6 +556,9 @@ def run_b200(args, rank, local_rank, world):
         e2e = {"value": world * nw * N * args.steps / dt_max, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "crowds": ncr,
                "ms_per_step": 1e3 * dt_max / args.steps,
+               # how the per-electron calls were served: 2 = mailbox exchanges with a resident walker-segment kernel,
+               # 1 = kernel launches per call (qmcb_crowd_host_kernel)
+               "host_kernel_mode": sorted({c_.host_kernel for c_ in crowds}),
                "path": "qmcb_host_vmc_run: per-electron qmcb_twf_mw_eval_grad / qmcb_ps_mw_make_move / "
                        "qmcb_twf_mw_calc_ratio_grad / qmcb_twf_mw_accept_reject with host buffers, accept test on the host"}
         e2e["device_driver"] = e2e_dd

@@ -2607,7 +2607,10 @@ struct Crowd : CrowdBase
       return true;
     }
     else
+    {
+      hd.tried = true; // (complex orbitals: the per-electron calls are launches; host_kernel() reports 1)
       return false;
+    }
   }
   unsigned hd_seq(int iat, int second) const { return hd.seq0 + 2u * (unsigned)(iat - hd.iat0) + (unsigned)second; }
   // one 16-byte chunk {lo, hi} of a mailbox written by ONE store, so that the kernel's 16-byte read sees the tag (in the
