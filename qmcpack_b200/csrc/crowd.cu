@@ -866,7 +866,7 @@ struct Crowd : CrowdBase
   bool fused = false;
   double seg_reserved_sms = 0.0;
   SegRng segrng{};
-  DevBuf<unsigned> seg_flags, seg_tot_tag;
+  DevBuf<unsigned> seg_flags, seg_tot_tag, seg_btot;
   DevBuf<unsigned long long> seg_tot_val;
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_logs = false;
@@ -2465,7 +2465,9 @@ struct Crowd : CrowdBase
     A(seg_flags, (size_t)N * cap);
     A(seg_tot_val, (size_t)N + 1);
     A(seg_tot_tag, (size_t)N + 1);
+    A(seg_btot, (size_t)N * 32);
     segrng.flags = seg_flags.p, segrng.tot_val = seg_tot_val.p, segrng.tot_tag = seg_tot_tag.p, segrng.stride = cap;
+    segrng.btot = seg_btot.p;
   }
   int vmc_sweep_kernel() const override { return vmc_ready ? (fused ? 2 : 1) : 0; }
   int host_kernel() const override { return hd.tried ? (hd.enabled ? 2 : 1) : 0; }

@@ -517,8 +517,15 @@ struct J2Pair
 // jl: JAS_LIST entries of shared memory for the group
 template<typename RT>
 __device__ __forceinline__ void jastrow_accept_body(const Group& g, const JastrowDev<RT>& J, const int iw, const int iat,
-                                                    unsigned short* jl)
+                                                    unsigned short* jl, long long* tr = nullptr /* debug trace (segment.cuh) */)
 {
+#define JAS_TR(id)             \
+  do                           \
+  {                            \
+    if (tr && g.tid == 0)      \
+      tr[id] = clock64();      \
+  } while (0)
+  JAS_TR(36);
   const int tid = g.tid, N = J.N, np = J.npad;
   const int lane = tid & 31, wg = tid >> 5, nwg = g.n >> 5;
   if (J.has_j2)
@@ -605,6 +612,7 @@ __device__ __forceinline__ void jastrow_accept_body(const Group& g, const Jastro
         }
       }
       __syncwarp();
+      JAS_TR(37);
       // pass 2: full warps over the list
       for (int e0 = lane; e0 < cnt; e0 += CH * 32)
       {
@@ -644,6 +652,7 @@ __device__ __forceinline__ void jastrow_accept_body(const Group& g, const Jastro
             update(j0 + c * g.n, q[c]);
       }
     }
+    JAS_TR(38);
     if (tid == 0)
     {
       J.j2_log[iw] += (double)(Uold_iat - vgl[0]); // TwoBodyJastrow.cpp:656-659
@@ -668,6 +677,8 @@ __device__ __forceinline__ void jastrow_accept_body(const Group& g, const Jastro
   // ParticleSet::mw_accept_rejectMove (ParticleSet.cpp:717-758): commit the position
   if (tid < 3)
     J.rsoa[(size_t)iw * 3 * np + tid * np + iat] = J.newpos[3 * iw + tid];
+  JAS_TR(39);
+#undef JAS_TR
 }
 
 template<typename RT>

@@ -43,6 +43,15 @@ constexpr int SEG_NSTAGE = 3;
 constexpr int SEG_ROWS   = 8;   // stencil rows per stage
 constexpr int SEG_BOXW   = 192; // components per TMA box (two boxes per stage at CPT = 2)
 constexpr int SEG_NQ     = 8;   // stages per evaluation
+// Threads of the determinant accept + next-row group in the phase after the Metropolis decision; the other SEG_TPB - SEG_DET
+// run the Jastrow accept.  An absolute-clock trace of the phase (QMCB_SEG_TRACE) shows the determinant side done in ~4 us
+// on 128 threads while the Jastrow accept of an accepted move takes ~12 us on the other 128 and holds the CTA barrier;
+// giving the Jastrow side 160 or 192 threads changed nothing (30.8 / 31.5 / 30.7 ms of segment kernels per sweep at
+// 64 / 96 / 128 determinant threads): its time is a chain of dependent accesses, not a lack of threads.
+#ifndef QMCB_SEG_DET
+#define QMCB_SEG_DET 128
+#endif
+constexpr int SEG_DET = QMCB_SEG_DET;
 
 // per-sweep arrays of the cross-walker RNG order (zero-initialised once; entries are tagged with the sweep number)
 struct SegRng
@@ -50,6 +59,7 @@ struct SegRng
   unsigned* flags;             // [N][stride]  (tag << 1) | needs_draw
   unsigned long long* tot_val; // [N + 1] raw outputs consumed before move m
   unsigned* tot_tag;           // [N + 1]
+  unsigned* btot;              // [N][32]  (tag << 8) | draws needed by the walkers 32 b .. 32 b + 31 (published by the block's last walker)
   int stride;                  // walker capacity of the crowd
 };
 
@@ -102,6 +112,23 @@ __host__ __device__ inline SegLayout seg_layout(int n, int k, int N, int nions)
 #define SEG_STAMP(slot, who) \
   do                         \
   {                          \
+  } while (0)
+#endif
+// absolute-clock trace of ONE walker's CTA over a few moves (debug builds: -DQMCB_SEG_TRACE=<walker index>): lane 0 of every
+// warp records clock64() at labelled points into a global array that the CTA prints at the end of the launch -- the only way
+// to see the critical path across the warp roles and barriers of the kernel
+#ifdef QMCB_SEG_TRACE
+__device__ long long g_seg_trace[4][8][40];
+#define SEG_TR(id)                                                                                   \
+  do                                                                                                 \
+  {                                                                                                  \
+    if (trace_on && (threadIdx.x & 31) == 0)                                                         \
+      g_seg_trace[m - 8][threadIdx.x >> 5][id] = clock64();                                          \
+  } while (0)
+#else
+#define SEG_TR(id) \
+  do               \
+  {                \
   } while (0)
 #endif
 namespace ptx
@@ -204,7 +231,11 @@ __device__ __forceinline__ void seg_propose(const DriverDev<T>& Dr, const Jastro
 }
 
 // what the Metropolis test of (iw, iat) needs from memory besides the orbital dots: fetched by the Metropolis warp WHILE
-// the spline gather of the same move runs, so that the test itself is arithmetic plus the cross-walker look-back
+// the spline gather of the same move runs, so that the test itself is arithmetic plus the cross-walker look-back.
+// The crowd's stream position (tot[m], published by the LAST walker when its test of the previous move is done) is NOT
+// waited for here: this warp would hold the CTA barrier behind the gather, and with it the staging and the dot sweeps
+// of the other warps, which do not depend on it (an absolute-clock trace showed the consumers idle at that barrier for
+// 4 - 17 us per move); seg_metropolis picks it up after publishing this walker's flag.
 template<typename T>
 struct SegMetroPre
 {
@@ -231,18 +262,9 @@ __device__ __forceinline__ SegMetroPre<T> seg_metro_prefetch(const DriverDev<T>&
     const T* dr = Dr.deltas + ((size_t)iat * Dr.nw + iw) * 3;
     P.rr        = Dr.tauovermass * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
   }
-  P.tag = ((*R.sweep) & 0x3fffffffu) + 1u;
-  if (iat == 0)
-    P.base = R.pos[0]; // left by the sweep prologue (rng_advance_kernel)
-  else
-  {
-    volatile unsigned* tt = SR.tot_tag + iat;
-    while (*tt != P.tag)
-      __nanosleep(100);
-    __threadfence();
-    P.base = *((volatile unsigned long long*)(SR.tot_val + iat));
-  }
-  P.raw_spec = R.ring[(unsigned)((P.base + (unsigned long long)iw) & R.ring_mask)];
+  P.tag      = ((*R.sweep) & 0x3fffffffu) + 1u;
+  P.base     = 0;
+  P.raw_spec = 0;
   return P;
 }
 
@@ -252,8 +274,14 @@ __device__ __forceinline__ SegMetroPre<T> seg_metro_prefetch(const DriverDev<T>&
 template<typename T>
 __device__ __forceinline__ bool seg_metropolis(const DriverDev<T>& Dr, const JastrowDev<T>& J, const RngDev& R, const SegRng& SR,
                                                const int iw, const int iat, const T q[4], const T* js, const SegMetroPre<T>& P,
-                                               T& rdet_out)
+                                               T& rdet_out, long long* tr = nullptr)
 {
+#define SEG_MTR(id)                      \
+  do                                     \
+  {                                      \
+    if (tr && (threadIdx.x & 31) == 0)   \
+      tr[id] = clock64();                \
+  } while (0)
   const int lane = threadIdx.x & 31;
   const T rdet   = q[0];
   double ratio   = (double)rdet;
@@ -295,23 +323,64 @@ __device__ __forceinline__ bool seg_metropolis(const DriverDev<T>& Dr, const Jas
     prob              = (T)(ratio * ratio * (double)exp(log_gb - log_gf));
     need              = !reject && prob >= eps;
   }
+  SEG_MTR(30);
   // ---- position of this walker's draw in the crowd's stream
   const unsigned tag    = P.tag;
   volatile unsigned* fl = SR.flags + (size_t)iat * SR.stride;
   if (lane == 0)
     fl[iw] = (tag << 1) | (need ? 1u : 0u);
-  const unsigned long long base = P.base;
-  unsigned cnt                  = 0;
-  // (eight flags per lane in flight at once instead of this load-and-wait loop was measured: 35.6 vs 30.4 ms of segment
-  // kernels per sweep -- slower, as in the two-kernel path: the extra live registers spill at 64 per thread and early
-  // readers re-poll flags that are not published yet)
-  for (int j = lane; j < iw; j += 32)
+  // ---- #{ j < iw : need[j] }.  Two levels: the last walker of every block of 32 publishes the block's count as soon as
+  // the block's flags are in; a walker adds the counts of the blocks below its own (one load per lane) and the flags of
+  // its own block below itself (one load per lane) -- two short dependent round trips to L2.  The flat loop over all lower
+  // flags (iw / 32 dependent polls per lane) cost the last walkers of a 512-walker crowd 5 - 9 us per move, and the last
+  // walker's test is what every other walker waits for (`base` below).
+  unsigned cnt   = 0;
+  const int nblk = (Dr.nw + 31) >> 5;
+  const bool two_level = nblk <= 32;
+  const int lb = iw >> 5, li = iw & 31;
+  volatile unsigned* bt = SR.btot + (size_t)iat * 32;
+  const unsigned tag24  = (tag & 0xffffffu) << 8;
+  unsigned below        = 0;
+  if (two_level)
   {
-    unsigned f;
-    while (((f = fl[j]) >> 1) != tag)
-      __nanosleep(100);
-    cnt += f & 1u;
+    unsigned f = 0;
+    if (lane < li)
+      while (((f = fl[32 * lb + lane]) >> 1) != tag)
+        __nanosleep(60);
+    below = __popc(__ballot_sync(0xffffffffu, lane < li && (f & 1u)));
+    if ((li == 31 || iw == Dr.nw - 1) && lane == 0)
+      bt[lb] = tag24 | (below + (need ? 1u : 0u));
   }
+  // raw outputs consumed before this move: left by the sweep prologue (rng_advance_kernel) for the first electron,
+  // otherwise published by the last walker after its test of the previous move
+  unsigned long long base;
+  if (iat == 0)
+    base = R.pos[0];
+  else
+  {
+    volatile unsigned* tt = SR.tot_tag + iat;
+    while (*tt != tag)
+      __nanosleep(100);
+    __threadfence();
+    base = *((volatile unsigned long long*)(SR.tot_val + iat));
+  }
+  if (two_level)
+  {
+    unsigned v = tag24;
+    if (lane < lb)
+      while (((v = bt[lane]) & 0xffffff00u) != tag24)
+        __nanosleep(60);
+    cnt = (lane < lb ? (v & 0xffu) : 0u) + (lane == 0 ? below : 0u);
+  }
+  else
+    for (int j = lane; j < iw; j += 32)
+    {
+      unsigned f;
+      while (((f = fl[j]) >> 1) != tag)
+        __nanosleep(100);
+      cnt += f & 1u;
+    }
+  SEG_MTR(31);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -329,10 +398,11 @@ __device__ __forceinline__ bool seg_metropolis(const DriverDev<T>& Dr, const Jas
     }
     if (need)
     {
-      const uint32_t raw = cnt == (unsigned)iw ? P.raw_spec : R.ring[(unsigned)((base + cnt) & R.ring_mask)];
+      const uint32_t raw = R.ring[(unsigned)((base + cnt) & R.ring_mask)];
       const double u     = (double)raw / 4294967296.0;
       acc                = Dr.dmc ? (u < (double)prob) : (u < (double)(prob * exp(log_gb - log_gf)));
     }
+    SEG_MTR(32);
     Dr.accepted[iw] = acc ? 1 : 0;
     if (Dr.dmc)
     {
@@ -348,7 +418,9 @@ __device__ __forceinline__ bool seg_metropolis(const DriverDev<T>& Dr, const Jas
       Dr.accept_log[(size_t)iat * Dr.nw + iw] = acc ? 1 : 0;
   }
   rdet_out = rdet;
+  SEG_MTR(33);
   return __shfl_sync(0xffffffffu, acc ? 1 : 0, 0) != 0;
+#undef SEG_MTR
 }
 
 // ---- host-driven mode (template parameter HD): the Metropolis test and the drift stay with the CALLER (QMCPACK's batched
@@ -607,6 +679,10 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
   {
     const bool part1 = m >= 0, part2 = m + 1 < nmoves;
     const int iat = iat0 + m, row = row0 + m, c = c0 + m; // the move being decided (part1); c = slot it appends
+#ifdef QMCB_SEG_TRACE
+    const bool trace_on = iw == QMCB_SEG_TRACE && iat0 == 32 && m >= 8 && m < 12;
+#endif
+    SEG_TR(0); // loop top (after B3 of the previous move)
     const int cn = c + 1;                                   // pending delays when the next row is prepared
 
     if (part1)
@@ -670,8 +746,10 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           else
             seg_propose<T, false>(Dr, J, iw, iat, sg, np3);
           SEG_STAMP(0, 0); // barrier wake-up + proposal
+          SEG_TR(5);
           jastrow_move_warps<T>(warp, SEG_NCONS / 32, J, iw, iat, np3, jl, jred + warp * 16);
           SEG_STAMP(1, 0); // Jastrow sums
+          SEG_TR(6);
         }
         T cz[4], dcz[4], d2cz[4];
 #ifdef QMCB_SEG_ROLLED
@@ -687,6 +765,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           ptx::mbar_wait(&full_bar[stage], ph);
           if (qq == 0)
           {
+            SEG_TR(7);
             load4<T>(hdr + SPL_HDR_C, cz);
             load4<T>(hdr + SPL_HDR_C + 4, dcz);
             load4<T>(hdr + SPL_HDR_C + 8, d2cz);
@@ -724,6 +803,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
             ptx::mbar_arrive(&empty_bar[stage]);
         }
         SEG_STAMP(2, 0); // eight slabs
+        SEG_TR(8);
         // epilogue: lattice units -> Cartesian, sign, rows into shared memory, dots with the inverse row
         const int bc_sign = *reinterpret_cast<const int*>(hdr + SPL_HDR_SGN);
         const T sgn   = (bc_sign & 1) ? T(-1) : T(1);
@@ -756,6 +836,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         warp_fold<T, 4>(acc); // lane l holds the total of value l >> 3
         if ((lane & 7) == 0)
           rgp[warp * 4 + (lane >> 3)] = acc[0];
+        SEG_TR(9);
       }
       else if (warp == 6)
       {
@@ -765,6 +846,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           np3[0] = s_np[0], np3[1] = s_np[1], np3[2] = s_np[2];
         else
           seg_propose<T, true>(Dr, J, iw, iat, sg, np3);
+        SEG_TR(1);
         T* scratch = hdr + SPL_HDR;
         T ru[3];
         const int bc_sign = convert_pos<T, T>(S, np3, ru);
@@ -817,9 +899,12 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         else if (lane == 19)
           *reinterpret_cast<int*>(hdr + SPL_HDR_SGN) = bc_sign;
         __syncwarp();
+        SEG_TR(2);
         const uint64_t pol = ptx::policy_evict_first();
         for (int qq = 0; qq < SEG_NQ; ++qq)
         {
+          if (qq == 3)
+            SEG_TR(3);
           const unsigned g  = gq + qq;
           const int stage   = g % SEG_NSTAGE;
           const unsigned ph = (g / SEG_NSTAGE) & 1u;
@@ -834,6 +919,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           }
           __syncwarp();
         }
+        SEG_TR(4);
       }
       else
       {
@@ -859,10 +945,12 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         if constexpr (!HD)
           mpre = seg_metro_prefetch<T>(Dr, J, R, SR, iw, iat, sg);
         SEG_STAMP(8, 224); // Metropolis prefetch incl. the wait for the previous move's total
+        SEG_TR(10);
       }
       gq += SEG_NQ;
       SEG_STAMP(3, 0); // epilogue
       __syncthreads(); // B1
+      SEG_TR(11);
       SEG_STAMP(4, 0);   // wait at B1
       SEG_STAMP(9, 224); // wait at B1 (Metropolis warp)
 #ifdef QMCB_SEG_TIMING
@@ -937,12 +1025,20 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
             s_abort = 1;
         }
         else
+        {
+          SEG_TR(16);
+#ifdef QMCB_SEG_TRACE
+          acc = seg_metropolis<T>(Dr, J, R, SR, iw, iat, q, jsum, mpre, rdet, trace_on ? &g_seg_trace[m - 8][7][0] : nullptr);
+#else
           acc = seg_metropolis<T>(Dr, J, R, SR, iw, iat, q, jsum, mpre, rdet);
+#endif
+        }
         if (lane == 0)
         {
           s_acc   = acc ? 1 : 0;
           s_ratio = rdet;
         }
+        SEG_TR(18);
         SEG_STAMP(10, 224); // Metropolis test
       }
     }
@@ -967,6 +1063,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           glrow[2 * n + j] = gl[2 * n + j];
         }
       }
+      SEG_TR(12);
       ptx::fence_proxy_async(); // vrow / glrow live in the ring region: generic writes before the next TMA requests
       if (!part1 && c0 > 0)
       {
@@ -980,6 +1077,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         }
       }
       ga.sync();
+      SEG_TR(13);
       SEG_STAMP(5, 0); // staging of the next row
       const T* Va     = D.V + (size_t)iw * k * n;
       const T* Ub     = D.U + (size_t)iw * k * n;
@@ -1033,6 +1131,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
               pB[u1] = s1;
           }
         }
+        SEG_TR(14);
         if (cA > 0)
         {
           // (the slice of phi replaces the slice of x in the same registers)
@@ -1109,6 +1208,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         }
       }
     }
+    SEG_TR(15);
     SEG_STAMP(6, 0); // dots
     __syncthreads(); // B2
     if constexpr (HD)
@@ -1118,6 +1218,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           ptx::mbar_wait(v_bar, v_phase); // (no bulk copy may be in flight into this CTA's shared memory at exit)
         break;
       }
+    SEG_TR(19);
     SEG_STAMP(7, 0);    // wait at B2
     SEG_STAMP(11, 224); // wait at B2 (Metropolis warp)
 #ifdef QMCB_SEG_TIMING
@@ -1125,10 +1226,10 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
       printf("abs iw %d m %d tid %d after B2 clock %lld\n", iw, m, tid, (long long)clock64());
 #endif
 
-    // ======================= determinant accept + next row (threads 0-127) || Jastrow accept (threads 128-255) =======================
-    if (tid < SEG_TPB / 2)
+    // ======================= determinant accept + next row (threads 0 .. SEG_DET-1) || Jastrow accept (the others) =======================
+    if (tid < SEG_DET)
     {
-      const Group gd{tid, SEG_TPB / 2, 1};
+      const Group gd{tid, SEG_DET, 1};
       if (part1)
       {
         const bool acc = s_acc != 0;
@@ -1148,6 +1249,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
             st_stream(gl + 3 * n + j, phi[4 * n + j]);
           }
         }
+        SEG_TR(20);
         if (acc)
         {
           // bordered update of Binv (DelayedUpdate.h:113-141) in shared memory; w is the one left by this row's preparation
@@ -1195,6 +1297,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         }
         gd.sync();
       }
+      SEG_TR(21);
       if (part2)
       {
         // p'[a] = U[a].x : rows < cB from the staging phase; the appended row is phi.x on accept, 0 for a pseudo-accept
@@ -1209,6 +1312,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           w[tid] = -sacc; // w = -Binv^T p'  (DelayedUpdate.h:100-101)
         }
         gd.sync();
+        SEG_TR(22);
         // x += V^T w : the staged rows from shared memory, rows beyond the staging capacity from L2, the row appended
         // by this move from vrow; then the gradient dots with the staged gradient rows
         const T* Vm = D.V + (size_t)iw * k * n;
@@ -1270,19 +1374,29 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
             acc3[2] += xv * glrow[2 * n + j];
           }
         }
+        SEG_TR(23);
         group_sum<T, 3>(gd, acc3, red);
         if (tid < 3)
           sg[tid] = tid == 0 ? acc3[0] : (tid == 1 ? acc3[1] : acc3[2]);
       }
       // the ring region (vrow, glrow) goes back to the TMA engine
       ptx::fence_proxy_async();
+      SEG_TR(24);
       SEG_STAMP(12, 0); // determinant accept + next row
     }
     else if (part1 && s_acc != 0)
-      jastrow_accept_body<T>(Group{tid - SEG_TPB / 2, SEG_TPB / 2, 2}, J, iw, iat, jl);
+    {
+#ifdef QMCB_SEG_TRACE
+      jastrow_accept_body<T>(Group{tid - SEG_DET, SEG_TPB - SEG_DET, 2}, J, iw, iat, jl,
+                             trace_on ? &g_seg_trace[m - 8][SEG_DET / 32][0] : nullptr);
+#else
+      jastrow_accept_body<T>(Group{tid - SEG_DET, SEG_TPB - SEG_DET, 2}, J, iw, iat, jl);
+#endif
+    }
     // (pulling the rows the NEXT move's staging reads cold -- stale inverse row, gradient rows, Gaussians of electron
     // row + 2 -- into L2 from this phase was measured too: 1278 vs 1259 us per segment, i.e. slightly slower, like the
     // prefetch under the gather (QMCB_SEG_PREFETCH above); the staging is not DRAM-latency bound)
+    SEG_TR(25);
     SEG_STAMP(13, 224); // Jastrow accept
     if (nvs > 0)
       v_phase ^= 1u;
@@ -1305,6 +1419,22 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
            seg_tim[5] / nmoves, seg_tim[6] / nmoves, seg_tim[7] / nmoves, seg_tim[12] / nmoves, seg_tim[14] / nmoves,
            seg_tim[8] / nmoves, seg_tim[9] / nmoves, seg_tim[10] / nmoves, seg_tim[11] / nmoves, seg_tim[13] / nmoves,
            seg_tim[15] / nmoves);
+#endif
+#ifdef QMCB_SEG_TRACE
+  __syncthreads();
+  if (iw == QMCB_SEG_TRACE && iat0 == 32 && tid == 0)
+    for (int mm = 0; mm < 4; ++mm)
+    {
+      const long long t0 = g_seg_trace[mm][0][0];
+      for (int wv = 0; wv < 8; ++wv)
+      {
+        printf("trace iw %d move %d warp %d :", iw, 8 + mm, wv);
+        for (int id = 0; id < 40; ++id)
+          if (g_seg_trace[mm][wv][id] != 0)
+            printf(" %d=%lld", id, g_seg_trace[mm][wv][id] - t0);
+        printf("\n");
+      }
+    }
 #endif
   // the flush (and any later API call) finds the core and w in memory
   const int cF = c0 + mdone;
