@@ -995,6 +995,8 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           }
           __syncwarp();
         }
+        // (forming the Jastrow ratios -- two double-precision exponentials -- on this warp BEFORE the barrier, behind a
+        // named-barrier hand-over from the consumers' Jastrow pass, was measured: 29.9 vs 29.5 ms per sweep, slower)
         T rdet;
         bool acc;
         if constexpr (HD)
