@@ -709,7 +709,8 @@ __device__ __forceinline__ void jastrow_accept_body(const Group& g, const Jastro
       d2U[iat]         = vgl[4];
     }
   }
-  if (J.has_j1 && tid == 0)
+  // (on another warp than the J2 commit above: each is a short chain of dependent global read-modify-writes)
+  if (J.has_j1 && tid == (g.n > 32 ? 32 : 0))
   {
     const RT* cur = J.j1_cur + (size_t)iw * 5;
     RT* Vat       = J.Vat + (size_t)iw * N;

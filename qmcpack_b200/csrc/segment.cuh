@@ -43,6 +43,13 @@ constexpr int SEG_NSTAGE = 3;
 constexpr int SEG_ROWS   = 8;   // stencil rows per stage
 constexpr int SEG_BOXW   = 192; // components per TMA box (two boxes per stage at CPT = 2)
 constexpr int SEG_NQ     = 8;   // stages per evaluation
+// warps that share the Jastrow sums of the proposed position: the six consumers (6), or the consumers plus warp 7 (7), which
+// is idle under the gather once its Metropolis inputs are fetched (832 candidates at NiO-a64: 4 blocks per lane instead of
+// 5 on the critical warps).  Measured: 31.3 ms of segment kernels per sweep with 7 against 28.5 ms with 6.
+#ifndef QMCB_SEG_JW
+#define QMCB_SEG_JW 6
+#endif
+constexpr int SEG_JW = QMCB_SEG_JW;
 // Threads of the determinant accept + next-row group in the phase after the Metropolis decision; the other SEG_TPB - SEG_DET
 // run the Jastrow accept.  An absolute-clock trace of the phase (QMCB_SEG_TRACE) shows the determinant side done in ~4 us
 // on 128 threads while the Jastrow accept of an accepted move takes ~12 us on the other 128 and holds the CTA barrier;
@@ -86,7 +93,7 @@ __host__ __device__ inline SegLayout seg_layout(int n, int k, int N, int nions)
   L.sg = o, o += 16 * (unsigned)sizeof(T);
   L.hdr = o, o += up((SPL_HDR + SPL_SCRATCH + 4) * (unsigned)sizeof(T), 16);
   L.bars = o, o += 64;
-  L.jred = o, o += 96 * (unsigned)sizeof(T); // per-consumer-warp partials of the ten Jastrow sums [6][16]
+  L.jred = o, o += 128 * (unsigned)sizeof(T); // per-warp partials of the ten Jastrow sums [SEG_JW][16]
   L.jsum = o, o += 16 * (unsigned)sizeof(T); // the sums of the move being decided
   L.tim = o = up(o, 16), o += 192 + 16;      // cycle stamps of the timing build; the last 16 bytes: log|det|, phase
   L.jl_entries = (int)up((unsigned)(N + nions + 256), 32);
@@ -241,6 +248,7 @@ struct SegMetroPre
 {
   T uat_old, vat_old;          // Uat[iat], Vat[iat] of the committed configuration
   T disp[3], delta[3];         // proposed displacement and its Gaussian part
+  T np[3];                     // the proposed position
   T rr;                        // DMC: tau |Gaussian|^2
   unsigned tag;                // sweep tag of the look-back arrays
   unsigned long long base;     // raw outputs consumed before this move
@@ -254,6 +262,7 @@ __device__ __forceinline__ SegMetroPre<T> seg_metro_prefetch(const DriverDev<T>&
   SegMetroPre<T> P;
   T np3[3];
   seg_propose<T, false>(Dr, J, iw, iat, g_det, np3, P.disp, P.delta);
+  P.np[0] = np3[0], P.np[1] = np3[1], P.np[2] = np3[2];
   P.uat_old = J.has_j2 ? J.Uat[(size_t)iw * J.npad + iat] : T(0);
   P.vat_old = J.has_j1 ? J.Vat[(size_t)iw * J.N + iat] : T(0);
   P.rr      = T(0);
@@ -300,6 +309,17 @@ __device__ __forceinline__ bool seg_metropolis(const DriverDev<T>& Dr, const Jas
     gn[1] += js[7];
     gn[2] += js[8];
   }
+  const T eps = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
+  T prob      = (T)(ratio * ratio); // std::norm(ratio), VMCBatched.cpp:152
+  if (isnan(ratio) && lane == 0 && Dr.err)
+    atomicOr(Dr.err, QMCB_ERR_NAN_RATIO); // NaNguard::checkOneParticleRatio (TrialWaveFunction.cpp:549): the host throws
+  bool need             = prob >= eps;
+  const unsigned tag    = P.tag;
+  volatile unsigned* fl = SR.flags + (size_t)iat * SR.stride;
+  // VMC: whether this walker draws depends on the ratio alone -- the flag goes out BEFORE the Green's functions are
+  // evaluated (every walker above this one waits for it)
+  if (!Dr.dmc && lane == 0)
+    fl[iw] = (tag << 1) | (need ? 1u : 0u);
   T log_gf = T(0), log_gb = T(0);
   if (Dr.use_drift)
   {
@@ -311,24 +331,16 @@ __device__ __forceinline__ bool seg_metropolis(const DriverDev<T>& Dr, const Jas
     dr[2] += P.disp[2];
     log_gb = -Dr.oneover2tau * (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
   }
-  const T eps = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
-  T prob      = (T)(ratio * ratio); // std::norm(ratio), VMCBatched.cpp:152
-  if (isnan(ratio) && lane == 0 && Dr.err)
-    atomicOr(Dr.err, QMCB_ERR_NAN_RATIO); // NaNguard::checkOneParticleRatio (TrialWaveFunction.cpp:549): the host throws
-  bool need   = prob >= eps;
   if (Dr.dmc)
   {
     // DMCBatched.cpp:188-250 (see metropolis_warp in crowd.cu)
     const bool reject = !(ratio > 0.0);
     prob              = (T)(ratio * ratio * (double)exp(log_gb - log_gf));
     need              = !reject && prob >= eps;
+    if (lane == 0)
+      fl[iw] = (tag << 1) | (need ? 1u : 0u);
   }
   SEG_MTR(30);
-  // ---- position of this walker's draw in the crowd's stream
-  const unsigned tag    = P.tag;
-  volatile unsigned* fl = SR.flags + (size_t)iat * SR.stride;
-  if (lane == 0)
-    fl[iw] = (tag << 1) | (need ? 1u : 0u);
   // ---- #{ j < iw : need[j] }.  Two levels: the last walker of every block of 32 publishes the block's count as soon as
   // the block's flags are in; a walker adds the counts of the blocks below its own (one load per lane) and the flags of
   // its own block below itself (one load per lane) -- two short dependent round trips to L2.  The flat loop over all lower
@@ -747,7 +759,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
             seg_propose<T, false>(Dr, J, iw, iat, sg, np3);
           SEG_STAMP(0, 0); // barrier wake-up + proposal
           SEG_TR(5);
-          jastrow_move_warps<T>(warp, SEG_NCONS / 32, J, iw, iat, np3, jl, jred + warp * 16);
+          jastrow_move_warps<T>(warp, SEG_JW, J, iw, iat, np3, jl, jred + warp * 16);
           SEG_STAMP(1, 0); // Jastrow sums
           SEG_TR(6);
         }
@@ -944,6 +956,16 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
 #endif
         if constexpr (!HD)
           mpre = seg_metro_prefetch<T>(Dr, J, R, SR, iw, iat, sg);
+        if (SEG_JW == 7 && (J.has_j2 || J.has_j1))
+        {
+          // this warp's share of the Jastrow sums (SEG_JW)
+          T np3[3];
+          if constexpr (HD)
+            np3[0] = s_np[0], np3[1] = s_np[1], np3[2] = s_np[2];
+          else
+            np3[0] = mpre.np[0], np3[1] = mpre.np[1], np3[2] = mpre.np[2];
+          jastrow_move_warps<T>(6, SEG_JW, J, iw, iat, np3, jl, jred + 6 * 16);
+        }
         SEG_STAMP(8, 224); // Metropolis prefetch incl. the wait for the previous move's total
         SEG_TR(10);
       }
@@ -985,7 +1007,7 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           if (lane < 10)
           {
             T t = T(0);
-            for (int pw = 0; pw < SEG_NCONS / 32; ++pw)
+            for (int pw = 0; pw < SEG_JW; ++pw)
               t += jred[pw * 16 + lane];
             jsum[lane] = t;
             if (lane < 5 && J.has_j2)
@@ -1232,6 +1254,9 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
     if (tid < SEG_DET)
     {
       const Group gd{tid, SEG_DET, 1};
+      // (pulling the next proposal's cold inputs -- the electron's Gaussians and one-body Jastrow gradient -- into L2 from
+      // here was measured: 29.4 vs 28.5 ms of segment kernels per sweep; like every other prefetch tried in this kernel
+      // it made things slower)
       if (part1)
       {
         const bool acc = s_acc != 0;
