@@ -54,7 +54,8 @@ constexpr int SEG_JW = QMCB_SEG_JW;
 // run the Jastrow accept.  An absolute-clock trace of the phase (QMCB_SEG_TRACE) shows the determinant side done in ~4 us
 // on 128 threads while the Jastrow accept of an accepted move takes ~12 us on the other 128 and holds the CTA barrier;
 // giving the Jastrow side 160 or 192 threads changed nothing (30.8 / 31.5 / 30.7 ms of segment kernels per sweep at
-// 64 / 96 / 128 determinant threads): its time is a chain of dependent accesses, not a lack of threads.
+// 64 / 96 / 128 determinant threads): its time is a chain of dependent accesses, not a lack of threads.  A split that
+// follows the decision (64 determinant threads on an accepted move, 128 on a rejected one) was slower too: 29.3 vs 28.5 ms.
 #ifndef QMCB_SEG_DET
 #define QMCB_SEG_DET 128
 #endif
