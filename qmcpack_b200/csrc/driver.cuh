@@ -178,12 +178,27 @@ __global__ void rng_advance_kernel(RngDev R, unsigned long long n, int last_pari
 }
 
 // ref: DriftModifierUNR.cpp:20-31 (a = 1)
+// (QMCB_SEG_SMALL: one out-of-line copy instead of one inlined copy per caller -- a double-precision square root and
+// division each; the walker-segment kernel calls it from four places and is instruction-cache bound, segment.cuh)
+#ifndef QMCB_SEG_SMALL
+#define QMCB_SEG_SMALL 1
+#endif
+#if QMCB_SEG_SMALL
+#define QMCB_DRIFT_INLINE __noinline__
+#else
+#define QMCB_DRIFT_INLINE __forceinline__
+#endif
+template<typename RT>
+__device__ QMCB_DRIFT_INLINE RT drift_scale(const RT tau, const RT vsq)
+{
+  const RT eps = sizeof(RT) == 4 ? RT(1.1920929e-07f) : RT(2.220446049250313e-16);
+  return vsq < eps ? tau : (RT)((-1.0 + sqrt(1.0 + 2.0 * (double)RT(1) * (double)tau * (double)vsq)) / (double)(RT(1) * vsq));
+}
 template<typename RT>
 __device__ __forceinline__ void get_drift(RT tau, const RT qf[3], RT drift[3])
 {
   const RT vsq = qf[0] * qf[0] + qf[1] * qf[1] + qf[2] * qf[2];
-  const RT eps = sizeof(RT) == 4 ? RT(1.1920929e-07f) : RT(2.220446049250313e-16);
-  const RT sc  = vsq < eps ? tau : (RT)((-1.0 + sqrt(1.0 + 2.0 * (double)RT(1) * (double)tau * (double)vsq)) / (double)(RT(1) * vsq));
+  const RT sc  = drift_scale<RT>(tau, vsq);
   drift[0]     = qf[0] * sc;
   drift[1]     = qf[1] * sc;
   drift[2]     = qf[2] * sc;

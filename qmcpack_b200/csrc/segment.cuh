@@ -768,10 +768,14 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
           SEG_TR(6);
         }
         T cz[4], dcz[4], d2cz[4];
-#ifdef QMCB_SEG_ROLLED
-#pragma unroll 1
-#else
+        // NOT unrolled: the kernel's executed code is ~115 KB (ncu: 7400 SASS instructions touched per launch, "no
+        // instruction" the third-largest stall reason) and eight warp roles run different parts of it at once, so it
+        // lives or dies by the instruction cache -- the rolled loop is 6 % faster than the 8x unrolled one (26.6 vs 28.4 ms
+        // of segment kernels per sweep), and most "harmless" additions to this kernel measured slower for the same reason
+#ifdef QMCB_SEG_UNROLLED
 #pragma unroll
+#else
+#pragma unroll 1
 #endif
         for (int qq = 0; qq < SEG_NQ; ++qq)
         {
@@ -917,6 +921,12 @@ __global__ void __launch_bounds__(SEG_TPB, (sizeof(T) == 4 ? 4 : 2))
         __syncwarp();
         SEG_TR(2);
         const uint64_t pol = ptx::policy_evict_first();
+#ifndef QMCB_SEG_SMALL
+#define QMCB_SEG_SMALL 1
+#endif
+#if QMCB_SEG_SMALL
+#pragma unroll 1
+#endif
         for (int qq = 0; qq < SEG_NQ; ++qq)
         {
           if (qq == 3)
