@@ -442,29 +442,22 @@ struct JastrowMove
     __syncwarp();
     for (int e = lane; e < cnt; e += 32)
     {
-      const int idx = seg[e];
+      // (one copy of the distance + functor code for both kinds of partner: the walker-segment kernel is instruction-cache
+      // bound, segment.cuh)
+      const int idx  = seg[e];
+      const bool is2 = idx < n2;
+      const int j    = is2 ? idx : idx - n2;
+      const RT* ps   = is2 ? rs : J.ion_rsoa;
+      const int st   = is2 ? np : J.npad_ion;
       RT r, dx, dy, dz, du, d2u;
-      if (idx < n2)
-      {
-        min_image(J.cell, pos, rs[idx], rs[np + idx], rs[2 * np + idx], idx, iat, r, dx, dy, dz);
-        const RT u = functor_eval(J.F2[gi + (idx < J.n_up ? 0 : 1)], r, du, d2u);
-        acc[0] += u;
-        acc[1] += du * dx;
-        acc[2] += du * dy;
-        acc[3] += du * dz;
-        acc[4] += d2u + RT(2) * du;
-      }
+      min_image(J.cell, pos, ps[j], ps[st + j], ps[2 * st + j], j, is2 ? iat : 0, r, dx, dy, dz);
+      const FunctorDev<RT>& F = is2 ? J.F2[gi + (idx < J.n_up ? 0 : 1)] : J.F1[J.ion_grp[j]];
+      const RT u  = functor_eval(F, r, du, d2u);
+      const RT c1 = du * dx, c2 = du * dy, c3 = du * dz, c4 = d2u + RT(2) * du;
+      if (is2)
+        acc[0] += u, acc[1] += c1, acc[2] += c2, acc[3] += c3, acc[4] += c4;
       else
-      {
-        const int j = idx - n2;
-        min_image(J.cell, pos, J.ion_rsoa[j], J.ion_rsoa[J.npad_ion + j], J.ion_rsoa[2 * J.npad_ion + j], j, 0, r, dx, dy, dz);
-        const RT u = functor_eval(J.F1[J.ion_grp[j]], r, du, d2u);
-        acc[5] += u;
-        acc[6] += du * dx;
-        acc[7] += du * dy;
-        acc[8] += du * dz;
-        acc[9] += d2u + RT(2) * du;
-      }
+        acc[5] += u, acc[6] += c1, acc[7] += c2, acc[8] += c3, acc[9] += c4;
     }
     warp_fold<RT, 16>(acc); // lane l holds the total of value l >> 1
     if ((lane & 1) == 0 && (lane >> 1) < 10)

@@ -296,20 +296,16 @@ __device__ __forceinline__ bool seg_metropolis(const DriverDev<T>& Dr, const Jas
   const T rdet   = q[0];
   double ratio   = (double)rdet;
   T gn[3]        = {q[1] / rdet, q[2] / rdet, q[3] / rdet};
-  if (J.has_j2)
-  {
-    ratio = ratio * exp((double)(P.uat_old - js[0]));
-    gn[0] += js[1];
-    gn[1] += js[2];
-    gn[2] += js[3];
-  }
-  if (J.has_j1)
-  {
-    ratio = ratio * exp((double)(P.vat_old - js[5]));
-    gn[0] += js[6];
-    gn[1] += js[7];
-    gn[2] += js[8];
-  }
+  // (one copy of the double-precision exponential for both Jastrow ratios, J2 first: the kernel is instruction-cache bound)
+#pragma unroll 1
+  for (int t = 0; t < 2; ++t)
+    if (t == 0 ? J.has_j2 : J.has_j1)
+    {
+      ratio = ratio * exp((double)((t == 0 ? P.uat_old : P.vat_old) - js[5 * t]));
+      gn[0] += js[5 * t + 1];
+      gn[1] += js[5 * t + 2];
+      gn[2] += js[5 * t + 3];
+    }
   const T eps = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
   T prob      = (T)(ratio * ratio); // std::norm(ratio), VMCBatched.cpp:152
   if (isnan(ratio) && lane == 0 && Dr.err)
